@@ -1,0 +1,211 @@
+/*
+ * qgcm_b200.h -- C ABI of libqgcm_b200.so, the B200-native replacement for the
+ * per-timestep hot path of Q-GCM v1.5.0 (reference fork jinkakei/q-gcm).
+ *
+ * The reference has no FFI: its seam is the set of argument-less Fortran module
+ * procedures called from the main loop (src/q-gcm.F:1222-1269) plus the inline
+ * time-level averaging block (src/q-gcm.F:1328-1407), all acting on module-global
+ * static arrays.  Each entry point below replaces exactly one of those procedures;
+ * the Fortran side keeps the same subroutine names and forwards through the
+ * ISO_C_BINDING interface module shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; the message is then
+ *     available from qgcm_last_error() (reference convention is print + stop,
+ *     src/nc_subs.F:84-112, src/ocisubs.F:361-365).
+ *   - all host arrays are Fortran column-major, unpadded, double precision, exactly
+ *     as declared in the reference data modules (src/ocstate_data.F:39-42,
+ *     src/intrfac_data.F:39-48, src/ochomog_data.F:44-69, ...).
+ *   - the library owns the device mirrors; host arrays are stale between
+ *     qgcm_get_field calls.  Step calls are asynchronous on one CUDA stream per GPU;
+ *     qgcm_get_field / qgcm_get_scalars / qgcm_sync synchronise.
+ *   - there is no CPU fallback: qgcm_create fails if no sm_100 device is present.
+ */
+#ifndef QGCM_B200_H
+#define QGCM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QGCM_NLMAX 9          /* nlmax in src/eigmode.f:86 */
+#define QGCM_ABI_VERSION 1
+
+/* cpp macros of src/make.config:11-45 become run-time flags */
+enum {
+  QGCM_OCEAN_ONLY   = 1 << 0,   /* -Docean_only   */
+  QGCM_ATMOS_ONLY   = 1 << 1,   /* -Datmos_only   */
+  QGCM_CYCLIC_OCEAN = 1 << 2,   /* -Dcyclic_ocean */
+  QGCM_SB_HFLUX     = 1 << 3,   /* -Dsb_hflux     */
+  QGCM_NB_HFLUX     = 1 << 4,   /* -Dnb_hflux     */
+  QGCM_TAU_UDIFF    = 1 << 5    /* -Dtau_udiff    */
+};
+
+/*
+ * Everything the hot path needs that the Fortran main program has computed by
+ * src/q-gcm.F:976 (after eigmod, radiat, topset).  Compile-time PARAMETERs of
+ * src/parameters_data.F:41-119 and the positional values of src/in_param.f:31-142
+ * arrive here as plain run-time fields.  Matrices are Fortran column-major with
+ * leading dimension nlo (ocean) / nla (atmosphere), packed at the array start.
+ */
+typedef struct qgcm_config {
+  int32_t abi_version;        /* must be QGCM_ABI_VERSION */
+  int32_t struct_bytes;       /* sizeof(qgcm_config) as seen by the caller */
+  int32_t flags;              /* QGCM_* bit mask */
+  int32_t device;             /* CUDA device ordinal for this process */
+  /* src/parameters_data.F:41-88 */
+  int32_t nxto, nyto, nlo;    /* ocean T cells and layers; nxpo=nxto+1, nypo=nyto+1 */
+  int32_t nxta, nyta, nla;    /* atmosphere T cells and layers */
+  int32_t ndxr, nx1, ny1;     /* dxa/dxo, ocean start indices in the atmos grid */
+  int32_t nstr;               /* dto/dta */
+  /* y-slab partition of the ocean (multi-GPU).  rank r owns p rows
+   * [jp0, jp0+nyp_loc); single GPU: nranks=1. */
+  int32_t nranks, rank;
+  int32_t reserved_i[4];
+  /* src/parameters_data.F:96-99 */
+  double fnot, beta;
+  /* src/in_param.f:31-142 */
+  double dxo, dta;
+  double delek, cdat, rhoat, rhooc, cpat, cpoc;
+  double bccoat, bccooc, xcexp, ycexp;
+  double xlamda, hmoc, st2d, st4d;
+  double hmat, hmamin, ahmd, at2d, at4d, hmadmp;
+  /* outputs of radiat, src/radsubs.f:544-560 and src/radiate_data.F:34-38 */
+  double tsbdy, tnbdy, fspco;
+  double Bmup, B1down, Cmup, C1down, D0up, Dmup, Dmdown, bface, cface, dface;
+  double Aup[QGCM_NLMAX * QGCM_NLMAX], Adown[QGCM_NLMAX * QGCM_NLMAX];
+  double Bup[QGCM_NLMAX], Cup[QGCM_NLMAX], Dup[QGCM_NLMAX];
+  double rbetat[QGCM_NLMAX], aface[QGCM_NLMAX];
+  /* layer vectors, src/occonst_data.F:36-44, src/atconst_data.F:36-44 */
+  double hoc[QGCM_NLMAX], gpoc[QGCM_NLMAX], ah2oc[QGCM_NLMAX], ah4oc[QGCM_NLMAX];
+  double toc[QGCM_NLMAX];
+  double hat[QGCM_NLMAX], gpat[QGCM_NLMAX], ah4at[QGCM_NLMAX], tat[QGCM_NLMAX];
+  /* outputs of eigmod, src/eigmode.f:386-428 */
+  double amatoc[QGCM_NLMAX * QGCM_NLMAX];
+  double ctl2moc[QGCM_NLMAX * QGCM_NLMAX], ctm2loc[QGCM_NLMAX * QGCM_NLMAX];
+  double rdm2oc[QGCM_NLMAX];
+  double amatat[QGCM_NLMAX * QGCM_NLMAX];
+  double ctl2mat[QGCM_NLMAX * QGCM_NLMAX], ctm2lat[QGCM_NLMAX * QGCM_NLMAX];
+  double rdm2at[QGCM_NLMAX];
+  double reserved_d[8];
+} qgcm_config;
+
+/*
+ * Host mirror of the scalar state that the hot path mutates:
+ * constraint variables (src/ochomog_data.F:57-69, src/athomog_data.F:43-55) and the
+ * monitor scalars the step routines write as side effects (src/monitor_data.F:41-61).
+ */
+typedef struct qgcm_scalars {
+  /* ocean constraints */
+  double xon[QGCM_NLMAX], dpioc[QGCM_NLMAX], dpiocp[QGCM_NLMAX];
+  double ocncs[QGCM_NLMAX], ocncn[QGCM_NLMAX], ocncsp[QGCM_NLMAX], ocncnp[QGCM_NLMAX];
+  double enisoc[QGCM_NLMAX], eninoc[QGCM_NLMAX];
+  double ajisoc[QGCM_NLMAX], ajinoc[QGCM_NLMAX];
+  double ap3soc[QGCM_NLMAX], ap3noc[QGCM_NLMAX], ap5soc[QGCM_NLMAX], ap5noc[QGCM_NLMAX];
+  double txisoc, txinoc, bdrins, bdrinn;
+  /* ocean homogeneous-solution constants (homsol, src/conhoms.F:386-640) */
+  double aipohs[QGCM_NLMAX];
+  double cdiffo[QGCM_NLMAX * QGCM_NLMAX], cdhoc[QGCM_NLMAX * QGCM_NLMAX];
+  double hc1soc[QGCM_NLMAX], hc2soc[QGCM_NLMAX], hc1noc[QGCM_NLMAX], hc2noc[QGCM_NLMAX];
+  double aipcho[QGCM_NLMAX], hbsioc, aipbho;
+  /* ocean monitors */
+  double cfraoc, centoc;
+  double ttmads, vfmads, ttmdfs, ttmadn, vfmadn, ttmdfn;
+  double ermaso[QGCM_NLMAX], emfroc[QGCM_NLMAX];
+  double xinhom_oc[QGCM_NLMAX];       /* last xinhom(m) of ocinvq (debug/monitor) */
+  /* atmosphere constraints */
+  double xan[QGCM_NLMAX], dpiat[QGCM_NLMAX], dpiatp[QGCM_NLMAX];
+  double atmcs[QGCM_NLMAX], atmcn[QGCM_NLMAX], atmcsp[QGCM_NLMAX], atmcnp[QGCM_NLMAX];
+  double enisat[QGCM_NLMAX], eninat[QGCM_NLMAX];
+  double ajisat[QGCM_NLMAX], ajinat[QGCM_NLMAX];
+  double ap5sat[QGCM_NLMAX], ap5nat[QGCM_NLMAX];
+  double txisat, txinat;
+  double hc1sat[QGCM_NLMAX], hc2sat[QGCM_NLMAX], hc1nat[QGCM_NLMAX], hc2nat[QGCM_NLMAX];
+  double aipcha[QGCM_NLMAX], hbsiat, aipbha;
+  /* atmosphere monitors */
+  double cfraat, centat;
+  double ermasa[QGCM_NLMAX], emfrat[QGCM_NLMAX];
+  double xinhom_at[QGCM_NLMAX];
+  double arlaav, slhfav, oradav, arocav;
+  double reserved_d[16];
+} qgcm_scalars;
+
+typedef struct qgcm_model qgcm_model;   /* opaque */
+
+/* ---- lifetime ---------------------------------------------------------------- */
+
+/* Allocates device mirrors of the module storage of src/ocstate_data.F:39-55,
+ * src/atstate_data.F:37-40, src/intrfac_data.F:39-48, src/ochomog_data.F:44-69,
+ * builds the Helmholtz coefficient tables that src/q-gcm.F:929-973 computes
+ * (bd2oc/bd2at, aoc/aat) and the transform plans replacing dsinti/drffti. */
+int qgcm_create(const qgcm_config *cfg, qgcm_model **out);
+int qgcm_destroy(qgcm_model *m);
+const char *qgcm_last_error(void);
+int qgcm_abi_version(void);
+
+/* ---- state transfer ----------------------------------------------------------- */
+
+/* name is the reference's Fortran variable name, lower case: "po","pom","qo","qom",
+ * "sst","sstm","wekto","wekpo","entoc","tauxo","tauyo","fnetoc","ddynoc","ochom",
+ * "pch1oc","pch2oc","pbhoc", and the atmosphere twins "pa","pam","qa","qam","ast",
+ * "astm","hmixa","hmixam","wekta","wekpa","entat","tauxa","tauya","fnetat","ddynat",
+ * "dtopat","xc1ast","uekat","vekat","sstbar","astbar","pch1at","pch2at","pbhat".
+ * n is the element count and must match the Fortran declaration. */
+int qgcm_set_field(qgcm_model *m, const char *name, const double *host, int64_t n);
+int qgcm_get_field(qgcm_model *m, const char *name, double *host, int64_t n);
+int qgcm_field_size(qgcm_model *m, const char *name, int64_t *n);
+int qgcm_set_scalars(qgcm_model *m, const qgcm_scalars *s);
+int qgcm_get_scalars(qgcm_model *m, qgcm_scalars *s);
+int qgcm_sync(qgcm_model *m);
+
+/* ---- initialisation-time procedures that use the device solver ---------------- */
+
+/* constr, src/conhoms.F:44-314: dpioc, dpiocp (and ocncs.. / atmcs.. ) from p. */
+int qgcm_constr(qgcm_model *m);
+/* homsol, src/conhoms.F:318-818: ochom/aipohs/cdiffo/cdhoc (box) or
+ * pch1oc/pch2oc/pbhoc/hc* (cyclic), and the atmosphere twins. */
+int qgcm_homsol(qgcm_model *m);
+/* q from p for both time levels: qcomp + ocqbdy (+merqcy), src/q-gcm.F:719-732,
+ * and qcomp + atqzbd + merqcy for the atmosphere, src/q-gcm.F:738-749. */
+int qgcm_qcomp_ocean(qgcm_model *m);
+int qgcm_qcomp_atmos(qgcm_model *m);
+/* hsbxoc / hscyoc / hscyat, src/ocisubs.F:415-618, src/atisubs.F:301-395, on a
+ * host array wrk(nxp,nyp) with coefficient vector b(nxt); which: 0 ocean, 1 atmos. */
+int qgcm_helmholtz(qgcm_model *m, int which, double *wrk, const double *b);
+
+/* ---- the per-timestep procedures (src/q-gcm.F:1222-1269) ---------------------- */
+
+int qgcm_xforc(qgcm_model *m);      /* src/xfosubs.F:52-858   */
+int qgcm_oml(qgcm_model *m);        /* src/omlsubs.F:47-236   */
+int qgcm_qgostep(qgcm_model *m);    /* src/qgosubs.F:45-221   */
+int qgcm_ocinvq(qgcm_model *m);     /* src/ocisubs.F:64-407   */
+int qgcm_ocqbdy(qgcm_model *m);     /* src/vorsubs.F:245-388, call ocqbdy(qo,po) */
+int qgcm_aml(qgcm_model *m);        /* src/amlsubs.F:47-238   */
+int qgcm_qgastep(qgcm_model *m);    /* src/qgasubs.F:45-148   */
+int qgcm_atinvq(qgcm_model *m);     /* src/atisubs.F:60-293   */
+int qgcm_atqzbd(qgcm_model *m);     /* src/vorsubs.F:396-480, call atqzbd(qa,pa) */
+int qgcm_tlavg_ocean(qgcm_model *m);  /* src/q-gcm.F:1328-1366 */
+int qgcm_tlavg_atmos(qgcm_model *m);  /* src/q-gcm.F:1370-1407 */
+
+/* oml + qgostep + ocinvq + ocqbdy, the body of src/q-gcm.F:1229-1249 */
+int qgcm_ocean_step(qgcm_model *m);
+/* aml + qgastep + atinvq + atqzbd, src/q-gcm.F:1257-1269 */
+int qgcm_atmos_step(qgcm_model *m);
+/* The loop body of src/q-gcm.F:1220-1408 for nt = nt_first..nt_last inclusive:
+ * ocean step when mod(nt,nstr)==1 (every step when nstr==1),
+ * atmosphere step unless ocean_only, time-level averaging on its cadence. */
+int qgcm_run(qgcm_model *m, int64_t nt_first, int64_t nt_last);
+
+/* ---- instrumentation ---------------------------------------------------------- */
+
+/* number of kernels launched by this model since creation */
+int64_t qgcm_launch_count(qgcm_model *m);
+/* cudaStream_t the model launches on, as an opaque pointer (for event timing) */
+void *qgcm_stream(qgcm_model *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QGCM_B200_H */

@@ -1,0 +1,97 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle for the Q-GCM hot path (parity UNPINNED by the
+// reference's own tests: the reference ships no golden vectors and cannot be compiled
+// in this image, see oracle/README.md).  Never linked into or imported by the product.
+//
+// Loop-for-loop C++ restatement of the reference's Fortran step routines, same loop
+// order and expression association, compiled with -ffp-contract=off.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../include/qgcm_b200.h"
+#include "orc_fft.h"
+
+namespace orc {
+
+typedef std::vector<double> vec;
+
+struct Model {
+  qgcm_config c;
+  bool ocean_only, atmos_only, cyclic, sb_hflux, nb_hflux, tau_udiff;
+  // grid (src/parameters_data.F:78-88)
+  int nxto, nyto, nxpo, nypo, nlo;
+  int nxta, nyta, nxpa, nypa, nla;
+  int ndxr, nx1, ny1, nstr;
+  int nxtaor, nytaor, nxpaor, nypaor;
+  // derived constants (src/q-gcm.F:377-452)
+  double fnot, beta;
+  double dxo, dyo, hdxom1, dxom2, xlo, ylo, rdxof0, rrcpoc, tdto, dto, ocnorm;
+  double dxa, dya, hdxam1, dxam2, xla, yla, rdxaf0, rrcpat, tdta, dta, atnorm, raoro;
+  vec ypo, yporel, yto, ytorel, ypa, yparel, yta, ytarel;
+  // Helmholtz (src/q-gcm.F:929-973)
+  double aoc, aat;
+  vec bd2oc, bd2at;
+  FftPlan planoc, planat;
+  // ocean state (src/ocstate_data.F:39-55, src/intrfac_data.F:39-48)
+  vec po, pom, qo, qom, wekpo, wekto, entoc, ddynoc;
+  vec sst, sstm, sstbar, tauxo, tauyo, fnetoc;
+  // ocean homogeneous solutions (src/ochomog_data.F:44-55)
+  vec ochom, pch1oc, pch2oc, pbhoc;
+  // atmosphere state (src/atstate_data.F:37-40)
+  vec pa, pam, qa, qam, wekpa, wekta, entat, ddynat, dtopat, xc1ast;
+  vec ast, astm, astbar, hmixa, hmixam, tauxa, tauya, fnetat, uekat, vekat;
+  vec pch1at, pch2at, pbhat;
+  // xforc module storage (src/xfosubs.F:43-46)
+  vec stbbb, stbus, stbun, stbvs, stbvn;  // bicubic weights (bcuini)
+  bool bcu_ready = false;
+  qgcm_scalars s;
+
+  explicit Model(const qgcm_config &cfg);
+  vec *field(const std::string &name);
+
+  // src/intsubs.f
+  static double xintt(const double *v, int nxt, int nyt);
+  static double xintp(const double *v, int nxp, int nyp);
+  // src/vorsubs.F
+  void qcomp(double *q, const double *p, const double *aaa, const double *yprel, double dxm2,
+             int nxp, int nyp, int nl, const double *ddyn, int kbot) const;
+  void merqcy(double *q, const double *p, const double *aaa, const double *yprel, double dxm2,
+              int nxp, int nyp, int nl, const double *ddyn, int kbot) const;
+  void ocqbdy(double *q, const double *p);
+  void atqzbd(double *q, const double *p);
+  // src/qgosubs.F
+  void qgostep();
+  void ocadif(double *dqdt, const double *d2p, double ah2ock, double ah4ock, double bcfaco,
+              const double *p, const double *q, double adfaco, int k);
+  // src/ocisubs.F
+  void ocinvq();
+  void hsbxoc(double *wrk, const double *boc);
+  void hscyoc(double *wrk, const double *boc);
+  // src/omlsubs.F
+  void oml();
+  void omladf(double *rhs, const double *po1);
+  // src/xfosubs.F
+  void xforc();
+  void xforc_ocean_ekman();
+  // src/conhoms.F
+  void constr();
+  void homsol();
+  // src/q-gcm.F:1328-1407
+  void tlavg_ocean();
+  void tlavg_atmos();
+  // src/qgasubs.F, src/atisubs.F, src/amlsubs.F
+  void qgastep();
+  void atadif(double *dqdt, const double *d2p, double ah4atk, double bcfaat, const double *p,
+              const double *q, double adfaca, int k);
+  void atinvq();
+  void hscyat(double *wrk, const double *bat);
+  void aml();
+  void amladf(double *rhsat, double *rhshm, const double *pa1);
+  // src/q-gcm.F:719-749
+  void qcomp_ocean();
+  void qcomp_atmos();
+  void run(int64_t nt_first, int64_t nt_last);
+};
+
+}  // namespace orc

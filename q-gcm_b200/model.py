@@ -1,0 +1,167 @@
+"""ctypes binding of the C ABI in include/qgcm_b200.h.
+
+``Model`` is the product binding (libqgcm_b200.so, CUDA only).  Its methods carry the
+names of the reference subroutines they replace (src/q-gcm.F:1222-1269) so the parity
+tests read like the reference's main loop.  ``CModel`` is the generic binding the
+tests also point at the oracle's liborc.so (same struct layout, ``orc_`` prefix).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .abi import QgcmConfig, QgcmScalars, declared_functions
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def library_path():
+    return os.path.join(_HERE, "csrc", "libqgcm_b200.so")
+
+
+def load_library():
+    """load libqgcm_b200.so; raises (never falls back) if it has not been built"""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise RuntimeError(
+                "libqgcm_b200.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                "there is no CPU fallback" % path)
+        _LIB = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    return _LIB
+
+
+class CModel:
+    """one model instance behind a C ABI with the given symbol prefix"""
+
+    def __init__(self, lib, prefix, cfg: QgcmConfig):
+        self._lib = lib
+        self._pfx = prefix
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        create = self._fn("create")
+        create.argtypes = [C.POINTER(QgcmConfig), C.POINTER(C.c_void_p)]
+        rc = create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError("%screate failed: %s" % (prefix, self._err()))
+        self.nxpo, self.nypo = cfg.nxto + 1, cfg.nyto + 1
+        self.nxpa, self.nypa = cfg.nxta + 1, cfg.nyta + 1
+
+    # -- plumbing
+    def _fn(self, name):
+        return getattr(self._lib, self._pfx + name)
+
+    def _err(self):
+        f = self._fn("last_error")
+        f.restype = C.c_char_p
+        return (f() or b"").decode()
+
+    def _call(self, name, *args):
+        f = self._fn(name)
+        f.restype = C.c_int
+        rc = f(self._h, *args)
+        if rc != 0:
+            raise RuntimeError("%s%s failed: %s" % (self._pfx, name, self._err()))
+
+    def close(self):
+        if self._h:
+            self._fn("destroy")(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- state transfer
+    def field_size(self, name):
+        n = C.c_int64()
+        self._call("field_size", name.encode(), C.byref(n))
+        return n.value
+
+    def set_field(self, name, arr):
+        a = np.ascontiguousarray(np.asarray(arr, dtype=np.float64).ravel(order="F"))
+        self._call("set_field", name.encode(), a.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(a.size))
+
+    def get_field(self, name, shape=None):
+        n = self.field_size(name)
+        out = np.empty(n, dtype=np.float64)
+        self._call("get_field", name.encode(), out.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(n))
+        if shape is not None:
+            out = out.reshape(shape, order="F")
+        return out
+
+    def set_scalars(self, s: QgcmScalars):
+        self._call("set_scalars", C.byref(s))
+
+    def get_scalars(self) -> QgcmScalars:
+        s = QgcmScalars()
+        self._call("get_scalars", C.byref(s))
+        return s
+
+    def helmholtz(self, which, wrk, b):
+        w = np.ascontiguousarray(np.asarray(wrk, dtype=np.float64).ravel(order="F"))
+        bb = np.ascontiguousarray(np.asarray(b, dtype=np.float64))
+        self._call("helmholtz", C.c_int(which), w.ctypes.data_as(C.POINTER(C.c_double)),
+                   bb.ctypes.data_as(C.POINTER(C.c_double)))
+        return w.reshape(np.asarray(wrk).shape, order="F")
+
+    # -- the reference's procedures
+    def constr(self): self._call("constr")
+    def homsol(self): self._call("homsol")
+    def qcomp_ocean(self): self._call("qcomp_ocean")
+    def qcomp_atmos(self): self._call("qcomp_atmos")
+    def xforc(self): self._call("xforc")
+    def oml(self): self._call("oml")
+    def qgostep(self): self._call("qgostep")
+    def ocinvq(self): self._call("ocinvq")
+    def ocqbdy(self): self._call("ocqbdy")
+    def aml(self): self._call("aml")
+    def qgastep(self): self._call("qgastep")
+    def atinvq(self): self._call("atinvq")
+    def atqzbd(self): self._call("atqzbd")
+    def tlavg_ocean(self): self._call("tlavg_ocean")
+    def tlavg_atmos(self): self._call("tlavg_atmos")
+    def ocean_step(self): self._call("ocean_step")
+    def atmos_step(self): self._call("atmos_step")
+
+    def run(self, nt_first, nt_last):
+        self._call("run", C.c_int64(nt_first), C.c_int64(nt_last))
+
+    # -- convenience: whole-state load/store used by tests and bench
+    OCEAN_FIELDS = ("po", "pom", "qo", "qom", "sst", "sstm", "wekto", "wekpo", "entoc", "tauxo", "tauyo",
+                    "fnetoc", "ddynoc")
+    ATMOS_FIELDS = ("pa", "pam", "qa", "qam", "ast", "astm", "hmixa", "hmixam", "wekta", "wekpa", "entat",
+                    "tauxa", "tauya", "fnetat", "ddynat", "dtopat", "xc1ast", "uekat", "vekat")
+
+    def load_state(self, state: dict):
+        for k, v in state.items():
+            self.set_field(k, v)
+
+
+class Model(CModel):
+    """the CUDA model (libqgcm_b200.so)"""
+
+    def __init__(self, cfg: QgcmConfig):
+        super().__init__(load_library(), "qgcm_", cfg)
+
+    def sync(self):
+        self._call("sync")
+
+    def launch_count(self):
+        f = self._lib.qgcm_launch_count
+        f.restype = C.c_int64
+        return int(f(self._h))
+
+    def stream(self):
+        f = self._lib.qgcm_stream
+        f.restype = C.c_void_p
+        return f(self._h)
+
+    @staticmethod
+    def exported_symbols_ok():
+        lib = load_library()
+        return [n for n in declared_functions() if not hasattr(lib, n)]
