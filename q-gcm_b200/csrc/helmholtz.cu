@@ -1,0 +1,610 @@
+// Batched modified-Helmholtz solver: replaces hsbxoc / hscyoc / hscyat
+// (src/ocisubs.F:415-618, src/atisubs.F:301-395) and the FFTPACK routines they call
+// (src/fftpack/newbihar/dsint.f, drfftf.f, drfftb.f).
+//
+//   x-direction : one thread block per (mode, row); the row lives in shared memory, a
+//                 Stockham mixed-radix complex FFT of length n/2 plus the real / sine
+//                 pre- and post-processing (published FFTPACK algorithm, dsint.f:17-43).
+//   y-direction : the constant-coefficient tridiagonal systems (one per wavenumber)
+//                 are partitioned into chunks of TRI_L rows.  Each chunk is solved
+//                 locally in registers (Thomas), the chunk interfaces are coupled by a
+//                 small block-tridiagonal system per wavenumber, and the correction
+//                 (two precomputed spike vectors, Toeplitz => identical for every
+//                 chunk) is applied on the fly when the inverse transform loads a row.
+//                 All global accesses are full-row coalesced; no transpose.
+#include <cmath>
+
+#include "qgcm_internal.h"
+
+namespace qg {
+
+// --------------------------------------------------------------------------------------
+// complex helpers
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cmulmi(double2 a) { return make_double2(a.y, -a.x); }  // a * (-i)
+__device__ __forceinline__ double2 cscale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+
+template <int R>
+__device__ __forceinline__ void dft(double2 *v);
+
+template <>
+__device__ __forceinline__ void dft<2>(double2 *v) {
+  double2 a = v[0], b = v[1];
+  v[0] = cadd(a, b);
+  v[1] = csub(a, b);
+}
+template <>
+__device__ __forceinline__ void dft<4>(double2 *v) {
+  double2 a = cadd(v[0], v[2]), b = csub(v[0], v[2]), c = cadd(v[1], v[3]), d = cmulmi(csub(v[1], v[3]));
+  v[0] = cadd(a, c);
+  v[1] = cadd(b, d);
+  v[2] = csub(a, c);
+  v[3] = csub(b, d);
+}
+template <>
+__device__ __forceinline__ void dft<3>(double2 *v) {
+  const double s = 0.86602540378443864676;
+  double2 t1 = cadd(v[1], v[2]);
+  double2 t2 = make_double2(v[0].x - 0.5 * t1.x, v[0].y - 0.5 * t1.y);
+  double2 t3 = cscale(cmulmi(csub(v[1], v[2])), s);
+  v[0] = cadd(v[0], t1);
+  v[1] = cadd(t2, t3);
+  v[2] = csub(t2, t3);
+}
+template <>
+__device__ __forceinline__ void dft<5>(double2 *v) {
+  const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
+  const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
+  double2 a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]);
+  double2 b1 = cmulmi(csub(v[1], v[4])), b2 = cmulmi(csub(v[2], v[3]));
+  double2 r1 = make_double2(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
+  double2 r2 = make_double2(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+  double2 i1 = make_double2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+  double2 i2 = make_double2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+  v[0] = cadd(v[0], cadd(a1, a2));
+  v[1] = cadd(r1, i1);
+  v[4] = csub(r1, i1);
+  v[2] = cadd(r2, i2);
+  v[3] = csub(r2, i2);
+}
+template <>
+__device__ __forceinline__ void dft<8>(double2 *v) {
+  const double h = 0.70710678118654752440;
+  // three radix-2 stages (decimation in time on the 8 inputs)
+  double2 e[4] = {v[0], v[2], v[4], v[6]};
+  double2 o[4] = {v[1], v[3], v[5], v[7]};
+  dft<4>(e);
+  dft<4>(o);
+  double2 w1 = make_double2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));     // o1 * e^{-i pi/4}
+  double2 w2 = cmulmi(o[2]);                                                   // o2 * (-i)
+  double2 w3 = make_double2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));    // o3 * e^{-3i pi/4}
+  v[0] = cadd(e[0], o[0]);
+  v[4] = csub(e[0], o[0]);
+  v[1] = cadd(e[1], w1);
+  v[5] = csub(e[1], w1);
+  v[2] = cadd(e[2], w2);
+  v[6] = csub(e[2], w2);
+  v[3] = cadd(e[3], w3);
+  v[7] = csub(e[3], w3);
+}
+
+// One Stockham pass of radix R over the complex array `in` (length M) into `out`.
+// Ns = product of the radices of the previous passes.
+template <int R>
+__device__ __forceinline__ void fft_pass(const double2 *__restrict__ in, double2 *__restrict__ out, int M, int Ns,
+                                         const double2 *__restrict__ wm) {
+  const int L = M / R;
+  const int tws = M / (Ns * R);
+  for (int j = threadIdx.x; j < L; j += blockDim.x) {
+    const int k = j % Ns;
+    const int j0 = (j - k) * R + k;
+    double2 v[R];
+    v[0] = in[j];
+    if (Ns == 1) {
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[r] = in[j + r * L];
+    } else {
+      const int tw = k * tws;
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[r] = cmul(in[j + r * L], __ldg(&wm[r * tw]));
+    }
+    dft<R>(v);
+#pragma unroll
+    for (int r = 0; r < R; ++r) out[j0 + r * Ns] = v[r];
+  }
+}
+
+struct FftDev {
+  int n, m, nrad;
+  int radix[16];
+  const double2 *wm, *wn;
+  const double *sintw;
+};
+
+// forward complex FFT of length p.m; data in a, scratch b; returns pointer holding the result
+__device__ __forceinline__ double2 *cfft_smem(const FftDev &p, double2 *a, double2 *b) {
+  int Ns = 1;
+  for (int s = 0; s < p.nrad; ++s) {
+    const int R = p.radix[s];
+    switch (R) {
+      case 2: fft_pass<2>(a, b, p.m, Ns, p.wm); break;
+      case 3: fft_pass<3>(a, b, p.m, Ns, p.wm); break;
+      case 4: fft_pass<4>(a, b, p.m, Ns, p.wm); break;
+      case 5: fft_pass<5>(a, b, p.m, Ns, p.wm); break;
+      default: fft_pass<8>(a, b, p.m, Ns, p.wm); break;
+    }
+    __syncthreads();
+    double2 *t = a;
+    a = b;
+    b = t;
+    Ns *= R;
+  }
+  return a;
+}
+
+// block-wide sum, result valid in every thread; red must hold 32 doubles
+__device__ __forceinline__ double block_sum(double v, double *red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < nw; ++i) t += red[i];   // fixed order: deterministic
+  return t;
+}
+
+// Parameters of one x-transform launch
+struct XfArgs {
+  FftDev f;
+  int kind;        // 0 DST-I, 1 real FFT
+  int inverse;     // 0 forward (rhs -> spectrum), 1 inverse (tridiagonal solution -> field)
+  int ld, nyp, nxp;
+  size_t lsz;      // mode stride
+  int nchunk, lastlen;
+  double ftnorm;
+  double *wrk;
+  const double *vl, *vll, *yx;   // spike tables and interface values (inverse only)
+  double *rowsum;                // [nmodes][nyp] (inverse only)
+};
+
+// value of the tridiagonal solution at (mode, interior row r, column col): local chunk
+// solution plus the two spike corrections, times ftnorm (src/ocisubs.F:484-487)
+__device__ __forceinline__ double corrected(const XfArgs &a, int mode, int r, int col, double u0) {
+  if (a.nchunk > 1) {
+    const int c = r / TRI_L, jl = r - c * TRI_L;
+    const size_t tb = ((size_t)mode * TRI_L) * a.ld;
+    const size_t yb = ((size_t)mode * 2 * a.nchunk) * a.ld;
+    const double yp = a.yx[yb + (size_t)c * a.ld + col];
+    const double xn = a.yx[yb + (size_t)(a.nchunk + c) * a.ld + col];
+    const double vleft = (c == a.nchunk - 1) ? a.vll[tb + (size_t)jl * a.ld + col] : a.vl[tb + (size_t)jl * a.ld + col];
+    const double vright = a.vl[tb + (size_t)(TRI_L - 1 - jl) * a.ld + col];
+    u0 = u0 + yp * vleft + xn * vright;
+  }
+  return a.ftnorm * u0;
+}
+
+// grid (nrows, nmodes); dynamic smem = 2*n doubles*... (two complex buffers of length m) + 64 doubles
+__global__ void __launch_bounds__(256) k_xform(XfArgs a) {
+  extern __shared__ double2 smem2[];
+  const int N = a.f.n, M = a.f.m;
+  double2 *A = smem2, *B = smem2 + M;
+  double *red = reinterpret_cast<double *>(smem2 + 2 * M);
+  const int r = blockIdx.x;            // interior row index, j = r + 2
+  const int mode = blockIdx.y;
+  double *row = a.wrk + (size_t)mode * a.lsz + (size_t)(r + 1) * a.ld;
+  double *Ar = reinterpret_cast<double *>(A), *Br = reinterpret_cast<double *>(B);
+  const int T = blockDim.x, t = threadIdx.x;
+
+  if (a.kind == 0) {
+    // ---------------- DST-I of row(2:nxto), dsint.f:17-43 ----------------
+    for (int k = t + 1; k < N; k += T) {
+      double x = row[k];
+      if (a.inverse) x = corrected(a, mode, r, k, x);
+      Br[k] = x;
+    }
+    __syncthreads();
+    for (int k = t; k <= M; k += T) {
+      if (k == 0) {
+        Ar[0] = 0.0;
+      } else if (k == M) {
+        Ar[M] = 4.0 * Br[M];
+      } else {
+        const double xa = Br[k], xb = Br[N - k];
+        const double t1 = xa - xb, t2 = a.f.sintw[k] * (xa + xb);
+        Ar[k] = t1 + t2;
+        Ar[N - k] = t2 - t1;
+      }
+    }
+    __syncthreads();
+    double2 *Z = cfft_smem(a.f, A, B);
+    double2 *O = (Z == A) ? B : A;
+    // real post-processing: F_k, k = 0..M-1 (F_M is not needed by the sine transform)
+    for (int k = t; k < M; k += T) {
+      double2 F;
+      if (k == 0) {
+        F = make_double2(Z[0].x + Z[0].y, 0.0);
+      } else {
+        const double2 za = Z[k], zb = cconj(Z[M - k]);
+        const double2 e = cscale(cadd(za, zb), 0.5);
+        const double2 o = cmul(cscale(cmulmi(csub(za, zb)), 0.5), a.f.wn[k]);
+        F = cadd(e, o);
+      }
+      O[k] = F;
+    }
+    __syncthreads();
+    // odd outputs are a running sum of Re F (dsint.f:33-37): chunked block scan
+    double *Or = reinterpret_cast<double *>(O);   // Re F_k at Or[2k], Im F_k at Or[2k+1]
+    double *Zr = reinterpret_cast<double *>(Z);   // output array out[1..N-1]
+    const int per = (M + T - 1) / T;
+    const int k0 = t * per, k1 = min(M, k0 + per);
+    double loc = 0.0;
+    for (int k = k0; k < k1; ++k) loc += (k == 0) ? 0.5 * Or[0] : Or[2 * k];
+    // exclusive scan of per-thread totals
+    const int lane = t & 31, w = t >> 5, nw = (T + 31) >> 5;
+    double inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double nb = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += nb;
+    }
+    if (lane == 31) red[w] = inc;
+    __syncthreads();
+    double woff = 0.0;
+    for (int i = 0; i < w; ++i) woff += red[i];
+    (void)nw;
+    double run = woff + inc - loc;
+    for (int k = k0; k < k1; ++k) {
+      run += (k == 0) ? 0.5 * Or[0] : Or[2 * k];
+      Zr[2 * k + 1] = run;                      // out_{2k+1}
+      if (k >= 1) Zr[2 * k] = -Or[2 * k + 1];   // out_{2k} = -Im F_k
+    }
+    __syncthreads();
+    double part = 0.0;
+    for (int k = t + 1; k < N; k += T) {
+      const double v = Zr[k];
+      row[k] = v;
+      part += v;
+    }
+    if (a.inverse) {
+      if (t == 0) {
+        row[0] = 0.0;
+        row[a.nxp - 1] = 0.0;
+      }
+      const double s = block_sum(part, red);
+      if (t == 0) a.rowsum[(size_t)mode * a.nyp + (r + 1)] = s;
+    }
+  } else if (!a.inverse) {
+    // ---------------- forward real FFT, packed order (fft.doc:96-114) ----------------
+    for (int k = t; k < N; k += T) Ar[k] = row[k];
+    __syncthreads();
+    double2 *Z = cfft_smem(a.f, A, B);
+    for (int k = t; k <= M; k += T) {
+      if (k == 0) {
+        row[0] = Z[0].x + Z[0].y;
+      } else if (k == M) {
+        row[N - 1] = Z[0].x - Z[0].y;
+      } else {
+        const double2 za = Z[k], zb = cconj(Z[M - k]);
+        const double2 e = cscale(cadd(za, zb), 0.5);
+        const double2 o = cmul(cscale(cmulmi(csub(za, zb)), 0.5), a.f.wn[k]);
+        const double2 F = cadd(e, o);
+        row[2 * k - 1] = F.x;
+        row[2 * k] = F.y;
+      }
+    }
+  } else {
+    // ---------------- inverse real FFT (drfftb), then periodic wrap ----------------
+    for (int k = t; k < N; k += T) Br[k] = corrected(a, mode, r, k, row[k]);
+    __syncthreads();
+    for (int k = t; k < M; k += T) {
+      double2 xa, xb;   // X_k, conj X_{M-k}
+      if (k == 0) {
+        xa = make_double2(Br[0], 0.0);
+        xb = make_double2(Br[N - 1], 0.0);
+      } else {
+        xa = make_double2(Br[2 * k - 1], Br[2 * k]);
+        xb = make_double2(Br[2 * (M - k) - 1], -Br[2 * (M - k)]);
+      }
+      const double2 e = cadd(xa, xb);
+      const double2 d = csub(xa, xb);
+      const double2 wc = cconj(a.f.wn[k]);
+      const double2 dw = cmul(d, wc);
+      const double2 o = make_double2(-dw.y, dw.x);   // i * dw
+      A[k] = cconj(cadd(e, o));
+    }
+    __syncthreads();
+    double2 *Z = cfft_smem(a.f, A, B);
+    double part = 0.0;
+    for (int k = t; k < M; k += T) {
+      const double v0 = Z[k].x, v1 = -Z[k].y;
+      row[2 * k] = v0;
+      row[2 * k + 1] = v1;
+      part += (k == 0) ? v1 : (v0 + v1);   // x_0 is added below with its two half weights
+    }
+    if (t == 0) row[a.nxp - 1] = Z[0].x;
+    double s = block_sum(part, red);
+    // xintp row sum: 0.5*v(1) + sum_{2}^{nxp-1} + 0.5*v(nxp), v(nxp) = v(1)
+    if (t == 0) a.rowsum[(size_t)mode * a.nyp + (r + 1)] = 0.5 * Z[0].x + s + 0.5 * Z[0].x;
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// y-direction: partitioned tridiagonal solve
+// --------------------------------------------------------------------------------------
+struct TriArgs {
+  int ld, nyp, nk, koff, nchunk, lastlen, nmodes;
+  size_t lsz;
+  double a;
+  double *wrk;
+  const double *bcoef;
+  double *binv, *vl, *vll, *pt, *fg, *yx;
+};
+
+// one thread per (column, mode): elimination reciprocals, spike vectors, interface pivots
+__global__ void k_tri_tables(TriArgs t) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int mode = blockIdx.y;
+  if (s >= t.nk) return;
+  const int col = t.koff + s;
+  const double b = t.bcoef[(size_t)mode * t.ld + col], a = t.a;
+  double binv[TRI_L], w[TRI_L];
+  binv[0] = 1.0 / b;
+  for (int j = 1; j < TRI_L; ++j) binv[j] = 1.0 / (b - a * (a * binv[j - 1]));
+  const size_t tb = ((size_t)mode * TRI_L) * t.ld + col;
+  for (int j = 0; j < TRI_L; ++j) t.binv[tb + (size_t)j * t.ld] = binv[j];
+  double alpha = 0.0, eps = 0.0, alphal = 0.0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int len = pass == 0 ? TRI_L : t.lastlen;
+    w[0] = (-a) * binv[0];
+    for (int j = 1; j < len; ++j) w[j] = (-a * w[j - 1]) * binv[j];
+    for (int j = len - 2; j >= 0; --j) w[j] = w[j] - (a * binv[j]) * w[j + 1];
+    double *dst = pass == 0 ? t.vl : t.vll;
+    for (int j = 0; j < TRI_L; ++j) dst[tb + (size_t)j * t.ld] = j < len ? w[j] : 0.0;
+    if (pass == 0) {
+      alpha = w[0];
+      eps = w[TRI_L - 1];
+    } else {
+      alphal = w[0];
+    }
+  }
+  // interface c (between chunks c-1 and c), c = 1..C-1: D'_c = [[1, p_c],[q_c, 1]]
+  const int C = t.nchunk;
+  double p = -alpha;
+  for (int c = 1; c < C; ++c) {
+    const double q = (c == C - 1) ? -alphal : -alpha;
+    t.pt[((size_t)mode * C + c) * t.ld + col] = p;
+    p = -alpha + eps * eps * p / (1.0 - p * q);
+  }
+}
+
+// chunk-local Thomas solve entirely in registers; grid (ceil(nk/128), nchunk, nmodes)
+__global__ void __launch_bounds__(128) k_tri_local(TriArgs t) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y, mode = blockIdx.z;
+  if (s >= t.nk) return;
+  const int col = t.koff + s;
+  const int len = (c == t.nchunk - 1) ? t.lastlen : TRI_L;
+  double *base = t.wrk + (size_t)mode * t.lsz + (size_t)(1 + c * TRI_L) * t.ld + col;
+  const double *bi = t.binv + ((size_t)mode * TRI_L) * t.ld + col;
+  const double a = t.a;
+  double u[TRI_L], g[TRI_L];
+#pragma unroll
+  for (int j = 0; j < TRI_L; ++j) {
+    u[j] = (j < len) ? base[(size_t)j * t.ld] : 0.0;
+    g[j] = bi[(size_t)j * t.ld];
+  }
+  u[0] = u[0] * g[0];
+#pragma unroll
+  for (int j = 1; j < TRI_L; ++j) u[j] = (u[j] - a * u[j - 1]) * g[j];
+#pragma unroll
+  for (int j = TRI_L - 2; j >= 0; --j)
+    if (j < len - 1) u[j] = u[j] - (a * g[j]) * u[j + 1];
+#pragma unroll
+  for (int j = 0; j < TRI_L; ++j)
+    if (j < len) base[(size_t)j * t.ld] = u[j];
+  if (t.nchunk > 1) {
+    double last = u[0];
+#pragma unroll
+    for (int j = 1; j < TRI_L; ++j)
+      if (j == len - 1) last = u[j];
+    const size_t fb = ((size_t)mode * 2 * t.nchunk) * t.ld + col;
+    t.fg[fb + (size_t)c * t.ld] = u[0];                    // f_c : first row of the chunk
+    t.fg[fb + (size_t)(t.nchunk + c) * t.ld] = last;       // g_c : last row of the chunk
+  }
+}
+
+// interface system: one thread per (column, mode), block Thomas over the chunks
+__global__ void k_tri_reduced(TriArgs t) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int mode = blockIdx.y;
+  if (s >= t.nk) return;
+  const int col = t.koff + s;
+  const int C = t.nchunk;
+  const size_t tb = ((size_t)mode * TRI_L) * t.ld + col;
+  const double alpha = t.vl[tb], eps = t.vl[tb + (size_t)(TRI_L - 1) * t.ld], alphal = t.vll[tb];
+  const size_t fb = ((size_t)mode * 2 * C) * t.ld + col;
+  double *f = t.fg + fb, *g = t.fg + fb + (size_t)C * t.ld;      // f[c], g[c] at stride ld
+  double *yp = t.yx + fb, *xn = t.yx + fb + (size_t)C * t.ld;
+  const double *pt = t.pt + ((size_t)mode * C) * t.ld + col;
+  // forward elimination: h0_c overwrites g[c-1]
+  double h0 = g[0], h1 = f[t.ld], p = pt[t.ld], q = (1 == C - 1) ? -alphal : -alpha;
+  for (int c = 2; c < C; ++c) {
+    const double t0 = (h0 - p * h1) / (1.0 - p * q);
+    h0 = g[(size_t)(c - 1) * t.ld] + eps * t0;
+    g[(size_t)(c - 1) * t.ld] = h0;
+    h1 = f[(size_t)c * t.ld];
+    p = pt[(size_t)c * t.ld];
+    q = (c == C - 1) ? -alphal : -alpha;
+  }
+  // back substitution
+  double xnext = 0.0;
+  yp[0] = 0.0;
+  xn[(size_t)(C - 1) * t.ld] = 0.0;
+  for (int c = C - 1; c >= 1; --c) {
+    const double pc = pt[(size_t)c * t.ld];
+    const double qc = (c == C - 1) ? -alphal : -alpha;
+    const double hh0 = g[(size_t)(c - 1) * t.ld];
+    const double hh1 = f[(size_t)c * t.ld] + eps * xnext;
+    const double det = 1.0 - pc * qc;
+    const double y = (hh0 - pc * hh1) / det;    // y_{c-1}: last row of chunk c-1
+    const double x = (hh1 - qc * hh0) / det;    // x_c    : first row of chunk c
+    yp[(size_t)c * t.ld] = y;
+    xn[(size_t)(c - 1) * t.ld] = x;
+    xnext = x;
+  }
+}
+
+__global__ void k_zero_rows(double *wrk, size_t lsz, int ld, int nyp, int nxp, int nmodes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nxp) return;
+  for (int m = 0; m < nmodes; ++m) {
+    wrk[(size_t)m * lsz + i] = 0.0;
+    wrk[(size_t)m * lsz + (size_t)(nyp - 1) * ld + i] = 0.0;
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------
+static bool factorize(int m, int *radix, int &nrad) {
+  nrad = 0;
+  // odd radices first (conflict-free shared-memory scatter while Ns is small), then 8/4/2
+  while (m % 5 == 0) { radix[nrad++] = 5; m /= 5; }
+  while (m % 3 == 0) { radix[nrad++] = 3; m /= 3; }
+  while (m % 8 == 0) { radix[nrad++] = 8; m /= 8; }
+  while (m % 4 == 0) { radix[nrad++] = 4; m /= 4; }
+  while (m % 2 == 0) { radix[nrad++] = 2; m /= 2; }
+  return m == 1 && nrad <= 16;
+}
+
+void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, const double *rdm2, int nmodes) {
+  hp.kind = kind;
+  hp.n = g.nxt;
+  if (hp.n % 2 != 0) throw std::runtime_error("helmholtz: nxt must be even");
+  hp.m = hp.n / 2;
+  if (!factorize(hp.m, hp.radix, hp.nrad))
+    throw std::runtime_error("helmholtz: nxt/2 must factor into 2,3,5 (src/parameters_data.F:63-67 recommends the same)");
+  hp.nmodes = nmodes;
+  hp.ld = g.ld;
+  hp.nyp = g.nyp;
+  hp.nxp = g.nxp;
+  hp.nrows = g.nyp - 2;
+  hp.nchunk = (hp.nrows + TRI_L - 1) / TRI_L;
+  hp.lastlen = hp.nrows - (hp.nchunk - 1) * TRI_L;
+  hp.nk = kind == 0 ? hp.n - 1 : hp.n;
+  hp.koff = kind == 0 ? 1 : 0;
+  hp.a = g.dxm2;  // dy = dx (src/q-gcm.F:413, :930)
+  hp.ftnorm = kind == 0 ? 0.5 / hp.n : 1.0 / hp.n;
+  hp.smem_bytes = (size_t)2 * hp.m * sizeof(double2) + 64 * sizeof(double);
+  // twiddles in extended precision, rounded once
+  std::vector<double2> wm(hp.m), wn(hp.m + 1);
+  std::vector<double> sw(hp.m);
+  const long double PI_L = 3.141592653589793238462643383279502884L;
+  for (int k = 0; k < hp.m; ++k) {
+    long double a = -2.0L * PI_L * k / hp.m;
+    wm[k] = make_double2((double)cosl(a), (double)sinl(a));
+    sw[k] = (double)(2.0L * sinl(PI_L * k / hp.n));
+  }
+  for (int k = 0; k <= hp.m; ++k) {
+    long double a = -2.0L * PI_L * k / hp.n;
+    wn[k] = make_double2((double)cosl(a), (double)sinl(a));
+  }
+  hp.wm = (double2 *)dalloc(md, sizeof(double2) * hp.m);
+  hp.wn = (double2 *)dalloc(md, sizeof(double2) * (hp.m + 1));
+  hp.sintw = (double *)dalloc(md, sizeof(double) * hp.m);
+  QG_CUDA(cudaMemcpy(hp.wm, wm.data(), sizeof(double2) * hp.m, cudaMemcpyHostToDevice));
+  QG_CUDA(cudaMemcpy(hp.wn, wn.data(), sizeof(double2) * (hp.m + 1), cudaMemcpyHostToDevice));
+  QG_CUDA(cudaMemcpy(hp.sintw, sw.data(), sizeof(double) * hp.m, cudaMemcpyHostToDevice));
+  const size_t row = (size_t)hp.ld;
+  hp.bcoef = (double *)dalloc(md, sizeof(double) * nmodes * row);
+  hp.binv = (double *)dalloc(md, sizeof(double) * nmodes * TRI_L * row);
+  hp.vl = (double *)dalloc(md, sizeof(double) * nmodes * TRI_L * row);
+  hp.vll = (double *)dalloc(md, sizeof(double) * nmodes * TRI_L * row);
+  hp.pt = (double *)dalloc(md, sizeof(double) * nmodes * hp.nchunk * row);
+  hp.fg = (double *)dalloc(md, sizeof(double) * nmodes * 2 * hp.nchunk * row);
+  hp.yx = (double *)dalloc(md, sizeof(double) * nmodes * 2 * hp.nchunk * row);
+  hp.rowsum = (double *)dalloc(md, sizeof(double) * nmodes * hp.nyp);
+  QG_CUDA(cudaMemset(hp.rowsum, 0, sizeof(double) * nmodes * hp.nyp));
+  QG_CUDA(cudaFuncSetAttribute(k_xform, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.smem_bytes));
+  // diagonal b(i) = bd2(i) - rdm2(m), src/q-gcm.F:929-973 and src/ocisubs.F:148-150
+  const double PI = 3.14159265358979324, TWOPI = 6.28318530717958648;
+  std::vector<double> bd2(hp.n, 0.0), b((size_t)nmodes * hp.n);
+  const double a = hp.a, dxm2 = g.dxm2;
+  const int nxt = hp.n;
+  if (kind == 1) {
+    for (int i = 2; i <= nxt / 2; ++i) {
+      int i1 = 2 * i - 1;
+      bd2[i1 - 2] = -2.0 * a + 2.0 * dxm2 * (cos((i - 1) * TWOPI / nxt) - 1.0);
+      bd2[i1 - 1] = bd2[i1 - 2];
+    }
+    bd2[0] = -2.0 * a;
+    bd2[nxt - 1] = -2.0 * a - 4.0 * dxm2;
+  } else {
+    for (int i = 2; i <= nxt; ++i) bd2[i - 2] = -2.0 * a + 2.0 * dxm2 * (cos((i - 1) * PI / nxt) - 1.0);
+    bd2[nxt - 1] = 0.0;
+  }
+  for (int mo = 0; mo < nmodes; ++mo)
+    for (int i = 0; i < nxt; ++i) b[(size_t)mo * nxt + i] = bd2[i] - rdm2[mo];
+  helm_set_diag(md, hp, b.data());
+}
+
+static TriArgs tri_args(HelmPlan &hp, double *wrk, size_t lsz, int nmodes) {
+  TriArgs t;
+  t.ld = hp.ld; t.nyp = hp.nyp; t.nk = hp.nk; t.koff = hp.koff; t.nchunk = hp.nchunk;
+  t.lastlen = hp.lastlen; t.nmodes = nmodes; t.lsz = lsz; t.a = hp.a; t.wrk = wrk;
+  t.bcoef = hp.bcoef; t.binv = hp.binv; t.vl = hp.vl; t.vll = hp.vll; t.pt = hp.pt; t.fg = hp.fg; t.yx = hp.yx;
+  return t;
+}
+
+// b_host: [nmodes][n] in the reference's ordering: box b(i-1) multiplies wavenumber column
+// i (src/ocisubs.F:472), periodic b(i) column i (src/ocisubs.F:577)
+void helm_set_diag(qgcm_model *md, HelmPlan &hp, const double *b_host) {
+  std::vector<double> tmp((size_t)hp.nmodes * hp.ld, 1.0);
+  for (int mo = 0; mo < hp.nmodes; ++mo)
+    for (int s = 0; s < hp.nk; ++s) tmp[(size_t)mo * hp.ld + hp.koff + s] = b_host[(size_t)mo * hp.n + s];
+  QG_CUDA(cudaMemcpyAsync(hp.bcoef, tmp.data(), sizeof(double) * tmp.size(), cudaMemcpyHostToDevice, md->stream));
+  QG_CUDA(cudaStreamSynchronize(md->stream));
+  TriArgs t = tri_args(hp, nullptr, 0, hp.nmodes);
+  dim3 grid((hp.nk + 127) / 128, hp.nmodes);
+  k_tri_tables<<<grid, 128, 0, md->stream>>>(t);
+  md->launches++;
+  QG_CUDA(cudaGetLastError());
+}
+
+// in place on wrk[nmodes][nyp][ld]: rhs -> solution with zero boundary values
+void helm_solve(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
+  const size_t lsz = (size_t)hp.ld * hp.nyp;
+  XfArgs x;
+  x.f.n = hp.n; x.f.m = hp.m; x.f.nrad = hp.nrad;
+  for (int i = 0; i < 16; ++i) x.f.radix[i] = hp.radix[i];
+  x.f.wm = hp.wm; x.f.wn = hp.wn; x.f.sintw = hp.sintw;
+  x.kind = hp.kind; x.inverse = 0; x.ld = hp.ld; x.nyp = hp.nyp; x.nxp = hp.nxp; x.lsz = lsz;
+  x.nchunk = hp.nchunk; x.lastlen = hp.lastlen; x.ftnorm = hp.ftnorm; x.wrk = wrk;
+  x.vl = hp.vl; x.vll = hp.vll; x.yx = hp.yx; x.rowsum = hp.rowsum;
+  dim3 gx(hp.nrows, nmodes);
+  k_xform<<<gx, 256, hp.smem_bytes, md->stream>>>(x);
+  TriArgs t = tri_args(hp, wrk, lsz, nmodes);
+  dim3 gl((hp.nk + 127) / 128, hp.nchunk, nmodes);
+  k_tri_local<<<gl, 128, 0, md->stream>>>(t);
+  md->launches += 2;
+  if (hp.nchunk > 1) {
+    dim3 gr((hp.nk + 127) / 128, nmodes);
+    k_tri_reduced<<<gr, 128, 0, md->stream>>>(t);
+    md->launches++;
+  }
+  x.inverse = 1;
+  k_xform<<<gx, 256, hp.smem_bytes, md->stream>>>(x);
+  k_zero_rows<<<(hp.nxp + 255) / 256, 256, 0, md->stream>>>(wrk, lsz, hp.ld, hp.nyp, hp.nxp, nmodes);
+  md->launches += 2;
+  QG_CUDA(cudaGetLastError());
+}
+
+}  // namespace qg

@@ -1,0 +1,462 @@
+// PV inversion around the Helmholtz solver: ocinvq (src/ocisubs.F:64-407) and atinvq
+// (src/atisubs.F:60-293): layer->mode RHS, the constraint algebra on the device-resident
+// scalars, homogeneous-solution add and mode->layer projection; plus the init-time
+// producers that use the same solver: homsol and constr (src/conhoms.F:44-818).
+#include "qgcm_internal.h"
+
+namespace qg {
+
+struct InvArgs {
+  Grid g;
+  int atmos, nl;
+  double f0, beta;
+  double ctl2m[NLMAX * NLMAX], ctm2l[NLMAX * NLMAX];
+  const double *q, *ddyn, *yrel;
+  double *wrk;
+  const double *hom;        // box: ochom [nl-1][nyp][ld]
+  const double *pch1, *pch2, *pbh;   // channel: [nl-1][nyp], [nyp]
+  double *pnew;             // written over the lagged-p buffer
+  const double *coef;       // device: box hclco[nl-1]; channel c3, c1[nl-1], c2[nl-1]
+};
+
+// wrk_m = f0 * sum_k ctl2m(k,m) (q_k - beta*y - [k==kbot] ddyn), rows 2..nyp-1, all i
+// (src/ocisubs.F:117-139, src/atisubs.F:106-126)
+__global__ void __launch_bounds__(256) k_l2m(InvArgs a) {
+  const Grid &g = a.g;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y + 1;   // 0-based interior row
+  if (i >= g.nxp) return;
+  const double betay = a.beta * a.yrel[j];
+  const size_t idx = (size_t)j * g.ld + i;
+  const int nl = a.nl, kbot = a.atmos ? 0 : nl - 1;
+  double ql[NLMAX];
+  for (int k = 0; k < nl; ++k) ql[k] = a.q[k * g.lsz + idx] - betay;
+  ql[kbot] = ql[kbot] - a.ddyn[idx];
+  for (int m = 0; m < nl; ++m) {
+    double qm = 0.0;
+    for (int k = 0; k < nl; ++k) qm = qm + a.ctl2m[k + nl * m] * ql[k];
+    a.wrk[m * g.lsz + idx] = a.f0 * qm;
+  }
+}
+
+// p_k = sum_m ctm2l(m,k) (wrk_m + homogeneous_m) at every point
+// (src/ocisubs.F:300-327 channel, :377-401 box; src/atisubs.F:264-291)
+__global__ void __launch_bounds__(256) k_m2l(InvArgs a) {
+  const Grid &g = a.g;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= g.nxp) return;
+  const size_t idx = (size_t)j * g.ld + i;
+  const int nl = a.nl;
+  double pm[NLMAX];
+  if (g.cyclic) {
+    pm[0] = a.wrk[idx] + a.coef[0] * a.pbh[j];
+    for (int m = 1; m < nl; ++m) {
+      const double homcor = a.coef[m] * a.pch1[(m - 1) * g.nyp + j] + a.coef[nl - 1 + m] * a.pch2[(m - 1) * g.nyp + j];
+      pm[m] = a.wrk[m * g.lsz + idx] + homcor;
+    }
+  } else {
+    pm[0] = a.wrk[idx];
+    for (int m = 1; m < nl; ++m) pm[m] = a.wrk[m * g.lsz + idx] + a.coef[m - 1] * a.hom[(m - 1) * g.lsz + idx];
+  }
+  for (int k = 0; k < nl; ++k) {
+    double pl = 0.0;
+    for (int m = 0; m < nl; ++m) pl = pl + a.ctm2l[m + nl * k] * pm[m];
+    a.pnew[k * g.lsz + idx] = pl;
+  }
+}
+
+// dense solve with partial pivoting plus one refinement sweep: DGETRS + DGERFS at
+// src/ocisubs.F:359-370 (LAPACK is not vendored by the reference; published algorithm)
+__device__ void lu_solve_refine(const double *a, int n, const double *rhs, double *x) {
+  double lu[NLMAX * NLMAX];
+  int piv[NLMAX];
+  for (int i = 0; i < n * n; ++i) lu[i] = a[i];
+  for (int kk = 0; kk < n; ++kk) {
+    int p = kk;
+    for (int i = kk + 1; i < n; ++i)
+      if (fabs(lu[i + n * kk]) > fabs(lu[p + n * kk])) p = i;
+    piv[kk] = p;
+    if (p != kk)
+      for (int j = 0; j < n; ++j) { double t = lu[kk + n * j]; lu[kk + n * j] = lu[p + n * j]; lu[p + n * j] = t; }
+    for (int i = kk + 1; i < n; ++i) {
+      lu[i + n * kk] /= lu[kk + n * kk];
+      for (int j = kk + 1; j < n; ++j) lu[i + n * j] -= lu[i + n * kk] * lu[kk + n * j];
+    }
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    double b[NLMAX];
+    if (pass == 0) {
+      for (int i = 0; i < n; ++i) b[i] = rhs[i];
+    } else {
+      for (int i = 0; i < n; ++i) {
+        double acc = rhs[i];
+        for (int j = 0; j < n; ++j) acc -= a[i + n * j] * x[j];
+        b[i] = acc;
+      }
+    }
+    for (int kk = 0; kk < n; ++kk) { double t = b[kk]; b[kk] = b[piv[kk]]; b[piv[kk]] = t; }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < i; ++j) b[i] -= lu[i + n * j] * b[j];
+    for (int i = n - 1; i >= 0; --i) {
+      for (int j = i + 1; j < n; ++j) b[i] -= lu[i + n * j] * b[j];
+      b[i] /= lu[i + n * i];
+    }
+    for (int i = 0; i < n; ++i) x[i] = pass == 0 ? b[i] : x[i] + b[i];
+  }
+}
+
+struct ScalArgs {
+  int atmos, cyclic, nl, nyp;
+  double dx, f0, tdt, xl, yl;
+  double h[NLMAX], gp[NLMAX], ctl2m[NLMAX * NLMAX], ctm2l[NLMAX * NLMAX];
+  const double *rowsum;   // [nl][nyp]
+  qgcm_scalars *sc;
+  double *coef;
+};
+
+// Single-thread constraint algebra on device-resident scalars, so the step never
+// synchronises with the host (src/ocisubs.F:146-162, :174-294, :333-370;
+// src/atisubs.F:137-258).  xinhom(m) = dx*dy * sum of the xintp row sums.
+__global__ void k_inv_scalars(ScalArgs a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  qgcm_scalars *s = a.sc;
+  const int nl = a.nl, nyp = a.nyp;
+  const double ecrit = 1.0e-13;
+  double xinhom[NLMAX], ayis[NLMAX], ayin[NLMAX];
+  for (int m = 0; m < nl; ++m) {
+    double sump = 0.0;
+    for (int j = 1; j < nyp - 1; ++j) sump = sump + a.rowsum[m * nyp + j];
+    xinhom[m] = sump * a.dx * a.dx;   // boundary rows are exactly zero
+    ayis[m] = a.rowsum[m * nyp + 1];              // dx/dy = 1
+    ayin[m] = -a.rowsum[m * nyp + nyp - 2];
+    if (a.atmos) s->xinhom_at[m] = xinhom[m]; else s->xinhom_oc[m] = xinhom[m];
+  }
+  if (!a.cyclic) {
+    // finite box: mass constraints (src/ocisubs.F:333-370)
+    double aient[NLMAX], rhs[NLMAX], hclco[NLMAX];
+    aient[0] = s->xon[0];
+    for (int k = 1; k < nl - 1; ++k) aient[k] = 0.0;
+    for (int k = 0; k < nl - 1; ++k) {
+      const double aitmp = s->dpioc[k];
+      s->dpioc[k] = s->dpiocp[k] - a.tdt * a.gp[k] * aient[k];
+      s->dpiocp[k] = aitmp;
+      double rhsum = 0.0;
+      for (int m = 0; m < nl; ++m) rhsum = rhsum + s->cdiffo[m + nl * k] * xinhom[m];
+      rhs[k] = s->dpioc[k] - rhsum;
+    }
+    lu_solve_refine(s->cdhoc, nl - 1, rhs, hclco);
+    for (int k = 0; k < nl - 1; ++k) a.coef[k] = hclco[k];
+    return;
+  }
+  // periodic channel: momentum constraints
+  double rhss[NLMAX], rhsn[NLMAX], snew[NLMAX], nnew[NLMAX], clhss[NLMAX], clhsn[NLMAX];
+  double c1[NLMAX], c2[NLMAX], c3, aipmod[NLMAX], aiplay[NLMAX];
+  const double entfac = 0.5 * a.dx * a.f0 * a.f0;
+  const double *h = a.h;
+  if (!a.atmos) {
+    rhss[0] = (entfac / h[0]) * s->enisoc[0] + (a.f0 / h[0]) * s->txisoc + s->ajisoc[0] - s->ap3soc[0] + s->ap5soc[0];
+    rhsn[0] = (entfac / h[0]) * s->eninoc[0] - (a.f0 / h[0]) * s->txinoc + s->ajinoc[0] + s->ap3noc[0] - s->ap5noc[0];
+    for (int k = 1; k < nl - 1; ++k) {
+      rhss[k] = (entfac / h[k]) * (s->enisoc[k] - s->enisoc[k - 1]) + s->ajisoc[k] - s->ap3soc[k] + s->ap5soc[k];
+      rhsn[k] = (entfac / h[k]) * (s->eninoc[k] - s->eninoc[k - 1]) + s->ajinoc[k] + s->ap3noc[k] - s->ap5noc[k];
+    }
+    rhss[nl - 1] = -(entfac / h[nl - 1]) * s->enisoc[nl - 2] + s->ajisoc[nl - 1] - s->ap3soc[nl - 1] + s->ap5soc[nl - 1] +
+                   (a.f0 / h[nl - 1]) * s->bdrins;
+    rhsn[nl - 1] = -(entfac / h[nl - 1]) * s->eninoc[nl - 2] + s->ajinoc[nl - 1] + s->ap3noc[nl - 1] - s->ap5noc[nl - 1] -
+                   (a.f0 / h[nl - 1]) * s->bdrinn;
+  } else {
+    rhss[0] = -(entfac / h[0]) * s->enisat[0] - (a.f0 / h[0]) * s->txisat + s->ajisat[0] + s->ap5sat[0];
+    rhsn[0] = -(entfac / h[0]) * s->eninat[0] + (a.f0 / h[0]) * s->txinat + s->ajinat[0] - s->ap5nat[0];
+    for (int k = 1; k < nl - 1; ++k) {
+      rhss[k] = -(entfac / h[k]) * (s->enisat[k] - s->enisat[k - 1]) + s->ajisat[k] + s->ap5sat[k];
+      rhsn[k] = -(entfac / h[k]) * (s->eninat[k] - s->eninat[k - 1]) + s->ajinat[k] - s->ap5nat[k];
+    }
+    rhss[nl - 1] = (entfac / h[nl - 1]) * s->enisat[nl - 2] + s->ajisat[nl - 1] + s->ap5sat[nl - 1];
+    rhsn[nl - 1] = (entfac / h[nl - 1]) * s->eninat[nl - 2] + s->ajinat[nl - 1] - s->ap5nat[nl - 1];
+  }
+  double *cs = a.atmos ? s->atmcs : s->ocncs, *cn = a.atmos ? s->atmcn : s->ocncn;
+  double *csp = a.atmos ? s->atmcsp : s->ocncsp, *cnp = a.atmos ? s->atmcnp : s->ocncnp;
+  for (int k = 0; k < nl; ++k) {
+    snew[k] = csp[k] + a.tdt * rhss[k];
+    nnew[k] = cnp[k] + a.tdt * rhsn[k];
+    csp[k] = cs[k];
+    cnp[k] = cn[k];
+    cs[k] = snew[k];
+    cn[k] = nnew[k];
+  }
+  for (int m = 0; m < nl; ++m) {
+    clhss[m] = 0.0;
+    clhsn[m] = 0.0;
+    for (int k = 0; k < nl; ++k) {
+      clhss[m] = clhss[m] + a.ctl2m[k + nl * m] * snew[k];
+      clhsn[m] = clhsn[m] + a.ctl2m[k + nl * m] * nnew[k];
+    }
+    clhss[m] = clhss[m] + ayis[m];
+    clhsn[m] = clhsn[m] - ayin[m];
+  }
+  const double *hc1s = a.atmos ? s->hc1sat : s->hc1soc, *hc2s = a.atmos ? s->hc2sat : s->hc2soc;
+  const double *hc1n = a.atmos ? s->hc1nat : s->hc1noc, *hc2n = a.atmos ? s->hc2nat : s->hc2noc;
+  const double *aipch = a.atmos ? s->aipcha : s->aipcho;
+  const double hbsi = a.atmos ? s->hbsiat : s->hbsioc, aipbh = a.atmos ? s->aipbha : s->aipbho;
+  c3 = clhss[0] * hbsi;
+  for (int m = 0; m < nl - 1; ++m) {
+    c1[m] = hc2n[m] * clhss[m + 1] - hc2s[m] * clhsn[m + 1];
+    c2[m] = hc1s[m] * clhsn[m + 1] - hc1n[m] * clhss[m + 1];
+  }
+  aipmod[0] = xinhom[0] + c3 * aipbh;
+  for (int m = 1; m < nl; ++m) aipmod[m] = xinhom[m] + (c1[m - 1] + c2[m - 1]) * aipch[m - 1];
+  for (int k = 0; k < nl; ++k) {
+    double pl = 0.0;
+    for (int m = 0; m < nl; ++m) pl = pl + a.ctm2l[m + nl * k] * aipmod[m];
+    aiplay[k] = pl;
+  }
+  double *dpi = a.atmos ? s->dpiat : s->dpioc, *dpip = a.atmos ? s->dpiatp : s->dpiocp;
+  const double *xn = a.atmos ? s->xan : s->xon;
+  double *erma = a.atmos ? s->ermasa : s->ermaso, *emfr = a.atmos ? s->emfrat : s->emfroc;
+  for (int k = 0; k < nl - 1; ++k) {
+    // sign conventions: ocean dpioc = p(k+1)-p(k) (ocisubs.F:272), atmosphere p(k)-p(k+1) (atisubs.F:237)
+    const double est1 = a.atmos ? aiplay[k] - aiplay[k + 1] : aiplay[k + 1] - aiplay[k];
+    const double est2 = dpip[k] - a.tdt * a.gp[k] * xn[k];
+    const double edif = est1 - est2;
+    const double esum = fabs(est1) + fabs(est2);
+    erma[k] = edif;
+    emfr[k] = (esum > (ecrit * a.xl * a.yl * a.tdt * a.gp[k])) ? 2.0 * edif / esum : 0.0;
+    dpip[k] = dpi[k];
+    dpi[k] = est1;
+  }
+  a.coef[0] = c3;
+  for (int m = 1; m < nl; ++m) {
+    a.coef[m] = c1[m - 1];
+    a.coef[nl - 1 + m] = c2[m - 1];
+  }
+}
+
+static void fill_inv(qgcm_model *m, bool atmos, InvArgs &a) {
+  const Grid &g = atmos ? m->ga : m->go;
+  const LayerConsts &lc = atmos ? m->la : m->lo;
+  a.g = g;
+  a.atmos = atmos;
+  a.nl = g.nl;
+  a.f0 = m->fnot;
+  a.beta = m->beta;
+  for (int i = 0; i < NLMAX * NLMAX; ++i) { a.ctl2m[i] = lc.ctl2m[i]; a.ctm2l[i] = lc.ctm2l[i]; }
+  a.q = m->F(atmos ? "qa" : "qo");
+  a.ddyn = m->F(atmos ? "ddynat" : "ddynoc");
+  a.yrel = atmos ? m->yparel : m->yporel;
+  a.wrk = atmos ? m->wrk_a : m->wrk_o;
+  a.hom = (!atmos && !g.cyclic) ? m->F("ochom") : nullptr;
+  a.pch1 = g.cyclic ? m->F(atmos ? "pch1at" : "pch1oc") : nullptr;
+  a.pch2 = g.cyclic ? m->F(atmos ? "pch2at" : "pch2oc") : nullptr;
+  a.pbh = g.cyclic ? m->F(atmos ? "pbhat" : "pbhoc") : nullptr;
+  a.pnew = m->F(atmos ? "pam" : "pom");
+  a.coef = m->d_coef + (atmos ? 64 : 0);
+}
+
+static void invert(qgcm_model *m, bool atmos) {
+  InvArgs a;
+  fill_inv(m, atmos, a);
+  const Grid &g = a.g;
+  HelmPlan &hp = atmos ? m->hpa : m->hpo;
+  dim3 gi((g.nxp + 255) / 256, g.nyp - 2);
+  k_l2m<<<gi, 256, 0, m->stream>>>(a);
+  m->launches++;
+  helm_solve(m, hp, a.wrk, g.nl);
+  ScalArgs s;
+  const LayerConsts &lc = atmos ? m->la : m->lo;
+  s.atmos = atmos; s.cyclic = g.cyclic; s.nl = g.nl; s.nyp = g.nyp;
+  s.dx = g.dx; s.f0 = m->fnot; s.tdt = g.tdt; s.xl = g.xl; s.yl = g.yl;
+  for (int k = 0; k < NLMAX; ++k) { s.h[k] = lc.h[k]; s.gp[k] = lc.gp[k]; }
+  for (int i = 0; i < NLMAX * NLMAX; ++i) { s.ctl2m[i] = lc.ctl2m[i]; s.ctm2l[i] = lc.ctm2l[i]; }
+  s.rowsum = hp.rowsum;
+  s.sc = m->d_scal;
+  s.coef = (double *)a.coef;
+  k_inv_scalars<<<1, 32, 0, m->stream>>>(s);
+  dim3 gm((g.nxp + 255) / 256, g.nyp);
+  k_m2l<<<gm, 256, 0, m->stream>>>(a);
+  m->launches += 2;
+  QG_CUDA(cudaGetLastError());
+  // pom <- po, po <- new: pointer rotation (src/ocisubs.F:392, src/atisubs.F:282)
+  m->swapf(atmos ? "pa" : "po", atmos ? "pam" : "pom");
+}
+
+void launch_ocinvq(qgcm_model *m) { invert(m, false); }
+void launch_atinvq(qgcm_model *m) { invert(m, true); }
+
+// ------------------------------------------------------------------------------------
+// homsol (src/conhoms.F:318-818) through the device solver
+// ------------------------------------------------------------------------------------
+__global__ void k_fill_rows(double *w, int ld, int nyp, int nxp, const double *rowval, double cst, int use_row) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= nxp) return;
+  w[(size_t)j * ld + i] = use_row ? rowval[j] : cst;
+}
+// out = base + rdm2 * sol, and record xintp row sums of `out`
+__global__ void __launch_bounds__(256) k_hom_finish(double *out, const double *sol, int ld, int nyp, int nxp,
+                                                    const double *rowval, double cst, int use_row, double rdm2,
+                                                    double *rowsum) {
+  __shared__ double red[32];
+  const int j = blockIdx.x;
+  double part = 0.0;
+  for (int i = threadIdx.x; i < nxp; i += blockDim.x) {
+    const double v = (use_row ? rowval[j] : cst) + rdm2 * sol[(size_t)j * ld + i];
+    out[(size_t)j * ld + i] = v;
+    part += (i == 0 || i == nxp - 1) ? 0.5 * v : v;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+  if (lane == 0) red[w] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+    rowsum[j] = t;
+  }
+}
+
+static double xintp_from_rowsums(const std::vector<double> &rs) {
+  const int nyp = (int)rs.size();
+  double sump = 0.0;
+  for (int j = 1; j < nyp - 1; ++j) sump += rs[j];
+  return sump + 0.5 * (rs[0] + rs[nyp - 1]);
+}
+
+static void homsol_channel(qgcm_model *m, bool atmos) {
+  const Grid &g = atmos ? m->ga : m->go;
+  const LayerConsts &lc = atmos ? m->la : m->lo;
+  HelmPlan &hp = atmos ? m->hpa : m->hpo;
+  const std::vector<double> &yp = atmos ? m->h_ypa : m->h_ypo;
+  const int nyp = g.nyp, nl = g.nl;
+  qgcm_scalars s;
+  QG_CUDA(cudaMemcpyAsync(&s, m->d_scal, sizeof(s), cudaMemcpyDeviceToHost, m->stream));
+  QG_CUDA(cudaStreamSynchronize(m->stream));
+  std::vector<double> pbh(nyp), l1(nyp), l2(nyp), rs(nyp), col(nyp);
+  for (int j = 1; j <= nyp; ++j) pbh[j - 1] = (double)(nyp - j) / (double)(nyp - 1);
+  double *d_pbh = m->F(atmos ? "pbhat" : "pbhoc");
+  QG_CUDA(cudaMemcpy(d_pbh, pbh.data(), sizeof(double) * nyp, cudaMemcpyHostToDevice));
+  (atmos ? s.hbsiat : s.hbsioc) = g.yl / g.xl;
+  (atmos ? s.aipbha : s.aipbho) = 0.5 * g.xl * g.yl;
+  double *wrk = atmos ? m->wrk_a : m->wrk_o;   // modes 0,1 of the work array as the two RHS
+  double *d_row = m->d_red;                     // 2*nyp + nyp doubles of scratch
+  double *d_p1 = m->F(atmos ? "pch1at" : "pch1oc"), *d_p2 = m->F(atmos ? "pch2at" : "pch2oc");
+  std::vector<double> p1(nyp), p2(nyp);
+  for (int mo = 1; mo <= nl - 1; ++mo) {
+    const double rdm2 = lc.rdm2[mo];
+    for (int j = 0; j < nyp; ++j) {
+      l1[j] = (yp[nyp - 1] - yp[j]) / g.yl;
+      l2[j] = (yp[j] - yp[0]) / g.yl;
+    }
+    // both right-hand sides solved as a batch of two "modes" with mode mo's operator:
+    // build a temporary diagonal table with the same coefficients in slots 0 and 1
+    std::vector<double> b((size_t)nl * hp.n);
+    {
+      const double PI2 = 6.28318530717958648;
+      std::vector<double> bd2(hp.n);
+      const double a = hp.a;
+      for (int i = 2; i <= hp.n / 2; ++i) {
+        int i1 = 2 * i - 1;
+        bd2[i1 - 2] = -2.0 * a + 2.0 * g.dxm2 * (cos((i - 1) * PI2 / hp.n) - 1.0);
+        bd2[i1 - 1] = bd2[i1 - 2];
+      }
+      bd2[0] = -2.0 * a;
+      bd2[hp.n - 1] = -2.0 * a - 4.0 * g.dxm2;
+      for (int q = 0; q < nl; ++q)
+        for (int i = 0; i < hp.n; ++i) b[(size_t)q * hp.n + i] = bd2[i] - rdm2;
+    }
+    helm_set_diag(m, hp, b.data());
+    QG_CUDA(cudaMemcpy(d_row, l1.data(), sizeof(double) * nyp, cudaMemcpyHostToDevice));
+    QG_CUDA(cudaMemcpy(d_row + nyp, l2.data(), sizeof(double) * nyp, cudaMemcpyHostToDevice));
+    dim3 gf((g.nxp + 255) / 256, nyp);
+    k_fill_rows<<<gf, 256, 0, m->stream>>>(wrk, g.ld, nyp, g.nxp, d_row, 0.0, 1);
+    k_fill_rows<<<gf, 256, 0, m->stream>>>(wrk + g.lsz, g.ld, nyp, g.nxp, d_row + nyp, 0.0, 1);
+    helm_solve(m, hp, wrk, 2);
+    double aip[2];
+    for (int q = 0; q < 2; ++q) {
+      k_hom_finish<<<nyp, 256, 0, m->stream>>>(wrk + q * g.lsz, wrk + q * g.lsz, g.ld, nyp, g.nxp, d_row + q * nyp, 0.0, 1,
+                                               rdm2, d_row + 2 * nyp);
+      m->launches += 2;
+      QG_CUDA(cudaMemcpyAsync(rs.data(), d_row + 2 * nyp, sizeof(double) * nyp, cudaMemcpyDeviceToHost, m->stream));
+      // column 1 of the solution is the 1-D profile (src/conhoms.F:478-479)
+      QG_CUDA(cudaMemcpy2DAsync(col.data(), sizeof(double), wrk + q * g.lsz, sizeof(double) * g.ld, sizeof(double), nyp,
+                                cudaMemcpyDeviceToHost, m->stream));
+      QG_CUDA(cudaStreamSynchronize(m->stream));
+      aip[q] = xintp_from_rowsums(rs);
+      (q == 0 ? p1 : p2) = col;
+    }
+    QG_CUDA(cudaMemcpy(d_p1 + (size_t)(mo - 1) * nyp, p1.data(), sizeof(double) * nyp, cudaMemcpyHostToDevice));
+    QG_CUDA(cudaMemcpy(d_p2 + (size_t)(mo - 1) * nyp, p2.data(), sizeof(double) * nyp, cudaMemcpyHostToDevice));
+    const double dx = g.dx, dy = g.dx, xl = g.xl;
+    (atmos ? s.aipcha : s.aipcho)[mo - 1] = 0.5 * (aip[0] + aip[1]) * dx * dy;
+    double pch1ys = (p1[1] - p1[0]) / dy, pch2ys = (p2[1] - p2[0]) / dy;
+    double pch1yn = (p1[nyp - 1] - p1[nyp - 2]) / dy, pch2yn = (p2[nyp - 1] - p2[nyp - 2]) / dy;
+    pch1ys = -pch1ys + 0.5 * dy * rdm2 * p1[0];
+    pch2ys = -pch2ys + 0.5 * dy * rdm2 * p2[0];
+    pch1yn = pch1yn + 0.5 * dy * rdm2 * p1[nyp - 1];
+    pch2yn = pch2yn + 0.5 * dy * rdm2 * p2[nyp - 1];
+    pch1ys *= xl; pch2ys *= xl; pch1yn *= xl; pch2yn *= xl;
+    const double det = pch1ys * pch2yn - pch2ys * pch1yn;
+    (atmos ? s.hc1sat : s.hc1soc)[mo - 1] = pch1ys / det;
+    (atmos ? s.hc2sat : s.hc2soc)[mo - 1] = pch2ys / det;
+    (atmos ? s.hc1nat : s.hc1noc)[mo - 1] = pch1yn / det;
+    (atmos ? s.hc2nat : s.hc2noc)[mo - 1] = pch2yn / det;
+  }
+  // restore the per-mode operators for the time loop
+  {
+    std::vector<double> b((size_t)nl * hp.n), bd2(hp.n);
+    const double PI2 = 6.28318530717958648, a = hp.a;
+    for (int i = 2; i <= hp.n / 2; ++i) {
+      int i1 = 2 * i - 1;
+      bd2[i1 - 2] = -2.0 * a + 2.0 * g.dxm2 * (cos((i - 1) * PI2 / hp.n) - 1.0);
+      bd2[i1 - 1] = bd2[i1 - 2];
+    }
+    bd2[0] = -2.0 * a;
+    bd2[hp.n - 1] = -2.0 * a - 4.0 * g.dxm2;
+    for (int q = 0; q < nl; ++q)
+      for (int i = 0; i < hp.n; ++i) b[(size_t)q * hp.n + i] = bd2[i] - lc.rdm2[q];
+    helm_set_diag(m, hp, b.data());
+  }
+  QG_CUDA(cudaMemcpy(m->d_scal, &s, sizeof(s), cudaMemcpyHostToDevice));
+}
+
+static void homsol_box(qgcm_model *m) {
+  const Grid &g = m->go;
+  const LayerConsts &lc = m->lo;
+  HelmPlan &hp = m->hpo;
+  const int nl = g.nl, nyp = g.nyp;
+  qgcm_scalars s;
+  QG_CUDA(cudaMemcpyAsync(&s, m->d_scal, sizeof(s), cudaMemcpyDeviceToHost, m->stream));
+  QG_CUDA(cudaStreamSynchronize(m->stream));
+  double *ochom = m->F("ochom");
+  std::vector<double> rs(nyp);
+  // ochom(:,:,m) = 1 + rdm2(m+1) * sol0, sol0 solving (del2 - rdm2(m+1)) sol0 = 1.
+  // The per-mode operator table already holds mode m+1 in slot m, so solve all nl slots
+  // with rhs = 1 and keep slots 1..nl-1.
+  dim3 gf((g.nxp + 255) / 256, nyp);
+  for (int q = 0; q < nl; ++q) k_fill_rows<<<gf, 256, 0, m->stream>>>(m->wrk_o + q * g.lsz, g.ld, nyp, g.nxp, nullptr, 1.0, 0);
+  m->launches += nl;
+  helm_solve(m, hp, m->wrk_o, nl);
+  for (int mo = 1; mo <= nl - 1; ++mo) {
+    k_hom_finish<<<nyp, 256, 0, m->stream>>>(ochom + (size_t)(mo - 1) * g.lsz, m->wrk_o + (size_t)mo * g.lsz, g.ld, nyp,
+                                             g.nxp, nullptr, 1.0, 0, lc.rdm2[mo], m->d_red);
+    m->launches++;
+    QG_CUDA(cudaMemcpyAsync(rs.data(), m->d_red, sizeof(double) * nyp, cudaMemcpyDeviceToHost, m->stream));
+    QG_CUDA(cudaStreamSynchronize(m->stream));
+    s.aipohs[mo - 1] = xintp_from_rowsums(rs) * g.dx * g.dx;
+  }
+  for (int k = 1; k <= nl - 1; ++k) {
+    for (int mo = 1; mo <= nl; ++mo)
+      s.cdiffo[(mo - 1) + nl * (k - 1)] = lc.ctm2l[(mo - 1) + nl * k] - lc.ctm2l[(mo - 1) + nl * (k - 1)];
+    for (int mo = 1; mo <= nl - 1; ++mo)
+      s.cdhoc[(k - 1) + (nl - 1) * (mo - 1)] = (lc.ctm2l[mo + nl * k] - lc.ctm2l[mo + nl * (k - 1)]) * s.aipohs[mo - 1];
+  }
+  QG_CUDA(cudaMemcpy(m->d_scal, &s, sizeof(s), cudaMemcpyHostToDevice));
+}
+
+void launch_homsol(qgcm_model *m) {
+  if (m->has_ocean) {
+    if (m->cyclic) homsol_channel(m, false); else homsol_box(m);
+  }
+  if (m->has_atmos) homsol_channel(m, true);
+}
+
+}  // namespace qg

@@ -1,0 +1,351 @@
+// Ocean mixed layer: oml + omladf (src/omlsubs.F:47-763).
+//
+// Pass 1 (k_oml_step): per T-cell tile, stage sstm (halo 2), sst (halo 1) and the p-grid
+//   corner values of po(:,:,1), tauxo, tauyo in shared memory; compute del2(sstm) with
+//   every boundary-condition variant, the C-grid flux-form advection, del2+del4
+//   diffusion, the sst prediction, entrainment and convective adjustment; write the new
+//   sst to a third buffer (sstm is read with a stencil, so it cannot be updated in
+//   place) and xfo, and emit per-block partial sums for xfosum / cfrasm / centsm.
+// Pass 2 (k_oml_entoc): subtract the global mean from xfo and average the four
+//   surrounding T cells onto p points (entoc), with xintp row sums for xon(1).
+// The reference needs ~24 field passes for this; here it is 11.
+#include "qgcm_internal.h"
+
+namespace qg {
+
+constexpr int OX = 64, OY = 8;   // T-cell tile
+
+struct OmlArgs {
+  Grid g;
+  int sb, nb;
+  double tsbdy, tnbdy;
+  double uvgfac, rhf0hm, d2tfac, d4tfac, hdxm1;
+  double hmoinv, dtoinv, entfac, rrcpoc, toc1, tdt;
+  const double *po1, *taux, *tauy, *sst, *sstm, *wekt, *fnet;
+  double *sstnew, *xfo;
+  double *part;      // [3][nblocks] partial sums
+  int nblocks;
+  double *entoc;
+  double *rowsum;    // [nyp] xintp row sums of entoc
+  qgcm_scalars *sc;
+};
+
+__device__ __forceinline__ int wrapt(int i, int nxt, int cyc) {
+  if (!cyc) return i;
+  if (i < 0) i += nxt;
+  if (i >= nxt) i -= nxt;
+  return i;
+}
+
+__global__ void __launch_bounds__(256) k_oml_step(OmlArgs a) {
+  __shared__ double s_tm[OY + 4][OX + 4];   // sstm, halo 2
+  __shared__ double s_t[OY + 2][OX + 2];    // sst, halo 1
+  __shared__ double s_d2[OY + 2][OX + 2];   // del2t, halo 1
+  __shared__ double s_p[OY + 1][OX + 1], s_tx[OY + 1][OX + 1], s_ty[OY + 1][OX + 1];
+  __shared__ double red[3][8];
+  const Grid &g = a.g;
+  const int nxt = g.nxt, nyt = g.nyt, ld = g.ld, cyc = g.cyclic;
+  const int i0 = blockIdx.x * OX, j0 = blockIdx.y * OY;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < (OY + 4) * (OX + 4); e += 256) {
+    const int ly = e / (OX + 4), lx = e - ly * (OX + 4);
+    const int gj = j0 + ly - 2, gi = wrapt(i0 + lx - 2, nxt, cyc);
+    s_tm[ly][lx] = (gj >= 0 && gj < nyt && gi >= 0 && gi < nxt) ? a.sstm[(size_t)gj * ld + gi] : 0.0;
+  }
+  for (int e = tid; e < (OY + 2) * (OX + 2); e += 256) {
+    const int ly = e / (OX + 2), lx = e - ly * (OX + 2);
+    const int gj = j0 + ly - 1, gi = wrapt(i0 + lx - 1, nxt, cyc);
+    s_t[ly][lx] = (gj >= 0 && gj < nyt && gi >= 0 && gi < nxt) ? a.sst[(size_t)gj * ld + gi] : 0.0;
+  }
+  for (int e = tid; e < (OY + 1) * (OX + 1); e += 256) {
+    const int ly = e / (OX + 1), lx = e - ly * (OX + 1);
+    const int gj = j0 + ly, gi = i0 + lx;
+    const bool in = gj < g.nyp && gi < g.nxp;
+    const size_t idx = (size_t)gj * ld + gi;
+    s_p[ly][lx] = in ? a.po1[idx] : 0.0;
+    s_tx[ly][lx] = in ? a.taux[idx] : 0.0;
+    s_ty[ly][lx] = in ? a.tauy[idx] : 0.0;
+  }
+  __syncthreads();
+  // ---- del2t on the halo-1 region (omlsubs.F:291-682)
+  for (int e = tid; e < (OY + 2) * (OX + 2); e += 256) {
+    const int ly = e / (OX + 2), lx = e - ly * (OX + 2);
+    const int gj = j0 + ly - 1;
+    int gi = i0 + lx - 1;
+    double v = 0.0;
+    const bool inx = cyc ? true : (gi >= 0 && gi < nxt);
+    if (gj >= 0 && gj < nyt && inx) {
+      gi = wrapt(gi, nxt, cyc);
+      const int y = ly + 1, x = lx + 1;   // position in s_tm
+      const double c = s_tm[y][x];
+      const bool hasW = cyc || gi > 0, hasE = cyc || gi < nxt - 1;
+      double sum = 0.0, n = 0.0;
+      if (gj == 0) {
+        // order W, E, N, tsbdy (omlsubs.F:411-418, :474-490, :531-547)
+        if (hasW) { sum = s_tm[y][x - 1]; n += 1.0; }
+        if (hasE) { sum = (n > 0.0) ? sum + s_tm[y][x + 1] : s_tm[y][x + 1]; n += 1.0; }
+        sum = sum + s_tm[y + 1][x]; n += 1.0;
+        if (a.sb) { sum = sum + a.tsbdy; n += 1.0; }
+        v = sum - n * c;
+      } else if (gj == nyt - 1) {
+        // order S, W, tnbdy, E (omlsubs.F:443-450, :589-604); the cyclic NE corner adds
+        // tnbdy last (omlsubs.F:647-648)
+        sum = s_tm[y - 1][x]; n = 1.0;
+        if (hasW) { sum = sum + s_tm[y][x - 1]; n += 1.0; }
+        const bool ne_cyc = cyc && gi == nxt - 1;
+        if (a.nb && !ne_cyc) { sum = sum + a.tnbdy; n += 1.0; }
+        if (hasE) { sum = sum + s_tm[y][x + 1]; n += 1.0; }
+        if (a.nb && ne_cyc) v = sum - 4.0 * c + a.tnbdy;
+        else v = sum - n * c;
+      } else {
+        sum = s_tm[y - 1][x]; n = 1.0;
+        if (hasW) { sum = sum + s_tm[y][x - 1]; n += 1.0; }
+        if (hasE) { sum = sum + s_tm[y][x + 1]; n += 1.0; }
+        sum = sum + s_tm[y + 1][x]; n += 1.0;
+        v = sum - n * c;
+      }
+    }
+    s_d2[ly][lx] = v;
+  }
+  __syncthreads();
+  // ---- advection + diffusion + time step (omlsubs.F:297-384, :728-758, :94-127)
+  double pxfo = 0.0, pcfr = 0.0, pcen = 0.0;
+  for (int e = tid; e < OY * OX; e += 256) {
+    const int ly = e / OX, lx = e - ly * OX;
+    const int gj = j0 + ly, gi = i0 + lx;
+    if (gj >= nyt || gi >= nxt) continue;
+    const int y = ly + 1, x = lx + 1;   // in s_t / s_d2
+    const double tc = s_t[y][x];
+    double um = -a.uvgfac * (s_p[ly + 1][lx] - s_p[ly][lx]) + a.rhf0hm * (s_ty[ly + 1][lx] + s_ty[ly][lx]);
+    double up = -a.uvgfac * (s_p[ly + 1][lx + 1] - s_p[ly][lx + 1]) + a.rhf0hm * (s_ty[ly + 1][lx + 1] + s_ty[ly][lx + 1]);
+    double tm = tc + s_t[y][x - 1], tp = tc + s_t[y][x + 1];
+    if (!cyc && gi == 0) { um = 0.0; tm = 0.0; }
+    if (!cyc && gi == nxt - 1) { up = 0.0; tp = 0.0; }
+    const double hxadv = a.hdxm1 * (up * tp - um * tm);
+    const double vs = a.uvgfac * (s_p[ly][lx + 1] - s_p[ly][lx]) - a.rhf0hm * (s_tx[ly][lx + 1] + s_tx[ly][lx]);
+    const double vn = a.uvgfac * (s_p[ly + 1][lx + 1] - s_p[ly + 1][lx]) - a.rhf0hm * (s_tx[ly + 1][lx + 1] + s_tx[ly + 1][lx]);
+    double hyadv;
+    if (gj == 0) {
+      const double tpn = tc + s_t[y + 1][x];
+      if (a.sb) {
+        const double vm = -a.rhf0hm * (s_tx[ly][lx + 1] + s_tx[ly][lx]);
+        const double tms = tc + a.tsbdy;
+        hyadv = a.hdxm1 * (vn * tpn - vm * tms);
+      } else {
+        hyadv = a.hdxm1 * (vn * tpn);
+      }
+    } else if (gj == nyt - 1) {
+      const double tms = s_t[y - 1][x] + tc;
+      if (a.nb) {
+        const double vp = -a.rhf0hm * (s_tx[ly + 1][lx + 1] + s_tx[ly + 1][lx]);
+        const double tpn = tc + a.tnbdy;
+        hyadv = a.hdxm1 * (vp * tpn - vs * tms);
+      } else {
+        hyadv = a.hdxm1 * (-vs * tms);
+      }
+    } else {
+      hyadv = a.hdxm1 * (vn * (s_t[y + 1][x] + tc) - vs * (tc + s_t[y - 1][x]));
+    }
+    double rhs = -(hxadv + hyadv);
+    // dummy columns of del2t: no diffusive flux through solid W/E walls
+    const double dc = s_d2[y][x];
+    const double dw = (!cyc && gi == 0) ? dc : s_d2[y][x - 1];
+    const double de = (!cyc && gi == nxt - 1) ? dc : s_d2[y][x + 1];
+    double d4;
+    if (gj == 0) d4 = dw + de + s_d2[y + 1][x] - 3.0 * dc;
+    else if (gj == nyt - 1) d4 = s_d2[y - 1][x] + dw + de - 3.0 * dc;
+    else d4 = s_d2[y - 1][x] + dw + de + s_d2[y + 1][x] - 4.0 * dc;
+    rhs = rhs + a.d2tfac * dc - a.d4tfac * d4;
+    // predict, entrain, convect (omlsubs.F:101-125)
+    const size_t idx = (size_t)gj * ld + gi;
+    const double tmc = s_tm[ly + 2][lx + 2], wek = a.wekt[idx];
+    const double diabat = 0.5 * wek * (tmc + a.toc1);
+    double sstnew = tmc + a.tdt * (rhs + a.hmoinv * (a.rrcpoc * a.fnet[idx] + diabat));
+    const double xfoent = -(0.5 * a.dtoinv) * wek * (tmc - a.toc1);
+    const double dtonew = a.toc1 - sstnew;
+    const double coneno = a.entfac * fmax(0.0, dtonew);
+    const double xf = xfoent - coneno;
+    sstnew = sstnew + fmax(0.0, dtonew);
+    a.xfo[idx] = xf;
+    a.sstnew[idx] = sstnew;
+    pxfo += xf;
+    pcfr += (-dtonew >= 0.0) ? 0.0 : 1.0;   // 0.5 - sign(0.5, -dtonew)
+    pcen -= coneno;
+  }
+  // block partial sums (fixed order)
+  const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pxfo += __shfl_down_sync(0xffffffffu, pxfo, o);
+    pcfr += __shfl_down_sync(0xffffffffu, pcfr, o);
+    pcen += __shfl_down_sync(0xffffffffu, pcen, o);
+  }
+  if (lane == 0) { red[0][w] = pxfo; red[1][w] = pcfr; red[2][w] = pcen; }
+  __syncthreads();
+  if (tid < 3) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[tid][i];
+    a.part[(size_t)tid * a.nblocks + blockIdx.y * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// sum the block partials in a fixed order; one block of 256 threads
+__global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy) {
+  __shared__ double red[3][8];
+  double s[3] = {0.0, 0.0, 0.0};
+  for (int q = 0; q < 3; ++q)
+    for (int i = threadIdx.x; i < a.nblocks; i += 256) s[q] += a.part[(size_t)q * a.nblocks + i];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int q = 0; q < 3; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_down_sync(0xffffffffu, s[q], o);
+    if (lane == 0) red[q][w] = s[q];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[3] = {0.0, 0.0, 0.0};
+    for (int q = 0; q < 3; ++q)
+      for (int i = 0; i < 8; ++i) t[q] += red[q][i];
+    a.part[0] = t[0];                       // xfosum, read by k_oml_entoc
+    a.sc->cfraoc = t[1] * a.g.norm;         // omlsubs.F:211
+    a.sc->centoc = t[2] * dxdy;             // omlsubs.F:212
+  }
+}
+
+// entoc = 4-point average of (xfo - mean) with the edge/corner rules (omlsubs.F:151-205);
+// one block per p row; also the xintp row sum of that row (intsubs.f:103-131)
+__global__ void __launch_bounds__(256) k_oml_entoc(OmlArgs a) {
+  __shared__ double red[8];
+  const Grid &g = a.g;
+  const int j = blockIdx.x;   // 0-based p row
+  const int nxp = g.nxp, nyp = g.nyp, nxt = g.nxt, nyt = g.nyt, ld = g.ld, cyc = g.cyclic;
+  const double mean = a.part[0] * g.norm;   // xfosum*ocnorm
+  double part = 0.0;
+  for (int i = threadIdx.x; i < nxp; i += 256) {
+    // T cells around p point (i,j): (i-1,j-1), (i,j-1), (i-1,j), (i,j) in 0-based T indices
+    const int jm = j - 1, jc = j;
+    int im = i - 1, ic = i;
+    double v;
+    const bool rowS = (j == 0), rowN = (j == nyp - 1);
+    const bool colW = (i == 0), colE = (i == nxp - 1);
+    if (cyc) {
+      if (colW || colE) { im = nxt - 1; ic = 0; }
+    }
+#define X(ii, jj) (a.xfo[(size_t)(jj) * ld + (ii)] - mean)
+    if (!rowS && !rowN) {
+      if (!cyc && colW) v = 0.5 * (X(0, jm) + X(0, jc));
+      else if (!cyc && colE) v = 0.5 * (X(nxt - 1, jm) + X(nxt - 1, jc));
+      else v = 0.25 * (X(im, jm) + X(ic, jm) + X(im, jc) + X(ic, jc));
+    } else {
+      const int jt = rowS ? 0 : nyt - 1;
+      if (!cyc && colW) v = X(0, jt);
+      else if (!cyc && colE) v = X(nxt - 1, jt);
+      else v = 0.5 * (X(im, jt) + X(ic, jt));
+    }
+#undef X
+    a.entoc[(size_t)j * ld + i] = v;
+    part += (colW || colE) ? 0.5 * v : v;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+  if (lane == 0) red[w] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    a.rowsum[j] = t;
+  }
+}
+
+// xon(1) = dx*dy*xintp(entoc); channel: enisoc(1), eninoc(1) (omlsubs.F:214-233)
+__global__ void k_oml_finish(OmlArgs a, double dx) {
+  if (threadIdx.x != 0) return;
+  const int nyp = a.g.nyp;
+  double sump = 0.0;
+  for (int j = 1; j < nyp - 1; ++j) sump += a.rowsum[j];
+  const double x = sump + 0.5 * (a.rowsum[0] + a.rowsum[nyp - 1]);
+  a.sc->xon[0] = x * dx * dx;
+  if (a.g.cyclic) {
+    a.sc->enisoc[0] = dx * a.rowsum[0];
+    a.sc->eninoc[0] = dx * a.rowsum[nyp - 1];
+  }
+}
+
+// boundary-flux monitors of the sb_hflux / nb_hflux options (omlsubs.F:684-726)
+__global__ void __launch_bounds__(256) k_oml_monitors(OmlArgs a) {
+  __shared__ double red[6][8];
+  const Grid &g = a.g;
+  const int nxt = g.nxt, nyt = g.nyt, ld = g.ld;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < nxt; i += 256) {
+    if (a.sb) {
+      const double vm = -a.rhf0hm * (a.taux[i + 1] + a.taux[i]);
+      const double tm = a.sst[i] + a.tsbdy;
+      s[0] += vm; s[1] += vm * tm; s[2] -= (a.sstm[i] - a.tsbdy);
+    }
+    if (a.nb) {
+      const double vp = -a.rhf0hm * (a.taux[(size_t)nyt * ld + i + 1] + a.taux[(size_t)nyt * ld + i]);
+      const double tp = a.sst[(size_t)(nyt - 1) * ld + i] + a.tnbdy;
+      s[3] -= vp; s[4] -= vp * tp; s[5] += (a.tnbdy - a.sstm[(size_t)(nyt - 1) * ld + i]);
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int q = 0; q < 6; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_down_sync(0xffffffffu, s[q], o);
+    if (lane == 0) red[q][w] = s[q];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[6];
+    for (int q = 0; q < 6; ++q) { t[q] = 0.0; for (int i = 0; i < 8; ++i) t[q] += red[q][i]; }
+    const double n = (double)nxt;
+    a.sc->vfmads = t[0] / n; a.sc->ttmads = a.hdxm1 * t[1] / n; a.sc->ttmdfs = a.d2tfac * t[2] / n;
+    a.sc->vfmadn = t[3] / n; a.sc->ttmadn = a.hdxm1 * t[4] / n; a.sc->ttmdfn = a.d2tfac * t[5] / n;
+  }
+}
+
+void launch_oml(qgcm_model *m) {
+  OmlArgs a;
+  const Grid &g = m->go;
+  const qgcm_config &c = m->cfg;
+  a.g = g;
+  a.sb = m->sb_hflux; a.nb = m->nb_hflux;
+  a.tsbdy = c.tsbdy; a.tnbdy = c.tnbdy;
+  a.uvgfac = c.ycexp * g.rdxf0;
+  a.rhf0hm = 0.5 / (m->fnot * c.hmoc);
+  a.d2tfac = c.st2d * g.dxm2;
+  a.d4tfac = c.st4d * g.dxm2 * g.dxm2;
+  a.hdxm1 = g.hdxm1;
+  a.hmoinv = 1.0 / c.hmoc;
+  a.dtoinv = 1.0 / (c.toc[0] - c.toc[1]);
+  a.entfac = c.hmoc * a.dtoinv / g.tdt;
+  a.rrcpoc = m->rrcpoc;
+  a.toc1 = c.toc[0];
+  a.tdt = g.tdt;
+  a.po1 = m->F("po"); a.taux = m->F("tauxo"); a.tauy = m->F("tauyo");
+  a.sst = m->F("sst"); a.sstm = m->F("sstm"); a.wekt = m->F("wekto"); a.fnet = m->F("fnetoc");
+  a.sstnew = m->sstnew; a.xfo = m->xfo;
+  dim3 grid((g.nxt + OX - 1) / OX, (g.nyt + OY - 1) / OY);
+  a.nblocks = grid.x * grid.y;
+  a.part = m->d_red;
+  a.rowsum = m->d_red + 3 * (size_t)a.nblocks;
+  a.entoc = m->F("entoc");
+  a.sc = m->d_scal;
+  if (m->red_elems < 3 * (size_t)a.nblocks + g.nyp) throw std::runtime_error("oml: reduction scratch too small");
+  k_oml_monitors<<<1, 256, 0, m->stream>>>(a);
+  k_oml_step<<<grid, 256, 0, m->stream>>>(a);
+  k_oml_reduce<<<1, 256, 0, m->stream>>>(a, g.dx * g.dx);
+  k_oml_entoc<<<g.nyp, 256, 0, m->stream>>>(a);
+  k_oml_finish<<<1, 32, 0, m->stream>>>(a, g.dx);
+  m->launches += 5;
+  QG_CUDA(cudaGetLastError());
+  // sstm <- sst, sst <- new: three-buffer rotation (omlsubs.F:124-125)
+  double *old_m = m->fields.at("sstm").d;
+  m->fields.at("sstm").d = m->fields.at("sst").d;
+  m->fields.at("sst").d = m->sstnew;
+  m->sstnew = old_m;
+}
+
+}  // namespace qg

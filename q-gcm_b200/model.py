@@ -2,8 +2,8 @@
 
 ``Model`` is the product binding (libqgcm_b200.so, CUDA only).  Its methods carry the
 names of the reference subroutines they replace (src/q-gcm.F:1222-1269) so the parity
-tests read like the reference's main loop.  ``CModel`` is the generic binding the
-tests also point at the oracle's liborc.so (same struct layout, ``orc_`` prefix).
+tests read like the reference's main loop.  ``CModel`` is the generic binding (library + symbol
+prefix); the tests reuse it to drive their CPU checker through the same struct layout.
 """
 import ctypes as C
 import os

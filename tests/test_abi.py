@@ -1,0 +1,64 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/qgcm_b200.h declares, agrees with the ctypes mirror on struct sizes, and fails
+loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+
+def test_header_declares_reference_procedures(qg):
+    names = qg.abi.declared_functions()
+    for proc in ("xforc", "oml", "qgostep", "ocinvq", "ocqbdy", "aml", "qgastep", "atinvq", "atqzbd",
+                 "tlavg_ocean", "tlavg_atmos", "ocean_step", "run", "homsol", "constr", "helmholtz"):
+        assert "qgcm_" + proc in names
+
+
+def test_header_cites_reference_lines():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "qgcm_b200.h")).read()
+    assert len(re.findall(r"src/[\w\-\.]+\.[Ff]:\d+", text)) >= 20
+
+
+def test_library_exports_every_declared_symbol(qg):
+    lib = qg.load_library()
+    missing = [n for n in qg.abi.declared_functions() if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.qgcm_abi_version() == qg.abi.ABI_VERSION
+
+
+def test_struct_layout_is_plain_c(qg):
+    # only int32/double members: no padding surprises between C and ctypes
+    assert C.sizeof(qg.QgcmConfig) % 8 == 0
+    assert C.sizeof(qg.QgcmScalars) % 8 == 0
+    n_int = sum(1 for _, t in qg.QgcmConfig._fields_ if t is C.c_int32 or getattr(t, "_type_", None) is C.c_int32)
+    assert n_int >= 16
+
+
+def test_no_cpu_fallback(qg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    cfg = qg.build_config(qg.named_config("dg_oo").scaled(6, 5))
+    with pytest.raises(RuntimeError) as e:
+        qg.Model(cfg)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_abi_mismatch_is_rejected(qg):
+    cfg = qg.build_config(qg.named_config("dg_oo").scaled(6, 5))
+    cfg.struct_bytes = 12
+    with pytest.raises(RuntimeError):
+        qg.Model(cfg)
+
+
+def test_product_never_imports_oracle():
+    """the package and bench's product path must not reference oracle/"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "q-gcm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"pyorc|liborc|\borc_|oracle/", text), f

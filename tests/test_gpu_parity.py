@@ -1,0 +1,137 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on identical seeded
+inputs.  Tolerance: FP64 relative L2 <= 1e-11 per field (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from util import TOL, rel_l2, small_configs, make_pair, compare, compare_scalars, integral_scale, OCEAN_CHECK
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["box_dg", "box_natl1km", "chan_so"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_init_sequence(qg, pyorc, case):
+    """constr, qcomp+ocqbdy(+merqcy), xforc Ekman tail, homsol (src/q-gcm.F:711-976)"""
+    p = small_configs(qg)[case]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    compare(gpu, cpu, ("qo", "qom", "wekto", "wekpo"), label=case)
+    if p.has("cyclic_ocean"):
+        compare(gpu, cpu, ("pch1oc", "pch2oc", "pbhoc"), label=case)
+        compare_scalars(gpu, cpu, ("dpioc", "dpiocp"), tol=1e-12, floor=integral_scale(cpu, p))
+        compare_scalars(gpu, cpu, ("ocncs", "ocncn", "ocncsp", "ocncnp", "hc1soc", "hc2soc",
+                                   "hc1noc", "hc2noc", "aipcho", "hbsioc", "aipbho", "txisoc", "txinoc"))
+    else:
+        compare(gpu, cpu, ("ochom",), label=case)
+        compare_scalars(gpu, cpu, ("dpioc", "dpiocp", "aipohs", "cdiffo", "cdhoc"))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_helmholtz_matches_oracle_and_operator(qg, pyorc, case):
+    """hsbxoc / hscyoc: same answer as the oracle, and the 5-point operator applied to
+    the answer returns the right-hand side (SURVEY.md 8c identity)"""
+    p = small_configs(qg)[case]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    rng = np.random.default_rng(7)
+    nxp, nyp, nxt = p.nxpo, p.nypo, p.nxto
+    rhs = rng.standard_normal((nxp, nyp))
+    cyc = p.has("cyclic_ocean")
+    if cyc:
+        rhs[-1, :] = rhs[0, :]
+    dx = p.dxo
+    a = 1.0 / dx ** 2
+    bd2 = np.zeros(nxt)
+    if cyc:
+        for i in range(2, nxt // 2 + 1):
+            bd2[2 * i - 3] = -2 * a + 2 * a * (np.cos((i - 1) * 2 * np.pi / nxt) - 1.0)
+            bd2[2 * i - 2] = bd2[2 * i - 3]
+        bd2[0] = -2 * a
+        bd2[nxt - 1] = -2 * a - 4 * a
+    else:
+        bd2[: nxt - 1] = -2 * a + 2 * a * (np.cos(np.arange(1, nxt) * np.pi / nxt) - 1.0)
+    for mode in (0, 1, 2):
+        rd = cfg.rdm2oc[mode]
+        b = bd2 - rd
+        sg = gpu.helmholtz(0, rhs, b)
+        sc = cpu.helmholtz(0, rhs, b)
+        assert rel_l2(sg, sc) <= 1e-12, (case, mode)
+        if cyc:
+            ext = np.vstack([sg[-2:-1, :], sg, sg[1:2, :]])
+            lap = (ext[2:, 1:-1] + ext[:-2, 1:-1] + sg[:, 2:] + sg[:, :-2] - 4 * sg[:, 1:-1]) * a - rd * sg[:, 1:-1]
+            want = rhs[:, 1:-1]
+        else:
+            lap = (sg[2:, 1:-1] + sg[:-2, 1:-1] + sg[1:-1, 2:] + sg[1:-1, :-2] - 4 * sg[1:-1, 1:-1]) * a - rd * sg[1:-1, 1:-1]
+            want = rhs[1:-1, 1:-1]
+        if mode > 0:  # the barotropic periodic problem has a null space in the k=0 column
+            assert rel_l2(lap, want) <= 1e-10, (case, mode)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_each_procedure(qg, pyorc, case):
+    """oml, qgostep, ocinvq, ocqbdy one at a time, in main-loop order"""
+    p = small_configs(qg)[case]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    for step in ("oml", "qgostep", "ocinvq", "ocqbdy"):
+        getattr(gpu, step)()
+        getattr(cpu, step)()
+        compare(gpu, cpu, OCEAN_CHECK, label="%s after %s" % (case, step))
+    fl = integral_scale(cpu, p)
+    compare_scalars(gpu, cpu, ("dpioc", "dpiocp", "xinhom_oc"), tol=1e-11, floor=fl)
+    compare_scalars(gpu, cpu, ("xon",), tol=1e-11, floor=integral_scale(cpu, p, "entoc"))
+    compare_scalars(gpu, cpu, ("centoc", "cfraoc"), tol=1e-9)
+    if p.has("cyclic_ocean"):
+        compare_scalars(gpu, cpu, ("ocncs", "ocncn"), tol=1e-9)
+        # boundary-strip sums are sums of signed terms: compare against the largest of them
+        sc = cpu.get_scalars().as_dict()
+        for grp in (("ajisoc", "ajinoc"), ("ap5soc", "ap5noc"), ("enisoc", "eninoc"), ("bdrins", "bdrinn")):
+            fl2 = max(np.abs(np.atleast_1d(sc[g])).max() for g in grp)
+            compare_scalars(gpu, cpu, grp, tol=1e-7, floor=fl2)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_one_step_and_tlavg(qg, pyorc, case):
+    p = small_configs(qg)[case]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    gpu.run(1, 1)
+    cpu.run(1, 1)      # ocean step + time-level average (mod(nt-1, 25*nstr) == 0 at nt = 1)
+    compare(gpu, cpu, OCEAN_CHECK, label=case)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_hundred_steps_drift(qg, pyorc, case):
+    """100 ocean steps; drift bound documented in DESIGN.md (measured envelope << 1e-8)"""
+    p = small_configs(qg)[case]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    n = 100 * p.nstr
+    gpu.run(1, n)
+    cpu.run(1, n)
+    for name in ("po", "qo", "sst"):
+        e = rel_l2(gpu.get_field(name), cpu.get_field(name))
+        assert e <= 1e-8, (case, name, e)
+        assert np.isfinite(gpu.get_field(name)).all()
+
+
+def test_eddy_state(qg, pyorc):
+    """the fork's own Gaussian-eddy initial state with zero forcing"""
+    p = small_configs(qg)["box_dg"]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p, kind="eddy")
+    gpu.run(1, 10)
+    cpu.run(1, 10)
+    compare(gpu, cpu, ("po", "qo", "sst", "entoc"), label="eddy")
+
+
+def test_roundtrip_and_errors(qg):
+    p = small_configs(qg)["box_dg"]
+    cfg = qg.build_config(p)
+    m = qg.Model(cfg)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((p.nxpo, p.nypo, p.nlo))
+    m.set_field("po", x)
+    assert np.array_equal(m.get_field("po", x.shape), x)
+    t = rng.standard_normal((p.nxto, p.nyto))
+    m.set_field("sst", t)
+    assert np.array_equal(m.get_field("sst", t.shape), t)
+    with pytest.raises(RuntimeError):
+        m.set_field("nosuchfield", t)
+    with pytest.raises(RuntimeError):
+        m.set_field("po", t)

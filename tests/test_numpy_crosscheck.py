@@ -1,0 +1,236 @@
+"""Second, independent implementation of the step routines, written from the Fortran with
+vectorised numpy/scipy (scipy.fft.dst / rfft, scipy.linalg.solve_banded), compared with the
+oracle's loop restatement.  Interior points only where the
+boundary zoo would make the re-derivation as long as the oracle itself."""
+import numpy as np
+import pytest
+import scipy.fft as sf
+import scipy.linalg as sla
+
+from util import small_configs, rel_l2
+
+
+def lap5(f, dxm2):
+    return (f[1:-1, :-2] + f[:-2, 1:-1] + f[2:, 1:-1] + f[1:-1, 2:] - 4.0 * f[1:-1, 1:-1]) * dxm2
+
+
+def jac9(q, p):
+    """Arakawa 9-point J(q,p) numerator at interior points (src/qgosubs.F:376-388)"""
+    c = (slice(1, -1), slice(1, -1))
+    def s(a, di, dj):
+        return a[1 + di: a.shape[0] - 1 + di, 1 + dj: a.shape[1] - 1 + dj]
+    return ((s(q, 1, 0) - s(q, -1, 0)) * (s(p, 0, 1) - s(p, 0, -1)) + (s(q, 0, -1) - s(q, 0, 1)) * (s(p, 1, 0) - s(p, -1, 0))
+            + s(q, 1, 0) * (s(p, 1, 1) - s(p, 1, -1)) - s(q, -1, 0) * (s(p, -1, 1) - s(p, -1, -1))
+            - s(q, 0, 1) * (s(p, 1, 1) - s(p, -1, 1)) + s(q, 0, -1) * (s(p, 1, -1) - s(p, -1, -1))
+            + s(p, 0, 1) * (s(q, 1, 1) - s(q, -1, 1)) - s(p, 0, -1) * (s(q, 1, -1) - s(q, -1, -1))
+            - s(p, 1, 0) * (s(q, 1, 1) - s(q, 1, -1)) + s(p, -1, 0) * (s(q, -1, 1) - s(q, -1, -1)))
+
+
+def test_qgostep_box_interior(qg, pyorc):
+    p = small_configs(qg)["box_dg"]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.oml()
+    sh = (p.nxpo, p.nypo, p.nlo)
+    po, pom, qo, qom = (m.get_field(n, sh) for n in ("po", "pom", "qo", "qom"))
+    wek, ent = m.get_field("wekpo", sh[:2]), m.get_field("entoc", sh[:2])
+    m.qgostep()
+    qnew = m.get_field("qo", sh)
+    dxm2 = 1.0 / p.dxo ** 2
+    bcf = p.bccooc * dxm2 / (0.5 * p.bccooc + 1.0)
+    adf = 1.0 / (12.0 * p.dxo ** 2 * p.fnot)
+    tdt = 2.0 * p.dto
+    for k in range(p.nlo):
+        d2 = np.zeros(sh[:2])
+        d2[1:-1, 1:-1] = lap5(pom[:, :, k], dxm2)
+        d2[:, 0] = bcf * (pom[:, 1, k] - pom[:, 0, k]); d2[:, -1] = bcf * (pom[:, -2, k] - pom[:, -1, k])
+        d2[0, 1:-1] = bcf * (pom[1, 1:-1, k] - pom[0, 1:-1, k]); d2[-1, 1:-1] = bcf * (pom[-2, 1:-1, k] - pom[-1, 1:-1, k])
+        d4 = np.zeros(sh[:2])
+        d4[1:-1, 1:-1] = lap5(d2, dxm2)
+        d4[:, 0] = bcf * (d2[:, 1] - d2[:, 0]); d4[:, -1] = bcf * (d2[:, -2] - d2[:, -1])
+        d4[0, 1:-1] = bcf * (d2[1, 1:-1] - d2[0, 1:-1]); d4[-1, 1:-1] = bcf * (d2[-2, 1:-1] - d2[-1, 1:-1])
+        d6 = lap5(d4, dxm2)
+        dq = adf * jac9(qo[:, :, k], po[:, :, k]) + (p.ah2oc[k] / p.fnot) * d4[1:-1, 1:-1] - (p.ah4oc[k] / p.fnot) * d6
+        if k == 0:
+            dq = dq + (p.fnot / p.hoc[0]) * (wek[1:-1, 1:-1] - ent[1:-1, 1:-1])
+        if k == 1:
+            dq = dq + (p.fnot / p.hoc[1]) * ent[1:-1, 1:-1]
+        if k == p.nlo - 1:
+            dq = dq - 0.5 * np.sign(p.fnot) * p.delek / p.hoc[-1] * d2[1:-1, 1:-1]
+        want = qom[1:-1, 1:-1, k] + tdt * dq
+        assert rel_l2(qnew[1:-1, 1:-1, k], want) <= 1e-13, k
+
+
+def test_qgostep_channel_interior(qg, pyorc):
+    p = small_configs(qg)["chan_so"]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    sh = (p.nxpo, p.nypo, p.nlo)
+    po, pom, qo, qom = (m.get_field(n, sh) for n in ("po", "pom", "qo", "qom"))
+    wek, ent = m.get_field("wekpo", sh[:2]), m.get_field("entoc", sh[:2])
+    m.qgostep()
+    qnew = m.get_field("qo", sh)
+    dxm2 = 1.0 / p.dxo ** 2
+    bcf = p.bccooc * dxm2 / (0.5 * p.bccooc + 1.0)
+    adf = 1.0 / (12.0 * p.dxo ** 2 * p.fnot)
+    tdt = 2.0 * p.dto
+
+    def per(f):   # periodic extension by one column each side (column nxp == column 1)
+        return np.vstack([f[-2:-1], f, f[1:2]])
+
+    for k in range(p.nlo):
+        pm = per(pom[:, :, k])
+        d2 = np.zeros(sh[:2])
+        d2[:, 1:-1] = lap5(pm, dxm2)
+        d2[:, 0] = bcf * (pom[:, 1, k] - pom[:, 0, k]); d2[:, -1] = bcf * (pom[:, -2, k] - pom[:, -1, k])
+        d4 = np.zeros(sh[:2])
+        d4[:, 1:-1] = lap5(per(d2), dxm2)
+        d4[:, 0] = bcf * (d2[:, 1] - d2[:, 0]); d4[:, -1] = bcf * (d2[:, -2] - d2[:, -1])
+        d6 = lap5(per(d4), dxm2)
+        dq = adf * jac9(per(qo[:, :, k]), per(po[:, :, k])) + (p.ah2oc[k] / p.fnot) * d4[:, 1:-1] - (p.ah4oc[k] / p.fnot) * d6
+        if k == 0:
+            dq = dq + (p.fnot / p.hoc[0]) * (wek[:, 1:-1] - ent[:, 1:-1])
+        if k == 1:
+            dq = dq + (p.fnot / p.hoc[1]) * ent[:, 1:-1]
+        if k == p.nlo - 1:
+            dq = dq - 0.5 * np.sign(p.fnot) * p.delek / p.hoc[-1] * d2[:, 1:-1]
+        want = qom[:, 1:-1, k] + tdt * dq
+        assert rel_l2(qnew[:, 1:-1, k], want) <= 1e-13, k
+
+
+def test_hsbxoc_against_scipy(qg, pyorc):
+    """box solver = DST-I rows, banded solve per wavenumber, DST-I rows (src/ocisubs.F:461-509)"""
+    p = small_configs(qg)["box_dg"]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    rng = np.random.default_rng(11)
+    nxp, nyp, nxt = p.nxpo, p.nypo, p.nxto
+    rhs = rng.standard_normal((nxp, nyp))
+    a = 1.0 / p.dxo ** 2
+    rd = cfg.rdm2oc[2]
+    k = np.arange(1, nxt)
+    b = -2 * a + 2 * a * (np.cos(k * np.pi / nxt) - 1.0) - rd
+    bfull = np.zeros(nxt); bfull[: nxt - 1] = b
+    got = m.helmholtz(0, rhs, bfull)
+    spec = sf.dst(rhs[1:-1, 1:-1], type=1, axis=0)
+    sol = np.empty_like(spec)
+    n = nyp - 2
+    for i in range(nxt - 1):
+        ab = np.zeros((3, n)); ab[0, 1:] = a; ab[1, :] = b[i]; ab[2, :-1] = a
+        sol[i] = sla.solve_banded((1, 1), ab, spec[i])
+    want = sf.dst(sol * (0.5 / nxt), type=1, axis=0)
+    assert rel_l2(got[1:-1, 1:-1], want) <= 1e-13
+
+
+def test_hscyoc_against_scipy(qg, pyorc):
+    """channel solver = rfft rows, banded solve per wavenumber, irfft rows (src/ocisubs.F:566-604)"""
+    p = small_configs(qg)["chan_so"]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    rng = np.random.default_rng(12)
+    nxp, nyp, nxt = p.nxpo, p.nypo, p.nxto
+    rhs = rng.standard_normal((nxp, nyp)); rhs[-1] = rhs[0]
+    a = 1.0 / p.dxo ** 2
+    rd = cfg.rdm2oc[1]
+    bd2 = np.zeros(nxt)
+    for i in range(2, nxt // 2 + 1):
+        bd2[2 * i - 3] = -2 * a + 2 * a * (np.cos((i - 1) * 2 * np.pi / nxt) - 1.0)
+        bd2[2 * i - 2] = bd2[2 * i - 3]
+    bd2[0] = -2 * a; bd2[nxt - 1] = -6 * a
+    got = m.helmholtz(0, rhs, bd2 - rd)
+    spec = sf.rfft(rhs[:nxt, 1:-1], axis=0)
+    kk = np.arange(nxt // 2 + 1)
+    bk = -2 * a + 2 * a * (np.cos(kk * 2 * np.pi / nxt) - 1.0) - rd
+    n = nyp - 2
+    sol = np.empty_like(spec)
+    for i in range(nxt // 2 + 1):
+        ab = np.zeros((3, n)); ab[0, 1:] = a; ab[1, :] = bk[i]; ab[2, :-1] = a
+        sol[i] = sla.solve_banded((1, 1), ab, spec[i].real) + 1j * sla.solve_banded((1, 1), ab, spec[i].imag)
+    want = sf.irfft(sol, n=nxt, axis=0)
+    assert rel_l2(got[:nxt, 1:-1], want) <= 1e-13
+    assert np.array_equal(got[-1], got[0])
+
+
+def test_ocinvq_box_against_numpy(qg, pyorc):
+    """layer->mode, invert, constrain, mode->layer with numpy linear algebra"""
+    p = small_configs(qg)["box_dg"]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.oml(); m.qgostep()
+    sh = (p.nxpo, p.nypo, p.nlo)
+    qo = m.get_field("qo", sh)
+    ochom = m.get_field("ochom", (p.nxpo, p.nypo, p.nlo - 1))
+    s0 = m.get_scalars()
+    nl = p.nlo
+    l2m = np.array(cfg.ctl2moc[: nl * nl]).reshape(nl, nl, order="F")
+    m2l = np.array(cfg.ctm2loc[: nl * nl]).reshape(nl, nl, order="F")
+    yrel = (p.ny1 - 1) * p.dxa + np.arange(p.nypo) * p.dxo - 0.5 * p.nyta * p.dxa
+    ql = qo - (p.beta * yrel)[None, :, None]
+    wrk = p.fnot * np.einsum("km,ijk->ijm", l2m, ql)
+    a = 1.0 / p.dxo ** 2
+    nxt = p.nxto
+    kk = np.arange(1, nxt)
+    xin = np.zeros(nl)
+    pm = np.zeros(sh)
+    for mo in range(nl):
+        b = -2 * a + 2 * a * (np.cos(kk * np.pi / nxt) - 1.0) - cfg.rdm2oc[mo]
+        spec = sf.dst(wrk[1:-1, 1:-1, mo], type=1, axis=0)
+        n = p.nypo - 2
+        sol = np.empty_like(spec)
+        for i in range(nxt - 1):
+            ab = np.zeros((3, n)); ab[0, 1:] = a; ab[1, :] = b[i]; ab[2, :-1] = a
+            sol[i] = sla.solve_banded((1, 1), ab, spec[i])
+        pm[1:-1, 1:-1, mo] = sf.dst(sol * (0.5 / nxt), type=1, axis=0)
+        xin[mo] = pm[:, :, mo].sum() * p.dxo ** 2
+    tdt = 2 * p.dto
+    dpi_new = np.array(s0.dpiocp[: nl - 1]) - tdt * np.array(p.gpoc) * np.array([s0.xon[0]] + [0.0] * (nl - 2))
+    cdiffo = np.array(s0.cdiffo[: nl * (nl - 1)]).reshape(nl, nl - 1, order="F")
+    cdhoc = np.array(s0.cdhoc[: (nl - 1) ** 2]).reshape(nl - 1, nl - 1, order="F")
+    hcl = np.linalg.solve(cdhoc, dpi_new - cdiffo.T @ xin)
+    for mo in range(1, nl):
+        pm[:, :, mo] += hcl[mo - 1] * ochom[:, :, mo - 1]
+    want = np.einsum("mk,ijm->ijk", m2l, pm)
+    m.ocinvq()
+    got = m.get_field("po", sh)
+    assert rel_l2(got, want) <= 1e-12
+
+
+def test_oml_interior_against_numpy(qg, pyorc):
+    """C-grid advection + del2/del4 diffusion + sst update at points two cells from any wall"""
+    p = small_configs(qg)["box_dg"]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    nxt, nyt = p.nxto, p.nyto
+    po = m.get_field("po", (p.nxpo, p.nypo, p.nlo))[:, :, 0]
+    tx, ty = m.get_field("tauxo", (p.nxpo, p.nypo)), m.get_field("tauyo", (p.nxpo, p.nypo))
+    sst, sstm = m.get_field("sst", (nxt, nyt)), m.get_field("sstm", (nxt, nyt))
+    wek, fnet = m.get_field("wekto", (nxt, nyt)), m.get_field("fnetoc", (nxt, nyt))
+    m.oml()
+    got = m.get_field("sst", (nxt, nyt))
+    uvg = p.ycexp / (p.dxo * p.fnot)
+    rh = 0.5 / (p.fnot * p.hmoc)
+    hdx = 0.5 / p.dxo
+    # face velocities on the whole grid: u(i,j) west face of cell i (p column i), v(i,j) south face
+    u = -uvg * (po[:, 1:] - po[:, :-1]) + rh * (ty[:, 1:] + ty[:, :-1])          # (nxp, nyt)
+    v = uvg * (po[1:, :] - po[:-1, :]) - rh * (tx[1:, :] + tx[:-1, :])            # (nxt, nyp)
+    I = slice(2, nxt - 2); J = slice(2, nyt - 2)
+    def sh_(a, di, dj):
+        return a[2 + di: nxt - 2 + di, 2 + dj: nyt - 2 + dj]
+    um, up = u[2:nxt - 2, J], u[3:nxt - 1, J]
+    vm, vp = v[I, 2:nyt - 2], v[I, 3:nyt - 1]
+    hx = hdx * (up * (sh_(sst, 0, 0) + sh_(sst, 1, 0)) - um * (sh_(sst, -1, 0) + sh_(sst, 0, 0)))
+    hy = hdx * (vp * (sh_(sst, 0, 1) + sh_(sst, 0, 0)) - vm * (sh_(sst, 0, 0) + sh_(sst, 0, -1)))
+    d2 = np.zeros((nxt, nyt))
+    d2[1:-1, 1:-1] = sstm[1:-1, :-2] + sstm[:-2, 1:-1] + sstm[2:, 1:-1] + sstm[1:-1, 2:] - 4 * sstm[1:-1, 1:-1]
+    dxm2 = 1.0 / p.dxo ** 2
+    d4 = sh_(d2, 0, -1) + sh_(d2, -1, 0) + sh_(d2, 1, 0) + sh_(d2, 0, 1) - 4 * sh_(d2, 0, 0)
+    rhs = -(hx + hy) + p.st2d * dxm2 * sh_(d2, 0, 0) - p.st4d * dxm2 ** 2 * d4
+    toc1 = cfg.toc[0]
+    rrcp = 1.0 / (p.rhooc * p.cpoc)
+    new = sh_(sstm, 0, 0) + 2 * p.dto * (rhs + (rrcp * sh_(fnet, 0, 0) + 0.5 * sh_(wek, 0, 0) * (sh_(sstm, 0, 0) + toc1)) / p.hmoc)
+    new = new + np.maximum(0.0, toc1 - new)
+    assert rel_l2(got[I, J], new) <= 1e-13
