@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the Q-GCM ocean step on B200 (BASELINE.json metric: ocean timesteps/s and
+grid-point-updates/s on the NAtl 1 km ocean-only deck, with the HBM-roofline fraction).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload natl1km] [--impl reference]
+
+A "step" is one ocean timestep (oml + qgostep + ocinvq + ocqbdy, plus the time-level
+average on its 1-in-25 cadence) on synthetic fields of the deck's grid shape.
+
+* value : steps/s with the whole state resident in HBM (timed with CUDA events on the
+          library's stream, max over ranks).
+* e2e   : the same step driven through the C ABI with HOST buffers: every step uploads
+          the externally supplied forcing (tauxo, tauyo, fnetoc) from pinned memory with
+          qgcm_set_field, runs qgcm_ocean_step and reads the scalar state back with
+          qgcm_get_scalars.
+* roofline : per-kernel CUDA-event times from the library's own instrumentation
+          (qgcm_profile) over a second pass of the same K steps; the dominant kernel's
+          algorithmic bytes / its mean launch time against MEASURED_PEAKS.json.
+* cpu_baseline / --impl reference : the CPU restatement of the reference algorithm
+          (oracle/liborc.so, C++/OpenMP, all host cores) on a bounded sample of the same
+          workload.  The real Fortran reference cannot be built in this image (no Fortran
+          compiler), so kind = "port".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ocean_timesteps_per_s"
+UNIT = "steps/s"
+
+
+def passes_per_launch(kernel, cyclic):
+    """algorithmic field passes (8*nxpo*nypo bytes each) one launch of `kernel` must move;
+    SURVEY.md section 8(d) / DESIGN.md kernel table"""
+    table = {
+        "k_oml_step": 9.0, "k_oml_entoc": 2.0,
+        "k_qgstep": 17.0,
+        "k_l2m": 7.0, "k_xform": 6.0, "k_tri_local": 6.0,
+        "k_m2l": 6.0 if cyclic else 8.0,
+        "k_avg2": None,
+    }
+    return table.get(kernel)
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_case(qg, workload, device):
+    p = qg.named_config(workload)
+    cfg = qg.build_config(p, device=device)
+    return p, cfg
+
+
+def cpu_sample(qg, p, cfg, budget_s=20.0, max_steps=4):
+    """time the CPU port on the same workload: as many ocean steps as fit the budget"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyorc
+    pyorc.build()
+    cores = len(os.sched_getaffinity(0))
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    o = pyorc.Oracle(cfg)
+    qg.synth.init_model(o, p, cfg, "random")
+    o.ocean_step()   # warm-up (page faults of the automatic arrays)
+    t0 = time.time()
+    n = 0
+    while n < max_steps:
+        o.ocean_step()
+        n += 1
+        if time.time() - t0 > budget_s:
+            break
+    dt = time.time() - t0
+    o.close()
+    return n / dt, cores, "%d ocean steps of %s (%dx%dx%d) after 1 warm-up" % (n, p.name, p.nxpo, p.nypo, p.nlo)
+
+
+def run_reference(args, qg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    p, cfg = build_case(qg, args.workload, 0)
+    # each "step" of the reference arm is one CPU ocean step; K and W are honoured but
+    # clamped so the whole run stays within a few minutes
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyorc
+    pyorc.build()
+    cores = len(os.sched_getaffinity(0))
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    o = pyorc.Oracle(cfg)
+    qg.synth.init_model(o, p, cfg, "random")
+    warm = max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        o.ocean_step()
+    t0 = time.time()
+    n = 0
+    while n < args.steps:
+        o.ocean_step()
+        n += 1
+        if time.time() - t0 > 120.0:
+            break
+    dt = time.time() - t0
+    v = n / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+        "warmup": warm, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s ocean-only %dx%dx%d" % (p.name, p.nxpo, p.nypo, p.nlo)},
+        "gpt_updates_per_s": v * p.nxpo * p.nypo * p.nlo / 1e9,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d CPU ocean steps (C++/OpenMP restatement of the reference; the Fortran "
+                                   "reference cannot be compiled here)" % n},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="natl1km")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    import _pkg
+    qg = _pkg.load()
+    if args.impl == "reference":
+        run_reference(args, qg)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    p, cfg = build_case(qg, args.workload, local)
+    m = qg.Model(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.sync()
+    stream = torch.cuda.ExternalStream(m.stream(), device=local)
+    nstr = p.nstr
+    cad = 25   # time-level average every 25 ocean steps (src/q-gcm.F:1328)
+
+    def ocean_steps(n, first):
+        for s in range(first, first + n):
+            m.ocean_step()
+            if s % cad == 0:
+                m.tlavg_ocean()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        m.sync()
+        torch.cuda.synchronize()
+
+    ocean_steps(args.warmup, 1)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = m.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ocean_steps(args.steps, args.warmup + 1)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = m.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # N > 1: the y-slab partition is not built yet, every rank advances an independent
+    # replica of the full domain (weak scaling in the number of domains)
+    value = world * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel profile pass (CUDA events inside the library) ----
+    m._lib.qgcm_profile(m._h, 1)
+    ocean_steps(args.steps, args.warmup + args.steps + 1)
+    buf = C.create_string_buffer(1 << 16)
+    m._call("profile_report", buf, C.c_int64(len(buf)))
+    m._lib.qgcm_profile(m._h, 0)
+    prof = {}
+    for ln in buf.value.decode().splitlines():
+        name, cnt, tot = ln.split()
+        prof[name] = (int(cnt), float(tot))
+    tot_ms = sum(v[1] for v in prof.values())
+    fieldpass = 8.0 * p.nxpo * p.nypo
+    peak, peak_src = hbm_peak()
+    kern = {}
+    for name, (cnt, tms) in prof.items():
+        pp = passes_per_launch(name, p.has("cyclic_ocean"))
+        ent = {"launches": cnt, "ms_per_launch": tms / cnt, "share": tms / tot_ms}
+        if pp:
+            ent["GBps"] = pp * fieldpass / (tms / cnt * 1e-3) / 1e9
+            ent["frac"] = ent["GBps"] / peak
+        kern[name] = ent
+    dom = max(prof, key=lambda k: prof[k][1])
+    dpp = passes_per_launch(dom, p.has("cyclic_ocean")) or 0.0
+    dms = prof[dom][1] / prof[dom][0]
+    ach = dpp * fieldpass / (dms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src,
+            "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "algorithmic_bytes_per_launch": dpp * fieldpass, "ms_per_launch": dms,
+            "share_of_step": prof[dom][1] / tot_ms}
+    step_bytes = (61.0 if not p.has("cyclic_ocean") else 59.0) * fieldpass
+    step_frac = step_bytes * value / world / 1e9 / peak
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        names = ("tauxo", "tauyo", "fnetoc")
+        host = {n: torch.from_numpy(m.get_field(n)).pin_memory() for n in names}
+        ptr = {n: C.cast(host[n].data_ptr(), C.POINTER(C.c_double)) for n in names}
+        nel = {n: host[n].numel() for n in names}
+        scal = qg.QgcmScalars()
+        ke = max(3, min(args.steps, 20))
+
+        def e2e_step():
+            for n in names:
+                m._call("set_field", n.encode(), ptr[n], C.c_int64(nel[n]))
+            m.ocean_step()
+            m._call("get_scalars", C.byref(scal))
+
+        e2e_step()
+        barrier()
+        e0.record(stream)
+        for _ in range(ke):
+            e2e_step()
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * ke / (float(t.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(sum(nel.values()) * 8), "d2h_bytes_per_step": int(C.sizeof(scal)),
+               "steps": ke, "def": "per step: qgcm_set_field(tauxo,tauyo,fnetoc) from pinned host memory + "
+                                   "qgcm_ocean_step + qgcm_get_scalars"}
+
+    finite = bool(np.isfinite(m.get_field("po")).all())
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample = cpu_sample(qg, p, cfg)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s ocean-only %dx%dx%d, box, dto=%gs" % (p.name, p.nxpo, p.nypo, p.nlo, p.dto),
+                       "parallelism": "1 domain per GPU" if world > 1 else "single GPU",
+                       "l2": "state (%.1f GB) is far larger than L2; no flush needed" %
+                             (4 * p.nlo * fieldpass / 1e9),
+                       "state_finite": finite},
+            "gpt_updates_per_s": value * p.nxpo * p.nypo * p.nlo / 1e9,
+            "step_roofline_frac": step_frac,
+            "step_algorithmic_bytes": step_bytes,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "kernels": kern,
+            "e2e": e2e,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -202,6 +202,10 @@ int qgcm_run(qgcm_model *m, int64_t nt_first, int64_t nt_last);
 
 /* number of kernels launched by this model since creation */
 int64_t qgcm_launch_count(qgcm_model *m);
+/* per-kernel timing with CUDA events on the launching stream: enable (1) / disable (0)
+ * clears the records; the report is one text line per kernel: "name launches total_ms" */
+int qgcm_profile(qgcm_model *m, int enable);
+int qgcm_profile_report(qgcm_model *m, char *buf, int64_t nbuf);
 /* cudaStream_t the model launches on, as an opaque pointer (for event timing) */
 void *qgcm_stream(qgcm_model *m);
 

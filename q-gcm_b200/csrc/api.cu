@@ -26,6 +26,30 @@ void *dalloc(qgcm_model *m, size_t bytes) {
   return p;
 }
 
+static cudaEvent_t prof_event(qgcm_model *m) {
+  if (!m->prof_pool.empty()) {
+    cudaEvent_t e = m->prof_pool.back();
+    m->prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  QG_CUDA(cudaEventCreate(&e));
+  return e;
+}
+void prof_begin(qgcm_model *m, const char *name) {
+  if (!m->prof) return;
+  qgcm_model::ProfRec r;
+  r.name = name;
+  r.e0 = prof_event(m);
+  r.e1 = prof_event(m);
+  QG_CUDA(cudaEventRecord(r.e0, m->stream));
+  m->prof_recs.push_back(r);
+}
+void prof_end(qgcm_model *m) {
+  if (!m->prof) return;
+  QG_CUDA(cudaEventRecord(m->prof_recs.back().e1, m->stream));
+}
+
 static void add_field(qgcm_model *m, const char *name, int nx, int ny, int nl, int ld, size_t lsz = 0) {
   qgcm_model::Field f;
   f.nx = nx; f.ny = ny; f.nl = nl; f.ld = ld; f.lsz = lsz;
@@ -342,6 +366,38 @@ int qgcm_run(qgcm_model *m, int64_t nt_first, int64_t nt_last) {
 }
 
 int64_t qgcm_launch_count(qgcm_model *m) { return m ? m->launches : 0; }
+
+int qgcm_profile(qgcm_model *m, int enable) {
+  QG_TRY({
+    QG_CUDA(cudaStreamSynchronize(m->stream));
+    for (auto &r : m->prof_recs) { m->prof_pool.push_back(r.e0); m->prof_pool.push_back(r.e1); }
+    m->prof_recs.clear();
+    m->prof = enable != 0;
+  });
+}
+
+int qgcm_profile_report(qgcm_model *m, char *buf, int64_t nbuf) {
+  QG_TRY({
+    QG_CUDA(cudaStreamSynchronize(m->stream));
+    std::map<std::string, std::pair<double, long>> acc;
+    std::vector<std::string> order;
+    for (auto &r : m->prof_recs) {
+      float ms = 0.f;
+      QG_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+      if (!acc.count(r.name)) order.push_back(r.name);
+      acc[r.name].first += ms;
+      acc[r.name].second += 1;
+    }
+    std::string out;
+    for (auto &n : order) {
+      char line[256];
+      snprintf(line, sizeof(line), "%s %ld %.6f\n", n.c_str(), acc[n].second, acc[n].first);
+      out += line;
+    }
+    if ((int64_t)out.size() + 1 > nbuf) throw std::runtime_error("qgcm_profile_report: buffer too small");
+    std::memcpy(buf, out.c_str(), out.size() + 1);
+  });
+}
 void *qgcm_stream(qgcm_model *m) { return m ? (void *)m->stream : nullptr; }
 
 }  // extern "C"

@@ -574,8 +574,7 @@ void helm_set_diag(qgcm_model *md, HelmPlan &hp, const double *b_host) {
   QG_CUDA(cudaStreamSynchronize(md->stream));
   TriArgs t = tri_args(hp, nullptr, 0, hp.nmodes);
   dim3 grid((hp.nk + 127) / 128, hp.nmodes);
-  k_tri_tables<<<grid, 128, 0, md->stream>>>(t);
-  md->launches++;
+  QG_LAUNCH(md, "k_tri_tables", grid, 128, 0, k_tri_tables, t);
   QG_CUDA(cudaGetLastError());
 }
 
@@ -590,20 +589,17 @@ void helm_solve(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
   x.nchunk = hp.nchunk; x.lastlen = hp.lastlen; x.ftnorm = hp.ftnorm; x.wrk = wrk;
   x.vl = hp.vl; x.vll = hp.vll; x.yx = hp.yx; x.rowsum = hp.rowsum;
   dim3 gx(hp.nrows, nmodes);
-  k_xform<<<gx, 256, hp.smem_bytes, md->stream>>>(x);
+  QG_LAUNCH(md, "k_xform", gx, 256, hp.smem_bytes, k_xform, x);
   TriArgs t = tri_args(hp, wrk, lsz, nmodes);
   dim3 gl((hp.nk + 127) / 128, hp.nchunk, nmodes);
-  k_tri_local<<<gl, 128, 0, md->stream>>>(t);
-  md->launches += 2;
+  QG_LAUNCH(md, "k_tri_local", gl, 128, 0, k_tri_local, t);
   if (hp.nchunk > 1) {
     dim3 gr((hp.nk + 127) / 128, nmodes);
-    k_tri_reduced<<<gr, 128, 0, md->stream>>>(t);
-    md->launches++;
+    QG_LAUNCH(md, "k_tri_reduced", gr, 128, 0, k_tri_reduced, t);
   }
   x.inverse = 1;
-  k_xform<<<gx, 256, hp.smem_bytes, md->stream>>>(x);
-  k_zero_rows<<<(hp.nxp + 255) / 256, 256, 0, md->stream>>>(wrk, lsz, hp.ld, hp.nyp, hp.nxp, nmodes);
-  md->launches += 2;
+  QG_LAUNCH(md, "k_xform", gx, 256, hp.smem_bytes, k_xform, x);
+  QG_LAUNCH(md, "k_zero_rows", (hp.nxp + 255) / 256, 256, 0, k_zero_rows, wrk, lsz, hp.ld, hp.nyp, hp.nxp, nmodes);
   QG_CUDA(cudaGetLastError());
 }
 

@@ -259,8 +259,7 @@ static void invert(qgcm_model *m, bool atmos) {
   const Grid &g = a.g;
   HelmPlan &hp = atmos ? m->hpa : m->hpo;
   dim3 gi((g.nxp + 255) / 256, g.nyp - 2);
-  k_l2m<<<gi, 256, 0, m->stream>>>(a);
-  m->launches++;
+  QG_LAUNCH(m, "k_l2m", gi, 256, 0, k_l2m, a);
   helm_solve(m, hp, a.wrk, g.nl);
   ScalArgs s;
   const LayerConsts &lc = atmos ? m->la : m->lo;
@@ -271,10 +270,9 @@ static void invert(qgcm_model *m, bool atmos) {
   s.rowsum = hp.rowsum;
   s.sc = m->d_scal;
   s.coef = (double *)a.coef;
-  k_inv_scalars<<<1, 32, 0, m->stream>>>(s);
+  QG_LAUNCH(m, "k_inv_scalars", 1, 32, 0, k_inv_scalars, s);
   dim3 gm((g.nxp + 255) / 256, g.nyp);
-  k_m2l<<<gm, 256, 0, m->stream>>>(a);
-  m->launches += 2;
+  QG_LAUNCH(m, "k_m2l", gm, 256, 0, k_m2l, a);
   QG_CUDA(cudaGetLastError());
   // pom <- po, po <- new: pointer rotation (src/ocisubs.F:392, src/atisubs.F:282)
   m->swapf(atmos ? "pa" : "po", atmos ? "pam" : "pom");
@@ -367,14 +365,13 @@ static void homsol_channel(qgcm_model *m, bool atmos) {
     QG_CUDA(cudaMemcpy(d_row, l1.data(), sizeof(double) * nyp, cudaMemcpyHostToDevice));
     QG_CUDA(cudaMemcpy(d_row + nyp, l2.data(), sizeof(double) * nyp, cudaMemcpyHostToDevice));
     dim3 gf((g.nxp + 255) / 256, nyp);
-    k_fill_rows<<<gf, 256, 0, m->stream>>>(wrk, g.ld, nyp, g.nxp, d_row, 0.0, 1);
-    k_fill_rows<<<gf, 256, 0, m->stream>>>(wrk + g.lsz, g.ld, nyp, g.nxp, d_row + nyp, 0.0, 1);
+    QG_LAUNCH(m, "k_fill_rows", gf, 256, 0, k_fill_rows, wrk, g.ld, nyp, g.nxp, d_row, 0.0, 1);
+    QG_LAUNCH(m, "k_fill_rows", gf, 256, 0, k_fill_rows, wrk + g.lsz, g.ld, nyp, g.nxp, d_row + nyp, 0.0, 1);
     helm_solve(m, hp, wrk, 2);
     double aip[2];
     for (int q = 0; q < 2; ++q) {
-      k_hom_finish<<<nyp, 256, 0, m->stream>>>(wrk + q * g.lsz, wrk + q * g.lsz, g.ld, nyp, g.nxp, d_row + q * nyp, 0.0, 1,
+      QG_LAUNCH(m, "k_hom_finish", nyp, 256, 0, k_hom_finish, wrk + q * g.lsz, wrk + q * g.lsz, g.ld, nyp, g.nxp, d_row + q * nyp, 0.0, 1,
                                                rdm2, d_row + 2 * nyp);
-      m->launches += 2;
       QG_CUDA(cudaMemcpyAsync(rs.data(), d_row + 2 * nyp, sizeof(double) * nyp, cudaMemcpyDeviceToHost, m->stream));
       // column 1 of the solution is the 1-D profile (src/conhoms.F:478-479)
       QG_CUDA(cudaMemcpy2DAsync(col.data(), sizeof(double), wrk + q * g.lsz, sizeof(double) * g.ld, sizeof(double), nyp,
@@ -432,13 +429,11 @@ static void homsol_box(qgcm_model *m) {
   // The per-mode operator table already holds mode m+1 in slot m, so solve all nl slots
   // with rhs = 1 and keep slots 1..nl-1.
   dim3 gf((g.nxp + 255) / 256, nyp);
-  for (int q = 0; q < nl; ++q) k_fill_rows<<<gf, 256, 0, m->stream>>>(m->wrk_o + q * g.lsz, g.ld, nyp, g.nxp, nullptr, 1.0, 0);
-  m->launches += nl;
+  for (int q = 0; q < nl; ++q) QG_LAUNCH(m, "k_fill_rows", gf, 256, 0, k_fill_rows, m->wrk_o + q * g.lsz, g.ld, nyp, g.nxp, nullptr, 1.0, 0);
   helm_solve(m, hp, m->wrk_o, nl);
   for (int mo = 1; mo <= nl - 1; ++mo) {
-    k_hom_finish<<<nyp, 256, 0, m->stream>>>(ochom + (size_t)(mo - 1) * g.lsz, m->wrk_o + (size_t)mo * g.lsz, g.ld, nyp,
+    QG_LAUNCH(m, "k_hom_finish", nyp, 256, 0, k_hom_finish, ochom + (size_t)(mo - 1) * g.lsz, m->wrk_o + (size_t)mo * g.lsz, g.ld, nyp,
                                              g.nxp, nullptr, 1.0, 0, lc.rdm2[mo], m->d_red);
-    m->launches++;
     QG_CUDA(cudaMemcpyAsync(rs.data(), m->d_red, sizeof(double) * nyp, cudaMemcpyDeviceToHost, m->stream));
     QG_CUDA(cudaStreamSynchronize(m->stream));
     s.aipohs[mo - 1] = xintp_from_rowsums(rs) * g.dx * g.dx;

@@ -76,16 +76,14 @@ void launch_ocqbdy(qgcm_model *m, double *q, const double *p) {
   BdyArgs a;
   fill_bdy(m, false, a, q, p);
   const int n = max(a.g.nxp, a.g.nyp);
-  k_qbdy<<<dim3((n + 255) / 256, a.g.cyclic ? 2 : 4, a.g.nl), 256, 0, m->stream>>>(a);
-  m->launches++;
+  QG_LAUNCH(m, "k_qbdy", dim3((n + 255) / 256, a.g.cyclic ? 2 : 4, a.g.nl), 256, 0, k_qbdy, a);
   QG_CUDA(cudaGetLastError());
 }
 
 void launch_atqzbd(qgcm_model *m, double *q, const double *p) {
   BdyArgs a;
   fill_bdy(m, true, a, q, p);
-  k_qbdy<<<dim3((a.g.nxp + 255) / 256, 2, a.g.nl), 256, 0, m->stream>>>(a);
-  m->launches++;
+  QG_LAUNCH(m, "k_qbdy", dim3((a.g.nxp + 255) / 256, 2, a.g.nl), 256, 0, k_qbdy, a);
   QG_CUDA(cudaGetLastError());
 }
 
@@ -119,8 +117,7 @@ __global__ void __launch_bounds__(256) k_qcomp(BdyArgs a) {
 void launch_qcomp(qgcm_model *m, bool ocean, double *q, const double *p) {
   BdyArgs a;
   fill_bdy(m, !ocean, a, q, p);
-  k_qcomp<<<dim3((a.g.nxp + 255) / 256, a.g.nyp - 2, a.g.nl), 256, 0, m->stream>>>(a);
-  m->launches++;
+  QG_LAUNCH(m, "k_qcomp", dim3((a.g.nxp + 255) / 256, a.g.nyp - 2, a.g.nl), 256, 0, k_qcomp, a);
   QG_CUDA(cudaGetLastError());
 }
 
@@ -180,12 +177,10 @@ __global__ void __launch_bounds__(256) k_txis(Grid g, double dx, const double *t
 void launch_xforc_ocean_ekman(qgcm_model *m) {
   const Grid &g = m->go;
   const double hxofac = 0.5 * g.rdxf0;
-  k_wekto<<<dim3((g.nxt + 255) / 256, g.nyt), 256, 0, m->stream>>>(g, hxofac, m->F("tauxo"), m->F("tauyo"), m->F("wekto"));
-  k_wekpo<<<dim3((g.nxp + 255) / 256, g.nyp), 256, 0, m->stream>>>(g, m->F("wekto"), m->F("wekpo"));
-  m->launches += 2;
+  QG_LAUNCH(m, "k_wekto", dim3((g.nxt + 255) / 256, g.nyt), 256, 0, k_wekto, g, hxofac, m->F("tauxo"), m->F("tauyo"), m->F("wekto"));
+  QG_LAUNCH(m, "k_wekpo", dim3((g.nxp + 255) / 256, g.nyp), 256, 0, k_wekpo, g, m->F("wekto"), m->F("wekpo"));
   if (g.cyclic) {
-    k_txis<<<1, 256, 0, m->stream>>>(g, g.dx, m->F("tauxo"), &m->d_scal->txisoc, &m->d_scal->txinoc);
-    m->launches++;
+    QG_LAUNCH(m, "k_txis", 1, 256, 0, k_txis, g, g.dx, m->F("tauxo"), &m->d_scal->txisoc, &m->d_scal->txinoc);
   }
   QG_CUDA(cudaGetLastError());
 }
@@ -215,16 +210,14 @@ __global__ void k_avg_scalars(qgcm_scalars *s, int atmos, int cyclic, int nl) {
   }
 }
 static void avg(qgcm_model *m, const char *a, const char *b, size_t n) {
-  k_avg2<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->F(a), m->F(b), n);
-  m->launches++;
+  QG_LAUNCH(m, "k_avg2", (unsigned)((n + 255) / 256), 256, 0, k_avg2, m->F(a), m->F(b), n);
 }
 void launch_tlavg_ocean(qgcm_model *m) {
   const Grid &g = m->go;
   avg(m, "qo", "qom", g.lsz * g.nl);
   avg(m, "po", "pom", g.lsz * g.nl);
   avg(m, "sst", "sstm", (size_t)g.ld * g.nyt);
-  k_avg_scalars<<<1, 32, 0, m->stream>>>(m->d_scal, 0, g.cyclic, g.nl);
-  m->launches++;
+  QG_LAUNCH(m, "k_avg_scalars", 1, 32, 0, k_avg_scalars, m->d_scal, 0, g.cyclic, g.nl);
   QG_CUDA(cudaGetLastError());
 }
 void launch_tlavg_atmos(qgcm_model *m) {
@@ -233,8 +226,7 @@ void launch_tlavg_atmos(qgcm_model *m) {
   avg(m, "pa", "pam", g.lsz * g.nl);
   avg(m, "ast", "astm", (size_t)g.ld * g.nyt);
   avg(m, "hmixa", "hmixam", (size_t)g.ld * g.nyt);
-  k_avg_scalars<<<1, 32, 0, m->stream>>>(m->d_scal, 1, 1, g.nl);
-  m->launches++;
+  QG_LAUNCH(m, "k_avg_scalars", 1, 32, 0, k_avg_scalars, m->d_scal, 1, 1, g.nl);
   QG_CUDA(cudaGetLastError());
 }
 
@@ -264,8 +256,7 @@ __global__ void __launch_bounds__(256) k_diff_rowsum(Grid g, const double *pa, c
 
 static double xintp_diff(qgcm_model *m, const Grid &g, const double *a, const double *b) {
   std::vector<double> rs(g.nyp);
-  k_diff_rowsum<<<g.nyp, 256, 0, m->stream>>>(g, a, b, m->d_red);
-  m->launches++;
+  QG_LAUNCH(m, "k_diff_rowsum", g.nyp, 256, 0, k_diff_rowsum, g, a, b, m->d_red);
   QG_CUDA(cudaMemcpyAsync(rs.data(), m->d_red, sizeof(double) * g.nyp, cudaMemcpyDeviceToHost, m->stream));
   QG_CUDA(cudaStreamSynchronize(m->stream));
   double sump = 0.0;

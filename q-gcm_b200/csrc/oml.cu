@@ -334,12 +334,11 @@ void launch_oml(qgcm_model *m) {
   a.entoc = m->F("entoc");
   a.sc = m->d_scal;
   if (m->red_elems < 3 * (size_t)a.nblocks + g.nyp) throw std::runtime_error("oml: reduction scratch too small");
-  k_oml_monitors<<<1, 256, 0, m->stream>>>(a);
-  k_oml_step<<<grid, 256, 0, m->stream>>>(a);
-  k_oml_reduce<<<1, 256, 0, m->stream>>>(a, g.dx * g.dx);
-  k_oml_entoc<<<g.nyp, 256, 0, m->stream>>>(a);
-  k_oml_finish<<<1, 32, 0, m->stream>>>(a, g.dx);
-  m->launches += 5;
+  QG_LAUNCH(m, "k_oml_monitors", 1, 256, 0, k_oml_monitors, a);
+  QG_LAUNCH(m, "k_oml_step", grid, 256, 0, k_oml_step, a);
+  QG_LAUNCH(m, "k_oml_reduce", 1, 256, 0, k_oml_reduce, a, g.dx * g.dx);
+  QG_LAUNCH(m, "k_oml_entoc", g.nyp, 256, 0, k_oml_entoc, a);
+  QG_LAUNCH(m, "k_oml_finish", 1, 32, 0, k_oml_finish, a, g.dx);
   QG_CUDA(cudaGetLastError());
   // sstm <- sst, sst <- new: three-buffer rotation (omlsubs.F:124-125)
   double *old_m = m->fields.at("sstm").d;

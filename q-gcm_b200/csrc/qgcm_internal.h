@@ -18,6 +18,16 @@
                                __FILE__ ":" + std::to_string(__LINE__));                    \
   } while (0)
 
+// every kernel launch goes through this macro: counts it and, when profiling is on,
+// brackets it with CUDA events on the launching stream
+#define QG_LAUNCH(m, name, grid, block, smem, kern, ...)            \
+  do {                                                              \
+    qg::prof_begin(m, name);                                        \
+    kern<<<grid, block, smem, (m)->stream>>>(__VA_ARGS__);          \
+    qg::prof_end(m);                                                \
+    (m)->launches++;                                                \
+  } while (0)
+
 namespace qg {
 
 constexpr int NLMAX = QGCM_NLMAX;
@@ -111,6 +121,11 @@ struct qgcm_model {
   double *wrk_o = nullptr, *wrk_a = nullptr;   // modal work arrays [nl][nyp][ld]
   double *xfo = nullptr, *xfa = nullptr, *sstnew = nullptr, *astnew = nullptr, *hmnew = nullptr;
   std::vector<void *> allocs;
+  // per-kernel event timing (qgcm_profile)
+  bool prof = false;
+  struct ProfRec { const char *name; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
 
   double *F(const char *name) { return fields.at(name).d; }
   void swapf(const char *a, const char *b) { std::swap(fields.at(a).d, fields.at(b).d); }
@@ -119,6 +134,8 @@ struct qgcm_model {
 namespace qg {
 
 void *dalloc(qgcm_model *m, size_t bytes);
+void prof_begin(qgcm_model *m, const char *name);
+void prof_end(qgcm_model *m);
 
 // helmholtz.cu
 void helm_plan_create(qgcm_model *m, HelmPlan &hp, const Grid &g, int kind, const double *rdm2, int nmodes);

@@ -317,12 +317,10 @@ static void launch(qgcm_model *m, bool atmos) {
   a.ent = m->F(atmos ? "entat" : "entoc");
   if (g.cyclic) {
     s.pm = a.pm; s.p = a.p; s.q = a.q;
-    k_strips<<<dim3(g.nl, 2), 256, 0, m->stream>>>(s);
-    m->launches++;
+    QG_LAUNCH(m, "k_strips", dim3(g.nl, 2), 256, 0, k_strips, s);
   }
   dim3 grid((g.nxp + TX - 1) / TX, (g.nyp + TY - 1) / TY, g.nl);
-  k_qgstep<<<grid, 256, 0, m->stream>>>(a);
-  m->launches++;
+  QG_LAUNCH(m, "k_qgstep", grid, 256, 0, k_qgstep, a);
   QG_CUDA(cudaGetLastError());
   m->swapf(nq, nqm);   // new q lives in the old qom buffer; old q becomes qom
 }

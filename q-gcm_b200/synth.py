@@ -61,8 +61,10 @@ def _bandlimited(rng, nx, ny, amp, periodic_x, nmode=8):
     return f / nmode
 
 
-def ocean_state(p, cfg, kind="random", seed=SEED):
-    """dict of Fortran-shaped arrays for every ocean input field except q"""
+def ocean_state(p, cfg, kind="random", seed=SEED, amp=1.0):
+    """dict of Fortran-shaped arrays for every ocean input field except q.  ``amp`` scales
+    the pressure amplitude (reduced-size test grids keep the full-size Courant number by
+    scaling p with the domain length)"""
     rng = np.random.default_rng(seed)
     nxp, nyp, nxt, nyt, nl = p.nxpo, p.nypo, p.nxto, p.nyto, p.nlo
     cyc = p.has("cyclic_ocean")
@@ -88,7 +90,7 @@ def ocean_state(p, cfg, kind="random", seed=SEED):
     else:
         amps = [2.0, 1.0, 0.5] + [0.25] * max(0, nl - 3)
         for k in range(nl):
-            po[:, :, k] = _bandlimited(rng, nxp, nyp, amps[k], cyc)
+            po[:, :, k] = _bandlimited(rng, nxp, nyp, amp * amps[k], cyc)
         st["po"] = po
         st["pom"] = po * (1.0 - 1.0e-3)
         sstbar = np.asarray(rad["sstbar"])
@@ -134,11 +136,14 @@ def atmos_state(p, cfg, kind="random", seed=SEED + 1):
     return st
 
 
-def init_model(m, p, cfg, kind="random", seed=SEED):
+def init_model(m, p, cfg, kind="random", seed=SEED, amp=None):
     """the start-up sequence of src/q-gcm.F:597-976 on a model (oracle or CUDA):
     load state, constr, q from p, first xforc, zero entrainment, homsol."""
+    if amp is None:
+        # keep the advective Courant number of the full-size decks (4800 km basins)
+        amp = min(1.0, (p.nxto * p.dxo) / 4.8e6 * 4.0)
     if not p.has("atmos_only"):
-        st = ocean_state(p, cfg, kind, seed)
+        st = ocean_state(p, cfg, kind, seed, amp)
         for k, v in st.items():
             m.set_field(k, v)
     if not p.has("ocean_only"):
