@@ -380,86 +380,95 @@ __global__ void k_tri_tables(TriArgs t) {
   double p = -alpha;
   for (int c = 1; c < C; ++c) {
     const double q = (c == C - 1) ? -alphal : -alpha;
-    t.pt[((size_t)mode * C + c) * t.ld + col] = p;
-    p = -alpha + eps * eps * p / (1.0 - p * q);
+    const double dinv = 1.0 / (1.0 - p * q);
+    t.pt[((size_t)mode * 2 * C + c) * t.ld + col] = p;
+    t.pt[((size_t)mode * 2 * C + C + c) * t.ld + col] = dinv;
+    p = -alpha + eps * eps * p * dinv;
   }
 }
 
-// chunk-local Thomas solve entirely in registers; grid (ceil(nk/128), nchunk, nmodes)
-__global__ void __launch_bounds__(128) k_tri_local(TriArgs t) {
+// chunk-local Thomas solve: the chunk's right-hand side stays in registers, the
+// elimination reciprocals stream from an L2-resident table; grid (ceil(nk/128), nchunk, nmodes)
+__global__ void __launch_bounds__(128, 3) k_tri_local(TriArgs t) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y, mode = blockIdx.z;
   if (s >= t.nk) return;
   const int col = t.koff + s;
   const int len = (c == t.nchunk - 1) ? t.lastlen : TRI_L;
-  double *base = t.wrk + (size_t)mode * t.lsz + (size_t)(1 + c * TRI_L) * t.ld + col;
-  const double *bi = t.binv + ((size_t)mode * TRI_L) * t.ld + col;
+  double *__restrict__ base = t.wrk + (size_t)mode * t.lsz + (size_t)(1 + c * TRI_L) * t.ld + col;
+  const double *__restrict__ bi = t.binv + ((size_t)mode * TRI_L) * t.ld + col;
   const double a = t.a;
-  double u[TRI_L], g[TRI_L];
+  const int ld = t.ld;
+  double u[TRI_L];
 #pragma unroll
-  for (int j = 0; j < TRI_L; ++j) {
-    u[j] = (j < len) ? base[(size_t)j * t.ld] : 0.0;
-    g[j] = bi[(size_t)j * t.ld];
+  for (int j = 0; j < TRI_L; ++j) u[j] = base[(size_t)min(j, len - 1) * ld];   // rows >= len: harmless duplicates
+  u[0] = u[0] * __ldg(bi);
+#pragma unroll
+  for (int j = 1; j < TRI_L; ++j) u[j] = (u[j] - a * u[j - 1]) * __ldg(bi + (size_t)j * ld);
+#pragma unroll
+  for (int j = TRI_L - 2; j >= 0; --j) {
+    const double v = u[j] - (a * __ldg(bi + (size_t)j * ld)) * u[j + 1];
+    u[j] = (j < len - 1) ? v : u[j];
   }
-  u[0] = u[0] * g[0];
-#pragma unroll
-  for (int j = 1; j < TRI_L; ++j) u[j] = (u[j] - a * u[j - 1]) * g[j];
-#pragma unroll
-  for (int j = TRI_L - 2; j >= 0; --j)
-    if (j < len - 1) u[j] = u[j] - (a * g[j]) * u[j + 1];
 #pragma unroll
   for (int j = 0; j < TRI_L; ++j)
-    if (j < len) base[(size_t)j * t.ld] = u[j];
+    if (j < len) base[(size_t)j * ld] = u[j];
   if (t.nchunk > 1) {
-    double last = u[0];
-#pragma unroll
-    for (int j = 1; j < TRI_L; ++j)
-      if (j == len - 1) last = u[j];
-    const size_t fb = ((size_t)mode * 2 * t.nchunk) * t.ld + col;
-    t.fg[fb + (size_t)c * t.ld] = u[0];                    // f_c : first row of the chunk
-    t.fg[fb + (size_t)(t.nchunk + c) * t.ld] = last;       // g_c : last row of the chunk
+    const size_t fb = ((size_t)mode * 2 * t.nchunk) * ld + col;
+    t.fg[fb + (size_t)c * ld] = u[0];                    // f_c : first row of the chunk
+    // g_c : last row of the chunk.  Only g_0..g_{C-2} enter the interface system and those
+    // chunks are always full, so the (ragged) last chunk may store a meaningless value.
+    t.fg[fb + (size_t)(t.nchunk + c) * ld] = u[TRI_L - 1];
   }
 }
 
-// interface system: one thread per (column, mode), block Thomas over the chunks
-__global__ void k_tri_reduced(TriArgs t) {
+// interface system: one thread per (column, mode), block Thomas over the chunks.  All
+// loads are independent of the recurrence (separate output array), so they pipeline.
+__global__ void __launch_bounds__(128) k_tri_reduced(TriArgs t) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int mode = blockIdx.y;
   if (s >= t.nk) return;
   const int col = t.koff + s;
-  const int C = t.nchunk;
-  const size_t tb = ((size_t)mode * TRI_L) * t.ld + col;
-  const double alpha = t.vl[tb], eps = t.vl[tb + (size_t)(TRI_L - 1) * t.ld], alphal = t.vll[tb];
-  const size_t fb = ((size_t)mode * 2 * C) * t.ld + col;
-  double *f = t.fg + fb, *g = t.fg + fb + (size_t)C * t.ld;      // f[c], g[c] at stride ld
-  double *yp = t.yx + fb, *xn = t.yx + fb + (size_t)C * t.ld;
-  const double *pt = t.pt + ((size_t)mode * C) * t.ld + col;
-  // forward elimination: h0_c overwrites g[c-1]
-  double h0 = g[0], h1 = f[t.ld], p = pt[t.ld], q = (1 == C - 1) ? -alphal : -alpha;
+  const int C = t.nchunk, ld = t.ld;
+  const size_t tb = ((size_t)mode * TRI_L) * ld + col;
+  const double alpha = t.vl[tb], eps = t.vl[tb + (size_t)(TRI_L - 1) * ld], alphal = t.vll[tb];
+  const size_t fb = ((size_t)mode * 2 * C) * ld + col;
+  const double *__restrict__ f = t.fg + fb;
+  const double *__restrict__ g = t.fg + fb + (size_t)C * ld;
+  double *__restrict__ yp = t.yx + fb;
+  double *__restrict__ xn = t.yx + fb + (size_t)C * ld;
+  const double *__restrict__ pt = t.pt + ((size_t)mode * 2 * C) * ld + col;   // p_c
+  const double *__restrict__ di = pt + (size_t)C * ld;                        // 1/(1 - p_c q_c)
+  // forward elimination: h0_c is parked in yp[c] (overwritten by the back substitution)
+  double h0 = g[0], h1 = f[ld], p = pt[ld], dinv = di[ld];
+  yp[ld] = h0;
+#pragma unroll 4
   for (int c = 2; c < C; ++c) {
-    const double t0 = (h0 - p * h1) / (1.0 - p * q);
-    h0 = g[(size_t)(c - 1) * t.ld] + eps * t0;
-    g[(size_t)(c - 1) * t.ld] = h0;
-    h1 = f[(size_t)c * t.ld];
-    p = pt[(size_t)c * t.ld];
-    q = (c == C - 1) ? -alphal : -alpha;
+    const double gc = g[(size_t)(c - 1) * ld], fc = f[(size_t)c * ld];
+    const double pc = pt[(size_t)c * ld], dc = di[(size_t)c * ld];
+    const double t0 = (h0 - p * h1) * dinv;
+    h0 = gc + eps * t0;
+    yp[(size_t)c * ld] = h0;
+    h1 = fc;
+    p = pc;
+    dinv = dc;
   }
   // back substitution
   double xnext = 0.0;
-  yp[0] = 0.0;
-  xn[(size_t)(C - 1) * t.ld] = 0.0;
+  xn[(size_t)(C - 1) * ld] = 0.0;
+#pragma unroll 4
   for (int c = C - 1; c >= 1; --c) {
-    const double pc = pt[(size_t)c * t.ld];
+    const double pc = pt[(size_t)c * ld], dc = di[(size_t)c * ld];
     const double qc = (c == C - 1) ? -alphal : -alpha;
-    const double hh0 = g[(size_t)(c - 1) * t.ld];
-    const double hh1 = f[(size_t)c * t.ld] + eps * xnext;
-    const double det = 1.0 - pc * qc;
-    const double y = (hh0 - pc * hh1) / det;    // y_{c-1}: last row of chunk c-1
-    const double x = (hh1 - qc * hh0) / det;    // x_c    : first row of chunk c
-    yp[(size_t)c * t.ld] = y;
-    xn[(size_t)(c - 1) * t.ld] = x;
+    const double hh0 = yp[(size_t)c * ld];
+    const double hh1 = f[(size_t)c * ld] + eps * xnext;
+    const double y = (hh0 - pc * hh1) * dc;    // y_{c-1}: last row of chunk c-1
+    const double x = (hh1 - qc * hh0) * dc;    // x_c    : first row of chunk c
+    yp[(size_t)c * ld] = y;
+    xn[(size_t)(c - 1) * ld] = x;
     xnext = x;
   }
+  yp[0] = 0.0;
 }
 
 __global__ void k_zero_rows(double *wrk, size_t lsz, int ld, int nyp, int nxp, int nmodes) {
@@ -528,7 +537,7 @@ void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, con
   hp.binv = (double *)dalloc(md, sizeof(double) * nmodes * TRI_L * row);
   hp.vl = (double *)dalloc(md, sizeof(double) * nmodes * TRI_L * row);
   hp.vll = (double *)dalloc(md, sizeof(double) * nmodes * TRI_L * row);
-  hp.pt = (double *)dalloc(md, sizeof(double) * nmodes * hp.nchunk * row);
+  hp.pt = (double *)dalloc(md, sizeof(double) * nmodes * 2 * hp.nchunk * row);
   hp.fg = (double *)dalloc(md, sizeof(double) * nmodes * 2 * hp.nchunk * row);
   hp.yx = (double *)dalloc(md, sizeof(double) * nmodes * 2 * hp.nchunk * row);
   hp.rowsum = (double *)dalloc(md, sizeof(double) * nmodes * hp.nyp);

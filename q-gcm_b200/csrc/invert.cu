@@ -118,15 +118,17 @@ struct ScalArgs {
 // Single-thread constraint algebra on device-resident scalars, so the step never
 // synchronises with the host (src/ocisubs.F:146-162, :174-294, :333-370;
 // src/atisubs.F:137-258).  xinhom(m) = dx*dy * sum of the xintp row sums.
-__global__ void k_inv_scalars(ScalArgs a) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(256) k_inv_scalars(ScalArgs a) {
+  __shared__ double red[8];
   qgcm_scalars *s = a.sc;
   const int nl = a.nl, nyp = a.nyp;
   const double ecrit = 1.0e-13;
   double xinhom[NLMAX], ayis[NLMAX], ayin[NLMAX];
+  double sums[NLMAX];
+  for (int m = 0; m < nl; ++m) sums[m] = block256_range_sum(a.rowsum + (size_t)m * nyp, 1, nyp - 1, red);
+  if (threadIdx.x != 0) return;
   for (int m = 0; m < nl; ++m) {
-    double sump = 0.0;
-    for (int j = 1; j < nyp - 1; ++j) sump = sump + a.rowsum[m * nyp + j];
+    const double sump = sums[m];
     xinhom[m] = sump * a.dx * a.dx;   // boundary rows are exactly zero
     ayis[m] = a.rowsum[m * nyp + 1];              // dx/dy = 1
     ayin[m] = -a.rowsum[m * nyp + nyp - 2];
@@ -270,7 +272,7 @@ static void invert(qgcm_model *m, bool atmos) {
   s.rowsum = hp.rowsum;
   s.sc = m->d_scal;
   s.coef = (double *)a.coef;
-  QG_LAUNCH(m, "k_inv_scalars", 1, 32, 0, k_inv_scalars, s);
+  QG_LAUNCH(m, "k_inv_scalars", 1, 256, 0, k_inv_scalars, s);
   dim3 gm((g.nxp + 255) / 256, g.nyp);
   QG_LAUNCH(m, "k_m2l", gm, 256, 0, k_m2l, a);
   QG_CUDA(cudaGetLastError());

@@ -259,11 +259,11 @@ __global__ void __launch_bounds__(256) k_oml_entoc(OmlArgs a) {
 }
 
 // xon(1) = dx*dy*xintp(entoc); channel: enisoc(1), eninoc(1) (omlsubs.F:214-233)
-__global__ void k_oml_finish(OmlArgs a, double dx) {
-  if (threadIdx.x != 0) return;
+__global__ void __launch_bounds__(256) k_oml_finish(OmlArgs a, double dx) {
+  __shared__ double red[8];
   const int nyp = a.g.nyp;
-  double sump = 0.0;
-  for (int j = 1; j < nyp - 1; ++j) sump += a.rowsum[j];
+  const double sump = block256_range_sum(a.rowsum, 1, nyp - 1, red);
+  if (threadIdx.x != 0) return;
   const double x = sump + 0.5 * (a.rowsum[0] + a.rowsum[nyp - 1]);
   a.sc->xon[0] = x * dx * dx;
   if (a.g.cyclic) {
@@ -338,7 +338,7 @@ void launch_oml(qgcm_model *m) {
   QG_LAUNCH(m, "k_oml_step", grid, 256, 0, k_oml_step, a);
   QG_LAUNCH(m, "k_oml_reduce", 1, 256, 0, k_oml_reduce, a, g.dx * g.dx);
   QG_LAUNCH(m, "k_oml_entoc", g.nyp, 256, 0, k_oml_entoc, a);
-  QG_LAUNCH(m, "k_oml_finish", 1, 32, 0, k_oml_finish, a, g.dx);
+  QG_LAUNCH(m, "k_oml_finish", 1, 256, 0, k_oml_finish, a, g.dx);
   QG_CUDA(cudaGetLastError());
   // sstm <- sst, sst <- new: three-buffer rotation (omlsubs.F:124-125)
   double *old_m = m->fields.at("sstm").d;

@@ -131,6 +131,26 @@ struct qgcm_model {
   void swapf(const char *a, const char *b) { std::swap(fields.at(a).d, fields.at(b).d); }
 };
 
+#ifdef __CUDACC__
+namespace qg {
+// deterministic sum of v[first..last) by one block of 256 threads (fixed strided partials,
+// fixed-order tree); every thread returns the total.  red: 8 doubles of shared memory.
+__device__ __forceinline__ double block256_range_sum(const double *v, int first, int last, double *red) {
+  double s = 0.0;
+  for (int i = first + threadIdx.x; i < last; i += 256) s += v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += red[i];
+  return t;
+}
+}  // namespace qg
+#endif
+
 namespace qg {
 
 void *dalloc(qgcm_model *m, size_t bytes);

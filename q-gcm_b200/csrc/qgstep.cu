@@ -11,10 +11,8 @@
 
 namespace qg {
 
-constexpr int TX = 64, TY = 14;          // output tile (46 KB of static shared memory)
-constexpr int PW = TX + 6, PH = TY + 6;  // pom tile (halo 3)
-constexpr int DW2 = TX + 4, DH2 = TY + 4;  // del2 tile (halo 2)
-constexpr int DW4 = TX + 2, DH4 = TY + 2;  // del4 / po / qo tiles (halo 1)
+constexpr int WOUT = 26;    // output columns per warp (32 lanes minus a halo of 3 each side)
+constexpr int RCH = 64;     // rows marched by one warp
 
 struct QgArgs {
   Grid g;
@@ -30,153 +28,121 @@ struct QgArgs {
   const double *wek, *ent;    // Ekman velocity and entrainment at p points
 };
 
-// canonical column for loads: periodic grids read column nxp as column 1
-__device__ __forceinline__ int wrapx(int i, int nxp, int cyclic) {
-  if (!cyclic) return i;
-  const int per = nxp - 1;
-  if (i < 0) i += per;
-  if (i >= per) i -= per;
-  return i;
-}
+__device__ __forceinline__ double shl(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }    // value of lane-1 (west)
+__device__ __forceinline__ double shr(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }  // value of lane+1 (east)
 
-__global__ void __launch_bounds__(256) k_qgstep(QgArgs a) {
-  __shared__ double s_pm[PH][PW];
-  __shared__ double s_d2[DH2][DW2];
-  __shared__ double s_d4[DH4][DW4];
-  __shared__ double s_p[DH4][DW4];
-  __shared__ double s_q[DH4][DW4];
+// Warp-marching stencil pipeline.  Each warp owns 32 consecutive columns (26 outputs +
+// halo 3) and marches north through RCH rows.  Every lane keeps its own column's last
+// three rows of pom, del2, del4, p and q in registers; east/west neighbours come from
+// warp shuffles, so the kernel uses no shared memory and no block barriers, and every
+// global access is a contiguous 256-byte row segment.
+__global__ void __launch_bounds__(128) k_qgstep(QgArgs a) {
   const Grid &g = a.g;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int k = blockIdx.z;
-  const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;   // 0-based origin of the output tile
+  const int wx = blockIdx.x * 4 + wib;
+  const int nxp = g.nxp, nyp = g.nyp, ld = g.ld, cyc = g.cyclic, per = nxp - 1;
+  if (wx * WOUT >= nxp) return;   // whole warp exits together
+  const int gi = wx * WOUT - 3 + lane;          // this lane's column (may be outside the domain)
+  int ci = gi;                                   // canonical column for loads
+  if (cyc) { if (ci < 0) ci += per; if (ci >= per) ci -= per; }
+  const bool incol = ci >= 0 && ci < nxp;
+  const bool wallW = !cyc && gi == 0, wallE = !cyc && gi == nxp - 1;
+  const bool outlane = lane >= 3 && lane < 3 + WOUT && gi < nxp;
+  const int ja = blockIdx.y * RCH, jb = min(nyp, ja + RCH);
   const size_t lo = (size_t)k * g.lsz;
-  const double *pm = a.pm + lo, *p = a.p + lo, *q = a.q + lo;
-  const int nxp = g.nxp, nyp = g.nyp, ld = g.ld, cyc = g.cyclic;
-  const int tid = threadIdx.x;
-
-  // ---- stage pom (halo 3), po and qo (halo 1); out-of-domain entries are never used
-  for (int e = tid; e < PH * PW; e += 256) {
-    const int ly = e / PW, lx = e - ly * PW;
-    const int gj = j0 + ly - 3;
-    int gi = i0 + lx - 3;
-    double v = 0.0;
-    if (gj >= 0 && gj < nyp) {
-      gi = wrapx(gi, nxp, cyc);
-      if (gi >= 0 && gi < nxp) v = pm[(size_t)gj * ld + gi];
-    }
-    s_pm[ly][lx] = v;
-  }
-  for (int e = tid; e < DH4 * DW4; e += 256) {
-    const int ly = e / DW4, lx = e - ly * DW4;
-    const int gj = j0 + ly - 1;
-    int gi = i0 + lx - 1;
-    double vp = 0.0, vq = 0.0;
-    if (gj >= 0 && gj < nyp) {
-      gi = wrapx(gi, nxp, cyc);
-      if (gi >= 0 && gi < nxp) {
-        vp = p[(size_t)gj * ld + gi];
-        vq = q[(size_t)gj * ld + gi];
-      }
-    }
-    s_p[ly][lx] = vp;
-    s_q[ly][lx] = vq;
-  }
-  __syncthreads();
-
-  // ---- del2 of pom on the halo-2 region (qgosubs.F:86-130 / qgasubs.F:74-100)
-  for (int e = tid; e < DH2 * DW2; e += 256) {
-    const int ly = e / DW2, lx = e - ly * DW2;
-    const int gj = j0 + ly - 2, gi = i0 + lx - 2;
-    const int py = ly + 1, px = lx + 1;   // position in s_pm
-    double v = 0.0;
-    if (gj >= 0 && gj < nyp && (cyc || (gi >= 0 && gi < nxp))) {
-      if (gj == 0)
-        v = a.bcfac * (s_pm[py + 1][px] - s_pm[py][px]);
-      else if (gj == nyp - 1)
-        v = a.bcfac * (s_pm[py - 1][px] - s_pm[py][px]);
-      else if (!cyc && gi == 0)
-        v = a.bcfac * (s_pm[py][px + 1] - s_pm[py][px]);
-      else if (!cyc && gi == nxp - 1)
-        v = a.bcfac * (s_pm[py][px - 1] - s_pm[py][px]);
-      else
-        v = (s_pm[py - 1][px] + s_pm[py][px - 1] + s_pm[py][px + 1] + s_pm[py + 1][px] - 4.0 * s_pm[py][px]) * g.dxm2;
-    }
-    s_d2[ly][lx] = v;
-  }
-  __syncthreads();
-  // ---- del4 on the halo-1 region (qgosubs.F:310-341 / qgasubs.F:218-237)
-  for (int e = tid; e < DH4 * DW4; e += 256) {
-    const int ly = e / DW4, lx = e - ly * DW4;
-    const int gj = j0 + ly - 1, gi = i0 + lx - 1;
-    const int py = ly + 1, px = lx + 1;   // position in s_d2
-    double v = 0.0;
-    if (gj >= 0 && gj < nyp && (cyc || (gi >= 0 && gi < nxp))) {
-      if (gj == 0)
-        v = a.bcfac * (s_d2[py + 1][px] - s_d2[py][px]);
-      else if (gj == nyp - 1)
-        v = a.bcfac * (s_d2[py - 1][px] - s_d2[py][px]);
-      else if (!cyc && gi == 0)
-        v = a.bcfac * (s_d2[py][px + 1] - s_d2[py][px]);
-      else if (!cyc && gi == nxp - 1)
-        v = a.bcfac * (s_d2[py][px - 1] - s_d2[py][px]);
-      else
-        v = g.dxm2 * (s_d2[py - 1][px] + s_d2[py][px - 1] + s_d2[py][px + 1] + s_d2[py + 1][px] - 4.0 * s_d2[py][px]);
-    }
-    s_d4[ly][lx] = v;
-  }
-  __syncthreads();
-
-  // ---- dq/dt, forcing, leapfrog (qgosubs.F:345-402, :184-219 / qgasubs.F:245-283, :115-146)
+  const double *__restrict__ pm = a.pm + lo + (incol ? ci : 0);
+  const double *__restrict__ p = a.p + lo + (incol ? ci : 0);
+  const double *__restrict__ q = a.q + lo + (incol ? ci : 0);
+  double *__restrict__ qm = a.qm + lo + (gi >= 0 && gi < nxp ? gi : 0);
+  const double *__restrict__ wek = a.wek + (incol ? ci : 0);
+  const double *__restrict__ ent = a.ent + (incol ? ci : 0);
+  const double dxm2 = g.dxm2, bcf = a.bcfac;
+  const double ah2f = a.ah2fac[k], ah4f = a.ah4fac[k], adf = a.adfac, tdt = g.tdt;
   const int nl = g.nl;
-  for (int e = tid; e < TY * TX; e += 256) {
-    const int ly = e / TX, lx = e - ly * TX;
-    const int gj = j0 + ly, gi = i0 + lx;
-    if (gj >= nyp || gi >= nxp) continue;
-    const size_t idx = (size_t)gj * ld + gi;
-    double *qm = a.qm + lo;
-    if (gj == 0 || gj == nyp - 1) {
+
+  double pm0 = 0, pm1 = 0, pm2 = 0, d2a = 0, d2b = 0, d2c = 0, d4a = 0, d4b = 0, d4c = 0;
+  double pA = 0, pB = 0, pC = 0, qA = 0, qB = 0, qC = 0;
+  // software pipeline: values for the next step are loaded one step ahead
+  const int r0 = ja - 3;
+  auto ld_pm = [&](int r) { return (incol && r >= 0 && r < nyp) ? pm[(size_t)r * ld] : 0.0; };
+  auto ld_p = [&](int r) { return (incol && r >= 0 && r < nyp) ? p[(size_t)r * ld] : 0.0; };
+  auto ld_q = [&](int r) { return (incol && r >= 0 && r < nyp) ? q[(size_t)r * ld] : 0.0; };
+  // prologue: rows needed before the first pipeline step
+  pm1 = ld_pm(r0 - 2);
+  pm2 = ld_pm(r0 - 1);
+  pB = ld_p(r0 - 4); pC = ld_p(r0 - 3);
+  qB = ld_q(r0 - 4); qC = ld_q(r0 - 3);
+  double npm = ld_pm(r0), np_ = ld_p(r0 - 2), nq = ld_q(r0 - 2);
+  for (int r = r0; r < jb + 3; ++r) {
+    pm0 = pm1; pm1 = pm2; pm2 = npm;
+    pA = pB; pB = pC; pC = np_;
+    qA = qB; qB = qC; qC = nq;
+    npm = ld_pm(r + 1); np_ = ld_p(r - 1); nq = ld_q(r - 1);
+    // ---- del2 at row r-1 (qgosubs.F:86-130 / qgasubs.F:74-100)
+    const int j2 = r - 1;
+    {
+      const double w = shl(pm1), e = shr(pm1);
+      double v;
+      if (j2 == 0) v = bcf * (pm2 - pm1);
+      else if (j2 == nyp - 1) v = bcf * (pm0 - pm1);
+      else if (wallW) v = bcf * (e - pm1);
+      else if (wallE) v = bcf * (w - pm1);
+      else v = (pm0 + w + e + pm2 - 4.0 * pm1) * dxm2;
+      d2a = d2b; d2b = d2c; d2c = v;
+    }
+    // ---- del4 at row r-2 (qgosubs.F:310-341 / qgasubs.F:218-237)
+    const int j4 = r - 2;
+    {
+      const double w = shl(d2b), e = shr(d2b);
+      double v;
+      if (j4 == 0) v = bcf * (d2c - d2b);
+      else if (j4 == nyp - 1) v = bcf * (d2a - d2b);
+      else if (wallW) v = bcf * (e - d2b);
+      else if (wallE) v = bcf * (w - d2b);
+      else v = dxm2 * (d2a + w + e + d2c - 4.0 * d2b);
+      d4a = d4b; d4b = d4c; d4c = v;
+    }
+    // ---- row r-3: del6, Jacobian, forcing, leapfrog
+    const int jo = r - 3;
+    const double d4w = shl(d4b), d4e = shr(d4b);
+    const double pAw = shl(pA), pAe = shr(pA), pBw = shl(pB), pBe = shr(pB), pCw = shl(pC), pCe = shr(pC);
+    const double qAw = shl(qA), qAe = shr(qA), qBw = shl(qB), qBe = shr(qB), qCw = shl(qC), qCe = shr(qC);
+    if (jo < ja || jo >= jb || !outlane) continue;
+    const size_t ro = (size_t)jo * ld;
+    if (jo == 0 || jo == nyp - 1) {
       // zonal boundary rows are not stepped: after the pointer rotation both time
       // levels hold the current boundary value (qgosubs.F:214-219)
-      qm[idx] = q[idx];
+      qm[ro] = qB;
       continue;
     }
-    const int y = ly + 1, x = lx + 1;   // position in the halo-1 tiles
     double dqdt;
-    if (!cyc && (gi == 0 || gi == nxp - 1)) {
+    if (wallW || wallE) {
       dqdt = 0.0;   // qgosubs.F:371, :397
     } else {
-      const double d6p = g.dxm2 * (s_d4[y - 1][x] + s_d4[y][x - 1] + s_d4[y][x + 1] + s_d4[y + 1][x] - 4.0 * s_d4[y][x]);
-#define Q(dx_, dy_) s_q[y + (dy_)][x + (dx_)]
-#define P(dx_, dy_) s_p[y + (dy_)][x + (dx_)]
-      const double jac = (Q(1, 0) - Q(-1, 0)) * (P(0, 1) - P(0, -1)) + (Q(0, -1) - Q(0, 1)) * (P(1, 0) - P(-1, 0)) +
-                         Q(1, 0) * (P(1, 1) - P(1, -1)) - Q(-1, 0) * (P(-1, 1) - P(-1, -1)) -
-                         Q(0, 1) * (P(1, 1) - P(-1, 1)) + Q(0, -1) * (P(1, -1) - P(-1, -1)) +
-                         P(0, 1) * (Q(1, 1) - Q(-1, 1)) - P(0, -1) * (Q(1, -1) - Q(-1, -1)) -
-                         P(1, 0) * (Q(1, 1) - Q(1, -1)) + P(-1, 0) * (Q(-1, 1) - Q(-1, -1));
-#undef Q
-#undef P
+      const double d6p = dxm2 * (d4a + d4w + d4e + d4c - 4.0 * d4b);
+      // rows A,B,C = j-1, j, j+1; suffix w/e = i-1, i+1 (qgosubs.F:376-388)
+      const double jac = (qBe - qBw) * (pC - pA) + (qA - qC) * (pBe - pBw) + qBe * (pCe - pAe) - qBw * (pCw - pAw) -
+                         qC * (pCe - pCw) + qA * (pAe - pAw) + pC * (qCe - qCw) - pA * (qAe - qAw) -
+                         pBe * (qCe - qAe) + pBw * (qCw - qAw);
       if (a.atmos) {
-        dqdt = a.adfac * jac - a.ah4fac[k] * d6p;
+        dqdt = adf * jac - ah4f * d6p;
       } else {
-        const double diffus = a.ah2fac[k] * s_d4[y][x] - a.ah4fac[k] * d6p;
-        dqdt = a.adfac * jac + diffus;
+        const double diffus = ah2f * d4b - ah4f * d6p;
+        dqdt = adf * jac + diffus;
       }
     }
-    // layer-specific forcing; columns read through the canonical map so periodic
-    // copies stay bit-identical
-    const int ci = wrapx(gi, nxp, cyc);
-    const size_t cidx = (size_t)gj * ld + ci;
     double qdot = dqdt;
     if (a.atmos) {
-      if (k == 0) qdot = dqdt + a.fohfac[0] * (a.ent[cidx] - a.wek[cidx]);
-      if (k == 1) qdot = dqdt - a.fohfac[1] * a.ent[cidx];
+      if (k == 0) qdot = dqdt + a.fohfac[0] * (ent[ro] - wek[ro]);
+      if (k == 1) qdot = dqdt - a.fohfac[1] * ent[ro];
     } else {
-      if (k == 0) qdot = dqdt + a.fohfac[0] * (a.wek[cidx] - a.ent[cidx]);
-      if (k == 1) qdot = dqdt + a.fohfac[1] * a.ent[cidx];
-      if (k == nl - 1) qdot = qdot - a.bdrfac * s_d2[y + 1][x + 1];
+      if (k == 0) qdot = dqdt + a.fohfac[0] * (wek[ro] - ent[ro]);
+      if (k == 1) qdot = dqdt + a.fohfac[1] * ent[ro];
+      if (k == nl - 1) qdot = qdot - a.bdrfac * d2a;   // d2a = del2p(i, jo) after the shifts above
     }
-    // qm is updated in place: read only this thread's own element (another block
-    // owns column 1, so the periodic copy must not be read through the canonical map)
-    qm[idx] = qm[idx] + g.tdt * qdot;
+    // qm is updated in place; each element is read and written by exactly one lane
+    qm[ro] = qm[ro] + tdt * qdot;
   }
 }
 
@@ -319,8 +285,9 @@ static void launch(qgcm_model *m, bool atmos) {
     s.pm = a.pm; s.p = a.p; s.q = a.q;
     QG_LAUNCH(m, "k_strips", dim3(g.nl, 2), 256, 0, k_strips, s);
   }
-  dim3 grid((g.nxp + TX - 1) / TX, (g.nyp + TY - 1) / TY, g.nl);
-  QG_LAUNCH(m, "k_qgstep", grid, 256, 0, k_qgstep, a);
+  const int nwx = (g.nxp + WOUT - 1) / WOUT;
+  dim3 grid((nwx + 3) / 4, (g.nyp + RCH - 1) / RCH, g.nl);
+  QG_LAUNCH(m, "k_qgstep", grid, 128, 0, k_qgstep, a);
   QG_CUDA(cudaGetLastError());
   m->swapf(nq, nqm);   // new q lives in the old qom buffer; old q becomes qom
 }
