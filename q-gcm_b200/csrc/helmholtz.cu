@@ -24,11 +24,18 @@ namespace qg {
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+  return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
 }
 __device__ __forceinline__ double2 cmulmi(double2 a) { return make_double2(a.y, -a.x); }  // a * (-i)
 __device__ __forceinline__ double2 cscale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
 __device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+
+// Internal twiddles W_R^{n2*k1} of the two-level (Cooley-Tukey) in-register butterflies,
+// filled by helm_plan_create.  Uniform index across a warp => constant-cache broadcast.
+__constant__ double2 c_ctw[160];
+__host__ __device__ constexpr int ctw_off(int R) {
+  return R == 6 ? 0 : R == 9 ? 6 : R == 10 ? 15 : R == 12 ? 25 : R == 15 ? 37 : R == 16 ? 52 : R == 20 ? 68 : R == 25 ? 88 : 113;
+}
 
 template <int R>
 __device__ __forceinline__ void dft(double2 *v);
@@ -76,7 +83,6 @@ __device__ __forceinline__ void dft<5>(double2 *v) {
 template <>
 __device__ __forceinline__ void dft<8>(double2 *v) {
   const double h = 0.70710678118654752440;
-  // three radix-2 stages (decimation in time on the 8 inputs)
   double2 e[4] = {v[0], v[2], v[4], v[6]};
   double2 o[4] = {v[1], v[3], v[5], v[7]};
   dft<4>(e);
@@ -94,25 +100,55 @@ __device__ __forceinline__ void dft<8>(double2 *v) {
   v[7] = csub(e[3], w3);
 }
 
+// R = RA*RB point DFT in registers: RB sub-DFTs of length RA over n1 (n = n1*RB + n2),
+// constant twiddles W_R^{n2 k1}, then RA sub-DFTs of length RB; output k = k1 + RA*k2.
+template <int RA, int RB>
+__device__ __forceinline__ void dft_ct(double2 *v) {
+  constexpr int R = RA * RB;
+  double2 y[R];
+#pragma unroll
+  for (int n2 = 0; n2 < RB; ++n2) {
+    double2 t[RA];
+#pragma unroll
+    for (int n1 = 0; n1 < RA; ++n1) t[n1] = v[n1 * RB + n2];
+    dft<RA>(t);
+#pragma unroll
+    for (int k1 = 0; k1 < RA; ++k1)
+      y[k1 * RB + n2] = (n2 == 0 || k1 == 0) ? t[k1] : cmul(t[k1], c_ctw[ctw_off(R) + k1 * RB + n2]);
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < RA; ++k1) {
+    double2 t[RB];
+#pragma unroll
+    for (int n2 = 0; n2 < RB; ++n2) t[n2] = y[k1 * RB + n2];
+    dft<RB>(t);
+#pragma unroll
+    for (int k2 = 0; k2 < RB; ++k2) v[k1 + RA * k2] = t[k2];
+  }
+}
+template <> __device__ __forceinline__ void dft<6>(double2 *v) { dft_ct<2, 3>(v); }
+template <> __device__ __forceinline__ void dft<9>(double2 *v) { dft_ct<3, 3>(v); }
+template <> __device__ __forceinline__ void dft<10>(double2 *v) { dft_ct<2, 5>(v); }
+template <> __device__ __forceinline__ void dft<12>(double2 *v) { dft_ct<4, 3>(v); }
+template <> __device__ __forceinline__ void dft<15>(double2 *v) { dft_ct<3, 5>(v); }
+template <> __device__ __forceinline__ void dft<16>(double2 *v) { dft_ct<4, 4>(v); }
+
 // One Stockham pass of radix R over the complex array `in` (length M) into `out`.
-// Ns = product of the radices of the previous passes.
+// Ns = product of the radices of the previous passes; tw = this pass's twiddle table,
+// laid out [r-1][k] so that consecutive lanes read consecutive entries.
 template <int R>
 __device__ __forceinline__ void fft_pass(const double2 *__restrict__ in, double2 *__restrict__ out, int M, int Ns,
-                                         const double2 *__restrict__ wm) {
+                                         const double2 *__restrict__ tw) {
   const int L = M / R;
-  const int tws = M / (Ns * R);
   for (int j = threadIdx.x; j < L; j += blockDim.x) {
-    const int k = j % Ns;
+    const int k = (Ns == 1) ? 0 : j % Ns;
     const int j0 = (j - k) * R + k;
     double2 v[R];
-    v[0] = in[j];
-    if (Ns == 1) {
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[r] = in[j + r * L];
-    } else {
-      const int tw = k * tws;
+    for (int r = 0; r < R; ++r) v[r] = in[j + r * L];
+    if (Ns > 1) {
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[r] = cmul(in[j + r * L], __ldg(&wm[r * tw]));
+      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], __ldg(&tw[(r - 1) * Ns + k]));
     }
     dft<R>(v);
 #pragma unroll
@@ -122,8 +158,9 @@ __device__ __forceinline__ void fft_pass(const double2 *__restrict__ in, double2
 
 struct FftDev {
   int n, m, nrad;
-  int radix[16];
-  const double2 *wm, *wn;
+  int radix[8];
+  int twoff[8];           // offset of each pass's twiddle table in tw
+  const double2 *tw, *wn;
   const double *sintw;
 };
 
@@ -132,12 +169,19 @@ __device__ __forceinline__ double2 *cfft_smem(const FftDev &p, double2 *a, doubl
   int Ns = 1;
   for (int s = 0; s < p.nrad; ++s) {
     const int R = p.radix[s];
+    const double2 *tw = p.tw + p.twoff[s];
     switch (R) {
-      case 2: fft_pass<2>(a, b, p.m, Ns, p.wm); break;
-      case 3: fft_pass<3>(a, b, p.m, Ns, p.wm); break;
-      case 4: fft_pass<4>(a, b, p.m, Ns, p.wm); break;
-      case 5: fft_pass<5>(a, b, p.m, Ns, p.wm); break;
-      default: fft_pass<8>(a, b, p.m, Ns, p.wm); break;
+      case 2: fft_pass<2>(a, b, p.m, Ns, tw); break;
+      case 3: fft_pass<3>(a, b, p.m, Ns, tw); break;
+      case 4: fft_pass<4>(a, b, p.m, Ns, tw); break;
+      case 5: fft_pass<5>(a, b, p.m, Ns, tw); break;
+      case 6: fft_pass<6>(a, b, p.m, Ns, tw); break;
+      case 8: fft_pass<8>(a, b, p.m, Ns, tw); break;
+      case 9: fft_pass<9>(a, b, p.m, Ns, tw); break;
+      case 10: fft_pass<10>(a, b, p.m, Ns, tw); break;
+      case 12: fft_pass<12>(a, b, p.m, Ns, tw); break;
+      case 15: fft_pass<15>(a, b, p.m, Ns, tw); break;
+      default: fft_pass<16>(a, b, p.m, Ns, tw); break;
     }
     __syncthreads();
     double2 *t = a;
@@ -182,43 +226,55 @@ __device__ __forceinline__ double corrected(const XfArgs &a, int mode, int r, in
     const int c = r / TRI_L, jl = r - c * TRI_L;
     const size_t tb = ((size_t)mode * TRI_L) * a.ld;
     const size_t yb = ((size_t)mode * 2 * a.nchunk) * a.ld;
-    const double yp = a.yx[yb + (size_t)c * a.ld + col];
-    const double xn = a.yx[yb + (size_t)(a.nchunk + c) * a.ld + col];
-    const double vleft = (c == a.nchunk - 1) ? a.vll[tb + (size_t)jl * a.ld + col] : a.vl[tb + (size_t)jl * a.ld + col];
-    const double vright = a.vl[tb + (size_t)(TRI_L - 1 - jl) * a.ld + col];
+    const double yp = __ldg(&a.yx[yb + (size_t)c * a.ld + col]);
+    const double xn = __ldg(&a.yx[yb + (size_t)(a.nchunk + c) * a.ld + col]);
+    const double *vlt = (c == a.nchunk - 1) ? a.vll : a.vl;
+    const double vleft = __ldg(&vlt[tb + (size_t)jl * a.ld + col]);
+    const double vright = __ldg(&a.vl[tb + (size_t)(TRI_L - 1 - jl) * a.ld + col]);
     u0 = u0 + yp * vleft + xn * vright;
   }
   return a.ftnorm * u0;
 }
 
-// grid (nrows, nmodes); dynamic smem = 2*n doubles*... (two complex buffers of length m) + 64 doubles
-__global__ void __launch_bounds__(256) k_xform(XfArgs a) {
+// F_k of the length-n real transform from the half-length complex transform Z (n = 2m):
+// F_k = (Z_k + conj Z_{m-k})/2 - (i/2) e^{-2 pi i k/n} (Z_k - conj Z_{m-k})
+__device__ __forceinline__ double2 real_post(double2 za, double2 zmk, double2 w) {
+  const double2 zb = cconj(zmk);
+  const double2 e = cscale(cadd(za, zb), 0.5);
+  const double2 o = cmul(cscale(cmulmi(csub(za, zb)), 0.5), w);
+  return cadd(e, o);
+}
+
+// grid (nrows, nmodes); dynamic smem: two complex buffers of length m, then 40 doubles
+__global__ void __launch_bounds__(256, 2) k_xform(XfArgs a) {
   extern __shared__ double2 smem2[];
   const int N = a.f.n, M = a.f.m;
   double2 *A = smem2, *B = smem2 + M;
   double *red = reinterpret_cast<double *>(smem2 + 2 * M);
   const int r = blockIdx.x;            // interior row index, j = r + 2
   const int mode = blockIdx.y;
-  double *row = a.wrk + (size_t)mode * a.lsz + (size_t)(r + 1) * a.ld;
-  double *Ar = reinterpret_cast<double *>(A), *Br = reinterpret_cast<double *>(B);
+  double *__restrict__ row = a.wrk + (size_t)mode * a.lsz + (size_t)(r + 1) * a.ld;
+  double *Ar = reinterpret_cast<double *>(A);
   const int T = blockDim.x, t = threadIdx.x;
+  const int lane = t & 31, w = t >> 5, nw = T >> 5;
 
   if (a.kind == 0) {
     // ---------------- DST-I of row(2:nxto), dsint.f:17-43 ----------------
-    for (int k = t + 1; k < N; k += T) {
-      double x = row[k];
-      if (a.inverse) x = corrected(a, mode, r, k, x);
-      Br[k] = x;
-    }
-    __syncthreads();
+    // load + pre-processing fused: t_k = (x_k - x_{N-k}) + 2 sin(k pi/N)(x_k + x_{N-k})
     for (int k = t; k <= M; k += T) {
       if (k == 0) {
         Ar[0] = 0.0;
       } else if (k == M) {
-        Ar[M] = 4.0 * Br[M];
+        double x = row[M];
+        if (a.inverse) x = corrected(a, mode, r, M, x);
+        Ar[M] = 4.0 * x;
       } else {
-        const double xa = Br[k], xb = Br[N - k];
-        const double t1 = xa - xb, t2 = a.f.sintw[k] * (xa + xb);
+        double xa = row[k], xb = row[N - k];
+        if (a.inverse) {
+          xa = corrected(a, mode, r, k, xa);
+          xb = corrected(a, mode, r, N - k, xb);
+        }
+        const double t1 = xa - xb, t2 = __ldg(&a.f.sintw[k]) * (xa + xb);
         Ar[k] = t1 + t2;
         Ar[N - k] = t2 - t1;
       }
@@ -226,50 +282,56 @@ __global__ void __launch_bounds__(256) k_xform(XfArgs a) {
     __syncthreads();
     double2 *Z = cfft_smem(a.f, A, B);
     double2 *O = (Z == A) ? B : A;
-    // real post-processing: F_k, k = 0..M-1 (F_M is not needed by the sine transform)
-    for (int k = t; k < M; k += T) {
-      double2 F;
+    double *Or = reinterpret_cast<double *>(O);
+    // real post-processing for the pair (k, M-k); even outputs out_{2k} = -Im F_k go to
+    // Or[2k], Re F_k (the summand of the odd outputs) is parked in Or[2k+1]
+    for (int k = t; k <= M / 2; k += T) {
       if (k == 0) {
-        F = make_double2(Z[0].x + Z[0].y, 0.0);
+        Or[1] = 0.5 * (Z[0].x + Z[0].y);          // out_1 = F_0 / 2
       } else {
-        const double2 za = Z[k], zb = cconj(Z[M - k]);
-        const double2 e = cscale(cadd(za, zb), 0.5);
-        const double2 o = cmul(cscale(cmulmi(csub(za, zb)), 0.5), a.f.wn[k]);
-        F = cadd(e, o);
+        const double2 za = Z[k], zb = Z[M - k];
+        const double2 Fa = real_post(za, zb, __ldg(&a.f.wn[k]));
+        Or[2 * k] = -Fa.y;
+        Or[2 * k + 1] = Fa.x;
+        if (k != M - k) {
+          const double2 Fb = real_post(zb, za, __ldg(&a.f.wn[M - k]));
+          Or[2 * (M - k)] = -Fb.y;
+          Or[2 * (M - k) + 1] = Fb.x;
+        }
       }
-      O[k] = F;
     }
     __syncthreads();
-    // odd outputs are a running sum of Re F (dsint.f:33-37): chunked block scan
-    double *Or = reinterpret_cast<double *>(O);   // Re F_k at Or[2k], Im F_k at Or[2k+1]
-    double *Zr = reinterpret_cast<double *>(Z);   // output array out[1..N-1]
-    const int per = (M + T - 1) / T;
-    const int k0 = t * per, k1 = min(M, k0 + per);
-    double loc = 0.0;
-    for (int k = k0; k < k1; ++k) loc += (k == 0) ? 0.5 * Or[0] : Or[2 * k];
-    // exclusive scan of per-thread totals
-    const int lane = t & 31, w = t >> 5, nw = (T + 31) >> 5;
-    double inc = loc;
+    // odd outputs are a running sum (dsint.f:33-37): out_{2k+1} = sum_{l<=k} Or[2l+1].
+    // Each warp scans a contiguous segment 32 elements at a time, then adds the offset
+    // of the preceding segments.
+    const int seg = (M + nw - 1) / nw;
+    const int s0 = w * seg, s1 = min(M, s0 + seg);
+    double carry = 0.0;
+    for (int base = s0; base < s1; base += 32) {
+      const int k = base + lane;
+      double v = (k < s1) ? Or[2 * k + 1] : 0.0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      double nb = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += nb;
+      for (int o = 1; o < 32; o <<= 1) {
+        const double nb = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += nb;
+      }
+      v += carry;
+      if (k < s1) Or[2 * k + 1] = v;
+      carry = __shfl_sync(0xffffffffu, v, 31);
     }
-    if (lane == 31) red[w] = inc;
+    if (lane == 0) red[w] = carry;
     __syncthreads();
-    double woff = 0.0;
-    for (int i = 0; i < w; ++i) woff += red[i];
-    (void)nw;
-    double run = woff + inc - loc;
-    for (int k = k0; k < k1; ++k) {
-      run += (k == 0) ? 0.5 * Or[0] : Or[2 * k];
-      Zr[2 * k + 1] = run;                      // out_{2k+1}
-      if (k >= 1) Zr[2 * k] = -Or[2 * k + 1];   // out_{2k} = -Im F_k
+    double off = 0.0;
+    for (int i = 0; i < w; ++i) off += red[i];
+    __syncthreads();
+    for (int base = s0; base < s1; base += 32) {
+      const int k = base + lane;
+      if (k < s1) Or[2 * k + 1] += off;
     }
     __syncthreads();
     double part = 0.0;
     for (int k = t + 1; k < N; k += T) {
-      const double v = Zr[k];
+      const double v = Or[k];
       row[k] = v;
       part += v;
     }
@@ -286,22 +348,29 @@ __global__ void __launch_bounds__(256) k_xform(XfArgs a) {
     for (int k = t; k < N; k += T) Ar[k] = row[k];
     __syncthreads();
     double2 *Z = cfft_smem(a.f, A, B);
-    for (int k = t; k <= M; k += T) {
+    double2 *O = (Z == A) ? B : A;
+    double *Or = reinterpret_cast<double *>(O);
+    for (int k = t; k <= M / 2; k += T) {
       if (k == 0) {
-        row[0] = Z[0].x + Z[0].y;
-      } else if (k == M) {
-        row[N - 1] = Z[0].x - Z[0].y;
+        Or[0] = Z[0].x + Z[0].y;
+        Or[N - 1] = Z[0].x - Z[0].y;
       } else {
-        const double2 za = Z[k], zb = cconj(Z[M - k]);
-        const double2 e = cscale(cadd(za, zb), 0.5);
-        const double2 o = cmul(cscale(cmulmi(csub(za, zb)), 0.5), a.f.wn[k]);
-        const double2 F = cadd(e, o);
-        row[2 * k - 1] = F.x;
-        row[2 * k] = F.y;
+        const double2 za = Z[k], zb = Z[M - k];
+        const double2 Fa = real_post(za, zb, __ldg(&a.f.wn[k]));
+        Or[2 * k - 1] = Fa.x;
+        Or[2 * k] = Fa.y;
+        if (k != M - k) {
+          const double2 Fb = real_post(zb, za, __ldg(&a.f.wn[M - k]));
+          Or[2 * (M - k) - 1] = Fb.x;
+          Or[2 * (M - k)] = Fb.y;
+        }
       }
     }
+    __syncthreads();
+    for (int k = t; k < N; k += T) row[k] = Or[k];
   } else {
     // ---------------- inverse real FFT (drfftb), then periodic wrap ----------------
+    double *Br = reinterpret_cast<double *>(B);
     for (int k = t; k < N; k += T) Br[k] = corrected(a, mode, r, k, row[k]);
     __syncthreads();
     for (int k = t; k < M; k += T) {
@@ -315,24 +384,24 @@ __global__ void __launch_bounds__(256) k_xform(XfArgs a) {
       }
       const double2 e = cadd(xa, xb);
       const double2 d = csub(xa, xb);
-      const double2 wc = cconj(a.f.wn[k]);
-      const double2 dw = cmul(d, wc);
+      const double2 dw = cmul(d, cconj(__ldg(&a.f.wn[k])));
       const double2 o = make_double2(-dw.y, dw.x);   // i * dw
       A[k] = cconj(cadd(e, o));
     }
     __syncthreads();
     double2 *Z = cfft_smem(a.f, A, B);
+    const double *Zr = reinterpret_cast<const double *>(Z);
+    // x_{2n} = Re Z_n, x_{2n+1} = -Im Z_n: the buffer is the output up to the sign of odd entries
     double part = 0.0;
-    for (int k = t; k < M; k += T) {
-      const double v0 = Z[k].x, v1 = -Z[k].y;
-      row[2 * k] = v0;
-      row[2 * k + 1] = v1;
-      part += (k == 0) ? v1 : (v0 + v1);   // x_0 is added below with its two half weights
+    for (int k = t; k < N; k += T) {
+      const double v = (k & 1) ? -Zr[k] : Zr[k];
+      row[k] = v;
+      if (k > 0) part += v;
     }
-    if (t == 0) row[a.nxp - 1] = Z[0].x;
-    double s = block_sum(part, red);
+    if (t == 0) row[a.nxp - 1] = Zr[0];
+    const double s = block_sum(part, red);
     // xintp row sum: 0.5*v(1) + sum_{2}^{nxp-1} + 0.5*v(nxp), v(nxp) = v(1)
-    if (t == 0) a.rowsum[(size_t)mode * a.nyp + (r + 1)] = 0.5 * Z[0].x + s + 0.5 * Z[0].x;
+    if (t == 0) a.rowsum[(size_t)mode * a.nyp + (r + 1)] = 0.5 * Zr[0] + s + 0.5 * Zr[0];
   }
 }
 
@@ -483,15 +552,23 @@ __global__ void k_zero_rows(double *wrk, size_t lsz, int ld, int nyp, int nxp, i
 // --------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------
+// Radix plan: an odd radix first (its stride-R shared-memory scatter is conflict-free while
+// Ns = 1), then the largest radices that divide what is left: three passes for every
+// benchmark length (2400 = 15*16*10, 1200 = 15*16*5, 480 = 15*16*2, 2304 = 9*16*16).
 static bool factorize(int m, int *radix, int &nrad) {
   nrad = 0;
-  // odd radices first (conflict-free shared-memory scatter while Ns is small), then 8/4/2
-  while (m % 5 == 0) { radix[nrad++] = 5; m /= 5; }
-  while (m % 3 == 0) { radix[nrad++] = 3; m /= 3; }
-  while (m % 8 == 0) { radix[nrad++] = 8; m /= 8; }
-  while (m % 4 == 0) { radix[nrad++] = 4; m /= 4; }
-  while (m % 2 == 0) { radix[nrad++] = 2; m /= 2; }
-  return m == 1 && nrad <= 16;
+  const int odd[4] = {15, 9, 5, 3};
+  for (int i = 0; i < 4; ++i)
+    if (m % odd[i] == 0) { radix[nrad++] = odd[i]; m /= odd[i]; break; }
+  const int rest[11] = {16, 10, 12, 8, 6, 9, 5, 4, 3, 2, 0};
+  while (m > 1 && nrad < 8) {
+    int i = 0;
+    while (rest[i] && m % rest[i] != 0) ++i;
+    if (!rest[i]) return false;
+    radix[nrad++] = rest[i];
+    m /= rest[i];
+  }
+  return m == 1;
 }
 
 void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, const double *rdm2, int nmodes) {
@@ -514,22 +591,48 @@ void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, con
   hp.ftnorm = kind == 0 ? 0.5 / hp.n : 1.0 / hp.n;
   hp.smem_bytes = (size_t)2 * hp.m * sizeof(double2) + 64 * sizeof(double);
   // twiddles in extended precision, rounded once
-  std::vector<double2> wm(hp.m), wn(hp.m + 1);
+  std::vector<double2> wm, wn(hp.m + 1);
   std::vector<double> sw(hp.m);
   const long double PI_L = 3.141592653589793238462643383279502884L;
-  for (int k = 0; k < hp.m; ++k) {
-    long double a = -2.0L * PI_L * k / hp.m;
-    wm[k] = make_double2((double)cosl(a), (double)sinl(a));
-    sw[k] = (double)(2.0L * sinl(PI_L * k / hp.n));
+  for (int k = 0; k < hp.m; ++k) sw[k] = (double)(2.0L * sinl(PI_L * k / hp.n));
+  // per-pass twiddle tables exp(-2 pi i r k / (Ns R)), laid out [r-1][k]
+  {
+    int Ns = 1;
+    for (int s = 0; s < hp.nrad; ++s) {
+      const int R = hp.radix[s];
+      hp.twoff[s] = (int)wm.size();
+      if (Ns > 1)
+        for (int r = 1; r < R; ++r)
+          for (int k = 0; k < Ns; ++k) {
+            long double a = -2.0L * PI_L * (long double)r * k / ((long double)Ns * R);
+            wm.push_back(make_double2((double)cosl(a), (double)sinl(a)));
+          }
+      Ns *= R;
+    }
+    if (wm.empty()) wm.push_back(make_double2(1.0, 0.0));
+  }
+  // constant internal twiddles of the compound butterflies
+  {
+    std::vector<double2> ct(160, make_double2(1.0, 0.0));
+    const int comp[8][2] = {{2, 3}, {3, 3}, {2, 5}, {4, 3}, {3, 5}, {4, 4}, {4, 5}, {5, 5}};
+    for (int c = 0; c < 8; ++c) {
+      const int RA = comp[c][0], RB = comp[c][1], R = RA * RB;
+      for (int k1 = 0; k1 < RA; ++k1)
+        for (int n2 = 0; n2 < RB; ++n2) {
+          long double a = -2.0L * PI_L * (long double)(n2 * k1) / R;
+          ct[ctw_off(R) + k1 * RB + n2] = make_double2((double)cosl(a), (double)sinl(a));
+        }
+    }
+    QG_CUDA(cudaMemcpyToSymbol(c_ctw, ct.data(), sizeof(double2) * 160));
   }
   for (int k = 0; k <= hp.m; ++k) {
     long double a = -2.0L * PI_L * k / hp.n;
     wn[k] = make_double2((double)cosl(a), (double)sinl(a));
   }
-  hp.wm = (double2 *)dalloc(md, sizeof(double2) * hp.m);
+  hp.wm = (double2 *)dalloc(md, sizeof(double2) * wm.size());
   hp.wn = (double2 *)dalloc(md, sizeof(double2) * (hp.m + 1));
   hp.sintw = (double *)dalloc(md, sizeof(double) * hp.m);
-  QG_CUDA(cudaMemcpy(hp.wm, wm.data(), sizeof(double2) * hp.m, cudaMemcpyHostToDevice));
+  QG_CUDA(cudaMemcpy(hp.wm, wm.data(), sizeof(double2) * wm.size(), cudaMemcpyHostToDevice));
   QG_CUDA(cudaMemcpy(hp.wn, wn.data(), sizeof(double2) * (hp.m + 1), cudaMemcpyHostToDevice));
   QG_CUDA(cudaMemcpy(hp.sintw, sw.data(), sizeof(double) * hp.m, cudaMemcpyHostToDevice));
   const size_t row = (size_t)hp.ld;
@@ -592,8 +695,8 @@ void helm_solve(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
   const size_t lsz = (size_t)hp.ld * hp.nyp;
   XfArgs x;
   x.f.n = hp.n; x.f.m = hp.m; x.f.nrad = hp.nrad;
-  for (int i = 0; i < 16; ++i) x.f.radix[i] = hp.radix[i];
-  x.f.wm = hp.wm; x.f.wn = hp.wn; x.f.sintw = hp.sintw;
+  for (int i = 0; i < 8; ++i) { x.f.radix[i] = hp.radix[i]; x.f.twoff[i] = hp.twoff[i]; }
+  x.f.tw = hp.wm; x.f.wn = hp.wn; x.f.sintw = hp.sintw;
   x.kind = hp.kind; x.inverse = 0; x.ld = hp.ld; x.nyp = hp.nyp; x.nxp = hp.nxp; x.lsz = lsz;
   x.nchunk = hp.nchunk; x.lastlen = hp.lastlen; x.ftnorm = hp.ftnorm; x.wrk = wrk;
   x.vl = hp.vl; x.vll = hp.vll; x.yx = hp.yx; x.rowsum = hp.rowsum;

@@ -59,7 +59,8 @@ struct HelmPlan {
   int n;             // real transform length (= nxt)
   int m;             // complex length n/2
   int nrad;
-  int radix[16];
+  int radix[8];
+  int twoff[8];     // per-pass twiddle table offsets
   int nmodes;        // batch (number of vertical modes)
   int ld, nyp, nxp;
   int nrows;         // interior rows nyp-2

@@ -31,18 +31,32 @@ struct QgArgs {
 __device__ __forceinline__ double shl(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }    // value of lane-1 (west)
 __device__ __forceinline__ double shr(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }  // value of lane+1 (east)
 
+constexpr int QG_D = 6;     // cp.async pipeline depth (row stages in flight per warp)
+constexpr int QG_NF = 6;    // fields per stage: pom, p, q, qm, wek, ent
+
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 // Warp-marching stencil pipeline.  Each warp owns 32 consecutive columns (26 outputs +
 // halo 3) and marches north through RCH rows.  Every lane keeps its own column's last
 // three rows of pom, del2, del4, p and q in registers; east/west neighbours come from
-// warp shuffles, so the kernel uses no shared memory and no block barriers, and every
-// global access is a contiguous 256-byte row segment.
+// warp shuffles (no block barriers), and the rows ahead are prefetched QG_D deep with
+// cp.async into a per-warp shared-memory ring in which each lane only ever touches its
+// own slots.  Every global access is a contiguous 256-byte row segment.
 __global__ void __launch_bounds__(128) k_qgstep(QgArgs a) {
+  extern __shared__ double ring_all[];
   const Grid &g = a.g;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int k = blockIdx.z;
   const int wx = blockIdx.x * 4 + wib;
   const int nxp = g.nxp, nyp = g.nyp, ld = g.ld, cyc = g.cyclic, per = nxp - 1;
   if (wx * WOUT >= nxp) return;   // whole warp exits together
+  double *ring = ring_all + (size_t)wib * (QG_D * QG_NF * 32) + lane;   // [stage][field] at stride 32
   const int gi = wx * WOUT - 3 + lane;          // this lane's column (may be outside the domain)
   int ci = gi;                                   // canonical column for loads
   if (cyc) { if (ci < 0) ci += per; if (ci >= per) ci -= per; }
@@ -51,34 +65,50 @@ __global__ void __launch_bounds__(128) k_qgstep(QgArgs a) {
   const bool outlane = lane >= 3 && lane < 3 + WOUT && gi < nxp;
   const int ja = blockIdx.y * RCH, jb = min(nyp, ja + RCH);
   const size_t lo = (size_t)k * g.lsz;
-  const double *__restrict__ pm = a.pm + lo + (incol ? ci : 0);
-  const double *__restrict__ p = a.p + lo + (incol ? ci : 0);
-  const double *__restrict__ q = a.q + lo + (incol ? ci : 0);
+  const int cc = incol ? ci : 0;
+  const double *__restrict__ pm = a.pm + lo + cc;
+  const double *__restrict__ p = a.p + lo + cc;
+  const double *__restrict__ q = a.q + lo + cc;
   double *__restrict__ qm = a.qm + lo + (gi >= 0 && gi < nxp ? gi : 0);
-  const double *__restrict__ wek = a.wek + (incol ? ci : 0);
-  const double *__restrict__ ent = a.ent + (incol ? ci : 0);
+  const double *__restrict__ wek = a.wek + cc;
+  const double *__restrict__ ent = a.ent + cc;
   const double dxm2 = g.dxm2, bcf = a.bcfac;
   const double ah2f = a.ah2fac[k], ah4f = a.ah4fac[k], adf = a.adfac, tdt = g.tdt;
   const int nl = g.nl;
+  const bool forced = k < 2;
+
+  // stage r carries pom(r), p(r-2), q(r-2), qm(r-3), wek(r-3), ent(r-3); rows outside the
+  // domain are clamped (their values only reach results that are never used)
+  auto issue = [&](int r) {
+    double *slot = ring + (size_t)((r + 8 * QG_D) % QG_D) * (QG_NF * 32);
+    const int r0c = min(max(r, 0), nyp - 1), r2c = min(max(r - 2, 0), nyp - 1), r3c = min(max(r - 3, 0), nyp - 1);
+    cp_async8(slot, pm + (size_t)r0c * ld);
+    cp_async8(slot + 32, p + (size_t)r2c * ld);
+    cp_async8(slot + 64, q + (size_t)r2c * ld);
+    cp_async8(slot + 96, qm + (size_t)r3c * ld);
+    if (forced) {
+      cp_async8(slot + 128, wek + (size_t)r3c * ld);
+      cp_async8(slot + 160, ent + (size_t)r3c * ld);
+    }
+    cp_async_commit();
+  };
 
   double pm0 = 0, pm1 = 0, pm2 = 0, d2a = 0, d2b = 0, d2c = 0, d4a = 0, d4b = 0, d4c = 0;
   double pA = 0, pB = 0, pC = 0, qA = 0, qB = 0, qC = 0;
-  // software pipeline: values for the next step are loaded one step ahead
+  double pAw = 0, pAe = 0, pBw = 0, pBe = 0, pCw = 0, pCe = 0, qAw = 0, qAe = 0, qBw = 0, qBe = 0, qCw = 0, qCe = 0;
   const int r0 = ja - 3;
-  auto ld_pm = [&](int r) { return (incol && r >= 0 && r < nyp) ? pm[(size_t)r * ld] : 0.0; };
-  auto ld_p = [&](int r) { return (incol && r >= 0 && r < nyp) ? p[(size_t)r * ld] : 0.0; };
-  auto ld_q = [&](int r) { return (incol && r >= 0 && r < nyp) ? q[(size_t)r * ld] : 0.0; };
-  // prologue: rows needed before the first pipeline step
-  pm1 = ld_pm(r0 - 2);
-  pm2 = ld_pm(r0 - 1);
-  pB = ld_p(r0 - 4); pC = ld_p(r0 - 3);
-  qB = ld_q(r0 - 4); qC = ld_q(r0 - 3);
-  double npm = ld_pm(r0), np_ = ld_p(r0 - 2), nq = ld_q(r0 - 2);
+#pragma unroll
+  for (int s = 0; s < QG_D - 1; ++s) issue(r0 + s);
+#pragma unroll 3
   for (int r = r0; r < jb + 3; ++r) {
-    pm0 = pm1; pm1 = pm2; pm2 = npm;
-    pA = pB; pB = pC; pC = np_;
-    qA = qB; qB = qC; qC = nq;
-    npm = ld_pm(r + 1); np_ = ld_p(r - 1); nq = ld_q(r - 1);
+    issue(r + QG_D - 1);
+    cp_async_wait<QG_D - 1>();
+    const double *slot = ring + (size_t)((r + 8 * QG_D) % QG_D) * (QG_NF * 32);
+    pm0 = pm1; pm1 = pm2; pm2 = slot[0];
+    pA = pB; pB = pC; pC = slot[32];
+    qA = qB; qB = qC; qC = slot[64];
+    pAw = pBw; pAe = pBe; pBw = pCw; pBe = pCe; pCw = shl(pC); pCe = shr(pC);
+    qAw = qBw; qAe = qBe; qBw = qCw; qBe = qCe; qCw = shl(qC); qCe = shr(qC);
     // ---- del2 at row r-1 (qgosubs.F:86-130 / qgasubs.F:74-100)
     const int j2 = r - 1;
     {
@@ -106,8 +136,6 @@ __global__ void __launch_bounds__(128) k_qgstep(QgArgs a) {
     // ---- row r-3: del6, Jacobian, forcing, leapfrog
     const int jo = r - 3;
     const double d4w = shl(d4b), d4e = shr(d4b);
-    const double pAw = shl(pA), pAe = shr(pA), pBw = shl(pB), pBe = shr(pB), pCw = shl(pC), pCe = shr(pC);
-    const double qAw = shl(qA), qAe = shr(qA), qBw = shl(qB), qBe = shr(qB), qCw = shl(qC), qCe = shr(qC);
     if (jo < ja || jo >= jb || !outlane) continue;
     const size_t ro = (size_t)jo * ld;
     if (jo == 0 || jo == nyp - 1) {
@@ -133,17 +161,21 @@ __global__ void __launch_bounds__(128) k_qgstep(QgArgs a) {
       }
     }
     double qdot = dqdt;
-    if (a.atmos) {
-      if (k == 0) qdot = dqdt + a.fohfac[0] * (ent[ro] - wek[ro]);
-      if (k == 1) qdot = dqdt - a.fohfac[1] * ent[ro];
-    } else {
-      if (k == 0) qdot = dqdt + a.fohfac[0] * (wek[ro] - ent[ro]);
-      if (k == 1) qdot = dqdt + a.fohfac[1] * ent[ro];
-      if (k == nl - 1) qdot = qdot - a.bdrfac * d2a;   // d2a = del2p(i, jo) after the shifts above
+    if (forced) {
+      const double wk = slot[128], en = slot[160];
+      if (a.atmos) {
+        if (k == 0) qdot = dqdt + a.fohfac[0] * (en - wk);
+        if (k == 1) qdot = dqdt - a.fohfac[1] * en;
+      } else {
+        if (k == 0) qdot = dqdt + a.fohfac[0] * (wk - en);
+        if (k == 1) qdot = dqdt + a.fohfac[1] * en;
+      }
     }
-    // qm is updated in place; each element is read and written by exactly one lane
-    qm[ro] = qm[ro] + tdt * qdot;
+    if (!a.atmos && k == nl - 1) qdot = qdot - a.bdrfac * d2a;   // d2a = del2p(i, jo) after the shifts above
+    // qm is updated in place; each element is read (prefetched) and written by exactly one lane
+    qm[ro] = slot[96] + tdt * qdot;
   }
+  cp_async_wait<0>();
 }
 
 // Boundary-strip sums feeding the momentum constraints of periodic channels:
@@ -287,7 +319,7 @@ static void launch(qgcm_model *m, bool atmos) {
   }
   const int nwx = (g.nxp + WOUT - 1) / WOUT;
   dim3 grid((nwx + 3) / 4, (g.nyp + RCH - 1) / RCH, g.nl);
-  QG_LAUNCH(m, "k_qgstep", grid, 128, 0, k_qgstep, a);
+  QG_LAUNCH(m, "k_qgstep", grid, 128, 4 * QG_D * QG_NF * 32 * sizeof(double), k_qgstep, a);
   QG_CUDA(cudaGetLastError());
   m->swapf(nq, nqm);   // new q lives in the old qom buffer; old q becomes qom
 }

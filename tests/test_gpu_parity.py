@@ -140,3 +140,24 @@ def test_roundtrip_and_errors(qg):
         m.set_field("nosuchfield", t)
     with pytest.raises(RuntimeError):
         m.set_field("po", t)
+
+
+@pytest.mark.parametrize("nxto,cyc", [(96, 0), (120, 0), (160, 0), (180, 0), (200, 0), (216, 0), (240, 1),
+                                      (288, 1), (400, 1), (324, 0), (480, 1), (960, 0)])
+def test_transform_lengths(qg, pyorc, nxto, cyc):
+    """every butterfly radix of the device plan (15, 9, 5, 3 first; then 16, 10, 12, 8, 6, 4, 2)
+    against the oracle's Helmholtz solve"""
+    base = qg.named_config("so_coupled" if cyc else "dg_oo")
+    p = base.scaled(nxto // 4, 18, nxta=nxto // 4 if cyc else None, nyta=36, ndxr=4, name="len%d" % nxto)
+    p.flags = ["ocean_only"] + (["cyclic_ocean"] if cyc else [])
+    cfg = qg.build_config(p)
+    gpu, cpu = qg.Model(cfg), pyorc.Oracle(cfg)
+    rng = np.random.default_rng(nxto)
+    rhs = rng.standard_normal((p.nxpo, p.nypo))
+    if cyc:
+        rhs[-1, :] = rhs[0, :]
+    a = 1.0 / p.dxo ** 2
+    b = np.full(p.nxto, -2.2 * a) - 3.0e-9 * np.arange(p.nxto)
+    sg = gpu.helmholtz(0, rhs, b)
+    sc = cpu.helmholtz(0, rhs, b)
+    assert rel_l2(sg, sc) <= 1e-12
