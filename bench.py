@@ -43,7 +43,7 @@ def passes_per_launch(kernel, cyclic):
     table = {
         "k_oml_step": 9.0, "k_oml_entoc": 2.0,
         "k_qgstep": 17.0,
-        "k_l2m": 7.0, "k_xform": 6.0, "k_tri_local": 6.0,
+        "k_l2m": 7.0, "k_xform": 6.0, "k_tri_local": 6.0, "k_tri_fg": 3.0,
         "k_m2l": 6.0 if cyclic else 8.0,
         "k_avg2": None,
     }

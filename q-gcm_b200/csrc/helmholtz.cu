@@ -12,6 +12,7 @@
 //                 (two precomputed spike vectors, Toeplitz => identical for every
 //                 chunk) is applied on the fly when the inverse transform loads a row.
 //                 All global accesses are full-row coalesced; no transpose.
+#include <algorithm>
 #include <cmath>
 
 #include "qgcm_internal.h"
@@ -212,29 +213,9 @@ struct XfArgs {
   int inverse;     // 0 forward (rhs -> spectrum), 1 inverse (tridiagonal solution -> field)
   int ld, nyp, nxp;
   size_t lsz;      // mode stride
-  int nchunk, lastlen;
-  double ftnorm;
   double *wrk;
-  const double *vl, *vll, *yx;   // spike tables and interface values (inverse only)
   double *rowsum;                // [nmodes][nyp] (inverse only)
 };
-
-// value of the tridiagonal solution at (mode, interior row r, column col): local chunk
-// solution plus the two spike corrections, times ftnorm (src/ocisubs.F:484-487)
-__device__ __forceinline__ double corrected(const XfArgs &a, int mode, int r, int col, double u0) {
-  if (a.nchunk > 1) {
-    const int c = r / TRI_L, jl = r - c * TRI_L;
-    const size_t tb = ((size_t)mode * TRI_L) * a.ld;
-    const size_t yb = ((size_t)mode * 2 * a.nchunk) * a.ld;
-    const double yp = __ldg(&a.yx[yb + (size_t)c * a.ld + col]);
-    const double xn = __ldg(&a.yx[yb + (size_t)(a.nchunk + c) * a.ld + col]);
-    const double *vlt = (c == a.nchunk - 1) ? a.vll : a.vl;
-    const double vleft = __ldg(&vlt[tb + (size_t)jl * a.ld + col]);
-    const double vright = __ldg(&a.vl[tb + (size_t)(TRI_L - 1 - jl) * a.ld + col]);
-    u0 = u0 + yp * vleft + xn * vright;
-  }
-  return a.ftnorm * u0;
-}
 
 // F_k of the length-n real transform from the half-length complex transform Z (n = 2m):
 // F_k = (Z_k + conj Z_{m-k})/2 - (i/2) e^{-2 pi i k/n} (Z_k - conj Z_{m-k})
@@ -265,15 +246,9 @@ __global__ void __launch_bounds__(256, 2) k_xform(XfArgs a) {
       if (k == 0) {
         Ar[0] = 0.0;
       } else if (k == M) {
-        double x = row[M];
-        if (a.inverse) x = corrected(a, mode, r, M, x);
-        Ar[M] = 4.0 * x;
+        Ar[M] = 4.0 * row[M];
       } else {
-        double xa = row[k], xb = row[N - k];
-        if (a.inverse) {
-          xa = corrected(a, mode, r, k, xa);
-          xb = corrected(a, mode, r, N - k, xb);
-        }
+        const double xa = row[k], xb = row[N - k];
         const double t1 = xa - xb, t2 = __ldg(&a.f.sintw[k]) * (xa + xb);
         Ar[k] = t1 + t2;
         Ar[N - k] = t2 - t1;
@@ -371,7 +346,7 @@ __global__ void __launch_bounds__(256, 2) k_xform(XfArgs a) {
   } else {
     // ---------------- inverse real FFT (drfftb), then periodic wrap ----------------
     double *Br = reinterpret_cast<double *>(B);
-    for (int k = t; k < N; k += T) Br[k] = corrected(a, mode, r, k, row[k]);
+    for (int k = t; k < N; k += T) Br[k] = row[k];
     __syncthreads();
     for (int k = t; k < M; k += T) {
       double2 xa, xb;   // X_k, conj X_{M-k}
@@ -406,12 +381,320 @@ __global__ void __launch_bounds__(256, 2) k_xform(XfArgs a) {
 }
 
 // --------------------------------------------------------------------------------------
+// Fast path for the box solver: DST-I rows whose half length is M = 2*10*12*R4 = 240*R4
+// (all box benchmark decks: 2400 = 240*10, 1200 = 240*5, 480 = 240*2).
+//
+//   * persistent blocks (2 per SM), each walks rows blockIdx.x, +gridDim.x, ...
+//   * the raw row is fetched by the TMA engine (cp.async.bulk global->shared, mbarrier
+//     completion) one row ahead of the arithmetic, so no warp ever waits on HBM;
+//   * the FFTPACK pre-processing (dsint.f:17-30) is fused into the register load of the
+//     first butterfly pass, its sine weights are rebuilt from a per-thread base angle and
+//     R1 constants (no table traffic);
+//   * four register butterfly passes (2, 10, 12, R4: one butterfly per thread in every
+//     in-place pass, radices <= 12 keep each pass under 128 registers at two blocks per SM) with in-place shared-memory exchanges; the last pass builds its
+//     twiddles as powers of a per-thread base (two loads) by squaring/multiplying;
+//   * real post-processing on the (k, M-k) pair, the running sum of dsint.f:33-37 as a
+//     one-sweep block scan over contiguous segments, and the interleaved result goes
+//     straight from registers to HBM with coalesced 16-byte stores.
+// All strides are compile-time constants.
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// read-only load the compiler may not hoist out of the row loop (keeps the per-thread bases
+// out of the register budget of the butterflies)
+__device__ __forceinline__ double2 ldg2_nohoist(const double2 *p) {
+  double2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// tw[r] = w^r, r = 1..R-1, from w and w^2: tw[2q] = tw[q]^2, tw[2q+1] = tw[q] tw[q+1]
+// (depth <= 3 products for R <= 16)
+template <int R>
+__device__ __forceinline__ void twiddle_apply(double2 *v, double2 w1, double2 w2) {
+  double2 tw[R > 2 ? R : 3];
+  tw[1] = w1;
+  tw[2] = w2;
+#pragma unroll
+  for (int r = 3; r < R; ++r) tw[r] = (r & 1) ? cmul(tw[r / 2], tw[r / 2 + 1]) : cmul(tw[r / 2], tw[r / 2]);
+#pragma unroll
+  for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw[r]);
+}
+
+__host__ __device__ constexpr int dst3_seg(int M) {
+  // values per thread in the running-sum sweep: even, >= M/256, divides M, preferably an
+  // odd number of 16-byte units (conflict-free 128-bit shared loads)
+  int best = 0;
+  for (int s = 2; s <= 64; s += 2)
+    if (M % s == 0 && s * 256 >= M) {
+      if (!best) best = s;
+      if ((s / 2) & 1) return s;
+    }
+  return best;
+}
+
+struct Dst4Args {
+  int nitems, nrows;        // (mode,row) work items; interior rows per mode
+  int ld, nyp, nxp;
+  size_t lsz;
+  double *wrk;
+  double *rowsum;
+  const double2 *s1base;    // [256][2] (2 sin, 2 cos) of pi*(2t)/N and pi*(2t+1)/N
+  const double2 *tw2;       // [R2-1][NS2] twiddles of pass 2
+  const double2 *tw3;       // [R3-1][NS3] twiddles of pass 3
+  const double2 *tw4base;   // [L4][2]  w, w^2 of pass 4
+  const double2 *wnbase;    // [L4]     exp(-2 pi i t/N)
+  double c1[16], s1[16];    // cos, sin of pi*512 b/N
+  double2 wnr[16];          // exp(-2 pi i q L4/N)
+};
+
+// In-place Stockham pass of radix R over W (length R*L): every thread first pulls its
+// butterflies (at most two) into registers, the block synchronises, then the results go to
+// their autosort positions.  tw is laid out [q-1][k], k < NS.
+template <int R, int L, int NS>
+__device__ __forceinline__ void dst4_mid_pass(double2 *W, const double2 *__restrict__ tw, int t) {
+  constexpr int NB = (L + 255) / 256;
+  static_assert(NB <= 2, "pass too long for one block");
+  double2 v[NB][R];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+#pragma unroll
+    for (int q = 0; q < R; ++q) v[b][q] = make_double2(0.0, 0.0);   // defined on every path: no value is carried between rows
+    const int j = t + 256 * b;
+    if (j < L) {
+      const int k = j % NS;
+#pragma unroll
+      for (int q = 0; q < R; ++q) v[b][q] = W[j + q * L];
+#pragma unroll
+      for (int q = 1; q < R; ++q) v[b][q] = cmul(v[b][q], ldg2_nohoist(tw + (q - 1) * NS + k));
+      dft<R>(v[b]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int j = t + 256 * b;
+    if (j < L) {
+      const int k = j % NS, j0 = (j - k) * R + k;
+#pragma unroll
+      for (int q = 0; q < R; ++q) W[j0 + q * NS] = v[b][q];
+    }
+  }
+}
+
+template <int R2, int R3, int R4, bool INV>
+__global__ void __launch_bounds__(256, 2) k_dst4(const Dst4Args a) {
+  constexpr int R1 = 2;
+  constexpr int M = R1 * R2 * R3 * R4, N = 2 * M;
+  constexpr int L1 = M / R1, L2 = M / R2, L3 = M / R3, L4 = M / R4;
+  constexpr int NS2 = R1, NS3 = R1 * R2, NS4 = R1 * R2 * R3;
+  constexpr int NB1 = (L1 + 255) / 256;
+  constexpr int SEG = dst3_seg(M), NSC = M / SEG;
+  static_assert(NB1 <= 8 && L2 <= 256 && L3 <= 256 && L4 <= 256 && NSC <= 256 && SEG > 0, "plan does not fit one block");
+  static_assert(NS4 == L4, "last pass must be a single sweep");
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double *IN = reinterpret_cast<double *>(smraw);                 // N doubles: raw row (TMA target)
+  const double2 *IN2 = reinterpret_cast<const double2 *>(smraw);
+  double2 *W = reinterpret_cast<double2 *>(smraw + (size_t)N * 8);   // M complex: exchange buffer
+  double *Wd = reinterpret_cast<double *>(W);
+  double *red = reinterpret_cast<double *>(smraw + (size_t)N * 8 + (size_t)M * 16);   // 32 doubles
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(red + 32);
+  const int t0 = threadIdx.x;
+  const uint32_t bar = smem_u32(mbar), in_s = smem_u32(IN);
+
+  int item = blockIdx.x;
+  if (t0 == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (item < a.nitems) {
+      const int mode = item / a.nrows, r = item - mode * a.nrows;
+      mbar_expect_tx(bar, N * 8);
+      bulk_g2s(in_s, a.wrk + (size_t)mode * a.lsz + (size_t)(r + 1) * a.ld, N * 8, bar);
+    }
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+  for (; item < a.nitems; item += gridDim.x, parity ^= 1) {
+    // the thread index is made opaque once per row: nothing derived from it (addresses,
+    // twiddle bases, predicates) is hoisted out of the row loop into long-lived registers
+    int t = t0;
+    asm volatile("" : "+r"(t));
+    const int lane = t & 31, wp = t >> 5;
+    const int mode = item / a.nrows, r = item - mode * a.nrows;
+    double *__restrict__ row = a.wrk + (size_t)mode * a.lsz + (size_t)(r + 1) * a.ld;
+    // ---- pass 1 (radix 2, no twiddles) fused with the DST pre-processing (dsint.f:17-30):
+    //      t_e = (x_e - x_{N-e}) + 2 sin(e pi/N) (x_e + x_{N-e}),  z_n = t_{2n} + i t_{2n+1};
+    //      butterfly j combines z_j and z_{j+M/2}, whose sine weights are 2 sin A and 2 cos A ----
+    {
+      mbar_wait(bar, parity);
+      const double2 b0 = ldg2_nohoist(a.s1base + 2 * t), b1 = ldg2_nohoist(a.s1base + 2 * t + 1);
+#pragma unroll
+      for (int b = 0; b < NB1; ++b) {
+        const int j = t + 256 * b;
+        if (j < L1) {
+          // rotate the thread's base angle by pi*512 b/N
+          const double sa0 = (b == 0) ? b0.x : fma(b0.x, a.c1[b], b0.y * a.s1[b]);
+          const double ca0 = (b == 0) ? b0.y : fma(b0.y, a.c1[b], -(b0.x * a.s1[b]));
+          const double sa1 = (b == 0) ? b1.x : fma(b1.x, a.c1[b], b1.y * a.s1[b]);
+          const double ca1 = (b == 0) ? b1.y : fma(b1.y, a.c1[b], -(b1.x * a.s1[b]));
+          const double2 xo0 = IN2[j], xo1 = IN2[j + L1];
+          const double p00 = IN[(j == 0) ? 0 : N - 2 * j], p01 = IN[N - 2 * j - 1];
+          const double p10 = IN[M - 2 * j], p11 = IN[M - 2 * j - 1];
+          double2 z0, z1;
+          z0.x = fma(sa0, xo0.x + p00, xo0.x - p00);
+          z0.y = fma(sa1, xo0.y + p01, xo0.y - p01);
+          z1.x = fma(ca0, xo1.x + p10, xo1.x - p10);
+          z1.y = fma(ca1, xo1.y + p11, xo1.y - p11);
+          if (j == 0) z0.x = 0.0;
+          W[2 * j] = cadd(z0, z1);
+          W[2 * j + 1] = csub(z0, z1);
+        }
+      }
+    }
+    __syncthreads();   // raw row consumed, pass 1 complete
+    if (t == 0) {
+      const int nxt = item + gridDim.x;
+      if (nxt < a.nitems) {
+        const int m2 = nxt / a.nrows, r2 = nxt - m2 * a.nrows;
+        mbar_expect_tx(bar, N * 8);
+        bulk_g2s(in_s, a.wrk + (size_t)m2 * a.lsz + (size_t)(r2 + 1) * a.ld, N * 8, bar);
+      }
+    }
+    dst4_mid_pass<R2, L2, NS2>(W, a.tw2, t);
+    __syncthreads();
+    dst4_mid_pass<R3, L3, NS3>(W, a.tw3, t);
+    __syncthreads();
+    // ---- pass 4 (radix R4): thread t ends with Z_k, k = t + q*L4 ----
+    double2 v[R4];
+#pragma unroll
+    for (int q = 0; q < R4; ++q) v[q] = make_double2(0.0, 0.0);
+    if (t < L4) {
+#pragma unroll
+      for (int q = 0; q < R4; ++q) v[q] = W[t + q * L4];
+      const double2 w1 = ldg2_nohoist(a.tw4base + 2 * t), w2 = ldg2_nohoist(a.tw4base + 2 * t + 1);
+      twiddle_apply<R4>(v, w1, w2);
+      dft<R4>(v);
+    }
+    __syncthreads();
+    if (t < L4) {
+#pragma unroll
+      for (int q = 0; q < R4; ++q) W[t + q * L4] = v[q];
+    }
+    __syncthreads();
+    // ---- real post-processing: even outputs -Im F_k stay in registers, Re F_k is the
+    //      summand of the odd outputs ----
+    double ev[R4], cs[R4];
+#pragma unroll
+    for (int q = 0; q < R4; ++q) ev[q] = cs[q] = 0.0;
+    if (t < L4) {
+      const double2 wb = ldg2_nohoist(a.wnbase + t);
+#pragma unroll
+      for (int q = 0; q < R4; ++q) {
+        const int k = t + q * L4;
+        const double2 zb = (q == 0) ? ((t == 0) ? v[0] : W[M - t]) : W[M - k];
+        const double2 w = (q == 0) ? wb : cmul(wb, a.wnr[q]);
+        const double2 F = real_post(v[q], zb, w);
+        ev[q] = -F.y;
+        cs[q] = F.x;
+        asm volatile("" ::: "memory");   // keep the partner loads in step with their use (register budget)
+      }
+      if (t == 0) {
+        ev[0] = 0.0;
+        cs[0] = 0.5 * (v[0].x + v[0].y);   // out_1 = F_0 / 2
+      }
+    }
+    __syncthreads();   // partners read
+    if (t < L4) {
+#pragma unroll
+      for (int q = 0; q < R4; ++q) Wd[t + q * L4] = cs[q];
+    }
+    __syncthreads();
+    // ---- running sum over k (dsint.f:33-37): contiguous segment per thread ----
+    {
+      double sg[SEG];
+#pragma unroll
+      for (int q = 0; q < SEG; ++q) sg[q] = 0.0;
+      double tot = 0.0;
+      if (t < NSC) {
+        const double2 *src = reinterpret_cast<const double2 *>(Wd + t * SEG);
+#pragma unroll
+        for (int q = 0; q < SEG / 2; ++q) {
+          const double2 c2 = src[q];
+          tot += c2.x;
+          sg[2 * q] = tot;
+          tot += c2.y;
+          sg[2 * q + 1] = tot;
+        }
+      }
+      double inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double nb = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += nb;
+      }
+      if (lane == 31) red[wp] = inc;
+      __syncthreads();
+      double off = inc - tot;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < wp) off += red[i];
+      if (t < NSC) {
+        double2 *dst = reinterpret_cast<double2 *>(Wd + t * SEG);
+#pragma unroll
+        for (int q = 0; q < SEG / 2; ++q) dst[q] = make_double2(sg[2 * q] + off, sg[2 * q + 1] + off);
+      }
+    }
+    __syncthreads();
+    // ---- interleave and store: row[2k] = even_k, row[2k+1] = odd_k ----
+    double part = 0.0;
+    if (t < L4) {
+      double2 *__restrict__ out = reinterpret_cast<double2 *>(row);
+#pragma unroll
+      for (int q = 0; q < R4; ++q) {
+        const int k = t + q * L4;
+        const double od = Wd[k];
+        out[k] = make_double2(ev[q], od);
+        if (INV) part += ev[q] + od;
+      }
+    }
+    if (INV) {
+      if (t == 0) row[a.nxp - 1] = 0.0;
+      const double sum = block_sum(part, red + 8);
+      if (t == 0) a.rowsum[(size_t)mode * a.nyp + (r + 1)] = sum;
+    } else {
+      __syncthreads();   // W is rewritten by the next row's first pass
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------
 // y-direction: partitioned tridiagonal solve
 // --------------------------------------------------------------------------------------
 struct TriArgs {
   int ld, nyp, nk, koff, nchunk, lastlen, nmodes;
   size_t lsz;
-  double a;
+  double a, ftnorm;
   double *wrk;
   const double *bcoef;
   double *binv, *vl, *vll, *pt, *fg, *yx;
@@ -456,8 +739,14 @@ __global__ void k_tri_tables(TriArgs t) {
   }
 }
 
-// chunk-local Thomas solve: the chunk's right-hand side stays in registers, the
-// elimination reciprocals stream from an L2-resident table; grid (ceil(nk/128), nchunk, nmodes)
+// Chunk-local Thomas solve in registers; the elimination reciprocals stream from an
+// L2-resident table.  grid (ceil(nk/128), nchunk, nmodes).
+//   FINAL = false : right-hand side with zero neighbours; only the first and last values of
+//                   the local solution are stored (f_c, g_c: the interface system's rhs).
+//   FINAL = true  : the neighbour values found by k_tri_reduced are moved to the right-hand
+//                   side of the chunk's first and last rows, so the local solve returns the
+//                   rows of the global solution; stored times ftnorm (src/ocisubs.F:484-487).
+template <bool FINAL>
 __global__ void __launch_bounds__(128, 3) k_tri_local(TriArgs t) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y, mode = blockIdx.z;
@@ -468,9 +757,16 @@ __global__ void __launch_bounds__(128, 3) k_tri_local(TriArgs t) {
   const double *__restrict__ bi = t.binv + ((size_t)mode * TRI_L) * t.ld + col;
   const double a = t.a;
   const int ld = t.ld;
+  const size_t fb = ((size_t)mode * 2 * t.nchunk) * ld + col;
   double u[TRI_L];
 #pragma unroll
   for (int j = 0; j < TRI_L; ++j) u[j] = base[(size_t)min(j, len - 1) * ld];   // rows >= len: harmless duplicates
+  if (FINAL && t.nchunk > 1) {
+    const double yp = t.yx[fb + (size_t)c * ld], xn = t.yx[fb + (size_t)(t.nchunk + c) * ld];
+    u[0] -= a * yp;
+#pragma unroll
+    for (int j = 0; j < TRI_L; ++j) u[j] = fma(-a, (j == len - 1) ? xn : 0.0, u[j]);
+  }
   u[0] = u[0] * __ldg(bi);
 #pragma unroll
   for (int j = 1; j < TRI_L; ++j) u[j] = (u[j] - a * u[j - 1]) * __ldg(bi + (size_t)j * ld);
@@ -479,11 +775,12 @@ __global__ void __launch_bounds__(128, 3) k_tri_local(TriArgs t) {
     const double v = u[j] - (a * __ldg(bi + (size_t)j * ld)) * u[j + 1];
     u[j] = (j < len - 1) ? v : u[j];
   }
+  if (FINAL) {
+    const double fn = t.ftnorm;
 #pragma unroll
-  for (int j = 0; j < TRI_L; ++j)
-    if (j < len) base[(size_t)j * ld] = u[j];
-  if (t.nchunk > 1) {
-    const size_t fb = ((size_t)mode * 2 * t.nchunk) * ld + col;
+    for (int j = 0; j < TRI_L; ++j)
+      if (j < len) base[(size_t)j * ld] = fn * u[j];
+  } else {
     t.fg[fb + (size_t)c * ld] = u[0];                    // f_c : first row of the chunk
     // g_c : last row of the chunk.  Only g_0..g_{C-2} enter the interface system and those
     // chunks are always full, so the (ragged) last chunk may store a meaningless value.
@@ -552,6 +849,99 @@ __global__ void k_zero_rows(double *wrk, size_t lsz, int ld, int nyp, int nxp, i
 // --------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------
+// ---- fast DST path: instantiated plans, tables, launch ----
+template <int R2, int R3, int R4>
+static void dst4_launch_t(qgcm_model *md, HelmPlan &hp, const Dst4Args &a, bool inverse) {
+  constexpr int M = 2 * R2 * R3 * R4;
+  const size_t smem = (size_t)2 * M * 16 + 32 * 8 + 16;
+  auto kf = k_dst4<R2, R3, R4, false>;
+  auto ki = k_dst4<R2, R3, R4, true>;
+  if (!hp.fast_attr) {
+    QG_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QG_CUDA(cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hp.fast_attr = 1;
+  }
+  const int grid = std::min(a.nitems, hp.fast_grid);
+  if (inverse)
+    QG_LAUNCH(md, "k_xform", grid, 256, smem, ki, a);
+  else
+    QG_LAUNCH(md, "k_xform", grid, 256, smem, kf, a);
+}
+
+// box decks whose half length is 240*R4 run the four-pass plan (2, 10, 12, R4)
+static int dst4_r4(const HelmPlan &hp) {
+  if (hp.kind != 0 || hp.m % 240 != 0) return 0;
+  const int r4 = hp.m / 240;
+  return (r4 == 2 || r4 == 3 || r4 == 4 || r4 == 5 || r4 == 6 || r4 == 8 || r4 == 10) ? r4 : 0;
+}
+
+static void dst4_launch(qgcm_model *md, HelmPlan &hp, double *wrk, size_t lsz, int nmodes, bool inverse) {
+  Dst4Args a;
+  a.nitems = nmodes * hp.nrows; a.nrows = hp.nrows; a.ld = hp.ld; a.nyp = hp.nyp; a.nxp = hp.nxp; a.lsz = lsz;
+  a.wrk = wrk; a.rowsum = hp.rowsum;
+  a.s1base = hp.s1base; a.tw2 = hp.tw2; a.tw3 = hp.tw3; a.tw4base = hp.tw4base; a.wnbase = hp.wnbase;
+  for (int i = 0; i < 16; ++i) { a.c1[i] = hp.c1[i]; a.s1[i] = hp.s1c[i]; a.wnr[i] = hp.wnr[i]; }
+  switch (hp.fast) {
+    case 2: dst4_launch_t<10, 12, 2>(md, hp, a, inverse); break;
+    case 3: dst4_launch_t<10, 12, 3>(md, hp, a, inverse); break;
+    case 4: dst4_launch_t<10, 12, 4>(md, hp, a, inverse); break;
+    case 5: dst4_launch_t<10, 12, 5>(md, hp, a, inverse); break;
+    case 6: dst4_launch_t<10, 12, 6>(md, hp, a, inverse); break;
+    case 8: dst4_launch_t<10, 12, 8>(md, hp, a, inverse); break;
+    case 10: dst4_launch_t<10, 12, 10>(md, hp, a, inverse); break;
+    default: throw std::runtime_error("helmholtz: no fast DST plan");
+  }
+}
+
+static void dst4_plan(qgcm_model *md, HelmPlan &hp) {
+  hp.fast = dst4_r4(hp);
+  if (!hp.fast) return;
+  const int R1 = 2, R2 = 10, R3 = 12, R4 = hp.fast;
+  const int M = hp.m, N = hp.n, L1 = M / R1, L4 = M / R4;
+  const long double PI_L = 3.141592653589793238462643383279502884L;
+  std::vector<double2> s1b(2 * 256), t2, t3, t4(2 * L4), wb(L4);
+  (void)L1;
+  for (int j = 0; j < 256; ++j)
+    for (int e = 0; e < 2; ++e) {
+      const long double ang = PI_L * (2 * j + e) / N;
+      s1b[2 * j + e] = make_double2((double)(2.0L * sinl(ang)), (double)(2.0L * cosl(ang)));
+    }
+  auto pass_table = [&](std::vector<double2> &tw, int R, int Ns) {
+    for (int q = 1; q < R; ++q)
+      for (int k = 0; k < Ns; ++k) {
+        const long double ang = -2.0L * PI_L * (long double)q * k / ((long double)Ns * R);
+        tw.push_back(make_double2((double)cosl(ang), (double)sinl(ang)));
+      }
+  };
+  pass_table(t2, R2, R1);
+  pass_table(t3, R3, R1 * R2);
+  for (int t = 0; t < L4; ++t) {
+    for (int e = 1; e <= 2; ++e) {
+      const long double ang = -2.0L * PI_L * e * t / M;
+      t4[2 * t + e - 1] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+    const long double ang = -2.0L * PI_L * t / N;
+    wb[t] = make_double2((double)cosl(ang), (double)sinl(ang));
+  }
+  for (int q = 0; q < 16; ++q) {
+    hp.c1[q] = (double)cosl(PI_L * 512 * q / N);     // first pass: butterfly j = t + 256 q
+    hp.s1c[q] = (double)sinl(PI_L * 512 * q / N);
+    const long double ang = -2.0L * PI_L * q * L4 / N;
+    hp.wnr[q] = make_double2((double)cosl(ang), (double)sinl(ang));
+  }
+  auto up = [&](const std::vector<double2> &v) {
+    double2 *d = (double2 *)dalloc(md, sizeof(double2) * v.size());
+    QG_CUDA(cudaMemcpy(d, v.data(), sizeof(double2) * v.size(), cudaMemcpyHostToDevice));
+    return d;
+  };
+  hp.s1base = up(s1b); hp.tw2 = up(t2); hp.tw3 = up(t3); hp.tw4base = up(t4); hp.wnbase = up(wb);
+  int dev = 0, sms = 0;
+  QG_CUDA(cudaGetDevice(&dev));
+  QG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  hp.fast_grid = 2 * sms;
+  hp.fast_attr = 0;
+}
+
 // Radix plan: an odd radix first (its stride-R shared-memory scatter is conflict-free while
 // Ns = 1), then the largest radices that divide what is left: three passes for every
 // benchmark length (2400 = 15*16*10, 1200 = 15*16*5, 480 = 15*16*2, 2304 = 9*16*16).
@@ -646,6 +1036,7 @@ void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, con
   hp.rowsum = (double *)dalloc(md, sizeof(double) * nmodes * hp.nyp);
   QG_CUDA(cudaMemset(hp.rowsum, 0, sizeof(double) * nmodes * hp.nyp));
   QG_CUDA(cudaFuncSetAttribute(k_xform, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.smem_bytes));
+  dst4_plan(md, hp);
   // diagonal b(i) = bd2(i) - rdm2(m), src/q-gcm.F:929-973 and src/ocisubs.F:148-150
   const double PI = 3.14159265358979324, TWOPI = 6.28318530717958648;
   std::vector<double> bd2(hp.n, 0.0), b((size_t)nmodes * hp.n);
@@ -671,7 +1062,7 @@ void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, con
 static TriArgs tri_args(HelmPlan &hp, double *wrk, size_t lsz, int nmodes) {
   TriArgs t;
   t.ld = hp.ld; t.nyp = hp.nyp; t.nk = hp.nk; t.koff = hp.koff; t.nchunk = hp.nchunk;
-  t.lastlen = hp.lastlen; t.nmodes = nmodes; t.lsz = lsz; t.a = hp.a; t.wrk = wrk;
+  t.lastlen = hp.lastlen; t.nmodes = nmodes; t.lsz = lsz; t.a = hp.a; t.ftnorm = hp.ftnorm; t.wrk = wrk;
   t.bcoef = hp.bcoef; t.binv = hp.binv; t.vl = hp.vl; t.vll = hp.vll; t.pt = hp.pt; t.fg = hp.fg; t.yx = hp.yx;
   return t;
 }
@@ -698,19 +1089,28 @@ void helm_solve(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
   for (int i = 0; i < 8; ++i) { x.f.radix[i] = hp.radix[i]; x.f.twoff[i] = hp.twoff[i]; }
   x.f.tw = hp.wm; x.f.wn = hp.wn; x.f.sintw = hp.sintw;
   x.kind = hp.kind; x.inverse = 0; x.ld = hp.ld; x.nyp = hp.nyp; x.nxp = hp.nxp; x.lsz = lsz;
-  x.nchunk = hp.nchunk; x.lastlen = hp.lastlen; x.ftnorm = hp.ftnorm; x.wrk = wrk;
-  x.vl = hp.vl; x.vll = hp.vll; x.yx = hp.yx; x.rowsum = hp.rowsum;
+  x.wrk = wrk; x.rowsum = hp.rowsum;
   dim3 gx(hp.nrows, nmodes);
-  QG_LAUNCH(md, "k_xform", gx, 256, hp.smem_bytes, k_xform, x);
+  if (hp.fast)
+    dst4_launch(md, hp, wrk, lsz, nmodes, false);
+  else
+    QG_LAUNCH(md, "k_xform", gx, 256, hp.smem_bytes, k_xform, x);
   TriArgs t = tri_args(hp, wrk, lsz, nmodes);
   dim3 gl((hp.nk + 127) / 128, hp.nchunk, nmodes);
-  QG_LAUNCH(md, "k_tri_local", gl, 128, 0, k_tri_local, t);
   if (hp.nchunk > 1) {
+    auto kfg = k_tri_local<false>;
+    QG_LAUNCH(md, "k_tri_fg", gl, 128, 0, kfg, t);
     dim3 gr((hp.nk + 127) / 128, nmodes);
     QG_LAUNCH(md, "k_tri_reduced", gr, 128, 0, k_tri_reduced, t);
   }
-  x.inverse = 1;
-  QG_LAUNCH(md, "k_xform", gx, 256, hp.smem_bytes, k_xform, x);
+  auto kfin = k_tri_local<true>;
+  QG_LAUNCH(md, "k_tri_local", gl, 128, 0, kfin, t);
+  if (hp.fast) {
+    dst4_launch(md, hp, wrk, lsz, nmodes, true);
+  } else {
+    x.inverse = 1;
+    QG_LAUNCH(md, "k_xform", gx, 256, hp.smem_bytes, k_xform, x);
+  }
   QG_LAUNCH(md, "k_zero_rows", (hp.nxp + 255) / 256, 256, 0, k_zero_rows, wrk, lsz, hp.ld, hp.nyp, hp.nxp, nmodes);
   QG_CUDA(cudaGetLastError());
 }

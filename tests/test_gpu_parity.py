@@ -7,7 +7,7 @@ from util import TOL, rel_l2, small_configs, make_pair, compare, compare_scalars
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["box_dg", "box_natl1km", "chan_so"]
+CASES = ["box_dg", "box_natl1km", "chan_so", "box_fast"]
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -143,10 +143,12 @@ def test_roundtrip_and_errors(qg):
 
 
 @pytest.mark.parametrize("nxto,cyc", [(96, 0), (120, 0), (160, 0), (180, 0), (200, 0), (216, 0), (240, 1),
-                                      (288, 1), (400, 1), (324, 0), (480, 1), (960, 0)])
+                                      (288, 1), (400, 1), (324, 0), (480, 1), (960, 0), (1440, 0), (1920, 0),
+                                      (2400, 0), (2880, 0), (3840, 0), (4800, 0)])
 def test_transform_lengths(qg, pyorc, nxto, cyc):
-    """every butterfly radix of the device plan (15, 9, 5, 3 first; then 16, 10, 12, 8, 6, 4, 2)
-    against the oracle's Helmholtz solve"""
+    """every butterfly radix of the generic device plan (15, 9, 5, 3 first; then 16, 10, 12, 8, 6, 4,
+    2) and every instantiation of the four-pass box plan (nxto = 480*R4, R4 = 2..10) against the
+    oracle's Helmholtz solve"""
     base = qg.named_config("so_coupled" if cyc else "dg_oo")
     p = base.scaled(nxto // 4, 18, nxta=nxto // 4 if cyc else None, nyta=36, ndxr=4, name="len%d" % nxto)
     p.flags = ["ocean_only"] + (["cyclic_ocean"] if cyc else [])

@@ -18,7 +18,10 @@ def small_configs(qg):
     box1 = qg.named_config("natl1km").scaled(3, 4, ndxr=40, name="box_natl1km")  # 120 x 160, nstr=1
     cyc = qg.named_config("so_coupled").scaled(6, 5, nxta=6, nyta=15, ndxr=16, name="chan_so")
     cyc.flags = ["ocean_only", "cyclic_ocean", "nb_hflux"]
-    return {"box_dg": box, "box_natl1km": box1, "chan_so": cyc}
+    # 960 x 480: long enough for the four-pass TMA-fed DST plan (half length 480 = 240*2), and
+    # 3*479 rows make every persistent block walk several rows
+    fast = qg.named_config("natl1km").scaled(24, 12, ndxr=40, name="box_fast")
+    return {"box_dg": box, "box_natl1km": box1, "chan_so": cyc, "box_fast": fast}
 
 
 def make_pair(qg, pyorc, p, kind="random", seed=None):
