@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(256, 2) k_xform(XfArgs a) {
 }
 
 // --------------------------------------------------------------------------------------
-// Fast path for the box solver: DST-I rows whose half length is M = 2*10*12*R4 = 240*R4
+// Fast path for the box solver: DST-I rows whose half length is M = 16*15*R3 = 240*R3
 // (all box benchmark decks: 2400 = 240*10, 1200 = 240*5, 480 = 240*2).
 //
 //   * persistent blocks (2 per SM), each walks rows blockIdx.x, +gridDim.x, ...
@@ -390,8 +390,9 @@ __global__ void __launch_bounds__(256, 2) k_xform(XfArgs a) {
 //   * the FFTPACK pre-processing (dsint.f:17-30) is fused into the register load of the
 //     first butterfly pass, its sine weights are rebuilt from a per-thread base angle and
 //     R1 constants (no table traffic);
-//   * four register butterfly passes (2, 10, 12, R4: one butterfly per thread in every
-//     in-place pass, radices <= 12 keep each pass under 128 registers at two blocks per SM) with in-place shared-memory exchanges; the last pass builds its
+//   * three register butterfly passes (16, 15, R3: one butterfly per thread in every pass,
+//     under 128 registers at two blocks per SM) with two shared-memory exchanges laid out
+//     free of bank conflicts (the first one skewed by i >> 4); the last pass builds its
 //     twiddles as powers of a per-thread base (two loads) by squaring/multiplying;
 //   * real post-processing on the (k, M-k) pair, the running sum of dsint.f:33-37 as a
 //     one-sweep block scan over contiguous segments, and the interleaved result goes
@@ -454,71 +455,36 @@ __host__ __device__ constexpr int dst3_seg(int M) {
   return best;
 }
 
-struct Dst4Args {
+struct Dst3Args {
   int nitems, nrows;        // (mode,row) work items; interior rows per mode
   int ld, nyp, nxp;
   size_t lsz;
   double *wrk;
   double *rowsum;
-  const double2 *s1base;    // [256][2] (2 sin, 2 cos) of pi*(2t)/N and pi*(2t+1)/N
-  const double2 *tw2;       // [R2-1][NS2] twiddles of pass 2
-  const double2 *tw3;       // [R3-1][NS3] twiddles of pass 3
-  const double2 *tw4base;   // [L4][2]  w, w^2 of pass 4
-  const double2 *wnbase;    // [L4]     exp(-2 pi i t/N)
-  double c1[16], s1[16];    // cos, sin of pi*512 b/N
-  double2 wnr[16];          // exp(-2 pi i q L4/N)
+  const double2 *s1base;    // [L1][2]  (2 sin, 2 cos) of pi*(2t)/N and pi*(2t+1)/N
+  const double2 *tw2;       // [R2-1][R1] twiddles of pass 2
+  const double2 *tw3base;   // [L3][2]  w, w^2 of pass 3
+  const double2 *wnbase;    // [L3]     exp(-2 pi i t/N)
+  double c1[16], s1[16];    // cos, sin of pi q/R1
+  double2 wnr[16];          // exp(-2 pi i q L3/N)
 };
 
-// In-place Stockham pass of radix R over W (length R*L): every thread first pulls its
-// butterflies (at most two) into registers, the block synchronises, then the results go to
-// their autosort positions.  tw is laid out [q-1][k], k < NS.
-template <int R, int L, int NS>
-__device__ __forceinline__ void dst4_mid_pass(double2 *W, const double2 *__restrict__ tw, int t) {
-  constexpr int NB = (L + 255) / 256;
-  static_assert(NB <= 2, "pass too long for one block");
-  double2 v[NB][R];
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-#pragma unroll
-    for (int q = 0; q < R; ++q) v[b][q] = make_double2(0.0, 0.0);   // defined on every path: no value is carried between rows
-    const int j = t + 256 * b;
-    if (j < L) {
-      const int k = j % NS;
-#pragma unroll
-      for (int q = 0; q < R; ++q) v[b][q] = W[j + q * L];
-#pragma unroll
-      for (int q = 1; q < R; ++q) v[b][q] = cmul(v[b][q], ldg2_nohoist(tw + (q - 1) * NS + k));
-      dft<R>(v[b]);
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    const int j = t + 256 * b;
-    if (j < L) {
-      const int k = j % NS, j0 = (j - k) * R + k;
-#pragma unroll
-      for (int q = 0; q < R; ++q) W[j0 + q * NS] = v[b][q];
-    }
-  }
-}
-
-template <int R2, int R3, int R4, bool INV>
-__global__ void __launch_bounds__(256, 2) k_dst4(const Dst4Args a) {
-  constexpr int R1 = 2;
-  constexpr int M = R1 * R2 * R3 * R4, N = 2 * M;
-  constexpr int L1 = M / R1, L2 = M / R2, L3 = M / R3, L4 = M / R4;
-  constexpr int NS2 = R1, NS3 = R1 * R2, NS4 = R1 * R2 * R3;
-  constexpr int NB1 = (L1 + 255) / 256;
+template <int R3, bool INV>
+__global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
+  constexpr int R1 = 16, R2 = 15;
+  constexpr int M = R1 * R2 * R3, N = 2 * M;
+  constexpr int L1 = M / R1, L2 = M / R2, L3 = M / R3;
+  constexpr int NS2 = R1, NS3 = R1 * R2;
+  constexpr int WSZ = M + M / 16;              // exchange buffer incl. the skew of pass 1's output
   constexpr int SEG = dst3_seg(M), NSC = M / SEG;
-  static_assert(NB1 <= 8 && L2 <= 256 && L3 <= 256 && L4 <= 256 && NSC <= 256 && SEG > 0, "plan does not fit one block");
-  static_assert(NS4 == L4, "last pass must be a single sweep");
+  static_assert(L1 <= 256 && L2 <= 256 && L3 <= 256 && NSC <= 256 && SEG > 0 && L2 % 16 == 0, "plan does not fit one block");
+  static_assert(NS3 == L3, "last pass must be a single sweep");
   extern __shared__ __align__(128) unsigned char smraw[];
   double *IN = reinterpret_cast<double *>(smraw);                 // N doubles: raw row (TMA target)
   const double2 *IN2 = reinterpret_cast<const double2 *>(smraw);
-  double2 *W = reinterpret_cast<double2 *>(smraw + (size_t)N * 8);   // M complex: exchange buffer
+  double2 *W = reinterpret_cast<double2 *>(smraw + (size_t)N * 8);   // exchange buffer
   double *Wd = reinterpret_cast<double *>(W);
-  double *red = reinterpret_cast<double *>(smraw + (size_t)N * 8 + (size_t)M * 16);   // 32 doubles
+  double *red = reinterpret_cast<double *>(smraw + (size_t)N * 8 + (size_t)WSZ * 16);   // 32 doubles
   uint64_t *mbar = reinterpret_cast<uint64_t *>(red + 32);
   const int t0 = threadIdx.x;
   const uint32_t bar = smem_u32(mbar), in_s = smem_u32(IN);
@@ -543,34 +509,29 @@ __global__ void __launch_bounds__(256, 2) k_dst4(const Dst4Args a) {
     const int lane = t & 31, wp = t >> 5;
     const int mode = item / a.nrows, r = item - mode * a.nrows;
     double *__restrict__ row = a.wrk + (size_t)mode * a.lsz + (size_t)(r + 1) * a.ld;
-    // ---- pass 1 (radix 2, no twiddles) fused with the DST pre-processing (dsint.f:17-30):
-    //      t_e = (x_e - x_{N-e}) + 2 sin(e pi/N) (x_e + x_{N-e}),  z_n = t_{2n} + i t_{2n+1};
-    //      butterfly j combines z_j and z_{j+M/2}, whose sine weights are 2 sin A and 2 cos A ----
-    {
+    // ---- pass 1 (radix 16, no twiddles) fused with the DST pre-processing (dsint.f:17-30):
+    //      t_e = (x_e - x_{N-e}) + 2 sin(e pi/N) (x_e + x_{N-e}),  z_n = t_{2n} + i t_{2n+1}.
+    //      Output position i = 16 t + q is stored at i + (i >> 4) = 17 t + q: conflict-free
+    //      stores here, and pass 2 reads t + 160 q at t + (t >> 4) + 170 q ----
+    if (t < L1) {
+      double2 v1[R1];
       mbar_wait(bar, parity);
       const double2 b0 = ldg2_nohoist(a.s1base + 2 * t), b1 = ldg2_nohoist(a.s1base + 2 * t + 1);
 #pragma unroll
-      for (int b = 0; b < NB1; ++b) {
-        const int j = t + 256 * b;
-        if (j < L1) {
-          // rotate the thread's base angle by pi*512 b/N
-          const double sa0 = (b == 0) ? b0.x : fma(b0.x, a.c1[b], b0.y * a.s1[b]);
-          const double ca0 = (b == 0) ? b0.y : fma(b0.y, a.c1[b], -(b0.x * a.s1[b]));
-          const double sa1 = (b == 0) ? b1.x : fma(b1.x, a.c1[b], b1.y * a.s1[b]);
-          const double ca1 = (b == 0) ? b1.y : fma(b1.y, a.c1[b], -(b1.x * a.s1[b]));
-          const double2 xo0 = IN2[j], xo1 = IN2[j + L1];
-          const double p00 = IN[(j == 0) ? 0 : N - 2 * j], p01 = IN[N - 2 * j - 1];
-          const double p10 = IN[M - 2 * j], p11 = IN[M - 2 * j - 1];
-          double2 z0, z1;
-          z0.x = fma(sa0, xo0.x + p00, xo0.x - p00);
-          z0.y = fma(sa1, xo0.y + p01, xo0.y - p01);
-          z1.x = fma(ca0, xo1.x + p10, xo1.x - p10);
-          z1.y = fma(ca1, xo1.y + p11, xo1.y - p11);
-          if (j == 0) z0.x = 0.0;
-          W[2 * j] = cadd(z0, z1);
-          W[2 * j + 1] = csub(z0, z1);
-        }
+      for (int q = 0; q < R1; ++q) {
+        const int n = t + q * L1;
+        const double2 xo = IN2[n];
+        const double xb0 = IN[(q == 0) ? ((t == 0) ? 0 : N - 2 * t) : N - 2 * n];
+        const double xb1 = IN[N - 2 * n - 1];
+        const double s0 = (q == 0) ? b0.x : fma(b0.x, a.c1[q], b0.y * a.s1[q]);
+        const double s1 = (q == 0) ? b1.x : fma(b1.x, a.c1[q], b1.y * a.s1[q]);
+        v1[q].x = fma(s0, xo.x + xb0, xo.x - xb0);
+        v1[q].y = fma(s1, xo.y + xb1, xo.y - xb1);
       }
+      if (t == 0) v1[0].x = 0.0;
+      dft<R1>(v1);
+#pragma unroll
+      for (int q = 0; q < R1; ++q) W[t * (R1 + 1) + q] = v1[q];
     }
     __syncthreads();   // raw row consumed, pass 1 complete
     if (t == 0) {
@@ -581,37 +542,54 @@ __global__ void __launch_bounds__(256, 2) k_dst4(const Dst4Args a) {
         bulk_g2s(in_s, a.wrk + (size_t)m2 * a.lsz + (size_t)(r2 + 1) * a.ld, N * 8, bar);
       }
     }
-    dst4_mid_pass<R2, L2, NS2>(W, a.tw2, t);
-    __syncthreads();
-    dst4_mid_pass<R3, L3, NS3>(W, a.tw3, t);
-    __syncthreads();
-    // ---- pass 4 (radix R4): thread t ends with Z_k, k = t + q*L4 ----
-    double2 v[R4];
+    // ---- pass 2 (radix 15), in place: all loads, barrier, autosort stores ----
+    {
+      double2 v[R2];
 #pragma unroll
-    for (int q = 0; q < R4; ++q) v[q] = make_double2(0.0, 0.0);
-    if (t < L4) {
+      for (int q = 0; q < R2; ++q) v[q] = make_double2(0.0, 0.0);   // defined on every path: nothing is carried between rows
+      const int k2 = t % NS2, j0 = (t - k2) * R2 + k2;
+      if (t < L2) {
+        const double2 *src = W + t + (t >> 4);
 #pragma unroll
-      for (int q = 0; q < R4; ++q) v[q] = W[t + q * L4];
-      const double2 w1 = ldg2_nohoist(a.tw4base + 2 * t), w2 = ldg2_nohoist(a.tw4base + 2 * t + 1);
-      twiddle_apply<R4>(v, w1, w2);
-      dft<R4>(v);
+        for (int q = 0; q < R2; ++q) v[q] = src[q * (L2 + L2 / 16)];
+#pragma unroll
+        for (int q = 1; q < R2; ++q) v[q] = cmul(v[q], ldg2_nohoist(a.tw2 + (q - 1) * NS2 + k2));
+        dft<R2>(v);
+      }
+      __syncthreads();
+      if (t < L2) {
+#pragma unroll
+        for (int q = 0; q < R2; ++q) W[j0 + q * NS2] = v[q];
+      }
     }
     __syncthreads();
-    if (t < L4) {
+    // ---- pass 3 (radix R3): thread t ends with Z_k, k = t + q*L3 ----
+    double2 v[R3];
 #pragma unroll
-      for (int q = 0; q < R4; ++q) W[t + q * L4] = v[q];
+    for (int q = 0; q < R3; ++q) v[q] = make_double2(0.0, 0.0);
+    if (t < L3) {
+#pragma unroll
+      for (int q = 0; q < R3; ++q) v[q] = W[t + q * L3];
+      const double2 w1 = ldg2_nohoist(a.tw3base + 2 * t), w2 = ldg2_nohoist(a.tw3base + 2 * t + 1);
+      twiddle_apply<R3>(v, w1, w2);
+      dft<R3>(v);
+    }
+    __syncthreads();
+    if (t < L3) {
+#pragma unroll
+      for (int q = 0; q < R3; ++q) W[t + q * L3] = v[q];
     }
     __syncthreads();
     // ---- real post-processing: even outputs -Im F_k stay in registers, Re F_k is the
     //      summand of the odd outputs ----
-    double ev[R4], cs[R4];
+    double ev[R3], cs[R3];
 #pragma unroll
-    for (int q = 0; q < R4; ++q) ev[q] = cs[q] = 0.0;
-    if (t < L4) {
+    for (int q = 0; q < R3; ++q) ev[q] = cs[q] = 0.0;
+    if (t < L3) {
       const double2 wb = ldg2_nohoist(a.wnbase + t);
 #pragma unroll
-      for (int q = 0; q < R4; ++q) {
-        const int k = t + q * L4;
+      for (int q = 0; q < R3; ++q) {
+        const int k = t + q * L3;
         const double2 zb = (q == 0) ? ((t == 0) ? v[0] : W[M - t]) : W[M - k];
         const double2 w = (q == 0) ? wb : cmul(wb, a.wnr[q]);
         const double2 F = real_post(v[q], zb, w);
@@ -625,9 +603,9 @@ __global__ void __launch_bounds__(256, 2) k_dst4(const Dst4Args a) {
       }
     }
     __syncthreads();   // partners read
-    if (t < L4) {
+    if (t < L3) {
 #pragma unroll
-      for (int q = 0; q < R4; ++q) Wd[t + q * L4] = cs[q];
+      for (int q = 0; q < R3; ++q) Wd[t + q * L3] = cs[q];
     }
     __syncthreads();
     // ---- running sum over k (dsint.f:33-37): contiguous segment per thread ----
@@ -668,11 +646,11 @@ __global__ void __launch_bounds__(256, 2) k_dst4(const Dst4Args a) {
     __syncthreads();
     // ---- interleave and store: row[2k] = even_k, row[2k+1] = odd_k ----
     double part = 0.0;
-    if (t < L4) {
+    if (t < L3) {
       double2 *__restrict__ out = reinterpret_cast<double2 *>(row);
 #pragma unroll
-      for (int q = 0; q < R4; ++q) {
-        const int k = t + q * L4;
+      for (int q = 0; q < R3; ++q) {
+        const int k = t + q * L3;
         const double od = Wd[k];
         out[k] = make_double2(ev[q], od);
         if (INV) part += ev[q] + od;
@@ -850,12 +828,12 @@ __global__ void k_zero_rows(double *wrk, size_t lsz, int ld, int nyp, int nxp, i
 // host side
 // --------------------------------------------------------------------------------------
 // ---- fast DST path: instantiated plans, tables, launch ----
-template <int R2, int R3, int R4>
-static void dst4_launch_t(qgcm_model *md, HelmPlan &hp, const Dst4Args &a, bool inverse) {
-  constexpr int M = 2 * R2 * R3 * R4;
-  const size_t smem = (size_t)2 * M * 16 + 32 * 8 + 16;
-  auto kf = k_dst4<R2, R3, R4, false>;
-  auto ki = k_dst4<R2, R3, R4, true>;
+template <int R3>
+static void dst3_launch_t(qgcm_model *md, HelmPlan &hp, const Dst3Args &a, bool inverse) {
+  constexpr int M = 16 * 15 * R3;
+  const size_t smem = (size_t)M * 16 + (size_t)(M + M / 16) * 16 + 32 * 8 + 16;
+  auto kf = k_dst3<R3, false>;
+  auto ki = k_dst3<R3, true>;
   if (!hp.fast_attr) {
     QG_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QG_CUDA(cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -868,65 +846,60 @@ static void dst4_launch_t(qgcm_model *md, HelmPlan &hp, const Dst4Args &a, bool 
     QG_LAUNCH(md, "k_xform", grid, 256, smem, kf, a);
 }
 
-// box decks whose half length is 240*R4 run the four-pass plan (2, 10, 12, R4)
-static int dst4_r4(const HelmPlan &hp) {
+// box decks whose half length is 240*R3 run the three-pass plan (16, 15, R3)
+static int dst3_r3(const HelmPlan &hp) {
   if (hp.kind != 0 || hp.m % 240 != 0) return 0;
-  const int r4 = hp.m / 240;
-  return (r4 == 2 || r4 == 3 || r4 == 4 || r4 == 5 || r4 == 6 || r4 == 8 || r4 == 10) ? r4 : 0;
+  const int r3 = hp.m / 240;
+  return (r3 == 2 || r3 == 3 || r3 == 4 || r3 == 5 || r3 == 6 || r3 == 8 || r3 == 10) ? r3 : 0;
 }
 
-static void dst4_launch(qgcm_model *md, HelmPlan &hp, double *wrk, size_t lsz, int nmodes, bool inverse) {
-  Dst4Args a;
+static void dst3_launch(qgcm_model *md, HelmPlan &hp, double *wrk, size_t lsz, int nmodes, bool inverse) {
+  Dst3Args a;
   a.nitems = nmodes * hp.nrows; a.nrows = hp.nrows; a.ld = hp.ld; a.nyp = hp.nyp; a.nxp = hp.nxp; a.lsz = lsz;
   a.wrk = wrk; a.rowsum = hp.rowsum;
-  a.s1base = hp.s1base; a.tw2 = hp.tw2; a.tw3 = hp.tw3; a.tw4base = hp.tw4base; a.wnbase = hp.wnbase;
+  a.s1base = hp.s1base; a.tw2 = hp.tw2; a.tw3base = hp.tw3base; a.wnbase = hp.wnbase;
   for (int i = 0; i < 16; ++i) { a.c1[i] = hp.c1[i]; a.s1[i] = hp.s1c[i]; a.wnr[i] = hp.wnr[i]; }
   switch (hp.fast) {
-    case 2: dst4_launch_t<10, 12, 2>(md, hp, a, inverse); break;
-    case 3: dst4_launch_t<10, 12, 3>(md, hp, a, inverse); break;
-    case 4: dst4_launch_t<10, 12, 4>(md, hp, a, inverse); break;
-    case 5: dst4_launch_t<10, 12, 5>(md, hp, a, inverse); break;
-    case 6: dst4_launch_t<10, 12, 6>(md, hp, a, inverse); break;
-    case 8: dst4_launch_t<10, 12, 8>(md, hp, a, inverse); break;
-    case 10: dst4_launch_t<10, 12, 10>(md, hp, a, inverse); break;
+    case 2: dst3_launch_t<2>(md, hp, a, inverse); break;
+    case 3: dst3_launch_t<3>(md, hp, a, inverse); break;
+    case 4: dst3_launch_t<4>(md, hp, a, inverse); break;
+    case 5: dst3_launch_t<5>(md, hp, a, inverse); break;
+    case 6: dst3_launch_t<6>(md, hp, a, inverse); break;
+    case 8: dst3_launch_t<8>(md, hp, a, inverse); break;
+    case 10: dst3_launch_t<10>(md, hp, a, inverse); break;
     default: throw std::runtime_error("helmholtz: no fast DST plan");
   }
 }
 
-static void dst4_plan(qgcm_model *md, HelmPlan &hp) {
-  hp.fast = dst4_r4(hp);
+static void dst3_plan(qgcm_model *md, HelmPlan &hp) {
+  hp.fast = dst3_r3(hp);
   if (!hp.fast) return;
-  const int R1 = 2, R2 = 10, R3 = 12, R4 = hp.fast;
-  const int M = hp.m, N = hp.n, L1 = M / R1, L4 = M / R4;
+  const int R1 = 16, R2 = 15, R3 = hp.fast;
+  const int M = hp.m, N = hp.n, L1 = M / R1, L3 = M / R3;
   const long double PI_L = 3.141592653589793238462643383279502884L;
-  std::vector<double2> s1b(2 * 256), t2, t3, t4(2 * L4), wb(L4);
-  (void)L1;
-  for (int j = 0; j < 256; ++j)
+  std::vector<double2> s1b(2 * L1), t2, t3(2 * L3), wb(L3);
+  for (int j = 0; j < L1; ++j)
     for (int e = 0; e < 2; ++e) {
       const long double ang = PI_L * (2 * j + e) / N;
       s1b[2 * j + e] = make_double2((double)(2.0L * sinl(ang)), (double)(2.0L * cosl(ang)));
     }
-  auto pass_table = [&](std::vector<double2> &tw, int R, int Ns) {
-    for (int q = 1; q < R; ++q)
-      for (int k = 0; k < Ns; ++k) {
-        const long double ang = -2.0L * PI_L * (long double)q * k / ((long double)Ns * R);
-        tw.push_back(make_double2((double)cosl(ang), (double)sinl(ang)));
-      }
-  };
-  pass_table(t2, R2, R1);
-  pass_table(t3, R3, R1 * R2);
-  for (int t = 0; t < L4; ++t) {
+  for (int q = 1; q < R2; ++q)
+    for (int k = 0; k < R1; ++k) {
+      const long double ang = -2.0L * PI_L * (long double)q * k / ((long double)R1 * R2);
+      t2.push_back(make_double2((double)cosl(ang), (double)sinl(ang)));
+    }
+  for (int t = 0; t < L3; ++t) {
     for (int e = 1; e <= 2; ++e) {
       const long double ang = -2.0L * PI_L * e * t / M;
-      t4[2 * t + e - 1] = make_double2((double)cosl(ang), (double)sinl(ang));
+      t3[2 * t + e - 1] = make_double2((double)cosl(ang), (double)sinl(ang));
     }
     const long double ang = -2.0L * PI_L * t / N;
     wb[t] = make_double2((double)cosl(ang), (double)sinl(ang));
   }
   for (int q = 0; q < 16; ++q) {
-    hp.c1[q] = (double)cosl(PI_L * 512 * q / N);     // first pass: butterfly j = t + 256 q
-    hp.s1c[q] = (double)sinl(PI_L * 512 * q / N);
-    const long double ang = -2.0L * PI_L * q * L4 / N;
+    hp.c1[q] = (double)cosl(PI_L * q / R1);
+    hp.s1c[q] = (double)sinl(PI_L * q / R1);
+    const long double ang = -2.0L * PI_L * q * L3 / N;
     hp.wnr[q] = make_double2((double)cosl(ang), (double)sinl(ang));
   }
   auto up = [&](const std::vector<double2> &v) {
@@ -934,7 +907,7 @@ static void dst4_plan(qgcm_model *md, HelmPlan &hp) {
     QG_CUDA(cudaMemcpy(d, v.data(), sizeof(double2) * v.size(), cudaMemcpyHostToDevice));
     return d;
   };
-  hp.s1base = up(s1b); hp.tw2 = up(t2); hp.tw3 = up(t3); hp.tw4base = up(t4); hp.wnbase = up(wb);
+  hp.s1base = up(s1b); hp.tw2 = up(t2); hp.tw3base = up(t3); hp.wnbase = up(wb);
   int dev = 0, sms = 0;
   QG_CUDA(cudaGetDevice(&dev));
   QG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1036,7 +1009,7 @@ void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, con
   hp.rowsum = (double *)dalloc(md, sizeof(double) * nmodes * hp.nyp);
   QG_CUDA(cudaMemset(hp.rowsum, 0, sizeof(double) * nmodes * hp.nyp));
   QG_CUDA(cudaFuncSetAttribute(k_xform, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.smem_bytes));
-  dst4_plan(md, hp);
+  dst3_plan(md, hp);
   // diagonal b(i) = bd2(i) - rdm2(m), src/q-gcm.F:929-973 and src/ocisubs.F:148-150
   const double PI = 3.14159265358979324, TWOPI = 6.28318530717958648;
   std::vector<double> bd2(hp.n, 0.0), b((size_t)nmodes * hp.n);
@@ -1092,7 +1065,7 @@ void helm_solve(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
   x.wrk = wrk; x.rowsum = hp.rowsum;
   dim3 gx(hp.nrows, nmodes);
   if (hp.fast)
-    dst4_launch(md, hp, wrk, lsz, nmodes, false);
+    dst3_launch(md, hp, wrk, lsz, nmodes, false);
   else
     QG_LAUNCH(md, "k_xform", gx, 256, hp.smem_bytes, k_xform, x);
   TriArgs t = tri_args(hp, wrk, lsz, nmodes);
@@ -1106,7 +1079,7 @@ void helm_solve(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
   auto kfin = k_tri_local<true>;
   QG_LAUNCH(md, "k_tri_local", gl, 128, 0, kfin, t);
   if (hp.fast) {
-    dst4_launch(md, hp, wrk, lsz, nmodes, true);
+    dst3_launch(md, hp, wrk, lsz, nmodes, true);
   } else {
     x.inverse = 1;
     QG_LAUNCH(md, "k_xform", gx, 256, hp.smem_bytes, k_xform, x);

@@ -81,9 +81,9 @@ struct HelmPlan {
   double *pt = nullptr;      // [nmodes][nchunk][ld] block-Thomas pivots of the interface system
   double *fg = nullptr;      // [nmodes][2][nchunk][ld] first/last local values -> interface rhs
   double *yx = nullptr;      // [nmodes][2][nchunk][ld] neighbour values per chunk (yprev, xnext)
-  // fast four-pass DST path (helmholtz.cu, k_dst4); fast = R4 of the plan or 0
+  // fast three-pass DST path (helmholtz.cu, k_dst3); fast = R3 of the plan (16, 15, R3) or 0
   int fast = 0, fast_grid = 0, fast_attr = 0;
-  double2 *s1base = nullptr, *tw2 = nullptr, *tw3 = nullptr, *tw4base = nullptr, *wnbase = nullptr;
+  double2 *s1base = nullptr, *tw2 = nullptr, *tw3base = nullptr, *wnbase = nullptr;
   double c1[16], s1c[16];
   double2 wnr[16];
   double *rowsum = nullptr;  // [nmodes][nyp]  xintp row sums of the solution
