@@ -81,7 +81,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def stop(self, first=0):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -91,7 +91,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[first:]:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -228,11 +228,20 @@ def main():
         m.sync()
         torch.cuda.synchronize()
 
-    ocean_steps(args.warmup, 1)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # nvidia-smi needs ~0.5 s before its first sample
+    ocean_steps(args.warmup, 1)
+    barrier()
+    if rank == 0:
+        # keep the GPU under the same load until the sampler is live, so that the samples
+        # taken while the timed region runs are not its start-up transient
+        t_w = time.time()
+        while len(sampler.rows) < 2 and time.time() - t_w < 5.0:
+            ocean_steps(5, 1)
+            m.sync()
+    barrier()
+    n_before = len(sampler.rows)
     l0 = m.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -241,7 +250,16 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = m.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        # a timed region shorter than the sampling period: keep stepping (untimed) until at
+        # least three samples under the identical load exist
+        t_w = time.time()
+        while len(sampler.rows) - n_before < 3 and time.time() - t_w < 3.0:
+            ocean_steps(5, 1)
+            m.sync()
+        clocks = sampler.stop(first=n_before)
+        clocks["note"] = "sampled every 100 ms from the start of the timed region, same step loop"
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
