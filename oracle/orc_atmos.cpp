@@ -528,14 +528,4 @@ void Model::amladf(double *tmrhs, double *hmrhs, const double *pa1) {
 #undef VE
 }
 
-// src/xfosubs.F:52-858 -- full coupled forcing; ocean-only configurations only ever
-// execute the Ekman tail (src/xfosubs.F:568-709).
-void Model::xforc() {
-  if (ocean_only) {
-    xforc_ocean_ekman();
-    return;
-  }
-  throw std::runtime_error("orc::xforc: coupled forcing not restated yet");
-}
-
 }  // namespace orc

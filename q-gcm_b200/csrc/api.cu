@@ -1,6 +1,7 @@
 // C ABI of libqgcm_b200.so (include/qgcm_b200.h): lifetime, state transfer and the
 // main-loop procedures of src/q-gcm.F:1222-1269, :1328-1407.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "qgcm_internal.h"
@@ -48,6 +49,18 @@ void prof_begin(qgcm_model *m, const char *name) {
 void prof_end(qgcm_model *m) {
   if (!m->prof) return;
   QG_CUDA(cudaEventRecord(m->prof_recs.back().e1, m->stream));
+}
+
+void launch_check(qgcm_model *m, const char *name) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e == cudaSuccess) {
+    static const bool dbg = getenv("QGCM_DEBUG_SYNC") != nullptr;   // serialise to pin asynchronous faults
+    if (!dbg) return;
+    e = cudaStreamSynchronize(m->stream);
+    if (e == cudaSuccess) return;
+  }
+  cudaGetLastError();
+  throw std::runtime_error(std::string("kernel ") + name + ": " + cudaGetErrorString(e));
 }
 
 static void add_field(qgcm_model *m, const char *name, int nx, int ny, int nl, int ld, size_t lsz = 0) {
@@ -182,7 +195,7 @@ static qgcm_model *create(const qgcm_config *cfg) {
       m->astnew = (double *)dalloc(m, sizeof(double) * g.lsz);
       m->hmnew = (double *)dalloc(m, sizeof(double) * g.lsz);
       helm_plan_create(m, m->hpa, g, 1, cfg->rdm2at, g.nl);
-      const size_t nb = (size_t)((g.nxt + 63) / 64) * ((g.nyt + 7) / 8);
+      const size_t nb = (size_t)((g.nxt + 63) / 64) * ((g.nyt + 3) / 4);   // aml tiles are 64 x 4
       red = std::max(red, 3 * nb + 4 * (size_t)g.nyp);
     }
     m->red_elems = red + 64;

@@ -1008,7 +1008,15 @@ void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, con
   hp.yx = (double *)dalloc(md, sizeof(double) * nmodes * 2 * hp.nchunk * row);
   hp.rowsum = (double *)dalloc(md, sizeof(double) * nmodes * hp.nyp);
   QG_CUDA(cudaMemset(hp.rowsum, 0, sizeof(double) * nmodes * hp.nyp));
-  QG_CUDA(cudaFuncSetAttribute(k_xform, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.smem_bytes));
+  {
+    // the attribute belongs to the kernel, not to the plan: only ever raise it (an ocean and
+    // an atmosphere plan of different lengths coexist in coupled models)
+    static size_t xform_smem_cap = 48 * 1024;
+    if (hp.smem_bytes > xform_smem_cap) {
+      QG_CUDA(cudaFuncSetAttribute(k_xform, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.smem_bytes));
+      xform_smem_cap = hp.smem_bytes;
+    }
+  }
   dst3_plan(md, hp);
   // diagonal b(i) = bd2(i) - rdm2(m), src/q-gcm.F:929-973 and src/ocisubs.F:148-150
   const double PI = 3.14159265358979324, TWOPI = 6.28318530717958648;

@@ -24,6 +24,7 @@
   do {                                                              \
     qg::prof_begin(m, name);                                        \
     kern<<<grid, block, smem, (m)->stream>>>(__VA_ARGS__);          \
+    qg::launch_check(m, name);                                      \
     qg::prof_end(m);                                                \
     (m)->launches++;                                                \
   } while (0)
@@ -90,6 +91,20 @@ struct HelmPlan {
   double *ayrow = nullptr;   // [nmodes][2]    periodic: line sums of rows 2 and nyp-1
 };
 
+// Scratch and tables of the coupled forcing xforc (atmos.cu); built on first use
+struct XfPlan {
+  bool ready = false;
+  int nxf = 0, nyf = 0, ldf = 0;         // ocean-resolution atmosphere p grid (nxpaor x nypaor) and its pitch
+  double *u1 = nullptr, *v1 = nullptr;   // layer-1 geostrophic velocity at atmosphere p points [nypa][ld]
+  double *taux = nullptr, *tauy = nullptr;   // stress on the fine grid [nyf][ldf]
+  double *stb = nullptr;                 // bicubic weights [5][(ndxr+1)^2][16]: general, u-south, v-south, u-north, v-north
+  int *iam = nullptr, *iap = nullptr, *jam = nullptr, *jap = nullptr;   // bilint subscripts (0-based)
+  double *wpx = nullptr, *wmx = nullptr, *wpy = nullptr, *wmy = nullptr;
+  double *fsp_o = nullptr, *fsp_a = nullptr;   // fsprim at ocean / atmosphere T rows
+  double *part = nullptr;                // per-block partial sums
+  int npart = 0;
+};
+
 struct Model;
 
 }  // namespace qg
@@ -124,6 +139,7 @@ struct qgcm_model {
   double *d_red = nullptr;               // reduction scratch
   size_t red_elems = 0;
   qg::HelmPlan hpo, hpa;
+  qg::XfPlan xf;
   double *wrk_o = nullptr, *wrk_a = nullptr;   // modal work arrays [nl][nyp][ld]
   double *xfo = nullptr, *xfa = nullptr, *sstnew = nullptr, *astnew = nullptr, *hmnew = nullptr;
   std::vector<void *> allocs;
@@ -162,6 +178,7 @@ namespace qg {
 void *dalloc(qgcm_model *m, size_t bytes);
 void prof_begin(qgcm_model *m, const char *name);
 void prof_end(qgcm_model *m);
+void launch_check(qgcm_model *m, const char *name);   // names the kernel whose launch was rejected
 
 // helmholtz.cu
 void helm_plan_create(qgcm_model *m, HelmPlan &hp, const Grid &g, int kind, const double *rdm2, int nmodes);

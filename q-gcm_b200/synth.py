@@ -116,7 +116,9 @@ def atmos_state(p, cfg, kind="random", seed=SEED + 1):
     rad = cfg._radiation
     st = {}
     pa = np.zeros((nxp, nyp, nl))
-    amps = [2.0e3, 1.0e3, 0.5e3] + [0.25e3] * max(0, nl - 3)
+    # keep the geostrophic wind of the full-size deck (30720 km channel) on reduced grids
+    scale = min(1.0, (p.nxta * p.ndxr * p.dxo) / 3.072e7)
+    amps = [a * scale for a in [2.0e3, 1.0e3, 0.5e3] + [0.25e3] * max(0, nl - 3)]
     if kind != "eddy":
         for k in range(nl):
             pa[:, :, k] = _bandlimited(rng, nxp, nyp, amps[k], True)

@@ -163,3 +163,76 @@ def test_transform_lengths(qg, pyorc, nxto, cyc):
     sg = gpu.helmholtz(0, rhs, b)
     sc = cpu.helmholtz(0, rhs, b)
     assert rel_l2(sg, sc) <= 1e-12
+
+
+# ------------------------------------------------------------------------------------------
+# coupled decks: xforc (src/xfosubs.F), aml (src/amlsubs.F), qgastep, atinvq, atqzbd
+# ------------------------------------------------------------------------------------------
+ATMOS_CHECK = ("pa", "pam", "qa", "qam", "ast", "astm", "hmixa", "hmixam", "entat", "wekta", "wekpa",
+               "tauxa", "tauya", "uekat", "vekat", "fnetat")
+COUPLED = ["cpl_dg", "cpl_so", "cpl_dg_udiff"]
+
+
+def coupled_configs(qg):
+    """reduced double-gyre (box ocean, sb_hflux) and Southern-Ocean (channel, fnot < 0, nb_hflux)
+    coupled decks at the decks' own grid ratio ndxr = 16, plus the velocity-difference stress"""
+    dg = qg.named_config("dg_coupled").scaled(6, 5, ndxr=16, name="cpl_dg")             # ocean 96 x 80, atmos 12 x 10
+    so = qg.named_config("so_coupled").scaled(12, 3, nxta=12, nyta=9, ndxr=16, name="cpl_so")   # ocean 192 x 48
+    ud = qg.named_config("dg_coupled").scaled(6, 5, ndxr=16, name="cpl_dg_udiff")
+    ud.flags = list(ud.flags) + ["tau_udiff"]
+    return {"cpl_dg": dg, "cpl_so": so, "cpl_dg_udiff": ud}
+
+
+XF_SCALARS = ("txisat", "txinat", "arlaav", "slhfav", "oradav", "arocav")
+
+
+@pytest.mark.parametrize("case", COUPLED)
+def test_coupled_init_and_xforc(qg, pyorc, case):
+    p = coupled_configs(qg)[case]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)     # ends with the first xforc and homsol
+    compare(gpu, cpu, ATMOS_CHECK + ("tauxo", "tauyo", "wekto", "wekpo", "fnetoc", "qo", "qom"), label=case)
+    compare(gpu, cpu, ("pch1at", "pch2at", "pbhat"), label=case)
+    compare_scalars(gpu, cpu, XF_SCALARS, tol=1e-10)
+    compare_scalars(gpu, cpu, ("dpiat", "dpiatp"), tol=1e-11, floor=float(np.abs(cpu.get_field("pa")).sum() * (p.ndxr * p.dxo) ** 2))
+
+
+@pytest.mark.parametrize("ndxr", [3, 5, 8])
+def test_xforc_grid_ratios(qg, pyorc, ndxr):
+    """odd ratios exercise the half-weight box average and the two-row line integrals
+    (src/xfosubs.F:446-471, :493-505)"""
+    p = qg.named_config("dg_coupled").scaled(6, 5, ndxr=ndxr, name="xf_ndxr%d" % ndxr)
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    compare(gpu, cpu, ("tauxa", "tauya", "uekat", "vekat", "wekta", "wekpa", "tauxo", "tauyo", "wekto", "wekpo",
+                       "fnetoc", "fnetat"), label="ndxr=%d" % ndxr)
+    compare_scalars(gpu, cpu, XF_SCALARS, tol=1e-10)
+
+
+@pytest.mark.parametrize("case", COUPLED)
+def test_coupled_each_procedure(qg, pyorc, case):
+    """one coupled step in main-loop order (src/q-gcm.F:1222-1269), compared after every call"""
+    p = coupled_configs(qg)[case]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    for step in ("xforc", "oml", "qgostep", "ocinvq", "ocqbdy", "aml", "qgastep", "atinvq", "atqzbd"):
+        getattr(gpu, step)()
+        getattr(cpu, step)()
+        compare(gpu, cpu, OCEAN_CHECK + ("tauxo", "tauyo", "fnetoc") + ATMOS_CHECK, label="%s after %s" % (case, step))
+    compare_scalars(gpu, cpu, ("cfraat", "centat"), tol=1e-9)
+    compare_scalars(gpu, cpu, ("xan",), tol=1e-11, floor=float(np.abs(cpu.get_field("entat")).sum() * (p.ndxr * p.dxo) ** 2))
+    compare_scalars(gpu, cpu, ("atmcs", "atmcn"), tol=1e-9)
+
+
+@pytest.mark.parametrize("case", COUPLED)
+def test_coupled_steps_and_drift(qg, pyorc, case):
+    """nt = 1..7 (three ocean steps at nstr = 3, both time-level averages at nt = 1), then on to
+    100 atmosphere steps with the documented drift bound"""
+    p = coupled_configs(qg)[case]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    gpu.run(1, 7)
+    cpu.run(1, 7)
+    compare(gpu, cpu, OCEAN_CHECK + ATMOS_CHECK, tol=1e-10, label=case)
+    gpu.run(8, 100)
+    cpu.run(8, 100)
+    for name in ("po", "qo", "sst", "pa", "qa", "ast", "hmixa"):
+        e = rel_l2(gpu.get_field(name), cpu.get_field(name))
+        assert e <= 1e-8, (case, name, e)
+        assert np.isfinite(gpu.get_field(name)).all()
