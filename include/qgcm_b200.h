@@ -198,6 +198,27 @@ int qgcm_atmos_step(qgcm_model *m);
  * atmosphere step unless ocean_only, time-level averaging on its cadence. */
 int qgcm_run(qgcm_model *m, int64_t nt_first, int64_t nt_last);
 
+/* ---- y-slab multi-GPU (new: the reference is single-node OpenMP over j, src/qgosubs.F:173-184)
+ *
+ * The ocean-only box decks (NAtl) partition into contiguous slabs of p rows, one per GPU, the
+ * same way the reference's OpenMP loops partition j.  cfg.nranks / cfg.rank select the slab;
+ * qgcm_set_field / qgcm_get_field still take the reference's GLOBAL host arrays: a slab
+ * uploads the rows it holds and downloads the rows it owns (the other rows of the host
+ * array are left untouched, so calling qgcm_get_field for every rank on one buffer
+ * assembles the global field).  With a communicator in place qgcm_constr, qgcm_homsol,
+ * qgcm_qcomp_ocean, qgcm_ocean_step, qgcm_tlavg_ocean and qgcm_run act on the partition;
+ * the per-procedure calls qgcm_oml / qgcm_ocinvq are single-GPU only. */
+
+/* p rows [*jp0, *jp0 + *nyp_own) of nyp_global owned by `rank`; pure host arithmetic */
+int qgcm_slab_bounds(int32_t nyp_global, int32_t nranks, int32_t rank, int32_t *jp0, int32_t *nyp_own);
+/* one process per GPU: rank 0 fills a 128-byte NCCL id, the host program broadcasts it
+ * (MPI_Bcast in the Fortran driver, torch.distributed in bench.py), every rank joins */
+int qgcm_nccl_unique_id(void *id128);
+int qgcm_comm_init_nccl(qgcm_model *m, const void *id128);
+/* all ranks in one process on one device (tests on a single GPU): models[r] must be rank r
+ * of an n-rank partition; afterwards a partition call on any member steps every rank */
+int qgcm_group_create(qgcm_model **models, int32_t n);
+
 /* ---- instrumentation ---------------------------------------------------------- */
 
 /* number of kernels launched by this model since creation */

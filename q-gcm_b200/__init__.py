@@ -12,5 +12,5 @@ There is no CPU fallback: constructing a Model without the CUDA library raises.
 """
 from .abi import QgcmConfig, QgcmScalars, FLAGS, NLMAX  # noqa: F401
 from .params import Params, named_config, build_config  # noqa: F401
-from .model import Model, CModel, load_library, library_path  # noqa: F401
+from .model import Model, CModel, SlabGroup, slab_config, slab_bounds, load_library, library_path  # noqa: F401
 from . import synth  # noqa: F401

@@ -63,9 +63,16 @@ void launch_check(qgcm_model *m, const char *name) {
   throw std::runtime_error(std::string("kernel ") + name + ": " + cudaGetErrorString(e));
 }
 
-static void add_field(qgcm_model *m, const char *name, int nx, int ny, int nl, int ld, size_t lsz = 0) {
+static void add_field(qgcm_model *m, const char *name, int nx, int ny, int nl, int ld, size_t lsz = 0, const Grid *slab = nullptr) {
   qgcm_model::Field f;
   f.nx = nx; f.ny = ny; f.nl = nl; f.ld = ld; f.lsz = lsz;
+  f.nyg = ny; f.joff = 0; f.o0 = 0; f.o1 = ny;
+  if (slab && ld) {   // gridded field of a y-slab: host arrays are global, the device holds local rows
+    f.nyg = slab->nyp_g - (slab->nyp - ny);   // p fields: nyp_g, T fields: nyp_g - 1
+    f.joff = slab->jg0;
+    f.o0 = slab->own0;
+    f.o1 = std::min(slab->own1, ny);
+  }
   // gridded fields (ld != 0) use the grid's p-row layer stride lsz for T and p arrays
   // alike; dense (ld == 0) arrays are nx*ny*nl
   f.elems = ld ? lsz * nl : (size_t)nx * ny * nl;
@@ -82,6 +89,19 @@ static void make_grid(Grid &g, int nxt, int nyt, int nl, int cyclic, double dx, 
   g.norm = 1.0 / ((double)nxt * nyt);
   g.xl = nxt * dx; g.yl = nyt * dx;
   g.tdt = 2.0 * dt;
+  g.jg0 = 0; g.nyp_g = g.nyp; g.own0 = 0; g.own1 = g.nyp;
+}
+
+// y-slab of the global grid for (nranks, rank): owned p rows plus HALO rows on the inner sides
+static void make_slab(Grid &g, int nranks, int rank) {
+  const Grid full = g;
+  int p0, p1;
+  slab_bounds(full.nyp, nranks, rank, &p0, &p1);
+  const int lo = std::max(0, p0 - HALO), hi = std::min(full.nyp, p1 + HALO);
+  g.nyp = hi - lo; g.nyt = g.nyp - 1;
+  g.lsz = (size_t)g.ld * g.nyp;
+  g.jg0 = lo; g.nyp_g = full.nyp; g.own0 = p0 - lo; g.own1 = p1 - lo;
+  // norm, yl keep the global values
 }
 
 static double *upload(qgcm_model *m, const std::vector<double> &v) {
@@ -104,7 +124,6 @@ static qgcm_model *create(const qgcm_config *cfg) {
   if (prop.major < 10) throw std::runtime_error("qgcm_create: kernels are built for sm_100a (Blackwell) only");
   if (cfg->nlo < 2 || cfg->nlo > QGCM_NLMAX || cfg->nla < 2 || cfg->nla > QGCM_NLMAX)
     throw std::runtime_error("qgcm_create: layer count out of range");
-  if (cfg->nranks != 1) throw std::runtime_error("qgcm_create: nranks>1 needs qgcm_create_slab (not in this build)");
   qgcm_model *m = new qgcm_model();
   try {
     m->cfg = *cfg;
@@ -126,6 +145,16 @@ static qgcm_model *create(const qgcm_config *cfg) {
     m->rrcpoc = 1.0 / (cfg->rhooc * cfg->cpoc);
     m->raoro = cfg->rhoat / cfg->rhooc;
     make_grid(m->go, cfg->nxto, cfg->nyto, cfg->nlo, m->cyclic, cfg->dxo, cfg->fnot, m->dto);
+    m->nranks = std::max(1, (int)cfg->nranks);
+    m->rank = m->nranks > 1 ? cfg->rank : 0;
+    if (m->nranks > 1) {
+      if (!m->ocean_only || m->cyclic)
+        throw std::runtime_error("qgcm_create: y-slab partitioning covers the ocean-only box decks (NAtl); "
+                                 "coupled and channel decks run on one GPU");
+      if (m->rank < 0 || m->rank >= m->nranks) throw std::runtime_error("qgcm_create: bad rank");
+      if ((cfg->nyto + 1) / m->nranks < 4 * HALO) throw std::runtime_error("qgcm_create: slabs thinner than 4 halo widths");
+      make_slab(m->go, m->nranks, m->rank);
+    }
     make_grid(m->ga, cfg->nxta, cfg->nyta, cfg->nla, 1, dxa, cfg->fnot, m->dta);
     const double yla = cfg->nyta * dxa;
     for (int k = 0; k < NLMAX; ++k) {
@@ -140,28 +169,29 @@ static qgcm_model *create(const qgcm_config *cfg) {
     }
     m->d_scal = (qgcm_scalars *)dalloc(m, sizeof(qgcm_scalars));
     m->d_coef = (double *)dalloc(m, sizeof(double) * 128);
+    m->d_cv = (double *)dalloc(m, sizeof(double) * 32);
     size_t red = 0;
     if (m->has_ocean) {
       const Grid &g = m->go;
       std::vector<double> ypo(g.nyp), yporel(g.nyp), ytorel(g.nyt);
       for (int j = 1; j <= g.nyp; ++j) {
-        ypo[j - 1] = (cfg->ny1 - 1) * dxa + (j - 1) * g.dx;
+        ypo[j - 1] = (cfg->ny1 - 1) * dxa + (g.jg0 + j - 1) * g.dx;
         yporel[j - 1] = ypo[j - 1] - 0.5 * yla;
       }
       for (int j = 1; j <= g.nyt; ++j) ytorel[j - 1] = (ypo[j - 1] + 0.5 * g.dx) - 0.5 * yla;
       m->h_ypo = ypo;
       m->yporel = upload(m, yporel);
       m->ytorel = upload(m, ytorel);
-      for (const char *n : {"po", "pom", "qo", "qom"}) add_field(m, n, g.nxp, g.nyp, g.nl, g.ld, g.lsz);
-      for (const char *n : {"wekpo", "entoc", "ddynoc", "tauxo", "tauyo"}) add_field(m, n, g.nxp, g.nyp, 1, g.ld, g.lsz);
-      for (const char *n : {"sst", "sstm", "wekto", "fnetoc"}) add_field(m, n, g.nxt, g.nyt, 1, g.ld, g.lsz);
-      add_field(m, "sstbar", g.nyt, 1, 1, 0);
+      for (const char *n : {"po", "pom", "qo", "qom"}) add_field(m, n, g.nxp, g.nyp, g.nl, g.ld, g.lsz, &g);
+      for (const char *n : {"wekpo", "entoc", "ddynoc", "tauxo", "tauyo"}) add_field(m, n, g.nxp, g.nyp, 1, g.ld, g.lsz, &g);
+      for (const char *n : {"sst", "sstm", "wekto", "fnetoc"}) add_field(m, n, g.nxt, g.nyt, 1, g.ld, g.lsz, &g);
+      add_field(m, "sstbar", g.nyp_g - 1, 1, 1, 0);
       if (m->cyclic) {
         add_field(m, "pch1oc", g.nyp, g.nl - 1, 1, 0);
         add_field(m, "pch2oc", g.nyp, g.nl - 1, 1, 0);
         add_field(m, "pbhoc", g.nyp, 1, 1, 0);
       } else {
-        add_field(m, "ochom", g.nxp, g.nyp, g.nl - 1, g.ld, g.lsz);
+        add_field(m, "ochom", g.nxp, g.nyp, g.nl - 1, g.ld, g.lsz, &g);
       }
       m->wrk_o = (double *)dalloc(m, sizeof(double) * g.lsz * g.nl);
       m->xfo = (double *)dalloc(m, sizeof(double) * g.lsz);
@@ -214,7 +244,7 @@ static qgcm_model::Field &lookup(qgcm_model *m, const char *name, int64_t n) {
   auto it = m->fields.find(name);
   if (it == m->fields.end()) throw std::runtime_error(std::string("unknown field '") + name + "'");
   qgcm_model::Field &f = it->second;
-  if (n >= 0 && n != (int64_t)f.nx * f.ny * f.nl)
+  if (n >= 0 && n != (int64_t)f.nx * f.nyg * f.nl)
     throw std::runtime_error(std::string("field '") + name + "': element count mismatch");
   return f;
 }
@@ -226,15 +256,17 @@ static void copy_field(qgcm_model *m, qgcm_model::Field &f, double *host, bool t
     else QG_CUDA(cudaMemcpyAsync(host, f.d, bytes, cudaMemcpyDeviceToHost, m->stream));
   } else {
     const size_t lsz = f.lsz;   // device layer stride
+    // host arrays are the reference's global arrays; a slab uploads its local rows (owned +
+    // halo) and downloads the rows it owns, leaving the rest of the host array untouched
     for (int k = 0; k < f.nl; ++k) {
       double *d = f.d + (size_t)k * lsz;
-      double *h = host + (size_t)k * f.nx * f.ny;
+      double *h = host + (size_t)k * f.nx * f.nyg + (size_t)f.joff * f.nx;
       if (to_device)
         QG_CUDA(cudaMemcpy2DAsync(d, sizeof(double) * f.ld, h, sizeof(double) * f.nx, sizeof(double) * f.nx, f.ny,
                                   cudaMemcpyHostToDevice, m->stream));
       else
-        QG_CUDA(cudaMemcpy2DAsync(h, sizeof(double) * f.nx, d, sizeof(double) * f.ld, sizeof(double) * f.nx, f.ny,
-                                  cudaMemcpyDeviceToHost, m->stream));
+        QG_CUDA(cudaMemcpy2DAsync(h + (size_t)f.o0 * f.nx, sizeof(double) * f.nx, d + (size_t)f.o0 * f.ld, sizeof(double) * f.ld,
+                                  sizeof(double) * f.nx, f.o1 - f.o0, cudaMemcpyDeviceToHost, m->stream));
     }
   }
   QG_CUDA(cudaStreamSynchronize(m->stream));
@@ -244,6 +276,7 @@ void launch_xforc(qgcm_model *m);
 void launch_aml(qgcm_model *m);
 
 static void ocean_step(qgcm_model *m) {
+  if (m->nranks > 1) { slab_ocean_step(ranks_of(m)); return; }
   launch_oml(m);
   launch_qgostep(m);
   launch_ocinvq(m);
@@ -272,13 +305,14 @@ int qgcm_destroy(qgcm_model *m) {
   cudaSetDevice(m->cfg.device);
   cudaStreamSynchronize(m->stream);
   for (void *p : m->allocs) cudaFree(p);
-  cudaStreamDestroy(m->stream);
+  if (m->nccl) { try { nccl_destroy(m); } catch (...) {} }
+  if (!m->shared_stream) cudaStreamDestroy(m->stream);
   delete m;
   return 0;
 }
 
 int qgcm_field_size(qgcm_model *m, const char *name, int64_t *n) {
-  QG_TRY(qgcm_model::Field &f = lookup(m, name, -1); *n = (int64_t)f.nx * f.ny * f.nl);
+  QG_TRY(qgcm_model::Field &f = lookup(m, name, -1); *n = (int64_t)f.nx * f.nyg * f.nl);
 }
 int qgcm_set_field(qgcm_model *m, const char *name, const double *host, int64_t n) {
   QG_TRY(copy_field(m, lookup(m, name, n), const_cast<double *>(host), true));
@@ -299,8 +333,9 @@ int qgcm_sync(qgcm_model *m) { QG_TRY(QG_CUDA(cudaStreamSynchronize(m->stream)))
 int qgcm_constr(qgcm_model *m) { QG_TRY(launch_constr(m)); }
 int qgcm_homsol(qgcm_model *m) { QG_TRY(launch_homsol(m)); }
 int qgcm_qcomp_ocean(qgcm_model *m) {
-  QG_TRY(launch_qcomp(m, true, m->F("qo"), m->F("po")); launch_qcomp(m, true, m->F("qom"), m->F("pom"));
-         launch_ocqbdy(m, m->F("qo"), m->F("po")); launch_ocqbdy(m, m->F("qom"), m->F("pom")));
+  QG_TRY(if (m->nranks > 1) { slab_qcomp_ocean(ranks_of(m)); } else {
+         launch_qcomp(m, true, m->F("qo"), m->F("po")); launch_qcomp(m, true, m->F("qom"), m->F("pom"));
+         launch_ocqbdy(m, m->F("qo"), m->F("po")); launch_ocqbdy(m, m->F("qom"), m->F("pom")); });
 }
 int qgcm_qcomp_atmos(qgcm_model *m) {
   QG_TRY(launch_qcomp(m, false, m->F("qa"), m->F("pa")); launch_qcomp(m, false, m->F("qam"), m->F("pam"));
@@ -354,7 +389,7 @@ int qgcm_aml(qgcm_model *m) { QG_TRY(launch_aml(m)); }
 int qgcm_qgastep(qgcm_model *m) { QG_TRY(launch_qgastep(m)); }
 int qgcm_atinvq(qgcm_model *m) { QG_TRY(launch_atinvq(m)); }
 int qgcm_atqzbd(qgcm_model *m) { QG_TRY(launch_atqzbd(m, m->F("qa"), m->F("pa"))); }
-int qgcm_tlavg_ocean(qgcm_model *m) { QG_TRY(launch_tlavg_ocean(m)); }
+int qgcm_tlavg_ocean(qgcm_model *m) { QG_TRY(slab_tlavg_ocean(ranks_of(m))); }
 int qgcm_tlavg_atmos(qgcm_model *m) { QG_TRY(launch_tlavg_atmos(m)); }
 int qgcm_ocean_step(qgcm_model *m) { QG_TRY(ocean_step(m)); }
 int qgcm_atmos_step(qgcm_model *m) { QG_TRY(atmos_step(m)); }
@@ -372,11 +407,25 @@ int qgcm_run(qgcm_model *m, int64_t nt_first, int64_t nt_last) {
         if (m->has_ocean) ocean_step(m);
       }
       if (m->has_atmos) atmos_step(m);
-      if (m->has_ocean && ((nt - 1) % (25 * (int64_t)nstr) == 0)) launch_tlavg_ocean(m);
+      if (m->has_ocean && ((nt - 1) % (25 * (int64_t)nstr) == 0)) slab_tlavg_ocean(ranks_of(m));
       if (m->has_atmos && ((nt - 1) % 100 == 0)) launch_tlavg_atmos(m);
     }
   });
 }
+
+// ---- y-slab multi-GPU (ocean-only box decks) ----
+int qgcm_slab_bounds(int32_t nyp_global, int32_t nranks, int32_t rank, int32_t *jp0, int32_t *nyp_own) {
+  QG_TRY({
+    if (nranks < 1 || rank < 0 || rank >= nranks || nyp_global < nranks) throw std::runtime_error("qgcm_slab_bounds: bad arguments");
+    int p0, p1;
+    slab_bounds(nyp_global, nranks, rank, &p0, &p1);
+    *jp0 = p0;
+    *nyp_own = p1 - p0;
+  });
+}
+int qgcm_nccl_unique_id(void *id128) { QG_TRY(nccl_unique_id(id128)); }
+int qgcm_comm_init_nccl(qgcm_model *m, const void *id128) { QG_TRY(nccl_init(m, id128)); }
+int qgcm_group_create(qgcm_model **models, int32_t n) { QG_TRY(group_create(models, n)); }
 
 int64_t qgcm_launch_count(qgcm_model *m) { return m ? m->launches : 0; }
 

@@ -211,7 +211,7 @@ struct XfArgs {
   FftDev f;
   int kind;        // 0 DST-I, 1 real FFT
   int inverse;     // 0 forward (rhs -> spectrum), 1 inverse (tridiagonal solution -> field)
-  int ld, nyp, nxp;
+  int ld, nyp, nxp, row0;
   size_t lsz;      // mode stride
   double *wrk;
   double *rowsum;                // [nmodes][nyp] (inverse only)
@@ -232,9 +232,9 @@ __global__ void __launch_bounds__(256, 2) k_xform(XfArgs a) {
   const int N = a.f.n, M = a.f.m;
   double2 *A = smem2, *B = smem2 + M;
   double *red = reinterpret_cast<double *>(smem2 + 2 * M);
-  const int r = blockIdx.x;            // interior row index, j = r + 2
+  const int r = blockIdx.x;            // solved row index, local row r + row0
   const int mode = blockIdx.y;
-  double *__restrict__ row = a.wrk + (size_t)mode * a.lsz + (size_t)(r + 1) * a.ld;
+  double *__restrict__ row = a.wrk + (size_t)mode * a.lsz + (size_t)(r + a.row0) * a.ld;
   double *Ar = reinterpret_cast<double *>(A);
   const int T = blockDim.x, t = threadIdx.x;
   const int lane = t & 31, w = t >> 5, nw = T >> 5;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256, 2) k_xform(XfArgs a) {
         row[a.nxp - 1] = 0.0;
       }
       const double s = block_sum(part, red);
-      if (t == 0) a.rowsum[(size_t)mode * a.nyp + (r + 1)] = s;
+      if (t == 0) a.rowsum[(size_t)mode * a.nyp + (r + a.row0)] = s;
     }
   } else if (!a.inverse) {
     // ---------------- forward real FFT, packed order (fft.doc:96-114) ----------------
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(256, 2) k_xform(XfArgs a) {
     if (t == 0) row[a.nxp - 1] = Zr[0];
     const double s = block_sum(part, red);
     // xintp row sum: 0.5*v(1) + sum_{2}^{nxp-1} + 0.5*v(nxp), v(nxp) = v(1)
-    if (t == 0) a.rowsum[(size_t)mode * a.nyp + (r + 1)] = 0.5 * Zr[0] + s + 0.5 * Zr[0];
+    if (t == 0) a.rowsum[(size_t)mode * a.nyp + (r + a.row0)] = 0.5 * Zr[0] + s + 0.5 * Zr[0];
   }
 }
 
@@ -456,8 +456,8 @@ __host__ __device__ constexpr int dst3_seg(int M) {
 }
 
 struct Dst3Args {
-  int nitems, nrows;        // (mode,row) work items; interior rows per mode
-  int ld, nyp, nxp;
+  int nitems, nrows;        // (mode,row) work items; solved rows per mode
+  int ld, nyp, nxp, row0;
   size_t lsz;
   double *wrk;
   double *rowsum;
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
     if (item < a.nitems) {
       const int mode = item / a.nrows, r = item - mode * a.nrows;
       mbar_expect_tx(bar, N * 8);
-      bulk_g2s(in_s, a.wrk + (size_t)mode * a.lsz + (size_t)(r + 1) * a.ld, N * 8, bar);
+      bulk_g2s(in_s, a.wrk + (size_t)mode * a.lsz + (size_t)(r + a.row0) * a.ld, N * 8, bar);
     }
   }
   __syncthreads();
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
     asm volatile("" : "+r"(t));
     const int lane = t & 31, wp = t >> 5;
     const int mode = item / a.nrows, r = item - mode * a.nrows;
-    double *__restrict__ row = a.wrk + (size_t)mode * a.lsz + (size_t)(r + 1) * a.ld;
+    double *__restrict__ row = a.wrk + (size_t)mode * a.lsz + (size_t)(r + a.row0) * a.ld;
     // ---- pass 1 (radix 16, no twiddles) fused with the DST pre-processing (dsint.f:17-30):
     //      t_e = (x_e - x_{N-e}) + 2 sin(e pi/N) (x_e + x_{N-e}),  z_n = t_{2n} + i t_{2n+1}.
     //      Output position i = 16 t + q is stored at i + (i >> 4) = 17 t + q: conflict-free
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       if (nxt < a.nitems) {
         const int m2 = nxt / a.nrows, r2 = nxt - m2 * a.nrows;
         mbar_expect_tx(bar, N * 8);
-        bulk_g2s(in_s, a.wrk + (size_t)m2 * a.lsz + (size_t)(r2 + 1) * a.ld, N * 8, bar);
+        bulk_g2s(in_s, a.wrk + (size_t)m2 * a.lsz + (size_t)(r2 + a.row0) * a.ld, N * 8, bar);
       }
     }
     // ---- pass 2 (radix 15), in place: all loads, barrier, autosort stores ----
@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
     if (INV) {
       if (t == 0) row[a.nxp - 1] = 0.0;
       const double sum = block_sum(part, red + 8);
-      if (t == 0) a.rowsum[(size_t)mode * a.nyp + (r + 1)] = sum;
+      if (t == 0) a.rowsum[(size_t)mode * a.nyp + (r + a.row0)] = sum;
     } else {
       __syncthreads();   // W is rewritten by the next row's first pass
     }
@@ -670,8 +670,9 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
 // y-direction: partitioned tridiagonal solve
 // --------------------------------------------------------------------------------------
 struct TriArgs {
-  int ld, nyp, nk, koff, nchunk, lastlen, nmodes;
+  int ld, nyp, nk, koff, nchunk, lastlen, nmodes, row0;
   size_t lsz;
+  int use_yx, nranks;
   double a, ftnorm;
   double *wrk;
   const double *bcoef;
@@ -731,7 +732,7 @@ __global__ void __launch_bounds__(128, 3) k_tri_local(TriArgs t) {
   if (s >= t.nk) return;
   const int col = t.koff + s;
   const int len = (c == t.nchunk - 1) ? t.lastlen : TRI_L;
-  double *__restrict__ base = t.wrk + (size_t)mode * t.lsz + (size_t)(1 + c * TRI_L) * t.ld + col;
+  double *__restrict__ base = t.wrk + (size_t)mode * t.lsz + (size_t)(t.row0 + c * TRI_L) * t.ld + col;
   const double *__restrict__ bi = t.binv + ((size_t)mode * TRI_L) * t.ld + col;
   const double a = t.a;
   const int ld = t.ld;
@@ -739,7 +740,7 @@ __global__ void __launch_bounds__(128, 3) k_tri_local(TriArgs t) {
   double u[TRI_L];
 #pragma unroll
   for (int j = 0; j < TRI_L; ++j) u[j] = base[(size_t)min(j, len - 1) * ld];   // rows >= len: harmless duplicates
-  if (FINAL && t.nchunk > 1) {
+  if (FINAL && t.use_yx) {
     const double yp = t.yx[fb + (size_t)c * ld], xn = t.yx[fb + (size_t)(t.nchunk + c) * ld];
     u[0] -= a * yp;
 #pragma unroll
@@ -758,11 +759,14 @@ __global__ void __launch_bounds__(128, 3) k_tri_local(TriArgs t) {
 #pragma unroll
     for (int j = 0; j < TRI_L; ++j)
       if (j < len) base[(size_t)j * ld] = fn * u[j];
-  } else {
+  } else if (t.nchunk > 1 || t.nranks > 1) {
     t.fg[fb + (size_t)c * ld] = u[0];                    // f_c : first row of the chunk
-    // g_c : last row of the chunk.  Only g_0..g_{C-2} enter the interface system and those
-    // chunks are always full, so the (ragged) last chunk may store a meaningless value.
-    t.fg[fb + (size_t)(t.nchunk + c) * ld] = u[TRI_L - 1];
+    // g_c : last row of the chunk (the ragged last chunk ends at row len-1; its g only matters
+    // to the slab coupling of multi-GPU runs)
+    double gl = u[TRI_L - 1];
+#pragma unroll
+    for (int j = 0; j < TRI_L - 1; ++j) gl = (j == len - 1) ? u[j] : gl;
+    t.fg[fb + (size_t)(t.nchunk + c) * ld] = gl;
   }
 }
 
@@ -815,12 +819,133 @@ __global__ void __launch_bounds__(128) k_tri_reduced(TriArgs t) {
   yp[0] = 0.0;
 }
 
-__global__ void k_zero_rows(double *wrk, size_t lsz, int ld, int nyp, int nxp, int nmodes) {
+// --------------------------------------------------------------------------------------
+// y-slab coupling (multi-GPU): a slab is one more level of the same partition.  Its local
+// solution (zero neighbours) has first/last rows F_s, G_s; the true rows obey
+//   X_s = F_s + alpha_s Y_{s-1} + eps_s X_{s+1},   Y_s = G_s + eps_s Y_{s-1} + alpha_s X_{s+1}
+// with (alpha_s, eps_s) the first/last values of the slab's left spike (Toeplitz: the right
+// spike is its mirror image).  F, G are all-gathered (2 rows per mode and rank), every rank
+// solves the 2*nranks unknowns per wavenumber redundantly and keeps its neighbours' rows.
+// --------------------------------------------------------------------------------------
+struct SlabArgs {
+  int ld, nk, koff, nchunk, lastlen, nmodes, nranks, rank;
+  int nrows_of[16];          // solved rows of every slab
+  double a;
+  const double *bcoef, *vl, *vll;
+  double *fg, *yx;
+  double *ae;                // [nmodes][nranks][2][ld]
+  double *send;              // [nmodes][2][ld]
+  const double *all;         // [nranks][nmodes][2][ld]
+  double *outer;             // [nmodes][2][ld]
+};
+
+// alpha_s = -a (T^-1)_{00}, eps_s = -a (T^-1)_{n-1,0}: one forward elimination per slab length
+__global__ void k_slab_spikes(SlabArgs t) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x, mode = blockIdx.y;
+  if (s >= t.nk) return;
+  const int col = t.koff + s;
+  const double b = t.bcoef[(size_t)mode * t.ld + col], a = t.a;
+  for (int r = 0; r < t.nranks; ++r) {
+    const int n = t.nrows_of[r];
+    double denom = b, cp = a / b, dp = -a / b;
+    for (int j = 1; j < n; ++j) {
+      denom = b - a * cp;
+      cp = a / denom;
+      dp = (-a * dp) / denom;
+    }
+    t.ae[(((size_t)mode * t.nranks + r) * 2 + 0) * t.ld + col] = -a / denom;
+    t.ae[(((size_t)mode * t.nranks + r) * 2 + 1) * t.ld + col] = dp;
+  }
+}
+
+// first and last rows of the slab-local solution from the chunk interface solve
+__global__ void k_slab_fg(SlabArgs t) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x, mode = blockIdx.y;
+  if (s >= t.nk) return;
+  const int col = t.koff + s, C = t.nchunk, ld = t.ld;
+  const size_t fb = ((size_t)mode * 2 * C) * ld + col, tb = ((size_t)mode * TRI_L) * ld + col;
+  double F = t.fg[fb], G = t.fg[fb + (size_t)(C + C - 1) * ld];
+  if (C > 1) {
+    const double eps = t.vl[tb + (size_t)(TRI_L - 1) * ld], epsl = t.vll[tb + (size_t)(t.lastlen - 1) * ld];
+    F += eps * t.yx[fb + (size_t)C * ld];                 // xn[0]: first row of chunk 1
+    G += epsl * t.yx[fb + (size_t)(C - 1) * ld];          // yp[C-1]: last row of chunk C-2
+  }
+  t.send[((size_t)mode * 2 + 0) * ld + col] = F;
+  t.send[((size_t)mode * 2 + 1) * ld + col] = G;
+}
+
+// the inter-slab system (2*nranks unknowns per wavenumber, dense elimination with partial
+// pivoting), the neighbour rows of this slab, and their effect on the first/last chunk's f, g
+__global__ void k_slab_solve(SlabArgs t) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x, mode = blockIdx.y;
+  if (s >= t.nk) return;
+  const int col = t.koff + s, N = t.nranks, n2 = 2 * N, ld = t.ld;
+  double A[16][17];
+  for (int i = 0; i < n2; ++i)
+    for (int j = 0; j <= n2; ++j) A[i][j] = 0.0;
+  for (int r = 0; r < N; ++r) {
+    const double al = t.ae[(((size_t)mode * N + r) * 2 + 0) * ld + col], ep = t.ae[(((size_t)mode * N + r) * 2 + 1) * ld + col];
+    const double F = t.all[(((size_t)r * t.nmodes + mode) * 2 + 0) * ld + col];
+    const double G = t.all[(((size_t)r * t.nmodes + mode) * 2 + 1) * ld + col];
+    const int ix = 2 * r, iy = 2 * r + 1;
+    A[ix][ix] = 1.0; A[iy][iy] = 1.0;
+    if (r > 0) { A[ix][2 * (r - 1) + 1] = -al; A[iy][2 * (r - 1) + 1] = -ep; }
+    if (r < N - 1) { A[ix][2 * (r + 1)] = -ep; A[iy][2 * (r + 1)] = -al; }
+    A[ix][n2] = F; A[iy][n2] = G;
+  }
+  for (int k = 0; k < n2; ++k) {
+    int p = k;
+    for (int i = k + 1; i < n2; ++i)
+      if (fabs(A[i][k]) > fabs(A[p][k])) p = i;
+    if (p != k)
+      for (int j = k; j <= n2; ++j) { const double tmp = A[k][j]; A[k][j] = A[p][j]; A[p][j] = tmp; }
+    const double inv = 1.0 / A[k][k];
+    for (int i = k + 1; i < n2; ++i) {
+      const double f = A[i][k] * inv;
+      if (f != 0.0)
+        for (int j = k; j <= n2; ++j) A[i][j] -= f * A[k][j];
+    }
+  }
+  double z[16];
+  for (int i = n2 - 1; i >= 0; --i) {
+    double acc = A[i][n2];
+    for (int j = i + 1; j < n2; ++j) acc -= A[i][j] * z[j];
+    z[i] = acc / A[i][i];
+  }
+  const double yprev = (t.rank > 0) ? z[2 * (t.rank - 1) + 1] : 0.0;
+  const double xnext = (t.rank < N - 1) ? z[2 * (t.rank + 1)] : 0.0;
+  t.outer[((size_t)mode * 2 + 0) * ld + col] = yprev;
+  t.outer[((size_t)mode * 2 + 1) * ld + col] = xnext;
+  // neighbour rows act on the first chunk through its left spike and on the last chunk
+  // through its right spike (mirror of its left spike)
+  const int C = t.nchunk;
+  if (C > 1) {
+    const size_t fb = ((size_t)mode * 2 * C) * ld + col, tb = ((size_t)mode * TRI_L) * ld + col;
+    const double alpha = t.vl[tb], eps = t.vl[tb + (size_t)(TRI_L - 1) * ld];
+    const double alphal = t.vll[tb], epsl = t.vll[tb + (size_t)(t.lastlen - 1) * ld];
+    t.fg[fb] += yprev * alpha;
+    t.fg[fb + (size_t)C * ld] += yprev * eps;
+    t.fg[fb + (size_t)(C - 1) * ld] += xnext * epsl;
+    t.fg[fb + (size_t)(C + C - 1) * ld] += xnext * alphal;
+  }
+}
+
+// after the second interface solve: the outermost neighbours are the adjacent slabs' rows
+__global__ void k_slab_outer(SlabArgs t) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x, mode = blockIdx.y;
+  if (s >= t.nk) return;
+  const int col = t.koff + s, C = t.nchunk, ld = t.ld;
+  const size_t fb = ((size_t)mode * 2 * C) * ld + col;
+  t.yx[fb] = t.outer[((size_t)mode * 2 + 0) * ld + col];
+  t.yx[fb + (size_t)(C + C - 1) * ld] = t.outer[((size_t)mode * 2 + 1) * ld + col];
+}
+
+__global__ void k_zero_rows(double *wrk, size_t lsz, int ld, int nyp, int nxp, int nmodes, int south, int north) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nxp) return;
   for (int m = 0; m < nmodes; ++m) {
-    wrk[(size_t)m * lsz + i] = 0.0;
-    wrk[(size_t)m * lsz + (size_t)(nyp - 1) * ld + i] = 0.0;
+    if (south) wrk[(size_t)m * lsz + i] = 0.0;
+    if (north) wrk[(size_t)m * lsz + (size_t)(nyp - 1) * ld + i] = 0.0;
   }
 }
 
@@ -855,7 +980,7 @@ static int dst3_r3(const HelmPlan &hp) {
 
 static void dst3_launch(qgcm_model *md, HelmPlan &hp, double *wrk, size_t lsz, int nmodes, bool inverse) {
   Dst3Args a;
-  a.nitems = nmodes * hp.nrows; a.nrows = hp.nrows; a.ld = hp.ld; a.nyp = hp.nyp; a.nxp = hp.nxp; a.lsz = lsz;
+  a.nitems = nmodes * hp.nrows; a.nrows = hp.nrows; a.ld = hp.ld; a.nyp = hp.nyp; a.nxp = hp.nxp; a.row0 = hp.row0; a.lsz = lsz;
   a.wrk = wrk; a.rowsum = hp.rowsum;
   a.s1base = hp.s1base; a.tw2 = hp.tw2; a.tw3base = hp.tw3base; a.wnbase = hp.wnbase;
   for (int i = 0; i < 16; ++i) { a.c1[i] = hp.c1[i]; a.s1[i] = hp.s1c[i]; a.wnr[i] = hp.wnr[i]; }
@@ -945,7 +1070,10 @@ void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, con
   hp.ld = g.ld;
   hp.nyp = g.nyp;
   hp.nxp = g.nxp;
-  hp.nrows = g.nyp - 2;
+  hp.nranks = md->nranks; hp.rank = md->rank;
+  hp.row0 = g.own0 + (g.wall_s() ? 1 : 0);
+  hp.nrows = (g.own1 - (g.wall_n() ? 1 : 0)) - hp.row0;
+  hp.wall_s = g.wall_s(); hp.wall_n = g.wall_n();
   hp.nchunk = (hp.nrows + TRI_L - 1) / TRI_L;
   hp.lastlen = hp.nrows - (hp.nchunk - 1) * TRI_L;
   hp.nk = kind == 0 ? hp.n - 1 : hp.n;
@@ -1007,6 +1135,19 @@ void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, con
   hp.fg = (double *)dalloc(md, sizeof(double) * nmodes * 2 * hp.nchunk * row);
   hp.yx = (double *)dalloc(md, sizeof(double) * nmodes * 2 * hp.nchunk * row);
   hp.rowsum = (double *)dalloc(md, sizeof(double) * nmodes * hp.nyp);
+  for (int r = 0; r < 16; ++r) hp.slab_rows[r] = 0;
+  if (hp.nranks > 1) {
+    if (hp.nranks > 8) throw std::runtime_error("helmholtz: at most 8 y-slabs");
+    for (int r = 0; r < hp.nranks; ++r) {
+      int p0, p1;
+      slab_bounds(g.nyp_g, hp.nranks, r, &p0, &p1);
+      hp.slab_rows[r] = (p1 - (p1 == g.nyp_g ? 1 : 0)) - (p0 + (p0 == 0 ? 1 : 0));
+    }
+    hp.slab_ae = (double *)dalloc(md, sizeof(double) * nmodes * hp.nranks * 2 * row);
+    hp.slab_fg = (double *)dalloc(md, sizeof(double) * hp.nranks * nmodes * 2 * row);
+    hp.slab_send = (double *)dalloc(md, sizeof(double) * nmodes * 2 * row);
+    hp.slab_yx = (double *)dalloc(md, sizeof(double) * nmodes * 2 * row);
+  }
   QG_CUDA(cudaMemset(hp.rowsum, 0, sizeof(double) * nmodes * hp.nyp));
   {
     // the attribute belongs to the kernel, not to the plan: only ever raise it (an ocean and
@@ -1043,10 +1184,13 @@ void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, con
 static TriArgs tri_args(HelmPlan &hp, double *wrk, size_t lsz, int nmodes) {
   TriArgs t;
   t.ld = hp.ld; t.nyp = hp.nyp; t.nk = hp.nk; t.koff = hp.koff; t.nchunk = hp.nchunk;
-  t.lastlen = hp.lastlen; t.nmodes = nmodes; t.lsz = lsz; t.a = hp.a; t.ftnorm = hp.ftnorm; t.wrk = wrk;
+  t.lastlen = hp.lastlen; t.nmodes = nmodes; t.row0 = hp.row0;
+  t.use_yx = (hp.nchunk > 1 || hp.nranks > 1) ? 1 : 0; t.nranks = hp.nranks; t.lsz = lsz; t.a = hp.a; t.ftnorm = hp.ftnorm; t.wrk = wrk;
   t.bcoef = hp.bcoef; t.binv = hp.binv; t.vl = hp.vl; t.vll = hp.vll; t.pt = hp.pt; t.fg = hp.fg; t.yx = hp.yx;
   return t;
 }
+
+static SlabArgs slab_args(HelmPlan &hp, int nmodes);
 
 // b_host: [nmodes][n] in the reference's ordering: box b(i-1) multiplies wavenumber column
 // i (src/ocisubs.F:472), periodic b(i) column i (src/ocisubs.F:577)
@@ -1059,41 +1203,89 @@ void helm_set_diag(qgcm_model *md, HelmPlan &hp, const double *b_host) {
   TriArgs t = tri_args(hp, nullptr, 0, hp.nmodes);
   dim3 grid((hp.nk + 127) / 128, hp.nmodes);
   QG_LAUNCH(md, "k_tri_tables", grid, 128, 0, k_tri_tables, t);
+  if (hp.nranks > 1) {
+    SlabArgs sa = slab_args(hp, hp.nmodes);
+    QG_LAUNCH(md, "k_slab_spikes", grid, 128, 0, k_slab_spikes, sa);
+  }
   QG_CUDA(cudaGetLastError());
 }
 
-// in place on wrk[nmodes][nyp][ld]: rhs -> solution with zero boundary values
-void helm_solve(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
-  const size_t lsz = (size_t)hp.ld * hp.nyp;
+static SlabArgs slab_args(HelmPlan &hp, int nmodes) {
+  SlabArgs t;
+  t.ld = hp.ld; t.nk = hp.nk; t.koff = hp.koff; t.nchunk = hp.nchunk; t.lastlen = hp.lastlen; t.nmodes = nmodes;
+  t.nranks = hp.nranks; t.rank = hp.rank; t.a = hp.a;
+  for (int r = 0; r < 16; ++r) t.nrows_of[r] = hp.slab_rows[r];
+  t.bcoef = hp.bcoef; t.vl = hp.vl; t.vll = hp.vll; t.fg = hp.fg; t.yx = hp.yx;
+  t.ae = hp.slab_ae; t.send = hp.slab_send; t.all = hp.slab_fg; t.outer = hp.slab_yx;
+  return t;
+}
+
+static XfArgs xf_args(HelmPlan &hp, double *wrk, size_t lsz) {
   XfArgs x;
   x.f.n = hp.n; x.f.m = hp.m; x.f.nrad = hp.nrad;
   for (int i = 0; i < 8; ++i) { x.f.radix[i] = hp.radix[i]; x.f.twoff[i] = hp.twoff[i]; }
   x.f.tw = hp.wm; x.f.wn = hp.wn; x.f.sintw = hp.sintw;
-  x.kind = hp.kind; x.inverse = 0; x.ld = hp.ld; x.nyp = hp.nyp; x.nxp = hp.nxp; x.lsz = lsz;
+  x.kind = hp.kind; x.inverse = 0; x.ld = hp.ld; x.nyp = hp.nyp; x.nxp = hp.nxp; x.row0 = hp.row0; x.lsz = lsz;
   x.wrk = wrk; x.rowsum = hp.rowsum;
+  return x;
+}
+
+// first half: forward transform, chunk-local solves, chunk interface system; with slabs also
+// the first/last rows of the slab-local solution (hp.slab_send, to be all-gathered)
+void helm_solve_a(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
+  const size_t lsz = (size_t)hp.ld * hp.nyp;
+  XfArgs x = xf_args(hp, wrk, lsz);
   dim3 gx(hp.nrows, nmodes);
   if (hp.fast)
     dst3_launch(md, hp, wrk, lsz, nmodes, false);
   else
     QG_LAUNCH(md, "k_xform", gx, 256, hp.smem_bytes, k_xform, x);
   TriArgs t = tri_args(hp, wrk, lsz, nmodes);
-  dim3 gl((hp.nk + 127) / 128, hp.nchunk, nmodes);
-  if (hp.nchunk > 1) {
+  dim3 gl((hp.nk + 127) / 128, hp.nchunk, nmodes), gr((hp.nk + 127) / 128, nmodes);
+  if (hp.nchunk > 1 || hp.nranks > 1) {
     auto kfg = k_tri_local<false>;
     QG_LAUNCH(md, "k_tri_fg", gl, 128, 0, kfg, t);
-    dim3 gr((hp.nk + 127) / 128, nmodes);
-    QG_LAUNCH(md, "k_tri_reduced", gr, 128, 0, k_tri_reduced, t);
+  }
+  if (hp.nchunk > 1) QG_LAUNCH(md, "k_tri_reduced", gr, 128, 0, k_tri_reduced, t);
+  if (hp.nranks > 1) {
+    SlabArgs sa = slab_args(hp, nmodes);
+    QG_LAUNCH(md, "k_slab_fg", gr, 128, 0, k_slab_fg, sa);
+  }
+}
+
+// second half: (slabs: inter-slab system from the gathered rows, interface system again with
+// the neighbour rows) final chunk solves, inverse transform, wall rows
+void helm_solve_b(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
+  const size_t lsz = (size_t)hp.ld * hp.nyp;
+  TriArgs t = tri_args(hp, wrk, lsz, nmodes);
+  dim3 gl((hp.nk + 127) / 128, hp.nchunk, nmodes), gr((hp.nk + 127) / 128, nmodes);
+  if (hp.nranks > 1) {
+    SlabArgs sa = slab_args(hp, nmodes);
+    QG_LAUNCH(md, "k_slab_solve", gr, 128, 0, k_slab_solve, sa);
+    if (hp.nchunk > 1) QG_LAUNCH(md, "k_tri_reduced", gr, 128, 0, k_tri_reduced, t);
+    QG_LAUNCH(md, "k_slab_outer", gr, 128, 0, k_slab_outer, sa);
   }
   auto kfin = k_tri_local<true>;
   QG_LAUNCH(md, "k_tri_local", gl, 128, 0, kfin, t);
   if (hp.fast) {
     dst3_launch(md, hp, wrk, lsz, nmodes, true);
   } else {
+    XfArgs x = xf_args(hp, wrk, lsz);
+    dim3 gx(hp.nrows, nmodes);
     x.inverse = 1;
     QG_LAUNCH(md, "k_xform", gx, 256, hp.smem_bytes, k_xform, x);
   }
-  QG_LAUNCH(md, "k_zero_rows", (hp.nxp + 255) / 256, 256, 0, k_zero_rows, wrk, lsz, hp.ld, hp.nyp, hp.nxp, nmodes);
+  QG_LAUNCH(md, "k_zero_rows", (hp.nxp + 255) / 256, 256, 0, k_zero_rows, wrk, lsz, hp.ld, hp.nyp, hp.nxp, nmodes, hp.wall_s,
+            hp.wall_n);
   QG_CUDA(cudaGetLastError());
+}
+
+// in place on wrk[nmodes][nyp][ld]: rhs -> solution with zero boundary values (one GPU; the
+// slab drivers in slab.cu call the two halves around an all-gather)
+void helm_solve(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
+  if (hp.nranks > 1) throw std::runtime_error("helm_solve: a y-slab model must be driven through the slab procedures");
+  helm_solve_a(md, hp, wrk, nmodes);
+  helm_solve_b(md, hp, wrk, nmodes);
 }
 
 }  // namespace qg

@@ -113,7 +113,19 @@ struct ScalArgs {
   const double *rowsum;   // [nl][nyp]
   qgcm_scalars *sc;
   double *coef;
+  // y-slabs (box ocean): cv[3] = xon(1), cv[4+m] = xinhom(m), already summed over the ranks
+  const double *cv;
 };
+
+// y-slabs: this rank's share of the xintp integrals of the modal solutions -> cv[4+m]
+__global__ void __launch_bounds__(256) k_inv_partials(const double *rowsum, int nl, int nyp, int lo, int hi, double dx, double *cv) {
+  __shared__ double red[8];
+  for (int m = 0; m < nl; ++m) {
+    const double s = block256_range_sum(rowsum + (size_t)m * nyp, lo, hi, red);   // wall rows are exactly zero
+    if (threadIdx.x == 0) cv[4 + m] = s * dx * dx;
+    __syncthreads();
+  }
+}
 
 // Single-thread constraint algebra on device-resident scalars, so the step never
 // synchronises with the host (src/ocisubs.F:146-162, :174-294, :333-370;
@@ -125,11 +137,12 @@ __global__ void __launch_bounds__(256) k_inv_scalars(ScalArgs a) {
   const double ecrit = 1.0e-13;
   double xinhom[NLMAX], ayis[NLMAX], ayin[NLMAX];
   double sums[NLMAX];
-  for (int m = 0; m < nl; ++m) sums[m] = block256_range_sum(a.rowsum + (size_t)m * nyp, 1, nyp - 1, red);
+  for (int m = 0; m < nl; ++m) sums[m] = a.cv ? 0.0 : block256_range_sum(a.rowsum + (size_t)m * nyp, 1, nyp - 1, red);
   if (threadIdx.x != 0) return;
+  if (a.cv) s->xon[0] = a.cv[3];
   for (int m = 0; m < nl; ++m) {
     const double sump = sums[m];
-    xinhom[m] = sump * a.dx * a.dx;   // boundary rows are exactly zero
+    xinhom[m] = a.cv ? a.cv[4 + m] : sump * a.dx * a.dx;   // boundary rows are exactly zero
     ayis[m] = a.rowsum[m * nyp + 1];              // dx/dy = 1
     ayin[m] = -a.rowsum[m * nyp + nyp - 2];
     if (a.atmos) s->xinhom_at[m] = xinhom[m]; else s->xinhom_oc[m] = xinhom[m];
@@ -255,14 +268,9 @@ static void fill_inv(qgcm_model *m, bool atmos, InvArgs &a) {
   a.coef = m->d_coef + (atmos ? 64 : 0);
 }
 
-static void invert(qgcm_model *m, bool atmos) {
-  InvArgs a;
-  fill_inv(m, atmos, a);
+static void inv_scalars_m2l(qgcm_model *m, bool atmos, const InvArgs &a) {
   const Grid &g = a.g;
   HelmPlan &hp = atmos ? m->hpa : m->hpo;
-  dim3 gi((g.nxp + 255) / 256, g.nyp - 2);
-  QG_LAUNCH(m, "k_l2m", gi, 256, 0, k_l2m, a);
-  helm_solve(m, hp, a.wrk, g.nl);
   ScalArgs s;
   const LayerConsts &lc = atmos ? m->la : m->lo;
   s.atmos = atmos; s.cyclic = g.cyclic; s.nl = g.nl; s.nyp = g.nyp;
@@ -272,12 +280,46 @@ static void invert(qgcm_model *m, bool atmos) {
   s.rowsum = hp.rowsum;
   s.sc = m->d_scal;
   s.coef = (double *)a.coef;
+  s.cv = (!atmos && m->nranks > 1) ? m->d_cv : nullptr;
   QG_LAUNCH(m, "k_inv_scalars", 1, 256, 0, k_inv_scalars, s);
   dim3 gm((g.nxp + 255) / 256, g.nyp);
   QG_LAUNCH(m, "k_m2l", gm, 256, 0, k_m2l, a);
   QG_CUDA(cudaGetLastError());
   // pom <- po, po <- new: pointer rotation (src/ocisubs.F:392, src/atisubs.F:282)
   m->swapf(atmos ? "pa" : "po", atmos ? "pam" : "pom");
+}
+
+static void invert(qgcm_model *m, bool atmos) {
+  InvArgs a;
+  fill_inv(m, atmos, a);
+  const Grid &g = a.g;
+  HelmPlan &hp = atmos ? m->hpa : m->hpo;
+  dim3 gi((g.nxp + 255) / 256, g.nyp - 2);
+  QG_LAUNCH(m, "k_l2m", gi, 256, 0, k_l2m, a);
+  helm_solve(m, hp, a.wrk, g.nl);
+  inv_scalars_m2l(m, atmos, a);
+}
+
+// y-slab pieces of ocinvq (the drivers in slab.cu put an all-gather after a and an all-reduce
+// after b)
+void ocinvq_phase_a(qgcm_model *m) {
+  InvArgs a;
+  fill_inv(m, false, a);
+  const Grid &g = a.g;
+  dim3 gi((g.nxp + 255) / 256, g.nyp - 2);
+  QG_LAUNCH(m, "k_l2m", gi, 256, 0, k_l2m, a);
+  helm_solve_a(m, m->hpo, a.wrk, g.nl);
+}
+void ocinvq_phase_b(qgcm_model *m) {
+  const Grid &g = m->go;
+  HelmPlan &hp = m->hpo;
+  helm_solve_b(m, hp, m->wrk_o, g.nl);
+  QG_LAUNCH(m, "k_inv_partials", 1, 256, 0, k_inv_partials, hp.rowsum, g.nl, g.nyp, hp.row0, hp.row0 + hp.nrows, g.dx, m->d_cv);
+}
+void ocinvq_phase_c(qgcm_model *m) {
+  InvArgs a;
+  fill_inv(m, false, a);
+  inv_scalars_m2l(m, false, a);
 }
 
 void launch_ocinvq(qgcm_model *m) { invert(m, false); }
@@ -319,6 +361,15 @@ static double xintp_from_rowsums(const std::vector<double> &rs) {
   double sump = 0.0;
   for (int j = 1; j < nyp - 1; ++j) sump += rs[j];
   return sump + 0.5 * (rs[0] + rs[nyp - 1]);
+}
+// the same integral restricted to the rows a y-slab owns (its share of the global sum)
+static double xintp_share(const Grid &g, const std::vector<double> &rs) {
+  const int lo = g.own0 + (g.wall_s() ? 1 : 0), hi = g.own1 - (g.wall_n() ? 1 : 0);
+  double sump = 0.0;
+  for (int j = lo; j < hi; ++j) sump += rs[j];
+  if (g.wall_s()) sump += 0.5 * rs[0];
+  if (g.wall_n()) sump += 0.5 * rs[g.nyp - 1];
+  return sump;
 }
 
 static void homsol_channel(qgcm_model *m, bool atmos) {
@@ -417,29 +468,42 @@ static void homsol_channel(qgcm_model *m, bool atmos) {
   QG_CUDA(cudaMemcpy(m->d_scal, &s, sizeof(s), cudaMemcpyHostToDevice));
 }
 
-static void homsol_box(qgcm_model *m) {
+// homsol for the box ocean (src/conhoms.F:549-640) in three pieces so that the y-slab driver
+// can put the solver's all-gather after a and the all-reduce of the integrals after b.
+// ochom(:,:,m) = 1 + rdm2(m+1) * sol0, sol0 solving (del2 - rdm2(m+1)) sol0 = 1.  The per-mode
+// operator table already holds mode m+1 in slot m, so all nl slots are solved with rhs = 1
+// and slots 1..nl-1 are kept.
+void homsol_box_a(qgcm_model *m) {
+  const Grid &g = m->go;
+  dim3 gf((g.nxp + 255) / 256, g.nyp);
+  for (int q = 0; q < g.nl; ++q)
+    QG_LAUNCH(m, "k_fill_rows", gf, 256, 0, k_fill_rows, m->wrk_o + q * g.lsz, g.ld, g.nyp, g.nxp, nullptr, 1.0, 0);
+  helm_solve_a(m, m->hpo, m->wrk_o, g.nl);
+}
+void homsol_box_b(qgcm_model *m, std::vector<double> &share) {
   const Grid &g = m->go;
   const LayerConsts &lc = m->lo;
-  HelmPlan &hp = m->hpo;
   const int nl = g.nl, nyp = g.nyp;
-  qgcm_scalars s;
-  QG_CUDA(cudaMemcpyAsync(&s, m->d_scal, sizeof(s), cudaMemcpyDeviceToHost, m->stream));
-  QG_CUDA(cudaStreamSynchronize(m->stream));
+  helm_solve_b(m, m->hpo, m->wrk_o, nl);
   double *ochom = m->F("ochom");
   std::vector<double> rs(nyp);
-  // ochom(:,:,m) = 1 + rdm2(m+1) * sol0, sol0 solving (del2 - rdm2(m+1)) sol0 = 1.
-  // The per-mode operator table already holds mode m+1 in slot m, so solve all nl slots
-  // with rhs = 1 and keep slots 1..nl-1.
-  dim3 gf((g.nxp + 255) / 256, nyp);
-  for (int q = 0; q < nl; ++q) QG_LAUNCH(m, "k_fill_rows", gf, 256, 0, k_fill_rows, m->wrk_o + q * g.lsz, g.ld, nyp, g.nxp, nullptr, 1.0, 0);
-  helm_solve(m, hp, m->wrk_o, nl);
+  share.assign(nl - 1, 0.0);
   for (int mo = 1; mo <= nl - 1; ++mo) {
     QG_LAUNCH(m, "k_hom_finish", nyp, 256, 0, k_hom_finish, ochom + (size_t)(mo - 1) * g.lsz, m->wrk_o + (size_t)mo * g.lsz, g.ld, nyp,
                                              g.nxp, nullptr, 1.0, 0, lc.rdm2[mo], m->d_red);
     QG_CUDA(cudaMemcpyAsync(rs.data(), m->d_red, sizeof(double) * nyp, cudaMemcpyDeviceToHost, m->stream));
     QG_CUDA(cudaStreamSynchronize(m->stream));
-    s.aipohs[mo - 1] = xintp_from_rowsums(rs) * g.dx * g.dx;
+    share[mo - 1] = xintp_share(g, rs) * g.dx * g.dx;
   }
+}
+void homsol_box_c(qgcm_model *m, const std::vector<double> &aipohs) {
+  const Grid &g = m->go;
+  const LayerConsts &lc = m->lo;
+  const int nl = g.nl;
+  qgcm_scalars s;
+  QG_CUDA(cudaMemcpyAsync(&s, m->d_scal, sizeof(s), cudaMemcpyDeviceToHost, m->stream));
+  QG_CUDA(cudaStreamSynchronize(m->stream));
+  for (int mo = 1; mo <= nl - 1; ++mo) s.aipohs[mo - 1] = aipohs[mo - 1];
   for (int k = 1; k <= nl - 1; ++k) {
     for (int mo = 1; mo <= nl; ++mo)
       s.cdiffo[(mo - 1) + nl * (k - 1)] = lc.ctm2l[(mo - 1) + nl * k] - lc.ctm2l[(mo - 1) + nl * (k - 1)];
@@ -449,7 +513,15 @@ static void homsol_box(qgcm_model *m) {
   QG_CUDA(cudaMemcpy(m->d_scal, &s, sizeof(s), cudaMemcpyHostToDevice));
 }
 
+static void homsol_box(qgcm_model *m) {
+  std::vector<double> aip;
+  homsol_box_a(m);
+  homsol_box_b(m, aip);
+  homsol_box_c(m, aip);
+}
+
 void launch_homsol(qgcm_model *m) {
+  if (m->nranks > 1) { slab_homsol(ranks_of(m)); return; }
   if (m->has_ocean) {
     if (m->cyclic) homsol_channel(m, false); else homsol_box(m);
   }

@@ -213,6 +213,7 @@ static void avg(qgcm_model *m, const char *a, const char *b, size_t n) {
   QG_LAUNCH(m, "k_avg2", (unsigned)((n + 255) / 256), 256, 0, k_avg2, m->F(a), m->F(b), n);
 }
 void launch_tlavg_ocean(qgcm_model *m) {
+  // y-slabs: both time levels carry valid halos, so the average needs no exchange
   const Grid &g = m->go;
   avg(m, "qo", "qom", g.lsz * g.nl);
   avg(m, "po", "pom", g.lsz * g.nl);
@@ -254,14 +255,36 @@ __global__ void __launch_bounds__(256) k_diff_rowsum(Grid g, const double *pa, c
   }
 }
 
+// xintp(a - b) over the rows this rank owns (the whole grid on one GPU)
 static double xintp_diff(qgcm_model *m, const Grid &g, const double *a, const double *b) {
   std::vector<double> rs(g.nyp);
   QG_LAUNCH(m, "k_diff_rowsum", g.nyp, 256, 0, k_diff_rowsum, g, a, b, m->d_red);
   QG_CUDA(cudaMemcpyAsync(rs.data(), m->d_red, sizeof(double) * g.nyp, cudaMemcpyDeviceToHost, m->stream));
   QG_CUDA(cudaStreamSynchronize(m->stream));
+  const int lo = g.own0 + (g.wall_s() ? 1 : 0), hi = g.own1 - (g.wall_n() ? 1 : 0);
   double sump = 0.0;
-  for (int j = 1; j < g.nyp - 1; ++j) sump += rs[j];
-  return sump + 0.5 * (rs[0] + rs[g.nyp - 1]);
+  for (int j = lo; j < hi; ++j) sump += rs[j];
+  if (g.wall_s()) sump += 0.5 * rs[0];
+  if (g.wall_n()) sump += 0.5 * rs[g.nyp - 1];
+  return sump;
+}
+
+// y-slabs: this rank's share of dpiocp(k), dpioc(k) (src/conhoms.F:44-314), then the totals
+void constr_ocean_share(qgcm_model *m, std::vector<double> &v) {
+  const Grid &g = m->go;
+  const double *po = m->F("po"), *pom = m->F("pom");
+  v.assign(2 * (g.nl - 1), 0.0);
+  for (int k = 0; k < g.nl - 1; ++k) {
+    v[2 * k] = xintp_diff(m, g, pom + (k + 1) * g.lsz, pom + k * g.lsz) * g.dx * g.dx;
+    v[2 * k + 1] = xintp_diff(m, g, po + (k + 1) * g.lsz, po + k * g.lsz) * g.dx * g.dx;
+  }
+}
+void constr_ocean_store(qgcm_model *m, const std::vector<double> &v) {
+  qgcm_scalars s;
+  QG_CUDA(cudaMemcpyAsync(&s, m->d_scal, sizeof(s), cudaMemcpyDeviceToHost, m->stream));
+  QG_CUDA(cudaStreamSynchronize(m->stream));
+  for (int k = 0; k < m->go.nl - 1; ++k) { s.dpiocp[k] = v[2 * k]; s.dpioc[k] = v[2 * k + 1]; }
+  QG_CUDA(cudaMemcpy(m->d_scal, &s, sizeof(s), cudaMemcpyHostToDevice));
 }
 
 static void constr_lines(qgcm_model *m, const Grid &g, const LayerConsts &lc, const double *p, const double *pm,
@@ -303,6 +326,7 @@ static void constr_lines(qgcm_model *m, const Grid &g, const LayerConsts &lc, co
 }
 
 void launch_constr(qgcm_model *m) {
+  if (m->nranks > 1) { slab_constr(ranks_of(m)); return; }
   qgcm_scalars s;
   QG_CUDA(cudaMemcpyAsync(&s, m->d_scal, sizeof(s), cudaMemcpyDeviceToHost, m->stream));
   QG_CUDA(cudaStreamSynchronize(m->stream));

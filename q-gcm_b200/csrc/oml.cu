@@ -9,6 +9,8 @@
 // Pass 2 (k_oml_entoc): subtract the global mean from xfo and average the four
 //   surrounding T cells onto p points (entoc), with xintp row sums for xon(1).
 // The reference needs ~24 field passes for this; here it is 11.
+#include <algorithm>
+
 #include "qgcm_internal.h"
 
 namespace qg {
@@ -28,6 +30,10 @@ struct OmlArgs {
   double *entoc;
   double *rowsum;    // [nyp] xintp row sums of entoc
   qgcm_scalars *sc;
+  // y-slabs: T rows [t0, t1) and p rows [p0, p1) are owned by this rank; the three sums and
+  // the entoc integral travel through the reduction vector cv
+  int t0, t1, p0, p1, multi;
+  double *cv;
 };
 
 __device__ __forceinline__ int wrapt(int i, int nxt, int cyc) {
@@ -168,9 +174,11 @@ __global__ void __launch_bounds__(256) k_oml_step(OmlArgs a) {
     sstnew = sstnew + fmax(0.0, dtonew);
     a.xfo[idx] = xf;
     a.sstnew[idx] = sstnew;
-    pxfo += xf;
-    pcfr += (-dtonew >= 0.0) ? 0.0 : 1.0;   // 0.5 - sign(0.5, -dtonew)
-    pcen -= coneno;
+    if (gj >= a.t0 && gj < a.t1) {            // halo rows of a slab belong to the neighbour's sums
+      pxfo += xf;
+      pcfr += (-dtonew >= 0.0) ? 0.0 : 1.0;   // 0.5 - sign(0.5, -dtonew)
+      pcen -= coneno;
+    }
   }
   // block partial sums (fixed order)
   const int lane = tid & 31, w = tid >> 5;
@@ -206,9 +214,13 @@ __global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy) {
     double t[3] = {0.0, 0.0, 0.0};
     for (int q = 0; q < 3; ++q)
       for (int i = 0; i < 8; ++i) t[q] += red[q][i];
-    a.part[0] = t[0];                       // xfosum, read by k_oml_entoc
-    a.sc->cfraoc = t[1] * a.g.norm;         // omlsubs.F:211
-    a.sc->centoc = t[2] * dxdy;             // omlsubs.F:212
+    a.cv[0] = t[0];                         // xfosum, read by k_oml_entoc (after the all-reduce on slabs)
+    a.cv[1] = t[1];
+    a.cv[2] = t[2];
+    if (!a.multi) {
+      a.sc->cfraoc = t[1] * a.g.norm;       // omlsubs.F:211
+      a.sc->centoc = t[2] * dxdy;           // omlsubs.F:212
+    }
   }
 }
 
@@ -219,7 +231,7 @@ __global__ void __launch_bounds__(256) k_oml_entoc(OmlArgs a) {
   const Grid &g = a.g;
   const int j = blockIdx.x;   // 0-based p row
   const int nxp = g.nxp, nyp = g.nyp, nxt = g.nxt, nyt = g.nyt, ld = g.ld, cyc = g.cyclic;
-  const double mean = a.part[0] * g.norm;   // xfosum*ocnorm
+  const double mean = a.cv[0] * g.norm;   // xfosum*ocnorm
   double part = 0.0;
   for (int i = threadIdx.x; i < nxp; i += 256) {
     // T cells around p point (i,j): (i-1,j-1), (i,j-1), (i-1,j), (i,j) in 0-based T indices
@@ -262,6 +274,19 @@ __global__ void __launch_bounds__(256) k_oml_entoc(OmlArgs a) {
 __global__ void __launch_bounds__(256) k_oml_finish(OmlArgs a, double dx) {
   __shared__ double red[8];
   const int nyp = a.g.nyp;
+  if (a.multi) {
+    // owned rows only; the rows on the real walls carry half weight (intsubs.f:120-131)
+    const int lo = a.p0 + (a.g.wall_s() ? 1 : 0), hi = a.p1 - (a.g.wall_n() ? 1 : 0);
+    const double sump = block256_range_sum(a.rowsum, lo, hi, red);
+    if (threadIdx.x != 0) return;
+    double x = sump;
+    if (a.g.wall_s()) x += 0.5 * a.rowsum[0];
+    if (a.g.wall_n()) x += 0.5 * a.rowsum[nyp - 1];
+    a.cv[3] = x * dx * dx;
+    a.sc->cfraoc = a.cv[1] * a.g.norm;
+    a.sc->centoc = a.cv[2] * dx * dx;
+    return;
+  }
   const double sump = block256_range_sum(a.rowsum, 1, nyp - 1, red);
   if (threadIdx.x != 0) return;
   const double x = sump + 0.5 * (a.rowsum[0] + a.rowsum[nyp - 1]);
@@ -279,12 +304,12 @@ __global__ void __launch_bounds__(256) k_oml_monitors(OmlArgs a) {
   const int nxt = g.nxt, nyt = g.nyt, ld = g.ld;
   double s[6] = {0, 0, 0, 0, 0, 0};
   for (int i = threadIdx.x; i < nxt; i += 256) {
-    if (a.sb) {
+    if (a.sb && g.wall_s()) {   // y-slabs: the rank that holds the wall owns these monitors
       const double vm = -a.rhf0hm * (a.taux[i + 1] + a.taux[i]);
       const double tm = a.sst[i] + a.tsbdy;
       s[0] += vm; s[1] += vm * tm; s[2] -= (a.sstm[i] - a.tsbdy);
     }
-    if (a.nb) {
+    if (a.nb && g.wall_n()) {
       const double vp = -a.rhf0hm * (a.taux[(size_t)nyt * ld + i + 1] + a.taux[(size_t)nyt * ld + i]);
       const double tp = a.sst[(size_t)(nyt - 1) * ld + i] + a.tnbdy;
       s[3] -= vp; s[4] -= vp * tp; s[5] += (a.tnbdy - a.sstm[(size_t)(nyt - 1) * ld + i]);
@@ -306,7 +331,7 @@ __global__ void __launch_bounds__(256) k_oml_monitors(OmlArgs a) {
   }
 }
 
-void launch_oml(qgcm_model *m) {
+static OmlArgs oml_args(qgcm_model *m, dim3 &grid) {
   OmlArgs a;
   const Grid &g = m->go;
   const qgcm_config &c = m->cfg;
@@ -327,16 +352,36 @@ void launch_oml(qgcm_model *m) {
   a.po1 = m->F("po"); a.taux = m->F("tauxo"); a.tauy = m->F("tauyo");
   a.sst = m->F("sst"); a.sstm = m->F("sstm"); a.wekt = m->F("wekto"); a.fnet = m->F("fnetoc");
   a.sstnew = m->sstnew; a.xfo = m->xfo;
-  dim3 grid((g.nxt + OX - 1) / OX, (g.nyt + OY - 1) / OY);
+  grid = dim3((g.nxt + OX - 1) / OX, (g.nyt + OY - 1) / OY);
   a.nblocks = grid.x * grid.y;
   a.part = m->d_red;
   a.rowsum = m->d_red + 3 * (size_t)a.nblocks;
   a.entoc = m->F("entoc");
   a.sc = m->d_scal;
+  a.multi = m->nranks > 1;
+  a.p0 = g.own0; a.p1 = g.own1;
+  a.t0 = g.own0; a.t1 = std::min(g.own1, g.nyt);
+  a.cv = m->d_cv;
   if (m->red_elems < 3 * (size_t)a.nblocks + g.nyp) throw std::runtime_error("oml: reduction scratch too small");
+  return a;
+}
+
+// monitors, the fused advection/diffusion/entrainment step, and its three sums (local to the
+// rank on y-slabs: d_cv[0..2] are all-reduced before phase b)
+void oml_phase_a(qgcm_model *m) {
+  dim3 grid;
+  OmlArgs a = oml_args(m, grid);
+  const Grid &g = m->go;
   QG_LAUNCH(m, "k_oml_monitors", 1, 256, 0, k_oml_monitors, a);
   QG_LAUNCH(m, "k_oml_step", grid, 256, 0, k_oml_step, a);
   QG_LAUNCH(m, "k_oml_reduce", 1, 256, 0, k_oml_reduce, a, g.dx * g.dx);
+}
+
+// entoc from xfo minus the global mean, its integral (y-slabs: the rank's share in d_cv[3])
+void oml_phase_b(qgcm_model *m) {
+  dim3 grid;
+  OmlArgs a = oml_args(m, grid);
+  const Grid &g = m->go;
   QG_LAUNCH(m, "k_oml_entoc", g.nyp, 256, 0, k_oml_entoc, a);
   QG_LAUNCH(m, "k_oml_finish", 1, 256, 0, k_oml_finish, a, g.dx);
   QG_CUDA(cudaGetLastError());
@@ -345,6 +390,12 @@ void launch_oml(qgcm_model *m) {
   m->fields.at("sstm").d = m->fields.at("sst").d;
   m->fields.at("sst").d = m->sstnew;
   m->sstnew = old_m;
+}
+
+void launch_oml(qgcm_model *m) {
+  if (m->nranks > 1) throw std::runtime_error("qgcm_oml: a y-slab model is stepped with qgcm_ocean_step");
+  oml_phase_a(m);
+  oml_phase_b(m);
 }
 
 }  // namespace qg

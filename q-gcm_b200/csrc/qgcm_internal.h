@@ -45,7 +45,14 @@ struct Grid {
   double dx, dxm2, hdxm1, rdxf0, norm;  // dx, 1/dx^2, 0.5/dx, 1/(dx f0), 1/(nxt*nyt)
   double xl, yl;
   double tdt;       // 2*dt
+  // y-slab partition (multi-GPU): this grid holds global p rows [jg0, jg0+nyp) of nyp_g, of
+  // which local rows [own0, own1) are owned (the rest are halo copies); single GPU:
+  // jg0 = 0, own0 = 0, own1 = nyp = nyp_g.  norm, yl stay the global values.
+  int jg0, nyp_g, own0, own1;
+  __host__ __device__ bool wall_s() const { return jg0 == 0; }
+  __host__ __device__ bool wall_n() const { return jg0 + nyp == nyp_g; }
 };
+constexpr int HALO = 3;   // halo rows kept on either side of a slab (del-6th of pom needs 3)
 
 // Device-side constants small enough to pass by value to kernels
 struct LayerConsts {
@@ -64,7 +71,8 @@ struct HelmPlan {
   int twoff[8];     // per-pass twiddle table offsets
   int nmodes;        // batch (number of vertical modes)
   int ld, nyp, nxp;
-  int nrows;         // interior rows nyp-2
+  int row0;          // first solved local row (1 on a single GPU; own0 (+1 at the southern wall) in a slab)
+  int nrows;         // solved rows: the interior rows this rank owns
   int nchunk;        // ceil(nrows / TRI_L)
   int lastlen;       // rows in the last chunk
   int nk;            // number of wavenumber columns solved (n-1 box, n periodic)
@@ -87,6 +95,13 @@ struct HelmPlan {
   double2 *s1base = nullptr, *tw2 = nullptr, *tw3base = nullptr, *wnbase = nullptr;
   double c1[16], s1c[16];
   double2 wnr[16];
+  // y-slab coupling (nranks > 1): every slab is one more level of the same partition
+  int nranks = 1, rank = 0, wall_s = 1, wall_n = 1;
+  int slab_rows[16];           // solved rows of every slab
+  double *slab_send = nullptr; // [nmodes][2][ld] first/last rows of this slab's local solution
+  double *slab_ae = nullptr;   // [nmodes][nranks][2][ld] left-spike first/last values (alpha, eps) of every slab
+  double *slab_fg = nullptr;   // [nranks][nmodes][2][ld] all-gathered first/last rows of the slab-local solutions
+  double *slab_yx = nullptr;   // [nmodes][2][ld] true neighbour rows of this slab (Y of the slab below, X of the one above)
   double *rowsum = nullptr;  // [nmodes][nyp]  xintp row sums of the solution
   double *ayrow = nullptr;   // [nmodes][2]    periodic: line sums of rows 2 and nyp-1
 };
@@ -128,6 +143,7 @@ struct qgcm_model {
   struct Field {
     double *d = nullptr;
     int nx = 0, ny = 0, nl = 1, ld = 0;   // ld == 0: dense 1-D/2-D small array
+    int nyg = 0, joff = 0, o0 = 0, o1 = 0;   // y-slab: global rows, global index of local row 0, owned local rows
     size_t lsz = 0;                       // device layer stride (gridded fields)
     size_t elems = 0;                     // device elements allocated
   };
@@ -140,6 +156,13 @@ struct qgcm_model {
   size_t red_elems = 0;
   qg::HelmPlan hpo, hpa;
   qg::XfPlan xf;
+  // multi-GPU: rank layout, communicator (NCCL, or in-process peers sharing one stream) and
+  // the small device vector that carries all-reduce payloads
+  int nranks = 1, rank = 0;
+  void *nccl = nullptr;
+  std::vector<qgcm_model *> peers;       // loopback group (all ranks in this process), empty otherwise
+  double *d_cv = nullptr;                // [32] reduction payload
+  bool shared_stream = false;            // loopback ranks > 0 borrow rank 0's stream
   double *wrk_o = nullptr, *wrk_a = nullptr;   // modal work arrays [nl][nyp][ld]
   double *xfo = nullptr, *xfa = nullptr, *sstnew = nullptr, *astnew = nullptr, *hmnew = nullptr;
   std::vector<void *> allocs;
@@ -201,5 +224,36 @@ void launch_aml(qgcm_model *m);
 void launch_atqzbd(qgcm_model *m, double *q, const double *p);
 void launch_tlavg_atmos(qgcm_model *m);
 void launch_xforc(qgcm_model *m);
+
+// slab.cu: y-slab multi-GPU drivers.  `ms` is the set of ranks this process drives: one model
+// with an NCCL communicator, or every rank of an in-process loopback group.
+typedef std::vector<qgcm_model *> Ranks;
+void slab_bounds(int nyp_global, int nranks, int rank, int *p0, int *p1);
+void comm_allreduce_cv(const Ranks &ms, size_t off, int n);
+void comm_allreduce_host(const Ranks &ms, std::vector<std::vector<double>> &vals);
+void comm_halo(const Ranks &ms, const std::vector<const char *> &fields);
+void nccl_unique_id(void *out128);
+void nccl_init(qgcm_model *m, const void *id128);
+void nccl_destroy(qgcm_model *m);
+void group_create(qgcm_model **models, int n);
+Ranks ranks_of(qgcm_model *m);
+void slab_ocean_step(const Ranks &ms);
+void slab_constr(const Ranks &ms);
+void slab_homsol(const Ranks &ms);
+void slab_qcomp_ocean(const Ranks &ms);
+void slab_tlavg_ocean(const Ranks &ms);
+// pieces of the single-GPU launchers that the slab drivers interleave with communication
+void oml_phase_a(qgcm_model *m);                 // up to the local partial sums (d_cv[0..2])
+void oml_phase_b(qgcm_model *m);                 // entoc and its local integral (d_cv[3])
+void ocinvq_phase_a(qgcm_model *m);              // l2m, forward transform, local chunk solve, slab first/last rows
+void ocinvq_phase_b(qgcm_model *m);              // slab coupling, final rows, inverse transform, local integrals (d_cv[4..])
+void ocinvq_phase_c(qgcm_model *m);              // constraint algebra, mode->layer
+void homsol_box_a(qgcm_model *m);
+void homsol_box_b(qgcm_model *m, std::vector<double> &share);
+void homsol_box_c(qgcm_model *m, const std::vector<double> &aipohs);
+void constr_ocean_share(qgcm_model *m, std::vector<double> &v);
+void constr_ocean_store(qgcm_model *m, const std::vector<double> &v);
+void helm_solve_a(qgcm_model *m, HelmPlan &hp, double *wrk, int nmodes);
+void helm_solve_b(qgcm_model *m, HelmPlan &hp, double *wrk, int nmodes);
 
 }  // namespace qg

@@ -165,3 +165,82 @@ class Model(CModel):
     def exported_symbols_ok():
         lib = load_library()
         return [n for n in declared_functions() if not hasattr(lib, n)]
+
+    # -- y-slab multi-GPU, one process per GPU
+    @staticmethod
+    def nccl_unique_id():
+        buf = C.create_string_buffer(128)
+        lib = load_library()
+        if lib.qgcm_nccl_unique_id(buf) != 0:
+            f = lib.qgcm_last_error
+            f.restype = C.c_char_p
+            raise RuntimeError("qgcm_nccl_unique_id failed: %s" % (f() or b"").decode())
+        return buf.raw
+
+    def comm_init_nccl(self, id128: bytes):
+        self._call("comm_init_nccl", C.c_char_p(id128))
+
+
+def slab_config(cfg: QgcmConfig, nranks: int, rank: int) -> QgcmConfig:
+    """copy of cfg that selects y-slab `rank` of `nranks` (include/qgcm_b200.h, nranks/rank)"""
+    c = type(cfg).from_buffer_copy(cfg)
+    c.nranks, c.rank = nranks, rank
+    for k, v in cfg.__dict__.items():      # host-side extras attached by build_config
+        setattr(c, k, v)
+    return c
+
+
+def slab_bounds(nyp_global, nranks, rank):
+    """owned p rows [j0, j0 + n) of a rank (pure host arithmetic in the library)"""
+    j0, n = C.c_int32(), C.c_int32()
+    lib = load_library()
+    if lib.qgcm_slab_bounds(C.c_int32(nyp_global), C.c_int32(nranks), C.c_int32(rank), C.byref(j0), C.byref(n)) != 0:
+        raise RuntimeError("qgcm_slab_bounds failed")
+    return j0.value, n.value
+
+
+class SlabGroup:
+    """every rank of a y-slab partition in this process, on one device (qgcm_group_create).
+    Mirrors the Model interface for the procedures that act on a partition, so the parity
+    tests drive 2..8 slabs on a single GPU exactly as they drive one model."""
+
+    def __init__(self, cfg: QgcmConfig, nranks: int):
+        self.cfg = cfg
+        self.ranks = [Model(slab_config(cfg, nranks, r)) for r in range(nranks)]
+        arr = (C.c_void_p * nranks)(*[m._h for m in self.ranks])
+        lib = load_library()
+        if lib.qgcm_group_create(arr, C.c_int32(nranks)) != 0:
+            raise RuntimeError("qgcm_group_create failed: %s" % self.ranks[0]._err())
+
+    def set_field(self, name, arr):
+        for m in self.ranks:
+            m.set_field(name, arr)
+
+    def get_field(self, name, shape=None):
+        n = self.ranks[0].field_size(name)
+        out = np.full(n, np.nan, dtype=np.float64)
+        for m in self.ranks:      # each rank fills the rows it owns
+            m._call("get_field", name.encode(), out.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(n))
+        return out.reshape(shape, order="F") if shape is not None else out
+
+    def get_scalars(self):
+        return self.ranks[0].get_scalars()
+
+    # a partition call on any member steps every rank
+    def constr(self): self.ranks[0].constr()
+    def homsol(self): self.ranks[0].homsol()
+    def qcomp_ocean(self): self.ranks[0].qcomp_ocean()
+    def ocean_step(self): self.ranks[0].ocean_step()
+    def tlavg_ocean(self): self.ranks[0].tlavg_ocean()
+    def run(self, a, b): self.ranks[0].run(a, b)
+
+    def xforc(self):
+        for m in self.ranks:
+            m.xforc()
+
+    def sync(self):
+        for m in self.ranks:
+            m.sync()
+
+    def launch_count(self):
+        return sum(m.launch_count() for m in self.ranks)
