@@ -189,6 +189,9 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
+    # the bench prints ONE JSON line on stdout: keep NCCL's version banner out of it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import _pkg
     qg = _pkg.load()
     if args.impl == "reference":
@@ -209,7 +212,18 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     p, cfg = build_case(qg, args.workload, local)
-    m = qg.Model(cfg)
+    if world > 1:
+        # strong scaling: ONE domain cut into y-slabs, one per GPU; the ranks exchange halo
+        # rows, the 2-row-per-mode slab coupling of the Helmholtz solve and a few scalars over
+        # NCCL (q-gcm_b200/csrc/slab.cu).  Rank 0 makes the NCCL id, torch.distributed carries it.
+        ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            ident.copy_(torch.frombuffer(bytearray(qg.Model.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(ident, 0)
+        m = qg.Model(qg.slab_config(cfg, world, rank))
+        m.comm_init_nccl(bytes(ident.cpu().numpy().tobytes()))
+    else:
+        m = qg.Model(cfg)
     qg.synth.init_model(m, p, cfg, "random")
     m.sync()
     stream = torch.cuda.ExternalStream(m.stream(), device=local)
@@ -233,13 +247,22 @@ def main():
         sampler.start()          # nvidia-smi needs ~0.5 s before its first sample
     ocean_steps(args.warmup, 1)
     barrier()
-    if rank == 0:
-        # keep the GPU under the same load until the sampler is live, so that the samples
-        # taken while the timed region runs are not its start-up transient
-        t_w = time.time()
-        while len(sampler.rows) < 2 and time.time() - t_w < 5.0:
+    def step_while(cond):
+        """keep stepping (untimed) while rank 0's condition holds; the step is collective on
+        y-slabs, so every rank follows rank 0's decision"""
+        while True:
+            go = torch.tensor([1 if (rank == 0 and cond()) else 0], dtype=torch.int32, device="cuda")
+            if world > 1:
+                dist.broadcast(go, 0)
+            if int(go.item()) == 0:
+                break
             ocean_steps(5, 1)
             m.sync()
+
+    # keep the GPU under the same load until the sampler is live, so that the samples taken
+    # while the timed region runs are not its start-up transient
+    t_w = time.time()
+    step_while(lambda: len(sampler.rows) < 2 and time.time() - t_w < 5.0)
     barrier()
     n_before = len(sampler.rows)
     l0 = m.launch_count()
@@ -251,22 +274,19 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = m.launch_count() - l0
     clocks = None
+    # a timed region shorter than the sampling period: keep stepping (untimed) until at least
+    # three samples under the identical load exist
+    t_w = time.time()
+    step_while(lambda: len(sampler.rows) - n_before < 3 and time.time() - t_w < 3.0)
     if rank == 0:
-        # a timed region shorter than the sampling period: keep stepping (untimed) until at
-        # least three samples under the identical load exist
-        t_w = time.time()
-        while len(sampler.rows) - n_before < 3 and time.time() - t_w < 3.0:
-            ocean_steps(5, 1)
-            m.sync()
         clocks = sampler.stop(first=n_before)
         clocks["note"] = "sampled every 100 ms from the start of the timed region, same step loop"
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    # N > 1: the y-slab partition is not built yet, every rank advances an independent
-    # replica of the full domain (weak scaling in the number of domains)
-    value = world * args.steps / (ms * 1e-3)
+    # N > 1: one domain in y-slabs, so the job's throughput is steps of that one domain
+    value = args.steps / (ms * 1e-3)
 
     # ---- per-kernel profile pass (CUDA events inside the library) ----
     m._lib.qgcm_profile(m._h, 1)
@@ -286,25 +306,28 @@ def main():
         pp = passes_per_launch(name, p.has("cyclic_ocean"))
         ent = {"launches": cnt, "ms_per_launch": tms / cnt, "share": tms / tot_ms}
         if pp:
-            ent["GBps"] = pp * fieldpass / (tms / cnt * 1e-3) / 1e9
+            ent["GBps"] = pp * fieldpass / world / (tms / cnt * 1e-3) / 1e9     # a rank moves 1/world of the rows
             ent["frac"] = ent["GBps"] / peak
         kern[name] = ent
     dom = max(prof, key=lambda k: prof[k][1])
     dpp = passes_per_launch(dom, p.has("cyclic_ocean")) or 0.0
     dms = prof[dom][1] / prof[dom][0]
-    ach = dpp * fieldpass / (dms * 1e-3) / 1e9
+    ach = dpp * fieldpass / world / (dms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src,
             "unit": "GB/s", "frac": ach / peak, "traffic": None,
-            "algorithmic_bytes_per_launch": dpp * fieldpass, "ms_per_launch": dms,
+            "algorithmic_bytes_per_launch": dpp * fieldpass / world, "ms_per_launch": dms,
             "share_of_step": prof[dom][1] / tot_ms}
     step_bytes = (61.0 if not p.has("cyclic_ocean") else 59.0) * fieldpass
-    step_frac = step_bytes * value / world / 1e9 / peak
+    step_frac = step_bytes * value / world / 1e9 / peak     # per-GPU share of the step's bytes against one GPU's peak
 
     # ---- end to end through the C ABI with host buffers ----
     e2e = None
     if not args.no_e2e:
         names = ("tauxo", "tauyo", "fnetoc")
-        host = {n: torch.from_numpy(m.get_field(n)).pin_memory() for n in names}
+        # the externally supplied forcing as the Fortran side holds it: global host arrays
+        st = qg.synth.ocean_state(p, cfg, "random", qg.synth.SEED, min(1.0, (p.nxto * p.dxo) / 4.8e6 * 4.0))
+        host = {n: torch.from_numpy(np.ascontiguousarray(np.asarray(st[n], dtype=np.float64).ravel(order="F"))).pin_memory()
+                for n in names}
         ptr = {n: C.cast(host[n].data_ptr(), C.POINTER(C.c_double)) for n in names}
         nel = {n: host[n].numel() for n in names}
         scal = qg.QgcmScalars()
@@ -326,12 +349,16 @@ def main():
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * ke / (float(t.item()) * 1e-3), "unit": UNIT,
+        e2e = {"value": ke / (float(t.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(sum(nel.values()) * 8), "d2h_bytes_per_step": int(C.sizeof(scal)),
                "steps": ke, "def": "per step: qgcm_set_field(tauxo,tauyo,fnetoc) from pinned host memory + "
                                    "qgcm_ocean_step + qgcm_get_scalars"}
 
-    finite = bool(np.isfinite(m.get_field("po")).all())
+    po = m.get_field("po")
+    if world > 1:       # a slab fills only the rows it owns
+        j0, n = qg.slab_bounds(p.nypo, world, rank)
+        po = po.reshape((p.nxpo, p.nypo, p.nlo), order="F")[:, j0:j0 + n, :]
+    finite = bool(np.isfinite(po).all())
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_sample(qg, p, cfg)
@@ -340,10 +367,12 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s ocean-only %dx%dx%d, box, dto=%gs" % (p.name, p.nxpo, p.nypo, p.nlo, p.dto),
-                       "parallelism": "1 domain per GPU" if world > 1 else "single GPU",
+                       "parallelism": ("%d y-slabs of one domain, NCCL halos + slab-coupled solve" % world) if world > 1
+                       else "single GPU",
                        "l2": "state (%.1f GB) is far larger than L2; no flush needed" %
                              (4 * p.nlo * fieldpass / 1e9),
                        "state_finite": finite},
