@@ -170,6 +170,7 @@ static qgcm_model *create(const qgcm_config *cfg) {
     m->d_scal = (qgcm_scalars *)dalloc(m, sizeof(qgcm_scalars));
     m->d_coef = (double *)dalloc(m, sizeof(double) * 128);
     m->d_cv = (double *)dalloc(m, sizeof(double) * 32);
+    m->d_ticket = (unsigned int *)dalloc(m, sizeof(unsigned int) * 4);
     size_t red = 0;
     if (m->has_ocean) {
       const Grid &g = m->go;
@@ -228,7 +229,7 @@ static qgcm_model *create(const qgcm_config *cfg) {
       const size_t nb = (size_t)((g.nxt + 63) / 64) * ((g.nyt + 3) / 4);   // aml tiles are 64 x 4
       red = std::max(red, 3 * nb + 4 * (size_t)g.nyp);
     }
-    m->red_elems = red + 64;
+    m->red_elems = red + 512;
     m->d_red = (double *)dalloc(m, sizeof(double) * m->red_elems);
     QG_CUDA(cudaStreamSynchronize(m->stream));
   } catch (...) {

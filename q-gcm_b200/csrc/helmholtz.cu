@@ -673,6 +673,9 @@ struct TriArgs {
   int ld, nyp, nk, koff, nchunk, lastlen, nmodes, row0;
   size_t lsz;
   int use_yx, nranks;
+  int slab_phase;              // k_tri_reduced on y-slabs: 1 = also emit the slab's first/last rows, 2 = outer neighbours are the adjacent slabs' rows
+  double *slab_send;           // [nmodes][2][ld]
+  const double *slab_outer;    // [nmodes][2][ld]
   double a, ftnorm;
   double *wrk;
   const double *bcoef;
@@ -763,9 +766,9 @@ __global__ void __launch_bounds__(128, 3) k_tri_local(TriArgs t) {
     t.fg[fb + (size_t)c * ld] = u[0];                    // f_c : first row of the chunk
     // g_c : last row of the chunk (the ragged last chunk ends at row len-1; its g only matters
     // to the slab coupling of multi-GPU runs)
-    double gl = u[TRI_L - 1];
+    double gl = 0.0;
 #pragma unroll
-    for (int j = 0; j < TRI_L - 1; ++j) gl = (j == len - 1) ? u[j] : gl;
+    for (int j = 0; j < TRI_L; ++j) gl = fma((j == len - 1) ? 1.0 : 0.0, u[j], gl);   // arithmetic select keeps u in registers
     t.fg[fb + (size_t)(t.nchunk + c) * ld] = gl;
   }
 }
@@ -817,6 +820,15 @@ __global__ void __launch_bounds__(128) k_tri_reduced(TriArgs t) {
     xnext = x;
   }
   yp[0] = 0.0;
+  if (t.slab_phase == 1) {
+    // first and last rows of the slab-local solution: f_0 + eps x_1, g_{C-1} + epsl y_{C-2}
+    const double epsl = t.vll[tb + (size_t)(t.lastlen - 1) * ld];
+    t.slab_send[((size_t)mode * 2 + 0) * ld + col] = f[0] + eps * xnext;
+    t.slab_send[((size_t)mode * 2 + 1) * ld + col] = g[(size_t)(C - 1) * ld] + epsl * yp[(size_t)(C - 1) * ld];
+  } else if (t.slab_phase == 2) {
+    yp[0] = t.slab_outer[((size_t)mode * 2 + 0) * ld + col];
+    xn[(size_t)(C - 1) * ld] = t.slab_outer[((size_t)mode * 2 + 1) * ld + col];
+  }
 }
 
 // --------------------------------------------------------------------------------------
@@ -874,46 +886,45 @@ __global__ void k_slab_fg(SlabArgs t) {
   t.send[((size_t)mode * 2 + 1) * ld + col] = G;
 }
 
-// the inter-slab system (2*nranks unknowns per wavenumber, dense elimination with partial
-// pivoting), the neighbour rows of this slab, and their effect on the first/last chunk's f, g
+// the inter-slab system, the neighbour rows of this slab, and their effect on the first/last
+// chunk's f, g.  Interface i (between slabs i-1 and i) couples Y_{i-1} and X_i:
+//   Y_{i-1} - alpha_{i-1} X_i = G_{i-1} + eps_{i-1} Y_{i-2},   X_i - alpha_i Y_{i-1} = F_i + eps_i X_{i+1}
+// which is an interleaved tridiagonal system: one forward sweep expressing
+// Y_{i-1} = P_i + Q_i X_{i+1}, X_i = xc_i + xq_i X_{i+1}, one back substitution.
 __global__ void k_slab_solve(SlabArgs t) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x, mode = blockIdx.y;
   if (s >= t.nk) return;
-  const int col = t.koff + s, N = t.nranks, n2 = 2 * N, ld = t.ld;
-  double A[16][17];
-  for (int i = 0; i < n2; ++i)
-    for (int j = 0; j <= n2; ++j) A[i][j] = 0.0;
-  for (int r = 0; r < N; ++r) {
-    const double al = t.ae[(((size_t)mode * N + r) * 2 + 0) * ld + col], ep = t.ae[(((size_t)mode * N + r) * 2 + 1) * ld + col];
-    const double F = t.all[(((size_t)r * t.nmodes + mode) * 2 + 0) * ld + col];
-    const double G = t.all[(((size_t)r * t.nmodes + mode) * 2 + 1) * ld + col];
-    const int ix = 2 * r, iy = 2 * r + 1;
-    A[ix][ix] = 1.0; A[iy][iy] = 1.0;
-    if (r > 0) { A[ix][2 * (r - 1) + 1] = -al; A[iy][2 * (r - 1) + 1] = -ep; }
-    if (r < N - 1) { A[ix][2 * (r + 1)] = -ep; A[iy][2 * (r + 1)] = -al; }
-    A[ix][n2] = F; A[iy][n2] = G;
-  }
-  for (int k = 0; k < n2; ++k) {
-    int p = k;
-    for (int i = k + 1; i < n2; ++i)
-      if (fabs(A[i][k]) > fabs(A[p][k])) p = i;
-    if (p != k)
-      for (int j = k; j <= n2; ++j) { const double tmp = A[k][j]; A[k][j] = A[p][j]; A[p][j] = tmp; }
-    const double inv = 1.0 / A[k][k];
-    for (int i = k + 1; i < n2; ++i) {
-      const double f = A[i][k] * inv;
-      if (f != 0.0)
-        for (int j = k; j <= n2; ++j) A[i][j] -= f * A[k][j];
+  const int col = t.koff + s, N = t.nranks, ld = t.ld;
+  double xc[8], xq[8], P[8], Q[8];
+  double Pp = 0.0, Qp = 0.0;
+#pragma unroll
+  for (int i = 1; i < 8; ++i) {
+    if (i < N) {
+      const double a_lo = t.ae[(((size_t)mode * N + i - 1) * 2 + 0) * ld + col], e_lo = t.ae[(((size_t)mode * N + i - 1) * 2 + 1) * ld + col];
+      const double a_hi = t.ae[(((size_t)mode * N + i) * 2 + 0) * ld + col], e_hi = t.ae[(((size_t)mode * N + i) * 2 + 1) * ld + col];
+      const double G = t.all[(((size_t)(i - 1) * t.nmodes + mode) * 2 + 1) * ld + col];
+      const double F = t.all[(((size_t)i * t.nmodes + mode) * 2 + 0) * ld + col];
+      const double gp = G + e_lo * Pp, A = a_lo + e_lo * Qp;
+      const double den = 1.0 / (1.0 - a_hi * A);
+      xc[i] = (F + a_hi * gp) * den;
+      xq[i] = e_hi * den;
+      P[i] = gp + A * xc[i];
+      Q[i] = A * xq[i];
+      Pp = P[i];
+      Qp = Q[i];
     }
   }
-  double z[16];
-  for (int i = n2 - 1; i >= 0; --i) {
-    double acc = A[i][n2];
-    for (int j = i + 1; j < n2; ++j) acc -= A[i][j] * z[j];
-    z[i] = acc / A[i][i];
+  double xnext_run = 0.0, yprev = 0.0, xnext = 0.0;
+#pragma unroll
+  for (int i = 7; i >= 1; --i) {
+    if (i < N) {
+      const double X = xc[i] + xq[i] * xnext_run;      // X_i
+      const double Y = P[i] + Q[i] * xnext_run;        // Y_{i-1}
+      if (i == t.rank) yprev = Y;
+      if (i == t.rank + 1) xnext = X;
+      xnext_run = X;
+    }
   }
-  const double yprev = (t.rank > 0) ? z[2 * (t.rank - 1) + 1] : 0.0;
-  const double xnext = (t.rank < N - 1) ? z[2 * (t.rank + 1)] : 0.0;
   t.outer[((size_t)mode * 2 + 0) * ld + col] = yprev;
   t.outer[((size_t)mode * 2 + 1) * ld + col] = xnext;
   // neighbour rows act on the first chunk through its left spike and on the last chunk
@@ -1185,7 +1196,8 @@ static TriArgs tri_args(HelmPlan &hp, double *wrk, size_t lsz, int nmodes) {
   TriArgs t;
   t.ld = hp.ld; t.nyp = hp.nyp; t.nk = hp.nk; t.koff = hp.koff; t.nchunk = hp.nchunk;
   t.lastlen = hp.lastlen; t.nmodes = nmodes; t.row0 = hp.row0;
-  t.use_yx = (hp.nchunk > 1 || hp.nranks > 1) ? 1 : 0; t.nranks = hp.nranks; t.lsz = lsz; t.a = hp.a; t.ftnorm = hp.ftnorm; t.wrk = wrk;
+  t.use_yx = (hp.nchunk > 1 || hp.nranks > 1) ? 1 : 0; t.nranks = hp.nranks;
+  t.slab_phase = 0; t.slab_send = hp.slab_send; t.slab_outer = hp.slab_yx; t.lsz = lsz; t.a = hp.a; t.ftnorm = hp.ftnorm; t.wrk = wrk;
   t.bcoef = hp.bcoef; t.binv = hp.binv; t.vl = hp.vl; t.vll = hp.vll; t.pt = hp.pt; t.fg = hp.fg; t.yx = hp.yx;
   return t;
 }
@@ -1246,8 +1258,9 @@ void helm_solve_a(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
     auto kfg = k_tri_local<false>;
     QG_LAUNCH(md, "k_tri_fg", gl, 128, 0, kfg, t);
   }
+  t.slab_phase = hp.nranks > 1 ? 1 : 0;
   if (hp.nchunk > 1) QG_LAUNCH(md, "k_tri_reduced", gr, 128, 0, k_tri_reduced, t);
-  if (hp.nranks > 1) {
+  if (hp.nranks > 1 && hp.nchunk == 1) {   // a one-chunk slab has no interface system to piggyback on
     SlabArgs sa = slab_args(hp, nmodes);
     QG_LAUNCH(md, "k_slab_fg", gr, 128, 0, k_slab_fg, sa);
   }
@@ -1262,8 +1275,11 @@ void helm_solve_b(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
   if (hp.nranks > 1) {
     SlabArgs sa = slab_args(hp, nmodes);
     QG_LAUNCH(md, "k_slab_solve", gr, 128, 0, k_slab_solve, sa);
-    if (hp.nchunk > 1) QG_LAUNCH(md, "k_tri_reduced", gr, 128, 0, k_tri_reduced, t);
-    QG_LAUNCH(md, "k_slab_outer", gr, 128, 0, k_slab_outer, sa);
+    t.slab_phase = 2;
+    if (hp.nchunk > 1)
+      QG_LAUNCH(md, "k_tri_reduced", gr, 128, 0, k_tri_reduced, t);
+    else
+      QG_LAUNCH(md, "k_slab_outer", gr, 128, 0, k_slab_outer, sa);
   }
   auto kfin = k_tri_local<true>;
   QG_LAUNCH(md, "k_tri_local", gl, 128, 0, kfin, t);

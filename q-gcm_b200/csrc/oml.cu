@@ -34,6 +34,8 @@ struct OmlArgs {
   // the entoc integral travel through the reduction vector cv
   int t0, t1, p0, p1, multi;
   double *cv;
+  double *part2;          // [3][ORB] slice sums of the block partials
+  unsigned int *ticket;   // last-block-done counter of k_oml_reduce
 };
 
 __device__ __forceinline__ int wrapt(int i, int nxt, int cyc) {
@@ -197,12 +199,53 @@ __global__ void __launch_bounds__(256) k_oml_step(OmlArgs a) {
   }
 }
 
-// sum the block partials in a fixed order; one block of 256 threads
+// boundary-flux monitors of the sb_hflux / nb_hflux options (omlsubs.F:684-726); called by
+// one whole block of 256 threads.  They read the old sst/sstm, which the step leaves intact.
+__device__ void oml_monitors(const OmlArgs &a, double (*red)[8]) {
+  const Grid &g = a.g;
+  const int nxt = g.nxt, nyt = g.nyt, ld = g.ld;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < nxt; i += 256) {
+    if (a.sb && g.wall_s()) {   // y-slabs: the rank that holds the wall owns these monitors
+      const double vm = -a.rhf0hm * (a.taux[i + 1] + a.taux[i]);
+      const double tm = a.sst[i] + a.tsbdy;
+      s[0] += vm; s[1] += vm * tm; s[2] -= (a.sstm[i] - a.tsbdy);
+    }
+    if (a.nb && g.wall_n()) {
+      const double vp = -a.rhf0hm * (a.taux[(size_t)nyt * ld + i + 1] + a.taux[(size_t)nyt * ld + i]);
+      const double tp = a.sst[(size_t)(nyt - 1) * ld + i] + a.tnbdy;
+      s[3] -= vp; s[4] -= vp * tp; s[5] += (a.tnbdy - a.sstm[(size_t)(nyt - 1) * ld + i]);
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  for (int q = 0; q < 6; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_down_sync(0xffffffffu, s[q], o);
+    if (lane == 0) red[q][w] = s[q];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[6];
+    for (int q = 0; q < 6; ++q) { t[q] = 0.0; for (int i = 0; i < 8; ++i) t[q] += red[q][i]; }
+    const double n = (double)nxt;
+    a.sc->vfmads = t[0] / n; a.sc->ttmads = a.hdxm1 * t[1] / n; a.sc->ttmdfs = a.d2tfac * t[2] / n;
+    a.sc->vfmadn = t[3] / n; a.sc->ttmadn = a.hdxm1 * t[4] / n; a.sc->ttmdfn = a.d2tfac * t[5] / n;
+  }
+}
+
+// Sum the block partials of k_oml_step in a fixed order.  ORB blocks each add a contiguous
+// slice; the block that finishes last (ticket counter) adds the ORB slice sums in index
+// order -- deterministic -- and also evaluates the boundary monitors.
+constexpr int ORB = 64;
 __global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy) {
-  __shared__ double red[3][8];
+  __shared__ double red[6][8];
+  __shared__ bool last;
+  const int per = (a.nblocks + ORB - 1) / ORB;
+  const int b0 = blockIdx.x * per, b1 = min(a.nblocks, b0 + per);
   double s[3] = {0.0, 0.0, 0.0};
   for (int q = 0; q < 3; ++q)
-    for (int i = threadIdx.x; i < a.nblocks; i += 256) s[q] += a.part[(size_t)q * a.nblocks + i];
+    for (int i = b0 + threadIdx.x; i < b1; i += 256) s[q] += a.part[(size_t)q * a.nblocks + i];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int q = 0; q < 3; ++q) {
 #pragma unroll
@@ -211,9 +254,22 @@ __global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy) {
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    for (int q = 0; q < 3; ++q) {
+      double t = 0.0;
+      for (int i = 0; i < 8; ++i) t += red[q][i];
+      a.part2[q * ORB + blockIdx.x] = t;
+    }
+    __threadfence();
+    last = (atomicAdd(a.ticket, 1u) == ORB - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    *a.ticket = 0u;
     double t[3] = {0.0, 0.0, 0.0};
     for (int q = 0; q < 3; ++q)
-      for (int i = 0; i < 8; ++i) t[q] += red[q][i];
+      for (int i = 0; i < ORB; ++i) t[q] += a.part2[q * ORB + i];
     a.cv[0] = t[0];                         // xfosum, read by k_oml_entoc (after the all-reduce on slabs)
     a.cv[1] = t[1];
     a.cv[2] = t[2];
@@ -222,6 +278,7 @@ __global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy) {
       a.sc->centoc = t[2] * dxdy;           // omlsubs.F:212
     }
   }
+  if (a.sb || a.nb) oml_monitors(a, red);
 }
 
 // entoc = 4-point average of (xfo - mean) with the edge/corner rules (omlsubs.F:151-205);
@@ -297,40 +354,6 @@ __global__ void __launch_bounds__(256) k_oml_finish(OmlArgs a, double dx) {
   }
 }
 
-// boundary-flux monitors of the sb_hflux / nb_hflux options (omlsubs.F:684-726)
-__global__ void __launch_bounds__(256) k_oml_monitors(OmlArgs a) {
-  __shared__ double red[6][8];
-  const Grid &g = a.g;
-  const int nxt = g.nxt, nyt = g.nyt, ld = g.ld;
-  double s[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = threadIdx.x; i < nxt; i += 256) {
-    if (a.sb && g.wall_s()) {   // y-slabs: the rank that holds the wall owns these monitors
-      const double vm = -a.rhf0hm * (a.taux[i + 1] + a.taux[i]);
-      const double tm = a.sst[i] + a.tsbdy;
-      s[0] += vm; s[1] += vm * tm; s[2] -= (a.sstm[i] - a.tsbdy);
-    }
-    if (a.nb && g.wall_n()) {
-      const double vp = -a.rhf0hm * (a.taux[(size_t)nyt * ld + i + 1] + a.taux[(size_t)nyt * ld + i]);
-      const double tp = a.sst[(size_t)(nyt - 1) * ld + i] + a.tnbdy;
-      s[3] -= vp; s[4] -= vp * tp; s[5] += (a.tnbdy - a.sstm[(size_t)(nyt - 1) * ld + i]);
-    }
-  }
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int q = 0; q < 6; ++q) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_down_sync(0xffffffffu, s[q], o);
-    if (lane == 0) red[q][w] = s[q];
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t[6];
-    for (int q = 0; q < 6; ++q) { t[q] = 0.0; for (int i = 0; i < 8; ++i) t[q] += red[q][i]; }
-    const double n = (double)nxt;
-    a.sc->vfmads = t[0] / n; a.sc->ttmads = a.hdxm1 * t[1] / n; a.sc->ttmdfs = a.d2tfac * t[2] / n;
-    a.sc->vfmadn = t[3] / n; a.sc->ttmadn = a.hdxm1 * t[4] / n; a.sc->ttmdfn = a.d2tfac * t[5] / n;
-  }
-}
-
 static OmlArgs oml_args(qgcm_model *m, dim3 &grid) {
   OmlArgs a;
   const Grid &g = m->go;
@@ -356,13 +379,15 @@ static OmlArgs oml_args(qgcm_model *m, dim3 &grid) {
   a.nblocks = grid.x * grid.y;
   a.part = m->d_red;
   a.rowsum = m->d_red + 3 * (size_t)a.nblocks;
+  a.part2 = a.rowsum + g.nyp;
+  a.ticket = m->d_ticket;
   a.entoc = m->F("entoc");
   a.sc = m->d_scal;
   a.multi = m->nranks > 1;
   a.p0 = g.own0; a.p1 = g.own1;
   a.t0 = g.own0; a.t1 = std::min(g.own1, g.nyt);
   a.cv = m->d_cv;
-  if (m->red_elems < 3 * (size_t)a.nblocks + g.nyp) throw std::runtime_error("oml: reduction scratch too small");
+  if (m->red_elems < 3 * (size_t)a.nblocks + g.nyp + 3 * 64) throw std::runtime_error("oml: reduction scratch too small");
   return a;
 }
 
@@ -372,9 +397,8 @@ void oml_phase_a(qgcm_model *m) {
   dim3 grid;
   OmlArgs a = oml_args(m, grid);
   const Grid &g = m->go;
-  QG_LAUNCH(m, "k_oml_monitors", 1, 256, 0, k_oml_monitors, a);
   QG_LAUNCH(m, "k_oml_step", grid, 256, 0, k_oml_step, a);
-  QG_LAUNCH(m, "k_oml_reduce", 1, 256, 0, k_oml_reduce, a, g.dx * g.dx);
+  QG_LAUNCH(m, "k_oml_reduce", ORB, 256, 0, k_oml_reduce, a, g.dx * g.dx);
 }
 
 // entoc from xfo minus the global mean, its integral (y-slabs: the rank's share in d_cv[3])

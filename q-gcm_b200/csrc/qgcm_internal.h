@@ -162,6 +162,7 @@ struct qgcm_model {
   void *nccl = nullptr;
   std::vector<qgcm_model *> peers;       // loopback group (all ranks in this process), empty otherwise
   double *d_cv = nullptr;                // [32] reduction payload
+  unsigned int *d_ticket = nullptr;      // last-block-done counters
   bool shared_stream = false;            // loopback ranks > 0 borrow rank 0's stream
   double *wrk_o = nullptr, *wrk_a = nullptr;   // modal work arrays [nl][nyp][ld]
   double *xfo = nullptr, *xfa = nullptr, *sstnew = nullptr, *astnew = nullptr, *hmnew = nullptr;
