@@ -198,7 +198,7 @@ static qgcm_model *create(const qgcm_config *cfg) {
       m->xfo = (double *)dalloc(m, sizeof(double) * g.lsz);
       m->sstnew = (double *)dalloc(m, sizeof(double) * g.lsz);
       helm_plan_create(m, m->hpo, g, m->cyclic ? 1 : 0, cfg->rdm2oc, g.nl);
-      const size_t nb = (size_t)((g.nxt + 63) / 64) * ((g.nyt + 7) / 8);
+      const size_t nb = (size_t)((g.nxt + 63) / 64) * ((g.nyt + 7) / 8);   // >= the oml tile count (64 x 12 tiles)
       red = std::max(red, 3 * nb + 4 * (size_t)g.nyp);
     }
     if (m->has_atmos) {

@@ -790,34 +790,57 @@ __global__ void __launch_bounds__(128) k_tri_reduced(TriArgs t) {
   double *__restrict__ xn = t.yx + fb + (size_t)C * ld;
   const double *__restrict__ pt = t.pt + ((size_t)mode * 2 * C) * ld + col;   // p_c
   const double *__restrict__ di = pt + (size_t)C * ld;                        // 1/(1 - p_c q_c)
+  // Both sweeps are latency bound (one thread per wavenumber, ~C dependent steps), so the
+  // loads of PF chunks are issued together ahead of their dependent chain: one exposed
+  // memory latency per PF steps instead of one per step.
+  constexpr int PF = 8;
   // forward elimination: h0_c is parked in yp[c] (overwritten by the back substitution)
   double h0 = g[0], h1 = f[ld], p = pt[ld], dinv = di[ld];
   yp[ld] = h0;
-#pragma unroll 4
-  for (int c = 2; c < C; ++c) {
-    const double gc = g[(size_t)(c - 1) * ld], fc = f[(size_t)c * ld];
-    const double pc = pt[(size_t)c * ld], dc = di[(size_t)c * ld];
-    const double t0 = (h0 - p * h1) * dinv;
-    h0 = gc + eps * t0;
-    yp[(size_t)c * ld] = h0;
-    h1 = fc;
-    p = pc;
-    dinv = dc;
+  for (int c0 = 2; c0 < C; c0 += PF) {
+    double gc[PF], fc[PF], pc[PF], dc[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int c = min(c0 + u, C - 1);
+      gc[u] = g[(size_t)(c - 1) * ld]; fc[u] = f[(size_t)c * ld];
+      pc[u] = pt[(size_t)c * ld]; dc[u] = di[(size_t)c * ld];
+    }
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      if (c0 + u < C) {
+        const double t0 = (h0 - p * h1) * dinv;
+        h0 = gc[u] + eps * t0;
+        yp[(size_t)(c0 + u) * ld] = h0;
+        h1 = fc[u];
+        p = pc[u];
+        dinv = dc[u];
+      }
+    }
   }
   // back substitution
   double xnext = 0.0;
   xn[(size_t)(C - 1) * ld] = 0.0;
-#pragma unroll 4
-  for (int c = C - 1; c >= 1; --c) {
-    const double pc = pt[(size_t)c * ld], dc = di[(size_t)c * ld];
-    const double qc = (c == C - 1) ? -alphal : -alpha;
-    const double hh0 = yp[(size_t)c * ld];
-    const double hh1 = f[(size_t)c * ld] + eps * xnext;
-    const double y = (hh0 - pc * hh1) * dc;    // y_{c-1}: last row of chunk c-1
-    const double x = (hh1 - qc * hh0) * dc;    // x_c    : first row of chunk c
-    yp[(size_t)c * ld] = y;
-    xn[(size_t)(c - 1) * ld] = x;
-    xnext = x;
+  for (int c0 = C - 1; c0 >= 1; c0 -= PF) {
+    double pc[PF], dc[PF], hh[PF], fc[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int c = max(c0 - u, 1);
+      pc[u] = pt[(size_t)c * ld]; dc[u] = di[(size_t)c * ld];
+      hh[u] = yp[(size_t)c * ld]; fc[u] = f[(size_t)c * ld];
+    }
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int c = c0 - u;
+      if (c >= 1) {
+        const double qc = (c == C - 1) ? -alphal : -alpha;
+        const double hh1 = fc[u] + eps * xnext;
+        const double y = (hh[u] - pc[u] * hh1) * dc[u];    // y_{c-1}: last row of chunk c-1
+        const double x = (hh1 - qc * hh[u]) * dc[u];       // x_c    : first row of chunk c
+        yp[(size_t)c * ld] = y;
+        xn[(size_t)(c - 1) * ld] = x;
+        xnext = x;
+      }
+    }
   }
   yp[0] = 0.0;
   if (t.slab_phase == 1) {

@@ -23,19 +23,28 @@ struct InvArgs {
 // (src/ocisubs.F:117-139, src/atisubs.F:106-126)
 __global__ void __launch_bounds__(256) k_l2m(InvArgs a) {
   const Grid &g = a.g;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);   // two columns per thread: 16-byte accesses
   const int j = blockIdx.y + 1;   // 0-based interior row
   if (i >= g.nxp) return;
   const double betay = a.beta * a.yrel[j];
-  const size_t idx = (size_t)j * g.ld + i;
+  const size_t idx = (size_t)j * g.ld + i;     // rows are 128-byte aligned and ld >= nxp + 1 when nxp is odd
   const int nl = a.nl, kbot = a.atmos ? 0 : nl - 1;
-  double ql[NLMAX];
-  for (int k = 0; k < nl; ++k) ql[k] = a.q[k * g.lsz + idx] - betay;
-  ql[kbot] = ql[kbot] - a.ddyn[idx];
+  double2 ql[NLMAX];
+  for (int k = 0; k < nl; ++k) {
+    const double2 q = *reinterpret_cast<const double2 *>(a.q + k * g.lsz + idx);
+    ql[k] = make_double2(q.x - betay, q.y - betay);
+  }
+  const double2 dd = *reinterpret_cast<const double2 *>(a.ddyn + idx);
+  ql[kbot].x = ql[kbot].x - dd.x;
+  ql[kbot].y = ql[kbot].y - dd.y;
   for (int m = 0; m < nl; ++m) {
-    double qm = 0.0;
-    for (int k = 0; k < nl; ++k) qm = qm + a.ctl2m[k + nl * m] * ql[k];
-    a.wrk[m * g.lsz + idx] = a.f0 * qm;
+    double qx = 0.0, qy = 0.0;
+    for (int k = 0; k < nl; ++k) {
+      qx = qx + a.ctl2m[k + nl * m] * ql[k].x;
+      qy = qy + a.ctl2m[k + nl * m] * ql[k].y;
+    }
+    // the pad column beyond nxp (odd nxp) receives a value nobody reads
+    *reinterpret_cast<double2 *>(a.wrk + m * g.lsz + idx) = make_double2(a.f0 * qx, a.f0 * qy);
   }
 }
 
@@ -294,7 +303,7 @@ static void invert(qgcm_model *m, bool atmos) {
   fill_inv(m, atmos, a);
   const Grid &g = a.g;
   HelmPlan &hp = atmos ? m->hpa : m->hpo;
-  dim3 gi((g.nxp + 255) / 256, g.nyp - 2);
+  dim3 gi((g.nxp + 511) / 512, g.nyp - 2);
   QG_LAUNCH(m, "k_l2m", gi, 256, 0, k_l2m, a);
   helm_solve(m, hp, a.wrk, g.nl);
   inv_scalars_m2l(m, atmos, a);
@@ -306,7 +315,7 @@ void ocinvq_phase_a(qgcm_model *m) {
   InvArgs a;
   fill_inv(m, false, a);
   const Grid &g = a.g;
-  dim3 gi((g.nxp + 255) / 256, g.nyp - 2);
+  dim3 gi((g.nxp + 511) / 512, g.nyp - 2);
   QG_LAUNCH(m, "k_l2m", gi, 256, 0, k_l2m, a);
   helm_solve_a(m, m->hpo, a.wrk, g.nl);
 }

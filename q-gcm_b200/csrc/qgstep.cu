@@ -12,7 +12,7 @@
 namespace qg {
 
 constexpr int WOUT = 26;    // output columns per warp (32 lanes minus a halo of 3 each side)
-constexpr int RCH = 64;     // rows marched by one warp
+constexpr int RCH = 128;    // rows marched by one warp (6 pipeline fill rows per march)
 
 struct QgArgs {
   Grid g;
