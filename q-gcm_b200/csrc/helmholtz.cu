@@ -483,11 +483,12 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
   double *IN = reinterpret_cast<double *>(smraw);                 // N doubles: raw row (TMA target)
   const double2 *IN2 = reinterpret_cast<const double2 *>(smraw);
   double2 *W = reinterpret_cast<double2 *>(smraw + (size_t)N * 8);   // exchange buffer
-  double *Wd = reinterpret_cast<double *>(W);
-  double *red = reinterpret_cast<double *>(smraw + (size_t)N * 8 + (size_t)WSZ * 16);   // 32 doubles
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(red + 32);
+  double *SC = reinterpret_cast<double *>(smraw + (size_t)N * 8 + (size_t)WSZ * 16);   // M doubles: summands / running sums of the odd outputs
+  double *red = SC + M;                                                                // 64 doubles
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(red + 64);
   const int t0 = threadIdx.x;
   const uint32_t bar = smem_u32(mbar), in_s = smem_u32(IN);
+  int prev_slot = -1;      // rowsum slot of the previous row, finished one barrier later (INV)
 
   int item = blockIdx.x;
   if (t0 == 0) {
@@ -534,6 +535,13 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       for (int q = 0; q < R1; ++q) W[t * (R1 + 1) + q] = v1[q];
     }
     __syncthreads();   // raw row consumed, pass 1 complete
+    if (INV && t == 0 && prev_slot >= 0) {
+      // row sum of the previous row: the per-warp partials were parked before this barrier
+      double sum = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += red[16 + i];
+      a.rowsum[prev_slot] = sum;
+    }
     if (t == 0) {
       const int nxt = item + gridDim.x;
       if (nxt < a.nitems) {
@@ -602,10 +610,9 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
         cs[0] = 0.5 * (v[0].x + v[0].y);   // out_1 = F_0 / 2
       }
     }
-    __syncthreads();   // partners read
     if (t < L3) {
 #pragma unroll
-      for (int q = 0; q < R3; ++q) Wd[t + q * L3] = cs[q];
+      for (int q = 0; q < R3; ++q) SC[t + q * L3] = cs[q];
     }
     __syncthreads();
     // ---- running sum over k (dsint.f:33-37): contiguous segment per thread ----
@@ -615,7 +622,7 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       for (int q = 0; q < SEG; ++q) sg[q] = 0.0;
       double tot = 0.0;
       if (t < NSC) {
-        const double2 *src = reinterpret_cast<const double2 *>(Wd + t * SEG);
+        const double2 *src = reinterpret_cast<const double2 *>(SC + t * SEG);
 #pragma unroll
         for (int q = 0; q < SEG / 2; ++q) {
           const double2 c2 = src[q];
@@ -638,7 +645,7 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       for (int i = 0; i < 8; ++i)
         if (i < wp) off += red[i];
       if (t < NSC) {
-        double2 *dst = reinterpret_cast<double2 *>(Wd + t * SEG);
+        double2 *dst = reinterpret_cast<double2 *>(SC + t * SEG);
 #pragma unroll
         for (int q = 0; q < SEG / 2; ++q) dst[q] = make_double2(sg[2 * q] + off, sg[2 * q + 1] + off);
       }
@@ -651,17 +658,29 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
 #pragma unroll
       for (int q = 0; q < R3; ++q) {
         const int k = t + q * L3;
-        const double od = Wd[k];
+        const double od = SC[k];
         out[k] = make_double2(ev[q], od);
         if (INV) part += ev[q] + od;
       }
     }
     if (INV) {
+      // xintp row sum (intsubs.f:105-112): warp partials now, the eight-term sum after the next
+      // barrier (the next row's first one, or the one below the loop); W and SC are free for
+      // the next row without a barrier here because its first pass only writes W
       if (t == 0) row[a.nxp - 1] = 0.0;
-      const double sum = block_sum(part, red + 8);
-      if (t == 0) a.rowsum[(size_t)mode * a.nyp + (r + a.row0)] = sum;
-    } else {
-      __syncthreads();   // W is rewritten by the next row's first pass
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+      if (lane == 0) red[16 + wp] = part;
+      prev_slot = mode * a.nyp + (r + a.row0);
+    }
+  }
+  if (INV) {
+    __syncthreads();
+    if (t0 == 0 && prev_slot >= 0) {
+      double sum = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += red[16 + i];
+      a.rowsum[prev_slot] = sum;
     }
   }
 }
@@ -793,7 +812,7 @@ __global__ void __launch_bounds__(128) k_tri_reduced(TriArgs t) {
   // Both sweeps are latency bound (one thread per wavenumber, ~C dependent steps), so the
   // loads of PF chunks are issued together ahead of their dependent chain: one exposed
   // memory latency per PF steps instead of one per step.
-  constexpr int PF = 8;
+  constexpr int PF = 16;
   // forward elimination: h0_c is parked in yp[c] (overwritten by the back substitution)
   double h0 = g[0], h1 = f[ld], p = pt[ld], dinv = di[ld];
   yp[ld] = h0;
@@ -990,7 +1009,7 @@ __global__ void k_zero_rows(double *wrk, size_t lsz, int ld, int nyp, int nxp, i
 template <int R3>
 static void dst3_launch_t(qgcm_model *md, HelmPlan &hp, const Dst3Args &a, bool inverse) {
   constexpr int M = 16 * 15 * R3;
-  const size_t smem = (size_t)M * 16 + (size_t)(M + M / 16) * 16 + 32 * 8 + 16;
+  const size_t smem = (size_t)M * 16 + (size_t)(M + M / 16) * 16 + (size_t)M * 8 + 64 * 8 + 16;
   auto kf = k_dst3<R3, false>;
   auto ki = k_dst3<R3, true>;
   if (!hp.fast_attr) {
