@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(256) k_oml_entoc(OmlArgs a) {
   const int nxp = g.nxp, nyp = g.nyp, nxt = g.nxt, nyt = g.nyt, ld = g.ld, cyc = g.cyclic;
   const double mean = a.cv[0] * g.norm;   // xfosum*ocnorm
   double part = 0.0;
+#pragma unroll 4
   for (int i = threadIdx.x; i < nxp; i += 256) {
     // T cells around p point (i,j): (i-1,j-1), (i,j-1), (i-1,j), (i,j) in 0-based T indices
     const int jm = j - 1, jc = j;
