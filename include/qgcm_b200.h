@@ -156,6 +156,13 @@ int qgcm_abi_version(void);
 int qgcm_set_field(qgcm_model *m, const char *name, const double *host, int64_t n);
 int qgcm_get_field(qgcm_model *m, const char *name, double *host, int64_t n);
 int qgcm_field_size(qgcm_model *m, const char *name, int64_t *n);
+/* Overlapped upload for forcing that the host supplies while the model runs (the ocean-only
+ * reference reads tauxo/tauyo/fnetoc once, src/q-gcm.F:790-808; a host that updates them every
+ * step uses this pair).  `host` must be page-locked and stay valid until the commit.  The
+ * copy runs on a second stream into a shadow buffer; qgcm_commit_fields makes the step
+ * stream wait for it and switches the named fields over. */
+int qgcm_set_field_async(qgcm_model *m, const char *name, const double *host, int64_t n);
+int qgcm_commit_fields(qgcm_model *m);
 int qgcm_set_scalars(qgcm_model *m, const qgcm_scalars *s);
 int qgcm_get_scalars(qgcm_model *m, qgcm_scalars *s);
 int qgcm_sync(qgcm_model *m);

@@ -276,6 +276,44 @@ static void copy_field(qgcm_model *m, qgcm_model::Field &f, double *host, bool t
 void launch_xforc(qgcm_model *m);
 void launch_aml(qgcm_model *m);
 
+// Asynchronous upload of a gridded field from PINNED host memory: the copy runs on a second
+// stream into a shadow buffer while the model keeps stepping on the current one; the swap
+// happens at qgcm_commit_fields.
+static void set_field_async(qgcm_model *m, const char *name, const double *host, int64_t n) {
+  qgcm_model::Field &f = lookup(m, name, n);
+  if (!f.ld) throw std::runtime_error("qgcm_set_field_async: gridded fields only");
+  static const char *ok[] = {"tauxo", "tauyo", "fnetoc", "ddynoc", "tauxa", "tauya", "fnetat", "ddynat", "dtopat"};
+  bool allowed = false;
+  for (const char *o : ok) allowed = allowed || std::strcmp(o, name) == 0;
+  if (!allowed) throw std::runtime_error("qgcm_set_field_async: only forcing fields the step never writes or rotates");
+  if (!m->copy_stream) {
+    QG_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    QG_CUDA(cudaEventCreateWithFlags(&m->ev_copy, cudaEventDisableTiming));
+    QG_CUDA(cudaEventCreateWithFlags(&m->ev_step, cudaEventDisableTiming));
+  }
+  double *&shadow = m->shadow[name];
+  if (!shadow) shadow = (double *)dalloc(m, sizeof(double) * f.elems);
+  if (m->pending.empty()) {
+    // the shadow buffers were the live ones until the last commit: kernels enqueued before
+    // it may still read them
+    QG_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_step, 0));
+  }
+  for (int k = 0; k < f.nl; ++k) {
+    const double *h = host + (size_t)k * f.nx * f.nyg + (size_t)f.joff * f.nx;
+    QG_CUDA(cudaMemcpy2DAsync(shadow + (size_t)k * f.lsz, sizeof(double) * f.ld, h, sizeof(double) * f.nx, sizeof(double) * f.nx,
+                              f.ny, cudaMemcpyHostToDevice, m->copy_stream));
+  }
+  m->pending.push_back(name);
+}
+static void commit_fields(qgcm_model *m) {
+  if (m->pending.empty()) return;
+  QG_CUDA(cudaEventRecord(m->ev_copy, m->copy_stream));
+  QG_CUDA(cudaStreamWaitEvent(m->stream, m->ev_copy, 0));
+  for (const std::string &nm : m->pending) std::swap(m->fields.at(nm).d, m->shadow.at(nm));
+  m->pending.clear();
+  QG_CUDA(cudaEventRecord(m->ev_step, m->stream));   // everything that reads the retired buffers is before this point
+}
+
 static void ocean_step(qgcm_model *m) {
   if (m->nranks > 1) { slab_ocean_step(ranks_of(m)); return; }
   launch_oml(m);
@@ -307,6 +345,7 @@ int qgcm_destroy(qgcm_model *m) {
   cudaStreamSynchronize(m->stream);
   for (void *p : m->allocs) cudaFree(p);
   if (m->nccl) { try { nccl_destroy(m); } catch (...) {} }
+  if (m->copy_stream) { cudaStreamSynchronize(m->copy_stream); cudaStreamDestroy(m->copy_stream); cudaEventDestroy(m->ev_copy); cudaEventDestroy(m->ev_step); }
   if (!m->shared_stream) cudaStreamDestroy(m->stream);
   delete m;
   return 0;
@@ -321,6 +360,8 @@ int qgcm_set_field(qgcm_model *m, const char *name, const double *host, int64_t 
 int qgcm_get_field(qgcm_model *m, const char *name, double *host, int64_t n) {
   QG_TRY(copy_field(m, lookup(m, name, n), host, false));
 }
+int qgcm_set_field_async(qgcm_model *m, const char *name, const double *host, int64_t n) { QG_TRY(set_field_async(m, name, host, n)); }
+int qgcm_commit_fields(qgcm_model *m) { QG_TRY(commit_fields(m)); }
 int qgcm_set_scalars(qgcm_model *m, const qgcm_scalars *s) {
   QG_TRY(QG_CUDA(cudaMemcpyAsync(m->d_scal, s, sizeof(*s), cudaMemcpyHostToDevice, m->stream));
          QG_CUDA(cudaStreamSynchronize(m->stream)));

@@ -164,6 +164,11 @@ struct qgcm_model {
   double *d_cv = nullptr;                // [32] reduction payload
   unsigned int *d_ticket = nullptr;      // last-block-done counters
   bool shared_stream = false;            // loopback ranks > 0 borrow rank 0's stream
+  // qgcm_set_field_async: copy stream, shadow buffers, names waiting for qgcm_commit_fields
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr, ev_step = nullptr;
+  std::map<std::string, double *> shadow;
+  std::vector<std::string> pending;
   double *wrk_o = nullptr, *wrk_a = nullptr;   // modal work arrays [nl][nyp][ld]
   double *xfo = nullptr, *xfa = nullptr, *sstnew = nullptr, *astnew = nullptr, *hmnew = nullptr;
   std::vector<void *> allocs;

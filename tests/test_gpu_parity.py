@@ -142,6 +142,31 @@ def test_roundtrip_and_errors(qg):
         m.set_field("po", t)
 
 
+def test_async_forcing_upload(qg, pyorc):
+    """qgcm_set_field_async + qgcm_commit_fields: the step after the commit sees the new forcing,
+    the step before it the old one"""
+    import ctypes as C
+    import torch
+    p = small_configs(qg)["box_dg"]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    new = {n: 1.5 * cpu.get_field(n) for n in ("tauxo", "tauyo", "fnetoc")}
+    pinned = {n: torch.from_numpy(new[n].copy()).pin_memory() for n in new}
+    gpu.ocean_step()
+    for n, t in pinned.items():     # queued while the first step may still be running
+        gpu._call("set_field_async", n.encode(), C.cast(t.data_ptr(), C.POINTER(C.c_double)), C.c_int64(t.numel()))
+    gpu._call("commit_fields")
+    gpu.xforc()                      # wekto/wekpo from the new stress (src/xfosubs.F:568-709)
+    gpu.ocean_step()
+    cpu.ocean_step()
+    for n in new:
+        cpu.set_field(n, new[n])
+    cpu.xforc()
+    cpu.ocean_step()
+    compare(gpu, cpu, OCEAN_CHECK + ("tauxo", "tauyo", "fnetoc"), label="async forcing")
+    with pytest.raises(RuntimeError):
+        gpu._call("set_field_async", b"po", C.cast(pinned["tauxo"].data_ptr(), C.POINTER(C.c_double)), C.c_int64(1))
+
+
 @pytest.mark.parametrize("nxto,cyc", [(96, 0), (120, 0), (160, 0), (180, 0), (200, 0), (216, 0), (240, 1),
                                       (288, 1), (400, 1), (324, 0), (480, 1), (960, 0), (1440, 0), (1920, 0),
                                       (2400, 0), (2880, 0), (3840, 0), (4800, 0)])
