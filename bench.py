@@ -313,8 +313,15 @@ def main():
     dpp = passes_per_launch(dom, p.has("cyclic_ocean")) or 0.0
     dms = prof[dom][1] / prof[dom][0]
     ach = dpp * fieldpass / world / (dms * 1e-3) / 1e9
+    traffic = None
+    try:      # DRAM bytes per launch from the committed ncu --set full capture (single GPU, natl1km)
+        with open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")) as f:
+            if world == 1 and args.workload == "natl1km":
+                traffic = json.load(f)["bytes_per_launch"].get(dom)
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src,
-            "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
             "algorithmic_bytes_per_launch": dpp * fieldpass / world, "ms_per_launch": dms,
             "share_of_step": prof[dom][1] / tot_ms}
     step_bytes = (61.0 if not p.has("cyclic_ocean") else 59.0) * fieldpass
