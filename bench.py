@@ -167,7 +167,8 @@ def run_reference(args, qg):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
         "warmup": warm, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s ocean-only %dx%dx%d" % (p.name, p.nxpo, p.nypo, p.nlo)},
+        "config": {"workload": "%s ocean-only %dx%dx%d, box, dto=%gs" % (p.name, p.nxpo, p.nypo, p.nlo, p.dto),
+                   "parallelism": "%d host threads (OpenMP)" % cores},
         "gpt_updates_per_s": v * p.nxpo * p.nypo * p.nlo / 1e9,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d CPU ocean steps (C++/OpenMP restatement of the reference; the Fortran "
