@@ -10,6 +10,7 @@
 //   surrounding T cells onto p points (entoc), with xintp row sums for xon(1).
 // The reference needs ~24 field passes for this; here it is 11.
 #include <algorithm>
+#include <cstdlib>
 
 #include "qgcm_internal.h"
 
@@ -199,6 +200,245 @@ __global__ void __launch_bounds__(256) k_oml_step(OmlArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Marching version of the step (same arithmetic as k_oml_step, register reuse instead of
+// shared-memory tiles): a warp owns 32 T columns (28 outputs + halo 2 for del4 of sstm) and
+// marches north; every lane keeps three rows of sstm, del2t and sst and two rows of the
+// p-grid fields of its own column in registers, E/W neighbours come from warp shuffles and
+// the rows ahead are prefetched with cp.async into a per-warp ring.
+// ------------------------------------------------------------------------------------------
+constexpr int MW = 60;      // output columns per warp: 32 lanes x 2 columns minus a halo of 2 columns on either side
+constexpr int MR = 128;     // rows marched by one warp
+constexpr int MD = 4;       // prefetch depth (row stages in flight; 14 KB of shared memory per warp)
+constexpr int MNF = 7;      // fields per stage: sstm, sst, p, taux, tauy, wekt, fnet
+
+__device__ __forceinline__ void oml_cp16(double2 *smem_dst, const double *gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ double shw(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }     // value of lane-1 (west)
+__device__ __forceinline__ double she(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }   // value of lane+1 (east)
+
+// del2t of the lagged temperature at one T cell with every boundary-condition variant
+// (omlsubs.F:291-682); neighbour order as in the reference so the sums round identically
+__device__ __forceinline__ double oml_del2(const OmlArgs &a, int gi, int gj, int nxt, int nyt, int cyc, double c, double w,
+                                           double e, double s, double n) {
+  const bool hasW = cyc || gi > 0, hasE = cyc || gi < nxt - 1;
+  double sum, cnt;
+  if (gj == 0) {
+    sum = 0.0; cnt = 0.0;
+    if (hasW) { sum = w; cnt += 1.0; }
+    if (hasE) { sum = (cnt > 0.0) ? sum + e : e; cnt += 1.0; }
+    sum = sum + n; cnt += 1.0;
+    if (a.sb) { sum = sum + a.tsbdy; cnt += 1.0; }
+    return sum - cnt * c;
+  }
+  if (gj == nyt - 1) {
+    const bool ne_cyc = cyc && gi == nxt - 1;
+    sum = s; cnt = 1.0;
+    if (hasW) { sum = sum + w; cnt += 1.0; }
+    if (a.nb && !ne_cyc) { sum = sum + a.tnbdy; cnt += 1.0; }
+    if (hasE) { sum = sum + e; cnt += 1.0; }
+    if (a.nb && ne_cyc) return sum - 4.0 * c + a.tnbdy;
+    return sum - cnt * c;
+  }
+  sum = s; cnt = 1.0;
+  if (hasW) { sum = sum + w; cnt += 1.0; }
+  if (hasE) { sum = sum + e; cnt += 1.0; }
+  sum = sum + n; cnt += 1.0;
+  return sum - cnt * c;
+}
+
+// advection + diffusion + prediction + entrainment + convection at one T cell
+// (omlsubs.F:297-384, :728-758, :94-127); p/x/y are po(1), tauxo, tauyo at the cell's corners
+// (S/N row, plain = west corner, e = east corner)
+struct OmlOut { double sst, xf, cfr, cen; };
+__device__ __forceinline__ OmlOut oml_cell(const OmlArgs &a, int gi, int gj, int nxt, int nyt, int cyc, double tc, double tW,
+                                           double tE, double tS, double tN, double dcen, double dW, double dE, double dS, double dN,
+                                           double tmc, double pS, double pN, double pSe, double pNe, double xS, double xN, double xSe,
+                                           double xNe, double yS, double yN, double ySe, double yNe, double wek, double fnet) {
+  const bool wallW = !cyc && gi == 0, wallE = !cyc && gi == nxt - 1;
+  double um = -a.uvgfac * (pN - pS) + a.rhf0hm * (yN + yS);
+  double up = -a.uvgfac * (pNe - pSe) + a.rhf0hm * (yNe + ySe);
+  double tm = tc + tW, tp = tc + tE;
+  if (wallW) { um = 0.0; tm = 0.0; }
+  if (wallE) { up = 0.0; tp = 0.0; }
+  const double hxadv = a.hdxm1 * (up * tp - um * tm);
+  const double vs = a.uvgfac * (pSe - pS) - a.rhf0hm * (xSe + xS);
+  const double vn = a.uvgfac * (pNe - pN) - a.rhf0hm * (xNe + xN);
+  double hyadv;
+  if (gj == 0) {
+    const double tpn = tc + tN;
+    if (a.sb) {
+      const double vm = -a.rhf0hm * (xSe + xS);
+      const double tms = tc + a.tsbdy;
+      hyadv = a.hdxm1 * (vn * tpn - vm * tms);
+    } else {
+      hyadv = a.hdxm1 * (vn * tpn);
+    }
+  } else if (gj == nyt - 1) {
+    const double tms = tS + tc;
+    if (a.nb) {
+      const double vp = -a.rhf0hm * (xNe + xN);
+      const double tpn = tc + a.tnbdy;
+      hyadv = a.hdxm1 * (vp * tpn - vs * tms);
+    } else {
+      hyadv = a.hdxm1 * (-vs * tms);
+    }
+  } else {
+    hyadv = a.hdxm1 * (vn * (tN + tc) - vs * (tc + tS));
+  }
+  double rhs = -(hxadv + hyadv);
+  // dummy columns of del2t: no diffusive flux through solid W/E walls
+  const double dw = wallW ? dcen : dW;
+  const double de = wallE ? dcen : dE;
+  double d4;
+  if (gj == 0) d4 = dw + de + dN - 3.0 * dcen;
+  else if (gj == nyt - 1) d4 = dS + dw + de - 3.0 * dcen;
+  else d4 = dS + dw + de + dN - 4.0 * dcen;
+  rhs = rhs + a.d2tfac * dcen - a.d4tfac * d4;
+  const double diabat = 0.5 * wek * (tmc + a.toc1);
+  double sstnew = tmc + a.tdt * (rhs + a.hmoinv * (a.rrcpoc * fnet + diabat));
+  const double xfoent = -(0.5 * a.dtoinv) * wek * (tmc - a.toc1);
+  const double dtonew = a.toc1 - sstnew;
+  const double coneno = a.entfac * fmax(0.0, dtonew);
+  OmlOut o;
+  o.xf = xfoent - coneno;
+  o.sst = sstnew + fmax(0.0, dtonew);
+  o.cfr = (-dtonew >= 0.0) ? 0.0 : 1.0;   // 0.5 - sign(0.5, -dtonew)
+  o.cen = -coneno;
+  return o;
+}
+
+// grid (ceil(warps/4), ceil(nyt/MR)); each lane owns the even/odd column pair (g0, g0+1):
+// 16-byte cp.async and 16-byte stores, one shuffle pair per field row for two cells
+__global__ void __launch_bounds__(128) k_oml_march(OmlArgs a) {
+  extern __shared__ double2 oml_ring[];
+  __shared__ double red[3][4];
+  const Grid &g = a.g;
+  const int nxt = g.nxt, nyt = g.nyt, ld = g.ld, cyc = g.cyclic;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int wx = blockIdx.x * 4 + wib;
+  const bool active = wx * MW < nxt;                 // whole warp
+  double2 *ring = oml_ring + (size_t)wib * (MD * MNF * 32) + lane;
+  const int g0 = wx * MW - 2 + 2 * lane;             // first T column of this lane's pair (even)
+  int c0 = g0;                                       // canonical column of the pair
+  if (cyc) { if (c0 < 0) c0 += nxt; if (c0 >= nxt) c0 -= nxt; }
+  // the pair is loaded when its first column exists; a second column beyond the row's end is padding
+  const bool pairT = c0 >= 0 && c0 < nxt, pairP = cyc ? true : (c0 >= 0 && c0 <= nxt);
+  const bool t0ok = pairT, t1ok = pairT && (cyc || g0 + 1 < nxt);
+  const bool p1ok = cyc ? true : (pairP && g0 + 1 <= nxt);
+  const bool out0 = lane >= 1 && lane < 31 && g0 < nxt, out1 = lane >= 1 && lane < 31 && g0 + 1 < nxt;
+  const int ja = blockIdx.y * MR, jb = min(nyt, ja + MR);
+  const int cc = (pairT || pairP) ? c0 : 0;
+  double pxfo = 0.0, pcfr = 0.0, pcen = 0.0;
+  if (active) {
+#pragma unroll
+    for (int s = 0; s < MD * MNF; ++s) ring[s * 32] = make_double2(0.0, 0.0);   // rows/columns outside the domain read as zero
+    __syncwarp();
+    // stage r carries sstm(r), sst(r-1), p/taux/tauy at p row r-1, wekt/fnet(r-2)
+    auto issue = [&](int r) {
+      double2 *slot = ring + (size_t)((r + 8 * MD) % MD) * (MNF * 32);
+      if (r <= jb + 1) {     // not past the last row this march needs
+        if (pairT && r >= 0 && r < nyt) oml_cp16(slot, a.sstm + (size_t)r * ld + cc);
+        if (pairT && r - 1 >= 0 && r - 1 < nyt) oml_cp16(slot + 32, a.sst + (size_t)(r - 1) * ld + cc);
+        if (pairP && r - 1 >= 0 && r - 1 <= nyt) {
+          const size_t o = (size_t)(r - 1) * ld + cc;
+          oml_cp16(slot + 64, a.po1 + o);
+          oml_cp16(slot + 96, a.taux + o);
+          oml_cp16(slot + 128, a.tauy + o);
+        }
+        if (pairT && r - 2 >= 0 && r - 2 < nyt) {
+          const size_t o = (size_t)(r - 2) * ld + cc;
+          oml_cp16(slot + 160, a.wekt + o);
+          oml_cp16(slot + 192, a.fnet + o);
+        }
+      }
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    // [.][0] / [.][1]: the lane's two columns
+    double tm0[2] = {0, 0}, tm1[2] = {0, 0}, tm2[2] = {0, 0}, da[2] = {0, 0}, db[2] = {0, 0}, dc[2] = {0, 0};
+    double tA[2] = {0, 0}, tB[2] = {0, 0}, tC[2] = {0, 0};
+    double pS[2] = {0, 0}, pN[2] = {0, 0}, xS[2] = {0, 0}, xN[2] = {0, 0}, yS[2] = {0, 0}, yN[2] = {0, 0};
+    double pSx = 0, pNx = 0, xSx = 0, xNx = 0, ySx = 0, yNx = 0;   // p-grid values at the column east of the pair (lane+1's first)
+    const int r0 = ja - 2;
+#pragma unroll
+    for (int s = 0; s < MD - 1; ++s) issue(r0 + s);
+    for (int r = r0; r <= jb + 1; ++r) {
+      issue(r + MD - 1);
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(MD - 1) : "memory");
+      const double2 *slot = ring + (size_t)((r + 8 * MD) % MD) * (MNF * 32);
+      const bool in_tm = r >= 0 && r < nyt, in_t = r - 1 >= 0 && r - 1 < nyt, in_p = r - 1 >= 0 && r - 1 <= nyt;
+      {
+        const double2 vtm = slot[0], vt = slot[32], vp = slot[64], vx = slot[96], vy = slot[128];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tm0[c] = tm1[c]; tm1[c] = tm2[c];
+          tA[c] = tB[c]; tB[c] = tC[c];
+          pS[c] = pN[c]; xS[c] = xN[c]; yS[c] = yN[c];
+        }
+        pSx = pNx; xSx = xNx; ySx = yNx;
+        tm2[0] = (in_tm && t0ok) ? vtm.x : 0.0; tm2[1] = (in_tm && t1ok) ? vtm.y : 0.0;
+        tC[0] = (in_t && t0ok) ? vt.x : 0.0;    tC[1] = (in_t && t1ok) ? vt.y : 0.0;
+        pN[0] = (in_p && pairP) ? vp.x : 0.0;   pN[1] = (in_p && p1ok) ? vp.y : 0.0;
+        xN[0] = (in_p && pairP) ? vx.x : 0.0;   xN[1] = (in_p && p1ok) ? vx.y : 0.0;
+        yN[0] = (in_p && pairP) ? vy.x : 0.0;   yN[1] = (in_p && p1ok) ? vy.y : 0.0;
+        pNx = she(pN[0]); xNx = she(xN[0]); yNx = she(yN[0]);
+      }
+      // ---- del2t at T row r-1
+      {
+        const int gj = r - 1;
+        const double w0 = shw(tm1[1]), e1 = she(tm1[0]);
+        double v0 = 0.0, v1 = 0.0;
+        if (gj >= 0 && gj < nyt) {
+          if (t0ok) v0 = oml_del2(a, g0, gj, nxt, nyt, cyc, tm1[0], w0, tm1[1], tm0[0], tm2[0]);
+          if (t1ok) v1 = oml_del2(a, g0 + 1, gj, nxt, nyt, cyc, tm1[1], tm1[0], e1, tm0[1], tm2[1]);
+        }
+        da[0] = db[0]; db[0] = dc[0]; dc[0] = v0;
+        da[1] = db[1]; db[1] = dc[1]; dc[1] = v1;
+      }
+      // ---- T row r-2: the two cells of this lane
+      const int gj = r - 2;
+      const double tW0 = shw(tB[1]), tE1 = she(tB[0]), dW0 = shw(db[1]), dE1 = she(db[0]);
+      if (gj < ja || gj >= jb || !out0) continue;
+      const double2 wk = slot[160], fn = slot[192];
+      const OmlOut o0 = oml_cell(a, g0, gj, nxt, nyt, cyc, tB[0], tW0, tB[1], tA[0], tC[0], db[0], dW0, db[1], da[0], dc[0], tm0[0],
+                                 pS[0], pN[0], pS[1], pN[1], xS[0], xN[0], xS[1], xN[1], yS[0], yN[0], yS[1], yN[1], wk.x, fn.x);
+      OmlOut o1 = o0;
+      if (out1)
+        o1 = oml_cell(a, g0 + 1, gj, nxt, nyt, cyc, tB[1], tB[0], tE1, tA[1], tC[1], db[1], db[0], dE1, da[1], dc[1], tm0[1],
+                      pS[1], pN[1], pSx, pNx, xS[1], xN[1], xSx, xNx, yS[1], yN[1], ySx, yNx, wk.y, fn.y);
+      const size_t idx = (size_t)gj * ld + g0;
+      if (out1) {
+        *reinterpret_cast<double2 *>(a.xfo + idx) = make_double2(o0.xf, o1.xf);
+        *reinterpret_cast<double2 *>(a.sstnew + idx) = make_double2(o0.sst, o1.sst);
+      } else {
+        a.xfo[idx] = o0.xf;
+        a.sstnew[idx] = o0.sst;
+      }
+      if (gj >= a.t0 && gj < a.t1) {            // halo rows of a slab belong to the neighbour's sums
+        pxfo += o0.xf; pcfr += o0.cfr; pcen += o0.cen;
+        if (out1) { pxfo += o1.xf; pcfr += o1.cfr; pcen += o1.cen; }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  }
+  // block partial sums (fixed order)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pxfo += __shfl_down_sync(0xffffffffu, pxfo, o);
+    pcfr += __shfl_down_sync(0xffffffffu, pcfr, o);
+    pcen += __shfl_down_sync(0xffffffffu, pcen, o);
+  }
+  if (lane == 0) { red[0][wib] = pxfo; red[1][wib] = pcfr; red[2][wib] = pcen; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int i = 0; i < 4; ++i) t += red[threadIdx.x][i];
+    a.part[(size_t)threadIdx.x * a.nblocks + blockIdx.y * gridDim.x + blockIdx.x] = t;
+  }
+}
+
 // boundary-flux monitors of the sb_hflux / nb_hflux options (omlsubs.F:684-726); called by
 // one whole block of 256 threads.  They read the old sst/sstm, which the step leaves intact.
 __device__ void oml_monitors(const OmlArgs &a, double (*red)[8]) {
@@ -376,7 +616,10 @@ static OmlArgs oml_args(qgcm_model *m, dim3 &grid) {
   a.po1 = m->F("po"); a.taux = m->F("tauxo"); a.tauy = m->F("tauyo");
   a.sst = m->F("sst"); a.sstm = m->F("sstm"); a.wekt = m->F("wekto"); a.fnet = m->F("fnetoc");
   a.sstnew = m->sstnew; a.xfo = m->xfo;
-  grid = dim3((g.nxt + OX - 1) / OX, (g.nyt + OY - 1) / OY);
+  // QGCM_OML_TILES=1 selects the shared-memory tile kernel (kept for comparison)
+  static const bool tiles = getenv("QGCM_OML_TILES") != nullptr;
+  if (tiles) grid = dim3((g.nxt + OX - 1) / OX, (g.nyt + OY - 1) / OY);
+  else grid = dim3(((g.nxt + MW - 1) / MW + 3) / 4, (g.nyt + MR - 1) / MR);
   a.nblocks = grid.x * grid.y;
   a.part = m->d_red;
   a.rowsum = m->d_red + 3 * (size_t)a.nblocks;
@@ -398,7 +641,17 @@ void oml_phase_a(qgcm_model *m) {
   dim3 grid;
   OmlArgs a = oml_args(m, grid);
   const Grid &g = m->go;
-  QG_LAUNCH(m, "k_oml_step", grid, 256, 0, k_oml_step, a);
+  if (getenv("QGCM_OML_TILES")) {
+    QG_LAUNCH(m, "k_oml_step", grid, 256, 0, k_oml_step, a);
+  } else {
+    const size_t smem = 4 * MD * MNF * 32 * sizeof(double2);
+    static bool attr = false;
+    if (!attr) {
+      QG_CUDA(cudaFuncSetAttribute(k_oml_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    QG_LAUNCH(m, "k_oml_step", grid, 128, smem, k_oml_march, a);
+  }
   QG_LAUNCH(m, "k_oml_reduce", ORB, 256, 0, k_oml_reduce, a, g.dx * g.dx);
 }
 
