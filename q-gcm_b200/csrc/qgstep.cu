@@ -7,6 +7,8 @@
 // instead of round-tripping through HBM as the reference's del2p/d4p/dqdt arrays do.
 // q(new) is written over qom in place (qom is only read at the centre point), and the
 // host rotates the qo/qom pointers afterwards.
+#include <cstdlib>
+
 #include "qgcm_internal.h"
 
 namespace qg {
@@ -178,6 +180,190 @@ __global__ void __launch_bounds__(128) k_qgstep(QgArgs a) {
   cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------
+// Two-column version of the marching pipeline: each lane owns the even/odd column pair
+// (g0, g0+1), so every prefetch and store moves 16 bytes per lane and one shuffle pair per
+// field row serves two points.  A warp covers 64 columns, 56 outputs + a halo of 4 (the
+// del-6th needs 3; 4 keeps the pairs 16-byte aligned).  Same arithmetic as k_qgstep.
+// ------------------------------------------------------------------------------------------
+constexpr int W2OUT = 56;
+constexpr int Q2_D = 4;     // row stages in flight per warp
+__device__ __forceinline__ void cp_async16(double2 *smem_dst, const double *gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+// 5-point operator with the mixed condition on solid walls (qgosubs.F:86-130, :310-341)
+__device__ __forceinline__ double qg_lap(double c, double w, double e, double s, double n, int j, int nyp, bool wallW, bool wallE,
+                                         double bcf, double dxm2) {
+  if (j == 0) return bcf * (n - c);
+  if (j == nyp - 1) return bcf * (s - c);
+  if (wallW) return bcf * (e - c);
+  if (wallE) return bcf * (w - c);
+  return (s + w + e + n - 4.0 * c) * dxm2;
+}
+// Arakawa 9-point Jacobian J(q,p) at one point; rows A,B,C = j-1, j, j+1 (qgosubs.F:376-388)
+__device__ __forceinline__ double qg_jac(double pA, double pAw, double pAe, double pBw, double pBe, double pC, double pCw,
+                                         double pCe, double qA, double qAw, double qAe, double qBw, double qBe, double qC,
+                                         double qCw, double qCe) {
+  return (qBe - qBw) * (pC - pA) + (qA - qC) * (pBe - pBw) + qBe * (pCe - pAe) - qBw * (pCw - pAw) - qC * (pCe - pCw) +
+         qA * (pAe - pAw) + pC * (qCe - qCw) - pA * (qAe - qAw) - pBe * (qCe - qAe) + pBw * (qCw - qAw);
+}
+
+__global__ void __launch_bounds__(128) k_qgstep2(QgArgs a) {
+  extern __shared__ double2 ring2_all[];
+  const Grid &g = a.g;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int k = blockIdx.z;
+  const int wx = blockIdx.x * 4 + wib;
+  const int nxp = g.nxp, nyp = g.nyp, ld = g.ld, cyc = g.cyclic, per = nxp - 1;
+  if (wx * W2OUT >= nxp) return;   // whole warp exits together
+  double2 *ring = ring2_all + (size_t)wib * (Q2_D * QG_NF * 32) + lane;
+  const int g0 = wx * W2OUT - 4 + 2 * lane;      // first column of the pair (even)
+  int c0 = g0;                                    // canonical column for loads
+  if (cyc) { if (c0 < 0) c0 += per; if (c0 >= per) c0 -= per; }
+  const bool ld0 = c0 >= 0 && c0 < nxp;           // the pair is loaded when its first column exists
+  const bool v0 = ld0, v1 = ld0 && (cyc || c0 + 1 < nxp);   // column validity (second one may be row padding)
+  const bool wallW0 = !cyc && g0 == 0, wallE0 = !cyc && g0 == nxp - 1;
+  const bool wallE1 = !cyc && g0 + 1 == nxp - 1;  // the odd column is never the western wall
+  const bool outl = lane >= 2 && lane < 30;
+  const bool out0 = outl && g0 < nxp, out1 = outl && g0 + 1 < nxp;
+  const int ja = blockIdx.y * RCH, jb = min(nyp, ja + RCH);
+  const size_t lo = (size_t)k * g.lsz;
+  const int cc = ld0 ? c0 : 0;
+  const double *__restrict__ pm = a.pm + lo + cc;
+  const double *__restrict__ p = a.p + lo + cc;
+  const double *__restrict__ q = a.q + lo + cc;
+  double *__restrict__ qm = a.qm + lo + (g0 >= 0 && g0 < nxp ? g0 : 0);
+  const double *__restrict__ wek = a.wek + cc;
+  const double *__restrict__ ent = a.ent + cc;
+  const double dxm2 = g.dxm2, bcf = a.bcfac;
+  const double ah2f = a.ah2fac[k], ah4f = a.ah4fac[k], adf = a.adfac, tdt = g.tdt;
+  const int nl = g.nl;
+  const bool forced = k < 2;
+  const bool ldq = g0 >= 0 && g0 < nxp;
+
+#pragma unroll
+  for (int s = 0; s < Q2_D * QG_NF; ++s) ring[s * 32] = make_double2(0.0, 0.0);
+  __syncwarp();
+  // stage r carries pom(r), p(r-2), q(r-2), qm(r-3), wek(r-3), ent(r-3); rows outside the
+  // domain are clamped (their values only reach results that are never used)
+  auto issue = [&](int r) {
+    double2 *slot = ring + (size_t)((r + 8 * Q2_D) % Q2_D) * (QG_NF * 32);
+    const int r0c = min(max(r, 0), nyp - 1), r2c = min(max(r - 2, 0), nyp - 1), r3c = min(max(r - 3, 0), nyp - 1);
+    if (ld0) {
+      cp_async16(slot, pm + (size_t)r0c * ld);
+      cp_async16(slot + 32, p + (size_t)r2c * ld);
+      cp_async16(slot + 64, q + (size_t)r2c * ld);
+      if (forced) {
+        cp_async16(slot + 128, wek + (size_t)r3c * ld);
+        cp_async16(slot + 160, ent + (size_t)r3c * ld);
+      }
+    }
+    if (ldq) cp_async16(slot + 96, qm + (size_t)r3c * ld);
+    cp_async_commit();
+  };
+
+  // [0] / [1]: the lane's two columns; w0 = west neighbour of column 0 (lane-1's second column),
+  // e1 = east neighbour of column 1 (lane+1's first column)
+  double pm0[2] = {0, 0}, pm1[2] = {0, 0}, pm2[2] = {0, 0}, d2a[2] = {0, 0}, d2b[2] = {0, 0}, d2c[2] = {0, 0};
+  double d4a[2] = {0, 0}, d4b[2] = {0, 0}, d4c[2] = {0, 0};
+  double pA[2] = {0, 0}, pB[2] = {0, 0}, pC[2] = {0, 0}, qA[2] = {0, 0}, qB[2] = {0, 0}, qC[2] = {0, 0};
+  double pAw0 = 0, pAe1 = 0, pBw0 = 0, pBe1 = 0, pCw0 = 0, pCe1 = 0, qAw0 = 0, qAe1 = 0, qBw0 = 0, qBe1 = 0, qCw0 = 0, qCe1 = 0;
+  const int r0 = ja - 3;
+#pragma unroll
+  for (int s = 0; s < Q2_D - 1; ++s) issue(r0 + s);
+  for (int r = r0; r < jb + 3; ++r) {
+    issue(r + Q2_D - 1);
+    cp_async_wait<Q2_D - 1>();
+    const double2 *slot = ring + (size_t)((r + 8 * Q2_D) % Q2_D) * (QG_NF * 32);
+    {
+      const double2 vpm = slot[0], vp = slot[32], vq = slot[64];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        pm0[c] = pm1[c]; pm1[c] = pm2[c];
+        pA[c] = pB[c]; pB[c] = pC[c];
+        qA[c] = qB[c]; qB[c] = qC[c];
+      }
+      pm2[0] = vpm.x; pm2[1] = v1 ? vpm.y : 0.0;
+      pC[0] = vp.x; pC[1] = v1 ? vp.y : 0.0;
+      qC[0] = vq.x; qC[1] = v1 ? vq.y : 0.0;
+      pAw0 = pBw0; pAe1 = pBe1; pBw0 = pCw0; pBe1 = pCe1; pCw0 = shl(pC[1]); pCe1 = shr(pC[0]);
+      qAw0 = qBw0; qAe1 = qBe1; qBw0 = qCw0; qBe1 = qCe1; qCw0 = shl(qC[1]); qCe1 = shr(qC[0]);
+    }
+    // ---- del2 at row r-1
+    {
+      const int j2 = r - 1;
+      const double w0 = shl(pm1[1]), e1 = shr(pm1[0]);
+      const double a0 = qg_lap(pm1[0], w0, pm1[1], pm0[0], pm2[0], j2, nyp, wallW0, wallE0, bcf, dxm2);
+      const double a1 = qg_lap(pm1[1], pm1[0], e1, pm0[1], pm2[1], j2, nyp, false, wallE1, bcf, dxm2);
+      d2a[0] = d2b[0]; d2b[0] = d2c[0]; d2c[0] = a0;
+      d2a[1] = d2b[1]; d2b[1] = d2c[1]; d2c[1] = a1;
+    }
+    // ---- del4 at row r-2
+    {
+      const int j4 = r - 2;
+      const double w0 = shl(d2b[1]), e1 = shr(d2b[0]);
+      const double a0 = qg_lap(d2b[0], w0, d2b[1], d2a[0], d2c[0], j4, nyp, wallW0, wallE0, bcf, dxm2);
+      const double a1 = qg_lap(d2b[1], d2b[0], e1, d2a[1], d2c[1], j4, nyp, false, wallE1, bcf, dxm2);
+      d4a[0] = d4b[0]; d4b[0] = d4c[0]; d4c[0] = a0;
+      d4a[1] = d4b[1]; d4b[1] = d4c[1]; d4c[1] = a1;
+    }
+    // ---- row r-3: del6, Jacobian, forcing, leapfrog
+    const int jo = r - 3;
+    const double d4w0 = shl(d4b[1]), d4e1 = shr(d4b[0]);
+    if (jo < ja || jo >= jb || !out0) continue;
+    const size_t ro = (size_t)jo * ld;
+    const double2 qold = slot[96];
+    double qn[2];
+    if (jo == 0 || jo == nyp - 1) {
+      // zonal boundary rows are not stepped: after the pointer rotation both time
+      // levels hold the current boundary value (qgosubs.F:214-219)
+      qn[0] = qB[0]; qn[1] = qB[1];
+    } else {
+      double2 wk = make_double2(0.0, 0.0), en = make_double2(0.0, 0.0);
+      if (forced) { wk = slot[128]; en = slot[160]; }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const bool wall = c == 0 ? (wallW0 || wallE0) : wallE1;
+        double dqdt;
+        if (wall) {
+          dqdt = 0.0;   // qgosubs.F:371, :397
+        } else {
+          const double d4w = c == 0 ? d4w0 : d4b[0], d4e = c == 0 ? d4b[1] : d4e1;
+          const double d6p = dxm2 * (d4a[c] + d4w + d4e + d4c[c] - 4.0 * d4b[c]);
+          const double jac = c == 0 ? qg_jac(pA[0], pAw0, pA[1], pBw0, pB[1], pC[0], pCw0, pC[1], qA[0], qAw0, qA[1], qBw0, qB[1],
+                                             qC[0], qCw0, qC[1])
+                                    : qg_jac(pA[1], pA[0], pAe1, pB[0], pBe1, pC[1], pC[0], pCe1, qA[1], qA[0], qAe1, qB[0], qBe1,
+                                             qC[1], qC[0], qCe1);
+          if (a.atmos) {
+            dqdt = adf * jac - ah4f * d6p;
+          } else {
+            const double diffus = ah2f * d4b[c] - ah4f * d6p;
+            dqdt = adf * jac + diffus;
+          }
+        }
+        double qdot = dqdt;
+        if (forced) {
+          const double wkc = c == 0 ? wk.x : wk.y, enc = c == 0 ? en.x : en.y;
+          if (a.atmos) {
+            if (k == 0) qdot = dqdt + a.fohfac[0] * (enc - wkc);
+            if (k == 1) qdot = dqdt - a.fohfac[1] * enc;
+          } else {
+            if (k == 0) qdot = dqdt + a.fohfac[0] * (wkc - enc);
+            if (k == 1) qdot = dqdt + a.fohfac[1] * enc;
+          }
+        }
+        if (!a.atmos && k == nl - 1) qdot = qdot - a.bdrfac * d2a[c];   // d2a = del2p(i, jo) after the shifts above
+        qn[c] = (c == 0 ? qold.x : qold.y) + tdt * qdot;
+      }
+    }
+    // qm is updated in place; each element is read (prefetched) and written by exactly one lane
+    if (out1) *reinterpret_cast<double2 *>(qm + ro) = make_double2(qn[0], qn[1]);
+    else qm[ro] = qn[0];
+  }
+  cp_async_wait<0>();
+}
+
 // Boundary-strip sums feeding the momentum constraints of periodic channels:
 // Jacobian strips (qgosubs.F:284-296, :409-423), third/fifth-derivative strips
 // (:429-443; qgasubs.F:303-313) and the bottom-drag strip (qgosubs.F:155-162).
@@ -317,9 +503,23 @@ static void launch(qgcm_model *m, bool atmos) {
     s.pm = a.pm; s.p = a.p; s.q = a.q;
     QG_LAUNCH(m, "k_strips", dim3(g.nl, 2), 256, 0, k_strips, s);
   }
-  const int nwx = (g.nxp + WOUT - 1) / WOUT;
-  dim3 grid((nwx + 3) / 4, (g.nyp + RCH - 1) / RCH, g.nl);
-  QG_LAUNCH(m, "k_qgstep", grid, 128, 4 * QG_D * QG_NF * 32 * sizeof(double), k_qgstep, a);
+  // QGCM_QG_ONECOL=1 selects the one-column-per-lane kernel (kept for comparison)
+  static const bool onecol = getenv("QGCM_QG_ONECOL") != nullptr;
+  if (onecol) {
+    const int nwx = (g.nxp + WOUT - 1) / WOUT;
+    dim3 grid((nwx + 3) / 4, (g.nyp + RCH - 1) / RCH, g.nl);
+    QG_LAUNCH(m, "k_qgstep", grid, 128, 4 * QG_D * QG_NF * 32 * sizeof(double), k_qgstep, a);
+  } else {
+    const int nwx = (g.nxp + W2OUT - 1) / W2OUT;
+    dim3 grid((nwx + 3) / 4, (g.nyp + RCH - 1) / RCH, g.nl);
+    const size_t smem = 4 * Q2_D * QG_NF * 32 * sizeof(double2);
+    static bool attr = false;
+    if (!attr) {
+      QG_CUDA(cudaFuncSetAttribute(k_qgstep2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    QG_LAUNCH(m, "k_qgstep", grid, 128, smem, k_qgstep2, a);
+  }
   QG_CUDA(cudaGetLastError());
   m->swapf(nq, nqm);   // new q lives in the old qom buffer; old q becomes qom
 }
