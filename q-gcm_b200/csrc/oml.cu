@@ -37,6 +37,7 @@ struct OmlArgs {
   double *cv;
   double *part2;          // [3][ORB] slice sums of the block partials
   unsigned int *ticket;   // last-block-done counter of k_oml_reduce
+  int mrows;              // rows marched by one warp of k_oml_march
 };
 
 __device__ __forceinline__ int wrapt(int i, int nxt, int cyc) {
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(256) k_oml_step(OmlArgs a) {
 // the rows ahead are prefetched with cp.async into a per-warp ring.
 // ------------------------------------------------------------------------------------------
 constexpr int MW = 60;      // output columns per warp: 32 lanes x 2 columns minus a halo of 2 columns on either side
-constexpr int MR = 128;     // rows marched by one warp
+constexpr int MR = 128;     // most rows marched by one warp (fewer on small grids / slabs, to fill the GPU)
 constexpr int MD = 4;       // prefetch depth (row stages in flight; 14 KB of shared memory per warp)
 constexpr int MNF = 7;      // fields per stage: sstm, sst, p, taux, tauy, wekt, fnet
 
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(128) k_oml_march(OmlArgs a) {
   const bool t0ok = pairT, t1ok = pairT && (cyc || g0 + 1 < nxt);
   const bool p1ok = cyc ? true : (pairP && g0 + 1 <= nxt);
   const bool out0 = lane >= 1 && lane < 31 && g0 < nxt, out1 = lane >= 1 && lane < 31 && g0 + 1 < nxt;
-  const int ja = blockIdx.y * MR, jb = min(nyt, ja + MR);
+  const int ja = blockIdx.y * a.mrows, jb = min(nyt, ja + a.mrows);
   const int cc = (pairT || pairP) ? c0 : 0;
   double pxfo = 0.0, pcfr = 0.0, pcen = 0.0;
   if (active) {
@@ -616,10 +617,17 @@ static OmlArgs oml_args(qgcm_model *m, dim3 &grid) {
   a.po1 = m->F("po"); a.taux = m->F("tauxo"); a.tauy = m->F("tauyo");
   a.sst = m->F("sst"); a.sstm = m->F("sstm"); a.wekt = m->F("wekto"); a.fnet = m->F("fnetoc");
   a.sstnew = m->sstnew; a.xfo = m->xfo;
+  a.mrows = MR;
   // QGCM_OML_TILES=1 selects the shared-memory tile kernel (kept for comparison)
   static const bool tiles = getenv("QGCM_OML_TILES") != nullptr;
   if (tiles) grid = dim3((g.nxt + OX - 1) / OX, (g.nyt + OY - 1) / OY);
-  else grid = dim3(((g.nxt + MW - 1) / MW + 3) / 4, (g.nyt + MR - 1) / MR);
+  else {
+    // enough marches to fill 148 SMs x 16 warps, but at least 16 rows each (4 fill rows per march)
+    const int xw = (g.nxt + MW - 1) / MW;
+    const int chunks = std::max(1, (148 * 16 + xw - 1) / xw);
+    a.mrows = std::min(MR, std::max(16, (g.nyt + chunks - 1) / chunks));
+    grid = dim3((xw + 3) / 4, (g.nyt + a.mrows - 1) / a.mrows);
+  }
   a.nblocks = grid.x * grid.y;
   a.part = m->d_red;
   a.rowsum = m->d_red + 3 * (size_t)a.nblocks;

@@ -7,6 +7,7 @@
 // instead of round-tripping through HBM as the reference's del2p/d4p/dqdt arrays do.
 // q(new) is written over qom in place (qom is only read at the centre point), and the
 // host rotates the qo/qom pointers afterwards.
+#include <algorithm>
 #include <cstdlib>
 
 #include "qgcm_internal.h"
@@ -28,6 +29,7 @@ struct QgArgs {
   const double *pm, *p, *q;   // lagged p, current p, current q   [nl][nyp][ld]
   double *qm;                 // lagged q in, new q out (in place)
   const double *wek, *ent;    // Ekman velocity and entrainment at p points
+  int mrows;                  // rows marched by one warp of k_qgstep2 (<= RCH)
 };
 
 __device__ __forceinline__ double shl(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }    // value of lane-1 (west)
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(128) k_qgstep2(QgArgs a) {
   const bool wallE1 = !cyc && g0 + 1 == nxp - 1;  // the odd column is never the western wall
   const bool outl = lane >= 2 && lane < 30;
   const bool out0 = outl && g0 < nxp, out1 = outl && g0 + 1 < nxp;
-  const int ja = blockIdx.y * RCH, jb = min(nyp, ja + RCH);
+  const int ja = blockIdx.y * a.mrows, jb = min(nyp, ja + a.mrows);
   const size_t lo = (size_t)k * g.lsz;
   const int cc = ld0 ? c0 : 0;
   const double *__restrict__ pm = a.pm + lo + cc;
@@ -461,6 +463,7 @@ static void fill_common(qgcm_model *m, bool atmos, QgArgs &a, StripArgs &s) {
   const LayerConsts &lc = atmos ? m->la : m->lo;
   const double bcco = atmos ? m->cfg.bccoat : m->cfg.bccooc;
   a.g = g;
+  a.mrows = RCH;
   a.atmos = atmos;
   a.f0 = m->fnot;
   a.adfac = 1.0 / (12.0 * g.dx * g.dx * m->fnot);
@@ -510,8 +513,11 @@ static void launch(qgcm_model *m, bool atmos) {
     dim3 grid((nwx + 3) / 4, (g.nyp + RCH - 1) / RCH, g.nl);
     QG_LAUNCH(m, "k_qgstep", grid, 128, 4 * QG_D * QG_NF * 32 * sizeof(double), k_qgstep, a);
   } else {
+    // enough marches to fill 148 SMs x 16 warps, but at least 24 rows each (6 fill rows per march)
     const int nwx = (g.nxp + W2OUT - 1) / W2OUT;
-    dim3 grid((nwx + 3) / 4, (g.nyp + RCH - 1) / RCH, g.nl);
+    const int chunks = std::max(1, (148 * 16 + nwx * g.nl - 1) / (nwx * g.nl));
+    a.mrows = std::min(RCH, std::max(24, (g.nyp + chunks - 1) / chunks));
+    dim3 grid((nwx + 3) / 4, (g.nyp + a.mrows - 1) / a.mrows, g.nl);
     const size_t smem = 4 * Q2_D * QG_NF * 32 * sizeof(double2);
     static bool attr = false;
     if (!attr) {
