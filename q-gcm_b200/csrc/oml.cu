@@ -482,7 +482,7 @@ constexpr int ORB = 64;
 __global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy) {
   __shared__ double red[6][8];
   __shared__ bool last;
-  const int per = (a.nblocks + ORB - 1) / ORB;
+  const int per = (a.nblocks + (int)gridDim.x - 1) / (int)gridDim.x;
   const int b0 = blockIdx.x * per, b1 = min(a.nblocks, b0 + per);
   double s[3] = {0.0, 0.0, 0.0};
   for (int q = 0; q < 3; ++q)
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy) {
       a.part2[q * ORB + blockIdx.x] = t;
     }
     __threadfence();
-    last = (atomicAdd(a.ticket, 1u) == ORB - 1);
+    last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
   }
   __syncthreads();
   if (!last) return;
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy) {
     *a.ticket = 0u;
     double t[3] = {0.0, 0.0, 0.0};
     for (int q = 0; q < 3; ++q)
-      for (int i = 0; i < ORB; ++i) t[q] += a.part2[q * ORB + i];
+      for (int i = 0; i < (int)gridDim.x; ++i) t[q] += a.part2[q * ORB + i];
     a.cv[0] = t[0];                         // xfosum, read by k_oml_entoc (after the all-reduce on slabs)
     a.cv[1] = t[1];
     a.cv[2] = t[2];
@@ -530,33 +530,52 @@ __global__ void __launch_bounds__(256) k_oml_entoc(OmlArgs a) {
   const int j = blockIdx.x;   // 0-based p row
   const int nxp = g.nxp, nyp = g.nyp, nxt = g.nxt, nyt = g.nyt, ld = g.ld, cyc = g.cyclic;
   const double mean = a.cv[0] * g.norm;   // xfosum*ocnorm
-  double part = 0.0;
-#pragma unroll 4
-  for (int i = threadIdx.x; i < nxp; i += 256) {
-    // T cells around p point (i,j): (i-1,j-1), (i,j-1), (i-1,j), (i,j) in 0-based T indices
-    const int jm = j - 1, jc = j;
-    int im = i - 1, ic = i;
-    double v;
-    const bool rowS = (j == 0), rowN = (j == nyp - 1);
-    const bool colW = (i == 0), colE = (i == nxp - 1);
-    if (cyc) {
-      if (colW || colE) { im = nxt - 1; ic = 0; }
-    }
+  const bool rowS = (j == 0), rowN = (j == nyp - 1);
+  const int jm = j - 1, jc = j;
 #define X(ii, jj) (a.xfo[(size_t)(jj) * ld + (ii)] - mean)
+  // one p point with every edge/corner rule
+  auto point = [&](int i) {
+    // T cells around p point (i,j): (i-1,j-1), (i,j-1), (i-1,j), (i,j) in 0-based T indices
+    int im = i - 1, ic = i;
+    const bool colW = (i == 0), colE = (i == nxp - 1);
+    if (cyc && (colW || colE)) { im = nxt - 1; ic = 0; }
     if (!rowS && !rowN) {
-      if (!cyc && colW) v = 0.5 * (X(0, jm) + X(0, jc));
-      else if (!cyc && colE) v = 0.5 * (X(nxt - 1, jm) + X(nxt - 1, jc));
-      else v = 0.25 * (X(im, jm) + X(ic, jm) + X(im, jc) + X(ic, jc));
-    } else {
-      const int jt = rowS ? 0 : nyt - 1;
-      if (!cyc && colW) v = X(0, jt);
-      else if (!cyc && colE) v = X(nxt - 1, jt);
-      else v = 0.5 * (X(im, jt) + X(ic, jt));
+      if (!cyc && colW) return 0.5 * (X(0, jm) + X(0, jc));
+      if (!cyc && colE) return 0.5 * (X(nxt - 1, jm) + X(nxt - 1, jc));
+      return 0.25 * (X(im, jm) + X(ic, jm) + X(im, jc) + X(ic, jc));
     }
-#undef X
-    a.entoc[(size_t)j * ld + i] = v;
-    part += (colW || colE) ? 0.5 * v : v;
+    const int jt = rowS ? 0 : nyt - 1;
+    if (!cyc && colW) return X(0, jt);
+    if (!cyc && colE) return X(nxt - 1, jt);
+    return 0.5 * (X(im, jt) + X(ic, jt));
+  };
+  double part = 0.0;
+  // two p columns per thread: 16-byte loads of the T rows and a 16-byte store
+#pragma unroll 2
+  for (int i0 = 2 * threadIdx.x; i0 < nxp; i0 += 512) {
+    const int i1 = i0 + 1;
+    double v0, v1 = 0.0;
+    if (!rowS && !rowN && i0 >= 2 && i1 <= nxp - 2) {
+      const double2 am = *reinterpret_cast<const double2 *>(a.xfo + (size_t)jm * ld + i0);
+      const double2 ac = *reinterpret_cast<const double2 *>(a.xfo + (size_t)jc * ld + i0);
+      const double wm = X(i0 - 1, jm), wc = X(i0 - 1, jc);
+      const double m0 = am.x - mean, m1 = am.y - mean, c0 = ac.x - mean, c1 = ac.y - mean;
+      v0 = 0.25 * (wm + m0 + wc + c0);
+      v1 = 0.25 * (m0 + m1 + c0 + c1);
+      *reinterpret_cast<double2 *>(a.entoc + (size_t)j * ld + i0) = make_double2(v0, v1);
+      part += v0 + v1;
+    } else {
+      v0 = point(i0);
+      a.entoc[(size_t)j * ld + i0] = v0;
+      part += (i0 == 0 || i0 == nxp - 1) ? 0.5 * v0 : v0;
+      if (i1 < nxp) {
+        v1 = point(i1);
+        a.entoc[(size_t)j * ld + i1] = v1;
+        part += (i1 == nxp - 1) ? 0.5 * v1 : v1;
+      }
+    }
   }
+#undef X
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
@@ -660,7 +679,8 @@ void oml_phase_a(qgcm_model *m) {
     }
     QG_LAUNCH(m, "k_oml_step", grid, 128, smem, k_oml_march, a);
   }
-  QG_LAUNCH(m, "k_oml_reduce", ORB, 256, 0, k_oml_reduce, a, g.dx * g.dx);
+  // one block per 2048 partials (the marching kernel leaves a few hundred), at most ORB
+  QG_LAUNCH(m, "k_oml_reduce", std::min(ORB, (a.nblocks + 2047) / 2048), 256, 0, k_oml_reduce, a, g.dx * g.dx);
 }
 
 // entoc from xfo minus the global mean, its integral (y-slabs: the rank's share in d_cv[3])
