@@ -295,8 +295,10 @@ __global__ void __launch_bounds__(128) k_xf_stress(XfArgsK a) {
   const bool south = (jc == 0), north = (jc == nyta - 1);
   const int icm1 = (ic == 0) ? nxta - 1 : ic - 1, icp2 = (ic + 2) % nxta;
   const int ix[4] = {icm1, ic, ic + 1, icp2};
-  const double *wu = a.stb + (size_t)(south ? 1 : (north ? 3 : 0)) * (n + 1) * (n + 1) * 16 + (size_t)(ii + (n + 1) * jj) * 16;
-  const double *wv = a.stb + (size_t)(south ? 2 : (north ? 4 : 0)) * (n + 1) * (n + 1) * 16 + (size_t)(ii + (n + 1) * jj) * 16;
+  // weights are stored [variant][k][fine point] so that neighbouring lanes read neighbouring doubles
+  const int npt = (n + 1) * (n + 1);
+  const double *wu = a.stb + (size_t)(south ? 1 : (north ? 3 : 0)) * npt * 16 + (ii + (n + 1) * jj);
+  const double *wv = a.stb + (size_t)(south ? 2 : (north ? 4 : 0)) * npt * 16 + (ii + (n + 1) * jj);
   double usum = 0.0, vsum = 0.0;
 #pragma unroll
   for (int row = 0; row < 4; ++row) {
@@ -314,8 +316,8 @@ __global__ void __launch_bounds__(128) k_xf_stress(XfArgsK a) {
         ud = a.u1[(size_t)(jc + jd) * lda + ix[q]];
         vd = a.v1[(size_t)(jc + jd) * lda + ix[q]];
       }
-      usum = usum + ud * __ldg(wu + 4 * row + q);
-      vsum = vsum + vd * __ldg(wv + 4 * row + q);
+      usum = usum + ud * __ldg(wu + (size_t)(4 * row + q) * npt);
+      vsum = vsum + vd * __ldg(wv + (size_t)(4 * row + q) * npt);
     }
   }
   // velocity difference over the ocean (tau_udiff), src/xfosubs.F:250-300
@@ -660,7 +662,7 @@ void bicubic_variant(int variant, double bcdy, int n, double *out /* [(n+1)^2][1
       for (int k = 0; k < 16; ++k) {
         double s = 0.0;
         for (int q = 0; q < 16; ++q) s = s + bmat[q][k] * st[q];
-        out[(size_t)(ii + (n + 1) * jj) * 16 + k] = s;
+        out[(size_t)k * (n + 1) * (n + 1) + (ii + (n + 1) * jj)] = s;
       }
     }
 }

@@ -112,7 +112,7 @@ struct XfPlan {
   int nxf = 0, nyf = 0, ldf = 0;         // ocean-resolution atmosphere p grid (nxpaor x nypaor) and its pitch
   double *u1 = nullptr, *v1 = nullptr;   // layer-1 geostrophic velocity at atmosphere p points [nypa][ld]
   double *taux = nullptr, *tauy = nullptr;   // stress on the fine grid [nyf][ldf]
-  double *stb = nullptr;                 // bicubic weights [5][(ndxr+1)^2][16]: general, u-south, v-south, u-north, v-north
+  double *stb = nullptr;                 // bicubic weights [5][16][(ndxr+1)^2]: general, u-south, v-south, u-north, v-north
   int *iam = nullptr, *iap = nullptr, *jam = nullptr, *jap = nullptr;   // bilint subscripts (0-based)
   double *wpx = nullptr, *wmx = nullptr, *wpy = nullptr, *wmy = nullptr;
   double *fsp_o = nullptr, *fsp_a = nullptr;   // fsprim at ocean / atmosphere T rows

@@ -261,3 +261,20 @@ def test_coupled_steps_and_drift(qg, pyorc, case):
         e = rel_l2(gpu.get_field(name), cpu.get_field(name))
         assert e <= 1e-8, (case, name, e)
         assert np.isfinite(gpu.get_field(name)).all()
+
+
+@pytest.mark.parametrize("deck", ["dg_coupled", "so_coupled", "dg_oo"])
+def test_full_size_decks_one_coupled_step(qg, pyorc, deck):
+    """the shipped decks at their own resolution (BASELINE.json configs 0-2): double gyre
+    961^2 x 3 ocean (+ 385 x 97 x 3 atmosphere, ndxr = 16), Southern Ocean 4609 x 577 x 3
+    channel ocean + 289 x 109 x 3 atmosphere: start-up sequence, then nt = 1..nstr+1 (two
+    ocean steps, nstr+1 atmosphere steps, both time-level averages)"""
+    p = qg.named_config(deck)
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    n = p.nstr + 1
+    gpu.run(1, n)
+    cpu.run(1, n)
+    names = OCEAN_CHECK if p.has("ocean_only") else OCEAN_CHECK + ATMOS_CHECK + ("tauxo", "tauyo", "fnetoc")
+    compare(gpu, cpu, names, tol=1e-10 if not p.has("ocean_only") else TOL, label=deck)
+    for nm in ("po", "qo", "sst"):
+        assert np.isfinite(gpu.get_field(nm)).all()
