@@ -226,6 +226,25 @@ int qgcm_comm_init_nccl(qgcm_model *m, const void *id128);
  * of an n-rank partition; afterwards a partition call on any member steps every rank */
 int qgcm_group_create(qgcm_model **models, int32_t n);
 
+/* ---- device-side validity scan ---------------------------------
+ *
+ * valids, src/valsubs.F:43-630: extreme-value scan of po, qo, sst, wekto (and pa, qa, ast,
+ * wekta, tauxa, tauya) against the reference's fixed thresholds (:77-81) and the perturbed
+ * layer-thickness check of the ocean (:380-524, thkmin = 100 m, critpc = 20 %), evaluated on
+ * the device so that the every-0.25-day check (src/q-gcm.F:1278) does not download 2 GB.
+ * solnok = 0 means the reference would dump and stop.  The neighbourhood print-outs of
+ * scan2D/scan3D stay on the Fortran side (they run on downloaded fields after a failure).
+ * On a y-slab model the report covers the rows this rank owns; min/max and the hfbad
+ * percentages of the ranks combine by min/max/sum. */
+typedef struct qgcm_valids_report {
+  int32_t solnok, reserved;
+  double patmin, patmax, qatmin, qatmax, astmin, astmax, wtamin, wtamax, txamin, txamax, tyamin, tyamax;
+  double pocmin, pocmax, qocmin, qocmax, sstmin, sstmax, wtomin, wtomax;
+  double hfmint, hfmaxt, hfmini, hfmaxi, hfminb, hfmaxb;   /* full layer thickness: top, intermediate, bottom */
+  double hfbad[QGCM_NLMAX];                                /* % of the area thinner than thkmin, per layer */
+} qgcm_valids_report;
+int qgcm_valids(qgcm_model *m, qgcm_valids_report *rep);
+
 /* ---- instrumentation ---------------------------------------------------------- */
 
 /* number of kernels launched by this model since creation */

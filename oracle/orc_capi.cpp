@@ -89,6 +89,7 @@ int orc_atmos_step(Model *m) {
   ORC_TRY(m->aml(); m->qgastep(); m->atinvq(); m->atqzbd(m->qa.data(), m->pa.data()));
 }
 int orc_run(Model *m, int64_t a, int64_t b) { ORC_TRY(m->run(a, b)); }
+int orc_valids(Model *m, qgcm_valids_report *r) { ORC_TRY(m->valids(r)); }
 
 // transform primitives, for pinning against scipy.fft (tests/test_oracle_fft.py)
 int orc_rfftf(int n, double *r) {

@@ -91,6 +91,8 @@ struct Model {
   // src/q-gcm.F:719-749
   void qcomp_ocean();
   void qcomp_atmos();
+  // src/valsubs.F
+  void valids(qgcm_valids_report *rep);
   void run(int64_t nt_first, int64_t nt_last);
 };
 

@@ -469,6 +469,8 @@ int qgcm_nccl_unique_id(void *id128) { QG_TRY(nccl_unique_id(id128)); }
 int qgcm_comm_init_nccl(qgcm_model *m, const void *id128) { QG_TRY(nccl_init(m, id128)); }
 int qgcm_group_create(qgcm_model **models, int32_t n) { QG_TRY(group_create(models, n)); }
 
+int qgcm_valids(qgcm_model *m, qgcm_valids_report *rep) { QG_TRY(launch_valids(m, rep)); }
+
 int64_t qgcm_launch_count(qgcm_model *m) { return m ? m->launches : 0; }
 
 int qgcm_profile(qgcm_model *m, int enable) {

@@ -163,6 +163,7 @@ struct qgcm_model {
   std::vector<qgcm_model *> peers;       // loopback group (all ranks in this process), empty otherwise
   double *d_cv = nullptr;                // [32] reduction payload
   unsigned int *d_ticket = nullptr;      // last-block-done counters
+  double *d_val = nullptr;               // valids: per-block partials
   bool shared_stream = false;            // loopback ranks > 0 borrow rank 0's stream
   // qgcm_set_field_async: copy stream, shadow buffers, names waiting for qgcm_commit_fields
   cudaStream_t copy_stream = nullptr;
@@ -230,6 +231,7 @@ void launch_aml(qgcm_model *m);
 void launch_atqzbd(qgcm_model *m, double *q, const double *p);
 void launch_tlavg_atmos(qgcm_model *m);
 void launch_xforc(qgcm_model *m);
+void launch_valids(qgcm_model *m, qgcm_valids_report *rep);
 
 // slab.cu: y-slab multi-GPU drivers.  `ms` is the set of ranks this process drives: one model
 // with an NCCL communicator, or every rank of an in-process loopback group.

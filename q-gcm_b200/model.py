@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from .abi import QgcmConfig, QgcmScalars, declared_functions
+from .abi import QgcmConfig, QgcmScalars, QgcmValidsReport, declared_functions
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -131,6 +131,12 @@ class CModel:
     def run(self, nt_first, nt_last):
         self._call("run", C.c_int64(nt_first), C.c_int64(nt_last))
 
+    def valids(self) -> QgcmValidsReport:
+        """valids, src/valsubs.F:43: extreme-value and layer-thickness scan"""
+        r = QgcmValidsReport()
+        self._call("valids", C.byref(r))
+        return r
+
     # -- convenience: whole-state load/store used by tests and bench
     OCEAN_FIELDS = ("po", "pom", "qo", "qom", "sst", "sstm", "wekto", "wekpo", "entoc", "tauxo", "tauyo",
                     "fnetoc", "ddynoc")
@@ -237,6 +243,22 @@ class SlabGroup:
     def xforc(self):
         for m in self.ranks:
             m.xforc()
+
+    def valids(self):
+        """combine the per-slab reports as a multi-process driver would (min / max / sum)"""
+        reps = [m.valids() for m in self.ranks]
+        out = QgcmValidsReport()
+        for name, typ in out._fields_:
+            vals = [getattr(r, name) for r in reps]
+            if name == "hfbad":
+                for k in range(len(out.hfbad)):
+                    out.hfbad[k] = sum(v[k] for v in vals)
+            elif name.endswith("min") or name in ("hfmint", "hfmini", "hfminb"):
+                setattr(out, name, min(vals))
+            elif name.endswith("max") or name in ("hfmaxt", "hfmaxi", "hfmaxb"):
+                setattr(out, name, max(vals))
+        out.solnok = int(all(r.solnok for r in reps) and max(out.hfbad) <= 20.0)
+        return out
 
     def sync(self):
         for m in self.ranks:

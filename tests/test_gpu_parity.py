@@ -278,3 +278,56 @@ def test_full_size_decks_one_coupled_step(qg, pyorc, deck):
     compare(gpu, cpu, names, tol=1e-10 if not p.has("ocean_only") else TOL, label=deck)
     for nm in ("po", "qo", "sst"):
         assert np.isfinite(gpu.get_field(nm)).all()
+
+
+# ------------------------------------------------------------------------------------------
+# device-side valids (src/valsubs.F:43-630)
+# ------------------------------------------------------------------------------------------
+def _same_report(a, b):
+    da, db = a.as_dict(), b.as_dict()
+    assert da["solnok"] == db["solnok"]
+    for k, v in db.items():
+        if k in ("solnok", "reserved"):
+            continue
+        if k == "hfbad":
+            assert np.allclose(da[k], v, rtol=1e-12, atol=1e-12), (k, da[k], v)
+        else:
+            assert abs(da[k] - v) <= 1e-11 * max(abs(v), 1e-300), (k, da[k], v)
+
+
+@pytest.mark.parametrize("deck", ["cpl_dg", "box_dg"])
+def test_valids_report(qg, pyorc, deck):
+    p = coupled_configs(qg)[deck] if deck.startswith("cpl") else small_configs(qg)[deck]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    gpu.run(1, 2 * p.nstr)
+    cpu.run(1, 2 * p.nstr)
+    rg, rc = gpu.valids(), cpu.valids()
+    assert rc.solnok == 1
+    _same_report(rg, rc)
+    # thin the top layer over a fifth of the basin: the percentage criterion fails (critpc = 20 %)
+    po = cpu.get_field("po", (p.nxpo, p.nypo, p.nlo)).copy()
+    po[: p.nxpo // 4, :, 1] += 400.0 * cfg.gpoc[0]
+    for m in (gpu, cpu):
+        m.set_field("po", po)
+    rg, rc = gpu.valids(), cpu.valids()
+    assert rc.solnok == 0 and rc.hfbad[0] > 20.0
+    _same_report(rg, rc)
+    # an out-of-range sst alone also stops the run (sstext = 75 K)
+    sst = cpu.get_field("sst", (p.nxto, p.nyto)).copy()
+    sst[3, 5] = 80.0
+    for m in (gpu, cpu):
+        m.set_field("po", cpu.get_field("pom", (p.nxpo, p.nypo, p.nlo)))
+        m.set_field("sst", sst)
+    rg, rc = gpu.valids(), cpu.valids()
+    assert rc.solnok == 0 and rc.sstmax == 80.0
+    _same_report(rg, rc)
+
+
+def test_valids_over_slabs(qg, pyorc):
+    p = small_configs(qg)["box_dg"]
+    cfg = qg.build_config(p)
+    grp, cpu = qg.SlabGroup(cfg, 3), pyorc.Oracle(cfg)
+    for m in (grp, cpu):
+        qg.synth.init_model(m, p, cfg, "random")
+        m.run(1, 2 * p.nstr)
+    _same_report(grp.valids(), cpu.valids())
