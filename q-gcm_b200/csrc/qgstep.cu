@@ -1,10 +1,10 @@
 // Leapfrog vorticity step, shared by ocean (qgostep + ocadif, src/qgosubs.F:45-446) and
 // atmosphere (qgastep + atadif, src/qgasubs.F:45-317).
 //
-// One fused kernel per layer-tile: del2(pom) -> del4 -> del6, the Arakawa 9-point
-// Jacobian J(q,p), forcing, bottom drag and the leapfrog update, with the three
-// intermediate Laplacians staged in shared memory (halo 3 of pom, halo 1 of po/qo)
-// instead of round-tripping through HBM as the reference's del2p/d4p/dqdt arrays do.
+// One fused kernel: del2(pom) -> del4 -> del6, the Arakawa 9-point Jacobian J(q,p),
+// forcing, bottom drag and the leapfrog update, with the three intermediate Laplacians
+// kept in registers (halo 3 of pom, halo 1 of po/qo) instead of round-tripping through
+// HBM as the reference's del2p/d4p/dqdt arrays do.
 // q(new) is written over qom in place (qom is only read at the centre point), and the
 // host rotates the qo/qom pointers afterwards.
 #include <algorithm>
@@ -14,8 +14,7 @@
 
 namespace qg {
 
-constexpr int WOUT = 26;    // output columns per warp (32 lanes minus a halo of 3 each side)
-constexpr int RCH = 128;    // rows marched by one warp (6 pipeline fill rows per march)
+constexpr int RCH = 128;    // most rows marched by one warp (6 pipeline fill rows per march)
 
 struct QgArgs {
   Grid g;
@@ -35,158 +34,21 @@ struct QgArgs {
 __device__ __forceinline__ double shl(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }    // value of lane-1 (west)
 __device__ __forceinline__ double shr(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }  // value of lane+1 (east)
 
-constexpr int QG_D = 6;     // cp.async pipeline depth (row stages in flight per warp)
 constexpr int QG_NF = 6;    // fields per stage: pom, p, q, qm, wek, ent
 
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// Warp-marching stencil pipeline.  Each warp owns 32 consecutive columns (26 outputs +
-// halo 3) and marches north through RCH rows.  Every lane keeps its own column's last
-// three rows of pom, del2, del4, p and q in registers; east/west neighbours come from
-// warp shuffles (no block barriers), and the rows ahead are prefetched QG_D deep with
-// cp.async into a per-warp shared-memory ring in which each lane only ever touches its
-// own slots.  Every global access is a contiguous 256-byte row segment.
-__global__ void __launch_bounds__(128) k_qgstep(QgArgs a) {
-  extern __shared__ double ring_all[];
-  const Grid &g = a.g;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int k = blockIdx.z;
-  const int wx = blockIdx.x * 4 + wib;
-  const int nxp = g.nxp, nyp = g.nyp, ld = g.ld, cyc = g.cyclic, per = nxp - 1;
-  if (wx * WOUT >= nxp) return;   // whole warp exits together
-  double *ring = ring_all + (size_t)wib * (QG_D * QG_NF * 32) + lane;   // [stage][field] at stride 32
-  const int gi = wx * WOUT - 3 + lane;          // this lane's column (may be outside the domain)
-  int ci = gi;                                   // canonical column for loads
-  if (cyc) { if (ci < 0) ci += per; if (ci >= per) ci -= per; }
-  const bool incol = ci >= 0 && ci < nxp;
-  const bool wallW = !cyc && gi == 0, wallE = !cyc && gi == nxp - 1;
-  const bool outlane = lane >= 3 && lane < 3 + WOUT && gi < nxp;
-  const int ja = blockIdx.y * RCH, jb = min(nyp, ja + RCH);
-  const size_t lo = (size_t)k * g.lsz;
-  const int cc = incol ? ci : 0;
-  const double *__restrict__ pm = a.pm + lo + cc;
-  const double *__restrict__ p = a.p + lo + cc;
-  const double *__restrict__ q = a.q + lo + cc;
-  double *__restrict__ qm = a.qm + lo + (gi >= 0 && gi < nxp ? gi : 0);
-  const double *__restrict__ wek = a.wek + cc;
-  const double *__restrict__ ent = a.ent + cc;
-  const double dxm2 = g.dxm2, bcf = a.bcfac;
-  const double ah2f = a.ah2fac[k], ah4f = a.ah4fac[k], adf = a.adfac, tdt = g.tdt;
-  const int nl = g.nl;
-  const bool forced = k < 2;
-
-  // stage r carries pom(r), p(r-2), q(r-2), qm(r-3), wek(r-3), ent(r-3); rows outside the
-  // domain are clamped (their values only reach results that are never used)
-  auto issue = [&](int r) {
-    double *slot = ring + (size_t)((r + 8 * QG_D) % QG_D) * (QG_NF * 32);
-    const int r0c = min(max(r, 0), nyp - 1), r2c = min(max(r - 2, 0), nyp - 1), r3c = min(max(r - 3, 0), nyp - 1);
-    cp_async8(slot, pm + (size_t)r0c * ld);
-    cp_async8(slot + 32, p + (size_t)r2c * ld);
-    cp_async8(slot + 64, q + (size_t)r2c * ld);
-    cp_async8(slot + 96, qm + (size_t)r3c * ld);
-    if (forced) {
-      cp_async8(slot + 128, wek + (size_t)r3c * ld);
-      cp_async8(slot + 160, ent + (size_t)r3c * ld);
-    }
-    cp_async_commit();
-  };
-
-  double pm0 = 0, pm1 = 0, pm2 = 0, d2a = 0, d2b = 0, d2c = 0, d4a = 0, d4b = 0, d4c = 0;
-  double pA = 0, pB = 0, pC = 0, qA = 0, qB = 0, qC = 0;
-  double pAw = 0, pAe = 0, pBw = 0, pBe = 0, pCw = 0, pCe = 0, qAw = 0, qAe = 0, qBw = 0, qBe = 0, qCw = 0, qCe = 0;
-  const int r0 = ja - 3;
-#pragma unroll
-  for (int s = 0; s < QG_D - 1; ++s) issue(r0 + s);
-#pragma unroll 3
-  for (int r = r0; r < jb + 3; ++r) {
-    issue(r + QG_D - 1);
-    cp_async_wait<QG_D - 1>();
-    const double *slot = ring + (size_t)((r + 8 * QG_D) % QG_D) * (QG_NF * 32);
-    pm0 = pm1; pm1 = pm2; pm2 = slot[0];
-    pA = pB; pB = pC; pC = slot[32];
-    qA = qB; qB = qC; qC = slot[64];
-    pAw = pBw; pAe = pBe; pBw = pCw; pBe = pCe; pCw = shl(pC); pCe = shr(pC);
-    qAw = qBw; qAe = qBe; qBw = qCw; qBe = qCe; qCw = shl(qC); qCe = shr(qC);
-    // ---- del2 at row r-1 (qgosubs.F:86-130 / qgasubs.F:74-100)
-    const int j2 = r - 1;
-    {
-      const double w = shl(pm1), e = shr(pm1);
-      double v;
-      if (j2 == 0) v = bcf * (pm2 - pm1);
-      else if (j2 == nyp - 1) v = bcf * (pm0 - pm1);
-      else if (wallW) v = bcf * (e - pm1);
-      else if (wallE) v = bcf * (w - pm1);
-      else v = (pm0 + w + e + pm2 - 4.0 * pm1) * dxm2;
-      d2a = d2b; d2b = d2c; d2c = v;
-    }
-    // ---- del4 at row r-2 (qgosubs.F:310-341 / qgasubs.F:218-237)
-    const int j4 = r - 2;
-    {
-      const double w = shl(d2b), e = shr(d2b);
-      double v;
-      if (j4 == 0) v = bcf * (d2c - d2b);
-      else if (j4 == nyp - 1) v = bcf * (d2a - d2b);
-      else if (wallW) v = bcf * (e - d2b);
-      else if (wallE) v = bcf * (w - d2b);
-      else v = dxm2 * (d2a + w + e + d2c - 4.0 * d2b);
-      d4a = d4b; d4b = d4c; d4c = v;
-    }
-    // ---- row r-3: del6, Jacobian, forcing, leapfrog
-    const int jo = r - 3;
-    const double d4w = shl(d4b), d4e = shr(d4b);
-    if (jo < ja || jo >= jb || !outlane) continue;
-    const size_t ro = (size_t)jo * ld;
-    if (jo == 0 || jo == nyp - 1) {
-      // zonal boundary rows are not stepped: after the pointer rotation both time
-      // levels hold the current boundary value (qgosubs.F:214-219)
-      qm[ro] = qB;
-      continue;
-    }
-    double dqdt;
-    if (wallW || wallE) {
-      dqdt = 0.0;   // qgosubs.F:371, :397
-    } else {
-      const double d6p = dxm2 * (d4a + d4w + d4e + d4c - 4.0 * d4b);
-      // rows A,B,C = j-1, j, j+1; suffix w/e = i-1, i+1 (qgosubs.F:376-388)
-      const double jac = (qBe - qBw) * (pC - pA) + (qA - qC) * (pBe - pBw) + qBe * (pCe - pAe) - qBw * (pCw - pAw) -
-                         qC * (pCe - pCw) + qA * (pAe - pAw) + pC * (qCe - qCw) - pA * (qAe - qAw) -
-                         pBe * (qCe - qAe) + pBw * (qCw - qAw);
-      if (a.atmos) {
-        dqdt = adf * jac - ah4f * d6p;
-      } else {
-        const double diffus = ah2f * d4b - ah4f * d6p;
-        dqdt = adf * jac + diffus;
-      }
-    }
-    double qdot = dqdt;
-    if (forced) {
-      const double wk = slot[128], en = slot[160];
-      if (a.atmos) {
-        if (k == 0) qdot = dqdt + a.fohfac[0] * (en - wk);
-        if (k == 1) qdot = dqdt - a.fohfac[1] * en;
-      } else {
-        if (k == 0) qdot = dqdt + a.fohfac[0] * (wk - en);
-        if (k == 1) qdot = dqdt + a.fohfac[1] * en;
-      }
-    }
-    if (!a.atmos && k == nl - 1) qdot = qdot - a.bdrfac * d2a;   // d2a = del2p(i, jo) after the shifts above
-    // qm is updated in place; each element is read (prefetched) and written by exactly one lane
-    qm[ro] = slot[96] + tdt * qdot;
-  }
-  cp_async_wait<0>();
-}
-
 // ------------------------------------------------------------------------------------------
-// Two-column version of the marching pipeline: each lane owns the even/odd column pair
-// (g0, g0+1), so every prefetch and store moves 16 bytes per lane and one shuffle pair per
-// field row serves two points.  A warp covers 64 columns, 56 outputs + a halo of 4 (the
-// del-6th needs 3; 4 keeps the pairs 16-byte aligned).  Same arithmetic as k_qgstep.
+// Warp-marching stencil pipeline.  A warp covers 64 consecutive columns -- each lane owns the
+// even/odd pair (g0, g0+1), 56 outputs + a halo of 4 (the del-6th needs 3; 4 keeps the pairs
+// 16-byte aligned) -- and marches north.  Every lane keeps the last three rows of pom, del2,
+// del4, p and q of its two columns in registers; east/west neighbours come from one warp
+// shuffle pair per field row (no block barriers), and the rows ahead are prefetched Q2_D deep
+// with 16-byte cp.async into a per-warp shared-memory ring in which each lane only ever
+// touches its own slots.  (The first version kept one column per lane: 60 % of the HBM peak,
+// issue bound; this one 69 %.)
 // ------------------------------------------------------------------------------------------
 constexpr int W2OUT = 56;
 constexpr int Q2_D = 4;     // row stages in flight per warp
@@ -506,13 +368,7 @@ static void launch(qgcm_model *m, bool atmos) {
     s.pm = a.pm; s.p = a.p; s.q = a.q;
     QG_LAUNCH(m, "k_strips", dim3(g.nl, 2), 256, 0, k_strips, s);
   }
-  // QGCM_QG_ONECOL=1 selects the one-column-per-lane kernel (kept for comparison)
-  static const bool onecol = getenv("QGCM_QG_ONECOL") != nullptr;
-  if (onecol) {
-    const int nwx = (g.nxp + WOUT - 1) / WOUT;
-    dim3 grid((nwx + 3) / 4, (g.nyp + RCH - 1) / RCH, g.nl);
-    QG_LAUNCH(m, "k_qgstep", grid, 128, 4 * QG_D * QG_NF * 32 * sizeof(double), k_qgstep, a);
-  } else {
+  {
     // enough marches to fill 148 SMs x 16 warps, but at least 24 rows each (6 fill rows per march)
     const int nwx = (g.nxp + W2OUT - 1) / W2OUT;
     const int chunks = std::max(1, (148 * 16 + nwx * g.nl - 1) / (nwx * g.nl));
