@@ -113,6 +113,60 @@ def build_case(qg, workload, device):
     return p, cfg
 
 
+def slab_model(qg, cfg, world, rank, dist, torch, transport):
+    """one rank of the y-slab partition with its communicator(s): NCCL always (rank 0 makes the
+    id, torch.distributed carries it), the peer-memory mailboxes when asked for"""
+    ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        ident.copy_(torch.frombuffer(bytearray(qg.Model.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(ident, 0)
+    m = qg.Model(qg.slab_config(cfg, world, rank))
+    m.comm_init_nccl(bytes(ident.cpu().numpy().tobytes()))
+    if transport == "peer":
+        mine = torch.frombuffer(bytearray(m.peer_handle()), dtype=torch.uint8).cuda()
+        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allh, mine)
+        m.comm_init_peer([bytes(h.cpu().numpy().tobytes()) for h in allh])
+    dist.barrier()      # the mailbox waits give up after ~10 s: enter the first exchange together
+    return m
+
+
+def peer_self_check(qg, local, world, rank, dist, torch):
+    """the same three steps of a small box deck over NCCL and over the peer mailboxes must agree
+    on every rank (the sums differ only in their order); returns None or the reason to fall back"""
+    import numpy as np
+    p = qg.named_config("natl1km").scaled(24, 12, ndxr=40, name="peer_check")     # 960 x 480
+    if p.nypo < 16 * world:
+        return "check deck too small"
+    cfg = qg.build_config(p, device=local)
+    reason = None
+    out = {}
+    try:
+        for kind in ("nccl", "peer"):
+            m = slab_model(qg, cfg, world, rank, dist, torch, kind)
+            qg.synth.init_model(m, p, cfg, "random")
+            dist.barrier()
+            for _ in range(3):
+                m.ocean_step()
+            m.sync()
+            j0, n = qg.slab_bounds(p.nypo, world, rank)
+            out[kind] = {k: m.get_field(k).reshape((p.nxpo, p.nypo, p.nlo), order="F")[:, j0:j0 + n, :].copy() for k in ("po", "qo")}
+            dist.barrier()      # no rank unmaps a mailbox another rank may still be writing to
+            m.close()
+        for k in ("po", "qo"):
+            a, b = out["peer"][k], out["nccl"][k]
+            e = float(np.linalg.norm(a - b) / np.linalg.norm(b))
+            if not e <= 1e-12:
+                reason = "peer and NCCL transports differ on %s: %.2e" % (k, e)
+    except Exception as ex:       # noqa: BLE001 - any failure means "use NCCL"
+        reason = "peer transport unavailable: %s" % str(ex)[:200]
+    flag = torch.tensor([0 if reason is None else 1], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if int(flag.item()) and reason is None:
+        reason = "peer transport failed its self-check on another rank"
+    return reason
+
+
 def cpu_sample(qg, p, cfg, budget_s=20.0, max_steps=4):
     """time the CPU port on the same workload: as many ocean steps as fit the budget"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -197,6 +251,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--transport", default=os.environ.get("QGCM_SLAB_TRANSPORT", "peer"), choices=["peer", "nccl"],
+                    help="y-slab exchanges at N > 1: peer-memory mailboxes (default) or NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -223,20 +279,25 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     p, cfg = build_case(qg, args.workload, local)
+    transport, transport_note = None, None
     if world > 1:
         # strong scaling: ONE domain cut into y-slabs, one per GPU; the ranks exchange halo
-        # rows, the 2-row-per-mode slab coupling of the Helmholtz solve and a few scalars over
-        # NCCL (q-gcm_b200/csrc/slab.cu).  Rank 0 makes the NCCL id, torch.distributed carries it.
-        ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            ident.copy_(torch.frombuffer(bytearray(qg.Model.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(ident, 0)
-        m = qg.Model(qg.slab_config(cfg, world, rank))
-        m.comm_init_nccl(bytes(ident.cpu().numpy().tobytes()))
+        # rows, the 2-row-per-mode slab coupling of the Helmholtz solve and a few scalars
+        # (q-gcm_b200/csrc/slab.cu) -- through peer-memory mailboxes written by the kernels of
+        # the step over NVLink, or through NCCL (--transport nccl, and the fallback when the
+        # peer transport fails its self-check against NCCL on a small deck)
+        transport = args.transport
+        if transport == "peer":
+            transport_note = peer_self_check(qg, local, world, rank, dist, torch)
+            if transport_note is not None:
+                transport = "nccl"
+        m = slab_model(qg, cfg, world, rank, dist, torch, transport)
     else:
         m = qg.Model(cfg)
     qg.synth.init_model(m, p, cfg, "random")
     m.sync()
+    if world > 1:
+        dist.barrier()
     stream = torch.cuda.ExternalStream(m.stream(), device=local)
     nstr = p.nstr
     cad = 25   # time-level average every 25 ocean steps (src/q-gcm.F:1328)
@@ -408,8 +469,11 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s %s %dx%dx%d, %s, dto=%gs" % (p.name, "coupled" if coupled else "ocean-only", p.nxpo, p.nypo,
                                                                       p.nlo, "channel" if p.has("cyclic_ocean") else "box", p.dto),
-                       "parallelism": ("%d y-slabs of one domain, NCCL halos + slab-coupled solve" % world) if world > 1
+                       "parallelism": ("%d y-slabs of one domain, %s, slab-coupled solve (2 rows per mode exchanged)" %
+                                       (world, "exchanges by the step's own kernels through NVLink peer-memory mailboxes"
+                                        if transport == "peer" else "NCCL halos and reductions")) if world > 1
                        else "single GPU",
+                       "transport": transport, "transport_note": transport_note,
                        "l2": "state (%.1f GB) is far larger than L2; no flush needed" %
                              (4 * p.nlo * fieldpass / 1e9),
                        "state_finite": finite},
@@ -425,6 +489,9 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        m.sync()
+        dist.barrier()          # no rank unmaps a mailbox another rank may still be writing to
+        m.close()
         dist.destroy_process_group()
 
 

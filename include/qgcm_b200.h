@@ -222,6 +222,19 @@ int qgcm_slab_bounds(int32_t nyp_global, int32_t nranks, int32_t rank, int32_t *
  * (MPI_Bcast in the Fortran driver, torch.distributed in bench.py), every rank joins */
 int qgcm_nccl_unique_id(void *id128);
 int qgcm_comm_init_nccl(qgcm_model *m, const void *id128);
+/* Peer-memory transport (one process per GPU, all on one NVLink/NVSwitch node, <= 8 ranks):
+ * every rank exports the 64-byte CUDA IPC handle of its mailbox, the host program gathers the
+ * handles in rank order (MPI_Allgather / torch.distributed), every rank maps them.  Afterwards
+ * the exchanges of qgcm_ocean_step are stores into the peers' mailboxes plus epoch flags,
+ * issued by the kernels of the step themselves (no collective call on the step stream); the
+ * initialisation procedures use the same mailboxes, so NCCL is optional.  All ranks must call
+ * the partition procedures in the same order and enter each within ~10 s of the others: a
+ * rank that waits longer gives up, and the next synchronising call reports the error.
+ * qgcm_comm_transport switches a model that has both between NCCL (0) and peer memory (1);
+ * every rank must switch at the same point of the call sequence. */
+int qgcm_peer_handle(qgcm_model *m, void *handle64);
+int qgcm_comm_init_peer(qgcm_model *m, const void *handles, int32_t n);
+int qgcm_comm_transport(qgcm_model *m, int32_t kind);
 /* all ranks in one process on one device (tests on a single GPU): models[r] must be rank r
  * of an n-rank partition; afterwards a partition call on any member steps every rank */
 int qgcm_group_create(qgcm_model **models, int32_t n);

@@ -343,6 +343,7 @@ int qgcm_destroy(qgcm_model *m) {
   if (!m) return 0;
   cudaSetDevice(m->cfg.device);
   cudaStreamSynchronize(m->stream);
+  peer_close(m);
   for (void *p : m->allocs) cudaFree(p);
   if (m->nccl) { try { nccl_destroy(m); } catch (...) {} }
   if (m->copy_stream) { cudaStreamSynchronize(m->copy_stream); cudaStreamDestroy(m->copy_stream); cudaEventDestroy(m->ev_copy); cudaEventDestroy(m->ev_step); }
@@ -370,7 +371,16 @@ int qgcm_get_scalars(qgcm_model *m, qgcm_scalars *s) {
   QG_TRY(QG_CUDA(cudaMemcpyAsync(s, m->d_scal, sizeof(*s), cudaMemcpyDeviceToHost, m->stream));
          QG_CUDA(cudaStreamSynchronize(m->stream)));
 }
-int qgcm_sync(qgcm_model *m) { QG_TRY(QG_CUDA(cudaStreamSynchronize(m->stream))); }
+int qgcm_sync(qgcm_model *m) {
+  QG_TRY({
+    QG_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->d_peer_err && m->peer.n) {      // a peer-memory exchange gave up waiting for another rank
+      int e = 0;
+      QG_CUDA(cudaMemcpy(&e, m->d_peer_err, sizeof(int), cudaMemcpyDeviceToHost));
+      if (e) throw std::runtime_error("y-slab exchange timed out waiting for a peer rank");
+    }
+  });
+}
 
 int qgcm_constr(qgcm_model *m) { QG_TRY(launch_constr(m)); }
 int qgcm_homsol(qgcm_model *m) { QG_TRY(launch_homsol(m)); }
@@ -468,6 +478,9 @@ int qgcm_slab_bounds(int32_t nyp_global, int32_t nranks, int32_t rank, int32_t *
 int qgcm_nccl_unique_id(void *id128) { QG_TRY(nccl_unique_id(id128)); }
 int qgcm_comm_init_nccl(qgcm_model *m, const void *id128) { QG_TRY(nccl_init(m, id128)); }
 int qgcm_group_create(qgcm_model **models, int32_t n) { QG_TRY(group_create(models, n)); }
+int qgcm_peer_handle(qgcm_model *m, void *handle64) { QG_TRY(peer_export(m, handle64)); }
+int qgcm_comm_init_peer(qgcm_model *m, const void *handles, int32_t n) { QG_TRY(peer_init(m, handles, n)); }
+int qgcm_comm_transport(qgcm_model *m, int32_t kind) { QG_TRY(set_transport(m, kind)); }
 
 int qgcm_valids(qgcm_model *m, qgcm_valids_report *rep) { QG_TRY(launch_valids(m, rep)); }
 

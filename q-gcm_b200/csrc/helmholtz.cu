@@ -891,6 +891,8 @@ struct SlabArgs {
   double *send;              // [nmodes][2][ld]
   const double *all;         // [nranks][nmodes][2][ld]
   double *outer;             // [nmodes][2][ld]
+  PeerCtx peer;              // peer-memory transport: `all` is this rank's mailbox, filled by the peers' k_slab_push
+  int *peer_err;
 };
 
 // alpha_s = -a (T^-1)_{00}, eps_s = -a (T^-1)_{n-1,0}: one forward elimination per slab length
@@ -934,6 +936,13 @@ __global__ void k_slab_fg(SlabArgs t) {
 // which is an interleaved tridiagonal system: one forward sweep expressing
 // Y_{i-1} = P_i + Q_i X_{i+1}, X_i = xc_i + xq_i X_{i+1}, one back substitution.
 __global__ void k_slab_solve(SlabArgs t) {
+  if (t.peer.n) {      // the rows of every rank must have landed in the mailbox
+    if ((int)threadIdx.x < t.peer.n)
+      peer_wait(reinterpret_cast<const volatile unsigned long long *>(t.peer.box[t.peer.rank] + peer_off_flagf(t.peer.n)) + threadIdx.x,
+                t.peer.epoch, t.peer_err);
+    __syncthreads();
+    __threadfence_system();
+  }
   const int s = blockIdx.x * blockDim.x + threadIdx.x, mode = blockIdx.y;
   if (s >= t.nk) return;
   const int col = t.koff + s, N = t.nranks, ld = t.ld;
@@ -944,8 +953,8 @@ __global__ void k_slab_solve(SlabArgs t) {
     if (i < N) {
       const double a_lo = t.ae[(((size_t)mode * N + i - 1) * 2 + 0) * ld + col], e_lo = t.ae[(((size_t)mode * N + i - 1) * 2 + 1) * ld + col];
       const double a_hi = t.ae[(((size_t)mode * N + i) * 2 + 0) * ld + col], e_hi = t.ae[(((size_t)mode * N + i) * 2 + 1) * ld + col];
-      const double G = t.all[(((size_t)(i - 1) * t.nmodes + mode) * 2 + 1) * ld + col];
-      const double F = t.all[(((size_t)i * t.nmodes + mode) * 2 + 0) * ld + col];
+      const double G = __ldcg(t.all + (((size_t)(i - 1) * t.nmodes + mode) * 2 + 1) * ld + col);
+      const double F = __ldcg(t.all + (((size_t)i * t.nmodes + mode) * 2 + 0) * ld + col);
       const double gp = G + e_lo * Pp, A = a_lo + e_lo * Qp;
       const double den = 1.0 / (1.0 - a_hi * A);
       xc[i] = (F + a_hi * gp) * den;
@@ -1271,6 +1280,8 @@ static SlabArgs slab_args(HelmPlan &hp, int nmodes) {
   for (int r = 0; r < 16; ++r) t.nrows_of[r] = hp.slab_rows[r];
   t.bcoef = hp.bcoef; t.vl = hp.vl; t.vll = hp.vll; t.fg = hp.fg; t.yx = hp.yx;
   t.ae = hp.slab_ae; t.send = hp.slab_send; t.all = hp.slab_fg; t.outer = hp.slab_yx;
+  t.peer = hp.slab_peer; t.peer_err = hp.slab_err;
+  if (t.peer.n) t.all = t.peer.box[t.peer.rank] + peer_off_fg(t.peer.n, t.peer.fglen, (int)(t.peer.epoch & 1ull), 0);
   return t;
 }
 

@@ -127,13 +127,16 @@ struct ScalArgs {
 };
 
 // y-slabs: this rank's share of the xintp integrals of the modal solutions -> cv[4+m]
-__global__ void __launch_bounds__(256) k_inv_partials(const double *rowsum, int nl, int nyp, int lo, int hi, double dx, double *cv) {
+// (with the peer-memory transport it also sums cv[3 .. 4+nl) over the ranks)
+__global__ void __launch_bounds__(256) k_inv_partials(const double *rowsum, int nl, int nyp, int lo, int hi, double dx, double *cv,
+                                                      PeerCtx peer, int *peer_err) {
   __shared__ double red[8];
   for (int m = 0; m < nl; ++m) {
     const double s = block256_range_sum(rowsum + (size_t)m * nyp, lo, hi, red);   // wall rows are exactly zero
     if (threadIdx.x == 0) cv[4 + m] = s * dx * dx;
     __syncthreads();
   }
+  if (peer.n) peer_allreduce_block(peer, cv + 3, 1 + nl, cv + 3, peer_err);
 }
 
 // Single-thread constraint algebra on device-resident scalars, so the step never
@@ -323,7 +326,8 @@ void ocinvq_phase_b(qgcm_model *m) {
   const Grid &g = m->go;
   HelmPlan &hp = m->hpo;
   helm_solve_b(m, hp, m->wrk_o, g.nl);
-  QG_LAUNCH(m, "k_inv_partials", 1, 256, 0, k_inv_partials, hp.rowsum, g.nl, g.nyp, hp.row0, hp.row0 + hp.nrows, g.dx, m->d_cv);
+  QG_LAUNCH(m, "k_inv_partials", 1, 256, 0, k_inv_partials, hp.rowsum, g.nl, g.nyp, hp.row0, hp.row0 + hp.nrows, g.dx, m->d_cv,
+            peer_next_vec(m), m->d_peer_err);
 }
 void ocinvq_phase_c(qgcm_model *m) {
   InvArgs a;

@@ -37,6 +37,8 @@ struct OmlArgs {
   double *part2;          // [3][ORB] slice sums of the block partials
   unsigned int *ticket;   // last-block-done counter of k_oml_reduce
   int mrows;              // rows marched by one warp of k_oml_march
+  PeerCtx peer;           // y-slabs over peer memory: k_oml_reduce all-reduces its three sums itself
+  int *peer_err;
 };
 
 __device__ __forceinline__ int wrapt(int i, int nxt, int cyc) {
@@ -365,6 +367,10 @@ __global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy) {
       a.sc->centoc = t[2] * dxdy;           // omlsubs.F:212
     }
   }
+  if (a.peer.n) {       // the slab ranks' sums meet here, over NVLink peer memory
+    __syncthreads();
+    peer_allreduce_block(a.peer, a.cv, 3, a.cv, a.peer_err);
+  }
   if (a.sb || a.nb) oml_monitors(a, red);
 }
 
@@ -483,6 +489,8 @@ static OmlArgs oml_args(qgcm_model *m, dim3 &grid) {
   a.sst = m->F("sst"); a.sstm = m->F("sstm"); a.wekt = m->F("wekto"); a.fnet = m->F("fnetoc");
   a.sstnew = m->sstnew; a.xfo = m->xfo;
   a.mrows = MR;
+  a.peer = PeerCtx{};
+  a.peer_err = m->d_peer_err;
   {
     // enough marches to fill 148 SMs x 16 warps, but at least 16 rows each (4 fill rows per march)
     const int xw = (g.nxt + MW - 1) / MW;
@@ -520,6 +528,7 @@ void oml_phase_a(qgcm_model *m) {
     }
     QG_LAUNCH(m, "k_oml_step", grid, 128, smem, k_oml_march, a);
   }
+  a.peer = peer_next_vec(m);    // y-slabs over peer memory: the reduction all-reduces its sums itself
   // one block per 2048 partials (the marching kernel leaves a few hundred), at most ORB
   QG_LAUNCH(m, "k_oml_reduce", std::min(ORB, (a.nblocks + 2047) / 2048), 256, 0, k_oml_reduce, a, g.dx * g.dx);
 }

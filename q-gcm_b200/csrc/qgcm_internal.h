@@ -61,6 +61,36 @@ struct LayerConsts {
   double ctl2m[NLMAX * NLMAX], ctm2l[NLMAX * NLMAX], rdm2[NLMAX];
 };
 
+// Peer-memory transport of the y-slab ranks (one process per GPU, mailboxes mapped into each
+// other's address space with CUDA IPC).  The exchanges of an ocean step are done by the kernels
+// that produce or consume the data: they store into the peers' mailboxes over NVLink, publish an
+// epoch flag and spin on the flags the peers publish -- no collective library call on the step
+// stream.  Every exchange has two slots (epoch parity): a rank can only be one exchange of a
+// kind ahead of a peer, because finishing exchange e+1 needs that peer's flag e+1, which it
+// publishes after it has consumed exchange e.
+struct PeerCtx {
+  int n, rank;                  // n == 0: transport not set up (NCCL or loopback carries the exchange)
+  int fglen;                    // doubles per rank in the slab-row mailbox (nl * 2 * ld)
+  int halolen;                  // doubles per side in the halo mailbox (PEER_HALO_ROWS * ld)
+  double *box[8];               // mailbox of every rank (own allocation for self)
+  unsigned long long epoch;     // of this exchange; flags only ever increase
+};
+constexpr int PEER_VEC = 16;         // doubles per rank in an all-reduce
+constexpr int PEER_HALO_ROWS = 64;   // field-layer rows a halo exchange can carry per side
+// mailbox layout, in doubles: all-reduce vectors [2][n][PEER_VEC], flags (all-reduce [n],
+// slab rows [n], halo [2]), slab rows [2][n][fglen], halo rows [2][2][halolen]
+__host__ __device__ inline size_t peer_off_vec(int n, int slot, int src) { return (size_t)(slot * n + src) * PEER_VEC; }
+__host__ __device__ inline size_t peer_off_flagv(int n) { return (size_t)2 * n * PEER_VEC; }
+__host__ __device__ inline size_t peer_off_flagf(int n) { return peer_off_flagv(n) + n; }
+__host__ __device__ inline size_t peer_off_flagh(int n) { return peer_off_flagf(n) + n; }
+__host__ __device__ inline size_t peer_off_fg(int n, int fglen, int slot, int src) {
+  return ((peer_off_flagh(n) + 2 + 15) / 16) * 16 + (size_t)(slot * n + src) * fglen;
+}
+__host__ __device__ inline size_t peer_off_halo(int n, int fglen, int halolen, int slot, int side) {
+  return peer_off_fg(n, fglen, 2, 0) + (size_t)(slot * 2 + side) * halolen;
+}
+__host__ __device__ inline size_t peer_box_doubles(int n, int fglen, int halolen) { return peer_off_halo(n, fglen, halolen, 2, 0); }
+
 // Plan for the batched x-transform + partitioned y-tridiagonal Helmholtz solver
 struct HelmPlan {
   int kind;          // 0: DST-I rows (box), 1: real FFT rows (periodic)
@@ -102,6 +132,8 @@ struct HelmPlan {
   double *slab_ae = nullptr;   // [nmodes][nranks][2][ld] left-spike first/last values (alpha, eps) of every slab
   double *slab_fg = nullptr;   // [nranks][nmodes][2][ld] all-gathered first/last rows of the slab-local solutions
   double *slab_yx = nullptr;   // [nmodes][2][ld] true neighbour rows of this slab (Y of the slab below, X of the one above)
+  PeerCtx slab_peer = {};      // peer-memory transport: the gathered rows arrive in the mailbox, k_slab_solve waits for them
+  int *slab_err = nullptr;
   double *rowsum = nullptr;  // [nmodes][nyp]  xintp row sums of the solution
   double *ayrow = nullptr;   // [nmodes][2]    periodic: line sums of rows 2 and nyp-1
 };
@@ -165,6 +197,15 @@ struct qgcm_model {
   unsigned int *d_ticket = nullptr;      // last-block-done counters
   double *d_val = nullptr;               // valids: per-block partials
   bool shared_stream = false;            // loopback ranks > 0 borrow rank 0's stream
+  // peer-memory transport (slab.cu): own mailbox, peers' mapped mailboxes, exchange counters
+  double *mailbox = nullptr;
+  std::vector<void *> peer_maps;         // cudaIpcOpenMemHandle results to close
+  qg::PeerCtx peer = {};
+  bool use_peer = false;                 // qgcm_comm_init_peer / qgcm_comm_transport: exchanges go through the mailboxes
+  unsigned long long epoch_vec = 0, epoch_fg = 0, epoch_halo = 0;
+  unsigned int *d_ticket2 = nullptr;     // [0] slab-row push, [1] halo push
+  int *d_peer_err = nullptr;
+  unsigned int peer_checks = 0;
   // qgcm_set_field_async: copy stream, shadow buffers, names waiting for qgcm_commit_fields
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy = nullptr, ev_step = nullptr;
@@ -185,6 +226,43 @@ struct qgcm_model {
 
 #ifdef __CUDACC__
 namespace qg {
+// spin until *flag >= epoch.  A lost peer must not hang the device: the wait gives up after
+// ~10 s of GPU clock and raises *err, and once *err is set every later wait returns at once
+// (the step then finishes with whatever the mailbox holds and the host call reports the error)
+__device__ __forceinline__ void peer_wait(const volatile unsigned long long *flag, unsigned long long epoch, int *err) {
+  const long long t0 = clock64();
+  unsigned int spins = 0;
+  while (*flag < epoch) {
+    if ((++spins & 1023u) == 0) {
+      if (*reinterpret_cast<volatile int *>(err)) break;
+      if (clock64() - t0 > 20000000000LL) { *reinterpret_cast<volatile int *>(err) = 1; break; }
+    }
+  }
+}
+// All-reduce (sum, rank order) of my[0..n) over the slab ranks, executed by one whole block of
+// >= n_ranks*n threads: peer stores, system fence, epoch flags, wait, local sum.  out may alias my.
+__device__ __forceinline__ void peer_allreduce_block(const PeerCtx &c, const double *my, int n, double *out, int *err) {
+  const int slot = (int)(c.epoch & 1ull);
+  for (int idx = threadIdx.x; idx < c.n * n; idx += blockDim.x) {
+    const int r = idx / n, i = idx - r * n;
+    c.box[r][peer_off_vec(c.n, slot, c.rank) + i] = my[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < c.n) {
+    reinterpret_cast<volatile unsigned long long *>(c.box[threadIdx.x] + peer_off_flagv(c.n))[c.rank] = c.epoch;
+    peer_wait(reinterpret_cast<const volatile unsigned long long *>(c.box[c.rank] + peer_off_flagv(c.n)) + threadIdx.x, c.epoch, err);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < n) {
+    const volatile double *mine = c.box[c.rank];
+    double s = 0.0;
+    for (int r = 0; r < c.n; ++r) s += mine[peer_off_vec(c.n, slot, r) + threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
 // deterministic sum of v[first..last) by one block of 256 threads (fixed strided partials,
 // fixed-order tree); every thread returns the total.  red: 8 doubles of shared memory.
 __device__ __forceinline__ double block256_range_sum(const double *v, int first, int last, double *red) {
@@ -244,6 +322,12 @@ void nccl_unique_id(void *out128);
 void nccl_init(qgcm_model *m, const void *id128);
 void nccl_destroy(qgcm_model *m);
 void group_create(qgcm_model **models, int n);
+void peer_export(qgcm_model *m, void *handle64);
+void peer_init(qgcm_model *m, const void *handles, int n);
+void peer_close(qgcm_model *m);
+void set_transport(qgcm_model *m, int kind);
+bool peer_active(const qgcm_model *m);    // this model's exchanges go through the peer mailboxes
+PeerCtx peer_next_vec(qgcm_model *m);     // context of the next all-reduce (advances the epoch); n == 0 when not active
 Ranks ranks_of(qgcm_model *m);
 void slab_ocean_step(const Ranks &ms);
 void slab_constr(const Ranks &ms);

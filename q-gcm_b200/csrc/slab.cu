@@ -92,6 +92,180 @@ void nccl_destroy(qgcm_model *m) {
   m->nccl = nullptr;
 }
 
+// ---------------------------------------------------------------- peer-memory transport (CUDA IPC)
+// One process per GPU.  Every rank allocates a mailbox, hands out its CUDA IPC handle
+// (qgcm_peer_handle), the host program gathers the handles (MPI_Allgather in the Fortran driver,
+// torch.distributed in bench.py) and every rank maps the others' mailboxes
+// (qgcm_comm_init_peer).  From then on the exchanges of a step are stores into the peers'
+// mailboxes plus epoch flags, issued by the kernels of the step themselves.
+static int peer_halolen(const qgcm_model *m) { return PEER_HALO_ROWS * m->go.ld; }
+
+void peer_export(qgcm_model *m, void *handle64) {
+  if (m->nranks < 2) throw std::runtime_error("qgcm_peer_handle: model was created with nranks = 1");
+  if (m->nranks > 8) throw std::runtime_error("qgcm_peer_handle: at most 8 ranks");
+  if (!m->mailbox) {
+    const int fglen = m->go.nl * 2 * m->hpo.ld;
+    const size_t n = peer_box_doubles(m->nranks, fglen, peer_halolen(m));
+    m->mailbox = (double *)dalloc(m, sizeof(double) * n);
+    m->d_ticket2 = (unsigned int *)dalloc(m, sizeof(unsigned int) * 4);
+    m->d_peer_err = (int *)dalloc(m, sizeof(int) * 4);
+    QG_CUDA(cudaMemset(m->mailbox, 0, sizeof(double) * n));
+    QG_CUDA(cudaMemset(m->d_ticket2, 0, sizeof(unsigned int) * 4));
+    QG_CUDA(cudaMemset(m->d_peer_err, 0, sizeof(int) * 4));
+    QG_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  QG_CUDA(cudaIpcGetMemHandle(&h, m->mailbox));
+  static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+  std::memcpy(handle64, &h, sizeof(h));
+}
+
+// handles: nranks x 64 bytes, in rank order (every rank's qgcm_peer_handle)
+void peer_init(qgcm_model *m, const void *handles, int n) {
+  if (n != m->nranks || n > 8) throw std::runtime_error("qgcm_comm_init_peer: handle count differs from nranks (<= 8)");
+  if (!m->mailbox) throw std::runtime_error("qgcm_comm_init_peer: call qgcm_peer_handle first");
+  if (m->peer.n) throw std::runtime_error("qgcm_comm_init_peer: already initialised");
+  QG_CUDA(cudaSetDevice(m->cfg.device));
+  PeerCtx c = {};
+  c.n = n; c.rank = m->rank; c.fglen = m->go.nl * 2 * m->hpo.ld; c.halolen = peer_halolen(m); c.epoch = 0;
+  for (int r = 0; r < n; ++r) {
+    if (r == m->rank) { c.box[r] = m->mailbox; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char *)handles + (size_t)r * 64, sizeof(h));
+    void *p = nullptr;
+    QG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    m->peer_maps.push_back(p);
+    c.box[r] = (double *)p;
+  }
+  m->peer = c;
+  m->use_peer = true;
+}
+
+void peer_close(qgcm_model *m) {
+  for (void *p : m->peer_maps) cudaIpcCloseMemHandle(p);
+  m->peer_maps.clear();
+  m->peer.n = 0;
+  m->use_peer = false;
+}
+
+// kind 0: NCCL, 1: peer mailboxes.  Every rank must switch between the same two steps.
+void set_transport(qgcm_model *m, int kind) {
+  if (kind == 0) {
+    if (!m->nccl) throw std::runtime_error("qgcm_comm_transport: no NCCL communicator (qgcm_comm_init_nccl)");
+    m->use_peer = false;
+  } else if (kind == 1) {
+    if (!m->peer.n) throw std::runtime_error("qgcm_comm_transport: no peer mailboxes (qgcm_comm_init_peer)");
+    m->use_peer = true;
+  } else {
+    throw std::runtime_error("qgcm_comm_transport: kind is 0 (NCCL) or 1 (peer memory)");
+  }
+}
+
+bool peer_active(const qgcm_model *m) { return m->peers.empty() && m->use_peer && m->peer.n > 0; }
+
+PeerCtx peer_next_vec(qgcm_model *m) {
+  PeerCtx c = m->peer;
+  if (!peer_active(m)) { c.n = 0; return c; }
+  c.epoch = ++m->epoch_vec;
+  return c;
+}
+
+__global__ void __launch_bounds__(256) k_peer_allreduce(PeerCtx c, double *v, int n, int *err) {
+  peer_allreduce_block(c, v, n, v, err);
+}
+
+// this rank's slab rows (hpo.slab_send) into every rank's mailbox; the block that finishes last
+// publishes the epoch.  grid (blocks per peer, nranks).  The consumer (k_slab_solve) waits for
+// the flags of all ranks and reads the rows from its own mailbox.
+__global__ void __launch_bounds__(256) k_slab_push(PeerCtx c, const double *send, unsigned int *ticket) {
+  __shared__ bool last;
+  const int slot = (int)(c.epoch & 1ull);
+  double2 *dst = reinterpret_cast<double2 *>(c.box[blockIdx.y] + peer_off_fg(c.n, c.fglen, slot, c.rank));
+  const double2 *src = reinterpret_cast<const double2 *>(send);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.fglen / 2; i += gridDim.x * blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  if (threadIdx.x == 0) *ticket = 0u;
+  if ((int)threadIdx.x < c.n)
+    reinterpret_cast<volatile unsigned long long *>(c.box[threadIdx.x] + peer_off_flagf(c.n))[c.rank] = c.epoch;
+}
+
+// Halo exchange through the mailboxes.  One block per (row, side): side 0 carries my top owned
+// rows up (they land in the "from below" half of rank+1's mailbox), side 1 my bottom owned rows
+// down.  The last block to finish publishes the epoch to both neighbours; then every block waits
+// for the neighbour on its side and copies that neighbour's rows from the own mailbox into the
+// halo rows of the field.  Staging (instead of storing into the neighbour's field) matters: the
+// neighbour may still be inside its own step, writing those very rows.
+struct HaloArgs {
+  PeerCtx c;
+  int nfl, ld, nrows;          // field layers, row pitch, HALO
+  double *base[24];            // first row of every field layer
+  int ny[24];                  // rows the slab holds of that layer (T fields: one less than p fields)
+  int own0, own1;              // owned p rows [own0, own1) of the slab
+  unsigned int *ticket;
+  int *err;
+};
+__global__ void __launch_bounds__(256) k_halo_peer(HaloArgs a) {
+  __shared__ bool last;
+  const PeerCtx &c = a.c;
+  const int slot = (int)(c.epoch & 1ull);
+  const int fl = blockIdx.x / a.nrows, r = blockIdx.x - fl * a.nrows, side = blockIdx.y;
+  const int n2 = a.ld / 2;
+  const bool has_dn = c.rank > 0, has_up = c.rank + 1 < c.n;
+  // ---- push
+  if (side == 0 && has_up) {
+    const double2 *src = reinterpret_cast<const double2 *>(a.base[fl] + (size_t)(a.own1 - a.nrows + r) * a.ld);
+    double2 *dst = reinterpret_cast<double2 *>(c.box[c.rank + 1] + peer_off_halo(c.n, c.fglen, c.halolen, slot, 0) +
+                                               (size_t)(fl * a.nrows + r) * a.ld);
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = src[i];
+  }
+  if (side == 1 && has_dn) {
+    const double2 *src = reinterpret_cast<const double2 *>(a.base[fl] + (size_t)min(a.own0 + r, a.ny[fl] - 1) * a.ld);
+    double2 *dst = reinterpret_cast<double2 *>(c.box[c.rank - 1] + peer_off_halo(c.n, c.fglen, c.halolen, slot, 1) +
+                                               (size_t)(fl * a.nrows + r) * a.ld);
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = src[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(a.ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    if (threadIdx.x == 0) {
+      *a.ticket = 0u;
+      if (has_up) reinterpret_cast<volatile unsigned long long *>(c.box[c.rank + 1] + peer_off_flagh(c.n))[0] = c.epoch;
+      if (has_dn) reinterpret_cast<volatile unsigned long long *>(c.box[c.rank - 1] + peer_off_flagh(c.n))[1] = c.epoch;
+    }
+  }
+  // ---- pull: side 0 = rows from below into my bottom halo, side 1 = rows from above into my top halo
+  if ((side == 0 && !has_dn) || (side == 1 && !has_up)) return;
+  if (threadIdx.x == 0)
+    peer_wait(reinterpret_cast<const volatile unsigned long long *>(c.box[c.rank] + peer_off_flagh(c.n)) + side, c.epoch, a.err);
+  __syncthreads();
+  __threadfence_system();
+  const int row = side == 0 ? r : a.own1 + r;
+  if (row >= a.ny[fl]) return;          // T fields hold one halo row less above the owned rows
+  const double2 *src = reinterpret_cast<const double2 *>(c.box[c.rank] + peer_off_halo(c.n, c.fglen, c.halolen, slot, side) +
+                                                         (size_t)(fl * a.nrows + r) * a.ld);
+  double2 *dst = reinterpret_cast<double2 *>(a.base[fl] + (size_t)row * a.ld);
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    double2 v;
+    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(src + i));
+    dst[i] = v;
+  }
+}
+
+static void check_peer_err(qgcm_model *m) {
+  int e = 0;
+  QG_CUDA(cudaMemcpyAsync(&e, m->d_peer_err, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  QG_CUDA(cudaStreamSynchronize(m->stream));
+  if (e) throw std::runtime_error("y-slab exchange timed out waiting for a peer rank");
+}
+
 Ranks ranks_of(qgcm_model *m) {
   if (!m->peers.empty()) return m->peers;
   return Ranks{m};
@@ -100,8 +274,8 @@ Ranks ranks_of(qgcm_model *m) {
 static void check_comm(const Ranks &ms) {
   qgcm_model *m = ms[0];
   if (m->nranks == 1) return;
-  if (ms.size() == 1 && !m->nccl)
-    throw std::runtime_error("y-slab model has no communicator: call qgcm_comm_init_nccl or qgcm_group_create first");
+  if (ms.size() == 1 && !m->nccl && !peer_active(m))
+    throw std::runtime_error("y-slab model has no communicator: call qgcm_comm_init_nccl, qgcm_comm_init_peer or qgcm_group_create first");
   if (ms.size() > 1 && (int)ms.size() != m->nranks) throw std::runtime_error("loopback group does not hold every rank");
 }
 
@@ -121,6 +295,11 @@ void comm_allreduce_cv(const Ranks &ms, size_t off, int n) {
   check_comm(ms);
   qgcm_model *m0 = ms[0];
   if (m0->nranks == 1) return;
+  if (peer_active(m0)) {
+    if (n > PEER_VEC) throw std::runtime_error("comm_allreduce_cv: payload too large for the mailbox");
+    QG_LAUNCH(m0, "k_peer_allreduce", 1, 256, 0, k_peer_allreduce, peer_next_vec(m0), m0->d_cv + off, n, m0->d_peer_err);
+    return;
+  }
   if (ms.size() == 1) {
     nccl_ok(nccl().AllReduce(m0->d_cv + off, m0->d_cv + off, (size_t)n, NCCL_DOUBLE, NCCL_SUM, m0->nccl, m0->stream), "ncclAllReduce");
     return;
@@ -137,7 +316,7 @@ void comm_allreduce_host(const Ranks &ms, std::vector<std::vector<double>> &vals
   qgcm_model *m0 = ms[0];
   if (m0->nranks == 1) return;
   const size_t n = vals[0].size();
-  if (n > 24) throw std::runtime_error("comm_allreduce_host: payload too large");
+  if (n > (size_t)PEER_VEC) throw std::runtime_error("comm_allreduce_host: payload too large");
   for (size_t r = 0; r < ms.size(); ++r)
     QG_CUDA(cudaMemcpyAsync(ms[r]->d_cv + 8, vals[r].data(), sizeof(double) * n, cudaMemcpyHostToDevice, ms[r]->stream));
   comm_allreduce_cv(ms, 8, (int)n);
@@ -152,6 +331,16 @@ static void comm_allgather_slab(const Ranks &ms) {
   check_comm(ms);
   qgcm_model *m0 = ms[0];
   const size_t n = (size_t)m0->go.nl * 2 * m0->hpo.ld;
+  if (peer_active(m0)) {
+    // the rows go straight into every rank's mailbox; k_slab_solve waits for them there
+    PeerCtx c = m0->peer;
+    c.epoch = ++m0->epoch_fg;
+    m0->hpo.slab_peer = c;
+    m0->hpo.slab_err = m0->d_peer_err;
+    QG_LAUNCH(m0, "k_slab_push", dim3(4, c.n), 256, 0, k_slab_push, c, m0->hpo.slab_send, m0->d_ticket2);
+    return;
+  }
+  m0->hpo.slab_peer.n = 0;
   if (ms.size() == 1) {
     nccl_ok(nccl().AllGather(m0->hpo.slab_send, m0->hpo.slab_fg, n, NCCL_DOUBLE, m0->nccl, m0->stream), "ncclAllGather");
     return;
@@ -167,6 +356,27 @@ void comm_halo(const Ranks &ms, const std::vector<const char *> &names) {
   check_comm(ms);
   qgcm_model *m0 = ms[0];
   if (m0->nranks == 1) return;
+  if (peer_active(m0)) {
+    const Grid &g = m0->go;
+    HaloArgs a;
+    a.c = m0->peer;
+    a.c.epoch = ++m0->epoch_halo;
+    a.nfl = 0; a.ld = g.ld; a.nrows = HALO; a.own0 = g.own0; a.own1 = g.own1;
+    for (const char *nm : names) {
+      qgcm_model::Field &f = m0->fields.at(nm);
+      if (f.ld != g.ld) throw std::runtime_error("comm_halo: field pitch differs from the grid pitch");
+      for (int k = 0; k < f.nl; ++k) {
+        if (a.nfl >= 24 || (a.nfl + 1) * HALO > PEER_HALO_ROWS) throw std::runtime_error("comm_halo: too many field layers for the mailbox");
+        a.base[a.nfl] = f.d + (size_t)k * f.lsz;
+        a.ny[a.nfl] = f.ny;
+        ++a.nfl;
+      }
+    }
+    a.ticket = m0->d_ticket2 + 1;
+    a.err = m0->d_peer_err;
+    QG_LAUNCH(m0, "k_halo_peer", dim3(a.nfl * HALO, 2), 256, 0, k_halo_peer, a);
+    return;
+  }
   const bool loop = ms.size() > 1;
   if (!loop) nccl_ok(nccl().GroupStart(), "ncclGroupStart");
   for (qgcm_model *m : ms) {
@@ -208,8 +418,12 @@ void comm_halo(const Ranks &ms, const std::vector<const char *> &names) {
 // oml + qgostep + ocinvq + ocqbdy (src/q-gcm.F:1229-1249) over y-slabs
 void slab_ocean_step(const Ranks &ms) {
   check_comm(ms);
+  // with the peer-memory transport the kernels of the step carry the exchanges themselves:
+  // k_oml_reduce and k_inv_partials all-reduce their sums, k_slab_push/k_slab_solve move the
+  // slab rows, k_halo_peer the halo rows; otherwise NCCL (or the loopback copies) sit between
+  const bool peer = peer_active(ms[0]);
   for (qgcm_model *m : ms) oml_phase_a(m);
-  comm_allreduce_cv(ms, 0, 3);
+  if (!peer) comm_allreduce_cv(ms, 0, 3);
   for (qgcm_model *m : ms) {
     oml_phase_b(m);
     launch_qgostep(m);
@@ -217,12 +431,13 @@ void slab_ocean_step(const Ranks &ms) {
   }
   comm_allgather_slab(ms);
   for (qgcm_model *m : ms) ocinvq_phase_b(m);
-  comm_allreduce_cv(ms, 3, 1 + ms[0]->go.nl);
+  if (!peer) comm_allreduce_cv(ms, 3, 1 + ms[0]->go.nl);
   for (qgcm_model *m : ms) {
     ocinvq_phase_c(m);
     launch_ocqbdy(m, m->F("qo"), m->F("po"));
   }
   comm_halo(ms, {"po", "qo", "sst"});
+  if (peer && (++ms[0]->peer_checks & 63) == 0) check_peer_err(ms[0]);
 }
 
 void slab_constr(const Ranks &ms) {

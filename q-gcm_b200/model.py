@@ -186,6 +186,20 @@ class Model(CModel):
     def comm_init_nccl(self, id128: bytes):
         self._call("comm_init_nccl", C.c_char_p(id128))
 
+    # -- peer-memory transport: CUDA IPC mailboxes, exchanged by the host program
+    def peer_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._call("peer_handle", buf)
+        return buf.raw
+
+    def comm_init_peer(self, handles):
+        """handles: every rank's peer_handle(), in rank order"""
+        blob = b"".join(handles)
+        self._call("comm_init_peer", C.c_char_p(blob), C.c_int32(len(handles)))
+
+    def comm_transport(self, kind: str):
+        self._call("comm_transport", C.c_int32({"nccl": 0, "peer": 1}[kind]))
+
 
 def slab_config(cfg: QgcmConfig, nranks: int, rank: int) -> QgcmConfig:
     """copy of cfg that selects y-slab `rank` of `nranks` (include/qgcm_b200.h, nranks/rank)"""
