@@ -57,8 +57,11 @@ __device__ __forceinline__ int wrapt(int i, int nxt, int cyc) {
 // 72 %.)
 // ------------------------------------------------------------------------------------------
 constexpr int MW = 60;      // output columns per warp: 32 lanes x 2 columns minus a halo of 2 columns on either side
-constexpr int MR = 128;     // most rows marched by one warp (fewer on small grids / slabs, to fill the GPU)
-constexpr int MD = 4;       // prefetch depth (row stages in flight; 14 KB of shared memory per warp)
+constexpr int MR = 256;     // most rows marched by one warp (fewer on small grids / slabs, to fill the GPU)
+#ifndef QGCM_OML_MD
+#define QGCM_OML_MD 4
+#endif
+constexpr int MD = QGCM_OML_MD;       // prefetch depth (row stages in flight; 14 KB of shared memory per warp)
 constexpr int MNF = 7;      // fields per stage: sstm, sst, p, taux, tauy, wekt, fnet
 
 __device__ __forceinline__ void oml_cp16(double2 *smem_dst, const double *gsrc) {
@@ -294,6 +297,7 @@ __device__ void oml_monitors(const OmlArgs &a, double (*red)[8]) {
   const Grid &g = a.g;
   const int nxt = g.nxt, nyt = g.nyt, ld = g.ld;
   double s[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 4
   for (int i = threadIdx.x; i < nxt; i += 256) {
     if (a.sb && g.wall_s()) {   // y-slabs: the rank that holds the wall owns these monitors
       const double vm = -a.rhf0hm * (a.taux[i + 1] + a.taux[i]);
@@ -492,10 +496,19 @@ static OmlArgs oml_args(qgcm_model *m, dim3 &grid) {
   a.peer = PeerCtx{};
   a.peer_err = m->d_peer_err;
   {
-    // enough marches to fill 148 SMs x 16 warps, but at least 16 rows each (4 fill rows per march)
+    // marches sized to whole waves of resident blocks, at least 16 rows each (4 fill rows per march)
     const int xw = (g.nxt + MW - 1) / MW;
-    const int chunks = std::max(1, (148 * 16 + xw - 1) / xw);
-    a.mrows = std::min(MR, std::max(16, (g.nyt + chunks - 1) / chunks));
+    static int resident = 0;
+    if (!resident) {
+      const size_t smem = 4 * MD * MNF * 32 * sizeof(double2);
+      QG_CUDA(cudaFuncSetAttribute(k_oml_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0, sms = 0;
+      QG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_oml_march, 128, smem));
+      QG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->cfg.device));
+      resident = std::max(1, per_sm * sms);
+    }
+    a.mrows = pick_march_rows(g.nyt, (xw + 3) / 4, resident, 16, MR);
+    a.mrows = std::max(8, std::min(1024, env_int("QGCM_OML_MROWS", a.mrows)));
     grid = dim3((xw + 3) / 4, (g.nyt + a.mrows - 1) / a.mrows);
   }
   a.nblocks = grid.x * grid.y;

@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -90,6 +92,26 @@ __host__ __device__ inline size_t peer_off_halo(int n, int fglen, int halolen, i
   return peer_off_fg(n, fglen, 2, 0) + (size_t)(slot * 2 + side) * halolen;
 }
 __host__ __device__ inline size_t peer_box_doubles(int n, int fglen, int halolen) { return peer_off_halo(n, fglen, halolen, 2, 0); }
+
+// tuning override read at launch time (scripts/march_sweep.py); the defaults are the measured best
+inline int env_int(const char *name, int dflt) {
+  const char *v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
+// Rows per march of a marching kernel (k_qgstep2, k_oml_march).  Blocks that do not fit the
+// resident capacity of the GPU run as a second wave at full cost (measured: oml at 1 km, 480
+// blocks on 444 slots 0.46 ms, 440 blocks 0.33 ms), so the number of marches is the largest
+// that fills a whole number of waves, with the fewest waves whose marches stay under `cap` rows.
+//   bx: blocks per march row, resident: blocks the GPU holds at once, lo: shortest useful march
+inline int pick_march_rows(int nrows, int bx, int resident, int lo, int cap) {
+  for (int w = 1; w <= 64; ++w) {
+    const int c = std::max(1, (w * resident) / bx);
+    const int rows = (nrows + c - 1) / c;
+    if (rows <= cap) return std::max(lo, rows);
+  }
+  return cap;
+}
 
 // Plan for the batched x-transform + partitioned y-tridiagonal Helmholtz solver
 struct HelmPlan {

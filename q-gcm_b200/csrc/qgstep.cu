@@ -369,17 +369,21 @@ static void launch(qgcm_model *m, bool atmos) {
     QG_LAUNCH(m, "k_strips", dim3(g.nl, 2), 256, 0, k_strips, s);
   }
   {
-    // enough marches to fill 148 SMs x 16 warps, but at least 24 rows each (6 fill rows per march)
+    // marches sized to whole waves of resident blocks, at least 24 rows each (6 fill rows per march)
     const int nwx = (g.nxp + W2OUT - 1) / W2OUT;
-    const int chunks = std::max(1, (148 * 16 + nwx * g.nl - 1) / (nwx * g.nl));
-    a.mrows = std::min(RCH, std::max(24, (g.nyp + chunks - 1) / chunks));
-    dim3 grid((nwx + 3) / 4, (g.nyp + a.mrows - 1) / a.mrows, g.nl);
     const size_t smem = 4 * Q2_D * QG_NF * 32 * sizeof(double2);
-    static bool attr = false;
-    if (!attr) {
+    static int resident = 0;
+    if (!resident) {
       QG_CUDA(cudaFuncSetAttribute(k_qgstep2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
+      int per_sm = 0, sms = 0;
+      QG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qgstep2, 128, smem));
+      QG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->cfg.device));
+      resident = std::max(1, per_sm * sms);
     }
+    const int bx = ((nwx + 3) / 4) * g.nl;
+    a.mrows = pick_march_rows(g.nyp, bx, resident, 24, RCH);
+    a.mrows = std::max(8, std::min(1024, env_int("QGCM_QG_MROWS", a.mrows)));
+    dim3 grid((nwx + 3) / 4, (g.nyp + a.mrows - 1) / a.mrows, g.nl);
     QG_LAUNCH(m, "k_qgstep", grid, 128, smem, k_qgstep2, a);
   }
   QG_CUDA(cudaGetLastError());

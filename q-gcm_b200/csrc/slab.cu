@@ -209,25 +209,48 @@ struct HaloArgs {
   unsigned int *ticket;
   int *err;
 };
+constexpr int HALO_XS = 4;     // blocks per row
+__device__ __forceinline__ void halo_copy(double2 *dst, const double2 *src, int i0, int i1, bool vol) {
+  // three 16-byte loads in flight per thread before the first store
+  for (int i = i0 + (int)threadIdx.x; i < i1; i += 3 * 256) {
+    double2 v[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int j = i + u * 256;
+      if (j < i1) {
+        if (vol)
+          asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v[u].x), "=d"(v[u].y) : "l"(src + j));
+        else
+          v[u] = src[j];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int j = i + u * 256;
+      if (j < i1) dst[j] = v[u];
+    }
+  }
+}
 __global__ void __launch_bounds__(256) k_halo_peer(HaloArgs a) {
   __shared__ bool last;
   const PeerCtx &c = a.c;
   const int slot = (int)(c.epoch & 1ull);
-  const int fl = blockIdx.x / a.nrows, r = blockIdx.x - fl * a.nrows, side = blockIdx.y;
-  const int n2 = a.ld / 2;
+  const int xs = blockIdx.x % HALO_XS, rowid = blockIdx.x / HALO_XS;
+  const int fl = rowid / a.nrows, r = rowid - fl * a.nrows, side = blockIdx.y;
+  const int n2 = a.ld / 2, per = (n2 + HALO_XS - 1) / HALO_XS, i0 = xs * per, i1 = min(n2, i0 + per);
   const bool has_dn = c.rank > 0, has_up = c.rank + 1 < c.n;
   // ---- push
   if (side == 0 && has_up) {
     const double2 *src = reinterpret_cast<const double2 *>(a.base[fl] + (size_t)(a.own1 - a.nrows + r) * a.ld);
     double2 *dst = reinterpret_cast<double2 *>(c.box[c.rank + 1] + peer_off_halo(c.n, c.fglen, c.halolen, slot, 0) +
                                                (size_t)(fl * a.nrows + r) * a.ld);
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = src[i];
+    halo_copy(dst, src, i0, i1, false);
   }
   if (side == 1 && has_dn) {
     const double2 *src = reinterpret_cast<const double2 *>(a.base[fl] + (size_t)min(a.own0 + r, a.ny[fl] - 1) * a.ld);
     double2 *dst = reinterpret_cast<double2 *>(c.box[c.rank - 1] + peer_off_halo(c.n, c.fglen, c.halolen, slot, 1) +
                                                (size_t)(fl * a.nrows + r) * a.ld);
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = src[i];
+    halo_copy(dst, src, i0, i1, false);
   }
   __threadfence_system();
   __syncthreads();
@@ -251,12 +274,7 @@ __global__ void __launch_bounds__(256) k_halo_peer(HaloArgs a) {
   if (row >= a.ny[fl]) return;          // T fields hold one halo row less above the owned rows
   const double2 *src = reinterpret_cast<const double2 *>(c.box[c.rank] + peer_off_halo(c.n, c.fglen, c.halolen, slot, side) +
                                                          (size_t)(fl * a.nrows + r) * a.ld);
-  double2 *dst = reinterpret_cast<double2 *>(a.base[fl] + (size_t)row * a.ld);
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-    double2 v;
-    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(src + i));
-    dst[i] = v;
-  }
+  halo_copy(reinterpret_cast<double2 *>(a.base[fl] + (size_t)row * a.ld), src, i0, i1, true);
 }
 
 static void check_peer_err(qgcm_model *m) {
@@ -337,7 +355,7 @@ static void comm_allgather_slab(const Ranks &ms) {
     c.epoch = ++m0->epoch_fg;
     m0->hpo.slab_peer = c;
     m0->hpo.slab_err = m0->d_peer_err;
-    QG_LAUNCH(m0, "k_slab_push", dim3(4, c.n), 256, 0, k_slab_push, c, m0->hpo.slab_send, m0->d_ticket2);
+    QG_LAUNCH(m0, "k_slab_push", dim3(16, c.n), 256, 0, k_slab_push, c, m0->hpo.slab_send, m0->d_ticket2);
     return;
   }
   m0->hpo.slab_peer.n = 0;
@@ -374,7 +392,7 @@ void comm_halo(const Ranks &ms, const std::vector<const char *> &names) {
     }
     a.ticket = m0->d_ticket2 + 1;
     a.err = m0->d_peer_err;
-    QG_LAUNCH(m0, "k_halo_peer", dim3(a.nfl * HALO, 2), 256, 0, k_halo_peer, a);
+    QG_LAUNCH(m0, "k_halo_peer", dim3(a.nfl * HALO * HALO_XS, 2), 256, 0, k_halo_peer, a);
     return;
   }
   const bool loop = ms.size() > 1;

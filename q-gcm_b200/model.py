@@ -17,7 +17,8 @@ _LIB = None
 
 
 def library_path():
-    return os.path.join(_HERE, "csrc", "libqgcm_b200.so")
+    # QGCM_B200_LIB: an alternative build of the same library (kernel A/B experiments)
+    return os.environ.get("QGCM_B200_LIB") or os.path.join(_HERE, "csrc", "libqgcm_b200.so")
 
 
 def load_library():

@@ -20,12 +20,27 @@ def free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("case,nranks,steps", [("box_dg", 2, 3), ("box_dg", 3, 2), ("box_fast", 2, 3), ("box_fast", 4, 2)])
-def test_peer_transport_matches_oracle(case, nranks, steps):
+def run_ranks(case, nranks, steps):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks),
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
            os.path.join(ROOT, "scripts", "peer_worker.py"), "--case", case, "--steps", str(steps)]
     env = dict(os.environ, OMP_NUM_THREADS="2")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     ok = [ln for ln in r.stdout.splitlines() if ln.startswith("PEER_OK")]
-    assert r.returncode == 0 and len(ok) == nranks, "rc=%d\n%s\n%s" % (r.returncode, r.stdout[-3000:], r.stderr[-3000:])
+    return r, (r.returncode == 0 and len(ok) == nranks)
+
+
+@pytest.mark.parametrize("case,nranks,steps", [("box_dg", 2, 3), ("box_dg", 3, 2), ("box_fast", 2, 3), ("box_fast", 4, 2)])
+def test_peer_transport_matches_oracle(case, nranks, steps):
+    # the launcher's rendezvous (a TCP port picked here, then re-bound by torchrun) can lose a
+    # race with another process on a busy box: one retry, and the first attempt's output is kept
+    r, good = run_ranks(case, nranks, steps)
+    if not good:
+        log = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(log):
+            with open(os.path.join(log, "peer_fail_%s_%d.log" % (case, nranks)), "w") as f:
+                f.write("rc=%d\n%s\n%s" % (r.returncode, r.stdout, r.stderr))
+        if "differs from the oracle" in r.stdout + r.stderr:
+            pytest.fail("parity: %s" % (r.stdout + r.stderr)[-2000:])
+        r, good = run_ranks(case, nranks, steps)
+    assert good, "rc=%d\n%s\n%s" % (r.returncode, r.stdout[-3000:], r.stderr[-3000:])
