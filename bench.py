@@ -152,6 +152,9 @@ def peer_self_check(qg, local, world, rank, dist, torch):
             j0, n = qg.slab_bounds(p.nypo, world, rank)
             out[kind] = {k: m.get_field(k).reshape((p.nxpo, p.nypo, p.nlo), order="F")[:, j0:j0 + n, :].copy() for k in ("po", "qo")}
             dist.barrier()      # no rank unmaps a mailbox another rank may still be writing to
+            if kind == "peer":
+                m.comm_close_peer()
+                dist.barrier()  # no rank frees a mailbox another rank still maps
             m.close()
         for k in ("po", "qo"):
             a, b = out["peer"][k], out["nccl"][k]
@@ -491,6 +494,9 @@ def main():
     if world > 1:
         m.sync()
         dist.barrier()          # no rank unmaps a mailbox another rank may still be writing to
+        if transport == "peer":
+            m.comm_close_peer()
+            dist.barrier()      # no rank frees a mailbox another rank still maps
         m.close()
         dist.destroy_process_group()
 

@@ -235,6 +235,10 @@ int qgcm_comm_init_nccl(qgcm_model *m, const void *id128);
 int qgcm_peer_handle(qgcm_model *m, void *handle64);
 int qgcm_comm_init_peer(qgcm_model *m, const void *handles, int32_t n);
 int qgcm_comm_transport(qgcm_model *m, int32_t kind);
+/* Tear-down order (CUDA IPC rule: an exported buffer must not be freed while another process
+ * still maps it): every rank calls qgcm_comm_close_peer (unmaps the others' mailboxes), the
+ * host program synchronises the ranks (MPI_Barrier), then every rank calls qgcm_destroy. */
+int qgcm_comm_close_peer(qgcm_model *m);
 /* all ranks in one process on one device (tests on a single GPU): models[r] must be rank r
  * of an n-rank partition; afterwards a partition call on any member steps every rank */
 int qgcm_group_create(qgcm_model **models, int32_t n);

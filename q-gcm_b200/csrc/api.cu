@@ -22,7 +22,11 @@ namespace qg {
 void *dalloc(qgcm_model *m, size_t bytes) {
   void *p = nullptr;
   QG_CUDA(cudaMalloc(&p, bytes ? bytes : 8));
+  // zero-fill, complete before anything else touches the buffer: a memset on the legacy stream is
+  // asynchronous and not ordered with the model's non-blocking stream (under GPU contention it
+  // landed after the first kernel that filled a table).  Allocation is start-up work.
   QG_CUDA(cudaMemset(p, 0, bytes ? bytes : 8));
+  QG_CUDA(cudaDeviceSynchronize());
   m->allocs.push_back(p);
   return p;
 }
@@ -407,6 +411,7 @@ int qgcm_helmholtz(qgcm_model *m, int which, double *wrk, const double *b) {
     helm_set_diag(m, hp, bb.data());
     QG_CUDA(cudaMemcpy2DAsync(dw, sizeof(double) * g.ld, wrk, sizeof(double) * g.nxp, sizeof(double) * g.nxp, g.nyp,
                               cudaMemcpyHostToDevice, m->stream));
+    hp.walls_dirty = true;
     helm_solve(m, hp, dw, 1);
     QG_CUDA(cudaMemcpy2DAsync(wrk, sizeof(double) * g.nxp, dw, sizeof(double) * g.ld, sizeof(double) * g.nxp, g.nyp,
                               cudaMemcpyDeviceToHost, m->stream));
@@ -481,6 +486,12 @@ int qgcm_group_create(qgcm_model **models, int32_t n) { QG_TRY(group_create(mode
 int qgcm_peer_handle(qgcm_model *m, void *handle64) { QG_TRY(peer_export(m, handle64)); }
 int qgcm_comm_init_peer(qgcm_model *m, const void *handles, int32_t n) { QG_TRY(peer_init(m, handles, n)); }
 int qgcm_comm_transport(qgcm_model *m, int32_t kind) { QG_TRY(set_transport(m, kind)); }
+int qgcm_comm_close_peer(qgcm_model *m) {
+  QG_TRY({
+    QG_CUDA(cudaStreamSynchronize(m->stream));
+    peer_close(m);
+  });
+}
 
 int qgcm_valids(qgcm_model *m, qgcm_valids_report *rep) { QG_TRY(launch_valids(m, rep)); }
 

@@ -695,6 +695,8 @@ struct TriArgs {
   int slab_phase;              // k_tri_reduced on y-slabs: 1 = also emit the slab's first/last rows, 2 = outer neighbours are the adjacent slabs' rows
   double *slab_send;           // [nmodes][2][ld]
   const double *slab_outer;    // [nmodes][2][ld]
+  PeerCtx peer;                // slab_phase 1 over peer memory: the rows go to the ranks' mailboxes instead of slab_send
+  unsigned int *ticket;
   double a, ftnorm;
   double *wrk;
   const double *bcoef;
@@ -797,7 +799,7 @@ __global__ void __launch_bounds__(128, 3) k_tri_local(TriArgs t) {
 __global__ void __launch_bounds__(128) k_tri_reduced(TriArgs t) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int mode = blockIdx.y;
-  if (s >= t.nk) return;
+  if (s < t.nk) {
   const int col = t.koff + s;
   const int C = t.nchunk, ld = t.ld;
   const size_t tb = ((size_t)mode * TRI_L) * ld + col;
@@ -865,11 +867,35 @@ __global__ void __launch_bounds__(128) k_tri_reduced(TriArgs t) {
   if (t.slab_phase == 1) {
     // first and last rows of the slab-local solution: f_0 + eps x_1, g_{C-1} + epsl y_{C-2}
     const double epsl = t.vll[tb + (size_t)(t.lastlen - 1) * ld];
-    t.slab_send[((size_t)mode * 2 + 0) * ld + col] = f[0] + eps * xnext;
-    t.slab_send[((size_t)mode * 2 + 1) * ld + col] = g[(size_t)(C - 1) * ld] + epsl * yp[(size_t)(C - 1) * ld];
+    const double F = f[0] + eps * xnext, G = g[(size_t)(C - 1) * ld] + epsl * yp[(size_t)(C - 1) * ld];
+    if (t.peer.n) {
+      // peer-memory transport: the two rows go straight into every rank's mailbox
+      const size_t o = peer_off_fg(t.peer.n, t.peer.fglen, (int)(t.peer.epoch & 1ull), t.peer.rank) + ((size_t)mode * 2) * ld + col;
+      for (int r = 0; r < t.peer.n; ++r) {
+        t.peer.box[r][o] = F;
+        t.peer.box[r][o + ld] = G;
+      }
+    } else {
+      t.slab_send[((size_t)mode * 2 + 0) * ld + col] = F;
+      t.slab_send[((size_t)mode * 2 + 1) * ld + col] = G;
+    }
   } else if (t.slab_phase == 2) {
     yp[0] = t.slab_outer[((size_t)mode * 2 + 0) * ld + col];
     xn[(size_t)(C - 1) * ld] = t.slab_outer[((size_t)mode * 2 + 1) * ld + col];
+  }
+  }
+  if (t.slab_phase == 1 && t.peer.n) {
+    // the block that finishes last publishes the epoch to every rank (k_slab_solve waits for it)
+    __shared__ bool last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(t.ticket, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence_system();
+    if (threadIdx.x == 0) *t.ticket = 0u;
+    if ((int)threadIdx.x < t.peer.n)
+      reinterpret_cast<volatile unsigned long long *>(t.peer.box[threadIdx.x] + peer_off_flagf(t.peer.n))[t.peer.rank] = t.peer.epoch;
   }
 }
 
@@ -1210,7 +1236,7 @@ void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, con
     hp.slab_send = (double *)dalloc(md, sizeof(double) * nmodes * 2 * row);
     hp.slab_yx = (double *)dalloc(md, sizeof(double) * nmodes * 2 * row);
   }
-  QG_CUDA(cudaMemset(hp.rowsum, 0, sizeof(double) * nmodes * hp.nyp));
+  
   {
     // the attribute belongs to the kernel, not to the plan: only ever raise it (an ocean and
     // an atmosphere plan of different lengths coexist in coupled models)
@@ -1248,6 +1274,7 @@ static TriArgs tri_args(HelmPlan &hp, double *wrk, size_t lsz, int nmodes) {
   t.ld = hp.ld; t.nyp = hp.nyp; t.nk = hp.nk; t.koff = hp.koff; t.nchunk = hp.nchunk;
   t.lastlen = hp.lastlen; t.nmodes = nmodes; t.row0 = hp.row0;
   t.use_yx = (hp.nchunk > 1 || hp.nranks > 1) ? 1 : 0; t.nranks = hp.nranks;
+  t.peer.n = 0; t.ticket = nullptr;
   t.slab_phase = 0; t.slab_send = hp.slab_send; t.slab_outer = hp.slab_yx; t.lsz = lsz; t.a = hp.a; t.ftnorm = hp.ftnorm; t.wrk = wrk;
   t.bcoef = hp.bcoef; t.binv = hp.binv; t.vl = hp.vl; t.vll = hp.vll; t.pt = hp.pt; t.fg = hp.fg; t.yx = hp.yx;
   return t;
@@ -1312,6 +1339,16 @@ void helm_solve_a(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
     QG_LAUNCH(md, "k_tri_fg", gl, 128, 0, kfg, t);
   }
   t.slab_phase = hp.nranks > 1 ? 1 : 0;
+  hp.slab_pushed = false;
+  if (hp.nranks > 1 && hp.nchunk > 1 && peer_active(md) && !env_int("QGCM_PEER_NOFUSE", 0)) {
+    // peer-memory transport: the interface kernel itself delivers the slab's first/last rows
+    t.peer = md->peer;
+    t.peer.epoch = ++md->epoch_fg;
+    t.ticket = md->d_ticket2;
+    hp.slab_peer = t.peer;
+    hp.slab_err = md->d_peer_err;
+    hp.slab_pushed = true;
+  }
   if (hp.nchunk > 1) QG_LAUNCH(md, "k_tri_reduced", gr, 128, 0, k_tri_reduced, t);
   if (hp.nranks > 1 && hp.nchunk == 1) {   // a one-chunk slab has no interface system to piggyback on
     SlabArgs sa = slab_args(hp, nmodes);
@@ -1344,9 +1381,22 @@ void helm_solve_b(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
     x.inverse = 1;
     QG_LAUNCH(md, "k_xform", gx, 256, hp.smem_bytes, k_xform, x);
   }
-  QG_LAUNCH(md, "k_zero_rows", (hp.nxp + 255) / 256, 256, 0, k_zero_rows, wrk, lsz, hp.ld, hp.nyp, hp.nxp, nmodes, hp.wall_s,
-            hp.wall_n);
+  // the wall rows of the work array stay zero from one ocean/atmosphere step to the next (the
+  // right-hand side kernel writes interior rows only); only homsol and qgcm_helmholtz fill them
+  if (hp.walls_dirty) {
+    QG_LAUNCH(md, "k_zero_rows", (hp.nxp + 255) / 256, 256, 0, k_zero_rows, wrk, lsz, hp.ld, hp.nyp, hp.nxp, nmodes, hp.wall_s,
+              hp.wall_n);
+    hp.walls_dirty = false;
+  }
   QG_CUDA(cudaGetLastError());
+}
+
+// zero the wall rows of every mode of a work array whose rows a caller has filled (homsol):
+// the time loop relies on them staying zero
+void helm_clean_walls(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
+  const size_t lsz = (size_t)hp.ld * hp.nyp;
+  QG_LAUNCH(md, "k_zero_rows", (hp.nxp + 255) / 256, 256, 0, k_zero_rows, wrk, lsz, hp.ld, hp.nyp, hp.nxp, nmodes, hp.wall_s, hp.wall_n);
+  hp.walls_dirty = false;
 }
 
 // in place on wrk[nmodes][nyp][ld]: rhs -> solution with zero boundary values (one GPU; the

@@ -124,6 +124,13 @@ struct ScalArgs {
   double *coef;
   // y-slabs (box ocean): cv[3] = xon(1), cv[4+m] = xinhom(m), already summed over the ranks
   const double *cv;
+  // y-slabs over peer memory: this kernel also forms the rank's share of xinhom(m) from the
+  // solved rows [lo, hi) and sums cv[3 .. 4+nl) over the ranks itself (k_inv_partials and the
+  // all-reduce that would follow it are folded in)
+  PeerCtx peer;
+  int *peer_err;
+  double *cvw;
+  int lo, hi;
 };
 
 // y-slabs: this rank's share of the xintp integrals of the modal solutions -> cv[4+m]
@@ -149,6 +156,14 @@ __global__ void __launch_bounds__(256) k_inv_scalars(ScalArgs a) {
   const double ecrit = 1.0e-13;
   double xinhom[NLMAX], ayis[NLMAX], ayin[NLMAX];
   double sums[NLMAX];
+  if (a.peer.n) {
+    for (int m = 0; m < nl; ++m) {
+      const double sm = block256_range_sum(a.rowsum + (size_t)m * nyp, a.lo, a.hi, red);
+      if (threadIdx.x == 0) a.cvw[4 + m] = sm * a.dx * a.dx;
+      __syncthreads();
+    }
+    peer_allreduce_block(a.peer, a.cvw + 3, 1 + nl, a.cvw + 3, a.peer_err);
+  }
   for (int m = 0; m < nl; ++m) sums[m] = a.cv ? 0.0 : block256_range_sum(a.rowsum + (size_t)m * nyp, 1, nyp - 1, red);
   if (threadIdx.x != 0) return;
   if (a.cv) s->xon[0] = a.cv[3];
@@ -293,6 +308,8 @@ static void inv_scalars_m2l(qgcm_model *m, bool atmos, const InvArgs &a) {
   s.sc = m->d_scal;
   s.coef = (double *)a.coef;
   s.cv = (!atmos && m->nranks > 1) ? m->d_cv : nullptr;
+  s.peer.n = 0; s.peer_err = m->d_peer_err; s.cvw = m->d_cv; s.lo = hp.row0; s.hi = hp.row0 + hp.nrows;
+  if (!atmos && m->nranks > 1) s.peer = peer_next_vec(m);
   QG_LAUNCH(m, "k_inv_scalars", 1, 256, 0, k_inv_scalars, s);
   dim3 gm((g.nxp + 255) / 256, g.nyp);
   QG_LAUNCH(m, "k_m2l", gm, 256, 0, k_m2l, a);
@@ -326,8 +343,10 @@ void ocinvq_phase_b(qgcm_model *m) {
   const Grid &g = m->go;
   HelmPlan &hp = m->hpo;
   helm_solve_b(m, hp, m->wrk_o, g.nl);
+  if (peer_active(m)) return;      // k_inv_scalars forms and all-reduces the integrals itself
+  PeerCtx none = {};
   QG_LAUNCH(m, "k_inv_partials", 1, 256, 0, k_inv_partials, hp.rowsum, g.nl, g.nyp, hp.row0, hp.row0 + hp.nrows, g.dx, m->d_cv,
-            peer_next_vec(m), m->d_peer_err);
+            none, m->d_peer_err);
 }
 void ocinvq_phase_c(qgcm_model *m) {
   InvArgs a;
@@ -433,6 +452,7 @@ static void homsol_channel(qgcm_model *m, bool atmos) {
     dim3 gf((g.nxp + 255) / 256, nyp);
     QG_LAUNCH(m, "k_fill_rows", gf, 256, 0, k_fill_rows, wrk, g.ld, nyp, g.nxp, d_row, 0.0, 1);
     QG_LAUNCH(m, "k_fill_rows", gf, 256, 0, k_fill_rows, wrk + g.lsz, g.ld, nyp, g.nxp, d_row + nyp, 0.0, 1);
+    hp.walls_dirty = true;
     helm_solve(m, hp, wrk, 2);
     double aip[2];
     for (int q = 0; q < 2; ++q) {
@@ -478,6 +498,7 @@ static void homsol_channel(qgcm_model *m, bool atmos) {
       for (int i = 0; i < hp.n; ++i) b[(size_t)q * hp.n + i] = bd2[i] - lc.rdm2[q];
     helm_set_diag(m, hp, b.data());
   }
+  helm_clean_walls(m, hp, wrk, nl);     // k_hom_finish wrote the channel profiles over the wall rows
   QG_CUDA(cudaMemcpy(m->d_scal, &s, sizeof(s), cudaMemcpyHostToDevice));
 }
 
@@ -491,6 +512,7 @@ void homsol_box_a(qgcm_model *m) {
   dim3 gf((g.nxp + 255) / 256, g.nyp);
   for (int q = 0; q < g.nl; ++q)
     QG_LAUNCH(m, "k_fill_rows", gf, 256, 0, k_fill_rows, m->wrk_o + q * g.lsz, g.ld, g.nyp, g.nxp, nullptr, 1.0, 0);
+  m->hpo.walls_dirty = true;
   helm_solve_a(m, m->hpo, m->wrk_o, g.nl);
 }
 void homsol_box_b(qgcm_model *m, std::vector<double> &share) {
@@ -523,6 +545,7 @@ void homsol_box_c(qgcm_model *m, const std::vector<double> &aipohs) {
     for (int mo = 1; mo <= nl - 1; ++mo)
       s.cdhoc[(k - 1) + (nl - 1) * (mo - 1)] = (lc.ctm2l[mo + nl * k] - lc.ctm2l[mo + nl * (k - 1)]) * s.aipohs[mo - 1];
   }
+  helm_clean_walls(m, m->hpo, m->wrk_o, nl);
   QG_CUDA(cudaMemcpy(m->d_scal, &s, sizeof(s), cudaMemcpyHostToDevice));
 }
 

@@ -154,6 +154,8 @@ struct HelmPlan {
   double *slab_ae = nullptr;   // [nmodes][nranks][2][ld] left-spike first/last values (alpha, eps) of every slab
   double *slab_fg = nullptr;   // [nranks][nmodes][2][ld] all-gathered first/last rows of the slab-local solutions
   double *slab_yx = nullptr;   // [nmodes][2][ld] true neighbour rows of this slab (Y of the slab below, X of the one above)
+  bool walls_dirty = true;     // someone wrote the wall rows of the work array (homsol, qgcm_helmholtz): zero them after the solve
+  bool slab_pushed = false;    // helm_solve_a already delivered the slab rows to the peers' mailboxes
   PeerCtx slab_peer = {};      // peer-memory transport: the gathered rows arrive in the mailbox, k_slab_solve waits for them
   int *slab_err = nullptr;
   double *rowsum = nullptr;  // [nmodes][nyp]  xintp row sums of the solution
@@ -367,6 +369,7 @@ void homsol_box_b(qgcm_model *m, std::vector<double> &share);
 void homsol_box_c(qgcm_model *m, const std::vector<double> &aipohs);
 void constr_ocean_share(qgcm_model *m, std::vector<double> &v);
 void constr_ocean_store(qgcm_model *m, const std::vector<double> &v);
+void helm_clean_walls(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes);
 void helm_solve_a(qgcm_model *m, HelmPlan &hp, double *wrk, int nmodes);
 void helm_solve_b(qgcm_model *m, HelmPlan &hp, double *wrk, int nmodes);
 

@@ -351,6 +351,7 @@ static void comm_allgather_slab(const Ranks &ms) {
   const size_t n = (size_t)m0->go.nl * 2 * m0->hpo.ld;
   if (peer_active(m0)) {
     // the rows go straight into every rank's mailbox; k_slab_solve waits for them there
+    if (m0->hpo.slab_pushed) return;      // k_tri_reduced has delivered them already
     PeerCtx c = m0->peer;
     c.epoch = ++m0->epoch_fg;
     m0->hpo.slab_peer = c;

@@ -198,6 +198,10 @@ class Model(CModel):
         blob = b"".join(handles)
         self._call("comm_init_peer", C.c_char_p(blob), C.c_int32(len(handles)))
 
+    def comm_close_peer(self):
+        """unmap the other ranks' mailboxes; barrier between this and close() (CUDA IPC rule)"""
+        self._call("comm_close_peer")
+
     def comm_transport(self, kind: str):
         self._call("comm_transport", C.c_int32({"nccl": 0, "peer": 1}[kind]))
 

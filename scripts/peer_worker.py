@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--case", default="box_dg")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--also-nccl", action="store_true", help="repeat over NCCL and compare (needs one GPU per rank)")
+    ap.add_argument("--stress", type=int, default=0, help="repeat the peer run this many times and count failures")
     args = ap.parse_args()
 
     import torch
@@ -84,6 +85,33 @@ def main():
                 raise RuntimeError("rank %d %s: %s differs from the oracle: %.3e" % (rank, label, name, e))
         return worst
 
+    if args.stress:
+        n = args.steps * p.nstr + 1
+        cpu.run(1, n)
+        bad = []
+        for it in range(args.stress):
+            m = make("peer")
+            dist.barrier()
+            try:
+                for nt in range(1, n + 1):
+                    m.run(nt, nt)
+                    m.sync()
+                    nf = [k for k in ("sst", "entoc", "qo", "po", "pom") if not np.isfinite(owned(k, m.get_field(k))).all()]
+                    if nf:
+                        sc = m.get_scalars().as_dict()
+                        raise RuntimeError("nt=%d non-finite %s xon=%s dpioc=%s xinhom=%s" % (nt, nf, sc["xon"][:1], sc["dpioc"][:2], sc["xinhom_oc"][:3]))
+                check(m, "stress %d" % it)
+            except RuntimeError as ex:
+                bad.append((it, str(ex)[-200:]))
+            dist.barrier()
+            m.comm_close_peer()
+            dist.barrier()
+            m.close()
+        print("STRESS rank %d: %d/%d failed %s" % (rank, len(bad), args.stress, bad[:4]), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
     m = make("peer")
     w0 = check(m, "peer init")
     n = args.steps * p.nstr + 1
@@ -105,6 +133,8 @@ def main():
         m2.close()
     print(msg, flush=True)
     dist.barrier()      # no rank unmaps a mailbox another rank may still be writing to
+    m.comm_close_peer()
+    dist.barrier()      # no rank frees a mailbox another rank still maps
     m.close()
     dist.destroy_process_group()
 
