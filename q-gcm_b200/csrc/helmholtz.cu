@@ -794,19 +794,105 @@ __global__ void __launch_bounds__(128, 3) k_tri_local(TriArgs t) {
   }
 }
 
+struct SlabArgs {
+  int ld, nk, koff, nchunk, lastlen, nmodes, nranks, rank;
+  int nrows_of[16];          // solved rows of every slab
+  double a;
+  const double *bcoef, *vl, *vll;
+  double *fg, *yx;
+  double *ae;                // [nmodes][nranks][2][ld]
+  double *send;              // [nmodes][2][ld]
+  const double *all;         // [nranks][nmodes][2][ld]
+  double *outer;             // [nmodes][2][ld]
+  PeerCtx peer;              // peer-memory transport: `all` is this rank's mailbox, filled by the peers' k_slab_push
+  int *peer_err;
+};
+
+// y-slab coupling, per wavenumber column (the comment block "y-slab coupling" below explains
+// the algebra).  The inter-slab system, the neighbour rows of this slab, and their effect on the
+// first/last chunk's f, g.  Interface i (between slabs i-1 and i) couples Y_{i-1} and X_i:
+//   Y_{i-1} - alpha_{i-1} X_i = G_{i-1} + eps_{i-1} Y_{i-2},   X_i - alpha_i Y_{i-1} = F_i + eps_i X_{i+1}
+// which is an interleaved tridiagonal system: one forward sweep expressing
+// Y_{i-1} = P_i + Q_i X_{i+1}, X_i = xc_i + xq_i X_{i+1}, one back substitution.
+// peer-memory transport: the rows of every rank must have landed in the mailbox (whole block)
+__device__ __forceinline__ void slab_wait(const SlabArgs &t) {
+  if (t.peer.n) {
+    if ((int)threadIdx.x < t.peer.n)
+      peer_wait(reinterpret_cast<const volatile unsigned long long *>(t.peer.box[t.peer.rank] + peer_off_flagf(t.peer.n)) + threadIdx.x,
+                t.peer.epoch, t.peer_err);
+    __syncthreads();
+    __threadfence_system();
+  }
+}
+__device__ __forceinline__ void slab_solve_col(const SlabArgs &t, int s, int mode) {
+  const int col = t.koff + s, N = t.nranks, ld = t.ld;
+  double xc[8], xq[8], P[8], Q[8];
+  double Pp = 0.0, Qp = 0.0;
+#pragma unroll
+  for (int i = 1; i < 8; ++i) {
+    if (i < N) {
+      const double a_lo = t.ae[(((size_t)mode * N + i - 1) * 2 + 0) * ld + col], e_lo = t.ae[(((size_t)mode * N + i - 1) * 2 + 1) * ld + col];
+      const double a_hi = t.ae[(((size_t)mode * N + i) * 2 + 0) * ld + col], e_hi = t.ae[(((size_t)mode * N + i) * 2 + 1) * ld + col];
+      const double G = __ldcg(t.all + (((size_t)(i - 1) * t.nmodes + mode) * 2 + 1) * ld + col);
+      const double F = __ldcg(t.all + (((size_t)i * t.nmodes + mode) * 2 + 0) * ld + col);
+      const double gp = G + e_lo * Pp, A = a_lo + e_lo * Qp;
+      const double den = 1.0 / (1.0 - a_hi * A);
+      xc[i] = (F + a_hi * gp) * den;
+      xq[i] = e_hi * den;
+      P[i] = gp + A * xc[i];
+      Q[i] = A * xq[i];
+      Pp = P[i];
+      Qp = Q[i];
+    }
+  }
+  double xnext_run = 0.0, yprev = 0.0, xnext = 0.0;
+#pragma unroll
+  for (int i = 7; i >= 1; --i) {
+    if (i < N) {
+      const double X = xc[i] + xq[i] * xnext_run;      // X_i
+      const double Y = P[i] + Q[i] * xnext_run;        // Y_{i-1}
+      if (i == t.rank) yprev = Y;
+      if (i == t.rank + 1) xnext = X;
+      xnext_run = X;
+    }
+  }
+  t.outer[((size_t)mode * 2 + 0) * ld + col] = yprev;
+  t.outer[((size_t)mode * 2 + 1) * ld + col] = xnext;
+  // neighbour rows act on the first chunk through its left spike and on the last chunk
+  // through its right spike (mirror of its left spike)
+  const int C = t.nchunk;
+  if (C > 1) {
+    const size_t fb = ((size_t)mode * 2 * C) * ld + col, tb = ((size_t)mode * TRI_L) * ld + col;
+    const double alpha = t.vl[tb], eps = t.vl[tb + (size_t)(TRI_L - 1) * ld];
+    const double alphal = t.vll[tb], epsl = t.vll[tb + (size_t)(t.lastlen - 1) * ld];
+    t.fg[fb] += yprev * alpha;
+    t.fg[fb + (size_t)C * ld] += yprev * eps;
+    t.fg[fb + (size_t)(C - 1) * ld] += xnext * epsl;
+    t.fg[fb + (size_t)(C + C - 1) * ld] += xnext * alphal;
+  }
+}
+
 // interface system: one thread per (column, mode), block Thomas over the chunks.  All
 // loads are independent of the recurrence (separate output array), so they pipeline.
-__global__ void __launch_bounds__(128) k_tri_reduced(TriArgs t) {
+__global__ void __launch_bounds__(128) k_tri_reduced(TriArgs t, SlabArgs sa) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int mode = blockIdx.y;
+  if (t.slab_phase == 2) {
+    // y-slabs, second pass: first the inter-slab system of this column (it fixes the outer
+    // neighbours and adds their effect to the first/last chunk's f, g), then the chunk
+    // interfaces again -- one launch for what used to be k_slab_solve + k_tri_reduced
+    slab_wait(sa);
+    if (s < t.nk) slab_solve_col(sa, s, mode);
+  }
   if (s < t.nk) {
   const int col = t.koff + s;
   const int C = t.nchunk, ld = t.ld;
   const size_t tb = ((size_t)mode * TRI_L) * ld + col;
   const double alpha = t.vl[tb], eps = t.vl[tb + (size_t)(TRI_L - 1) * ld], alphal = t.vll[tb];
   const size_t fb = ((size_t)mode * 2 * C) * ld + col;
-  const double *__restrict__ f = t.fg + fb;
-  const double *__restrict__ g = t.fg + fb + (size_t)C * ld;
+  // (not __restrict__: on y-slabs the inter-slab solve above has just updated four of these values)
+  const double *f = t.fg + fb;
+  const double *g = t.fg + fb + (size_t)C * ld;
   double *__restrict__ yp = t.yx + fb;
   double *__restrict__ xn = t.yx + fb + (size_t)C * ld;
   const double *__restrict__ pt = t.pt + ((size_t)mode * 2 * C) * ld + col;   // p_c
@@ -907,20 +993,6 @@ __global__ void __launch_bounds__(128) k_tri_reduced(TriArgs t) {
 // spike is its mirror image).  F, G are all-gathered (2 rows per mode and rank), every rank
 // solves the 2*nranks unknowns per wavenumber redundantly and keeps its neighbours' rows.
 // --------------------------------------------------------------------------------------
-struct SlabArgs {
-  int ld, nk, koff, nchunk, lastlen, nmodes, nranks, rank;
-  int nrows_of[16];          // solved rows of every slab
-  double a;
-  const double *bcoef, *vl, *vll;
-  double *fg, *yx;
-  double *ae;                // [nmodes][nranks][2][ld]
-  double *send;              // [nmodes][2][ld]
-  const double *all;         // [nranks][nmodes][2][ld]
-  double *outer;             // [nmodes][2][ld]
-  PeerCtx peer;              // peer-memory transport: `all` is this rank's mailbox, filled by the peers' k_slab_push
-  int *peer_err;
-};
-
 // alpha_s = -a (T^-1)_{00}, eps_s = -a (T^-1)_{n-1,0}: one forward elimination per slab length
 __global__ void k_slab_spikes(SlabArgs t) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x, mode = blockIdx.y;
@@ -962,60 +1034,10 @@ __global__ void k_slab_fg(SlabArgs t) {
 // which is an interleaved tridiagonal system: one forward sweep expressing
 // Y_{i-1} = P_i + Q_i X_{i+1}, X_i = xc_i + xq_i X_{i+1}, one back substitution.
 __global__ void k_slab_solve(SlabArgs t) {
-  if (t.peer.n) {      // the rows of every rank must have landed in the mailbox
-    if ((int)threadIdx.x < t.peer.n)
-      peer_wait(reinterpret_cast<const volatile unsigned long long *>(t.peer.box[t.peer.rank] + peer_off_flagf(t.peer.n)) + threadIdx.x,
-                t.peer.epoch, t.peer_err);
-    __syncthreads();
-    __threadfence_system();
-  }
+  slab_wait(t);
   const int s = blockIdx.x * blockDim.x + threadIdx.x, mode = blockIdx.y;
   if (s >= t.nk) return;
-  const int col = t.koff + s, N = t.nranks, ld = t.ld;
-  double xc[8], xq[8], P[8], Q[8];
-  double Pp = 0.0, Qp = 0.0;
-#pragma unroll
-  for (int i = 1; i < 8; ++i) {
-    if (i < N) {
-      const double a_lo = t.ae[(((size_t)mode * N + i - 1) * 2 + 0) * ld + col], e_lo = t.ae[(((size_t)mode * N + i - 1) * 2 + 1) * ld + col];
-      const double a_hi = t.ae[(((size_t)mode * N + i) * 2 + 0) * ld + col], e_hi = t.ae[(((size_t)mode * N + i) * 2 + 1) * ld + col];
-      const double G = __ldcg(t.all + (((size_t)(i - 1) * t.nmodes + mode) * 2 + 1) * ld + col);
-      const double F = __ldcg(t.all + (((size_t)i * t.nmodes + mode) * 2 + 0) * ld + col);
-      const double gp = G + e_lo * Pp, A = a_lo + e_lo * Qp;
-      const double den = 1.0 / (1.0 - a_hi * A);
-      xc[i] = (F + a_hi * gp) * den;
-      xq[i] = e_hi * den;
-      P[i] = gp + A * xc[i];
-      Q[i] = A * xq[i];
-      Pp = P[i];
-      Qp = Q[i];
-    }
-  }
-  double xnext_run = 0.0, yprev = 0.0, xnext = 0.0;
-#pragma unroll
-  for (int i = 7; i >= 1; --i) {
-    if (i < N) {
-      const double X = xc[i] + xq[i] * xnext_run;      // X_i
-      const double Y = P[i] + Q[i] * xnext_run;        // Y_{i-1}
-      if (i == t.rank) yprev = Y;
-      if (i == t.rank + 1) xnext = X;
-      xnext_run = X;
-    }
-  }
-  t.outer[((size_t)mode * 2 + 0) * ld + col] = yprev;
-  t.outer[((size_t)mode * 2 + 1) * ld + col] = xnext;
-  // neighbour rows act on the first chunk through its left spike and on the last chunk
-  // through its right spike (mirror of its left spike)
-  const int C = t.nchunk;
-  if (C > 1) {
-    const size_t fb = ((size_t)mode * 2 * C) * ld + col, tb = ((size_t)mode * TRI_L) * ld + col;
-    const double alpha = t.vl[tb], eps = t.vl[tb + (size_t)(TRI_L - 1) * ld];
-    const double alphal = t.vll[tb], epsl = t.vll[tb + (size_t)(t.lastlen - 1) * ld];
-    t.fg[fb] += yprev * alpha;
-    t.fg[fb + (size_t)C * ld] += yprev * eps;
-    t.fg[fb + (size_t)(C - 1) * ld] += xnext * epsl;
-    t.fg[fb + (size_t)(C + C - 1) * ld] += xnext * alphal;
-  }
+  slab_solve_col(t, s, mode);
 }
 
 // after the second interface solve: the outermost neighbours are the adjacent slabs' rows
@@ -1349,7 +1371,7 @@ void helm_solve_a(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
     hp.slab_err = md->d_peer_err;
     hp.slab_pushed = true;
   }
-  if (hp.nchunk > 1) QG_LAUNCH(md, "k_tri_reduced", gr, 128, 0, k_tri_reduced, t);
+  if (hp.nchunk > 1) QG_LAUNCH(md, "k_tri_reduced", gr, 128, 0, k_tri_reduced, t, slab_args(hp, nmodes));
   if (hp.nranks > 1 && hp.nchunk == 1) {   // a one-chunk slab has no interface system to piggyback on
     SlabArgs sa = slab_args(hp, nmodes);
     QG_LAUNCH(md, "k_slab_fg", gr, 128, 0, k_slab_fg, sa);
@@ -1364,12 +1386,13 @@ void helm_solve_b(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
   dim3 gl((hp.nk + 127) / 128, hp.nchunk, nmodes), gr((hp.nk + 127) / 128, nmodes);
   if (hp.nranks > 1) {
     SlabArgs sa = slab_args(hp, nmodes);
-    QG_LAUNCH(md, "k_slab_solve", gr, 128, 0, k_slab_solve, sa);
     t.slab_phase = 2;
-    if (hp.nchunk > 1)
-      QG_LAUNCH(md, "k_tri_reduced", gr, 128, 0, k_tri_reduced, t);
-    else
+    if (hp.nchunk > 1) {
+      QG_LAUNCH(md, "k_tri_reduced", gr, 128, 0, k_tri_reduced, t, sa);      // includes the inter-slab solve
+    } else {
+      QG_LAUNCH(md, "k_slab_solve", gr, 128, 0, k_slab_solve, sa);
       QG_LAUNCH(md, "k_slab_outer", gr, 128, 0, k_slab_outer, sa);
+    }
   }
   auto kfin = k_tri_local<true>;
   QG_LAUNCH(md, "k_tri_local", gl, 128, 0, kfin, t);

@@ -156,12 +156,35 @@ __global__ void __launch_bounds__(256) k_inv_scalars(ScalArgs a) {
   const double ecrit = 1.0e-13;
   double xinhom[NLMAX], ayis[NLMAX], ayin[NLMAX];
   double sums[NLMAX];
+  // box: the scalar state the constraint algebra needs is fetched before the sums (and the
+  // all-reduce of the y-slab ranks), so that its latency hides behind them
+  double dpi0[NLMAX], dpip0[NLMAX], cdf[NLMAX * NLMAX], cdh[NLMAX * NLMAX], xon_own = 0.0;
+  if (threadIdx.x == 0 && !a.cyclic) {
+    xon_own = s->xon[0];
+    for (int k = 0; k < nl - 1; ++k) { dpi0[k] = s->dpioc[k]; dpip0[k] = s->dpiocp[k]; }
+    for (int i = 0; i < nl * (nl - 1); ++i) cdf[i] = s->cdiffo[i];
+    for (int i = 0; i < (nl - 1) * (nl - 1); ++i) cdh[i] = s->cdhoc[i];
+  }
   if (a.peer.n) {
+    // the three modal integrals together: one pass over the row sums, one block reduction
+    double sm[NLMAX];
     for (int m = 0; m < nl; ++m) {
-      const double sm = block256_range_sum(a.rowsum + (size_t)m * nyp, a.lo, a.hi, red);
-      if (threadIdx.x == 0) a.cvw[4 + m] = sm * a.dx * a.dx;
-      __syncthreads();
+      double acc = 0.0;
+      for (int i = a.lo + (int)threadIdx.x; i < a.hi; i += 256) acc += a.rowsum[(size_t)m * nyp + i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+      sm[m] = acc;
     }
+    __shared__ double red3[NLMAX][8];
+    if ((threadIdx.x & 31) == 0)
+      for (int m = 0; m < nl; ++m) red3[m][threadIdx.x >> 5] = sm[m];
+    __syncthreads();
+    if ((int)threadIdx.x < nl) {
+      double t = 0.0;
+      for (int i = 0; i < 8; ++i) t += red3[threadIdx.x][i];
+      a.cvw[4 + threadIdx.x] = t * a.dx * a.dx;
+    }
+    __syncthreads();
     peer_allreduce_block(a.peer, a.cvw + 3, 1 + nl, a.cvw + 3, a.peer_err);
   }
   for (int m = 0; m < nl; ++m) sums[m] = a.cv ? 0.0 : block256_range_sum(a.rowsum + (size_t)m * nyp, 1, nyp - 1, red);
@@ -170,24 +193,27 @@ __global__ void __launch_bounds__(256) k_inv_scalars(ScalArgs a) {
   for (int m = 0; m < nl; ++m) {
     const double sump = sums[m];
     xinhom[m] = a.cv ? a.cv[4 + m] : sump * a.dx * a.dx;   // boundary rows are exactly zero
-    ayis[m] = a.rowsum[m * nyp + 1];              // dx/dy = 1
-    ayin[m] = -a.rowsum[m * nyp + nyp - 2];
+    if (a.cyclic) {
+      ayis[m] = a.rowsum[m * nyp + 1];              // dx/dy = 1
+      ayin[m] = -a.rowsum[m * nyp + nyp - 2];
+    }
     if (a.atmos) s->xinhom_at[m] = xinhom[m]; else s->xinhom_oc[m] = xinhom[m];
   }
   if (!a.cyclic) {
     // finite box: mass constraints (src/ocisubs.F:333-370)
     double aient[NLMAX], rhs[NLMAX], hclco[NLMAX];
-    aient[0] = s->xon[0];
+    aient[0] = a.cv ? a.cv[3] : xon_own;
     for (int k = 1; k < nl - 1; ++k) aient[k] = 0.0;
     for (int k = 0; k < nl - 1; ++k) {
-      const double aitmp = s->dpioc[k];
-      s->dpioc[k] = s->dpiocp[k] - a.tdt * a.gp[k] * aient[k];
+      const double aitmp = dpi0[k];
+      const double dnew = dpip0[k] - a.tdt * a.gp[k] * aient[k];
+      s->dpioc[k] = dnew;
       s->dpiocp[k] = aitmp;
       double rhsum = 0.0;
-      for (int m = 0; m < nl; ++m) rhsum = rhsum + s->cdiffo[m + nl * k] * xinhom[m];
-      rhs[k] = s->dpioc[k] - rhsum;
+      for (int m = 0; m < nl; ++m) rhsum = rhsum + cdf[m + nl * k] * xinhom[m];
+      rhs[k] = dnew - rhsum;
     }
-    lu_solve_refine(s->cdhoc, nl - 1, rhs, hclco);
+    lu_solve_refine(cdh, nl - 1, rhs, hclco);
     for (int k = 0; k < nl - 1; ++k) a.coef[k] = hclco[k];
     return;
   }

@@ -331,10 +331,15 @@ __device__ void oml_monitors(const OmlArgs &a, double (*red)[8]) {
 // slice; the block that finishes last (ticket counter) adds the ORB slice sums in index
 // order -- deterministic -- and also evaluates the boundary monitors.
 constexpr int ORB = 64;
-__global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy) {
+// On decks with boundary heat-flux monitors one extra block evaluates them alongside.
+__global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy, int nred) {
   __shared__ double red[6][8];
   __shared__ bool last;
-  const int per = (a.nblocks + (int)gridDim.x - 1) / (int)gridDim.x;
+  if ((int)blockIdx.x >= nred) {       // the monitors only read the old fields: they run beside the reduction
+    oml_monitors(a, red);
+    return;
+  }
+  const int per = (a.nblocks + nred - 1) / nred;
   const int b0 = blockIdx.x * per, b1 = min(a.nblocks, b0 + per);
   double s[3] = {0.0, 0.0, 0.0};
   for (int q = 0; q < 3; ++q)
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy) {
       a.part2[q * ORB + blockIdx.x] = t;
     }
     __threadfence();
-    last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+    last = (atomicAdd(a.ticket, 1u) == (unsigned int)nred - 1u);
   }
   __syncthreads();
   if (!last) return;
@@ -362,7 +367,7 @@ __global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy) {
     *a.ticket = 0u;
     double t[3] = {0.0, 0.0, 0.0};
     for (int q = 0; q < 3; ++q)
-      for (int i = 0; i < (int)gridDim.x; ++i) t[q] += a.part2[q * ORB + i];
+      for (int i = 0; i < nred; ++i) t[q] += a.part2[q * ORB + i];
     a.cv[0] = t[0];                         // xfosum, read by k_oml_entoc (after the all-reduce on slabs)
     a.cv[1] = t[1];
     a.cv[2] = t[2];
@@ -375,7 +380,6 @@ __global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy) {
     __syncthreads();
     peer_allreduce_block(a.peer, a.cv, 3, a.cv, a.peer_err);
   }
-  if (a.sb || a.nb) oml_monitors(a, red);
 }
 
 // entoc = 4-point average of (xfo - mean) with the edge/corner rules (omlsubs.F:151-205);
@@ -543,7 +547,8 @@ void oml_phase_a(qgcm_model *m) {
   }
   a.peer = peer_next_vec(m);    // y-slabs over peer memory: the reduction all-reduces its sums itself
   // one block per 2048 partials (the marching kernel leaves a few hundred), at most ORB
-  QG_LAUNCH(m, "k_oml_reduce", std::min(ORB, (a.nblocks + 2047) / 2048), 256, 0, k_oml_reduce, a, g.dx * g.dx);
+  const int nred = std::min(ORB, (a.nblocks + 2047) / 2048);
+  QG_LAUNCH(m, "k_oml_reduce", nred + ((a.sb || a.nb) ? 1 : 0), 256, 0, k_oml_reduce, a, g.dx * g.dx, nred);
 }
 
 // entoc from xfo minus the global mean, its integral (y-slabs: the rank's share in d_cv[3])
