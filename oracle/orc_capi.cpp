@@ -90,6 +90,16 @@ int orc_atmos_step(Model *m) {
 }
 int orc_run(Model *m, int64_t a, int64_t b) { ORC_TRY(m->run(a, b)); }
 int orc_valids(Model *m, qgcm_valids_report *r) { ORC_TRY(m->valids(r)); }
+int orc_tavini(Model *m) { ORC_TRY(m->tavini(3)); }
+int orc_tavatm(Model *m) { ORC_TRY(m->tavatm()); }
+int orc_tavocn(Model *m) { ORC_TRY(m->tavocn()); }
+int orc_avg_ocn_k247(Model *m) { ORC_TRY(m->avg_ocn_k247()); }
+int orc_tav_counts(Model *m, int32_t *nsumat, int32_t *nsumoc, int32_t *nsum_ocavg) {
+  *nsumat = m->nsumat;
+  *nsumoc = m->nsumoc;
+  *nsum_ocavg = m->nsum_ocavg;
+  return 0;
+}
 
 // transform primitives, for pinning against scipy.fft (tests/test_oracle_fft.py)
 int orc_rfftf(int n, double *r) {

@@ -45,6 +45,11 @@ struct Model {
   // xforc module storage (src/xfosubs.F:43-46)
   vec stbbb, stbus, stbun, stbvs, stbvn;  // bicubic weights (bcuini)
   bool bcu_ready = false;
+  // running sums of src/timavge.F:46-85 (allocated by tavini)
+  vec txatav, tyatav, wtatav, fmatav, astav, patav, qatav, uufa, tufa, utufa, vvfa, tvfa, vtvfa;
+  vec txocav, tyocav, wpocav, wtocav, fmocav, sstav, pocav, qocav, uufo, tufo, utufo, vvfo, tvfo, vtvfo;
+  vec po_avg;
+  int nsumat = 0, nsumoc = 0, nsum_ocavg = 0;
   qgcm_scalars s;
 
   explicit Model(const qgcm_config &cfg);
@@ -93,6 +98,11 @@ struct Model {
   void qcomp_atmos();
   // src/valsubs.F
   void valids(qgcm_valids_report *rep);
+  // src/timavge.F
+  void tavini(int which = 3);
+  void tavatm();
+  void tavocn();
+  void avg_ocn_k247();
   void run(int64_t nt_first, int64_t nt_last);
 };
 

@@ -120,6 +120,9 @@ vec *Model::field(const std::string &n) {
   F(pa) F(pam) F(qa) F(qam) F(wekpa) F(wekta) F(entat) F(ddynat) F(dtopat) F(xc1ast)
   F(ast) F(astm) F(astbar) F(hmixa) F(hmixam) F(tauxa) F(tauya) F(fnetat) F(uekat) F(vekat)
   F(pch1at) F(pch2at) F(pbhat)
+  F(txatav) F(tyatav) F(wtatav) F(fmatav) F(astav) F(patav) F(qatav) F(uufa) F(tufa) F(utufa) F(vvfa) F(tvfa) F(vtvfa)
+  F(txocav) F(tyocav) F(wpocav) F(wtocav) F(fmocav) F(sstav) F(pocav) F(qocav) F(uufo) F(tufo) F(utufo) F(vvfo) F(tvfo)
+  F(vtvfo) F(po_avg)
 #undef F
   return nullptr;
 }

@@ -1,0 +1,29 @@
+#!/bin/bash
+# One gpurun call that validates a build: GPU parity tests, the default bench line, the ncu
+# launch list of the same command and one `ncu --set full` capture of the main kernels.
+#   gpurun --timeout 1200 -- 'bash scripts/gpu_validate.sh [tag]'
+# Outputs go to gpurun_out/<tag>_*; nothing measured under ncu is a bench value.
+tag=${1:-val}
+out=gpurun_out
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/${tag}_smi.txt 2>&1
+if [ "${SKIP_TESTS:-0}" != "1" ]; then
+  timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1
+  echo "pytest rc=$?" >> $out/${tag}_pytest.log
+  tail -3 $out/${tag}_pytest.log
+fi
+timeout 600 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
+echo "bench rc=$?"; cut -c1-400 $out/${tag}_bench_n1.json
+if [ "${SKIP_NCU:-0}" != "1" ]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+    --log-file $out/${tag}_launches_raw.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e \
+    > $out/${tag}_ncu_list.log 2>&1
+  echo "ncu list rc=$?"
+  # init launches ~ 40; skip into the steady step loop, capture one step's worth of every main kernel
+  timeout 900 ncu --set full --clock-control none --import-source on \
+    -k 'regex:k_dst3|k_qgstep|k_oml_march|k_oml_entoc|k_l2m|k_m2l|k_tri_local|k_tri_reduced' \
+    --launch-skip ${NCU_SKIP:-40} -c ${NCU_COUNT:-14} -o $out/${tag}_full -f \
+    python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > $out/${tag}_ncu_full.log 2>&1
+  echo "ncu full rc=$?"
+fi
+ls -la $out | tail -15
