@@ -40,7 +40,8 @@ enum {
   QGCM_CYCLIC_OCEAN = 1 << 2,   /* -Dcyclic_ocean */
   QGCM_SB_HFLUX     = 1 << 3,   /* -Dsb_hflux     */
   QGCM_NB_HFLUX     = 1 << 4,   /* -Dnb_hflux     */
-  QGCM_TAU_UDIFF    = 1 << 5    /* -Dtau_udiff    */
+  QGCM_TAU_UDIFF    = 1 << 5,   /* -Dtau_udiff    */
+  QGCM_OCNC_AVG_K247 = 1 << 6   /* -Docnc_avg_k247: qgcm_run accumulates po after every ocean step */
 };
 
 /*
@@ -261,6 +262,30 @@ typedef struct qgcm_valids_report {
   double hfbad[QGCM_NLMAX];                                /* % of the area thinner than thkmin, per layer */
 } qgcm_valids_report;
 int qgcm_valids(qgcm_model *m, qgcm_valids_report *rep);
+
+/* ---- device-side running sums and packed output ------------
+ *
+ * tavini / tavatm / tavocn, src/timavge.F:108-617, and the fork's avg_ocn_k247 (:624-660,
+ * called after every ocean step, src/q-gcm.F:1250-1252): the sums stay in HBM under the
+ * reference's array names -- "txocav","tyocav","wpocav","wtocav","fmocav","sstav","uufo",
+ * "tufo","utufo","vvfo","tvfo","vtvfo","pocav","qocav","po_avg" and the atmosphere twins
+ * "txatav","tyatav","wtatav","fmatav","astav","uufa","tufa","utufa","vvfa","tvfa","vtvfa",
+ * "patav","qatav" (shapes as declared at src/timavge.F:46-85) -- and are read with
+ * qgcm_get_field when tavout (src/timavge.F:667) needs them, so that the daily accumulation
+ * (src/q-gcm.F:1477-1482) does not download the state.  The sums are allocated on first use;
+ * qgcm_tavini zeroes them and the contribution counts nsumat, nsumoc, nsum_ocavg. */
+int qgcm_tavini(qgcm_model *m);
+int qgcm_tavatm(qgcm_model *m);
+int qgcm_tavocn(qgcm_model *m);
+int qgcm_avg_ocn_k247(qgcm_model *m);
+int qgcm_tav_counts(qgcm_model *m, int32_t *nsumat, int32_t *nsumoc, int32_t *nsum_ocavg);
+/* The sub-sampled vector that ocnc_out / atnc_out hand to nf_put_vara_double
+ * (src/nc_subs.F:869-890, :906-917, :1110-1130): host(i,j,k) = field(1+(i-1)*nsk, 1+(j-1)*nsk, k)
+ * with iw = min(mod(nx,nsk),1) + (nx-mod(nx,nsk))/nsk points per direction, packed on the
+ * device so that an output step moves 1/nsk^2 of the field over PCIe.  Any gridded field
+ * name of qgcm_get_field; n must equal the count qgcm_field_sub_size returns. */
+int qgcm_field_sub_size(qgcm_model *m, const char *name, int32_t nsk, int64_t *n);
+int qgcm_get_field_sub(qgcm_model *m, const char *name, int32_t nsk, double *host, int64_t n);
 
 /* ---- instrumentation ---------------------------------------------------------- */
 

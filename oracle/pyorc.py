@@ -38,6 +38,24 @@ class Oracle(qg.CModel):
         super().__init__(lib(), "orc_", cfg)
 
 
+def subsample(field, nsk):
+    """the wrk vector of ocnc_out / atnc_out (src/nc_subs.F:869-890): wrk(i + iw*(j-1) + iw*jw*(k-1)) =
+    f(1+(i-1)*nsk, 1+(j-1)*nsk, k) with iw = min(mod(nx,nsk),1) + (nx-mod(nx,nsk))/nsk; `field` is the
+    Fortran-shaped array (nx, ny[, nl])"""
+    f = np.asarray(field)
+    if f.ndim == 2:
+        f = f[:, :, None]
+    nx, ny, nl = f.shape
+    iw = min(nx % nsk, 1) + (nx - nx % nsk) // nsk
+    jw = min(ny % nsk, 1) + (ny - ny % nsk) // nsk
+    wrk = np.empty(iw * jw * nl)
+    for k in range(nl):
+        for j in range(jw):
+            for i in range(iw):
+                wrk[i + iw * j + iw * jw * k] = f[i * nsk, j * nsk, k]
+    return wrk
+
+
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 

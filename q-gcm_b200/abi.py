@@ -18,6 +18,7 @@ FLAGS = {
     "sb_hflux": 1 << 3,
     "nb_hflux": 1 << 4,
     "tau_udiff": 1 << 5,
+    "ocnc_avg_k247": 1 << 6,
 }
 
 

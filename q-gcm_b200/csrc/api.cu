@@ -67,7 +67,7 @@ void launch_check(qgcm_model *m, const char *name) {
   throw std::runtime_error(std::string("kernel ") + name + ": " + cudaGetErrorString(e));
 }
 
-static void add_field(qgcm_model *m, const char *name, int nx, int ny, int nl, int ld, size_t lsz = 0, const Grid *slab = nullptr) {
+void add_field(qgcm_model *m, const char *name, int nx, int ny, int nl, int ld, size_t lsz, const Grid *slab) {
   qgcm_model::Field f;
   f.nx = nx; f.ny = ny; f.nl = nl; f.ld = ld; f.lsz = lsz;
   f.nyg = ny; f.joff = 0; f.o0 = 0; f.o1 = ny;
@@ -461,7 +461,10 @@ int qgcm_run(qgcm_model *m, int64_t nt_first, int64_t nt_last) {
       const bool ocstep = (nstr == 1) ? true : (nt % nstr == 1);
       if (ocstep) {
         if (m->has_atmos) launch_xforc(m);
-        if (m->has_ocean) ocean_step(m);
+        if (m->has_ocean) {
+          ocean_step(m);
+          if (m->flags & QGCM_OCNC_AVG_K247) launch_avg_ocn_k247(m);   // src/q-gcm.F:1250-1252
+        }
       }
       if (m->has_atmos) atmos_step(m);
       if (m->has_ocean && ((nt - 1) % (25 * (int64_t)nstr) == 0)) slab_tlavg_ocean(ranks_of(m));
@@ -494,6 +497,18 @@ int qgcm_comm_close_peer(qgcm_model *m) {
 }
 
 int qgcm_valids(qgcm_model *m, qgcm_valids_report *rep) { QG_TRY(launch_valids(m, rep)); }
+
+int qgcm_tavini(qgcm_model *m) { QG_TRY(launch_tavini(m)); }
+int qgcm_tavocn(qgcm_model *m) { QG_TRY(launch_tavocn(m)); }
+int qgcm_tavatm(qgcm_model *m) { QG_TRY(launch_tavatm(m)); }
+int qgcm_avg_ocn_k247(qgcm_model *m) { QG_TRY(launch_avg_ocn_k247(m)); }
+int qgcm_tav_counts(qgcm_model *m, int32_t *nsumat, int32_t *nsumoc, int32_t *nsum_ocavg) {
+  QG_TRY(*nsumat = m->nsumat; *nsumoc = m->nsumoc; *nsum_ocavg = m->nsum_ocavg);
+}
+int qgcm_field_sub_size(qgcm_model *m, const char *name, int32_t nsk, int64_t *n) { QG_TRY(field_sub_size(m, name, nsk, n)); }
+int qgcm_get_field_sub(qgcm_model *m, const char *name, int32_t nsk, double *host, int64_t n) {
+  QG_TRY(get_field_sub(m, name, nsk, host, n));
+}
 
 int64_t qgcm_launch_count(qgcm_model *m) { return m ? m->launches : 0; }
 

@@ -220,6 +220,10 @@ struct qgcm_model {
   double *d_cv = nullptr;                // [32] reduction payload
   unsigned int *d_ticket = nullptr;      // last-block-done counters
   double *d_val = nullptr;               // valids: per-block partials
+  // running sums of src/timavge.F (timavg.cu): contribution counts; packing buffer of qgcm_get_field_sub
+  int nsumat = 0, nsumoc = 0, nsum_ocavg = 0;
+  double *d_pack = nullptr;
+  size_t pack_elems = 0;
   bool shared_stream = false;            // loopback ranks > 0 borrow rank 0's stream
   // peer-memory transport (slab.cu): own mailbox, peers' mapped mailboxes, exchange counters
   double *mailbox = nullptr;
@@ -334,6 +338,14 @@ void launch_atqzbd(qgcm_model *m, double *q, const double *p);
 void launch_tlavg_atmos(qgcm_model *m);
 void launch_xforc(qgcm_model *m);
 void launch_valids(qgcm_model *m, qgcm_valids_report *rep);
+// timavg.cu
+void add_field(qgcm_model *m, const char *name, int nx, int ny, int nl, int ld, size_t lsz = 0, const Grid *slab = nullptr);
+void launch_tavini(qgcm_model *m);
+void launch_tavocn(qgcm_model *m);
+void launch_tavatm(qgcm_model *m);
+void launch_avg_ocn_k247(qgcm_model *m);
+void field_sub_size(qgcm_model *m, const char *name, int nsk, int64_t *n);
+void get_field_sub(qgcm_model *m, const char *name, int nsk, double *host, int64_t n);
 
 // slab.cu: y-slab multi-GPU drivers.  `ms` is the set of ranks this process drives: one model
 // with an NCCL communicator, or every rank of an in-process loopback group.

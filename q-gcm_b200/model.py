@@ -138,6 +138,18 @@ class CModel:
         self._call("valids", C.byref(r))
         return r
 
+    # -- running sums of src/timavge.F (read them with get_field under the reference's names)
+    def tavini(self): self._call("tavini")
+    def tavatm(self): self._call("tavatm")
+    def tavocn(self): self._call("tavocn")
+    def avg_ocn_k247(self): self._call("avg_ocn_k247")
+
+    def tav_counts(self):
+        """(nsumat, nsumoc, nsum_ocavg), src/timavge.F:46, :76 and src/timinfo_data.F"""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._call("tav_counts", C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
     # -- convenience: whole-state load/store used by tests and bench
     OCEAN_FIELDS = ("po", "pom", "qo", "qom", "sst", "sstm", "wekto", "wekpo", "entoc", "tauxo", "tauyo",
                     "fnetoc", "ddynoc")
@@ -162,6 +174,15 @@ class Model(CModel):
         f = self._lib.qgcm_launch_count
         f.restype = C.c_int64
         return int(f(self._h))
+
+    def get_field_sub(self, name, nsk, out=None):
+        """the sub-sampled vector of ocnc_out / atnc_out (src/nc_subs.F:869-890), packed on the device"""
+        n = C.c_int64()
+        self._call("field_sub_size", name.encode(), C.c_int32(nsk), C.byref(n))
+        if out is None:
+            out = np.full(n.value, np.nan, dtype=np.float64)
+        self._call("get_field_sub", name.encode(), C.c_int32(nsk), out.ctypes.data_as(C.POINTER(C.c_double)), n)
+        return out
 
     def stream(self):
         f = self._lib.qgcm_stream
@@ -262,6 +283,28 @@ class SlabGroup:
     def xforc(self):
         for m in self.ranks:
             m.xforc()
+
+    # the diagnostic sums act on each rank's own rows
+    def tavini(self):
+        for m in self.ranks:
+            m.tavini()
+
+    def tavocn(self):
+        for m in self.ranks:
+            m.tavocn()
+
+    def avg_ocn_k247(self):
+        for m in self.ranks:
+            m.avg_ocn_k247()
+
+    def tav_counts(self):
+        return self.ranks[0].tav_counts()
+
+    def get_field_sub(self, name, nsk):
+        out = None
+        for m in self.ranks:      # each rank fills the sub-sampled rows it owns
+            out = m.get_field_sub(name, nsk, out)
+        return out
 
     def valids(self):
         """combine the per-slab reports as a multi-process driver would (min / max / sum)"""
