@@ -260,8 +260,10 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     # the bench prints ONE JSON line on stdout: keep NCCL's version banner out of it
+    # (NCCL writes its debug output, version banner included, to stdout unless told otherwise)
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.pop("NCCL_DEBUG", None)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import _pkg
     qg = _pkg.load()
     if args.impl == "reference":

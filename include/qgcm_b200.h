@@ -287,6 +287,15 @@ int qgcm_tav_counts(qgcm_model *m, int32_t *nsumat, int32_t *nsumoc, int32_t *ns
 int qgcm_field_sub_size(qgcm_model *m, const char *name, int32_t nsk, int64_t *n);
 int qgcm_get_field_sub(qgcm_model *m, const char *name, int32_t nsk, double *host, int64_t n);
 
+/* qocdiag_out, src/qocdiag.F:303-683 (-Dqoc_diag, e.g. examples/double_gyre_ocean_only; called
+ * between oml and qgostep at output steps, src/q-gcm.F:1237-1239): the ocean vorticity tendency
+ * and its component terms, evaluated on the device at the sub-sampled points only.
+ * host(ipwk, jpwk, nlo, 5), the last index in the reference's output order dqdt, qotjac, qt2dif,
+ * qt4dif, qotent; each (ipwk, jpwk) plane is the wrk vector of one nf_put_vara_double call
+ * (:616-672).  n must equal the count qgcm_qocdiag_size returns (5*ipwk*jpwk*nlo). */
+int qgcm_qocdiag_size(qgcm_model *m, int32_t nsko, int64_t *n);
+int qgcm_qocdiag(qgcm_model *m, int32_t nsko, double *host, int64_t n);
+
 /* ---- instrumentation ---------------------------------------------------------- */
 
 /* number of kernels launched by this model since creation */

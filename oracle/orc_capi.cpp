@@ -1,6 +1,8 @@
 // TEST INFRASTRUCTURE ONLY -- C entry points of the CPU oracle (liborc.so), loaded by
 // tests/ and by bench.py's cpu_baseline / --impl reference legs only.
+#include <algorithm>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 
 #include "orc_model.h"
@@ -94,6 +96,16 @@ int orc_tavini(Model *m) { ORC_TRY(m->tavini(3)); }
 int orc_tavatm(Model *m) { ORC_TRY(m->tavatm()); }
 int orc_tavocn(Model *m) { ORC_TRY(m->tavocn()); }
 int orc_avg_ocn_k247(Model *m) { ORC_TRY(m->avg_ocn_k247()); }
+int orc_qocdiag(Model *m, int32_t nsko, double *out, int64_t n) {
+  ORC_TRY({
+    int mw = m->nxpo % nsko;
+    const int64_t iw = std::min(mw, 1) + (m->nxpo - mw) / nsko;
+    mw = m->nypo % nsko;
+    const int64_t jw = std::min(mw, 1) + (m->nypo - mw) / nsko;
+    if (n != 5 * iw * jw * m->nlo) throw std::runtime_error("orc_qocdiag: element count mismatch");
+    m->qocdiag(nsko, out);
+  });
+}
 int orc_tav_counts(Model *m, int32_t *nsumat, int32_t *nsumoc, int32_t *nsum_ocavg) {
   *nsumat = m->nsumat;
   *nsumoc = m->nsumoc;

@@ -103,6 +103,8 @@ struct Model {
   void tavatm();
   void tavocn();
   void avg_ocn_k247();
+  // src/qocdiag.F:303-683
+  void qocdiag(int nsko, double *out);
   void run(int64_t nt_first, int64_t nt_last);
 };
 

@@ -510,6 +510,9 @@ int qgcm_get_field_sub(qgcm_model *m, const char *name, int32_t nsk, double *hos
   QG_TRY(get_field_sub(m, name, nsk, host, n));
 }
 
+int qgcm_qocdiag_size(qgcm_model *m, int32_t nsko, int64_t *n) { QG_TRY(qocdiag_size(m, nsko, n)); }
+int qgcm_qocdiag(qgcm_model *m, int32_t nsko, double *host, int64_t n) { QG_TRY(launch_qocdiag(m, nsko, host, n)); }
+
 int64_t qgcm_launch_count(qgcm_model *m) { return m ? m->launches : 0; }
 
 int qgcm_profile(qgcm_model *m, int enable) {

@@ -346,6 +346,9 @@ void launch_tavatm(qgcm_model *m);
 void launch_avg_ocn_k247(qgcm_model *m);
 void field_sub_size(qgcm_model *m, const char *name, int nsk, int64_t *n);
 void get_field_sub(qgcm_model *m, const char *name, int nsk, double *host, int64_t n);
+// qocdiag.cu
+void qocdiag_size(qgcm_model *m, int nsk, int64_t *n);
+void launch_qocdiag(qgcm_model *m, int nsk, double *host, int64_t n);
 
 // slab.cu: y-slab multi-GPU drivers.  `ms` is the set of ranks this process drives: one model
 // with an NCCL communicator, or every rank of an in-process loopback group.

@@ -150,6 +150,17 @@ class CModel:
         self._call("tav_counts", C.byref(a), C.byref(b), C.byref(c))
         return a.value, b.value, c.value
 
+    def qocdiag(self, nsko, out=None):
+        """qocdiag_out, src/qocdiag.F:303: (ipwk, jpwk, nlo, 5) = dqdt, qotjac, qt2dif, qt4dif, qotent"""
+        nx, ny = self.nxpo, self.nypo
+        iw = min(nx % nsko, 1) + (nx - nx % nsko) // nsko
+        jw = min(ny % nsko, 1) + (ny - ny % nsko) // nsko
+        n = 5 * iw * jw * self.cfg.nlo
+        if out is None:
+            out = np.full(n, np.nan, dtype=np.float64)
+        self._call("qocdiag", C.c_int32(nsko), out.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(n))
+        return out
+
     # -- convenience: whole-state load/store used by tests and bench
     OCEAN_FIELDS = ("po", "pom", "qo", "qom", "sst", "sstm", "wekto", "wekpo", "entoc", "tauxo", "tauyo",
                     "fnetoc", "ddynoc")
@@ -299,6 +310,12 @@ class SlabGroup:
 
     def tav_counts(self):
         return self.ranks[0].tav_counts()
+
+    def qocdiag(self, nsko):
+        out = None
+        for m in self.ranks:      # each rank fills the sub-sampled rows it owns
+            out = m.qocdiag(nsko, out)
+        return out
 
     def get_field_sub(self, name, nsk):
         out = None
