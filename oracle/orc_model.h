@@ -105,6 +105,8 @@ struct Model {
   void avg_ocn_k247();
   // src/qocdiag.F:303-683
   void qocdiag(int nsko, double *out);
+  // src/monitor_diag.F:480-840
+  void monnc_ocean(qgcm_monitor_ocean *rep);
   void run(int64_t nt_first, int64_t nt_last);
 };
 

@@ -1,0 +1,242 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (parity unpinned, see orc_model.h).
+// Restatement of the ocean section of monnc_comp (src/monitor_diag.F:480-840) with its helpers
+// del4bx (:900-1015), del4ch (:1020-1155) and genint (:1160-1210).  Same loops, same
+// expression association (including the reference's own ugdot expression, :676-677, whose
+// pom(i,j,k) terms cancel), without the OpenMP directives' reduction order.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "orc_model.h"
+
+namespace orc {
+
+#define IX2(i, j, nx) ((size_t)((i)-1) + (size_t)(nx) * (size_t)((j)-1))
+#define IX3(i, j, k, nx, ny) ((size_t)((i)-1) + (size_t)(nx) * ((size_t)((j)-1) + (size_t)(ny) * (size_t)((k)-1)))
+
+// src/monitor_diag.F:1160-1210
+static double genint(const double *val, int nx, int ny, double facwe, double facsn) {
+  double answer = 0.0;
+  for (int j = 2; j <= ny - 1; ++j) {
+    double sumi = facwe * val[IX2(1, j, nx)];
+    for (int i = 2; i <= nx - 1; ++i) sumi = sumi + val[IX2(i, j, nx)];
+    sumi = sumi + facwe * val[IX2(nx, j, nx)];
+    answer = answer + sumi;
+  }
+  double xxs = facwe * val[IX2(1, 1, nx)], xxn = facwe * val[IX2(1, ny, nx)];
+  for (int i = 2; i <= nx - 1; ++i) {
+    xxs = xxs + val[IX2(i, 1, nx)];
+    xxn = xxn + val[IX2(i, ny, nx)];
+  }
+  xxs = xxs + facwe * val[IX2(nx, 1, nx)];
+  xxn = xxn + facwe * val[IX2(nx, ny, nx)];
+  return answer + facsn * (xxs + xxn);
+}
+
+// one application of the Laplacian of del4bx (:925-968) / del4ch (:1048-1093)
+static void lap_onesided(const double *arr, int nx, int ny, double dxm2, bool cyclic, double *del2) {
+#define A(i, j) arr[IX2(i, j, nx)]
+#define D(i, j) del2[IX2(i, j, nx)]
+  for (int j = 2; j <= ny - 1; ++j) {
+    if (cyclic)
+      D(1, j) = dxm2 * (A(1, j - 1) + A(nx, j) + A(2, j) + A(1, j + 1) - 4.0 * A(1, j));
+    else
+      D(1, j) = dxm2 * (A(3, j) - 2.0 * A(2, j) + A(1, j) + A(1, j - 1) - 2.0 * A(1, j) + A(1, j + 1));
+    for (int i = 2; i <= nx - 1; ++i) D(i, j) = dxm2 * (A(i, j - 1) + A(i - 1, j) + A(i + 1, j) + A(i, j + 1) - 4.0 * A(i, j));
+    if (cyclic)
+      D(nx, j) = dxm2 * (A(nx, j - 1) + A(nx - 1, j) + A(1, j) + A(nx, j + 1) - 4.0 * A(nx, j));
+    else
+      D(nx, j) = dxm2 * (A(nx, j) - 2.0 * A(nx - 1, j) + A(nx - 2, j) + A(nx, j - 1) - 2.0 * A(nx, j) + A(nx, j + 1));
+  }
+  for (int i = 2; i <= nx - 1; ++i) {
+    D(i, 1) = dxm2 * (A(i - 1, 1) - 2.0 * A(i, 1) + A(i + 1, 1) + A(i, 3) - 2.0 * A(i, 2) + A(i, 1));
+    D(i, ny) = dxm2 * (A(i - 1, ny) - 2.0 * A(i, ny) + A(i + 1, ny) + A(i, ny) - 2.0 * A(i, ny - 1) + A(i, ny - 2));
+  }
+  if (cyclic) {
+    D(1, 1) = dxm2 * (A(nx, 1) - 2.0 * A(1, 1) + A(2, 1) + A(1, 3) - 2.0 * A(1, 2) + A(1, 1));
+    D(1, ny) = dxm2 * (A(nx, ny) - 2.0 * A(1, ny) + A(2, ny) + A(1, ny) - 2.0 * A(1, ny - 1) + A(1, ny - 2));
+    D(nx, 1) = dxm2 * (A(nx - 1, 1) - 2.0 * A(nx, 1) + A(1, 1) + A(nx, 3) - 2.0 * A(nx, 2) + A(nx, 1));
+    D(nx, ny) = dxm2 * (A(nx - 1, ny) - 2.0 * A(nx, ny) + A(1, ny) + A(nx, ny) - 2.0 * A(nx, ny - 1) + A(nx, ny - 2));
+  } else {
+    D(1, 1) = dxm2 * (A(3, 1) - 2.0 * A(2, 1) + A(1, 1) + A(1, 3) - 2.0 * A(1, 2) + A(1, 1));
+    D(nx, 1) = dxm2 * (A(nx, 1) - 2.0 * A(nx - 1, 1) + A(nx - 2, 1) + A(nx, 3) - 2.0 * A(nx, 2) + A(nx, 1));
+    D(1, ny) = dxm2 * (A(3, ny) - 2.0 * A(2, ny) + A(1, ny) + A(1, ny) - 2.0 * A(1, ny - 1) + A(1, ny - 2));
+    D(nx, ny) = dxm2 * (A(nx, ny) - 2.0 * A(nx - 1, ny) + A(nx - 2, ny) + A(nx, ny) - 2.0 * A(nx, ny - 1) + A(nx, ny - 2));
+  }
+#undef A
+#undef D
+}
+
+void Model::monnc_ocean(qgcm_monitor_ocean *r) {
+  std::memset(r, 0, sizeof(*r));
+  if (atmos_only) return;
+  const double rhooc = c.rhooc, cpoc = c.cpoc, delek = c.delek;
+  const size_t np = (size_t)nxpo * nypo;
+  vec octwk1((size_t)nxto * nypo), octwk2((size_t)nxto * nypo), octwk3((size_t)nxto * nypo), octwk4((size_t)nxto * nypo);
+  vec ocpwk1(np), ocpwk2(np), ocpwk3(np), ocpwk4(np), etaoc(np), ugoc((size_t)nxpo * nyto), vgoc((size_t)nxto * nypo);
+  // reference pressures on the equatorward side (:174-183)
+  double poref[QGCM_NLMAX] = {0};
+  for (int k = 1; k <= nlo; ++k) poref[k - 1] = (fnot > 0.0) ? po[IX3(1, 1, k, nxpo, nypo)] : po[IX3(1, nypo, k, nxpo, nypo)];
+  // Ekman velocity (:498-527)
+  r->wetmoc = genint(wekto.data(), nxto, nyto, 1.0, 1.0);
+  for (int j = 1; j <= nyto; ++j)
+    for (int i = 1; i <= nxto; ++i) octwk1[IX2(i, j, nxto)] = std::fabs(wekto[IX2(i, j, nxto)]);
+  r->watmoc = genint(octwk1.data(), nxto, nyto, 1.0, 1.0);
+  r->wepmoc = genint(wekpo.data(), nxpo, nypo, 0.5, 0.5);
+  for (size_t n = 0; n < np; ++n) ocpwk1[n] = std::fabs(wekpo[n]);
+  r->wapmoc = genint(ocpwk1.data(), nxpo, nypo, 0.5, 0.5);
+  r->wetmoc = r->wetmoc * ocnorm;
+  r->watmoc = r->watmoc * ocnorm;
+  r->wepmoc = r->wepmoc * ocnorm;
+  r->wapmoc = r->wapmoc * ocnorm;
+  // entrainment (:529-543)
+  r->entmoc = genint(entoc.data(), nxpo, nypo, 0.5, 0.5);
+  for (size_t n = 0; n < np; ++n) ocpwk1[n] = std::fabs(entoc[n]);
+  r->enamoc = genint(ocpwk1.data(), nxpo, nypo, 0.5, 0.5);
+  r->entmoc = r->entmoc * ocnorm;
+  r->enamoc = r->enamoc * ocnorm;
+  // interface displacements (:545-583)
+  for (int k = 1; k <= nlo - 1; ++k) {
+    const double rgpoc = 1.0 / c.gpoc[k - 1];
+    for (int j = 1; j <= nypo; ++j)
+      for (int i = 1; i <= nxpo; ++i) {
+        const double eta = rgpoc * (po[IX3(i, j, k + 1, nxpo, nypo)] - po[IX3(i, j, k, nxpo, nypo)]);
+        const double etadot = (rgpoc / dto) * (po[IX3(i, j, k, nxpo, nypo)] - po[IX3(i, j, k + 1, nxpo, nypo)] -
+                                               pom[IX3(i, j, k, nxpo, nypo)] + pom[IX3(i, j, k + 1, nxpo, nypo)]);
+        etaoc[IX2(i, j, nxpo)] = eta;
+        ocpwk1[IX2(i, j, nxpo)] = eta * eta;
+        ocpwk2[IX2(i, j, nxpo)] = eta * etadot;
+        ocpwk3[IX2(i, j, nxpo)] = eta * entoc[IX2(i, j, nxpo)];
+      }
+    const double etaint = genint(etaoc.data(), nxpo, nypo, 0.5, 0.5);
+    double et2now = genint(ocpwk1.data(), nxpo, nypo, 0.5, 0.5);
+    const double et2dot = genint(ocpwk2.data(), nxpo, nypo, 0.5, 0.5);
+    r->etamoc[k - 1] = etaint * ocnorm;
+    et2now = et2now * ocnorm;
+    r->ddtpeoc[k - 1] = rhooc * c.gpoc[k - 1] * et2dot;
+    r->et2moc[k - 1] = et2now;
+    if (k == 1) {
+      const double pkeint = genint(ocpwk3.data(), nxpo, nypo, 0.5, 0.5);
+      r->pkenoc = rhooc * c.gpoc[0] * pkeint * ocnorm;
+    }
+  }
+  // wind work (:588-617)
+  for (int j = 1; j <= nyto; ++j)
+    for (int i = 1; i <= nxpo; ++i) {
+      const double ugeos = -rdxof0 * (po[IX3(i, j + 1, 1, nxpo, nypo)] - po[IX3(i, j, 1, nxpo, nypo)]);
+      const double tauxav = 0.5 * (tauxo[IX2(i, j + 1, nxpo)] + tauxo[IX2(i, j, nxpo)]);
+      ocpwk1[IX2(i, j, nxpo)] = ugeos * tauxav;
+    }
+  const double utaux = genint(ocpwk1.data(), nxpo, nyto, 0.5, 1.0);
+  for (int j = 1; j <= nypo; ++j)
+    for (int i = 1; i <= nxto; ++i) {
+      const double vgeos = rdxof0 * (po[IX3(i + 1, j, 1, nxpo, nypo)] - po[IX3(i, j, 1, nxpo, nypo)]);
+      const double tauyav = 0.5 * (tauyo[IX2(i + 1, j, nxpo)] + tauyo[IX2(i, j, nxpo)]);
+      octwk1[IX2(i, j, nxto)] = vgeos * tauyav;
+    }
+  const double vtauy = genint(octwk1.data(), nxto, nypo, 1.0, 0.5);
+  r->utauoc = rhooc * (vtauy + utaux) * ocnorm;
+  // layer kinetic energy, dissipation, stream function (:620-752)
+  for (int k = 1; k <= nlo; ++k) {
+    for (int j = 1; j <= nyto; ++j)
+      for (int i = 1; i <= nxpo; ++i) ugoc[IX2(i, j, nxpo)] = -rdxof0 * (pom[IX3(i, j + 1, k, nxpo, nypo)] - pom[IX3(i, j, k, nxpo, nypo)]);
+    lap_onesided(ugoc.data(), nxpo, nyto, dxom2, cyclic, ocpwk1.data());
+    lap_onesided(ocpwk1.data(), nxpo, nyto, dxom2, cyclic, ocpwk2.data());
+    for (int j = 1; j <= nypo; ++j)
+      for (int i = 1; i <= nxto; ++i) vgoc[IX2(i, j, nxto)] = rdxof0 * (pom[IX3(i + 1, j, k, nxpo, nypo)] - pom[IX3(i, j, k, nxpo, nypo)]);
+    lap_onesided(vgoc.data(), nxto, nypo, dxom2, cyclic, octwk1.data());
+    lap_onesided(octwk1.data(), nxto, nypo, dxom2, cyclic, octwk2.data());
+    double pomin = 1.0e30, pomax = -1.0e30;
+    for (int j = 1; j <= nypo; ++j)
+      for (int i = 1; i <= nxpo; ++i) {
+        pomin = std::min(pomin, po[IX3(i, j, k, nxpo, nypo)]);
+        pomax = std::max(pomax, po[IX3(i, j, k, nxpo, nypo)]);
+      }
+    vec ujeto(nyto + 1);
+    for (int j = 1; j <= nyto; ++j) {
+      double ujet = 0.0, ugeos = 0.0;
+      for (int i = 1; i <= nxpo; ++i) {
+        ugeos = -rdxof0 * (po[IX3(i, j + 1, k, nxpo, nypo)] - po[IX3(i, j, k, nxpo, nypo)]);
+        const double ugdot = -(rdxof0 / dto) * (po[IX3(i, j + 1, k, nxpo, nypo)] - pom[IX3(i, j, k, nxpo, nypo)] -
+                                                pom[IX3(i, j + 1, k, nxpo, nypo)] + pom[IX3(i, j, k, nxpo, nypo)]);
+        ujet = ujet + ugeos;
+        ocpwk1[IX2(i, j, nxpo)] = ugeos * ocpwk1[IX2(i, j, nxpo)];
+        ocpwk2[IX2(i, j, nxpo)] = ugeos * ocpwk2[IX2(i, j, nxpo)];
+        ocpwk3[IX2(i, j, nxpo)] = ugeos * ugeos;
+        ocpwk4[IX2(i, j, nxpo)] = ugeos * ugdot;
+      }
+      ujet = ujet - ugeos;
+      ujeto[j] = std::fabs(ujet) / (double)nxto;
+    }
+    r->ocjpos[k - 1] = 0;
+    r->ocjval[k - 1] = 0.0;
+    for (int j = 1; j <= nyto; ++j)
+      if (ujeto[j] > r->ocjval[k - 1]) {
+        r->ocjpos[k - 1] = j;
+        r->ocjval[k - 1] = ujeto[j];
+      }
+    const double u2diss = genint(ocpwk1.data(), nxpo, nyto, 0.5, 1.0);
+    const double u4diss = genint(ocpwk2.data(), nxpo, nyto, 0.5, 1.0);
+    const double uke = genint(ocpwk3.data(), nxpo, nyto, 0.5, 1.0);
+    const double ukedot = genint(ocpwk4.data(), nxpo, nyto, 0.5, 1.0);
+    for (int j = 1; j <= nypo; ++j)
+      for (int i = 1; i <= nxto; ++i) {
+        const double vgeos = rdxof0 * (po[IX3(i + 1, j, k, nxpo, nypo)] - po[IX3(i, j, k, nxpo, nypo)]);
+        const double vgdot = (rdxof0 / dto) * (po[IX3(i + 1, j, k, nxpo, nypo)] - po[IX3(i, j, k, nxpo, nypo)] -
+                                               pom[IX3(i + 1, j, k, nxpo, nypo)] + pom[IX3(i, j, k, nxpo, nypo)]);
+        octwk1[IX2(i, j, nxto)] = vgeos * octwk1[IX2(i, j, nxto)];
+        octwk2[IX2(i, j, nxto)] = vgeos * octwk2[IX2(i, j, nxto)];
+        octwk3[IX2(i, j, nxto)] = vgeos * vgeos;
+        octwk4[IX2(i, j, nxto)] = vgeos * vgdot;
+      }
+    const double pint = genint(&po[IX3(1, 1, k, nxpo, nypo)], nxpo, nypo, 0.5, 0.5);
+    const double qint = genint(&qo[IX3(1, 1, k, nxpo, nypo)], nxpo, nypo, 0.5, 0.5);
+    const double v2diss = genint(octwk1.data(), nxto, nypo, 1.0, 0.5);
+    const double v4diss = genint(octwk2.data(), nxto, nypo, 1.0, 0.5);
+    const double vke = genint(octwk3.data(), nxto, nypo, 1.0, 0.5);
+    const double vkedot = genint(octwk4.data(), nxto, nypo, 1.0, 0.5);
+    r->pavgoc[k - 1] = pint * ocnorm;
+    r->qavgoc[k - 1] = qint * ocnorm;
+    r->ah2doc[k - 1] = -rhooc * c.ah2oc[k - 1] * c.hoc[k - 1] * (u2diss + v2diss) * ocnorm;
+    r->ah4doc[k - 1] = rhooc * c.ah4oc[k - 1] * c.hoc[k - 1] * (u4diss + v4diss) * ocnorm;
+    r->kealoc[k - 1] = 0.5 * rhooc * c.hoc[k - 1] * (uke + vke) * ocnorm;
+    r->ddtkeoc[k - 1] = rhooc * c.hoc[k - 1] * (ukedot + vkedot) * ocnorm;
+    double psiext = std::min(pomin / fnot, pomax / fnot);
+    r->osfmin[k - 1] = 1.0e-6 * c.hoc[k - 1] * (psiext - poref[k - 1] / fnot);
+    psiext = std::max(pomin / fnot, pomax / fnot);
+    r->osfmax[k - 1] = 1.0e-6 * c.hoc[k - 1] * (psiext - poref[k - 1] / fnot);
+    r->occirc[k - 1] = 1.0e-6 * c.hoc[k - 1] * (po[IX3(1, 1, k, nxpo, nypo)] - po[IX3(1, nypo, k, nxpo, nypo)]) / fnot;
+  }
+  // bottom drag (:755-783)
+  for (int j = 1; j <= nyto; ++j)
+    for (int i = 1; i <= nxpo; ++i) {
+      const double ugeos = -rdxof0 * (pom[IX3(i, j + 1, nlo, nxpo, nypo)] - pom[IX3(i, j, nlo, nxpo, nypo)]);
+      ocpwk1[IX2(i, j, nxpo)] = ugeos * ugeos;
+    }
+  const double u2d = genint(ocpwk1.data(), nxpo, nyto, 0.5, 1.0);
+  for (int j = 1; j <= nypo; ++j)
+    for (int i = 1; i <= nxto; ++i) {
+      const double vgeos = rdxof0 * (pom[IX3(i + 1, j, nlo, nxpo, nypo)] - pom[IX3(i, j, nlo, nxpo, nypo)]);
+      octwk1[IX2(i, j, nxto)] = vgeos * vgeos;
+    }
+  const double v2d = genint(octwk1.data(), nxto, nypo, 1.0, 0.5);
+  r->btdgoc = 0.5 * rhooc * delek * std::fabs(fnot) * (u2d + v2d) * ocnorm;
+  // mixed layer (:788-812)
+  r->sstmin = 1.0e30;
+  r->sstmax = -1.0e30;
+  for (int j = 1; j <= nyto; ++j)
+    for (int i = 1; i <= nxto; ++i) {
+      r->sstmin = std::min(r->sstmin, sst[IX2(i, j, nxto)]);
+      r->sstmax = std::max(r->sstmax, sst[IX2(i, j, nxto)]);
+      octwk1[IX2(i, j, nxto)] = sst[IX2(i, j, nxto)] * wekto[IX2(i, j, nxto)];
+    }
+  r->hfmloc = genint(octwk1.data(), nxto, nyto, 1.0, 1.0);
+  r->tmlmoc = genint(sst.data(), nxto, nyto, 1.0, 1.0);
+  r->tmlmoc = r->tmlmoc * ocnorm;
+  r->hfmloc = rhooc * cpoc * r->hfmloc * ocnorm;
+  // total circulation (:818-821)
+  r->occtot = 0.0;
+  for (int k = 1; k <= nlo; ++k) r->occtot = r->occtot + r->occirc[k - 1];
+}
+
+}  // namespace orc

@@ -78,3 +78,14 @@ class QgcmValidsReport(C.Structure):
 def declared_functions():
     """names of every extern "C" function the header declares"""
     return sorted(set(re.findall(r"\b(qgcm_\w+)\s*\(", re.sub(r"/\*.*?\*/", "", _TEXT, flags=re.S))))
+
+
+class QgcmMonitorOcean(C.Structure):
+    _fields_ = _parse_struct(_TEXT, "qgcm_monitor_ocean")
+
+    def as_dict(self):
+        out = {}
+        for name, typ in self._fields_:
+            v = getattr(self, name)
+            out[name] = list(v) if hasattr(v, "__len__") else v
+        return out

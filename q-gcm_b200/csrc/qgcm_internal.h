@@ -224,6 +224,8 @@ struct qgcm_model {
   int nsumat = 0, nsumoc = 0, nsum_ocavg = 0;
   double *d_pack = nullptr;
   size_t pack_elems = 0;
+  double *d_mon = nullptr, *d_monf = nullptr;   // qgcm_monnc_ocean: per-row sums; four scratch fields
+  size_t mon_elems = 0;
   bool shared_stream = false;            // loopback ranks > 0 borrow rank 0's stream
   // peer-memory transport (slab.cu): own mailbox, peers' mapped mailboxes, exchange counters
   double *mailbox = nullptr;
@@ -346,6 +348,8 @@ void launch_tavatm(qgcm_model *m);
 void launch_avg_ocn_k247(qgcm_model *m);
 void field_sub_size(qgcm_model *m, const char *name, int nsk, int64_t *n);
 void get_field_sub(qgcm_model *m, const char *name, int nsk, double *host, int64_t n);
+// monitor.cu
+void launch_monnc_ocean(qgcm_model *m, qgcm_monitor_ocean *rep);
 // qocdiag.cu
 void qocdiag_size(qgcm_model *m, int nsk, int64_t *n);
 void launch_qocdiag(qgcm_model *m, int nsk, double *host, int64_t n);

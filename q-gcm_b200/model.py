@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from .abi import QgcmConfig, QgcmScalars, QgcmValidsReport, declared_functions
+from .abi import QgcmConfig, QgcmScalars, QgcmValidsReport, QgcmMonitorOcean, declared_functions
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -149,6 +149,12 @@ class CModel:
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
         self._call("tav_counts", C.byref(a), C.byref(b), C.byref(c))
         return a.value, b.value, c.value
+
+    def monnc_ocean(self) -> QgcmMonitorOcean:
+        """ocean section of monnc_comp, src/monitor_diag.F:480-840"""
+        r = QgcmMonitorOcean()
+        self._call("monnc_ocean", C.byref(r))
+        return r
 
     def qocdiag(self, nsko, out=None):
         """qocdiag_out, src/qocdiag.F:303: (ipwk, jpwk, nlo, 5) = dqdt, qotjac, qt2dif, qt4dif, qotent"""

@@ -1,0 +1,135 @@
+"""The oracle's restatement of the ocean section of monnc_comp (src/monitor_diag.F:480-840, with
+del4bx/del4ch/genint) against an independent vectorised numpy evaluation written from the
+Fortran."""
+import numpy as np
+import pytest
+
+from util import small_configs
+
+
+def genint(v, fw, fs):
+    """src/monitor_diag.F:1160: area sum with weights fw on the W/E columns, fs on the S/N rows"""
+    w = np.ones(v.shape[0]); w[0] = w[-1] = fw
+    s = np.ones(v.shape[1]); s[0] = s[-1] = fs
+    return float(w @ v @ s)
+
+
+class V(float):
+    """a float that remembers the sum of magnitudes it was rounded against"""
+    def __new__(cls, x, scale):
+        o = float.__new__(cls, x)
+        o.scale = scale
+        return o
+
+    def _s(self, o):
+        return getattr(o, "scale", abs(float(o)))
+
+    def __add__(self, o): return V(float(self) + float(o), self.scale + self._s(o))
+    __radd__ = __add__
+    def __sub__(self, o): return V(float(self) - float(o), self.scale + self._s(o))
+    def __mul__(self, o): return V(float(self) * float(o), self.scale * abs(float(o)))
+    __rmul__ = __mul__
+    def __neg__(self): return V(-float(self), self.scale)
+
+
+def gint(v, fw, fs):
+    return V(genint(v, fw, fs), genint(np.abs(v), fw, fs))
+
+
+def lap1(a, dxm2, cyclic):
+    """one Laplacian of del4bx / del4ch: centred inside, one-sided second differences on walls,
+    periodic in x for the channel"""
+    if cyclic:
+        dxx = np.roll(a, 1, axis=0) - 2 * a + np.roll(a, -1, axis=0)
+    else:
+        dxx = np.empty_like(a)
+        dxx[1:-1] = a[:-2] - 2 * a[1:-1] + a[2:]
+        dxx[0] = a[2] - 2 * a[1] + a[0]
+        dxx[-1] = a[-1] - 2 * a[-2] + a[-3]
+    dyy = np.empty_like(a)
+    dyy[:, 1:-1] = a[:, :-2] - 2 * a[:, 1:-1] + a[:, 2:]
+    dyy[:, 0] = a[:, 2] - 2 * a[:, 1] + a[:, 0]
+    dyy[:, -1] = a[:, -1] - 2 * a[:, -2] + a[:, -3]
+    return dxm2 * (dxx + dyy)
+
+
+@pytest.mark.parametrize("case", ["box_dg", "chan_so"])
+def test_monnc_ocean_matches_numpy(qg, pyorc, case):
+    p = small_configs(qg)[case]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.run(1, 2 * p.nstr)
+    r = m.monnc_ocean().as_dict()
+    nxp, nyp, nxt, nyt, nl = p.nxpo, p.nypo, p.nxto, p.nyto, p.nlo
+    po, pom, qo = (m.get_field(n, (nxp, nyp, nl)) for n in ("po", "pom", "qo"))
+    sst, wekto = m.get_field("sst", (nxt, nyt)), m.get_field("wekto", (nxt, nyt))
+    wekpo, entoc = m.get_field("wekpo", (nxp, nyp)), m.get_field("entoc", (nxp, nyp))
+    tx, ty = m.get_field("tauxo", (nxp, nyp)), m.get_field("tauyo", (nxp, nyp))
+    norm = 1.0 / (nxt * nyt)
+    rdxf0 = 1.0 / (p.dxo * p.fnot)
+    dxm2 = 1.0 / p.dxo ** 2
+    cyc = p.has("cyclic_ocean")
+    want = {
+        "wetmoc": gint(wekto, 1, 1) * norm, "watmoc": gint(np.abs(wekto), 1, 1) * norm,
+        "wepmoc": gint(wekpo, .5, .5) * norm, "wapmoc": gint(np.abs(wekpo), .5, .5) * norm,
+        "entmoc": gint(entoc, .5, .5) * norm, "enamoc": gint(np.abs(entoc), .5, .5) * norm,
+        "tmlmoc": gint(sst, 1, 1) * norm, "hfmloc": cfg.rhooc * cfg.cpoc * gint(sst * wekto, 1, 1) * norm,
+        "sstmin": sst.min(), "sstmax": sst.max(),
+    }
+    ug1 = -rdxf0 * (po[:, 1:, 0] - po[:, :-1, 0])
+    vg1 = rdxf0 * (po[1:, :, 0] - po[:-1, :, 0])
+    want["utauoc"] = cfg.rhooc * (gint(vg1 * 0.5 * (ty[1:] + ty[:-1]), 1, .5)
+                                  + gint(ug1 * 0.5 * (tx[:, 1:] + tx[:, :-1]), .5, 1)) * norm
+    vec = {k: [] for k in ("etamoc", "et2moc", "ddtpeoc", "pavgoc", "qavgoc", "kealoc", "ddtkeoc", "ah2doc", "ah4doc",
+                           "osfmin", "osfmax", "occirc", "ocjval", "ocjpos")}
+    for k in range(nl - 1):
+        eta = (po[:, :, k + 1] - po[:, :, k]) / cfg.gpoc[k]
+        etadot = ((po[:, :, k] - po[:, :, k + 1]) - (pom[:, :, k] - pom[:, :, k + 1])) / (cfg.gpoc[k] * p.dto)
+        vec["etamoc"].append(gint(eta, .5, .5) * norm)
+        vec["et2moc"].append(gint(eta * eta, .5, .5) * norm)
+        vec["ddtpeoc"].append(cfg.rhooc * cfg.gpoc[k] * gint(eta * etadot, .5, .5))
+        if k == 0:
+            want["pkenoc"] = cfg.rhooc * cfg.gpoc[0] * gint(eta * entoc, .5, .5) * norm
+    pref = po[0, 0, :] if p.fnot > 0 else po[0, -1, :]
+    for k in range(nl):
+        ugm = -rdxf0 * (pom[:, 1:, k] - pom[:, :-1, k])
+        vgm = rdxf0 * (pom[1:, :, k] - pom[:-1, :, k])
+        u2, v2 = lap1(ugm, dxm2, cyc), lap1(vgm, dxm2, cyc)
+        u4, v4 = lap1(u2, dxm2, cyc), lap1(v2, dxm2, cyc)
+        ug = -rdxf0 * (po[:, 1:, k] - po[:, :-1, k])
+        vg = rdxf0 * (po[1:, :, k] - po[:-1, :, k])
+        # the reference's ugdot drops po(i,j,k): its two pom(i,j,k) terms cancel (src/monitor_diag.F:676-677)
+        ugdot = -(rdxf0 / p.dto) * (po[:, 1:, k] - pom[:, 1:, k])
+        vgdot = (rdxf0 / p.dto) * ((po[1:, :, k] - po[:-1, :, k]) - (pom[1:, :, k] - pom[:-1, :, k]))
+        h = cfg.hoc[k]
+        vec["pavgoc"].append(gint(po[:, :, k], .5, .5) * norm)
+        vec["qavgoc"].append(gint(qo[:, :, k], .5, .5) * norm)
+        vec["kealoc"].append(0.5 * cfg.rhooc * h * (gint(ug * ug, .5, 1) + gint(vg * vg, 1, .5)) * norm)
+        vec["ddtkeoc"].append(cfg.rhooc * h * (gint(ug * ugdot, .5, 1) + gint(vg * vgdot, 1, .5)) * norm)
+        vec["ah2doc"].append(-cfg.rhooc * cfg.ah2oc[k] * h * (gint(ug * u2, .5, 1) + gint(vg * v2, 1, .5)) * norm)
+        vec["ah4doc"].append(cfg.rhooc * cfg.ah4oc[k] * h * (gint(ug * u4, .5, 1) + gint(vg * v4, 1, .5)) * norm)
+        lo, hi = po[:, :, k].min() / p.fnot, po[:, :, k].max() / p.fnot
+        vec["osfmin"].append(1e-6 * h * (min(lo, hi) - pref[k] / p.fnot))
+        vec["osfmax"].append(1e-6 * h * (max(lo, hi) - pref[k] / p.fnot))
+        vec["occirc"].append(1e-6 * h * (po[0, 0, k] - po[0, -1, k]) / p.fnot)
+        ujet = np.abs(ug[:-1].sum(axis=0)) / nxt        # the end columns are counted once
+        vec["ocjval"].append(ujet.max())
+        vec["ocjpos"].append(int(ujet.argmax()) + 1)
+    ugb = -rdxf0 * (pom[:, 1:, -1] - pom[:, :-1, -1])
+    vgb = rdxf0 * (pom[1:, :, -1] - pom[:-1, :, -1])
+    want["btdgoc"] = 0.5 * cfg.rhooc * p.delek * abs(p.fnot) * (gint(ugb * ugb, .5, 1) + gint(vgb * vgb, 1, .5)) * norm
+    want["occtot"] = float(sum(vec["occirc"]))
+
+    def close(a, b, name, tol=1e-10):
+        assert abs(a - float(b)) <= tol * max(getattr(b, "scale", abs(b)), 1e-300), (case, name, a, float(b))
+
+    for k, v in want.items():
+        # sums of signed fields: compare against the sum of magnitudes' rounding
+        close(r[k], v, k, tol=1e-9)
+    for name, vals in vec.items():
+        for k, v in enumerate(vals):
+            if name == "ocjpos":
+                assert r[name][k] == v, (case, name, k)
+            else:
+                close(r[name][k], v, "%s[%d]" % (name, k), tol=1e-8 if name in ("ddtkeoc", "ddtpeoc", "ah2doc", "ah4doc") else 1e-9)
