@@ -214,6 +214,9 @@ def run_reference(args, qg):
     import pyorc
     pyorc.build()
     cores = len(os.sched_getaffinity(0))
+    if "TORCHELASTIC_RUN_ID" in os.environ:
+        # torchrun pins every worker to OMP_NUM_THREADS=1; only rank 0 works here, on all host cores
+        os.environ["OMP_NUM_THREADS"] = str(cores)
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     os.environ.setdefault("OMP_PROC_BIND", "close")
     o = pyorc.Oracle(cfg)
@@ -237,7 +240,7 @@ def run_reference(args, qg):
         "config": {"workload": "%s ocean-only %dx%dx%d, box, dto=%gs" % (p.name, p.nxpo, p.nypo, p.nlo, p.dto),
                    "parallelism": "%d host threads (OpenMP)" % cores},
         "gpt_updates_per_s": v * p.nxpo * p.nypo * p.nlo / 1e9,
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": int(os.environ.get("OMP_NUM_THREADS", cores)), "kind": "port",
                          "sample": "%d CPU ocean steps (C++/OpenMP restatement of the reference; the Fortran "
                                    "reference cannot be compiled here)" % n},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
