@@ -386,14 +386,17 @@ __global__ void __launch_bounds__(256, 2) k_xform(XfArgs a) {
 //
 //   * persistent blocks (2 per SM), each walks rows blockIdx.x, +gridDim.x, ...
 //   * the raw row is fetched by the TMA engine (cp.async.bulk global->shared, mbarrier
-//     completion) one row ahead of the arithmetic, so no warp ever waits on HBM;
+//     completion) while the previous row is post-processed and stored, so no warp ever
+//     waits on HBM;
 //   * the FFTPACK pre-processing (dsint.f:17-30) is fused into the register load of the
 //     first butterfly pass, its sine weights are rebuilt from a per-thread base angle and
 //     R1 constants (no table traffic);
 //   * three register butterfly passes (16, 15, R3: one butterfly per thread in every pass,
 //     under 128 registers at two blocks per SM) with two shared-memory exchanges laid out
-//     free of bank conflicts (the first one skewed by i >> 4); the last pass builds its
-//     twiddles as powers of a per-thread base (two loads) by squaring/multiplying;
+//     free of bank conflicts (the first one skewed by i >> 4); the exchanges ping-pong
+//     between the exchange buffer and the raw row's buffer (free once pass 1 has read it), so
+//     no pass needs a barrier between its loads and its stores: six block barriers per row;
+//     the last pass builds its twiddles as powers of a per-thread base (two loads);
 //   * real post-processing on the (k, M-k) pair, the running sum of dsint.f:33-37 as a
 //     one-sweep block scan over contiguous segments, and the interleaved result goes
 //     straight from registers to HBM with coalesced 16-byte stores.
@@ -482,6 +485,7 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
   extern __shared__ __align__(128) unsigned char smraw[];
   double *IN = reinterpret_cast<double *>(smraw);                 // N doubles: raw row (TMA target)
   const double2 *IN2 = reinterpret_cast<const double2 *>(smraw);
+  double2 *Z = reinterpret_cast<double2 *>(smraw);      // M complex values: the raw row's buffer, reused between passes 2 and 3
   double2 *W = reinterpret_cast<double2 *>(smraw + (size_t)N * 8);   // exchange buffer
   double *SC = reinterpret_cast<double *>(smraw + (size_t)N * 8 + (size_t)WSZ * 16);   // M doubles: summands / running sums of the odd outputs
   double *red = SC + M;                                                                // 64 doubles
@@ -542,15 +546,7 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       for (int i = 0; i < 8; ++i) sum += red[16 + i];
       a.rowsum[prev_slot] = sum;
     }
-    if (t == 0) {
-      const int nxt = item + gridDim.x;
-      if (nxt < a.nitems) {
-        const int m2 = nxt / a.nrows, r2 = nxt - m2 * a.nrows;
-        mbar_expect_tx(bar, N * 8);
-        bulk_g2s(in_s, a.wrk + (size_t)m2 * a.lsz + (size_t)(r2 + a.row0) * a.ld, N * 8, bar);
-      }
-    }
-    // ---- pass 2 (radix 15), in place: all loads, barrier, autosort stores ----
+    // ---- pass 2 (radix 15): exchange buffer -> raw-row buffer (autosort stores) ----
     {
       double2 v[R2];
 #pragma unroll
@@ -564,30 +560,40 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
         for (int q = 1; q < R2; ++q) v[q] = cmul(v[q], ldg2_nohoist(a.tw2 + (q - 1) * NS2 + k2));
         dft<R2>(v);
       }
-      __syncthreads();
+      // the raw row was consumed before the last barrier: its buffer takes this pass's output,
+      // so no barrier separates the loads from the stores
       if (t < L2) {
 #pragma unroll
-        for (int q = 0; q < R2; ++q) W[j0 + q * NS2] = v[q];
+        for (int q = 0; q < R2; ++q) Z[j0 + q * NS2] = v[q];
       }
     }
     __syncthreads();
-    // ---- pass 3 (radix R3): thread t ends with Z_k, k = t + q*L3 ----
+    // ---- pass 3 (radix R3), raw-row buffer -> exchange buffer: thread t ends with Z_k, k = t + q*L3 ----
     double2 v[R3];
 #pragma unroll
     for (int q = 0; q < R3; ++q) v[q] = make_double2(0.0, 0.0);
     if (t < L3) {
 #pragma unroll
-      for (int q = 0; q < R3; ++q) v[q] = W[t + q * L3];
+      for (int q = 0; q < R3; ++q) v[q] = Z[t + q * L3];
       const double2 w1 = ldg2_nohoist(a.tw3base + 2 * t), w2 = ldg2_nohoist(a.tw3base + 2 * t + 1);
       twiddle_apply<R3>(v, w1, w2);
       dft<R3>(v);
     }
-    __syncthreads();
     if (t < L3) {
 #pragma unroll
       for (int q = 0; q < R3; ++q) W[t + q * L3] = v[q];
     }
+    // generic-proxy stores of pass 2 into the buffer the bulk copy is about to overwrite
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    if (t == 0) {      // pass 3 has read the ping-pong buffer: the next raw row may land in it
+      const int nxt = item + gridDim.x;
+      if (nxt < a.nitems) {
+        const int m2 = nxt / a.nrows, r2 = nxt - m2 * a.nrows;
+        mbar_expect_tx(bar, N * 8);
+        bulk_g2s(in_s, a.wrk + (size_t)m2 * a.lsz + (size_t)(r2 + a.row0) * a.ld, N * 8, bar);
+      }
+    }
     // ---- real post-processing: even outputs -Im F_k stay in registers, Re F_k is the
     //      summand of the odd outputs ----
     double ev[R3], cs[R3];
