@@ -304,7 +304,8 @@ int qgcm_qocdiag(qgcm_model *m, int32_t nsko, double *host, int64_t n);
  * mixed-layer heat diagnostics -- the values monnc_comp stores in the module `monitor`
  * (src/monitor_data.F:41-61) for monnc_out, computed on the device from the resident state.
  * ocjpos is the reference's 1-based T-row index.  couroc (Courant numbers, :1450) stays on the
- * host.  Single GPU (the reductions are not combined across y-slabs yet). */
+ * host.  On a y-slab partition this is a partition call (like qgcm_constr): every rank sums the
+ * rows it owns, the shares are added across the ranks and every rank returns the same report. */
 typedef struct qgcm_monitor_ocean {
   double wetmoc, watmoc, wepmoc, wapmoc, entmoc, enamoc;
   double etamoc[QGCM_NLMAX], et2moc[QGCM_NLMAX], ddtpeoc[QGCM_NLMAX], pkenoc, utauoc;

@@ -185,24 +185,28 @@ __global__ void __launch_bounds__(256) k_mon_v(const double *p, const double *pm
   row_store<6>(v, out + j, pitch);
 }
 
-// genint's outer sum over the row sums (:1180-1207)
-static double rows_int(const double *row, int ny, double facsn) {
-  double answer = 0.0;
-  for (int j = 1; j < ny - 1; ++j) answer = answer + row[j];
-  return answer + facsn * (row[0] + row[ny - 1]);
-}
+// Slot layout of the per-row sums (pitch = local nyp):
+//   T 6 (wekto, |wekto|, sst*wekto, sst, sst min, sst max)      rows: T
+//   P 4 (wekpo, |wekpo|, entoc, |entoc|)                        rows: p
+//   eta 4 per interface (eta, eta^2, eta*etadot, eta*entoc)     rows: p
+//   pq 4 per layer (po, qo, po min, po max)                     rows: p
+//   u 7 per layer (u*del2, u*del4, u^2, u*udot, um^2, u*taux, jet sum)   rows: T
+//   v 6 per layer (v*del2, v*del4, v^2, v*vdot, vm^2, v*tauy)           rows: p
+struct MonLayout {
+  int nl, oT, oP, oE, oQ, oU, oV, nslot;
+  explicit MonLayout(int nl_) : nl(nl_) {
+    oT = 0; oP = 6; oE = 10; oQ = oE + 4 * (nl - 1); oU = oQ + 4 * nl; oV = oU + 7 * nl; nslot = oV + 6 * nl;
+  }
+  bool t_rows(int slot) const { return slot < oP || (slot >= oU && slot < oV); }   // defined on nyt rows
+};
 
-void launch_monnc_ocean(qgcm_model *m, qgcm_monitor_ocean *r) {
-  std::memset(r, 0, sizeof(*r));
-  if (!m->has_ocean) return;
-  if (m->nranks > 1) throw std::runtime_error("qgcm_monnc_ocean: the reductions are not combined across y-slabs yet (single GPU)");
+// launches the row kernels of one rank and brings the row sums and the two corner values of
+// po per layer to the host
+static void mon_rows(qgcm_model *m, const MonLayout &L, std::vector<double> &h, double *corner) {
   const Grid &g = m->go;
-  const qgcm_config &c = m->cfg;
   const int nl = g.nl, nxp = g.nxp, nyp = g.nyp, nxt = g.nxt, nyt = g.nyt, ld = g.ld;
   const size_t pitch = nyp;
-  // row-sum slots: T 6 | P 4 | eta 4 per interface | pq 4 per layer | u 7 per layer | v 6 per layer
-  const int oT = 0, oP = 6, oE = 10, oQ = oE + 4 * (nl - 1), oU = oQ + 4 * nl, oV = oU + 7 * nl, nslot = oV + 6 * nl;
-  const size_t need = (size_t)nslot * pitch;
+  const size_t need = (size_t)L.nslot * pitch;
   if (m->mon_elems < need) {
     m->d_mon = (double *)dalloc(m, sizeof(double) * need);
     m->mon_elems = need;
@@ -210,107 +214,208 @@ void launch_monnc_ocean(qgcm_model *m, qgcm_monitor_ocean *r) {
   double *rows = m->d_mon;
   const double *po = m->F("po"), *pom = m->F("pom"), *qo = m->F("qo");
   const double rdxf0 = g.rdxf0, dto = m->dto;
-  QG_LAUNCH(m, "k_mon_t", nyt, 256, 0, k_mon_t, m->F("wekto"), m->F("sst"), nxt, ld, rows + oT * pitch, pitch);
-  QG_LAUNCH(m, "k_mon_p", nyp, 256, 0, k_mon_p, m->F("wekpo"), m->F("entoc"), nxp, ld, rows + oP * pitch, pitch);
+  QG_LAUNCH(m, "k_mon_t", nyt, 256, 0, k_mon_t, m->F("wekto"), m->F("sst"), nxt, ld, rows + L.oT * pitch, pitch);
+  QG_LAUNCH(m, "k_mon_p", nyp, 256, 0, k_mon_p, m->F("wekpo"), m->F("entoc"), nxp, ld, rows + L.oP * pitch, pitch);
   for (int k = 0; k < nl - 1; ++k) {
     const double rgp = 1.0 / m->lo.gp[k];
     QG_LAUNCH(m, "k_mon_eta", nyp, 256, 0, k_mon_eta, po + (size_t)k * g.lsz, po + (size_t)(k + 1) * g.lsz, pom + (size_t)k * g.lsz,
-              pom + (size_t)(k + 1) * g.lsz, m->F("entoc"), rgp, rgp / dto, nxp, ld, rows + (size_t)(oE + 4 * k) * pitch, pitch);
+              pom + (size_t)(k + 1) * g.lsz, m->F("entoc"), rgp, rgp / dto, nxp, ld, rows + (size_t)(L.oE + 4 * k) * pitch, pitch);
   }
   if (!m->d_monf) m->d_monf = (double *)dalloc(m, sizeof(double) * 4 * g.lsz);
   double *ugm = m->d_monf, *vgm = ugm + g.lsz, *d2 = vgm + g.lsz, *d4 = d2 + g.lsz;
   const dim3 full((nxp + 255) / 256, nyp);
   for (int k = 0; k < nl; ++k) {
     const double *pk = po + (size_t)k * g.lsz, *pmk = pom + (size_t)k * g.lsz;
-    QG_LAUNCH(m, "k_mon_pq", nyp, 256, 0, k_mon_pq, pk, qo + (size_t)k * g.lsz, nxp, ld, rows + (size_t)(oQ + 4 * k) * pitch, pitch);
+    QG_LAUNCH(m, "k_mon_pq", nyp, 256, 0, k_mon_pq, pk, qo + (size_t)k * g.lsz, nxp, ld, rows + (size_t)(L.oQ + 4 * k) * pitch, pitch);
     QG_LAUNCH(m, "k_mon_geo", full, 256, 0, k_mon_geo, pmk, ugm, vgm, g, rdxf0);
+    // at the inner edge of a y-slab the one-sided formulas spoil del2 on the edge row and del4
+    // on two rows: halo rows (three per edge), never owned ones
     QG_LAUNCH(m, "k_mon_lap", dim3((nxp + 255) / 256, nyt), 256, 0, k_mon_lap, ugm, d2, nxp, nyt, ld, g.cyclic, g.dxm2);
     QG_LAUNCH(m, "k_mon_lap", dim3((nxp + 255) / 256, nyt), 256, 0, k_mon_lap, d2, d4, nxp, nyt, ld, g.cyclic, g.dxm2);
     QG_LAUNCH(m, "k_mon_u", nyt, 256, 0, k_mon_u, pk, pmk, ugm, d2, d4, m->F("tauxo"), rdxf0, rdxf0 / dto, nxp, ld,
-              rows + (size_t)(oU + 7 * k) * pitch, pitch);
+              rows + (size_t)(L.oU + 7 * k) * pitch, pitch);
     QG_LAUNCH(m, "k_mon_lap", dim3((nxt + 255) / 256, nyp), 256, 0, k_mon_lap, vgm, d2, nxt, nyp, ld, g.cyclic, g.dxm2);
     QG_LAUNCH(m, "k_mon_lap", dim3((nxt + 255) / 256, nyp), 256, 0, k_mon_lap, d2, d4, nxt, nyp, ld, g.cyclic, g.dxm2);
     QG_LAUNCH(m, "k_mon_v", nyp, 256, 0, k_mon_v, pk, pmk, vgm, d2, d4, m->F("tauyo"), rdxf0, rdxf0 / dto, nxt, ld,
-              rows + (size_t)(oV + 6 * k) * pitch, pitch);
+              rows + (size_t)(L.oV + 6 * k) * pitch, pitch);
   }
-  std::vector<double> h(need);
-  double corner[2 * NLMAX];       // po(1,1,k), po(1,nypo,k)
+  h.resize(need);
   QG_CUDA(cudaMemcpyAsync(h.data(), rows, sizeof(double) * need, cudaMemcpyDeviceToHost, m->stream));
   for (int k = 0; k < nl; ++k) {
-    QG_CUDA(cudaMemcpyAsync(&corner[2 * k], po + (size_t)k * g.lsz, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
-    QG_CUDA(cudaMemcpyAsync(&corner[2 * k + 1], po + (size_t)k * g.lsz + (size_t)(nyp - 1) * ld, sizeof(double), cudaMemcpyDeviceToHost,
-                            m->stream));
+    corner[2 * k] = corner[2 * k + 1] = 0.0;
+    if (g.wall_s())
+      QG_CUDA(cudaMemcpyAsync(&corner[2 * k], po + (size_t)k * g.lsz, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    if (g.wall_n())
+      QG_CUDA(cudaMemcpyAsync(&corner[2 * k + 1], po + (size_t)k * g.lsz + (size_t)(nyp - 1) * ld, sizeof(double), cudaMemcpyDeviceToHost,
+                              m->stream));
   }
   QG_CUDA(cudaStreamSynchronize(m->stream));
-  auto row = [&](int slot) { return h.data() + (size_t)slot * pitch; };
-  const double ocnorm = g.norm, rhooc = c.rhooc, fnot = m->fnot;
-  // Ekman velocity, entrainment (:498-543)
-  r->wetmoc = rows_int(row(oT + 0), nyt, 1.0) * ocnorm;
-  r->watmoc = rows_int(row(oT + 1), nyt, 1.0) * ocnorm;
-  r->wepmoc = rows_int(row(oP + 0), nyp, 0.5) * ocnorm;
-  r->wapmoc = rows_int(row(oP + 1), nyp, 0.5) * ocnorm;
-  r->entmoc = rows_int(row(oP + 2), nyp, 0.5) * ocnorm;
-  r->enamoc = rows_int(row(oP + 3), nyp, 0.5) * ocnorm;
-  // interface displacements (:547-583)
-  for (int k = 0; k < nl - 1; ++k) {
-    r->etamoc[k] = rows_int(row(oE + 4 * k), nyp, 0.5) * ocnorm;
-    r->et2moc[k] = rows_int(row(oE + 4 * k + 1), nyp, 0.5) * ocnorm;
-    r->ddtpeoc[k] = rhooc * m->lo.gp[k] * rows_int(row(oE + 4 * k + 2), nyp, 0.5);
-    if (k == 0) r->pkenoc = rhooc * m->lo.gp[0] * rows_int(row(oE + 3), nyp, 0.5) * ocnorm;
+}
+
+// What a rank contributes: per sum slot the sum over the interior rows it owns (genint's inner
+// rows, :1180-1190) and the values of the global southern / northern row if it owns them; its
+// extrema, jet candidates and corner values in a one-hot block per rank.  Every entry combines
+// across ranks by addition.
+struct MonShare {
+  std::vector<double> v;
+  int nsum, ngat;           // 3 per sum slot + 2*nl corners | per rank: sst min/max, po min/max, jet value/row per layer
+};
+static void mon_share(qgcm_model *m, const MonLayout &L, const std::vector<double> &h, const double *corner, MonShare &S) {
+  const Grid &g = m->go;
+  const int nl = g.nl, nranks = m->nranks, rank = m->rank;
+  const size_t pitch = g.nyp;
+  S.nsum = 3 * L.nslot + 2 * nl;
+  S.ngat = 2 + 4 * nl;
+  S.v.assign((size_t)S.nsum + (size_t)nranks * S.ngat, 0.0);
+  double *gat = S.v.data() + S.nsum + (size_t)rank * S.ngat;
+  auto owned = [&](bool trows, int &j0, int &j1, int &nyg) {
+    nyg = trows ? g.nyp_g - 1 : g.nyp_g;
+    j0 = g.own0;
+    j1 = std::min(g.own1, (trows ? g.nyt : g.nyp));
+  };
+  for (int slot = 0; slot < L.nslot; ++slot) {
+    int j0, j1, nyg;
+    owned(L.t_rows(slot), j0, j1, nyg);
+    const double *row = h.data() + (size_t)slot * pitch;
+    double in = 0.0;
+    for (int j = j0; j < j1; ++j) {
+      const int jg = g.jg0 + j;
+      if (jg == 0) S.v[3 * slot + 1] = row[j];
+      else if (jg == nyg - 1) S.v[3 * slot + 2] = row[j];
+      else in = in + row[j];
+    }
+    S.v[3 * slot] = in;
   }
-  // wind work (:588-617)
+  for (int k = 0; k < nl; ++k) {
+    S.v[3 * L.nslot + 2 * k] = corner[2 * k];
+    S.v[3 * L.nslot + 2 * k + 1] = corner[2 * k + 1];
+  }
+  // extrema and jet candidates over owned rows
+  int j0, j1, nyg;
+  owned(true, j0, j1, nyg);
+  double lo = 1.0e30, hi = -1.0e30;
+  for (int j = j0; j < j1; ++j) {
+    lo = std::min(lo, h[(size_t)(L.oT + 4) * pitch + j]);
+    hi = std::max(hi, h[(size_t)(L.oT + 5) * pitch + j]);
+  }
+  gat[0] = lo; gat[1] = hi;
+  for (int k = 0; k < nl; ++k) {
+    int p0, p1, nypg;
+    owned(false, p0, p1, nypg);
+    lo = 1.0e30; hi = -1.0e30;
+    for (int j = p0; j < p1; ++j) {
+      lo = std::min(lo, h[(size_t)(L.oQ + 4 * k + 2) * pitch + j]);
+      hi = std::max(hi, h[(size_t)(L.oQ + 4 * k + 3) * pitch + j]);
+    }
+    gat[2 + 4 * k] = lo; gat[2 + 4 * k + 1] = hi;
+    // largest |zonal mean u| among the owned T rows: first strict maximum, as :696-704
+    double best = 0.0; int brow = 0;
+    const double *uj = h.data() + (size_t)(L.oU + 7 * k + 6) * pitch;
+    for (int j = j0; j < j1; ++j) {
+      const double val = std::fabs(uj[j]) / (double)g.nxt;
+      if (val > best) { best = val; brow = g.jg0 + j + 1; }
+    }
+    gat[2 + 4 * k + 2] = best; gat[2 + 4 * k + 3] = (double)brow;
+  }
+}
+
+// the reference's scalar algebra on the combined sums (src/monitor_diag.F:498-821)
+static void mon_finish(qgcm_model *m, const MonLayout &L, const MonShare &S, qgcm_monitor_ocean *r) {
+  std::memset(r, 0, sizeof(*r));
+  const Grid &g = m->go;
+  const qgcm_config &c = m->cfg;
+  const int nl = g.nl, nranks = m->nranks;
+  const double ocnorm = g.norm, rhooc = c.rhooc, fnot = m->fnot;
+  auto gi = [&](int slot, double facsn) { return S.v[3 * slot] + facsn * (S.v[3 * slot + 1] + S.v[3 * slot + 2]); };   // genint :1205
+  auto gat = [&](int rk, int i) { return S.v[(size_t)S.nsum + (size_t)rk * S.ngat + i]; };
+  r->wetmoc = gi(L.oT + 0, 1.0) * ocnorm;
+  r->watmoc = gi(L.oT + 1, 1.0) * ocnorm;
+  r->wepmoc = gi(L.oP + 0, 0.5) * ocnorm;
+  r->wapmoc = gi(L.oP + 1, 0.5) * ocnorm;
+  r->entmoc = gi(L.oP + 2, 0.5) * ocnorm;
+  r->enamoc = gi(L.oP + 3, 0.5) * ocnorm;
+  for (int k = 0; k < nl - 1; ++k) {
+    r->etamoc[k] = gi(L.oE + 4 * k, 0.5) * ocnorm;
+    r->et2moc[k] = gi(L.oE + 4 * k + 1, 0.5) * ocnorm;
+    r->ddtpeoc[k] = rhooc * m->lo.gp[k] * gi(L.oE + 4 * k + 2, 0.5);
+    if (k == 0) r->pkenoc = rhooc * m->lo.gp[0] * gi(L.oE + 3, 0.5) * ocnorm;
+  }
   {
-    const double utaux = rows_int(row(oU + 5), nyt, 1.0), vtauy = rows_int(row(oV + 5), nyp, 0.5);
+    const double utaux = gi(L.oU + 5, 1.0), vtauy = gi(L.oV + 5, 0.5);
     r->utauoc = rhooc * (vtauy + utaux) * ocnorm;
   }
-  // layers (:620-752)
   for (int k = 0; k < nl; ++k) {
     const double hk = m->lo.h[k];
-    const double *u = row(oU + 7 * k), *v = row(oV + 6 * k);
-    const double u2diss = rows_int(u, nyt, 1.0), u4diss = rows_int(u + pitch, nyt, 1.0);
-    const double uke = rows_int(u + 2 * pitch, nyt, 1.0), ukedot = rows_int(u + 3 * pitch, nyt, 1.0);
-    const double v2diss = rows_int(v, nyp, 0.5), v4diss = rows_int(v + pitch, nyp, 0.5);
-    const double vke = rows_int(v + 2 * pitch, nyp, 0.5), vkedot = rows_int(v + 3 * pitch, nyp, 0.5);
-    r->pavgoc[k] = rows_int(row(oQ + 4 * k), nyp, 0.5) * ocnorm;
-    r->qavgoc[k] = rows_int(row(oQ + 4 * k + 1), nyp, 0.5) * ocnorm;
+    const int u = L.oU + 7 * k, v = L.oV + 6 * k;
+    const double u2diss = gi(u, 1.0), u4diss = gi(u + 1, 1.0), uke = gi(u + 2, 1.0), ukedot = gi(u + 3, 1.0);
+    const double v2diss = gi(v, 0.5), v4diss = gi(v + 1, 0.5), vke = gi(v + 2, 0.5), vkedot = gi(v + 3, 0.5);
+    r->pavgoc[k] = gi(L.oQ + 4 * k, 0.5) * ocnorm;
+    r->qavgoc[k] = gi(L.oQ + 4 * k + 1, 0.5) * ocnorm;
     r->ah2doc[k] = -rhooc * m->lo.ah2[k] * hk * (u2diss + v2diss) * ocnorm;
     r->ah4doc[k] = rhooc * m->lo.ah4[k] * hk * (u4diss + v4diss) * ocnorm;
     r->kealoc[k] = 0.5 * rhooc * hk * (uke + vke) * ocnorm;
     r->ddtkeoc[k] = rhooc * hk * (ukedot + vkedot) * ocnorm;
-    // jet position: largest |zonal mean u| (:696-704)
-    const double *uj = u + 6 * pitch;
+    double pomin = 1.0e30, pomax = -1.0e30;
     r->ocjpos[k] = 0;
     r->ocjval[k] = 0.0;
-    for (int j = 0; j < nyt; ++j) {
-      const double val = std::fabs(uj[j]) / (double)nxt;
-      if (val > r->ocjval[k]) { r->ocjpos[k] = j + 1; r->ocjval[k] = val; }
+    for (int rk = 0; rk < nranks; ++rk) {       // ranks hold increasing rows: the first strict maximum wins
+      pomin = std::min(pomin, gat(rk, 2 + 4 * k));
+      pomax = std::max(pomax, gat(rk, 2 + 4 * k + 1));
+      if (gat(rk, 2 + 4 * k + 2) > r->ocjval[k]) {
+        r->ocjval[k] = gat(rk, 2 + 4 * k + 2);
+        r->ocjpos[k] = (int32_t)gat(rk, 2 + 4 * k + 3);
+      }
     }
-    double pomin = 1.0e30, pomax = -1.0e30;
-    const double *lo = row(oQ + 4 * k + 2), *hi = row(oQ + 4 * k + 3);
-    for (int j = 0; j < nyp; ++j) { pomin = std::min(pomin, lo[j]); pomax = std::max(pomax, hi[j]); }
-    const double poref = (fnot > 0.0) ? corner[2 * k] : corner[2 * k + 1];
+    const double ps = S.v[3 * L.nslot + 2 * k], pn = S.v[3 * L.nslot + 2 * k + 1];   // po(1,1,k), po(1,nypo,k)
+    const double poref = (fnot > 0.0) ? ps : pn;
     double psiext = std::min(pomin / fnot, pomax / fnot);
     r->osfmin[k] = 1.0e-6 * hk * (psiext - poref / fnot);
     psiext = std::max(pomin / fnot, pomax / fnot);
     r->osfmax[k] = 1.0e-6 * hk * (psiext - poref / fnot);
-    r->occirc[k] = 1.0e-6 * hk * (corner[2 * k] - corner[2 * k + 1]) / fnot;
+    r->occirc[k] = 1.0e-6 * hk * (ps - pn) / fnot;
   }
-  // bottom drag (:755-783)
   {
-    const double u2 = rows_int(row(oU + 7 * (nl - 1) + 4), nyt, 1.0), v2 = rows_int(row(oV + 6 * (nl - 1) + 4), nyp, 0.5);
+    const double u2 = gi(L.oU + 7 * (nl - 1) + 4, 1.0), v2 = gi(L.oV + 6 * (nl - 1) + 4, 0.5);
     r->btdgoc = 0.5 * rhooc * c.delek * std::fabs(fnot) * (u2 + v2) * ocnorm;
   }
-  // mixed layer (:788-812)
   r->sstmin = 1.0e30;
   r->sstmax = -1.0e30;
-  for (int j = 0; j < nyt; ++j) {
-    r->sstmin = std::min(r->sstmin, row(oT + 4)[j]);
-    r->sstmax = std::max(r->sstmax, row(oT + 5)[j]);
+  for (int rk = 0; rk < nranks; ++rk) {
+    r->sstmin = std::min(r->sstmin, gat(rk, 0));
+    r->sstmax = std::max(r->sstmax, gat(rk, 1));
   }
-  r->hfmloc = rhooc * c.cpoc * rows_int(row(oT + 2), nyt, 1.0) * ocnorm;
-  r->tmlmoc = rows_int(row(oT + 3), nyt, 1.0) * ocnorm;
+  r->hfmloc = rhooc * c.cpoc * gi(L.oT + 2, 1.0) * ocnorm;
+  r->tmlmoc = gi(L.oT + 3, 1.0) * ocnorm;
   r->occtot = 0.0;
   for (int k = 0; k < nl; ++k) r->occtot = r->occtot + r->occirc[k];
+}
+
+// On a y-slab partition every rank sums the rows it owns and the shares are added across the
+// ranks (in chunks of the all-reduce payload; this runs once per model day).
+void launch_monnc_ocean(qgcm_model *m, qgcm_monitor_ocean *rep) {
+  std::memset(rep, 0, sizeof(*rep));
+  if (!m->has_ocean) return;
+  const Ranks ms = ranks_of(m);
+  const MonLayout L(m->go.nl);
+  std::vector<MonShare> S(ms.size());
+  for (size_t r = 0; r < ms.size(); ++r) {
+    std::vector<double> h;
+    double corner[2 * NLMAX];
+    mon_rows(ms[r], L, h, corner);
+    mon_share(ms[r], L, h, corner, S[r]);
+  }
+  if (m->nranks > 1) {
+    const size_t n = S[0].v.size();
+    for (size_t off = 0; off < n; off += PEER_VEC) {
+      const size_t len = std::min((size_t)PEER_VEC, n - off);
+      std::vector<std::vector<double>> part(ms.size());
+      for (size_t r = 0; r < ms.size(); ++r) part[r].assign(S[r].v.begin() + off, S[r].v.begin() + off + len);
+      comm_allreduce_host(ms, part);
+      for (size_t r = 0; r < ms.size(); ++r) std::copy(part[r].begin(), part[r].end(), S[r].v.begin() + off);
+    }
+  }
+  for (size_t r = 0; r < ms.size(); ++r)
+    if (ms[r] == m) mon_finish(m, L, S[r], rep);
 }
 
 }  // namespace qg

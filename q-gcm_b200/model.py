@@ -317,6 +317,9 @@ class SlabGroup:
     def tav_counts(self):
         return self.ranks[0].tav_counts()
 
+    def monnc_ocean(self):
+        return self.ranks[0].monnc_ocean()      # a partition call: the ranks' row sums are combined
+
     def qocdiag(self, nsko):
         out = None
         for m in self.ranks:      # each rank fills the sub-sampled rows it owns

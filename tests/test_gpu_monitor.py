@@ -83,3 +83,21 @@ def test_monnc_ocean_coupled(qg, pyorc):
     for m in (gpu, cpu):
         m.run(1, p.nstr)
     check(gpu, cpu, p, cfg, "cpl_dg")
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+def test_monnc_ocean_over_slabs(qg, pyorc, nranks):
+    """every rank sums the rows it owns; the shares are added across the ranks"""
+    p = small_configs(qg)["box_natl1km"] if nranks == 8 else small_configs(qg)["box_dg"]
+    cfg = qg.build_config(p)
+    grp = qg.SlabGroup(cfg, nranks)
+    cpu = pyorc.Oracle(cfg)
+    for m in (grp, cpu):
+        qg.synth.init_model(m, p, cfg, "random")
+        m.run(1, 2 * p.nstr)
+    check(grp, cpu, p, cfg, "%d slabs" % nranks)
+    for m in (grp, cpu):
+        m.run(2 * p.nstr + 1, 3 * p.nstr)
+    for name in ("po", "qo", "sst"):
+        e = np.linalg.norm(grp.get_field(name) - cpu.get_field(name)) / np.linalg.norm(cpu.get_field(name))
+        assert e <= 1e-11, (nranks, name, e)
