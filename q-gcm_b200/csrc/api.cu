@@ -308,6 +308,8 @@ static void set_field_async(qgcm_model *m, const char *name, const double *host,
                               f.ny, cudaMemcpyHostToDevice, m->copy_stream));
   }
   m->pending.push_back(name);
+  if (std::strcmp(name, "ddynoc") == 0) m->ddynoc_flat = false;     // contents unknown until inspected: read the field
+  if (std::strcmp(name, "ddynat") == 0) m->ddynat_flat = false;
 }
 static void commit_fields(qgcm_model *m) {
   if (m->pending.empty()) return;
@@ -360,7 +362,15 @@ int qgcm_field_size(qgcm_model *m, const char *name, int64_t *n) {
   QG_TRY(qgcm_model::Field &f = lookup(m, name, -1); *n = (int64_t)f.nx * f.nyg * f.nl);
 }
 int qgcm_set_field(qgcm_model *m, const char *name, const double *host, int64_t n) {
-  QG_TRY(copy_field(m, lookup(m, name, n), const_cast<double *>(host), true));
+  QG_TRY({
+    copy_field(m, lookup(m, name, n), const_cast<double *>(host), true);
+    const bool oc = std::strcmp(name, "ddynoc") == 0, at = std::strcmp(name, "ddynat") == 0;
+    if (oc || at) {      // flat bottom / no orography: remember it (invert.cu skips the field)
+      bool flat = true;
+      for (int64_t i = 0; i < n && flat; ++i) flat = (host[i] == 0.0);
+      (oc ? m->ddynoc_flat : m->ddynat_flat) = flat;
+    }
+  });
 }
 int qgcm_get_field(qgcm_model *m, const char *name, double *host, int64_t n) {
   QG_TRY(copy_field(m, lookup(m, name, n), host, false));

@@ -34,9 +34,11 @@ __global__ void __launch_bounds__(256) k_l2m(InvArgs a) {
     const double2 q = *reinterpret_cast<const double2 *>(a.q + k * g.lsz + idx);
     ql[k] = make_double2(q.x - betay, q.y - betay);
   }
-  const double2 dd = *reinterpret_cast<const double2 *>(a.ddyn + idx);
-  ql[kbot].x = ql[kbot].x - dd.x;
-  ql[kbot].y = ql[kbot].y - dd.y;
+  if (a.ddyn) {      // null over a flat bottom: x - 0 is x, so the field need not be read
+    const double2 dd = *reinterpret_cast<const double2 *>(a.ddyn + idx);
+    ql[kbot].x = ql[kbot].x - dd.x;
+    ql[kbot].y = ql[kbot].y - dd.y;
+  }
   for (int m = 0; m < nl; ++m) {
     double qx = 0.0, qy = 0.0;
     for (int k = 0; k < nl; ++k) {
@@ -310,7 +312,9 @@ static void fill_inv(qgcm_model *m, bool atmos, InvArgs &a) {
   a.beta = m->beta;
   for (int i = 0; i < NLMAX * NLMAX; ++i) { a.ctl2m[i] = lc.ctl2m[i]; a.ctm2l[i] = lc.ctm2l[i]; }
   a.q = m->F(atmos ? "qa" : "qo");
-  a.ddyn = m->F(atmos ? "ddynat" : "ddynoc");
+  // topset 'flat' (src/topsubs.F:99-107, :248-257) leaves ddyn identically zero: qgcm_set_field
+  // notes that and the right-hand side kernel then skips one of its seven field passes
+  a.ddyn = (atmos ? m->ddynat_flat : m->ddynoc_flat) ? nullptr : m->F(atmos ? "ddynat" : "ddynoc");
   a.yrel = atmos ? m->yparel : m->yporel;
   a.wrk = atmos ? m->wrk_a : m->wrk_o;
   a.hom = (!atmos && !g.cyclic) ? m->F("ochom") : nullptr;

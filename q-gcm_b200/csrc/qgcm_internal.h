@@ -241,6 +241,7 @@ struct qgcm_model {
   cudaEvent_t ev_copy = nullptr, ev_step = nullptr;
   std::map<std::string, double *> shadow;
   std::vector<std::string> pending;
+  bool ddynoc_flat = true, ddynat_flat = true;   // the topography field is identically zero (its device buffer starts zeroed)
   double *wrk_o = nullptr, *wrk_a = nullptr;   // modal work arrays [nl][nyp][ld]
   double *xfo = nullptr, *xfa = nullptr, *sstnew = nullptr, *astnew = nullptr, *hmnew = nullptr;
   std::vector<void *> allocs;

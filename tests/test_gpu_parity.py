@@ -151,6 +151,33 @@ def test_drift_curve_against_twin_envelope(qg, pyorc, case):
             json.dump(curve, f, indent=1)
 
 
+@pytest.mark.parametrize("case", ["box_dg", "chan_so"])
+def test_bottom_topography(qg, pyorc, case):
+    """a non-zero ddynoc = f0*dtopoc/H_nlo (src/topsubs.F:454): over a flat bottom the right-hand
+    side kernel skips that field, so the other branch needs its own case"""
+    p = small_configs(qg)[case]
+    cfg = qg.build_config(p)
+    gpu, cpu = qg.Model(cfg), pyorc.Oracle(cfg)
+    x = np.linspace(0.0, 1.0, p.nxpo)[:, None]
+    y = np.linspace(0.0, 1.0, p.nypo)[None, :]
+    ridge = 200.0 * np.exp(-((y - 0.4) / 0.15) ** 2) * (1.0 + 0.3 * np.cos(2 * np.pi * x))     # m, periodic in x
+    ddyn = p.fnot / p.hoc[p.nlo - 1] * ridge
+    for m in (gpu, cpu):
+        st = qg.synth.ocean_state(p, cfg, "random", qg.synth.SEED, min(1.0, (p.nxto * p.dxo) / 4.8e6 * 4.0))
+        st["ddynoc"] = ddyn
+        for k, v in st.items():
+            m.set_field(k, v)
+        m.constr(); m.qcomp_ocean(); m.xforc(); m.homsol()
+        m.run(1, 2 * p.nstr)
+    compare(gpu, cpu, OCEAN_CHECK, label=case + " with topography")
+    # and back to a flat bottom on the same models
+    for m in (gpu, cpu):
+        m.set_field("ddynoc", np.zeros_like(ddyn))
+        m.qcomp_ocean()
+        m.run(2 * p.nstr + 1, 3 * p.nstr)
+    compare(gpu, cpu, OCEAN_CHECK, label=case + " flat again")
+
+
 def test_eddy_state(qg, pyorc):
     """the fork's own Gaussian-eddy initial state with zero forcing"""
     p = small_configs(qg)["box_dg"]
