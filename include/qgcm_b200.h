@@ -296,15 +296,15 @@ int qgcm_get_field_sub(qgcm_model *m, const char *name, int32_t nsk, double *hos
 int qgcm_qocdiag_size(qgcm_model *m, int32_t nsko, int64_t *n);
 int qgcm_qocdiag(qgcm_model *m, int32_t nsko, double *host, int64_t n);
 
-/* monnc_comp, ocean section, src/monitor_diag.F:480-840 (called every dgnday, src/q-gcm.F:1442):
+/* monnc_comp, ocean section with couroc, src/monitor_diag.F:480-840, :1450-1925 (called every dgnday, src/q-gcm.F:1442):
  * Ekman-velocity and entrainment means, interface displacement moments, wind work, per-layer
  * kinetic energy, its tendency and the del-sqd/del-4th dissipation integrals (with the one-sided
  * boundary Laplacians of del4bx/del4ch, :900-1120, and the weighted area integral genint,
  * :1160-1210), jet position, stream-function extrema, layer transports, bottom drag and the
  * mixed-layer heat diagnostics -- the values monnc_comp stores in the module `monitor`
  * (src/monitor_data.F:41-61) for monnc_out, computed on the device from the resident state.
- * ocjpos is the reference's 1-based T-row index.  couroc (Courant numbers, :1450) stays on the
- * host.  On a y-slab partition this is a partition call (like qgcm_constr): every rank sums the
+ * ocjpos is the reference's 1-based T-row index.  The call includes couroc (:1450-1925), which
+ * monnc_comp invokes at :826.  On a y-slab partition this is a partition call (like qgcm_constr): every rank sums the
  * rows it owns, the shares are added across the ranks and every rank returns the same report. */
 typedef struct qgcm_monitor_ocean {
   double wetmoc, watmoc, wepmoc, wapmoc, entmoc, enamoc;
@@ -314,6 +314,10 @@ typedef struct qgcm_monitor_ocean {
   double pavgoc[QGCM_NLMAX], qavgoc[QGCM_NLMAX], ah2doc[QGCM_NLMAX], ah4doc[QGCM_NLMAX];
   double kealoc[QGCM_NLMAX], ddtkeoc[QGCM_NLMAX], osfmin[QGCM_NLMAX], osfmax[QGCM_NLMAX], occirc[QGCM_NLMAX];
   double btdgoc, sstmin, sstmax, hfmloc, tmlmoc, occtot;
+  /* couroc, src/monitor_diag.F:1450-1925: velocity extrema at the cell faces and the largest
+   * Courant number, mixed layer (geostrophic + Ekman) and every QG layer */
+  double umminoc, ummaxoc, vmminoc, vmmaxoc, cnmloc;
+  double ugminoc[QGCM_NLMAX], ugmaxoc[QGCM_NLMAX], vgminoc[QGCM_NLMAX], vgmaxoc[QGCM_NLMAX], cnqgoc[QGCM_NLMAX];
 } qgcm_monitor_ocean;
 int qgcm_monnc_ocean(qgcm_model *m, qgcm_monitor_ocean *rep);
 

@@ -107,6 +107,7 @@ struct Model {
   void qocdiag(int nsko, double *out);
   // src/monitor_diag.F:480-840
   void monnc_ocean(qgcm_monitor_ocean *rep);
+  void couroc(qgcm_monitor_ocean *rep);
   void run(int64_t nt_first, int64_t nt_last);
 };
 

@@ -237,6 +237,61 @@ void Model::monnc_ocean(qgcm_monitor_ocean *r) {
   // total circulation (:818-821)
   r->occtot = 0.0;
   for (int k = 1; k <= nlo; ++k) r->occtot = r->occtot + r->occirc[k - 1];
+  couroc(r);      // :826
+}
+
+// src/monitor_diag.F:1450-1925.  The reference walks every T cell with a recurrence on the
+// western/eastern face velocities (um, up) and the southern/northern ones (vm, vp), with the
+// boundary faces set by the configuration (no normal flow; Ekman outflow for the mixed layer
+// under sb_hflux / nb_hflux; periodic in a channel); restated here as one loop over the cells
+// with the face values spelled out.  Extrema do not depend on the order of the cells.  (In the
+// mixed-layer rows j = 1 and j = nyto the reference leaves the western face out of umin/umax,
+// :1566-1593, :1667-1690; the eastern face of the same row carries the same value in a channel
+// and both are zero in a box, so the extrema are the same.)
+void Model::couroc(qgcm_monitor_ocean *r) {
+  const double uvgfac = c.ycexp * rdxof0, rhf0hm = 0.5 / (fnot * c.hmoc);
+  for (int k = 0; k <= nlo; ++k) {       // k = 0: mixed layer (po(:,:,1) + Ekman), k >= 1: QG layer k
+    const bool ml = (k == 0);
+    const int kk = ml ? 1 : k;
+    const double ug = ml ? uvgfac : rdxof0, rh = ml ? rhf0hm : 0.0;
+    auto uface = [&](int f, int j) {     // face f = 1..nxto+1 of T row j
+      if (!cyclic && (f == 1 || f == nxto + 1)) return 0.0;
+      double u = -ug * (po[IX3(f, j + 1, kk, nxpo, nypo)] - po[IX3(f, j, kk, nxpo, nypo)]);
+      if (ml) u = u + rh * (tauyo[IX2(f, j + 1, nxpo)] + tauyo[IX2(f, j, nxpo)]);
+      return u;
+    };
+    auto vface = [&](int i, int jf) {    // face jf = 1..nyto+1 of T column i
+      if (jf == 1) return (ml && sb_hflux) ? -rh * (tauxo[IX2(i + 1, 1, nxpo)] + tauxo[IX2(i, 1, nxpo)]) : 0.0;
+      if (jf == nyto + 1) return (ml && nb_hflux) ? -rh * (tauxo[IX2(i + 1, nyto + 1, nxpo)] + tauxo[IX2(i, nyto + 1, nxpo)]) : 0.0;
+      double v = ug * (po[IX3(i + 1, jf, kk, nxpo, nypo)] - po[IX3(i, jf, kk, nxpo, nypo)]);
+      if (ml) v = v - rh * (tauxo[IX2(i + 1, jf, nxpo)] + tauxo[IX2(i, jf, nxpo)]);
+      return v;
+    };
+    double umin = 1.0e30, umax = -1.0e30, vmin = 1.0e30, vmax = -1.0e30, vsqmax = -1.0e30;
+    for (int j = 1; j <= nyto; ++j) {
+      double up = uface(1, j);
+      umin = std::min(umin, up);
+      umax = std::max(umax, up);
+      for (int i = 1; i <= nxto; ++i) {
+        const double um = up;
+        up = uface(i + 1, j);
+        const double vm = vface(i, j), vp = vface(i, j + 1);
+        umin = std::min(umin, up);
+        umax = std::max(umax, up);
+        vmin = std::min(vmin, std::min(vm, vp));
+        vmax = std::max(vmax, std::max(vm, vp));
+        const double velsqd = (um + up) * (um + up) + (vm + vp) * (vm + vp);
+        vsqmax = std::max(vsqmax, velsqd);
+      }
+    }
+    if (ml) {
+      r->umminoc = umin; r->ummaxoc = umax; r->vmminoc = vmin; r->vmmaxoc = vmax;
+      r->cnmloc = hdxom1 * dto * std::sqrt(vsqmax);
+    } else {
+      r->ugminoc[k - 1] = umin; r->ugmaxoc[k - 1] = umax; r->vgminoc[k - 1] = vmin; r->vgmaxoc[k - 1] = vmax;
+      r->cnqgoc[k - 1] = hdxom1 * dto * std::sqrt(vsqmax);
+    }
+  }
 }
 
 }  // namespace orc

@@ -185,6 +185,41 @@ __global__ void __launch_bounds__(256) k_mon_v(const double *p, const double *pm
   row_store<6>(v, out + j, pitch);
 }
 
+// couroc (:1450-1925): face velocities of one layer on T row j -- western/eastern faces um, up
+// and southern/northern faces vm, vp of every cell, with the boundary faces set by the
+// configuration -- reduced to the row's extrema of u and v and its largest (um+up)^2 + (vm+vp)^2.
+// ekman: the mixed layer (po(:,:,1) scaled by ycexp plus the Ekman drift); else a QG layer.
+__global__ void __launch_bounds__(256) k_mon_cour(const double *p, const double *taux, const double *tauy, Grid g, int ekman, int sflux,
+                                                  int nflux, double ug, double rh, double *out, size_t pitch) {
+  const int j = blockIdx.x, ld = g.ld, nxt = g.nxt;
+  const bool south = (j == 0 && g.wall_s()), north = (j == g.nyt - 1 && g.wall_n());
+  const double *p0 = p + (size_t)j * ld, *p1 = p0 + ld;
+  const double *tx0 = taux + (size_t)j * ld, *tx1 = tx0 + ld, *ty0 = tauy + (size_t)j * ld, *ty1 = ty0 + ld;
+  auto uface = [&](int f) {
+    if (!g.cyclic && (f == 0 || f == nxt)) return 0.0;
+    double u = -ug * (p1[f] - p0[f]);
+    if (ekman) u = u + rh * (ty1[f] + ty0[f]);
+    return u;
+  };
+  double ulo = 1.0e30, uhi = -1.0e30, vlo = 1.0e30, vhi = -1.0e30, vsq = -1.0e30;
+  for (int i = threadIdx.x; i < nxt; i += 256) {
+    const double um = uface(i), up = uface(i + 1);
+    double vm, vp;
+    if (south) vm = (ekman && sflux) ? -rh * (tx0[i + 1] + tx0[i]) : 0.0;
+    else { vm = ug * (p0[i + 1] - p0[i]); if (ekman) vm = vm - rh * (tx0[i + 1] + tx0[i]); }
+    if (north) vp = (ekman && nflux) ? -rh * (tx1[i + 1] + tx1[i]) : 0.0;
+    else { vp = ug * (p1[i + 1] - p1[i]); if (ekman) vp = vp - rh * (tx1[i + 1] + tx1[i]); }
+    if (i == 0) { ulo = fmin(ulo, um); uhi = fmax(uhi, um); }
+    ulo = fmin(ulo, up); uhi = fmax(uhi, up);
+    vlo = fmin(vlo, fmin(vm, vp)); vhi = fmax(vhi, fmax(vm, vp));
+    vsq = fmax(vsq, (um + up) * (um + up) + (vm + vp) * (vm + vp));
+  }
+  row_minmax(ulo, uhi, out + j, out + pitch + j);
+  row_minmax(vlo, vhi, out + 2 * pitch + j, out + 3 * pitch + j);
+  double dummy;
+  row_minmax(0.0, vsq, &dummy, out + 4 * pitch + j);
+}
+
 // Slot layout of the per-row sums (pitch = local nyp):
 //   T 6 (wekto, |wekto|, sst*wekto, sst, sst min, sst max)      rows: T
 //   P 4 (wekpo, |wekpo|, entoc, |entoc|)                        rows: p
@@ -192,10 +227,13 @@ __global__ void __launch_bounds__(256) k_mon_v(const double *p, const double *pm
 //   pq 4 per layer (po, qo, po min, po max)                     rows: p
 //   u 7 per layer (u*del2, u*del4, u^2, u*udot, um^2, u*taux, jet sum)   rows: T
 //   v 6 per layer (v*del2, v*del4, v^2, v*vdot, vm^2, v*tauy)           rows: p
+//   cour 5 per layer incl. the mixed layer (u min, u max, v min, v max, largest speed^2)   rows: T; extrema only
 struct MonLayout {
-  int nl, oT, oP, oE, oQ, oU, oV, nslot;
+  int nl, oT, oP, oE, oQ, oU, oV, oC, nsum, nslot;
   explicit MonLayout(int nl_) : nl(nl_) {
-    oT = 0; oP = 6; oE = 10; oQ = oE + 4 * (nl - 1); oU = oQ + 4 * nl; oV = oU + 7 * nl; nslot = oV + 6 * nl;
+    oT = 0; oP = 6; oE = 10; oQ = oE + 4 * (nl - 1); oU = oQ + 4 * nl; oV = oU + 7 * nl; oC = oV + 6 * nl;
+    nsum = oC;                       // slots below oC take part in the area sums
+    nslot = oC + 5 * (nl + 1);
   }
   bool t_rows(int slot) const { return slot < oP || (slot >= oU && slot < oV); }   // defined on nyt rows
 };
@@ -239,6 +277,14 @@ static void mon_rows(qgcm_model *m, const MonLayout &L, std::vector<double> &h, 
     QG_LAUNCH(m, "k_mon_v", nyp, 256, 0, k_mon_v, pk, pmk, vgm, d2, d4, m->F("tauyo"), rdxf0, rdxf0 / dto, nxt, ld,
               rows + (size_t)(L.oV + 6 * k) * pitch, pitch);
   }
+  {
+    const double rh = 0.5 / (m->fnot * m->cfg.hmoc);
+    QG_LAUNCH(m, "k_mon_cour", nyt, 256, 0, k_mon_cour, po, m->F("tauxo"), m->F("tauyo"), g, 1, (int)m->sb_hflux, (int)m->nb_hflux,
+              m->cfg.ycexp * rdxf0, rh, rows + (size_t)L.oC * pitch, pitch);
+    for (int k = 0; k < nl; ++k)
+      QG_LAUNCH(m, "k_mon_cour", nyt, 256, 0, k_mon_cour, po + (size_t)k * g.lsz, m->F("tauxo"), m->F("tauyo"), g, 0, 0, 0, rdxf0, 0.0,
+                rows + (size_t)(L.oC + 5 * (k + 1)) * pitch, pitch);
+  }
   h.resize(need);
   QG_CUDA(cudaMemcpyAsync(h.data(), rows, sizeof(double) * need, cudaMemcpyDeviceToHost, m->stream));
   for (int k = 0; k < nl; ++k) {
@@ -264,8 +310,8 @@ static void mon_share(qgcm_model *m, const MonLayout &L, const std::vector<doubl
   const Grid &g = m->go;
   const int nl = g.nl, nranks = m->nranks, rank = m->rank;
   const size_t pitch = g.nyp;
-  S.nsum = 3 * L.nslot + 2 * nl;
-  S.ngat = 2 + 4 * nl;
+  S.nsum = 3 * L.nsum + 2 * nl;
+  S.ngat = 2 + 4 * nl + 5 * (nl + 1);
   S.v.assign((size_t)S.nsum + (size_t)nranks * S.ngat, 0.0);
   double *gat = S.v.data() + S.nsum + (size_t)rank * S.ngat;
   auto owned = [&](bool trows, int &j0, int &j1, int &nyg) {
@@ -273,7 +319,7 @@ static void mon_share(qgcm_model *m, const MonLayout &L, const std::vector<doubl
     j0 = g.own0;
     j1 = std::min(g.own1, (trows ? g.nyt : g.nyp));
   };
-  for (int slot = 0; slot < L.nslot; ++slot) {
+  for (int slot = 0; slot < L.nsum; ++slot) {
     int j0, j1, nyg;
     owned(L.t_rows(slot), j0, j1, nyg);
     const double *row = h.data() + (size_t)slot * pitch;
@@ -287,8 +333,8 @@ static void mon_share(qgcm_model *m, const MonLayout &L, const std::vector<doubl
     S.v[3 * slot] = in;
   }
   for (int k = 0; k < nl; ++k) {
-    S.v[3 * L.nslot + 2 * k] = corner[2 * k];
-    S.v[3 * L.nslot + 2 * k + 1] = corner[2 * k + 1];
+    S.v[3 * L.nsum + 2 * k] = corner[2 * k];
+    S.v[3 * L.nsum + 2 * k + 1] = corner[2 * k + 1];
   }
   // extrema and jet candidates over owned rows
   int j0, j1, nyg;
@@ -316,6 +362,19 @@ static void mon_share(qgcm_model *m, const MonLayout &L, const std::vector<doubl
       if (val > best) { best = val; brow = g.jg0 + j + 1; }
     }
     gat[2 + 4 * k + 2] = best; gat[2 + 4 * k + 3] = (double)brow;
+  }
+  // couroc: extrema over the owned T rows, mixed layer first
+  for (int k = 0; k <= nl; ++k) {
+    double e[5] = {1.0e30, -1.0e30, 1.0e30, -1.0e30, -1.0e30};
+    const double *cr = h.data() + (size_t)(L.oC + 5 * k) * pitch;
+    for (int j = j0; j < j1; ++j) {
+      e[0] = std::min(e[0], cr[j]);
+      e[1] = std::max(e[1], cr[pitch + j]);
+      e[2] = std::min(e[2], cr[2 * pitch + j]);
+      e[3] = std::max(e[3], cr[3 * pitch + j]);
+      e[4] = std::max(e[4], cr[4 * pitch + j]);
+    }
+    for (int q = 0; q < 5; ++q) gat[2 + 4 * nl + 5 * k + q] = e[q];
   }
 }
 
@@ -366,7 +425,7 @@ static void mon_finish(qgcm_model *m, const MonLayout &L, const MonShare &S, qgc
         r->ocjpos[k] = (int32_t)gat(rk, 2 + 4 * k + 3);
       }
     }
-    const double ps = S.v[3 * L.nslot + 2 * k], pn = S.v[3 * L.nslot + 2 * k + 1];   // po(1,1,k), po(1,nypo,k)
+    const double ps = S.v[3 * L.nsum + 2 * k], pn = S.v[3 * L.nsum + 2 * k + 1];   // po(1,1,k), po(1,nypo,k)
     const double poref = (fnot > 0.0) ? ps : pn;
     double psiext = std::min(pomin / fnot, pomax / fnot);
     r->osfmin[k] = 1.0e-6 * hk * (psiext - poref / fnot);
@@ -388,6 +447,24 @@ static void mon_finish(qgcm_model *m, const MonLayout &L, const MonShare &S, qgc
   r->tmlmoc = gi(L.oT + 3, 1.0) * ocnorm;
   r->occtot = 0.0;
   for (int k = 0; k < nl; ++k) r->occtot = r->occtot + r->occirc[k];
+  // couroc (:1711-1715, :1915-1919)
+  const double cfac = g.hdxm1 * m->dto;
+  for (int k = 0; k <= nl; ++k) {
+    double e[5] = {1.0e30, -1.0e30, 1.0e30, -1.0e30, -1.0e30};
+    for (int rk = 0; rk < nranks; ++rk) {
+      const int b = 2 + 4 * nl + 5 * k;
+      e[0] = std::min(e[0], gat(rk, b)); e[1] = std::max(e[1], gat(rk, b + 1));
+      e[2] = std::min(e[2], gat(rk, b + 2)); e[3] = std::max(e[3], gat(rk, b + 3));
+      e[4] = std::max(e[4], gat(rk, b + 4));
+    }
+    if (k == 0) {
+      r->umminoc = e[0]; r->ummaxoc = e[1]; r->vmminoc = e[2]; r->vmmaxoc = e[3];
+      r->cnmloc = cfac * std::sqrt(e[4]);
+    } else {
+      r->ugminoc[k - 1] = e[0]; r->ugmaxoc[k - 1] = e[1]; r->vgminoc[k - 1] = e[2]; r->vgmaxoc[k - 1] = e[3];
+      r->cnqgoc[k - 1] = cfac * std::sqrt(e[4]);
+    }
+  }
 }
 
 // On a y-slab partition every rank sums the rows it owns and the shares are added across the

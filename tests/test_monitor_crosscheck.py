@@ -133,3 +133,41 @@ def test_monnc_ocean_matches_numpy(qg, pyorc, case):
                 assert r[name][k] == v, (case, name, k)
             else:
                 close(r[name][k], v, "%s[%d]" % (name, k), tol=1e-8 if name in ("ddtkeoc", "ddtpeoc", "ah2doc", "ah4doc") else 1e-9)
+
+
+@pytest.mark.parametrize("case", ["box_dg", "chan_so"])
+def test_couroc_matches_numpy(qg, pyorc, case):
+    """face velocities, their extrema and the Courant numbers of couroc (src/monitor_diag.F:1450-1925)"""
+    p = small_configs(qg)[case]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.run(1, 2 * p.nstr)
+    r = m.monnc_ocean().as_dict()
+    nxp, nyp, nl = p.nxpo, p.nypo, p.nlo
+    po = m.get_field("po", (nxp, nyp, nl))
+    tx, ty = m.get_field("tauxo", (nxp, nyp)), m.get_field("tauyo", (nxp, nyp))
+    rdxf0 = 1.0 / (p.dxo * p.fnot)
+    rh = 0.5 / (p.fnot * p.hmoc)
+    cyc = p.has("cyclic_ocean")
+
+    def faces(pk, ug, ekman):
+        u = -ug * (pk[:, 1:] - pk[:, :-1])                    # (nxp, nyt): every x face of every T row
+        v = ug * (pk[1:, :] - pk[:-1, :])                     # (nxt, nyp): every y face of every T column
+        if ekman:
+            u = u + rh * (ty[:, 1:] + ty[:, :-1])
+            v = v - rh * (tx[1:, :] + tx[:-1, :])
+        if not cyc:
+            u[0] = u[-1] = 0.0
+        v[:, 0] = -rh * (tx[1:, 0] + tx[:-1, 0]) if (ekman and p.has("sb_hflux")) else 0.0
+        v[:, -1] = -rh * (tx[1:, -1] + tx[:-1, -1]) if (ekman and p.has("nb_hflux")) else 0.0
+        vsq = (u[:-1] + u[1:]) ** 2 + (v[:, :-1] + v[:, 1:]) ** 2
+        return u.min(), u.max(), v.min(), v.max(), 0.5 / p.dxo * p.dto * np.sqrt(vsq.max())
+
+    want = faces(po[:, :, 0], p.ycexp * rdxf0, True)
+    got = (r["umminoc"], r["ummaxoc"], r["vmminoc"], r["vmmaxoc"], r["cnmloc"])
+    assert np.allclose(got, want, rtol=1e-12, atol=0.0), (case, got, want)
+    for k in range(nl):
+        want = faces(po[:, :, k], rdxf0, False)
+        got = (r["ugminoc"][k], r["ugmaxoc"][k], r["vgminoc"][k], r["vgmaxoc"][k], r["cnqgoc"][k])
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-300), (case, k, got, want)
