@@ -320,6 +320,23 @@ typedef struct qgcm_monitor_ocean {
   double ugminoc[QGCM_NLMAX], ugmaxoc[QGCM_NLMAX], vgminoc[QGCM_NLMAX], vgmaxoc[QGCM_NLMAX], cnqgoc[QGCM_NLMAX];
 } qgcm_monitor_ocean;
 int qgcm_monnc_ocean(qgcm_model *m, qgcm_monitor_ocean *rep);
+/* monnc_comp, atmosphere section with courat, src/monitor_diag.F:186-478, :1215-1445.  The
+ * reference's own slips are reproduced: vkedot integrates the stale workspace attwk3, which
+ * holds del-sqd of the lagged v (:391, :404), and the atmosphere has no del-sqd dissipation
+ * term.  davgat is the mean of dtopat (src/topsubs.F:429-430), formed from the device field.
+ * atstpos is the 1-based T-row index. */
+typedef struct qgcm_monitor_atmos {
+  double wetmat, watmat, wepmat, wapmat;
+  double entmat[QGCM_NLMAX], enamat[QGCM_NLMAX], etamat[QGCM_NLMAX], et2mat[QGCM_NLMAX], ddtpeat[QGCM_NLMAX], pkenat[QGCM_NLMAX];
+  double utauat;
+  double atstval[QGCM_NLMAX];
+  int32_t atstpos[QGCM_NLMAX], reserved_i;
+  double pavgat[QGCM_NLMAX], qavgat[QGCM_NLMAX], ah4dat[QGCM_NLMAX], kealat[QGCM_NLMAX], ddtkeat[QGCM_NLMAX];
+  double tmlmat, hmlmat, hcmlat, astmin, astmax, tmaooc, olrtop, davgat;
+  double umminat, ummaxat, vmminat, vmmaxat, cnmlat;
+  double ugminat[QGCM_NLMAX], ugmaxat[QGCM_NLMAX], vgminat[QGCM_NLMAX], vgmaxat[QGCM_NLMAX], cnqgat[QGCM_NLMAX];
+} qgcm_monitor_atmos;
+int qgcm_monnc_atmos(qgcm_model *m, qgcm_monitor_atmos *rep);
 
 /* ---- instrumentation ---------------------------------------------------------- */
 

@@ -107,6 +107,7 @@ int orc_qocdiag(Model *m, int32_t nsko, double *out, int64_t n) {
   });
 }
 int orc_monnc_ocean(Model *m, qgcm_monitor_ocean *r) { ORC_TRY(m->monnc_ocean(r)); }
+int orc_monnc_atmos(Model *m, qgcm_monitor_atmos *r) { ORC_TRY(m->monnc_atmos(r)); }
 int orc_tav_counts(Model *m, int32_t *nsumat, int32_t *nsumoc, int32_t *nsum_ocavg) {
   *nsumat = m->nsumat;
   *nsumoc = m->nsumoc;

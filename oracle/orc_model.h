@@ -108,6 +108,8 @@ struct Model {
   // src/monitor_diag.F:480-840
   void monnc_ocean(qgcm_monitor_ocean *rep);
   void couroc(qgcm_monitor_ocean *rep);
+  void monnc_atmos(qgcm_monitor_atmos *rep);
+  void courat(qgcm_monitor_atmos *rep);
   void run(int64_t nt_first, int64_t nt_last);
 };
 

@@ -294,4 +294,199 @@ void Model::couroc(qgcm_monitor_ocean *r) {
   }
 }
 
+// atmosphere section of monnc_comp, src/monitor_diag.F:186-478
+void Model::monnc_atmos(qgcm_monitor_atmos *r) {
+  std::memset(r, 0, sizeof(*r));
+  if (ocean_only) return;
+  const double rhoat = c.rhoat, cpat = c.cpat;
+  const size_t np = (size_t)nxpa * nypa;
+  vec attwk1((size_t)nxta * nypa), attwk2((size_t)nxta * nypa), attwk3((size_t)nxta * nypa);
+  vec atpwk1(np), atpwk2(np), atpwk3(np), etaat(np), ugat((size_t)nxpa * nyta), vgat((size_t)nxta * nypa);
+  // Ekman velocity (:204-226)
+  r->wetmat = genint(wekta.data(), nxta, nyta, 1.0, 1.0);
+  for (int j = 1; j <= nyta; ++j)
+    for (int i = 1; i <= nxta; ++i) attwk1[IX2(i, j, nxta)] = std::fabs(wekta[IX2(i, j, nxta)]);
+  r->watmat = genint(attwk1.data(), nxta, nyta, 1.0, 1.0);
+  r->wepmat = genint(wekpa.data(), nxpa, nypa, 0.5, 0.5);
+  for (size_t n = 0; n < np; ++n) atpwk1[n] = std::fabs(wekpa[n]);
+  r->wapmat = genint(atpwk1.data(), nxpa, nypa, 0.5, 0.5);
+  r->wetmat = r->wetmat * atnorm;
+  r->watmat = r->watmat * atnorm;
+  r->wepmat = r->wepmat * atnorm;
+  r->wapmat = r->wapmat * atnorm;
+  // entrainment across interface 1 (:233-249)
+  r->entmat[0] = genint(entat.data(), nxpa, nypa, 0.5, 0.5);
+  for (size_t n = 0; n < np; ++n) atpwk1[n] = std::fabs(entat[n]);
+  r->enamat[0] = genint(atpwk1.data(), nxpa, nypa, 0.5, 0.5);
+  r->entmat[0] = r->entmat[0] * atnorm;
+  r->enamat[0] = r->enamat[0] * atnorm;
+  // interface displacements (:254-290)
+  for (int k = 1; k <= nla - 1; ++k) {
+    const double rgpat = 1.0 / c.gpat[k - 1];
+    for (int j = 1; j <= nypa; ++j)
+      for (int i = 1; i <= nxpa; ++i) {
+        const double eta = rgpat * (pa[IX3(i, j, k, nxpa, nypa)] - pa[IX3(i, j, k + 1, nxpa, nypa)]);
+        const double etadot = (rgpat / dta) * (pa[IX3(i, j, k, nxpa, nypa)] - pa[IX3(i, j, k + 1, nxpa, nypa)] -
+                                               pam[IX3(i, j, k, nxpa, nypa)] + pam[IX3(i, j, k + 1, nxpa, nypa)]);
+        etaat[IX2(i, j, nxpa)] = eta;
+        atpwk1[IX2(i, j, nxpa)] = eta * eta;
+        atpwk2[IX2(i, j, nxpa)] = eta * etadot;
+        atpwk3[IX2(i, j, nxpa)] = eta * entat[IX2(i, j, nxpa)];
+      }
+    const double etaint = genint(etaat.data(), nxpa, nypa, 0.5, 0.5);
+    double et2now = genint(atpwk1.data(), nxpa, nypa, 0.5, 0.5);
+    const double et2dot = genint(atpwk2.data(), nxpa, nypa, 0.5, 0.5);
+    r->etamat[k - 1] = etaint * atnorm;
+    et2now = et2now * atnorm;
+    r->pkenat[k - 1] = 0.0;
+    r->ddtpeat[k - 1] = rhoat * c.gpat[k - 1] * et2dot;
+    r->et2mat[k - 1] = et2now;
+    if (k == 1) {
+      const double pkeint = genint(atpwk3.data(), nxpa, nypa, 0.5, 0.5);
+      r->pkenat[0] = rhoat * c.gpat[0] * pkeint * atnorm;
+    }
+  }
+  // wind work (:298-326)
+  for (int j = 1; j <= nyta; ++j)
+    for (int i = 1; i <= nxpa; ++i) {
+      const double ugeos = -rdxaf0 * (pa[IX3(i, j + 1, 1, nxpa, nypa)] - pa[IX3(i, j, 1, nxpa, nypa)]);
+      const double tauxav = 0.5 * (tauxa[IX2(i, j + 1, nxpa)] + tauxa[IX2(i, j, nxpa)]);
+      atpwk1[IX2(i, j, nxpa)] = ugeos * tauxav;
+    }
+  const double utaux = genint(atpwk1.data(), nxpa, nyta, 0.5, 1.0);
+  for (int j = 1; j <= nypa; ++j)
+    for (int i = 1; i <= nxta; ++i) {
+      const double vgeos = rdxaf0 * (pa[IX3(i + 1, j, 1, nxpa, nypa)] - pa[IX3(i, j, 1, nxpa, nypa)]);
+      const double tauyav = 0.5 * (tauya[IX2(i + 1, j, nxpa)] + tauya[IX2(i, j, nxpa)]);
+      attwk1[IX2(i, j, nxta)] = vgeos * tauyav;
+    }
+  const double vtauy = genint(attwk1.data(), nxta, nypa, 1.0, 0.5);
+  r->utauat = rhoat * (vtauy + utaux) * atnorm;
+  // layers (:330-418)
+  for (int k = 1; k <= nla; ++k) {
+    for (int j = 1; j <= nyta; ++j)
+      for (int i = 1; i <= nxpa; ++i) ugat[IX2(i, j, nxpa)] = -rdxaf0 * (pam[IX3(i, j + 1, k, nxpa, nypa)] - pam[IX3(i, j, k, nxpa, nypa)]);
+    lap_onesided(ugat.data(), nxpa, nyta, dxam2, true, atpwk3.data());      // del4ch: del-sqd in atpwk3,
+    lap_onesided(atpwk3.data(), nxpa, nyta, dxam2, true, atpwk1.data());    // del-4th in atpwk1
+    for (int j = 1; j <= nypa; ++j)
+      for (int i = 1; i <= nxta; ++i) vgat[IX2(i, j, nxta)] = rdxaf0 * (pam[IX3(i + 1, j, k, nxpa, nypa)] - pam[IX3(i, j, k, nxpa, nypa)]);
+    lap_onesided(vgat.data(), nxta, nypa, dxam2, true, attwk3.data());      // del-sqd in attwk3,
+    lap_onesided(attwk3.data(), nxta, nypa, dxam2, true, attwk2.data());    // del-4th in attwk2
+    vec ujeta(nyta + 1);
+    for (int j = 1; j <= nyta; ++j) {
+      double ujet = 0.0, ugeos = 0.0;
+      for (int i = 1; i <= nxpa; ++i) {
+        ugeos = -rdxaf0 * (pa[IX3(i, j + 1, k, nxpa, nypa)] - pa[IX3(i, j, k, nxpa, nypa)]);
+        const double ugdot = -(rdxaf0 / dta) * (pa[IX3(i, j + 1, k, nxpa, nypa)] - pa[IX3(i, j, k, nxpa, nypa)] -
+                                                pam[IX3(i, j + 1, k, nxpa, nypa)] + pam[IX3(i, j, k, nxpa, nypa)]);
+        ujet = ujet + ugeos;
+        atpwk1[IX2(i, j, nxpa)] = ugeos * atpwk1[IX2(i, j, nxpa)];
+        atpwk2[IX2(i, j, nxpa)] = ugeos * ugeos;
+        atpwk3[IX2(i, j, nxpa)] = ugeos * ugdot;
+      }
+      ujet = ujet - ugeos;
+      ujeta[j] = std::fabs(ujet) / (double)nxta;
+    }
+    r->atstpos[k - 1] = 0;
+    r->atstval[k - 1] = 0.0;
+    for (int j = 1; j <= nyta; ++j)
+      if (ujeta[j] > r->atstval[k - 1]) {
+        r->atstpos[k - 1] = j;
+        r->atstval[k - 1] = ujeta[j];
+      }
+    const double u4diss = genint(atpwk1.data(), nxpa, nyta, 0.5, 1.0);
+    const double uke = genint(atpwk2.data(), nxpa, nyta, 0.5, 1.0);
+    const double ukedot = genint(atpwk3.data(), nxpa, nyta, 0.5, 1.0);
+    for (int j = 1; j <= nypa; ++j)
+      for (int i = 1; i <= nxta; ++i) {
+        const double vgeos = rdxaf0 * (pa[IX3(i + 1, j, k, nxpa, nypa)] - pa[IX3(i, j, k, nxpa, nypa)]);
+        // vgdot is computed at :387-388 but never stored: attwk3 keeps del-sqd of the lagged v
+        attwk1[IX2(i, j, nxta)] = vgeos * attwk2[IX2(i, j, nxta)];
+        attwk2[IX2(i, j, nxta)] = vgeos * vgeos;
+      }
+    const double v4diss = genint(attwk1.data(), nxta, nypa, 1.0, 0.5);
+    const double vke = genint(attwk2.data(), nxta, nypa, 1.0, 0.5);
+    const double vkedot = genint(attwk3.data(), nxta, nypa, 1.0, 0.5);
+    const double pint = genint(&pa[IX3(1, 1, k, nxpa, nypa)], nxpa, nypa, 0.5, 0.5);
+    const double qint = genint(&qa[IX3(1, 1, k, nxpa, nypa)], nxpa, nypa, 0.5, 0.5);
+    r->pavgat[k - 1] = pint * atnorm;
+    r->qavgat[k - 1] = qint * atnorm;
+    r->ah4dat[k - 1] = rhoat * c.ah4at[k - 1] * c.hat[k - 1] * (u4diss + v4diss) * atnorm;
+    r->kealat[k - 1] = 0.5 * rhoat * c.hat[k - 1] * (uke + vke) * atnorm;
+    r->ddtkeat[k - 1] = rhoat * c.hat[k - 1] * (ukedot + vkedot) * atnorm;
+  }
+  // mixed layer (:424-451)
+  r->tmlmat = genint(ast.data(), nxta, nyta, 1.0, 1.0);
+  r->hmlmat = genint(hmixa.data(), nxta, nyta, 1.0, 1.0);
+  r->astmin = 1.0e30;
+  r->astmax = -1.0e30;
+  for (int j = 1; j <= nyta; ++j)
+    for (int i = 1; i <= nxta; ++i) {
+      r->astmin = std::min(r->astmin, ast[IX2(i, j, nxta)]);
+      r->astmax = std::max(r->astmax, ast[IX2(i, j, nxta)]);
+      attwk1[IX2(i, j, nxta)] = ast[IX2(i, j, nxta)] * hmixa[IX2(i, j, nxta)];
+    }
+  r->hcmlat = genint(attwk1.data(), nxta, nyta, 1.0, 1.0);
+  r->tmlmat = r->tmlmat * atnorm;
+  r->hmlmat = r->hmlmat * atnorm;
+  r->hcmlat = rhoat * cpat * r->hcmlat * atnorm;
+  // mean over the ocean (:454-461)
+  const int nxaooc = nxto / ndxr, nyaooc = nyto / ndxr;
+  double tmaooc = 0.0;
+  for (int j = ny1; j <= ny1 + nyaooc - 1; ++j)
+    for (int i = nx1; i <= nx1 + nxaooc - 1; ++i) tmaooc = tmaooc + ast[IX2(i, j, nxta)];
+  r->tmaooc = tmaooc / (double)(nxaooc * nyaooc);
+  // outgoing long wave radiation (:464-470); davgat as in src/topsubs.F:429-430
+  r->davgat = xintp(dtopat.data(), nxpa, nypa) * atnorm;
+  double olrtop = c.Bup[nla - 1] * (r->hmlmat - c.hmat) + c.Cup[nla - 1] * r->davgat + c.Dup[nla - 1] * r->tmlmat;
+  for (int i = 1; i <= nla - 1; ++i) olrtop = olrtop + c.Aup[(nla - 1) + nla * (i - 1)] * r->etamat[i - 1];
+  r->olrtop = olrtop;
+  courat(r);      // :475
+}
+
+// src/monitor_diag.F:1215-1445: as couroc for the periodic atmosphere; the mixed layer moves with
+// the geostrophic wind of layer 1 plus the Ekman velocities uekat, vekat, which also set v on
+// the zonal boundaries; the QG layers have v = 0 there
+void Model::courat(qgcm_monitor_atmos *r) {
+  for (int k = 0; k <= nla; ++k) {
+    const bool ml = (k == 0);
+    const int kk = ml ? 1 : k;
+    auto uface = [&](int f, int j) {
+      double u = -rdxaf0 * (pa[IX3(f, j + 1, kk, nxpa, nypa)] - pa[IX3(f, j, kk, nxpa, nypa)]);
+      if (ml) u = u + uekat[IX2(f, j, nxpa)];
+      return u;
+    };
+    auto vface = [&](int i, int jf) {
+      if (jf == 1 || jf == nyta + 1) return ml ? vekat[IX2(i, jf, nxta)] : 0.0;
+      double v = rdxaf0 * (pa[IX3(i + 1, jf, kk, nxpa, nypa)] - pa[IX3(i, jf, kk, nxpa, nypa)]);
+      if (ml) v = v + vekat[IX2(i, jf, nxta)];
+      return v;
+    };
+    double umin = 1.0e30, umax = -1.0e30, vmin = 1.0e30, vmax = -1.0e30, vsqmax = -1.0e30;
+    for (int j = 1; j <= nyta; ++j) {
+      double up = uface(1, j);
+      umin = std::min(umin, up);
+      umax = std::max(umax, up);
+      for (int i = 1; i <= nxta; ++i) {
+        const double um = up;
+        up = uface(i + 1, j);
+        const double vm = vface(i, j), vp = vface(i, j + 1);
+        umin = std::min(umin, up);
+        umax = std::max(umax, up);
+        vmin = std::min(vmin, std::min(vm, vp));
+        vmax = std::max(vmax, std::max(vm, vp));
+        const double velsqd = (um + up) * (um + up) + (vm + vp) * (vm + vp);
+        vsqmax = std::max(vsqmax, velsqd);
+      }
+    }
+    if (ml) {
+      r->umminat = umin; r->ummaxat = umax; r->vmminat = vmin; r->vmmaxat = vmax;
+      r->cnmlat = hdxam1 * dta * std::sqrt(vsqmax);
+    } else {
+      r->ugminat[k - 1] = umin; r->ugmaxat[k - 1] = umax; r->vgminat[k - 1] = vmin; r->vgmaxat[k - 1] = vmax;
+      r->cnqgat[k - 1] = hdxam1 * dta * std::sqrt(vsqmax);
+    }
+  }
+}
+
 }  // namespace orc

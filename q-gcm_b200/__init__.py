@@ -10,7 +10,7 @@ main program prepares before the loop (``params.py``: src/q-gcm.F:377-452,
 src/eigmode.f:41-440; ``synth.py``: SURVEY.md section 8d synthetic states).
 There is no CPU fallback: constructing a Model without the CUDA library raises.
 """
-from .abi import QgcmConfig, QgcmScalars, QgcmValidsReport, QgcmMonitorOcean, FLAGS, NLMAX  # noqa: F401
+from .abi import QgcmConfig, QgcmScalars, QgcmValidsReport, QgcmMonitorOcean, QgcmMonitorAtmos, FLAGS, NLMAX  # noqa: F401
 from .params import Params, named_config, build_config  # noqa: F401
 from .model import Model, CModel, SlabGroup, slab_config, slab_bounds, load_library, library_path  # noqa: F401
 from . import synth  # noqa: F401

@@ -89,3 +89,14 @@ class QgcmMonitorOcean(C.Structure):
             v = getattr(self, name)
             out[name] = list(v) if hasattr(v, "__len__") else v
         return out
+
+
+class QgcmMonitorAtmos(C.Structure):
+    _fields_ = _parse_struct(_TEXT, "qgcm_monitor_atmos")
+
+    def as_dict(self):
+        out = {}
+        for name, typ in self._fields_:
+            v = getattr(self, name)
+            out[name] = list(v) if hasattr(v, "__len__") else v
+        return out

@@ -521,6 +521,7 @@ int qgcm_get_field_sub(qgcm_model *m, const char *name, int32_t nsk, double *hos
 }
 
 int qgcm_monnc_ocean(qgcm_model *m, qgcm_monitor_ocean *rep) { QG_TRY(launch_monnc_ocean(m, rep)); }
+int qgcm_monnc_atmos(qgcm_model *m, qgcm_monitor_atmos *rep) { QG_TRY(launch_monnc_atmos(m, rep)); }
 int qgcm_qocdiag_size(qgcm_model *m, int32_t nsko, int64_t *n) { QG_TRY(qocdiag_size(m, nsko, n)); }
 int qgcm_qocdiag(qgcm_model *m, int32_t nsko, double *host, int64_t n) { QG_TRY(launch_qocdiag(m, nsko, host, n)); }
 

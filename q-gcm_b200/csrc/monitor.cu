@@ -153,14 +153,16 @@ __global__ void __launch_bounds__(256) k_mon_lap(const double *__restrict__ a, d
 // layer k, u points (nxp, nyt), W/E weight 0.5: ug*del2(ugm), ug*del4(ugm), ug^2, ug*ugdot, ugm^2,
 // ug*tauxav, and the zonal jet sum  (:593-601, :676-694, :759-766)
 __global__ void __launch_bounds__(256) k_mon_u(const double *p, const double *pm, const double *ugm, const double *d2, const double *d4,
-                                               const double *taux, double rdxf0, double rdxf0dt, int nxp, int ld, double *out, size_t pitch) {
+                                               const double *taux, double rdxf0, double rdxf0dt, int nxp, int ld, int atmos, double *out,
+                                               size_t pitch) {
   const int j = blockIdx.x;
   double v[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   for (int i = threadIdx.x; i < nxp; i += 256) {
     const size_t o = (size_t)j * ld + i;
     const double f = (i == 0 || i == nxp - 1) ? 0.5 : 1.0;
     const double ug = -rdxf0 * (p[o + ld] - p[o]);
-    const double ugdot = -rdxf0dt * (p[o + ld] - pm[o] - pm[o + ld] + pm[o]);     // as written at :676-677
+    // ocean: as written at :676-677 (its two pom(i,j,k) terms cancel); atmosphere: :354-355
+    const double ugdot = atmos ? -rdxf0dt * (p[o + ld] - p[o] - pm[o + ld] + pm[o]) : -rdxf0dt * (p[o + ld] - pm[o] - pm[o + ld] + pm[o]);
     v[0] += f * (ug * d2[o]); v[1] += f * (ug * d4[o]); v[2] += f * (ug * ug); v[3] += f * (ug * ugdot);
     v[4] += f * (ugm[o] * ugm[o]);
     v[5] += f * (ug * (0.5 * (taux[o + ld] + taux[o])));
@@ -171,14 +173,16 @@ __global__ void __launch_bounds__(256) k_mon_u(const double *p, const double *pm
 
 // layer k, v points (nxt, nyp), W/E weight 1  (:606-614, :700-712, :771-778)
 __global__ void __launch_bounds__(256) k_mon_v(const double *p, const double *pm, const double *vgm, const double *d2, const double *d4,
-                                               const double *tauy, double rdxf0, double rdxf0dt, int nxt, int ld, double *out, size_t pitch) {
+                                               const double *tauy, double rdxf0, double rdxf0dt, int nxt, int ld, int atmos, double *out,
+                                               size_t pitch) {
   const int j = blockIdx.x;
   double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   for (int i = threadIdx.x; i < nxt; i += 256) {
     const size_t o = (size_t)j * ld + i;
     const double vg = rdxf0 * (p[o + 1] - p[o]);
     const double vgdot = rdxf0dt * (p[o + 1] - p[o] - pm[o + 1] + pm[o]);
-    v[0] += vg * d2[o]; v[1] += vg * d4[o]; v[2] += vg * vg; v[3] += vg * vgdot;
+    // atmosphere: the reference integrates attwk3, which still holds del-sqd of the lagged v (:391, :404)
+    v[0] += vg * d2[o]; v[1] += vg * d4[o]; v[2] += vg * vg; v[3] += atmos ? d2[o] : vg * vgdot;
     v[4] += vgm[o] * vgm[o];
     v[5] += vg * (0.5 * (tauy[o + 1] + tauy[o]));
   }
@@ -189,8 +193,11 @@ __global__ void __launch_bounds__(256) k_mon_v(const double *p, const double *pm
 // and southern/northern faces vm, vp of every cell, with the boundary faces set by the
 // configuration -- reduced to the row's extrema of u and v and its largest (um+up)^2 + (vm+vp)^2.
 // ekman: the mixed layer (po(:,:,1) scaled by ycexp plus the Ekman drift); else a QG layer.
-__global__ void __launch_bounds__(256) k_mon_cour(const double *p, const double *taux, const double *tauy, Grid g, int ekman, int sflux,
-                                                  int nflux, double ug, double rh, double *out, size_t pitch) {
+// uek, vek non-null: the atmosphere's mixed layer (courat :1240-1310), which adds the Ekman
+// velocities at the faces and keeps vekat on the zonal boundaries.
+__global__ void __launch_bounds__(256) k_mon_cour(const double *p, const double *taux, const double *tauy, const double *uek,
+                                                  const double *vek, Grid g, int ekman, int sflux, int nflux, double ug, double rh,
+                                                  double *out, size_t pitch) {
   const int j = blockIdx.x, ld = g.ld, nxt = g.nxt;
   const bool south = (j == 0 && g.wall_s()), north = (j == g.nyt - 1 && g.wall_n());
   const double *p0 = p + (size_t)j * ld, *p1 = p0 + ld;
@@ -199,16 +206,25 @@ __global__ void __launch_bounds__(256) k_mon_cour(const double *p, const double 
     if (!g.cyclic && (f == 0 || f == nxt)) return 0.0;
     double u = -ug * (p1[f] - p0[f]);
     if (ekman) u = u + rh * (ty1[f] + ty0[f]);
+    if (uek) u = u + uek[(size_t)j * ld + f];
     return u;
   };
   double ulo = 1.0e30, uhi = -1.0e30, vlo = 1.0e30, vhi = -1.0e30, vsq = -1.0e30;
   for (int i = threadIdx.x; i < nxt; i += 256) {
     const double um = uface(i), up = uface(i + 1);
     double vm, vp;
-    if (south) vm = (ekman && sflux) ? -rh * (tx0[i + 1] + tx0[i]) : 0.0;
-    else { vm = ug * (p0[i + 1] - p0[i]); if (ekman) vm = vm - rh * (tx0[i + 1] + tx0[i]); }
-    if (north) vp = (ekman && nflux) ? -rh * (tx1[i + 1] + tx1[i]) : 0.0;
-    else { vp = ug * (p1[i + 1] - p1[i]); if (ekman) vp = vp - rh * (tx1[i + 1] + tx1[i]); }
+    if (south) vm = vek ? vek[(size_t)j * ld + i] : ((ekman && sflux) ? -rh * (tx0[i + 1] + tx0[i]) : 0.0);
+    else {
+      vm = ug * (p0[i + 1] - p0[i]);
+      if (ekman) vm = vm - rh * (tx0[i + 1] + tx0[i]);
+      if (vek) vm = vm + vek[(size_t)j * ld + i];
+    }
+    if (north) vp = vek ? vek[(size_t)(j + 1) * ld + i] : ((ekman && nflux) ? -rh * (tx1[i + 1] + tx1[i]) : 0.0);
+    else {
+      vp = ug * (p1[i + 1] - p1[i]);
+      if (ekman) vp = vp - rh * (tx1[i + 1] + tx1[i]);
+      if (vek) vp = vp + vek[(size_t)(j + 1) * ld + i];
+    }
     if (i == 0) { ulo = fmin(ulo, um); uhi = fmax(uhi, um); }
     ulo = fmin(ulo, up); uhi = fmax(uhi, up);
     vlo = fmin(vlo, fmin(vm, vp)); vhi = fmax(vhi, fmax(vm, vp));
@@ -218,6 +234,24 @@ __global__ void __launch_bounds__(256) k_mon_cour(const double *p, const double 
   row_minmax(vlo, vhi, out + 2 * pitch + j, out + 3 * pitch + j);
   double dummy;
   row_minmax(0.0, vsq, &dummy, out + 4 * pitch + j);
+}
+
+// atmosphere T grid: sums of wekta, |wekta|, ast*hmixa, ast, hmixa and of ast over the columns
+// above the ocean (zero outside the ocean's rows); extrema of ast  (:204-212, :424-461)
+__global__ void __launch_bounds__(256) k_mon_ta(const double *wekt, const double *ast, const double *hmix, int nxt, int ld, int i0, int i1,
+                                                int j0, int j1, double *out, size_t pitch) {
+  const int j = blockIdx.x;
+  const bool orow = (j >= j0 && j < j1);
+  double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, lo = 1.0e30, hi = -1.0e30;
+  for (int i = threadIdx.x; i < nxt; i += 256) {
+    const size_t o = (size_t)j * ld + i;
+    const double w = wekt[o], t = ast[o], h = hmix[o];
+    v[0] += w; v[1] += fabs(w); v[2] += t * h; v[3] += t; v[4] += h;
+    if (orow && i >= i0 && i < i1) v[5] += t;
+    lo = fmin(lo, t); hi = fmax(hi, t);
+  }
+  row_store<6>(v, out + j, pitch);
+  row_minmax(lo, hi, out + 6 * pitch + j, out + 7 * pitch + j);
 }
 
 // Slot layout of the per-row sums (pitch = local nyp):
@@ -270,19 +304,21 @@ static void mon_rows(qgcm_model *m, const MonLayout &L, std::vector<double> &h, 
     // on two rows: halo rows (three per edge), never owned ones
     QG_LAUNCH(m, "k_mon_lap", dim3((nxp + 255) / 256, nyt), 256, 0, k_mon_lap, ugm, d2, nxp, nyt, ld, g.cyclic, g.dxm2);
     QG_LAUNCH(m, "k_mon_lap", dim3((nxp + 255) / 256, nyt), 256, 0, k_mon_lap, d2, d4, nxp, nyt, ld, g.cyclic, g.dxm2);
-    QG_LAUNCH(m, "k_mon_u", nyt, 256, 0, k_mon_u, pk, pmk, ugm, d2, d4, m->F("tauxo"), rdxf0, rdxf0 / dto, nxp, ld,
+    QG_LAUNCH(m, "k_mon_u", nyt, 256, 0, k_mon_u, pk, pmk, ugm, d2, d4, m->F("tauxo"), rdxf0, rdxf0 / dto, nxp, ld, 0,
               rows + (size_t)(L.oU + 7 * k) * pitch, pitch);
     QG_LAUNCH(m, "k_mon_lap", dim3((nxt + 255) / 256, nyp), 256, 0, k_mon_lap, vgm, d2, nxt, nyp, ld, g.cyclic, g.dxm2);
     QG_LAUNCH(m, "k_mon_lap", dim3((nxt + 255) / 256, nyp), 256, 0, k_mon_lap, d2, d4, nxt, nyp, ld, g.cyclic, g.dxm2);
-    QG_LAUNCH(m, "k_mon_v", nyp, 256, 0, k_mon_v, pk, pmk, vgm, d2, d4, m->F("tauyo"), rdxf0, rdxf0 / dto, nxt, ld,
+    QG_LAUNCH(m, "k_mon_v", nyp, 256, 0, k_mon_v, pk, pmk, vgm, d2, d4, m->F("tauyo"), rdxf0, rdxf0 / dto, nxt, ld, 0,
               rows + (size_t)(L.oV + 6 * k) * pitch, pitch);
   }
   {
     const double rh = 0.5 / (m->fnot * m->cfg.hmoc);
-    QG_LAUNCH(m, "k_mon_cour", nyt, 256, 0, k_mon_cour, po, m->F("tauxo"), m->F("tauyo"), g, 1, (int)m->sb_hflux, (int)m->nb_hflux,
+    QG_LAUNCH(m, "k_mon_cour", nyt, 256, 0, k_mon_cour, po, m->F("tauxo"), m->F("tauyo"), (const double *)nullptr, (const double *)nullptr, g, 1,
+              (int)m->sb_hflux, (int)m->nb_hflux,
               m->cfg.ycexp * rdxf0, rh, rows + (size_t)L.oC * pitch, pitch);
     for (int k = 0; k < nl; ++k)
-      QG_LAUNCH(m, "k_mon_cour", nyt, 256, 0, k_mon_cour, po + (size_t)k * g.lsz, m->F("tauxo"), m->F("tauyo"), g, 0, 0, 0, rdxf0, 0.0,
+      QG_LAUNCH(m, "k_mon_cour", nyt, 256, 0, k_mon_cour, po + (size_t)k * g.lsz, m->F("tauxo"), m->F("tauyo"), (const double *)nullptr,
+                (const double *)nullptr, g, 0, 0, 0, rdxf0, 0.0,
                 rows + (size_t)(L.oC + 5 * (k + 1)) * pitch, pitch);
   }
   h.resize(need);
@@ -493,6 +529,139 @@ void launch_monnc_ocean(qgcm_model *m, qgcm_monitor_ocean *rep) {
   }
   for (size_t r = 0; r < ms.size(); ++r)
     if (ms[r] == m) mon_finish(m, L, S[r], rep);
+}
+
+// genint's outer sum over the row sums of a whole grid (:1180-1207)
+static double rows_int(const double *row, int ny, double facsn) {
+  double answer = 0.0;
+  for (int j = 1; j < ny - 1; ++j) answer = answer + row[j];
+  return answer + facsn * (row[0] + row[ny - 1]);
+}
+
+// ---- atmosphere section (src/monitor_diag.F:186-478) and courat (:1215-1445); one GPU ----
+void launch_monnc_atmos(qgcm_model *m, qgcm_monitor_atmos *r) {
+  std::memset(r, 0, sizeof(*r));
+  if (!m->has_atmos) return;
+  const Grid &g = m->ga;
+  const qgcm_config &c = m->cfg;
+  const int nl = g.nl, nxp = g.nxp, nyp = g.nyp, nxt = g.nxt, nyt = g.nyt, ld = g.ld;
+  const size_t pitch = nyp;
+  // slots: T 8 | P 4 | dtopat 4 | eta 4 per interface | pq 4 per layer | u 7 per layer | v 6 per layer | cour 5 per layer + mixed layer
+  const int oT = 0, oP = 8, oD = 12, oE = 16, oQ = oE + 4 * (nl - 1), oU = oQ + 4 * nl, oV = oU + 7 * nl, oC = oV + 6 * nl;
+  const int nslot = oC + 5 * (nl + 1);
+  const size_t need = (size_t)nslot * pitch;
+  if (m->mona_elems < need) {
+    m->d_mona = (double *)dalloc(m, sizeof(double) * need);
+    m->mona_elems = need;
+  }
+  if (!m->d_monaf) m->d_monaf = (double *)dalloc(m, sizeof(double) * 4 * g.lsz);
+  double *rows = m->d_mona;
+  double *ugm = m->d_monaf, *vgm = ugm + g.lsz, *d2 = vgm + g.lsz, *d4 = d2 + g.lsz;
+  const double *pa = m->F("pa"), *pam = m->F("pam"), *qa = m->F("qa");
+  const double rdxf0 = g.rdxf0, dta = m->dta;
+  const int nxaooc = m->go.nxt / c.ndxr, nyaooc = (m->go.nyp_g - 1) / c.ndxr;
+  QG_LAUNCH(m, "k_mon_ta", nyt, 256, 0, k_mon_ta, m->F("wekta"), m->F("ast"), m->F("hmixa"), nxt, ld, c.nx1 - 1, c.nx1 - 1 + nxaooc,
+            c.ny1 - 1, c.ny1 - 1 + nyaooc, rows + (size_t)oT * pitch, pitch);
+  QG_LAUNCH(m, "k_mon_p", nyp, 256, 0, k_mon_p, m->F("wekpa"), m->F("entat"), nxp, ld, rows + (size_t)oP * pitch, pitch);
+  QG_LAUNCH(m, "k_mon_p", nyp, 256, 0, k_mon_p, m->F("dtopat"), m->F("dtopat"), nxp, ld, rows + (size_t)oD * pitch, pitch);
+  for (int k = 0; k < nl - 1; ++k) {
+    const double rgp = 1.0 / m->la.gp[k];
+    // eta = rgp (pa_k - pa_k+1): the ocean kernel's (p_k+1 - p_k) with the sign carried by rgp (:259)
+    QG_LAUNCH(m, "k_mon_eta", nyp, 256, 0, k_mon_eta, pa + (size_t)k * g.lsz, pa + (size_t)(k + 1) * g.lsz, pam + (size_t)k * g.lsz,
+              pam + (size_t)(k + 1) * g.lsz, m->F("entat"), -rgp, rgp / dta, nxp, ld, rows + (size_t)(oE + 4 * k) * pitch, pitch);
+  }
+  const dim3 full((nxp + 255) / 256, nyp);
+  for (int k = 0; k < nl; ++k) {
+    const double *pk = pa + (size_t)k * g.lsz, *pmk = pam + (size_t)k * g.lsz;
+    QG_LAUNCH(m, "k_mon_pq", nyp, 256, 0, k_mon_pq, pk, qa + (size_t)k * g.lsz, nxp, ld, rows + (size_t)(oQ + 4 * k) * pitch, pitch);
+    QG_LAUNCH(m, "k_mon_geo", full, 256, 0, k_mon_geo, pmk, ugm, vgm, g, rdxf0);
+    QG_LAUNCH(m, "k_mon_lap", dim3((nxp + 255) / 256, nyt), 256, 0, k_mon_lap, ugm, d2, nxp, nyt, ld, 1, g.dxm2);
+    QG_LAUNCH(m, "k_mon_lap", dim3((nxp + 255) / 256, nyt), 256, 0, k_mon_lap, d2, d4, nxp, nyt, ld, 1, g.dxm2);
+    QG_LAUNCH(m, "k_mon_u", nyt, 256, 0, k_mon_u, pk, pmk, ugm, d2, d4, m->F("tauxa"), rdxf0, rdxf0 / dta, nxp, ld, 1,
+              rows + (size_t)(oU + 7 * k) * pitch, pitch);
+    QG_LAUNCH(m, "k_mon_lap", dim3((nxt + 255) / 256, nyp), 256, 0, k_mon_lap, vgm, d2, nxt, nyp, ld, 1, g.dxm2);
+    QG_LAUNCH(m, "k_mon_lap", dim3((nxt + 255) / 256, nyp), 256, 0, k_mon_lap, d2, d4, nxt, nyp, ld, 1, g.dxm2);
+    QG_LAUNCH(m, "k_mon_v", nyp, 256, 0, k_mon_v, pk, pmk, vgm, d2, d4, m->F("tauya"), rdxf0, rdxf0 / dta, nxt, ld, 1,
+              rows + (size_t)(oV + 6 * k) * pitch, pitch);
+  }
+  QG_LAUNCH(m, "k_mon_cour", nyt, 256, 0, k_mon_cour, pa, m->F("tauxa"), m->F("tauya"), (const double *)m->F("uekat"),
+            (const double *)m->F("vekat"), g, 0, 0, 0, rdxf0, 0.0, rows + (size_t)oC * pitch, pitch);
+  for (int k = 0; k < nl; ++k)
+    QG_LAUNCH(m, "k_mon_cour", nyt, 256, 0, k_mon_cour, pa + (size_t)k * g.lsz, m->F("tauxa"), m->F("tauya"), (const double *)nullptr,
+              (const double *)nullptr, g, 0, 0, 0, rdxf0, 0.0, rows + (size_t)(oC + 5 * (k + 1)) * pitch, pitch);
+  std::vector<double> h(need);
+  QG_CUDA(cudaMemcpyAsync(h.data(), rows, sizeof(double) * need, cudaMemcpyDeviceToHost, m->stream));
+  QG_CUDA(cudaStreamSynchronize(m->stream));
+  auto gi = [&](int slot, int ny, double facsn) { return rows_int(h.data() + (size_t)slot * pitch, ny, facsn); };
+  const double atnorm = g.norm, rhoat = c.rhoat;
+  r->wetmat = gi(oT + 0, nyt, 1.0) * atnorm;
+  r->watmat = gi(oT + 1, nyt, 1.0) * atnorm;
+  r->wepmat = gi(oP + 0, nyp, 0.5) * atnorm;
+  r->wapmat = gi(oP + 1, nyp, 0.5) * atnorm;
+  r->entmat[0] = gi(oP + 2, nyp, 0.5) * atnorm;
+  r->enamat[0] = gi(oP + 3, nyp, 0.5) * atnorm;
+  for (int k = 0; k < nl - 1; ++k) {
+    r->etamat[k] = gi(oE + 4 * k, nyp, 0.5) * atnorm;
+    r->et2mat[k] = gi(oE + 4 * k + 1, nyp, 0.5) * atnorm;
+    r->ddtpeat[k] = rhoat * m->la.gp[k] * gi(oE + 4 * k + 2, nyp, 0.5);
+    r->pkenat[k] = (k == 0) ? rhoat * m->la.gp[0] * gi(oE + 3, nyp, 0.5) * atnorm : 0.0;
+  }
+  {
+    const double utaux = gi(oU + 5, nyt, 1.0), vtauy = gi(oV + 5, nyp, 0.5);
+    r->utauat = rhoat * (vtauy + utaux) * atnorm;
+  }
+  for (int k = 0; k < nl; ++k) {
+    const double hk = m->la.h[k];
+    const int u = oU + 7 * k, v = oV + 6 * k;
+    const double u4diss = gi(u + 1, nyt, 1.0), uke = gi(u + 2, nyt, 1.0), ukedot = gi(u + 3, nyt, 1.0);
+    const double v4diss = gi(v + 1, nyp, 0.5), vke = gi(v + 2, nyp, 0.5), vkedot = gi(v + 3, nyp, 0.5);
+    r->pavgat[k] = gi(oQ + 4 * k, nyp, 0.5) * atnorm;
+    r->qavgat[k] = gi(oQ + 4 * k + 1, nyp, 0.5) * atnorm;
+    r->ah4dat[k] = rhoat * m->la.ah4[k] * hk * (u4diss + v4diss) * atnorm;
+    r->kealat[k] = 0.5 * rhoat * hk * (uke + vke) * atnorm;
+    r->ddtkeat[k] = rhoat * hk * (ukedot + vkedot) * atnorm;
+    const double *uj = h.data() + (size_t)(u + 6) * pitch;
+    r->atstpos[k] = 0;
+    r->atstval[k] = 0.0;
+    for (int j = 0; j < nyt; ++j) {
+      const double val = std::fabs(uj[j]) / (double)nxt;
+      if (val > r->atstval[k]) { r->atstpos[k] = j + 1; r->atstval[k] = val; }
+    }
+  }
+  r->tmlmat = gi(oT + 3, nyt, 1.0) * atnorm;
+  r->hmlmat = gi(oT + 4, nyt, 1.0) * atnorm;
+  r->hcmlat = rhoat * c.cpat * gi(oT + 2, nyt, 1.0) * atnorm;
+  r->astmin = 1.0e30;
+  r->astmax = -1.0e30;
+  double tmaooc = 0.0;
+  for (int j = 0; j < nyt; ++j) {
+    r->astmin = std::min(r->astmin, h[(size_t)(oT + 6) * pitch + j]);
+    r->astmax = std::max(r->astmax, h[(size_t)(oT + 7) * pitch + j]);
+    tmaooc = tmaooc + h[(size_t)(oT + 5) * pitch + j];
+  }
+  r->tmaooc = tmaooc / (double)(nxaooc * nyaooc);
+  // xintp of dtopat (src/intsubs.f:78-133) has genint's weights 0.5, 0.5
+  r->davgat = gi(oD, nyp, 0.5) * atnorm;
+  double olrtop = c.Bup[nl - 1] * (r->hmlmat - c.hmat) + c.Cup[nl - 1] * r->davgat + c.Dup[nl - 1] * r->tmlmat;
+  for (int i = 0; i < nl - 1; ++i) olrtop = olrtop + c.Aup[(nl - 1) + nl * i] * r->etamat[i];
+  r->olrtop = olrtop;
+  const double cfac = g.hdxm1 * dta;
+  for (int k = 0; k <= nl; ++k) {
+    double e[5] = {1.0e30, -1.0e30, 1.0e30, -1.0e30, -1.0e30};
+    const double *cr = h.data() + (size_t)(oC + 5 * k) * pitch;
+    for (int j = 0; j < nyt; ++j) {
+      e[0] = std::min(e[0], cr[j]); e[1] = std::max(e[1], cr[pitch + j]);
+      e[2] = std::min(e[2], cr[2 * pitch + j]); e[3] = std::max(e[3], cr[3 * pitch + j]);
+      e[4] = std::max(e[4], cr[4 * pitch + j]);
+    }
+    if (k == 0) {
+      r->umminat = e[0]; r->ummaxat = e[1]; r->vmminat = e[2]; r->vmmaxat = e[3];
+      r->cnmlat = cfac * std::sqrt(e[4]);
+    } else {
+      r->ugminat[k - 1] = e[0]; r->ugmaxat[k - 1] = e[1]; r->vgminat[k - 1] = e[2]; r->vgmaxat[k - 1] = e[3];
+      r->cnqgat[k - 1] = cfac * std::sqrt(e[4]);
+    }
+  }
 }
 
 }  // namespace qg

@@ -226,6 +226,8 @@ struct qgcm_model {
   size_t pack_elems = 0;
   double *d_mon = nullptr, *d_monf = nullptr;   // qgcm_monnc_ocean: per-row sums; four scratch fields
   size_t mon_elems = 0;
+  double *d_mona = nullptr, *d_monaf = nullptr;  // qgcm_monnc_atmos: the same for the atmosphere grid
+  size_t mona_elems = 0;
   bool shared_stream = false;            // loopback ranks > 0 borrow rank 0's stream
   // peer-memory transport (slab.cu): own mailbox, peers' mapped mailboxes, exchange counters
   double *mailbox = nullptr;
@@ -351,6 +353,7 @@ void field_sub_size(qgcm_model *m, const char *name, int nsk, int64_t *n);
 void get_field_sub(qgcm_model *m, const char *name, int nsk, double *host, int64_t n);
 // monitor.cu
 void launch_monnc_ocean(qgcm_model *m, qgcm_monitor_ocean *rep);
+void launch_monnc_atmos(qgcm_model *m, qgcm_monitor_atmos *rep);
 // qocdiag.cu
 void qocdiag_size(qgcm_model *m, int nsk, int64_t *n);
 void launch_qocdiag(qgcm_model *m, int nsk, double *host, int64_t n);

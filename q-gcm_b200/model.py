@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from .abi import QgcmConfig, QgcmScalars, QgcmValidsReport, QgcmMonitorOcean, declared_functions
+from .abi import QgcmConfig, QgcmScalars, QgcmValidsReport, QgcmMonitorOcean, QgcmMonitorAtmos, declared_functions
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -154,6 +154,12 @@ class CModel:
         """ocean section of monnc_comp, src/monitor_diag.F:480-840"""
         r = QgcmMonitorOcean()
         self._call("monnc_ocean", C.byref(r))
+        return r
+
+    def monnc_atmos(self) -> QgcmMonitorAtmos:
+        """atmosphere section of monnc_comp, src/monitor_diag.F:186-478"""
+        r = QgcmMonitorAtmos()
+        self._call("monnc_atmos", C.byref(r))
         return r
 
     def qocdiag(self, nsko, out=None):

@@ -101,3 +101,65 @@ def test_monnc_ocean_over_slabs(qg, pyorc, nranks):
     for name in ("po", "qo", "sst"):
         e = np.linalg.norm(grp.get_field(name) - cpu.get_field(name)) / np.linalg.norm(cpu.get_field(name))
         assert e <= 1e-11, (nranks, name, e)
+
+
+def atmos_scales(m, p, cfg, rep):
+    nxp, nyp, nl = p.nxta + 1, p.nyta + 1, p.nla
+    pa = m.get_field("pa", (nxp, nyp, nl))
+    pam = m.get_field("pam", (nxp, nyp, nl))
+    dxa = p.ndxr * p.dxo
+    ug = np.abs(np.diff(pam, axis=1)).mean() / (dxa * abs(p.fnot))
+    ast, hm = m.get_field("ast"), m.get_field("hmixa")
+    et2 = max(rep["et2mat"][:nl - 1])
+    s = {"wetmat": rep["watmat"], "wepmat": rep["wapmat"], "entmat": max(rep["enamat"]), "etamat": float(np.sqrt(et2)),
+         "pavgat": float(np.abs(pa).mean()), "qavgat": float(np.abs(m.get_field("qa")).mean()),
+         "tmlmat": float(np.abs(ast).mean()), "hcmlat": cfg.rhoat * cfg.cpat * float(np.abs(ast * hm).mean()),
+         "tmaooc": float(np.abs(ast).mean()),
+         "utauat": cfg.rhoat * float(np.abs(m.get_field("tauxa")).max()) * float(np.abs(pa).max()) / (dxa * abs(p.fnot)),
+         "ddtkeat": max(rep["kealat"][:nl]) / p.dta + cfg.rhoat * max(cfg.hat[:nl]) * ug * 8.0 / dxa ** 2,
+         "ddtpeat": cfg.rhoat * max(cfg.gpat[:nl - 1]) * et2 * p.nxta * p.nyta / p.dta,
+         "pkenat": cfg.rhoat * cfg.gpat[0] * float(np.sqrt(et2)) * max(rep["enamat"]),
+         "ah4dat": cfg.rhoat * max(cfg.ah4at[:nl]) * max(cfg.hat[:nl]) * ug * ug * 64.0 / dxa ** 4,
+         "olrtop": abs(cfg.Dup[nl - 1]) * float(np.abs(ast).mean()) + abs(cfg.Bup[nl - 1]) * p.hmat,
+         "davgat": max(float(np.abs(m.get_field("dtopat")).mean()), 1e-300), "u_scale": float(ug), "atstval": float(ug)}
+    return s
+
+
+@pytest.mark.parametrize("case", ["cpl_dg", "cpl_so", "cpl_dg_udiff"])
+def test_monnc_atmos(qg, pyorc, case):
+    p = coupled_configs(qg)[case]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    for stage in ("initial state", "after two ocean steps"):
+        a, b = gpu.monnc_atmos().as_dict(), cpu.monnc_atmos().as_dict()
+        sc = atmos_scales(cpu, p, cfg, b)
+        bad = []
+        for name, vb in b.items():
+            if name.startswith("reserved"):
+                continue
+            va = a[name]
+            if name == "atstpos":
+                for k in range(p.nla):
+                    if b["atstval"][k] > 1e-6 * sc["u_scale"] and va[k] != vb[k]:
+                        bad.append((name, k, va[k], vb[k]))
+                continue
+            xa, xb = np.atleast_1d(va).astype(float), np.atleast_1d(vb).astype(float)
+            scale = max(sc.get(name, 0.0), np.abs(xb).max(), 1e-300)
+            if not np.abs(xa - xb).max() <= 1e-10 * scale:
+                bad.append((name, xa.tolist(), xb.tolist(), scale))
+        assert not bad, "%s %s: %s" % (case, stage, bad)
+        for m in (gpu, cpu):
+            m.run(1, 2 * p.nstr) if stage == "initial state" else None
+    # the diagnostics leave the state alone
+    for m in (gpu, cpu):
+        m.run(2 * p.nstr + 1, 3 * p.nstr)
+    for name in ("pa", "qa", "ast", "po"):
+        e = np.linalg.norm(gpu.get_field(name) - cpu.get_field(name)) / np.linalg.norm(cpu.get_field(name))
+        assert e <= 1e-10, (case, name, e)
+
+
+def test_monnc_atmos_absent_in_ocean_only(qg):
+    p = small_configs(qg)["box_dg"]
+    cfg = qg.build_config(p)
+    m = qg.Model(cfg)
+    r = m.monnc_atmos().as_dict()
+    assert all(not np.any(np.atleast_1d(v)) for v in r.values())

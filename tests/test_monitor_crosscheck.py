@@ -171,3 +171,97 @@ def test_couroc_matches_numpy(qg, pyorc, case):
         want = faces(po[:, :, k], rdxf0, False)
         got = (r["ugminoc"][k], r["ugmaxoc"][k], r["vgminoc"][k], r["vgmaxoc"][k], r["cnqgoc"][k])
         assert np.allclose(got, want, rtol=1e-12, atol=1e-300), (case, k, got, want)
+
+
+def test_monnc_atmos_matches_numpy(qg, pyorc):
+    """atmosphere section (src/monitor_diag.F:186-478) and courat (:1215-1445), including the
+    reference's vkedot slip: it integrates del-sqd of the lagged v (the stale workspace attwk3)"""
+    p = qg.named_config("dg_coupled").scaled(6, 5, ndxr=16, name="cpl_dg")
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.run(1, 2 * p.nstr)
+    r = m.monnc_atmos().as_dict()
+    nxp, nyp, nxt, nyt, nl = p.nxta + 1, p.nyta + 1, p.nxta, p.nyta, p.nla
+    pa, pam, qa = (m.get_field(n, (nxp, nyp, nl)) for n in ("pa", "pam", "qa"))
+    ast, hm, wekta = (m.get_field(n, (nxt, nyt)) for n in ("ast", "hmixa", "wekta"))
+    wekpa, entat = m.get_field("wekpa", (nxp, nyp)), m.get_field("entat", (nxp, nyp))
+    tx, ty = m.get_field("tauxa", (nxp, nyp)), m.get_field("tauya", (nxp, nyp))
+    uek, vek = m.get_field("uekat", (nxp, nyt)), m.get_field("vekat", (nxt, nyp))
+    dxa = p.ndxr * p.dxo
+    norm, rdxf0, dxm2 = 1.0 / (nxt * nyt), 1.0 / (dxa * p.fnot), 1.0 / dxa ** 2
+    want = {
+        "wetmat": gint(wekta, 1, 1) * norm, "watmat": gint(np.abs(wekta), 1, 1) * norm,
+        "wepmat": gint(wekpa, .5, .5) * norm, "wapmat": gint(np.abs(wekpa), .5, .5) * norm,
+        "tmlmat": gint(ast, 1, 1) * norm, "hmlmat": gint(hm, 1, 1) * norm,
+        "hcmlat": cfg.rhoat * cfg.cpat * gint(ast * hm, 1, 1) * norm,
+        "astmin": ast.min(), "astmax": ast.max(),
+        "davgat": gint(m.get_field("dtopat", (nxp, nyp)), .5, .5) * norm,
+    }
+    nxa, nya = p.nxto // p.ndxr, p.nyto // p.ndxr
+    want["tmaooc"] = ast[p.nx1 - 1:p.nx1 - 1 + nxa, p.ny1 - 1:p.ny1 - 1 + nya].mean()
+    ug1 = -rdxf0 * (pa[:, 1:, 0] - pa[:, :-1, 0])
+    vg1 = rdxf0 * (pa[1:, :, 0] - pa[:-1, :, 0])
+    want["utauat"] = cfg.rhoat * (gint(vg1 * 0.5 * (ty[1:] + ty[:-1]), 1, .5) + gint(ug1 * 0.5 * (tx[:, 1:] + tx[:, :-1]), .5, 1)) * norm
+    vec = {k: [] for k in ("entmat", "enamat", "etamat", "et2mat", "ddtpeat", "pkenat", "pavgat", "qavgat", "kealat", "ddtkeat",
+                           "ah4dat", "atstval", "atstpos")}
+    vec["entmat"].append(gint(entat, .5, .5) * norm)
+    vec["enamat"].append(gint(np.abs(entat), .5, .5) * norm)
+    for k in range(nl - 1):
+        eta = (pa[:, :, k] - pa[:, :, k + 1]) / cfg.gpat[k]
+        etadot = ((pa[:, :, k] - pa[:, :, k + 1]) - (pam[:, :, k] - pam[:, :, k + 1])) / (cfg.gpat[k] * p.dta)
+        vec["etamat"].append(gint(eta, .5, .5) * norm)
+        vec["et2mat"].append(gint(eta * eta, .5, .5) * norm)
+        vec["ddtpeat"].append(cfg.rhoat * cfg.gpat[k] * gint(eta * etadot, .5, .5))
+        vec["pkenat"].append(cfg.rhoat * cfg.gpat[0] * gint(eta * entat, .5, .5) * norm if k == 0 else V(0.0, 1.0))
+    for k in range(nl):
+        ugm = -rdxf0 * (pam[:, 1:, k] - pam[:, :-1, k])
+        vgm = rdxf0 * (pam[1:, :, k] - pam[:-1, :, k])
+        u4 = lap1(lap1(ugm, dxm2, True), dxm2, True)
+        v2 = lap1(vgm, dxm2, True)
+        v4 = lap1(v2, dxm2, True)
+        ug = -rdxf0 * (pa[:, 1:, k] - pa[:, :-1, k])
+        vg = rdxf0 * (pa[1:, :, k] - pa[:-1, :, k])
+        ugdot = -(rdxf0 / p.dta) * ((pa[:, 1:, k] - pa[:, :-1, k]) - (pam[:, 1:, k] - pam[:, :-1, k]))
+        h = cfg.hat[k]
+        vec["pavgat"].append(gint(pa[:, :, k], .5, .5) * norm)
+        vec["qavgat"].append(gint(qa[:, :, k], .5, .5) * norm)
+        vec["kealat"].append(0.5 * cfg.rhoat * h * (gint(ug * ug, .5, 1) + gint(vg * vg, 1, .5)) * norm)
+        vec["ddtkeat"].append(cfg.rhoat * h * (gint(ug * ugdot, .5, 1) + gint(v2, 1, .5)) * norm)      # the vkedot slip
+        vec["ah4dat"].append(cfg.rhoat * cfg.ah4at[k] * h * (gint(ug * u4, .5, 1) + gint(vg * v4, 1, .5)) * norm)
+        ujet = np.abs(ug[:-1].sum(axis=0)) / nxt
+        vec["atstval"].append(ujet.max())
+        vec["atstpos"].append(int(ujet.argmax()) + 1)
+    olr = cfg.Bup[nl - 1] * (float(want["hmlmat"]) - p.hmat) + cfg.Cup[nl - 1] * float(want["davgat"]) + cfg.Dup[nl - 1] * float(want["tmlmat"])
+    for i in range(nl - 1):
+        olr += cfg.Aup[(nl - 1) + nl * i] * float(vec["etamat"][i])
+    want["olrtop"] = V(olr, abs(cfg.Dup[nl - 1]) * float(np.abs(ast).mean()) + abs(cfg.Bup[nl - 1]) * p.hmat)
+
+    def close(a, b, name, tol):
+        assert abs(a - float(b)) <= tol * max(getattr(b, "scale", abs(b)), 1e-300), (name, a, float(b))
+
+    for k, v in want.items():
+        close(r[k], v, k, 1e-9)
+    for name, vals in vec.items():
+        for k, v in enumerate(vals):
+            if name == "atstpos":
+                assert r[name][k] == v, (name, k)
+            else:
+                close(r[name][k], v, "%s[%d]" % (name, k), 1e-8)
+
+    def faces(pk, ekman):
+        u = -rdxf0 * (pk[:, 1:] - pk[:, :-1])
+        v = rdxf0 * (pk[1:, :] - pk[:-1, :])
+        if ekman:
+            u, v = u + uek, v + vek
+            v[:, 0], v[:, -1] = vek[:, 0], vek[:, -1]
+        else:
+            v[:, 0] = v[:, -1] = 0.0
+        vsq = (u[:-1] + u[1:]) ** 2 + (v[:, :-1] + v[:, 1:]) ** 2
+        return u.min(), u.max(), v.min(), v.max(), 0.5 / dxa * p.dta * np.sqrt(vsq.max())
+
+    got = (r["umminat"], r["ummaxat"], r["vmminat"], r["vmmaxat"], r["cnmlat"])
+    assert np.allclose(got, faces(pa[:, :, 0], True), rtol=1e-12, atol=0.0), got
+    for k in range(nl):
+        got = (r["ugminat"][k], r["ugmaxat"][k], r["vgminat"][k], r["vgmaxat"][k], r["cnqgat"][k])
+        assert np.allclose(got, faces(pa[:, :, k], False), rtol=1e-12, atol=1e-300), (k, got)
