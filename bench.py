@@ -414,7 +414,7 @@ def main():
             "algorithmic_bytes_per_launch": dpp * fieldpass / world, "ms_per_launch": dms,
             "share_of_step": prof[dom][1] / tot_ms}
     # ocean-only byte model; a coupled step moves the atmosphere and xforc too,
-    # which the 61-pass figure does not count, so its fraction is a lower bound
+    # which the 60-pass figure does not count, so its fraction is a lower bound
     step_bytes = (60.0 if not p.has("cyclic_ocean") else 58.0) * fieldpass
     step_frac = step_bytes * value / world / 1e9 / peak     # per-GPU share of the step's bytes against one GPU's peak
 

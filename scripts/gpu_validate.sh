@@ -26,4 +26,11 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > $out/${tag}_ncu_full.log 2>&1
   echo "ncu full rc=$?"
 fi
+if [ "${SKIP_DECKS:-0}" != "1" ]; then
+  # the other decks of BASELINE.json (parity cases at full size; not bench lines): device time only
+  for w in dg_oo natl2km dg_coupled so_coupled; do
+    timeout 300 python bench.py --workload $w --steps 30 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | grep '^{' > $out/${tag}_deck_$w.json
+    python -c "import json; d=json.load(open('$out/${tag}_deck_$w.json')); print('$w', 'ms/step %.4f' % d['ms_per_step'], 'steps/s %.1f' % d['value'])"
+  done
+fi
 ls -la $out | tail -15
