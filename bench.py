@@ -490,6 +490,8 @@ def main():
             "gpt_updates_per_s": value * p.nxpo * p.nypo * p.nlo / 1e9,
             "step_roofline_frac": step_frac,
             "step_algorithmic_bytes": step_bytes,
+            # SURVEY.md 8(d) counts the topography field as well (61 / 59 passes)
+            "step_roofline_frac_survey_bytes": step_frac * (step_bytes + fieldpass) / step_bytes,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
