@@ -234,3 +234,221 @@ def test_oml_interior_against_numpy(qg, pyorc):
     new = sh_(sstm, 0, 0) + 2 * p.dto * (rhs + (rrcp * sh_(fnet, 0, 0) + 0.5 * sh_(wek, 0, 0) * (sh_(sstm, 0, 0) + toc1)) / p.hmoc)
     new = new + np.maximum(0.0, toc1 - new)
     assert rel_l2(got[I, J], new) <= 1e-13
+
+
+# ---- boundary potential vorticity: ocqbdy (src/vorsubs.F:245-388) and atqzbd (:396-480) ----
+def _amat(flat, n):
+    return np.array(flat[: n * n]).reshape((n, n), order="F")
+
+
+@pytest.mark.parametrize("case", ["box_dg", "chan_so"])
+def test_ocqbdy_matches_numpy(qg, pyorc, case):
+    p = small_configs(qg)[case]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.ocean_step()
+    sh = (p.nxpo, p.nypo, p.nlo)
+    po = m.get_field("po", sh)
+    ddyn = m.get_field("ddynoc", sh[:2]) + 1e-9 * np.cos(np.arange(p.nxpo))[:, None]     # exercise the topography term
+    m.set_field("ddynoc", ddyn)
+    m.set_field("qo", np.full(sh, 7.0))            # every boundary value must be overwritten
+    m.ocqbdy()
+    q = m.get_field("qo", sh)
+    A = _amat(cfg.amatoc, p.nlo)
+    bcf = p.bccooc / p.dxo ** 2 / (0.5 * p.bccooc + 1.0) / p.fnot
+    ypo = (p.ny1 - 1) * p.ndxr * p.dxo + np.arange(p.nypo) * p.dxo
+    yrel = ypo - 0.5 * p.nyta * p.ndxr * p.dxo
+    fAp = p.fnot * np.einsum("kl,ijl->ijk", A, po)          # f0 (A p)_k at every point
+    want = np.full(sh, 7.0)
+    top = np.zeros(sh[:2] + (p.nlo,)); top[:, :, -1] = ddyn
+    want[:, 0, :] = bcf * (po[:, 1, :] - po[:, 0, :]) - fAp[:, 0, :] + p.beta * yrel[0] + top[:, 0, :]
+    want[:, -1, :] = bcf * (po[:, -2, :] - po[:, -1, :]) - fAp[:, -1, :] + p.beta * yrel[-1] + top[:, -1, :]
+    if not p.has("cyclic_ocean"):
+        by = (p.beta * yrel)[1:-1, None]
+        want[0, 1:-1, :] = bcf * (po[1, 1:-1, :] - po[0, 1:-1, :]) - fAp[0, 1:-1, :] + by + top[0, 1:-1, :]
+        want[-1, 1:-1, :] = bcf * (po[-2, 1:-1, :] - po[-1, 1:-1, :]) - fAp[-1, 1:-1, :] + by + top[-1, 1:-1, :]
+    assert rel_l2(q, want) <= 1e-13
+
+
+def test_atqzbd_matches_numpy_with_its_quirk(qg, pyorc):
+    """the top layer's southern row takes pa(i,2,nla), not pa(i,1,nla), in the stretching term
+    (src/vorsubs.F:470)"""
+    p = qg.named_config("dg_coupled").scaled(6, 5, ndxr=16, name="cpl_dg")
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.run(1, 2)
+    nxp, nyp, nl = p.nxta + 1, p.nyta + 1, p.nla
+    sh = (nxp, nyp, nl)
+    pa = m.get_field("pa", sh)
+    ddyn = m.get_field("ddynat", sh[:2])
+    m.set_field("qa", np.full(sh, 7.0))
+    m.atqzbd()
+    q = m.get_field("qa", sh)
+    A = _amat(cfg.amatat, nl)
+    dxa = p.ndxr * p.dxo
+    zbf = p.bccoat / dxa ** 2 / (0.5 * p.bccoat + 1.0) / p.fnot
+    yrel = np.arange(nyp) * dxa - 0.5 * p.nyta * dxa
+    fAp = p.fnot * np.einsum("kl,ijl->ijk", A, pa)
+    want = np.full(sh, 7.0)
+    bot = np.zeros(sh); bot[:, :, 0] = ddyn
+    want[:, 0, :] = zbf * (pa[:, 1, :] - pa[:, 0, :]) - fAp[:, 0, :] + p.beta * yrel[0] + bot[:, 0, :]
+    want[:, -1, :] = zbf * (pa[:, -2, :] - pa[:, -1, :]) - fAp[:, -1, :] + p.beta * yrel[-1] + bot[:, -1, :]
+    # the quirk: f0Ac multiplies pa(i,2,nla) on the southern row of the top layer
+    want[:, 0, -1] = (zbf * (pa[:, 1, -1] - pa[:, 0, -1])
+                      - p.fnot * (A[-1, -2] * pa[:, 0, -2] + A[-1, -1] * pa[:, 1, -1]) + p.beta * yrel[0])
+    assert rel_l2(q, want) <= 1e-13
+    plain = fAp[:, 0, -1]
+    assert rel_l2(q[:, 0, -1], zbf * (pa[:, 1, -1] - pa[:, 0, -1]) - plain + p.beta * yrel[0]) > 1e-9      # and it matters
+
+
+def test_qgastep_matches_numpy(qg, pyorc):
+    """atmosphere vorticity step (src/qgasubs.F:45-317): periodic channel, del-6th friction only,
+    entrainment/Ekman forcing with the atmosphere's signs (:122-124)"""
+    p = qg.named_config("dg_coupled").scaled(6, 5, ndxr=16, name="cpl_dg")
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.run(1, 2)
+    m.aml()
+    nxp, nyp, nl = p.nxta + 1, p.nyta + 1, p.nla
+    sh = (nxp, nyp, nl)
+    pa, pam, qa, qam = (m.get_field(n, sh) for n in ("pa", "pam", "qa", "qam"))
+    wek, ent = m.get_field("wekpa", sh[:2]), m.get_field("entat", sh[:2])
+    m.qgastep()
+    qnew = m.get_field("qa", sh)
+    dxa = p.ndxr * p.dxo
+    dxm2 = 1.0 / dxa ** 2
+    zbf = p.bccoat * dxm2 / (0.5 * p.bccoat + 1.0)
+    adf = 1.0 / (12.0 * dxa * dxa * p.fnot)
+
+    def lap(f):            # f on the nxta distinct columns; mixed condition on the zonal walls
+        out = np.empty_like(f)
+        out[:, 1:-1] = (f[:, :-2] + np.roll(f, 1, axis=0)[:, 1:-1] + np.roll(f, -1, axis=0)[:, 1:-1] + f[:, 2:] - 4.0 * f[:, 1:-1]) * dxm2
+        out[:, 0] = zbf * (f[:, 1] - f[:, 0])
+        out[:, -1] = zbf * (f[:, -2] - f[:, -1])
+        return out
+
+    def sx(a, d):
+        return np.roll(a, -d, axis=0)
+
+    for k in range(nl):
+        P, Q = pa[:-1, :, k], qa[:-1, :, k]            # drop the repeated column
+        d6 = lap(lap(lap(pam[:-1, :, k])))
+        c = slice(1, -1)
+        jac = ((sx(Q, 1)[:, c] - sx(Q, -1)[:, c]) * (P[:, 2:] - P[:, :-2]) + (Q[:, :-2] - Q[:, 2:]) * (sx(P, 1)[:, c] - sx(P, -1)[:, c])
+               + sx(Q, 1)[:, c] * (sx(P, 1)[:, 2:] - sx(P, 1)[:, :-2]) - sx(Q, -1)[:, c] * (sx(P, -1)[:, 2:] - sx(P, -1)[:, :-2])
+               - Q[:, 2:] * (sx(P, 1)[:, 2:] - sx(P, -1)[:, 2:]) + Q[:, :-2] * (sx(P, 1)[:, :-2] - sx(P, -1)[:, :-2])
+               + P[:, 2:] * (sx(Q, 1)[:, 2:] - sx(Q, -1)[:, 2:]) - P[:, :-2] * (sx(Q, 1)[:, :-2] - sx(Q, -1)[:, :-2])
+               - sx(P, 1)[:, c] * (sx(Q, 1)[:, 2:] - sx(Q, 1)[:, :-2]) + sx(P, -1)[:, c] * (sx(Q, -1)[:, 2:] - sx(Q, -1)[:, :-2]))
+        dq = adf * jac - (p.ah4at[k] / p.fnot) * d6[:, c]
+        if k == 0:
+            dq = dq + (p.fnot / p.hat[0]) * (ent[:-1, c] - wek[:-1, c])
+        if k == 1:
+            dq = dq - (p.fnot / p.hat[1]) * ent[:-1, c]
+        want = qam[:-1, c, k] + 2.0 * p.dta * dq
+        assert rel_l2(qnew[:-1, c, k], want) <= 1e-12, k
+        assert np.array_equal(qnew[-1, c, k], qnew[0, c, k])              # the periodic column is a copy
+    # zonal boundary rows are left for atqzbd; qam takes the old qa there (:138-145)
+    assert np.array_equal(m.get_field("qam", sh)[:, 0, :], qa[:, 0, :])
+
+
+@pytest.mark.parametrize("case", ["box_dg", "chan_so"])
+def test_time_level_average_matches_numpy(qg, pyorc, case):
+    """src/q-gcm.F:1328-1366: x <- (x + xm)/2 for qo, po, sst and the constraint scalars; the
+    lagged levels are left alone"""
+    p = small_configs(qg)[case]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.ocean_step()
+    m.ocean_step()
+    before = {n: m.get_field(n) for n in ("po", "pom", "qo", "qom", "sst", "sstm", "entoc")}
+    s0 = m.get_scalars().as_dict()
+    m.tlavg_ocean()
+    s1 = m.get_scalars().as_dict()
+    for new, old in (("po", "pom"), ("qo", "qom"), ("sst", "sstm")):
+        assert np.array_equal(m.get_field(new), 0.5 * (before[new] + before[old])), new
+        assert np.array_equal(m.get_field(old), before[old]), old
+    assert np.array_equal(m.get_field("entoc"), before["entoc"])
+    for k in range(p.nlo - 1):
+        assert s1["dpioc"][k] == 0.5 * (s0["dpioc"][k] + s0["dpiocp"][k])
+        assert s1["dpiocp"][k] == s0["dpiocp"][k]
+    if p.has("cyclic_ocean"):
+        for k in range(p.nlo):
+            assert s1["ocncs"][k] == 0.5 * (s0["ocncs"][k] + s0["ocncsp"][k])
+            assert s1["ocncn"][k] == 0.5 * (s0["ocncn"][k] + s0["ocncnp"][k])
+    else:
+        assert s1["ocncs"] == s0["ocncs"]
+
+
+def test_aml_interior_against_numpy(qg, pyorc):
+    """atmosphere mixed layer (src/amlsubs.F:47-563): C-grid advection of ast and hmixa by the
+    layer-1 geostrophic wind plus uekat/vekat, del-sqd/del-4th diffusion of ast, diffusion and
+    relaxation of hmixa with its floor, diabatic term, convective adjustment, entrainment
+    averaged to p points with the eta and topography terms.  Rows away from the zonal walls."""
+    p = qg.named_config("dg_coupled").scaled(6, 5, ndxr=16, name="cpl_dg")
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.run(1, 2)
+    nxt, nyt, nxp, nyp, nl = p.nxta, p.nyta, p.nxta + 1, p.nyta + 1, p.nla
+    g = lambda n, sh: m.get_field(n, sh)
+    ast, astm, hm, hmm = g("ast", (nxt, nyt)), g("astm", (nxt, nyt)), g("hmixa", (nxt, nyt)), g("hmixam", (nxt, nyt))
+    fnet, wekta, xc1 = g("fnetat", (nxt, nyt)), g("wekta", (nxt, nyt)), g("xc1ast", (nxt, nyt))
+    uek, vek = g("uekat", (nxp, nyt)), g("vekat", (nxt, nyp))
+    pa, pam, dtop = g("pa", (nxp, nyp, nl)), g("pam", (nxp, nyp, nl)), g("dtopat", (nxp, nyp))
+    m.aml()
+    ast_n, hm_n, ent_n = g("ast", (nxt, nyt)), g("hmixa", (nxt, nyt)), g("entat", (nxp, nyp))
+    assert np.array_equal(g("astm", (nxt, nyt)), ast) and np.array_equal(g("hmixam", (nxt, nyt)), hm)
+    dxa = p.ndxr * p.dxo
+    rdxf0, hdxm1, dxm2 = 1.0 / (dxa * p.fnot), 0.5 / dxa, 1.0 / dxa ** 2
+    tdt = 2.0 * p.dta
+    rrcpat = 1.0 / (cfg.rhoat * cfg.cpat)
+    p1 = pa[:, :, 0]
+    u = -rdxf0 * (p1[:, 1:] - p1[:, :-1]) + uek          # (nxp, nyt): x faces
+    v = rdxf0 * (p1[1:, :] - p1[:-1, :]) + vek           # (nxt, nyp): y faces
+    rows = slice(2, nyt - 2)                             # two T rows clear of the walls: plain stencils only
+    W = lambda a: np.roll(a, 1, axis=0)                  # value at i-1 (periodic)
+    E = lambda a: np.roll(a, -1, axis=0)
+
+    def flux_div(f):
+        um, up = u[:-1], u[1:]
+        x = hdxm1 * (up * (f + E(f)) - um * (W(f) + f))
+        y = np.zeros_like(f)
+        y[:, 1:-1] = hdxm1 * (v[:, 2:-1] * (f[:, 2:] + f[:, 1:-1]) - v[:, 1:-2] * (f[:, 1:-1] + f[:, :-2]))
+        return x + y
+
+    def lap(f):
+        out = np.zeros_like(f)
+        out[:, 1:-1] = f[:, :-2] + W(f)[:, 1:-1] + E(f)[:, 1:-1] + f[:, 2:] - 4.0 * f[:, 1:-1]
+        return out
+
+    d2t = lap(astm)
+    tmrhs = -flux_div(ast) + p.at2d * dxm2 * d2t - p.at4d * dxm2 ** 2 * lap(d2t)
+    hmrhs = -flux_div(hm) + p.ahmd * dxm2 * lap(hmm)
+    tat1, tat2 = cfg.tat[0], cfg.tat[1]
+    hdrcdt = p.hmadmp * rrcpat * tdt
+    diabcr = tat1 - 2.0 * hdrcdt
+    cold = astm <= diabcr
+    with np.errstate(divide="ignore", invalid="ignore"):
+        hnew = hmm + tdt * hmrhs - hdrcdt * (hmm - p.hmat) / (tat1 - astm)
+    dhfix = np.maximum(p.hmamin - hnew, 0.0)
+    hnew = np.where(cold, hnew + dhfix, p.hmat)
+    dtfix = np.where(cold, dhfix * (tat1 - astm) / hmm, 0.0)
+    trhtot = tmrhs + rrcpat * fnet / hmm - wekta * astm / p.hmat
+    astnew = astm + tdt * trhtot + dtfix
+    dtanew = tat1 - astnew
+    entfac = 1.0 / (tdt * (tat2 - tat1))
+    conena = entfac * hm * np.minimum(0.0, dtanew)
+    xfa = p.xcexp * cfg.bface * (hmm - p.hmat) + cfg.dface * (p.xcexp * astm + xc1) - p.xcexp * conena
+    astnew = astnew + np.minimum(0.0, dtanew)
+    assert rel_l2(ast_n[:, rows], astnew[:, rows]) <= 1e-12
+    assert rel_l2(hm_n[:, rows], hnew[:, rows]) <= 1e-12
+    # entrainment at p points i = 2..nxpa-1 of the same rows: four-point average plus the p-point terms
+    avg = 0.25 * (xfa[:-1, :-1] + xfa[1:, :-1] + xfa[:-1, 1:] + xfa[1:, 1:])       # p point (i+1, j+1), 0-based
+    adp = sum(cfg.aface[l] / cfg.gpat[l] * (pam[:, :, l] - pam[:, :, l + 1]) for l in range(nl - 1))
+    want = avg + (adp + cfg.cface * dtop)[1:-1, 1:-1]
+    prow = slice(3, nyt - 2)
+    assert rel_l2(ent_n[1:-1, 1:-1][:, prow], want[:, prow]) <= 1e-12
