@@ -452,3 +452,36 @@ def test_aml_interior_against_numpy(qg, pyorc):
     want = avg + (adp + cfg.cface * dtop)[1:-1, 1:-1]
     prow = slice(3, nyt - 2)
     assert rel_l2(ent_n[1:-1, 1:-1][:, prow], want[:, prow]) <= 1e-12
+
+
+def test_valids_matches_numpy(qg, pyorc):
+    """extreme-value scan and perturbed layer thicknesses of valids (src/valsubs.F:43-630): a
+    state with an interface displaced far enough for the thin-layer percentages to be non-zero"""
+    p = small_configs(qg)["box_dg"]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    sh = (p.nxpo, p.nypo, p.nlo)
+    po = m.get_field("po", sh)
+    x = np.linspace(-1.0, 1.0, p.nxpo)[:, None]
+    y = np.linspace(-1.0, 1.0, p.nypo)[None, :]
+    po[:, :, 0] -= 330.0 * cfg.gpoc[0] * np.exp(-(x ** 2 + y ** 2) / 0.1)      # lifts interface 1 by ~330 m into the 350 m top layer
+    m.set_field("po", po)
+    r = m.valids().as_dict()
+    for name, f in (("poc", po), ("qoc", m.get_field("qo")), ("sst", m.get_field("sst")), ("wto", m.get_field("wekto"))):
+        assert r[name + "min"] == f.min() and r[name + "max"] == f.max(), name
+    eta = [(po[:, :, k + 1] - po[:, :, k]) / cfg.gpoc[k] for k in range(p.nlo - 1)]
+    dtop = cfg.hoc[p.nlo - 1] / p.fnot * m.get_field("ddynoc", sh[:2])
+    hf = [cfg.hoc[0] - eta[0]] + [cfg.hoc[k] - eta[k] + eta[k - 1] for k in range(1, p.nlo - 1)] + [cfg.hoc[p.nlo - 1] + eta[-1] - dtop]
+    assert np.isclose(r["hfmint"], hf[0].min(), rtol=1e-14) and np.isclose(r["hfmaxt"], hf[0].max(), rtol=1e-14)
+    assert np.isclose(r["hfminb"], hf[-1].min(), rtol=1e-14) and np.isclose(r["hfmaxb"], hf[-1].max(), rtol=1e-14)
+    mid = np.array(hf[1:-1])
+    assert np.isclose(r["hfmini"], mid.min(), rtol=1e-14) and np.isclose(r["hfmaxi"], mid.max(), rtol=1e-14)
+    w = np.ones(p.nxpo)[:, None] * np.ones(p.nypo)[None, :]
+    w[0] *= 0.5; w[-1] *= 0.5; w[:, 0] *= 0.5; w[:, -1] *= 0.5
+    for k in range(p.nlo):
+        pct = 100.0 * (w * (hf[k] < 100.0)).sum() / (p.nxto * p.nyto)
+        assert np.isclose(r["hfbad"][k], pct, rtol=1e-12, atol=1e-12), (k, r["hfbad"][k], pct)
+    assert r["hfbad"][0] > 0.0                      # the bump did thin the top layer below 100 m somewhere
+    extreme = abs(po).max() >= 1.0e4
+    assert r["solnok"] == int(not extreme and max(r["hfbad"][:p.nlo]) <= 20.0)
