@@ -485,3 +485,82 @@ def test_valids_matches_numpy(qg, pyorc):
     assert r["hfbad"][0] > 0.0                      # the bump did thin the top layer below 100 m somewhere
     extreme = abs(po).max() >= 1.0e4
     assert r["solnok"] == int(not extreme and max(r["hfbad"][:p.nlo]) <= 20.0)
+
+
+def test_ocinvq_channel_against_numpy(qg, pyorc):
+    """channel ocean (src/ocisubs.F:174-327): constraint right-hand sides from the boundary
+    integrals, leapfrog of ocncs/ocncn, line integrals of the inhomogeneous modes, c1/c2/c3,
+    the homogeneous corrections pbhoc / pch1oc / pch2oc, continuity update and monitors"""
+    p = small_configs(qg)["chan_so"]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.ocean_step()
+    m.oml(); m.qgostep()
+    nl, nxp, nyp, nxt = p.nlo, p.nxpo, p.nypo, p.nxto
+    sh = (nxp, nyp, nl)
+    qo, po_old = m.get_field("qo", sh), m.get_field("po", sh)
+    pch1, pch2 = m.get_field("pch1oc", (nyp, nl - 1)), m.get_field("pch2oc", (nyp, nl - 1))
+    pbh = m.get_field("pbhoc")
+    s0 = m.get_scalars().as_dict()
+    l2m = np.array(cfg.ctl2moc[: nl * nl]).reshape(nl, nl, order="F")
+    m2l = np.array(cfg.ctm2loc[: nl * nl]).reshape(nl, nl, order="F")
+    yrel = (p.ny1 - 1) * p.dxa + np.arange(nyp) * p.dxo - 0.5 * p.nyta * p.dxa
+    wrk = np.zeros(sh)
+    wrk[:, 1:-1, :] = p.fnot * np.einsum("km,ijk->ijm", l2m, (qo - (p.beta * yrel)[None, :, None])[:, 1:-1, :])
+    a = 1.0 / p.dxo ** 2
+    kk = np.arange(nxt // 2 + 1)
+    pm = np.zeros(sh)
+    xin = np.zeros(nl)
+    n = nyp - 2
+    wts = np.ones(nxp); wts[0] = wts[-1] = 0.5
+    for mo in range(nl):
+        bk = -2 * a + 2 * a * (np.cos(kk * 2 * np.pi / nxt) - 1.0) - cfg.rdm2oc[mo]
+        spec = sf.rfft(wrk[:nxt, 1:-1, mo], axis=0)
+        sol = np.empty_like(spec)
+        for i in range(nxt // 2 + 1):
+            ab = np.zeros((3, n)); ab[0, 1:] = a; ab[1, :] = bk[i]; ab[2, :-1] = a
+            sol[i] = sla.solve_banded((1, 1), ab, spec[i].real) + 1j * sla.solve_banded((1, 1), ab, spec[i].imag)
+        pm[:nxt, 1:-1, mo] = sf.irfft(sol, n=nxt, axis=0)
+        pm[-1, :, mo] = pm[0, :, mo]
+        xin[mo] = (wts @ pm[:, 1:-1, mo]).sum() * p.dxo ** 2         # xintp: the wall rows are zero
+    tdt = 2 * p.dto
+    H = np.array(cfg.hoc[:nl])
+    entfac = 0.5 * p.dxo * p.fnot ** 2
+    A = {k: np.array(s0[k][:nl]) for k in ("enisoc", "eninoc", "ajisoc", "ajinoc", "ap3soc", "ap3noc", "ap5soc", "ap5noc",
+                                           "ocncs", "ocncn", "ocncsp", "ocncnp")}
+    en_s = np.concatenate([[0.0], A["enisoc"][: nl - 1], [0.0]])     # enisoc(0) = enisoc(nlo) = 0 in the layer differences
+    en_n = np.concatenate([[0.0], A["eninoc"][: nl - 1], [0.0]])
+    rhss = entfac / H * (en_s[1:] - en_s[:-1]) + A["ajisoc"] - A["ap3soc"] + A["ap5soc"]
+    rhsn = entfac / H * (en_n[1:] - en_n[:-1]) + A["ajinoc"] + A["ap3noc"] - A["ap5noc"]
+    rhss[0] += p.fnot / H[0] * s0["txisoc"]
+    rhsn[0] -= p.fnot / H[0] * s0["txinoc"]
+    rhss[-1] += p.fnot / H[-1] * s0["bdrins"]
+    rhsn[-1] -= p.fnot / H[-1] * s0["bdrinn"]
+    ocs_new, ocn_new = A["ocncsp"] + tdt * rhss, A["ocncnp"] + tdt * rhsn
+    ayis = np.array([wts @ pm[:, 1, mo] for mo in range(nl)])         # dx/dy = 1
+    ayin = np.array([-(wts @ pm[:, -2, mo]) for mo in range(nl)])
+    clhss = l2m.T @ ocs_new + ayis
+    clhsn = l2m.T @ ocn_new - ayin
+    c3 = clhss[0] * s0["hbsioc"]
+    hc1s, hc2s, hc1n, hc2n = (np.array(s0[k][: nl - 1]) for k in ("hc1soc", "hc2soc", "hc1noc", "hc2noc"))
+    c1 = hc2n * clhss[1:] - hc2s * clhsn[1:]
+    c2 = hc1s * clhsn[1:] - hc1n * clhss[1:]
+    aipmod = np.concatenate([[xin[0] + c3 * s0["aipbho"]], xin[1:] + (c1 + c2) * np.array(s0["aipcho"][: nl - 1])])
+    aiplay = m2l.T @ aipmod
+    pmode = pm.copy()
+    pmode[:, :, 0] += c3 * pbh[None, :]
+    for mo in range(1, nl):
+        pmode[:, :, mo] += (c1[mo - 1] * pch1[:, mo - 1] + c2[mo - 1] * pch2[:, mo - 1])[None, :]
+    want = np.einsum("mk,ijm->ijk", m2l, pmode)
+    m.ocinvq()
+    s1 = m.get_scalars().as_dict()
+    assert rel_l2(m.get_field("po", sh), want) <= 1e-12
+    assert np.array_equal(m.get_field("pom", sh), po_old)
+    assert np.allclose(s1["ocncs"][:nl], ocs_new, rtol=1e-12, atol=0.0) and np.allclose(s1["ocncn"][:nl], ocn_new, rtol=1e-12, atol=0.0)
+    assert s1["ocncsp"][:nl] == list(A["ocncs"]) and s1["ocncnp"][:nl] == list(A["ocncn"])
+    scale = np.abs(want).sum() * p.dxo ** 2
+    assert np.abs(np.array(s1["dpioc"][: nl - 1]) - (aiplay[1:] - aiplay[:-1])).max() <= 1e-12 * scale
+    assert s1["dpiocp"][: nl - 1] == s0["dpioc"][: nl - 1]
+    est2 = np.array(s0["dpiocp"][: nl - 1]) - tdt * np.array(cfg.gpoc[: nl - 1]) * np.array(s0["xon"][: nl - 1])
+    assert np.abs(np.array(s1["ermaso"][: nl - 1]) - ((aiplay[1:] - aiplay[:-1]) - est2)).max() <= 1e-12 * scale
