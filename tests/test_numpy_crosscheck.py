@@ -564,3 +564,81 @@ def test_ocinvq_channel_against_numpy(qg, pyorc):
     assert s1["dpiocp"][: nl - 1] == s0["dpioc"][: nl - 1]
     est2 = np.array(s0["dpiocp"][: nl - 1]) - tdt * np.array(cfg.gpoc[: nl - 1]) * np.array(s0["xon"][: nl - 1])
     assert np.abs(np.array(s1["ermaso"][: nl - 1]) - ((aiplay[1:] - aiplay[:-1]) - est2)).max() <= 1e-12 * scale
+
+
+def test_atinvq_against_numpy(qg, pyorc):
+    """atmosphere inversion (src/atisubs.F:60-293): topography enters layer 1, the constraint
+    right-hand sides and dpiat carry the atmosphere's signs, no del-cubed terms"""
+    p = qg.named_config("dg_coupled").scaled(6, 5, ndxr=16, name="cpl_dg")
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    dxa = p.ndxr * p.dxo
+    nl, nxp, nyp, nxt = p.nla, p.nxta + 1, p.nyta + 1, p.nxta
+    sh = (nxp, nyp, nl)
+    x = np.arange(nxp)[:, None] * 2 * np.pi / nxt
+    ddyn = 1e-6 * np.cos(x) * np.sin(np.linspace(0, np.pi, nyp))[None, :]       # exercise the topography term
+    m.set_field("ddynat", ddyn)
+    m.run(1, 2)
+    m.aml(); m.qgastep()
+    qa, pa_old = m.get_field("qa", sh), m.get_field("pa", sh)
+    pch1, pch2 = m.get_field("pch1at", (nyp, nl - 1)), m.get_field("pch2at", (nyp, nl - 1))
+    pbh = m.get_field("pbhat")
+    s0 = m.get_scalars().as_dict()
+    l2m = np.array(cfg.ctl2mat[: nl * nl]).reshape(nl, nl, order="F")
+    m2l = np.array(cfg.ctm2lat[: nl * nl]).reshape(nl, nl, order="F")
+    yrel = np.arange(nyp) * dxa - 0.5 * p.nyta * dxa
+    ql = qa - (p.beta * yrel)[None, :, None]
+    ql[:, :, 0] -= ddyn
+    wrk = np.zeros(sh)
+    wrk[:, 1:-1, :] = p.fnot * np.einsum("km,ijk->ijm", l2m, ql[:, 1:-1, :])
+    a = 1.0 / dxa ** 2
+    kk = np.arange(nxt // 2 + 1)
+    pm = np.zeros(sh)
+    xin = np.zeros(nl)
+    n = nyp - 2
+    wts = np.ones(nxp); wts[0] = wts[-1] = 0.5
+    for mo in range(nl):
+        bk = -2 * a + 2 * a * (np.cos(kk * 2 * np.pi / nxt) - 1.0) - cfg.rdm2at[mo]
+        spec = sf.rfft(wrk[:nxt, 1:-1, mo], axis=0)
+        sol = np.empty_like(spec)
+        for i in range(nxt // 2 + 1):
+            ab = np.zeros((3, n)); ab[0, 1:] = a; ab[1, :] = bk[i]; ab[2, :-1] = a
+            sol[i] = sla.solve_banded((1, 1), ab, spec[i].real) + 1j * sla.solve_banded((1, 1), ab, spec[i].imag)
+        pm[:nxt, 1:-1, mo] = sf.irfft(sol, n=nxt, axis=0)
+        pm[-1, :, mo] = pm[0, :, mo]
+        xin[mo] = (wts @ pm[:, 1:-1, mo]).sum() * dxa ** 2
+    tdt = 2 * p.dta
+    H = np.array(cfg.hat[:nl])
+    entfac = 0.5 * dxa * p.fnot ** 2
+    A = {k: np.array(s0[k][:nl]) for k in ("enisat", "eninat", "ajisat", "ajinat", "ap5sat", "ap5nat", "atmcs", "atmcn", "atmcsp", "atmcnp")}
+    en_s = np.concatenate([[0.0], A["enisat"][: nl - 1], [0.0]])
+    en_n = np.concatenate([[0.0], A["eninat"][: nl - 1], [0.0]])
+    rhss = -entfac / H * (en_s[1:] - en_s[:-1]) + A["ajisat"] + A["ap5sat"]
+    rhsn = -entfac / H * (en_n[1:] - en_n[:-1]) + A["ajinat"] - A["ap5nat"]
+    rhss[0] -= p.fnot / H[0] * s0["txisat"]
+    rhsn[0] += p.fnot / H[0] * s0["txinat"]
+    ats_new, atn_new = A["atmcsp"] + tdt * rhss, A["atmcnp"] + tdt * rhsn
+    ayis = np.array([wts @ pm[:, 1, mo] for mo in range(nl)])
+    ayin = np.array([-(wts @ pm[:, -2, mo]) for mo in range(nl)])
+    clhss = l2m.T @ ats_new + ayis
+    clhsn = l2m.T @ atn_new - ayin
+    c3 = clhss[0] * s0["hbsiat"]
+    hc1s, hc2s, hc1n, hc2n = (np.array(s0[k][: nl - 1]) for k in ("hc1sat", "hc2sat", "hc1nat", "hc2nat"))
+    c1 = hc2n * clhss[1:] - hc2s * clhsn[1:]
+    c2 = hc1s * clhsn[1:] - hc1n * clhss[1:]
+    aipmod = np.concatenate([[xin[0] + c3 * s0["aipbha"]], xin[1:] + (c1 + c2) * np.array(s0["aipcha"][: nl - 1])])
+    aiplay = m2l.T @ aipmod
+    pmode = pm.copy()
+    pmode[:, :, 0] += c3 * pbh[None, :]
+    for mo in range(1, nl):
+        pmode[:, :, mo] += (c1[mo - 1] * pch1[:, mo - 1] + c2[mo - 1] * pch2[:, mo - 1])[None, :]
+    want = np.einsum("mk,ijm->ijk", m2l, pmode)
+    m.atinvq()
+    s1 = m.get_scalars().as_dict()
+    assert rel_l2(m.get_field("pa", sh), want) <= 1e-12
+    assert np.array_equal(m.get_field("pam", sh), pa_old)
+    assert np.allclose(s1["atmcs"][:nl], ats_new, rtol=1e-12, atol=0.0) and np.allclose(s1["atmcn"][:nl], atn_new, rtol=1e-12, atol=0.0)
+    scale = np.abs(want).sum() * dxa ** 2
+    assert np.abs(np.array(s1["dpiat"][: nl - 1]) - (aiplay[:-1] - aiplay[1:])).max() <= 1e-12 * scale       # sign: layer k minus k+1
+    assert s1["dpiatp"][: nl - 1] == s0["dpiat"][: nl - 1]
