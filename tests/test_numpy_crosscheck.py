@@ -642,3 +642,44 @@ def test_atinvq_against_numpy(qg, pyorc):
     scale = np.abs(want).sum() * dxa ** 2
     assert np.abs(np.array(s1["dpiat"][: nl - 1]) - (aiplay[:-1] - aiplay[1:])).max() <= 1e-12 * scale       # sign: layer k minus k+1
     assert s1["dpiatp"][: nl - 1] == s0["dpiat"][: nl - 1]
+
+
+def test_homsol_box_against_numpy(qg, pyorc):
+    """homsol, finite box (src/conhoms.F:549-640): ochom_m = 1 + rdm2 * sol0 with
+    (del-sqd - rdm2) sol0 = 1, sol0 = 0 on the walls; aipohs, cdiffo, cdhoc from it"""
+    p = small_configs(qg)["box_dg"]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")        # ends with homsol
+    nl, nxp, nyp, nxt = p.nlo, p.nxpo, p.nypo, p.nxto
+    ochom = m.get_field("ochom", (nxp, nyp, nl - 1))
+    s = m.get_scalars().as_dict()
+    m2l = np.array(cfg.ctm2loc[: nl * nl]).reshape(nl, nl, order="F")
+    a = 1.0 / p.dxo ** 2
+    kk = np.arange(1, nxt)
+    n = nyp - 2
+    w = np.ones(nxp); w[0] = w[-1] = 0.5
+    wy = np.ones(nyp); wy[0] = wy[-1] = 0.5
+    aip = np.zeros(nl - 1)
+    for mo in range(nl - 1):
+        rd = cfg.rdm2oc[mo + 1]
+        b = -2 * a + 2 * a * (np.cos(kk * np.pi / nxt) - 1.0) - rd
+        spec = sf.dst(np.ones((nxt - 1, n)), type=1, axis=0)
+        sol = np.empty_like(spec)
+        for i in range(nxt - 1):
+            ab = np.zeros((3, n)); ab[0, 1:] = a; ab[1, :] = b[i]; ab[2, :-1] = a
+            sol[i] = sla.solve_banded((1, 1), ab, spec[i])
+        want = np.ones((nxp, nyp))
+        want[1:-1, 1:-1] = 1.0 + rd * sf.dst(sol * (0.5 / nxt), type=1, axis=0)
+        assert rel_l2(ochom[:, :, mo], want) <= 1e-12, mo
+        # the homogeneous problem itself: (del-sqd - rdm2) ochom = 0 inside, ochom = 1 on the walls
+        h = ochom[:, :, mo]
+        res = lap5(h, a) - rd * h[1:-1, 1:-1]
+        assert np.abs(res).max() <= 1e-9 * rd
+        aip[mo] = (w @ h @ wy) * p.dxo ** 2
+        assert np.isclose(s["aipohs"][mo], aip[mo], rtol=1e-12)
+    cdiffo = np.array(s["cdiffo"][: nl * (nl - 1)]).reshape(nl, nl - 1, order="F")
+    cdhoc = np.array(s["cdhoc"][: (nl - 1) ** 2]).reshape(nl - 1, nl - 1, order="F")
+    for k in range(nl - 1):
+        assert np.allclose(cdiffo[:, k], m2l[:, k + 1] - m2l[:, k], rtol=1e-14, atol=0.0)
+        assert np.allclose(cdhoc[k, :], (m2l[1:, k + 1] - m2l[1:, k]) * aip, rtol=1e-12, atol=0.0)
