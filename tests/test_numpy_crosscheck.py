@@ -683,3 +683,38 @@ def test_homsol_box_against_numpy(qg, pyorc):
     for k in range(nl - 1):
         assert np.allclose(cdiffo[:, k], m2l[:, k + 1] - m2l[:, k], rtol=1e-14, atol=0.0)
         assert np.allclose(cdhoc[k, :], (m2l[1:, k + 1] - m2l[1:, k]) * aip, rtol=1e-12, atol=0.0)
+
+
+@pytest.mark.parametrize("case", ["box_dg", "chan_so"])
+def test_constr_matches_numpy(qg, pyorc, case):
+    """constr (src/conhoms.F:44-200): area integrals of the interface pressure differences on
+    both time levels; in a channel the zonal line integrals of p_y and of A p"""
+    p = small_configs(qg)[case]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.ocean_step()
+    m.constr()
+    s = m.get_scalars().as_dict()
+    nl, nxp, nyp = p.nlo, p.nxpo, p.nypo
+    po, pom = m.get_field("po", (nxp, nyp, nl)), m.get_field("pom", (nxp, nyp, nl))
+    w = np.ones(nxp); w[0] = w[-1] = 0.5
+    wy = np.ones(nyp); wy[0] = wy[-1] = 0.5
+    dA = p.dxo ** 2
+    for k in range(nl - 1):
+        for name, f in (("dpioc", po), ("dpiocp", pom)):
+            d = f[:, :, k + 1] - f[:, :, k]
+            want, scale = (w @ d @ wy) * dA, (w @ np.abs(d) @ wy) * dA
+            assert abs(s[name][k] - want) <= 1e-12 * scale, (name, k)
+    if p.has("cyclic_ocean"):
+        A = _amat(cfg.amatoc, nl)
+        half = 0.5 * p.dxo * p.fnot ** 2
+        # the synthetic channel modes have vanishing zonal means: compare against the integrals of the magnitudes
+        def scale(f, j0, j1):
+            return (w @ np.abs(f[:, j1, :] - f[:, j0, :])).max() + half * (np.abs(A) @ (p.dxo * (w @ np.abs(f[:, j0, :])))).max()
+        for name, f in (("ocncs", po), ("ocncsp", pom)):
+            line = -(w @ (f[:, 1, :] - f[:, 0, :])) + half * (A @ (p.dxo * (w @ f[:, 0, :])))
+            assert np.abs(np.array(s[name][:nl]) - line).max() <= 1e-12 * scale(f, 0, 1), name
+        for name, f in (("ocncn", po), ("ocncnp", pom)):
+            line = (w @ (f[:, -1, :] - f[:, -2, :])) + half * (A @ (p.dxo * (w @ f[:, -1, :])))
+            assert np.abs(np.array(s[name][:nl]) - line).max() <= 1e-12 * scale(f, -1, -2), name
