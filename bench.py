@@ -484,8 +484,9 @@ def main():
                                         if transport == "peer" else "NCCL halos and reductions")) if world > 1
                        else "single GPU",
                        "transport": transport, "transport_note": transport_note,
-                       "l2": "state (%.1f GB) is far larger than L2; no flush needed" %
-                             (4 * p.nlo * fieldpass / 1e9),
+                       "l2": ("state (%.1f GB) is far larger than L2; no flush needed" if 4 * p.nlo * fieldpass > 4 * 126e6 else
+                              "state (%.2f GB) is comparable to the 126 MB L2 and is NOT flushed between steps: a parity-size "
+                              "deck, not a bench line") % (4 * p.nlo * fieldpass / 1e9),
                        "state_finite": finite},
             "gpt_updates_per_s": value * p.nxpo * p.nypo * p.nlo / 1e9,
             "step_roofline_frac": step_frac,
