@@ -62,3 +62,28 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"pyorc|liborc|\borc_|oracle/", text), f
+
+
+def test_header_and_library_work_from_plain_c(qg, tmp_path):
+    """examples/abi_smoke.c: the header is valid C99, the library links from C, the error
+    convention works, and the struct sizes the C compiler sees are the ones ctypes computes"""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "q-gcm_b200", "csrc")
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.check_call([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "examples", "abi_smoke.c"), "-L" + libdir, "-lqgcm_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    sizes = dict(re.findall(r"(\w+) (\d+)", r.stdout.split("sizeof:")[1].splitlines()[0]))
+    assert int(sizes["config"]) == C.sizeof(qg.QgcmConfig)
+    assert int(sizes["scalars"]) == C.sizeof(qg.QgcmScalars)
+    assert int(sizes["valids"]) == C.sizeof(qg.QgcmValidsReport)
+    assert int(sizes["monitor_ocean"]) == C.sizeof(qg.QgcmMonitorOcean)
+    assert int(sizes["monitor_atmos"]) == C.sizeof(qg.QgcmMonitorAtmos)
+    assert "ABI mismatch" in r.stdout
