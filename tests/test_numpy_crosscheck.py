@@ -718,3 +718,82 @@ def test_constr_matches_numpy(qg, pyorc, case):
         for name, f in (("ocncn", po), ("ocncnp", pom)):
             line = (w @ (f[:, -1, :] - f[:, -2, :])) + half * (A @ (p.dxo * (w @ f[:, -1, :])))
             assert np.abs(np.array(s[name][:nl]) - line).max() <= 1e-12 * scale(f, -1, -2), name
+
+
+def _oml_ghost_cells(qg, pyorc, p):
+    """the whole of oml/omladf (src/omlsubs.F:47-763) as a ghost-cell scheme: every boundary
+    variant of the reference (no-flux walls, periodic channel, Ekman outflow at tsbdy / tnbdy,
+    the four corners) is 'flux through a face = face velocity x sum of the two cell values'
+    and 'Laplacian with a ghost value outside', with the ghost chosen per boundary"""
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.ocean_step()                                  # so that sst and sstm differ
+    nxt, nyt, nxp, nyp = p.nxto, p.nyto, p.nxpo, p.nypo
+    po = m.get_field("po", (nxp, nyp, p.nlo))[:, :, 0]
+    tx, ty = m.get_field("tauxo", (nxp, nyp)), m.get_field("tauyo", (nxp, nyp))
+    sst, sstm = m.get_field("sst", (nxt, nyt)), m.get_field("sstm", (nxt, nyt))
+    wek, fnet = m.get_field("wekto", (nxt, nyt)), m.get_field("fnetoc", (nxt, nyt))
+    m.oml()
+    got_sst, got_ent = m.get_field("sst", (nxt, nyt)), m.get_field("entoc", (nxp, nyp))
+    s = m.get_scalars().as_dict()
+    cyc, sb, nb = p.has("cyclic_ocean"), p.has("sb_hflux"), p.has("nb_hflux")
+    uvg, rh, hdx = p.ycexp / (p.dxo * p.fnot), 0.5 / (p.fnot * p.hmoc), 0.5 / p.dxo
+    # face velocities: u on the nxp x faces of every T row, v on the nyp y faces of every T column
+    u = -uvg * (po[:, 1:] - po[:, :-1]) + rh * (ty[:, 1:] + ty[:, :-1])
+    v = uvg * (po[1:, :] - po[:-1, :]) - rh * (tx[1:, :] + tx[:-1, :])
+    if not cyc:
+        u[0] = u[-1] = 0.0
+    v[:, 0] = -rh * (tx[1:, 0] + tx[:-1, 0]) if sb else 0.0
+    v[:, -1] = -rh * (tx[1:, -1] + tx[:-1, -1]) if nb else 0.0
+
+    def pad(f, south, north, xmode):
+        """one ghost ring: x periodic or copy (no flux); y copy or a prescribed temperature"""
+        g = np.empty((f.shape[0] + 2, f.shape[1] + 2))
+        g[1:-1, 1:-1] = f
+        g[1:-1, 0] = f[:, 0] if south is None else south
+        g[1:-1, -1] = f[:, -1] if north is None else north
+        if xmode == "periodic":
+            g[0], g[-1] = g[-2], g[1]
+        else:
+            g[0], g[-1] = g[1], g[-2]
+        return g
+
+    xm = "periodic" if cyc else "copy"
+    T = pad(sst, cfg.tsbdy if sb else None, cfg.tnbdy if nb else None, xm)        # advected temperature
+    hx = hdx * (u[1:] * (T[1:-1, 1:-1] + T[2:, 1:-1]) - u[:-1] * (T[:-2, 1:-1] + T[1:-1, 1:-1]))
+    hy = hdx * (v[:, 1:] * (T[1:-1, 1:-1] + T[1:-1, 2:]) - v[:, :-1] * (T[1:-1, :-2] + T[1:-1, 1:-1]))
+    Tm = pad(sstm, cfg.tsbdy if sb else None, cfg.tnbdy if nb else None, xm)
+    lap = lambda g: g[1:-1, :-2] + g[:-2, 1:-1] + g[2:, 1:-1] + g[1:-1, 2:] - 4.0 * g[1:-1, 1:-1]
+    d2 = lap(Tm)
+    d4 = lap(pad(d2, None, None, xm))                # no diffusive flux of del-sqd T through any wall
+    dxm2 = 1.0 / p.dxo ** 2
+    rhs = -(hx + hy) + p.st2d * dxm2 * d2 - p.st4d * dxm2 ** 2 * d4
+    toc1, toc2 = cfg.toc[0], cfg.toc[1]
+    tdt = 2.0 * p.dto
+    rrcp = 1.0 / (p.rhooc * p.cpoc)
+    new = sstm + tdt * (rhs + (rrcp * fnet + 0.5 * wek * (sstm + toc1)) / p.hmoc)
+    dtonew = toc1 - new
+    dtoinv = 1.0 / (toc1 - toc2)
+    xfo = -(0.5 * dtoinv) * wek * (sstm - toc1) - (p.hmoc * dtoinv / tdt) * np.maximum(0.0, dtonew)
+    new = new + np.maximum(0.0, dtonew)
+    xfo = xfo - xfo.sum() / (nxt * nyt)
+    X = pad(xfo, None, None, xm)                     # edge and corner rules = averaging with copied ghosts
+    ent = 0.25 * (X[:-1, :-1] + X[1:, :-1] + X[:-1, 1:] + X[1:, 1:])
+    return (got_sst, new), (got_ent, ent), s, m, p
+
+
+@pytest.mark.parametrize("case", ["box_dg", "box_natl1km", "chan_so", "box_plain"])
+def test_oml_whole_domain_against_ghost_cell_scheme(qg, pyorc, case):
+    if case == "box_plain":
+        p = small_configs(qg)["box_dg"]
+        p.flags = ["ocean_only"]                     # neither sb_hflux nor nb_hflux
+    else:
+        p = small_configs(qg)[case]
+    (got_sst, want_sst), (got_ent, want_ent), s, m, p = _oml_ghost_cells(qg, pyorc, p)
+    assert rel_l2(got_sst, want_sst) <= 1e-13, case
+    scale = np.abs(want_ent).max()
+    assert np.abs(got_ent - want_ent).max() <= 1e-12 * scale, case
+    w = np.ones(p.nxpo); w[0] = w[-1] = 0.5
+    wy = np.ones(p.nypo); wy[0] = wy[-1] = 0.5
+    assert abs(s["xon"][0]) <= 1e-10 * (w @ np.abs(want_ent) @ wy) * p.dxo ** 2      # zero net entrainment
