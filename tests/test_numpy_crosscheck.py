@@ -797,3 +797,73 @@ def test_oml_whole_domain_against_ghost_cell_scheme(qg, pyorc, case):
     w = np.ones(p.nxpo); w[0] = w[-1] = 0.5
     wy = np.ones(p.nypo); wy[0] = wy[-1] = 0.5
     assert abs(s["xon"][0]) <= 1e-10 * (w @ np.abs(want_ent) @ wy) * p.dxo ** 2      # zero net entrainment
+
+
+@pytest.mark.parametrize("deck", ["dg_coupled", "so_coupled"])
+def test_aml_whole_domain_against_ghost_cell_scheme(qg, pyorc, deck):
+    """aml/amladf (src/amlsubs.F:47-563) on the whole atmosphere grid: periodic in x; on the zonal
+    walls no heat flux (temperature ghost = inside value, no advective flux), while the
+    thickness sees hmat outside and is carried through the wall by vekat"""
+    if deck == "dg_coupled":
+        p = qg.named_config(deck).scaled(6, 5, ndxr=16, name="cpl_dg")
+    else:
+        p = qg.named_config(deck).scaled(12, 3, nxta=12, nyta=9, ndxr=16, name="cpl_so")
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.run(1, 2)
+    nxt, nyt, nxp, nyp, nl = p.nxta, p.nyta, p.nxta + 1, p.nyta + 1, p.nla
+    g = lambda n, sh: m.get_field(n, sh)
+    ast, astm, hm, hmm = g("ast", (nxt, nyt)), g("astm", (nxt, nyt)), g("hmixa", (nxt, nyt)), g("hmixam", (nxt, nyt))
+    fnet, wekta, xc1 = g("fnetat", (nxt, nyt)), g("wekta", (nxt, nyt)), g("xc1ast", (nxt, nyt))
+    uek, vek = g("uekat", (nxp, nyt)), g("vekat", (nxt, nyp))
+    pa, pam, dtop = g("pa", (nxp, nyp, nl)), g("pam", (nxp, nyp, nl)), g("dtopat", (nxp, nyp))
+    m.aml()
+    ast_n, hm_n, ent_n = g("ast", (nxt, nyt)), g("hmixa", (nxt, nyt)), g("entat", (nxp, nyp))
+    dxa = p.ndxr * p.dxo
+    rdxf0, hdx, dxm2 = 1.0 / (dxa * p.fnot), 0.5 / dxa, 1.0 / dxa ** 2
+    tdt = 2.0 * p.dta
+    rrcpat = 1.0 / (cfg.rhoat * cfg.cpat)
+    p1 = pa[:, :, 0]
+    u = -rdxf0 * (p1[:, 1:] - p1[:, :-1]) + uek
+    v = rdxf0 * (p1[1:, :] - p1[:-1, :]) + vek
+    v[:, 0], v[:, -1] = vek[:, 0], vek[:, -1]            # p is uniform along the zonal walls
+
+    def pad(f, south, north):
+        gg = np.empty((f.shape[0] + 2, f.shape[1] + 2))
+        gg[1:-1, 1:-1] = f
+        gg[1:-1, 0] = f[:, 0] if south is None else south
+        gg[1:-1, -1] = f[:, -1] if north is None else north
+        gg[0], gg[-1] = gg[-2], gg[1]
+        return gg
+
+    lap = lambda gg: gg[1:-1, :-2] + gg[:-2, 1:-1] + gg[2:, 1:-1] + gg[1:-1, 2:] - 4.0 * gg[1:-1, 1:-1]
+
+    def flux_div(gg, vv):
+        x = hdx * (u[1:] * (gg[1:-1, 1:-1] + gg[2:, 1:-1]) - u[:-1] * (gg[:-2, 1:-1] + gg[1:-1, 1:-1]))
+        y = hdx * (vv[:, 1:] * (gg[1:-1, 1:-1] + gg[1:-1, 2:]) - vv[:, :-1] * (gg[1:-1, :-2] + gg[1:-1, 1:-1]))
+        return x + y
+
+    vT = v.copy(); vT[:, 0] = vT[:, -1] = 0.0            # no heat flux through the walls
+    d2 = lap(pad(astm, None, None))
+    tmrhs = -flux_div(pad(ast, None, None), vT) + p.at2d * dxm2 * d2 - p.at4d * dxm2 ** 2 * lap(pad(d2, None, None))
+    hmrhs = -flux_div(pad(hm, p.hmat, p.hmat), v) + p.ahmd * dxm2 * lap(pad(hmm, p.hmat, p.hmat))
+    tat1, tat2 = cfg.tat[0], cfg.tat[1]
+    hdrcdt = p.hmadmp * rrcpat * tdt
+    cold = astm <= tat1 - 2.0 * hdrcdt
+    with np.errstate(divide="ignore", invalid="ignore"):
+        hnew = hmm + tdt * hmrhs - hdrcdt * (hmm - p.hmat) / (tat1 - astm)
+    dhfix = np.maximum(p.hmamin - hnew, 0.0)
+    hnew = np.where(cold, hnew + dhfix, p.hmat)
+    dtfix = np.where(cold, dhfix * (tat1 - astm) / hmm, 0.0)
+    astnew = astm + tdt * (tmrhs + rrcpat * fnet / hmm - wekta * astm / p.hmat) + dtfix
+    dtanew = tat1 - astnew
+    conena = hm * np.minimum(0.0, dtanew) / (tdt * (tat2 - tat1))
+    xfa = p.xcexp * cfg.bface * (hmm - p.hmat) + cfg.dface * (p.xcexp * astm + xc1) - p.xcexp * conena
+    astnew = astnew + np.minimum(0.0, dtanew)
+    assert rel_l2(ast_n, astnew) <= 1e-13
+    assert rel_l2(hm_n, hnew) <= 1e-13
+    X = pad(xfa, None, None)
+    ent = 0.25 * (X[:-1, :-1] + X[1:, :-1] + X[:-1, 1:] + X[1:, 1:])
+    ent = ent + sum(cfg.aface[l] / cfg.gpat[l] * (pam[:, :, l] - pam[:, :, l + 1]) for l in range(nl - 1)) + cfg.cface * dtop
+    assert np.abs(ent_n - ent).max() <= 1e-12 * np.abs(ent).max()
