@@ -867,3 +867,39 @@ def test_aml_whole_domain_against_ghost_cell_scheme(qg, pyorc, deck):
     ent = 0.25 * (X[:-1, :-1] + X[1:, :-1] + X[:-1, 1:] + X[1:, 1:])
     ent = ent + sum(cfg.aface[l] / cfg.gpat[l] * (pam[:, :, l] - pam[:, :, l + 1]) for l in range(nl - 1)) + cfg.cface * dtop
     assert np.abs(ent_n - ent).max() <= 1e-12 * np.abs(ent).max()
+
+
+def test_qgostep_box_walls_and_time_levels(qg, pyorc):
+    """the parts of qgostep the interior check leaves out (src/qgosubs.F:184-219, SURVEY.md
+    quirk 5): the W/E wall columns are stepped with the forcing alone (dqdt = 0 there,
+    :371, :397), every interior row of qom takes the old qo, the zonal boundary rows of qo stay
+    and qom copies them"""
+    p = small_configs(qg)["box_dg"]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.ocean_step()
+    m.oml()
+    sh = (p.nxpo, p.nypo, p.nlo)
+    pom, qo, qom = (m.get_field(n, sh) for n in ("pom", "qo", "qom"))
+    wek, ent = m.get_field("wekpo", sh[:2]), m.get_field("entoc", sh[:2])
+    m.qgostep()
+    qnew, qmnew = m.get_field("qo", sh), m.get_field("qom", sh)
+    dxm2 = 1.0 / p.dxo ** 2
+    bcf = p.bccooc * dxm2 / (0.5 * p.bccooc + 1.0)
+    tdt = 2.0 * p.dto
+    rows = slice(1, -1)
+    for wall, inner in ((0, 1), (-1, -2)):
+        d2w = bcf * (pom[inner, rows, -1] - pom[wall, rows, -1])        # del-sqd of the bottom layer on the wall
+        for k in range(p.nlo):
+            f = np.zeros(p.nypo - 2)
+            if k == 0:
+                f = f + (p.fnot / p.hoc[0]) * (wek[wall, rows] - ent[wall, rows])
+            if k == 1:
+                f = f + (p.fnot / p.hoc[1]) * ent[wall, rows]
+            if k == p.nlo - 1:
+                f = f - 0.5 * np.sign(p.fnot) * p.delek / p.hoc[-1] * d2w
+            assert rel_l2(qnew[wall, rows, k], qom[wall, rows, k] + tdt * f) <= 1e-14, (wall, k)
+    assert np.array_equal(qmnew[:, rows, :], qo[:, rows, :])
+    for j in (0, -1):
+        assert np.array_equal(qnew[:, j, :], qo[:, j, :]) and np.array_equal(qmnew[:, j, :], qo[:, j, :])
