@@ -903,3 +903,47 @@ def test_qgostep_box_walls_and_time_levels(qg, pyorc):
     assert np.array_equal(qmnew[:, rows, :], qo[:, rows, :])
     for j in (0, -1):
         assert np.array_equal(qnew[:, j, :], qo[:, j, :]) and np.array_equal(qmnew[:, j, :], qo[:, j, :])
+
+
+def test_qgostep_channel_boundary_integrals(qg, pyorc):
+    """the zonal-boundary sums a channel feeds into its momentum constraints (src/qgosubs.F:
+    155-162 bdrins/bdrinn, :284-296 and :409-423 Jacobian strips, :429-443 third and fifth
+    derivative strips)"""
+    p = small_configs(qg)["chan_so"]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    m.ocean_step()
+    m.oml()
+    nl, nxt = p.nlo, p.nxto
+    sh = (p.nxpo, p.nypo, nl)
+    po, pom, qo = (m.get_field(n, sh)[:-1] for n in ("po", "pom", "qo"))       # the nxto distinct columns
+    m.qgostep()
+    s = m.get_scalars().as_dict()
+    dxm2 = 1.0 / p.dxo ** 2
+    bcf = p.bccooc * dxm2 / (0.5 * p.bccooc + 1.0)
+    adf = 1.0 / (12.0 * p.dxo ** 2 * p.fnot)
+
+    def lap(f):
+        out = np.empty_like(f)
+        out[:, 1:-1] = (f[:, :-2] + np.roll(f, 1, axis=0)[:, 1:-1] + np.roll(f, -1, axis=0)[:, 1:-1] + f[:, 2:] - 4.0 * f[:, 1:-1]) * dxm2
+        out[:, 0] = bcf * (f[:, 1] - f[:, 0])
+        out[:, -1] = bcf * (f[:, -2] - f[:, -1])
+        return out
+
+    dpx = lambda f, j: np.roll(f[:, j], -1) - np.roll(f[:, j], 1)           # p(i+1,j) - p(i-1,j), periodic
+    for k in range(nl):
+        P, Q = po[:, :, k], qo[:, :, k]
+        d2 = lap(pom[:, :, k]); d4 = lap(d2)
+        ajis = p.dxo ** 2 * p.fnot * adf * ((Q[:, 0] * dpx(P, 1)).sum() + 2.0 * (Q[:, 1] * dpx(P, 1)).sum())
+        ajin = -p.dxo ** 2 * p.fnot * adf * ((Q[:, -1] * dpx(P, -2)).sum() + 2.0 * (Q[:, -2] * dpx(P, -2)).sum())
+        sc = p.dxo ** 2 * abs(p.fnot * adf) * 3.0 * (np.abs(Q[:, 0]) * np.abs(dpx(P, 1))).sum()
+        assert abs(s["ajisoc"][k] - ajis) <= 1e-11 * sc and abs(s["ajinoc"][k] - ajin) <= 1e-11 * sc, k
+        for name, fld, coef, rows in (("ap3soc", d2, p.ah2oc[k], (1, 0)), ("ap3noc", d2, p.ah2oc[k], (-1, -2)),
+                                      ("ap5soc", d4, p.ah4oc[k], (1, 0)), ("ap5noc", d4, p.ah4oc[k], (-1, -2))):
+            diff = fld[:, rows[0]] - fld[:, rows[1]]
+            assert abs(s[name][k] - coef * diff.sum()) <= 1e-11 * max(coef, 1e-300) * np.abs(diff).sum(), (name, k)
+    bd = 0.5 * np.sign(p.fnot) * p.delek
+    ds, dn = pom[:, 1, -1] - pom[:, 0, -1], pom[:, -1, -1] - pom[:, -2, -1]
+    assert abs(s["bdrins"] - bd * ds.sum()) <= 1e-12 * abs(bd) * np.abs(ds).sum()
+    assert abs(s["bdrinn"] - bd * dn.sum()) <= 1e-12 * abs(bd) * np.abs(dn).sum()
