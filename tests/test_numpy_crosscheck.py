@@ -947,3 +947,62 @@ def test_qgostep_channel_boundary_integrals(qg, pyorc):
     ds, dn = pom[:, 1, -1] - pom[:, 0, -1], pom[:, -1, -1] - pom[:, -2, -1]
     assert abs(s["bdrins"] - bd * ds.sum()) <= 1e-12 * abs(bd) * np.abs(ds).sum()
     assert abs(s["bdrinn"] - bd * dn.sum()) <= 1e-12 * abs(bd) * np.abs(dn).sum()
+
+
+def _channel_homsol(ny, dx, rdm2, xl, yl):
+    """1-D version of the channel's homogeneous baroclinic solutions (src/conhoms.F:400-543):
+    pch = L(y) + rdm2 * sol0 with sol0'' - rdm2 sol0 = L(y), sol0 = 0 on both walls"""
+    a = 1.0 / dx ** 2
+    y = np.arange(ny) * dx
+    out = []
+    for L in ((y[-1] - y) / yl, (y - y[0]) / yl):
+        n = ny - 2
+        ab = np.zeros((3, n)); ab[0, 1:] = a; ab[1, :] = -2.0 * a - rdm2; ab[2, :-1] = a
+        sol = np.zeros(ny)
+        sol[1:-1] = sla.solve_banded((1, 1), ab, L[1:-1])
+        out.append(L + rdm2 * sol)
+    p1, p2 = out
+    w = np.ones(ny); w[0] = w[-1] = 0.5
+    aip = 0.5 * ((w @ p1) + (w @ p2)) * xl * dx
+    ys = lambda q: xl * (-(q[1] - q[0]) / dx + 0.5 * dx * rdm2 * q[0])
+    yn = lambda q: xl * ((q[-1] - q[-2]) / dx + 0.5 * dx * rdm2 * q[-1])
+    det = ys(p1) * yn(p2) - ys(p2) * yn(p1)
+    return p1, p2, aip, ys(p1) / det, ys(p2) / det, yn(p1) / det, yn(p2) / det
+
+
+def test_homsol_channel_against_numpy(qg, pyorc):
+    p = small_configs(qg)["chan_so"]
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    nl, nyp = p.nlo, p.nypo
+    s = m.get_scalars().as_dict()
+    pch1, pch2 = m.get_field("pch1oc", (nyp, nl - 1)), m.get_field("pch2oc", (nyp, nl - 1))
+    xl, yl = p.nxto * p.dxo, p.nyto * p.dxo
+    assert np.allclose(m.get_field("pbhoc"), (nyp - 1 - np.arange(nyp)) / (nyp - 1), rtol=1e-15, atol=0.0)
+    assert np.isclose(s["hbsioc"], yl / xl, rtol=1e-15) and np.isclose(s["aipbho"], 0.5 * xl * yl, rtol=1e-15)
+    for mo in range(nl - 1):
+        p1, p2, aip, h1s, h2s, h1n, h2n = _channel_homsol(nyp, p.dxo, cfg.rdm2oc[mo + 1], xl, yl)
+        assert rel_l2(pch1[:, mo], p1) <= 1e-12 and rel_l2(pch2[:, mo], p2) <= 1e-12, mo
+        assert np.isclose(s["aipcho"][mo], aip, rtol=1e-12)
+        for name, v in (("hc1soc", h1s), ("hc2soc", h2s), ("hc1noc", h1n), ("hc2noc", h2n)):
+            assert np.isclose(s[name][mo], v, rtol=1e-10), (name, mo)
+
+
+def test_homsol_atmosphere_against_numpy(qg, pyorc):
+    """the atmosphere's twin (src/conhoms.F:650-818)"""
+    p = qg.named_config("dg_coupled").scaled(6, 5, ndxr=16, name="cpl_dg")
+    cfg = qg.build_config(p)
+    m = pyorc.Oracle(cfg)
+    qg.synth.init_model(m, p, cfg, "random")
+    nl, nyp = p.nla, p.nyta + 1
+    dxa = p.ndxr * p.dxo
+    s = m.get_scalars().as_dict()
+    pch1, pch2 = m.get_field("pch1at", (nyp, nl - 1)), m.get_field("pch2at", (nyp, nl - 1))
+    xl, yl = p.nxta * dxa, p.nyta * dxa
+    for mo in range(nl - 1):
+        p1, p2, aip, h1s, h2s, h1n, h2n = _channel_homsol(nyp, dxa, cfg.rdm2at[mo + 1], xl, yl)
+        assert rel_l2(pch1[:, mo], p1) <= 1e-12 and rel_l2(pch2[:, mo], p2) <= 1e-12, mo
+        assert np.isclose(s["aipcha"][mo], aip, rtol=1e-12)
+        for name, v in (("hc1sat", h1s), ("hc2sat", h2s), ("hc1nat", h1n), ("hc2nat", h2n)):
+            assert np.isclose(s[name][mo], v, rtol=1e-10), (name, mo)
