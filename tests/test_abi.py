@@ -87,3 +87,31 @@ def test_header_and_library_work_from_plain_c(qg, tmp_path):
     assert int(sizes["monitor_ocean"]) == C.sizeof(qg.QgcmMonitorOcean)
     assert int(sizes["monitor_atmos"]) == C.sizeof(qg.QgcmMonitorAtmos)
     assert "ABI mismatch" in r.stdout
+
+
+def test_integration_md_fortran_mirror_matches_the_header(qg):
+    """no Fortran compiler exists here, so the bind(C) mirror of qgcm_config printed in
+    INTEGRATION.md is checked textually: same members, same order, same extents as the header"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"type, bind\(C\) :: qgcm_config(.*?)end type", text, re.S).group(1)
+    members = []
+    for line in block.splitlines():
+        line = line.split("!")[0].strip()
+        if "::" not in line:
+            continue
+        ftype, names = line.split("::")
+        base = C.c_int32 if "c_int32_t" in ftype else C.c_double
+        for decl in re.findall(r"(\w+)(?:\(([^)]*)\))?", names):
+            name, ext = decl
+            if not name:
+                continue
+            n = 1
+            if ext:
+                n = eval(ext.replace("QGCM_NLMAX", str(qg.abi.NLMAX)))
+            members.append((name.lower(), base, n))
+    header = []
+    for name, typ in qg.QgcmConfig._fields_:
+        is_array = hasattr(typ, "_length_")
+        header.append((name.lower(), typ._type_ if is_array else typ, typ._length_ if is_array else 1))
+    assert members == header
