@@ -5,7 +5,10 @@
 // Loop-for-loop C++ restatement of the reference's Fortran step routines, same loop
 // order and expression association, compiled with -ffp-contract=off.
 #pragma once
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -51,6 +54,20 @@ struct Model {
   vec po_avg;
   int nsumat = 0, nsumoc = 0, nsum_ocavg = 0;
   qgcm_scalars s;
+  // work arrays of the step routines.  The reference declares them as automatic arrays
+  // (e.g. dqdt(nxpo,nypo,nlo), src/qgosubs.F:65): stack storage that is neither zeroed nor
+  // re-mapped from call to call.  A fresh std::vector per call would add a serial zero-fill and
+  // a page fault per 4 KB of every temporary to each CPU step, so they persist here instead.
+  vec wk_del2p, wk_dqdt, wk_d4p, wk_wrk, wk_rhs, wk_xfo, wk_del2t;
+  vec wk_u1ator, wk_v1ator, wk_tauxaor, wk_tauyaor, wk_wektaor, wk_asto;      // xforc, src/xfosubs.F:100-118
+  // ORC_POISON=1 fills them with NaN at every use: no routine may rely on what a previous
+  // call left behind (tests/test_golden_fingerprints.py runs the fingerprints that way too)
+  static vec &work(vec &v, size_t n) {
+    if (v.size() != n) v.resize(n);
+    static const bool poison = std::getenv("ORC_POISON") != nullptr;
+    if (poison) std::fill(v.begin(), v.end(), std::nan(""));
+    return v;
+  }
 
   explicit Model(const qgcm_config &cfg);
   vec *field(const std::string &name);

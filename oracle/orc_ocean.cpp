@@ -287,7 +287,7 @@ void Model::qcomp_ocean() {
 // ---------------------------------------------------------------- src/qgosubs.F:45-221
 void Model::qgostep() {
   const size_t np = (size_t)nxpo * nypo;
-  vec del2p(np), dqdt(np * nlo);
+  vec &del2p = work(wk_del2p, np), &dqdt = work(wk_dqdt, np * nlo);
   const double adfaco = 1.0 / (12.0 * dxo * dyo * fnot);
   const double bcfaco = c.bccooc * dxom2 / (0.5 * c.bccooc + 1.0);
   double fohfac[QGCM_NLMAX];
@@ -359,7 +359,7 @@ void Model::qgostep() {
 void Model::ocadif(double *dqdt, const double *d2p, double ah2ock, double ah4ock, double bcfaco,
                    const double *p, const double *q, double adfaco, int k) {
   const size_t np = (size_t)nxpo * nypo;
-  vec d4p(np);
+  vec &d4p = work(wk_d4p, np);
   const double ah2fac = ah2ock / fnot;
   const double ah4fac = ah4ock / fnot;
 #define D2(i, j) d2p[IX2(i, j, nxpo)]
@@ -570,7 +570,7 @@ static void lu_solve_refine(const double *a, int n, const double *rhs, double *x
 void Model::ocinvq() {
   const double ecrito = 1.0e-13;
   const size_t np = (size_t)nxpo * nypo;
-  vec wrk(np * nlo);
+  vec &wrk = work(wk_wrk, np * nlo);
   double xinhom[QGCM_NLMAX];
 #define WRK(i, j, m) wrk[IX3(i, j, m, nxpo, nypo)]
 #define QO(i, j, k) qo[IX3(i, j, k, nxpo, nypo)]
@@ -725,7 +725,7 @@ void Model::ocinvq() {
 // ---------------------------------------------------------------- src/omlsubs.F:47-236
 void Model::oml() {
   const size_t nt = (size_t)nxto * nyto;
-  vec rhs(nt), xfo(nt);
+  vec &rhs = work(wk_rhs, nt), &xfo = work(wk_xfo, nt);
   const double hmoinv = 1.0 / c.hmoc;
   const double dtoinv = 1.0 / (c.toc[0] - c.toc[1]);
   const double entfac = c.hmoc * dtoinv / tdto;
@@ -813,7 +813,7 @@ void Model::omladf(double *rhs, const double *po1) {
   const double d4tfac = c.st4d * dxom2 * dxom2;
   const double tsbdy = c.tsbdy, tnbdy = c.tnbdy;
   const int nxd = nxto + 2;  // del2t(0:nxto+1,nyto)
-  vec del2t((size_t)nxd * nyto);
+  vec &del2t = work(wk_del2t, (size_t)nxd * nyto);
 #define D2T(i, j) del2t[(size_t)(i) + (size_t)nxd * ((j)-1)]
 #define PO1(i, j) po1[IX2(i, j, nxpo)]
 #define TX(i, j) tauxo[IX2(i, j, nxpo)]

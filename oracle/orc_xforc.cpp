@@ -307,7 +307,10 @@ void Model::xforc() {
     V1(nxpa, j) = V1(1, j);
   }
   const size_t nfine = (size_t)nxpaor * nypaor;
-  vec u1ator(nfine, 0.0), v1ator(nfine, 0.0), tauxaor(nfine), tauyaor(nfine);
+  vec &u1ator = work(wk_u1ator, nfine), &v1ator = work(wk_v1ator, nfine);
+  vec &tauxaor = work(wk_tauxaor, nfine), &tauyaor = work(wk_tauyaor, nfine);
+#pragma omp parallel for schedule(static)
+  for (size_t n = 0; n < nfine; ++n) u1ator[n] = v1ator[n] = 0.0;
   auvbcu(*this, u1at.data(), u1ator, v1at.data(), v1ator);
 #define UF(i, j) u1ator[IX2(i, j, nxpaor)]
 #define VF(i, j) v1ator[IX2(i, j, nxpaor)]
@@ -400,7 +403,7 @@ void Model::xforc() {
       wekta[IX2(ia, ja, nxta)] = -hmrdxa * (UE(ia + 1, ja) - UE(ia, ja) + VE(ia, ja + 1) - VE(ia, ja));
   }
   // Ekman pumping at ocean resolution on atmosphere T points, src/xfosubs.F:425-432
-  vec wektaor((size_t)nxtaor * nytaor);
+  vec &wektaor = work(wk_wektaor, (size_t)nxtaor * nytaor);
 #define WTF(i, j) wektaor[IX2(i, j, nxtaor)]
 #pragma omp parallel for schedule(static)
   for (int j = 1; j <= nytaor; ++j)
@@ -463,7 +466,8 @@ void Model::xforc() {
     xforc_ocean_ekman();
   }
   // ---- diabatic forcing, src/xfosubs.F:711-853 ----
-  vec xta(nxta), xto(nxto), asto((size_t)nxto * nyto);
+  vec xta(nxta), xto(nxto);
+  vec &asto = work(wk_asto, (size_t)nxto * nyto);
   for (int i = 1; i <= nxta; ++i) xta[i - 1] = (i - 1) * dxa + 0.5 * dxa;
   for (int i = 1; i <= nxto; ++i) xto[i - 1] = ((i - 1) * dxo + (nx1 - 1) * dxa) + 0.5 * dxo;
   bilint(*this, xta.data(), yta.data(), nxta, nyta, astm.data(), xto.data(), yto.data(), nxto, nyto, asto.data(), 1.0);

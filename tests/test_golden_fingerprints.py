@@ -43,3 +43,22 @@ def test_oracle_reproduces_its_fingerprints(qg, pyorc, case):
 def test_cuda_path_matches_the_committed_fingerprints(qg, pyorc, case):
     """the CUDA path against the committed fixtures alone: no oracle runs in this test"""
     _check(case, make_golden.run_case(qg, pyorc, make_golden.cases(qg)[case], make=qg.Model))
+
+
+def test_oracle_work_arrays_carry_nothing_between_calls():
+    """the oracle's persistent work arrays (the reference's automatic arrays) poisoned with NaN
+    before every use: the fingerprints must not move"""
+    import subprocess
+    code = (
+        "import sys, json\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import make_golden, _pkg, pyorc\n"
+        "qg = _pkg.load()\n"
+        "print(json.dumps({c: make_golden.run_case(qg, pyorc, make_golden.cases(qg)[c]) for c in ('box_dg', 'chan_so', 'cpl_dg')}))\n"
+    ) % (os.path.join(HERE, "golden"), os.path.dirname(HERE))
+    env = dict(os.environ, ORC_POISON="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    now = json.loads(r.stdout.strip().splitlines()[-1])
+    for case, vals in now.items():
+        _check(case, vals)
