@@ -113,6 +113,13 @@ inline int pick_march_rows(int nrows, int bx, int resident, int lo, int cap) {
   return cap;
 }
 
+// points per direction of the sub-sampled output of ocnc_out / atnc_out / qocdiag_out:
+// min(mod(n,nsk),1) + (n - mod(n,nsk))/nsk  (src/nc_subs.F:869-876)
+inline int sub_count(int n, int nsk) {
+  const int mwk = n % nsk;
+  return std::min(mwk, 1) + (n - mwk) / nsk;
+}
+
 // Plan for the batched x-transform + partitioned y-tridiagonal Helmholtz solver
 struct HelmPlan {
   int kind;          // 0: DST-I rows (box), 1: real FFT rows (periodic)

@@ -83,11 +83,6 @@ __global__ void __launch_bounds__(256) k_qd_terms(QdArgs a) {
   a.out[(size_t)4 * a.nl * plane + o] = ent;
 }
 
-static int sub_count(int n, int nsk) {
-  const int mwk = n % nsk;
-  return std::min(mwk, 1) + (n - mwk) / nsk;
-}
-
 void qocdiag_size(qgcm_model *m, int nsk, int64_t *n) {
   if (!m->has_ocean) throw std::runtime_error("qgcm_qocdiag: no ocean in this model");
   if (nsk < 1) throw std::runtime_error("qgcm_qocdiag: nsko must be >= 1");

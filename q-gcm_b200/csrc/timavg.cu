@@ -6,7 +6,7 @@
 // them with qgcm_get_field when tavout needs them (end of run) instead of downloading the
 // full state at every accumulation; the sub-sampled read returns exactly the vector the
 // reference hands to nf_put_vara_double.  These run at diagnostic cadence (once per model day
-// / per output interval): plain coalesced one-pass kernels, two columns (16 bytes) per lane.
+// / per output interval): plain coalesced one-pass kernels.
 #include <cstring>
 
 #include "qgcm_internal.h"
@@ -227,12 +227,6 @@ void launch_avg_ocn_k247(qgcm_model *m) {
   QG_LAUNCH(m, "k_accum", dim3((ld2 + 255) / 256, std::min(g.nyp, 592), g.nl), 256, 0, k_accum, m->F("po_avg"), m->F("po"), ld2, g.nyp,
             g.lsz / 2);
   m->nsum_ocavg++;
-}
-
-// iw = min(mod(nx,nsk),1) + (nx - mod(nx,nsk))/nsk points per direction (src/nc_subs.F:869-876)
-static int sub_count(int n, int nsk) {
-  const int mwk = n % nsk;
-  return std::min(mwk, 1) + (n - mwk) / nsk;
 }
 
 void field_sub_size(qgcm_model *m, const char *name, int nsk, int64_t *n) {
