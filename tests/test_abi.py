@@ -115,3 +115,15 @@ def test_integration_md_fortran_mirror_matches_the_header(qg):
         is_array = hasattr(typ, "_length_")
         header.append((name.lower(), typ._type_ if is_array else typ, typ._length_ if is_array else 1))
     assert members == header
+
+
+def test_generated_fortran_module_is_current():
+    """integration/qgcm_types.f90 (bind(C) types and one interface per entry point) is generated
+    from the header; a stale copy fails here"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "gen_fortran_types.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == open(os.path.join(root, "integration", "qgcm_types.f90")).read()
+    assert r.stdout.count("end function") == 55 and max(len(l) for l in r.stdout.splitlines()) <= 132
