@@ -135,3 +135,79 @@ def test_slab_bounds_host_only():
     assert qg.slab_bounds(4801, 8, 0) == (0, 601)
     assert qg.slab_bounds(4801, 8, 7) == (4201, 600)
     assert sum(qg.slab_bounds(4801, 8, r)[1] for r in range(8)) == 4801
+
+
+def _monitor_worker(rank, world, port, nyp, nx, q):
+    """the share algebra of qgcm_monnc_ocean on a y-slab partition (monitor.cu: mon_share /
+    mon_finish), restated in numpy over gloo: per sum slot the interior-row sum a rank owns plus
+    the global south / north row values if it owns them, combined by ONE all-reduce(sum);
+    extrema and jet candidates travel in a one-hot block per rank of the same vector"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sys.path.insert(0, root)
+        import _pkg
+        qg = _pkg.load()
+        rng = np.random.default_rng(5)
+        nyt = nyp - 1
+        pfield = rng.standard_normal((nx, nyp))          # a p-grid integrand (weights 0.5 W/E, 0.5 S/N)
+        tfield = rng.standard_normal((nx, nyt))          # a T-row integrand (u points: weights 0.5 W/E, 1 S/N)
+        ujet = rng.standard_normal(nyt)
+        ujet[[3, nyt - 4]] = 9.0                         # a tie: the first row must win (src/monitor_diag.F:696-704)
+        wx = np.ones(nx); wx[0] = wx[-1] = 0.5
+        j0, n = qg.slab_bounds(nyp, world, rank)
+        vec = np.zeros(6 + 4 * world)
+        for slot, (f, ny) in enumerate(((pfield, nyp), (tfield, nyt))):
+            rows = wx @ f                                # what the row kernels produce
+            j1 = min(j0 + n, ny)
+            for j in range(j0, j1):
+                if j == 0:
+                    vec[3 * slot + 1] = rows[j]
+                elif j == ny - 1:
+                    vec[3 * slot + 2] = rows[j]
+                else:
+                    vec[3 * slot] += rows[j]
+        own = slice(j0, min(j0 + n, nyt))
+        g = 6 + 4 * rank
+        vec[g], vec[g + 1] = tfield[:, own].min(), tfield[:, own].max()
+        best, brow = 0.0, 0
+        for j in range(own.start, own.stop):
+            if abs(ujet[j]) > best:
+                best, brow = abs(ujet[j]), j + 1
+        vec[g + 2], vec[g + 3] = best, brow
+        t = torch.from_numpy(vec)
+        dist.all_reduce(t)
+        vec = t.numpy()
+        gi = lambda slot, facsn: vec[3 * slot] + facsn * (vec[3 * slot + 1] + vec[3 * slot + 2])
+        wy = np.ones(nyp); wy[0] = wy[-1] = 0.5
+        e_p = abs(gi(0, 0.5) - wx @ pfield @ wy)
+        e_t = abs(gi(1, 1.0) - (wx @ tfield).sum())
+        lo = min(vec[6 + 4 * r] for r in range(world))
+        hi = max(vec[7 + 4 * r] for r in range(world))
+        jval, jpos = 0.0, 0
+        for r in range(world):                           # ranks hold increasing rows: first strict maximum wins
+            if vec[8 + 4 * r] > jval:
+                jval, jpos = vec[8 + 4 * r], int(vec[9 + 4 * r])
+        ok = (lo == tfield.min() and hi == tfield.max() and jval == 9.0 and jpos == 4)
+        q.put((rank, max(e_p, e_t), ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nyp", [(2, 41), (3, 100)])
+def test_monitor_share_algebra_over_gloo(world, nyp):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_monitor_worker, args=(r, world, port, nyp, 33, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, ok in res:
+        assert err <= 1e-11 and ok, (rank, err, ok)
