@@ -119,3 +119,26 @@ def test_atqzbd_quirk(qg, pyorc):
     betays = p.beta * (0.0 - 0.5 * yla)
     want = zb * (pa[:, 1, -1] - pa[:, 0, -1]) - (p.fnot * A[-1, -2] * pa[:, 0, -2] + p.fnot * A[-1, -1] * pa[:, 1, -1]) + betays
     assert np.allclose(qa[:, 0, -1], want, rtol=1e-13, atol=0)
+
+
+def test_modes_diagonalise_the_stretching_operator(qg):
+    """what the mode matrices are for (src/eigmode.f:41-440, src/ocisubs.F:117-139): with
+    q_k = del-sqd p_k - f0^2 (A p)_k, projecting layers onto modes turns f0^2 A into
+    diag(rdm2), i.e. ctl2m^T (f0^2 A) ctm2l^T = diag(rdm2); the barotropic mode is uniform in
+    the vertical, and the ocean's modes carry Flierl's normalisation sum_k H_k phi_k^2 = H"""
+    p = qg.named_config("dg_coupled")
+    cfg = qg.build_config(p)
+    for amat, l2m, m2l, rd, n, h, ocean in ((cfg.amatoc, cfg.ctl2moc, cfg.ctm2loc, cfg.rdm2oc, cfg.nlo, cfg.hoc, True),
+                                            (cfg.amatat, cfg.ctl2mat, cfg.ctm2lat, cfg.rdm2at, cfg.nla, cfg.hat, False)):
+        A = np.array(amat[: n * n]).reshape(n, n, order="F")
+        L = np.array(l2m[: n * n]).reshape(n, n, order="F")       # ctl2m(k,m)
+        M = np.array(m2l[: n * n]).reshape(n, n, order="F")       # ctm2l(m,k)
+        D = L.T @ (p.fnot ** 2 * A) @ M.T
+        want = np.diag(np.array(rd[:n]))
+        assert np.abs(D - want).max() <= 1e-10 * np.abs(want).max()
+        assert np.abs(A.sum(axis=1)).max() <= 1e-15 * np.abs(A).max()   # A annihilates a depth-independent p
+        assert np.allclose(M[0] / M[0, 0], 1.0, rtol=1e-12)       # so the barotropic mode is uniform
+        if ocean:
+            H = np.array(h[:n])
+            for m in range(n):
+                assert np.isclose((H * M[m] ** 2).sum(), H.sum(), rtol=1e-12) and M[m, 0] > 0.0
