@@ -172,7 +172,7 @@ def peer_self_check(qg, local, world, rank, dist, torch):
     return reason
 
 
-def cpu_sample(qg, p, cfg, budget_s=20.0, max_steps=4):
+def cpu_sample(qg, p, cfg, budget_s=15.0, max_steps=64):
     """time the CPU port on the same workload: as many ocean steps as fit the budget"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyorc
