@@ -243,6 +243,7 @@ def run_reference(args, qg):
                    "parallelism": "%d host threads (OpenMP)" % cores},
         "gpt_updates_per_s": v * p.nxpo * p.nypo * p.nlo / 1e9,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": int(os.environ.get("OMP_NUM_THREADS", cores)), "kind": "port",
+                         "effective_GBps": v * (58.0 if p.has("cyclic_ocean") else 60.0) * 8.0 * p.nxpo * p.nypo / 1e9,
                          "sample": "%d CPU ocean steps (C++/OpenMP restatement of the reference; the Fortran "
                                    "reference cannot be compiled here)" % n},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -469,7 +470,9 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_sample(qg, p, cfg)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        # effective_GBps: the same byte model as step_roofline_frac
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "effective_GBps": v * step_bytes / 1e9}
 
     if rank == 0:
         line = {
