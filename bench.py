@@ -110,6 +110,93 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_config(p, world, parallelism, transport=None, transport_note=None, extra=None):
+    """the `config` object of the JSON line: the same key set in both arms (the driver compares them)"""
+    coupled = not p.has("ocean_only")
+    fieldpass = 8.0 * p.nxpo * p.nypo
+    cfgd = {
+        "workload": "%s %s %dx%dx%d, %s, dto=%gs" % (p.name, "coupled" if coupled else "ocean-only", p.nxpo, p.nypo, p.nlo,
+                                                      "channel" if p.has("cyclic_ocean") else "box", p.dto),
+        "parallelism": parallelism,
+        "transport": transport, "transport_note": transport_note,
+        "l2": ("state (%.1f GB) is far larger than L2; no flush needed" if 4 * p.nlo * fieldpass > 4 * 126e6 else
+               "state (%.2f GB) is comparable to the 126 MB L2 and is NOT flushed between steps: a parity-size "
+               "deck, not a bench line") % (4 * p.nlo * fieldpass / 1e9),
+        "state_finite": None,
+    }
+    if extra:
+        cfgd.update(extra)
+    return cfgd
+
+
+def omp_all_cores():
+    """the oracle's OpenMP team on every host core this process may use.  torchrun exports
+    OMP_NUM_THREADS=1 to its workers and torch's libgomp has read it by the time the oracle is
+    loaded, so the team size is also set through the runtime call."""
+    cores = len(os.sched_getaffinity(0))
+    if "TORCHELASTIC_RUN_ID" in os.environ or "OMP_NUM_THREADS" not in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
+    except OSError:
+        pass
+    return int(os.environ["OMP_NUM_THREADS"])
+
+
+def verify_against_oracle(qg, m, p, cfg, world, rank, dist, torch, nsteps=2):
+    """--verify leg, outside every timed region: the model `m` (one GPU, or this rank's y-slab over
+    the transport the bench is about to time) and the CPU oracle on rank 0 take the same `nsteps`
+    ocean steps from the same synthetic state; every rank compares the rows it owns.  Returns
+    {field: relative L2 over the whole domain} on every rank.  The oracle's fields travel through
+    /dev/shm (ranks of one node), not through the GPU."""
+    import numpy as np
+    names = ("po", "qo", "sst", "entoc")
+    tag = "/dev/shm/qgcm_verify_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", str(os.getppid())))
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyorc
+        pyorc.build()
+        omp_all_cores()
+        o = pyorc.Oracle(cfg)
+        qg.synth.init_model(o, p, cfg, "random")
+        for _ in range(nsteps):
+            o.ocean_step()
+        os.makedirs(tag, exist_ok=True)
+        for n in names:
+            np.save(os.path.join(tag, n + ".npy"), o.get_field(n))
+        o.close()
+    if world > 1:
+        dist.barrier()      # the ranks enter the first exchange together (rank 0 was busy on the host)
+    for _ in range(nsteps):
+        m.ocean_step()
+    m.sync()
+    if world > 1:
+        dist.barrier()
+    j0, nown = qg.slab_bounds(p.nypo, world, rank) if world > 1 else (0, p.nypo)
+    acc = np.zeros(2 * len(names))
+    for i, n in enumerate(names):
+        ref = np.load(os.path.join(tag, n + ".npy"), mmap_mode="r")
+        got = m.get_field(n)
+        nx = p.nxpo if n in ("po", "qo", "entoc") else p.nxto
+        nyg = p.nypo if n in ("po", "qo", "entoc") else p.nyto
+        nl = ref.size // (nx * nyg)
+        a = got.reshape((nx, nyg, nl), order="F")[:, j0:min(j0 + nown, nyg), :]
+        b = np.asarray(ref).reshape((nx, nyg, nl), order="F")[:, j0:min(j0 + nown, nyg), :]
+        acc[2 * i] = float(((a - b) ** 2).sum())
+        acc[2 * i + 1] = float((b ** 2).sum())
+    if world > 1:
+        t = torch.tensor(acc, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        acc = t.cpu().numpy()
+        dist.barrier()
+    if rank == 0:
+        import shutil
+        shutil.rmtree(tag, ignore_errors=True)
+    return {n: float(np.sqrt(acc[2 * i] / acc[2 * i + 1])) if acc[2 * i + 1] > 0 else float(np.sqrt(acc[2 * i]))
+            for i, n in enumerate(names)}
+
+
 def build_case(qg, workload, device):
     p = qg.named_config(workload)
     cfg = qg.build_config(p, device=device)
@@ -178,9 +265,7 @@ def cpu_sample(qg, p, cfg, budget_s=15.0, max_steps=64):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyorc
     pyorc.build()
-    cores = len(os.sched_getaffinity(0))
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    os.environ.setdefault("OMP_PROC_BIND", "close")
+    cores = omp_all_cores()
     o = pyorc.Oracle(cfg)
     qg.synth.init_model(o, p, cfg, "random")
     coupled = not p.has("ocean_only")
@@ -207,46 +292,58 @@ def cpu_sample(qg, p, cfg, budget_s=15.0, max_steps=64):
 
 
 def run_reference(args, qg):
+    """--impl reference: the CPU restatement of the reference's own path (oracle/liborc.so, C++/OpenMP,
+    every host core) on the same workload; W warm-up steps and K timed steps as asked (a 1 km CPU step
+    costs ~0.3 s), bounded at a few minutes"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     p, cfg = build_case(qg, args.workload, 0)
-    # each "step" of the reference arm is one CPU ocean step; K and W are honoured but
-    # clamped so the whole run stays within a few minutes
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyorc
     pyorc.build()
-    cores = len(os.sched_getaffinity(0))
-    if "TORCHELASTIC_RUN_ID" in os.environ:
-        # torchrun pins every worker to OMP_NUM_THREADS=1; only rank 0 works here, on all host cores
-        os.environ["OMP_NUM_THREADS"] = str(cores)
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    os.environ.setdefault("OMP_PROC_BIND", "close")
+    cores = omp_all_cores()
     o = pyorc.Oracle(cfg)
     qg.synth.init_model(o, p, cfg, "random")
-    warm = max(1, min(args.warmup, 2))
+    coupled = not p.has("ocean_only")
+    state = {"nt": 1}
+
+    def step():
+        if coupled:
+            o.run(state["nt"], state["nt"] + p.nstr - 1)
+            state["nt"] += p.nstr
+        else:
+            o.ocean_step()
+
+    warm = max(args.warmup, 1)
+    t_w = time.time()
+    done_w = 0
     for _ in range(warm):
-        o.ocean_step()
+        step()
+        done_w += 1
+        if time.time() - t_w > 60.0:
+            break
     t0 = time.time()
     n = 0
     while n < args.steps:
-        o.ocean_step()
+        step()
         n += 1
-        if time.time() - t0 > 120.0:
+        if time.time() - t0 > 150.0:
             break
     dt = time.time() - t0
     v = n / dt
+    step_passes = 59.0 if p.has("cyclic_ocean") else 61.0
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
-        "warmup": warm, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": done_w, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s ocean-only %dx%dx%d, box, dto=%gs" % (p.name, p.nxpo, p.nypo, p.nlo, p.dto),
-                   "parallelism": "%d host threads (OpenMP)" % cores},
+        "config": workload_config(p, args.gpus, "%d host threads (OpenMP), no GPU" % cores),
         "gpt_updates_per_s": v * p.nxpo * p.nypo * p.nlo / 1e9,
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": int(os.environ.get("OMP_NUM_THREADS", cores)), "kind": "port",
-                         "effective_GBps": v * (59.0 if p.has("cyclic_ocean") else 61.0) * 8.0 * p.nxpo * p.nypo / 1e9,
-                         "sample": "%d CPU ocean steps (C++/OpenMP restatement of the reference; the Fortran "
-                                   "reference cannot be compiled here)" % n},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "effective_GBps": v * step_passes * 8.0 * p.nxpo * p.nypo / 1e9,
+                         "sample": "%d CPU ocean steps after %d warm-up (C++/OpenMP restatement of the reference; the "
+                                   "Fortran reference cannot be compiled here: no Fortran compiler in the image or on "
+                                   "the GPU box, profiles/r02_fortran_probe.txt)" % (n, done_w)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -261,6 +358,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true",
+                    help="skip the parity leg (two ocean steps against the CPU oracle before the warm-up, outside every timed region)")
     ap.add_argument("--transport", default=os.environ.get("QGCM_SLAB_TRANSPORT", "peer"), choices=["peer", "nccl"],
                     help="y-slab exchanges at N > 1: peer-memory mailboxes (default) or NCCL")
     args = ap.parse_args()
@@ -310,6 +409,10 @@ def main():
     m.sync()
     if world > 1:
         dist.barrier()
+    parity = None
+    if not args.no_verify and p.has("ocean_only"):
+        # parity at the benched size over the benched transport, before anything is timed
+        parity = verify_against_oracle(qg, m, p, cfg, world, rank, dist, torch)
     stream = torch.cuda.ExternalStream(m.stream(), device=local)
     nstr = p.nstr
     cad = 25   # time-level average every 25 ocean steps (src/q-gcm.F:1328)
@@ -482,19 +585,18 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if world > 1 else "weak",
+            "scaling": "strong",      # one fixed domain at every N (N > 1: y-slabs of it)
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s %s %dx%dx%d, %s, dto=%gs" % (p.name, "coupled" if coupled else "ocean-only", p.nxpo, p.nypo,
-                                                                      p.nlo, "channel" if p.has("cyclic_ocean") else "box", p.dto),
-                       "parallelism": ("%d y-slabs of one domain, %s, slab-coupled solve (2 rows per mode exchanged)" %
-                                       (world, "exchanges by the step's own kernels through NVLink peer-memory mailboxes"
-                                        if transport == "peer" else "NCCL halos and reductions")) if world > 1
-                       else "single GPU",
-                       "transport": transport, "transport_note": transport_note,
-                       "l2": ("state (%.1f GB) is far larger than L2; no flush needed" if 4 * p.nlo * fieldpass > 4 * 126e6 else
-                              "state (%.2f GB) is comparable to the 126 MB L2 and is NOT flushed between steps: a parity-size "
-                              "deck, not a bench line") % (4 * p.nlo * fieldpass / 1e9),
-                       "state_finite": finite},
+            "config": workload_config(
+                p, world,
+                ("%d y-slabs of one domain, %s, slab-coupled solve (2 rows per mode exchanged)" %
+                 (world, "exchanges by the step's own kernels through NVLink peer-memory mailboxes"
+                  if transport == "peer" else "NCCL halos and reductions")) if world > 1 else "single GPU",
+                transport, transport_note, {"state_finite": finite}),
+            # --verify: relative L2 against the CPU oracle after two ocean steps of this very workload
+            # on this very transport (every rank compares its own rows); the bar is 1e-11
+            "parity_rel_l2": parity,
+            "parity_ok": (max(parity.values()) <= 1e-11) if parity else None,
             "gpt_updates_per_s": value * p.nxpo * p.nypo * p.nlo / 1e9,
             "step_roofline_frac": step_frac,
             "step_algorithmic_bytes": step_bytes,

@@ -159,9 +159,12 @@ int qgcm_get_field(qgcm_model *m, const char *name, double *host, int64_t n);
 int qgcm_field_size(qgcm_model *m, const char *name, int64_t *n);
 /* Overlapped upload for forcing that the host supplies while the model runs (the ocean-only
  * reference reads tauxo/tauyo/fnetoc once, src/q-gcm.F:790-808; a host that updates them every
- * step uses this pair).  `host` must be page-locked and stay valid until the commit.  The
- * copy runs on a second stream into a shadow buffer; qgcm_commit_fields makes the step
- * stream wait for it and switches the named fields over. */
+ * step uses this pair).  `host` must be page-locked and must not be modified until the next
+ * synchronising call AFTER the commit (qgcm_sync, qgcm_get_field, qgcm_get_scalars) has
+ * returned: qgcm_commit_fields only orders the step stream behind the copy, it does not wait
+ * for the DMA on the host.  The copy runs on a second stream into a shadow buffer;
+ * qgcm_commit_fields makes the step stream wait for it and switches the named fields over
+ * (a field uploaded more than once before a commit keeps the last upload). */
 int qgcm_set_field_async(qgcm_model *m, const char *name, const double *host, int64_t n);
 int qgcm_commit_fields(qgcm_model *m);
 int qgcm_set_scalars(qgcm_model *m, const qgcm_scalars *s);
@@ -229,13 +232,20 @@ int qgcm_comm_init_nccl(qgcm_model *m, const void *id128);
  * the exchanges of qgcm_ocean_step are stores into the peers' mailboxes plus epoch flags,
  * issued by the kernels of the step themselves (no collective call on the step stream); the
  * initialisation procedures use the same mailboxes, so NCCL is optional.  All ranks must call
- * the partition procedures in the same order and enter each within ~10 s of the others: a
- * rank that waits longer gives up, and the next synchronising call reports the error.
+ * the partition procedures in the same order and enter each within the peer time-out of the
+ * others (120 s unless QGCM_PEER_TIMEOUT_S or qgcm_comm_peer_timeout says otherwise; a host
+ * that stalls one rank for longer -- restart or netCDF output on one rank -- puts an
+ * MPI_Barrier in front of the next step): a rank that waits longer gives up, its slab is then
+ * invalid, and every later call on that model, qgcm_get_field and qgcm_get_scalars included,
+ * fails with that error instead of handing back spoilt state (the flag lives in host-mapped
+ * memory, so the check costs no synchronisation and is made on every step).
  * qgcm_comm_transport switches a model that has both between NCCL (0) and peer memory (1);
  * every rank must switch at the same point of the call sequence. */
 int qgcm_peer_handle(qgcm_model *m, void *handle64);
 int qgcm_comm_init_peer(qgcm_model *m, const void *handles, int32_t n);
 int qgcm_comm_transport(qgcm_model *m, int32_t kind);
+/* give-up time of a mailbox wait in seconds (after qgcm_peer_handle; every rank the same) */
+int qgcm_comm_peer_timeout(qgcm_model *m, double seconds);
 /* Tear-down order (CUDA IPC rule: an exported buffer must not be freed while another process
  * still maps it): every rank calls qgcm_comm_close_peer (unmaps the others' mailboxes), the
  * host program synchronises the ranks (MPI_Barrier), then every rank calls qgcm_destroy. */

@@ -275,6 +275,7 @@ static void copy_field(qgcm_model *m, qgcm_model::Field &f, double *host, bool t
     }
   }
   QG_CUDA(cudaStreamSynchronize(m->stream));
+  if (!to_device) check_peer_err(m);      // never hand back state a timed-out exchange has spoilt
 }
 
 void launch_xforc(qgcm_model *m);
@@ -307,7 +308,9 @@ static void set_field_async(qgcm_model *m, const char *name, const double *host,
     QG_CUDA(cudaMemcpy2DAsync(shadow + (size_t)k * f.lsz, sizeof(double) * f.ld, h, sizeof(double) * f.nx, sizeof(double) * f.nx,
                               f.ny, cudaMemcpyHostToDevice, m->copy_stream));
   }
-  m->pending.push_back(name);
+  // a field uploaded twice before one commit overwrites its shadow buffer (same copy stream, in
+  // order) and is swapped exactly once
+  if (std::find(m->pending.begin(), m->pending.end(), name) == m->pending.end()) m->pending.push_back(name);
   if (std::strcmp(name, "ddynoc") == 0) m->ddynoc_flat = false;     // contents unknown until inspected: read the field
   if (std::strcmp(name, "ddynat") == 0) m->ddynat_flat = false;
 }
@@ -351,6 +354,7 @@ int qgcm_destroy(qgcm_model *m) {
   cudaStreamSynchronize(m->stream);
   peer_close(m);
   for (void *p : m->allocs) cudaFree(p);
+  if (m->h_peer_err) cudaFreeHost(m->h_peer_err);
   if (m->nccl) { try { nccl_destroy(m); } catch (...) {} }
   if (m->copy_stream) { cudaStreamSynchronize(m->copy_stream); cudaStreamDestroy(m->copy_stream); cudaEventDestroy(m->ev_copy); cudaEventDestroy(m->ev_step); }
   if (!m->shared_stream) cudaStreamDestroy(m->stream);
@@ -383,16 +387,13 @@ int qgcm_set_scalars(qgcm_model *m, const qgcm_scalars *s) {
 }
 int qgcm_get_scalars(qgcm_model *m, qgcm_scalars *s) {
   QG_TRY(QG_CUDA(cudaMemcpyAsync(s, m->d_scal, sizeof(*s), cudaMemcpyDeviceToHost, m->stream));
-         QG_CUDA(cudaStreamSynchronize(m->stream)));
+         QG_CUDA(cudaStreamSynchronize(m->stream));
+         check_peer_err(m));
 }
 int qgcm_sync(qgcm_model *m) {
   QG_TRY({
     QG_CUDA(cudaStreamSynchronize(m->stream));
-    if (m->d_peer_err && m->peer.n) {      // a peer-memory exchange gave up waiting for another rank
-      int e = 0;
-      QG_CUDA(cudaMemcpy(&e, m->d_peer_err, sizeof(int), cudaMemcpyDeviceToHost));
-      if (e) throw std::runtime_error("y-slab exchange timed out waiting for a peer rank");
-    }
+    check_peer_err(m);      // a peer-memory exchange gave up waiting for another rank
   });
 }
 
@@ -473,7 +474,8 @@ int qgcm_run(qgcm_model *m, int64_t nt_first, int64_t nt_last) {
         if (m->has_atmos) launch_xforc(m);
         if (m->has_ocean) {
           ocean_step(m);
-          if (m->flags & QGCM_OCNC_AVG_K247) launch_avg_ocn_k247(m);   // src/q-gcm.F:1250-1252
+          if (m->flags & QGCM_OCNC_AVG_K247)      // src/q-gcm.F:1250-1252; every rank of a loopback group
+            for (qgcm_model *r : ranks_of(m)) launch_avg_ocn_k247(r);
         }
       }
       if (m->has_atmos) atmos_step(m);
@@ -499,6 +501,7 @@ int qgcm_group_create(qgcm_model **models, int32_t n) { QG_TRY(group_create(mode
 int qgcm_peer_handle(qgcm_model *m, void *handle64) { QG_TRY(peer_export(m, handle64)); }
 int qgcm_comm_init_peer(qgcm_model *m, const void *handles, int32_t n) { QG_TRY(peer_init(m, handles, n)); }
 int qgcm_comm_transport(qgcm_model *m, int32_t kind) { QG_TRY(set_transport(m, kind)); }
+int qgcm_comm_peer_timeout(qgcm_model *m, double seconds) { QG_TRY(peer_set_timeout(m, seconds)); }
 int qgcm_comm_close_peer(qgcm_model *m) {
   QG_TRY({
     QG_CUDA(cudaStreamSynchronize(m->stream));

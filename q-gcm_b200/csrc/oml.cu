@@ -502,7 +502,7 @@ static OmlArgs oml_args(qgcm_model *m, dim3 &grid) {
   {
     // marches sized to whole waves of resident blocks, at least 16 rows each (4 fill rows per march)
     const int xw = (g.nxt + MW - 1) / MW;
-    static int resident = 0;
+    int &resident = m->oml_resident;
     if (!resident) {
       const size_t smem = 4 * MD * MNF * 32 * sizeof(double2);
       QG_CUDA(cudaFuncSetAttribute(k_oml_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -537,12 +537,7 @@ void oml_phase_a(qgcm_model *m) {
   OmlArgs a = oml_args(m, grid);
   const Grid &g = m->go;
   {
-    const size_t smem = 4 * MD * MNF * 32 * sizeof(double2);
-    static bool attr = false;
-    if (!attr) {
-      QG_CUDA(cudaFuncSetAttribute(k_oml_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
-    }
+    const size_t smem = 4 * MD * MNF * 32 * sizeof(double2);   // attribute set per model in oml_args
     QG_LAUNCH(m, "k_oml_step", grid, 128, smem, k_oml_march, a);
   }
   a.peer = peer_next_vec(m);    // y-slabs over peer memory: the reduction all-reduces its sums itself

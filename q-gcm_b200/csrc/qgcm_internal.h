@@ -243,17 +243,21 @@ struct qgcm_model {
   bool use_peer = false;                 // qgcm_comm_init_peer / qgcm_comm_transport: exchanges go through the mailboxes
   unsigned long long epoch_vec = 0, epoch_fg = 0, epoch_halo = 0;
   unsigned int *d_ticket2 = nullptr;     // [0] slab-row push, [1] halo push
-  int *d_peer_err = nullptr;
-  unsigned int peer_checks = 0;
+  int *d_peer_err = nullptr;             // device error block of the peer transport (layout at peer_wait)
+  int *h_peer_err = nullptr;             // host-mapped copy of its flag: read on every call, no stream sync needed
   // qgcm_set_field_async: copy stream, shadow buffers, names waiting for qgcm_commit_fields
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy = nullptr, ev_step = nullptr;
   std::map<std::string, double *> shadow;
-  std::vector<std::string> pending;
+  std::vector<std::string> pending;      // each name at most once: one buffer swap per commit
   bool ddynoc_flat = true, ddynat_flat = true;   // the topography field is identically zero (its device buffer starts zeroed)
   double *wrk_o = nullptr, *wrk_a = nullptr;   // modal work arrays [nl][nyp][ld]
   double *xfo = nullptr, *xfa = nullptr, *sstnew = nullptr, *astnew = nullptr, *hmnew = nullptr;
   std::vector<void *> allocs;
+  // per model (= per device): resident-block counts of the marching kernels; the dynamic
+  // shared-memory attribute is (re)set with them, so two models on two devices in one
+  // process each configure their own device
+  int qg_resident = 0, oml_resident = 0;
   // per-kernel event timing (qgcm_profile)
   bool prof = false;
   struct ProfRec { const char *name; cudaEvent_t e0, e1; };
@@ -266,16 +270,29 @@ struct qgcm_model {
 
 #ifdef __CUDACC__
 namespace qg {
-// spin until *flag >= epoch.  A lost peer must not hang the device: the wait gives up after
-// ~10 s of GPU clock and raises *err, and once *err is set every later wait returns at once
-// (the step then finishes with whatever the mailbox holds and the host call reports the error)
+// Error block of the peer transport, 8 ints in device memory (qgcm_model::d_peer_err):
+//   [0]    sticky error flag, read by every later wait
+//   [2,3]  64-bit address of a host-mapped copy of the flag (the host reads it on every call
+//          without synchronising the stream), 0 when absent
+//   [4,5]  64-bit give-up time of a wait in GPU clocks (qgcm_comm_peer_timeout, default 120 s)
+// spin until *flag >= epoch.  A lost peer must not hang the device for ever: the wait gives up
+// after the configured time and raises the flag (device copy and host-mapped copy); once it is
+// set every later wait returns at once, the step finishes with whatever the mailbox holds, and
+// the next library call of any kind on that model reports the error (slab.cu, check_peer_err).
 __device__ __forceinline__ void peer_wait(const volatile unsigned long long *flag, unsigned long long epoch, int *err) {
   const long long t0 = clock64();
   unsigned int spins = 0;
   while (*flag < epoch) {
     if ((++spins & 1023u) == 0) {
       if (*reinterpret_cast<volatile int *>(err)) break;
-      if (clock64() - t0 > 20000000000LL) { *reinterpret_cast<volatile int *>(err) = 1; break; }
+      const long long limit = *reinterpret_cast<volatile long long *>(err + 4);
+      if (clock64() - t0 > limit) {
+        *reinterpret_cast<volatile int *>(err) = 1;
+        int *host = *reinterpret_cast<int *volatile *>(err + 2);
+        if (host) *reinterpret_cast<volatile int *>(host) = 1;
+        __threadfence_system();
+        break;
+      }
     }
   }
 }
@@ -381,6 +398,8 @@ void peer_init(qgcm_model *m, const void *handles, int n);
 void peer_close(qgcm_model *m);
 void set_transport(qgcm_model *m, int kind);
 bool peer_active(const qgcm_model *m);    // this model's exchanges go through the peer mailboxes
+void check_peer_err(qgcm_model *m);       // throws once a peer exchange has timed out (host-side flag, no sync)
+void peer_set_timeout(qgcm_model *m, double seconds);
 PeerCtx peer_next_vec(qgcm_model *m);     // context of the next all-reduce (advances the epoch); n == 0 when not active
 Ranks ranks_of(qgcm_model *m);
 void slab_ocean_step(const Ranks &ms);

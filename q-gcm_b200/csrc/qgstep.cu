@@ -372,7 +372,7 @@ static void launch(qgcm_model *m, bool atmos) {
     // marches sized to whole waves of resident blocks, at least 24 rows each (6 fill rows per march)
     const int nwx = (g.nxp + W2OUT - 1) / W2OUT;
     const size_t smem = 4 * Q2_D * QG_NF * 32 * sizeof(double2);
-    static int resident = 0;
+    int &resident = m->qg_resident;
     if (!resident) {
       QG_CUDA(cudaFuncSetAttribute(k_qgstep2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 0, sms = 0;

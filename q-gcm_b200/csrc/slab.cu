@@ -108,10 +108,17 @@ void peer_export(qgcm_model *m, void *handle64) {
     const size_t n = peer_box_doubles(m->nranks, fglen, peer_halolen(m));
     m->mailbox = (double *)dalloc(m, sizeof(double) * n);
     m->d_ticket2 = (unsigned int *)dalloc(m, sizeof(unsigned int) * 4);
-    m->d_peer_err = (int *)dalloc(m, sizeof(int) * 4);
+    m->d_peer_err = (int *)dalloc(m, sizeof(int) * 8);
     QG_CUDA(cudaMemset(m->mailbox, 0, sizeof(double) * n));
     QG_CUDA(cudaMemset(m->d_ticket2, 0, sizeof(unsigned int) * 4));
-    QG_CUDA(cudaMemset(m->d_peer_err, 0, sizeof(int) * 4));
+    QG_CUDA(cudaHostAlloc((void **)&m->h_peer_err, sizeof(int) * 4, cudaHostAllocMapped));
+    m->h_peer_err[0] = 0;
+    int *dev_view = nullptr;
+    QG_CUDA(cudaHostGetDevicePointer((void **)&dev_view, m->h_peer_err, 0));
+    long long blk[4] = {0, (long long)(uintptr_t)dev_view, 0, 0};
+    QG_CUDA(cudaMemcpy(m->d_peer_err, blk, sizeof(blk), cudaMemcpyHostToDevice));
+    const char *ts = std::getenv("QGCM_PEER_TIMEOUT_S");
+    peer_set_timeout(m, (ts && *ts) ? std::atof(ts) : 120.0);
     QG_CUDA(cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t h;
@@ -277,11 +284,26 @@ __global__ void __launch_bounds__(256) k_halo_peer(HaloArgs a) {
   halo_copy(reinterpret_cast<double2 *>(a.base[fl] + (size_t)row * a.ld), src, i0, i1, true);
 }
 
-static void check_peer_err(qgcm_model *m) {
-  int e = 0;
-  QG_CUDA(cudaMemcpyAsync(&e, m->d_peer_err, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-  QG_CUDA(cudaStreamSynchronize(m->stream));
-  if (e) throw std::runtime_error("y-slab exchange timed out waiting for a peer rank");
+// The device raises the flag in host-mapped memory as well, so this is a plain host load: it is
+// made on every step and on every call that hands state back to the host (qgcm_get_field,
+// qgcm_get_scalars, qgcm_sync ...), after their stream synchronisation where they have one.
+void check_peer_err(qgcm_model *m) {
+  if (!m->h_peer_err) return;
+  if (*reinterpret_cast<volatile int *>(m->h_peer_err))
+    throw std::runtime_error("y-slab exchange timed out waiting for a peer rank (qgcm_comm_peer_timeout); the slab state is "
+                             "no longer valid: destroy the models of this partition and restart from the last restart file");
+}
+
+// give-up time of a mailbox wait.  Ranks must enter each ocean step within this time of each
+// other; a host that stalls one rank for longer (restart or netCDF output on one rank) should
+// put a host barrier in front of the next step or raise the limit.
+void peer_set_timeout(qgcm_model *m, double seconds) {
+  if (!m->d_peer_err) throw std::runtime_error("qgcm_comm_peer_timeout: call qgcm_peer_handle first");
+  if (!(seconds > 0.0)) throw std::runtime_error("qgcm_comm_peer_timeout: the time must be positive");
+  int khz = 1965000;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, m->cfg.device);
+  const long long clocks = (long long)std::min(seconds * 1e3 * (double)khz, 9.0e18);
+  QG_CUDA(cudaMemcpy(reinterpret_cast<long long *>(m->d_peer_err) + 2, &clocks, sizeof(clocks), cudaMemcpyHostToDevice));
 }
 
 Ranks ranks_of(qgcm_model *m) {
@@ -456,7 +478,7 @@ void slab_ocean_step(const Ranks &ms) {
     launch_ocqbdy(m, m->F("qo"), m->F("po"));
   }
   comm_halo(ms, {"po", "qo", "sst"});
-  if (peer && (++ms[0]->peer_checks & 63) == 0) check_peer_err(ms[0]);
+  if (peer) check_peer_err(ms[0]);      // host-mapped flag: no synchronisation, checked every step
 }
 
 void slab_constr(const Ranks &ms) {

@@ -246,6 +246,10 @@ class Model(CModel):
         """unmap the other ranks' mailboxes; barrier between this and close() (CUDA IPC rule)"""
         self._call("comm_close_peer")
 
+    def comm_peer_timeout(self, seconds: float):
+        """give-up time of a mailbox wait (default 120 s)"""
+        self._call("comm_peer_timeout", C.c_double(seconds))
+
     def comm_transport(self, kind: str):
         self._call("comm_transport", C.c_int32({"nccl": 0, "peer": 1}[kind]))
 

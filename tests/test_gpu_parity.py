@@ -229,6 +229,31 @@ def test_async_forcing_upload(qg, pyorc):
         gpu._call("set_field_async", b"po", C.cast(pinned["tauxo"].data_ptr(), C.POINTER(C.c_double)), C.c_int64(1))
 
 
+def test_async_upload_twice_before_one_commit(qg, pyorc):
+    """the same field uploaded twice before one commit is switched over exactly once and holds the
+    second upload (a double swap would leave the model stepping on the stale buffer)"""
+    import ctypes as C
+    import torch
+    p = small_configs(qg)["box_dg"]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    old = cpu.get_field("fnetoc")
+    first = torch.from_numpy((2.0 * old).copy()).pin_memory()
+    second = torch.from_numpy((3.0 * old).copy()).pin_memory()
+    for t in (first, second):
+        gpu._call("set_field_async", b"fnetoc", C.cast(t.data_ptr(), C.POINTER(C.c_double)), C.c_int64(t.numel()))
+    gpu._call("commit_fields")
+    gpu.sync()
+    assert np.array_equal(gpu.get_field("fnetoc"), 3.0 * old)
+    gpu.ocean_step()
+    cpu.set_field("fnetoc", 3.0 * old)
+    cpu.ocean_step()
+    compare(gpu, cpu, OCEAN_CHECK + ("fnetoc",), label="double upload")
+    # and once more: the buffers have changed roles, a single upload must still land
+    gpu._call("set_field_async", b"fnetoc", C.cast(first.data_ptr(), C.POINTER(C.c_double)), C.c_int64(first.numel()))
+    gpu._call("commit_fields")
+    assert np.array_equal(gpu.get_field("fnetoc"), 2.0 * old)
+
+
 @pytest.mark.parametrize("nxto,cyc", [(96, 0), (120, 0), (160, 0), (180, 0), (200, 0), (216, 0), (240, 1),
                                       (288, 1), (400, 1), (324, 0), (480, 1), (960, 0), (1440, 0), (1920, 0),
                                       (2400, 0), (2880, 0), (3840, 0), (4800, 0)])

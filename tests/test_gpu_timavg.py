@@ -94,6 +94,29 @@ def test_sums_over_slabs(qg, pyorc, nranks):
         assert np.array_equal(got, pyorc.subsample(grp.get_field(name, shape), nsk)), (nranks, name)
 
 
+def test_run_accumulates_po_avg_on_every_slab(qg, pyorc):
+    """qgcm_run with -Docnc_avg_k247 on a loopback partition: every rank adds its rows to po_avg
+    (src/q-gcm.F:1250-1252), not only the rank the call was made on"""
+    p = small_configs(qg)["box_dg"]
+    p.flags = list(p.flags) + ["ocnc_avg_k247"]
+    cfg = qg.build_config(p)
+    grp = qg.SlabGroup(cfg, 3)
+    cpu = pyorc.Oracle(cfg)
+    for m in (grp, cpu):
+        qg.synth.init_model(m, p, cfg, "random")
+    grp.run(1, 2 * p.nstr)
+    for nt in range(1, 2 * p.nstr + 1):
+        if nt % p.nstr == 1:
+            cpu.ocean_step()
+            cpu.avg_ocn_k247()
+        if (nt - 1) % (25 * p.nstr) == 0:
+            cpu.tlavg_ocean()
+    a, b = grp.get_field("po_avg"), cpu.get_field("po_avg")
+    assert np.isfinite(a).all()
+    assert rel_l2(a, b) <= TOL
+    assert float(np.abs(a.reshape((p.nxpo, p.nypo, p.nlo), order="F")[:, -5:, 0]).max()) > 0.0   # the last rank's rows too
+
+
 @pytest.mark.parametrize("nsk", [1, 2, 3, 7, 16])
 def test_subsampled_read(qg, pyorc, nsk):
     """bit-exact: the packed vector is a copy of every nsk-th point"""
