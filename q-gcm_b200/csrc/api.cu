@@ -352,6 +352,18 @@ int qgcm_destroy(qgcm_model *m) {
   if (!m) return 0;
   cudaSetDevice(m->cfg.device);
   cudaStreamSynchronize(m->stream);
+  // a member of an in-process loopback group leaves: the group is dissolved, and the ranks that
+  // borrowed this model's stream get one of their own (they may be destroyed in any order)
+  for (qgcm_model *p : m->peers) {
+    if (p == m) continue;
+    p->peers.clear();
+    if (p->shared_stream && p->stream == m->stream && !m->shared_stream) {
+      p->stream = nullptr;
+      cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+      p->shared_stream = false;
+    }
+  }
+  m->peers.clear();
   peer_close(m);
   for (void *p : m->allocs) cudaFree(p);
   if (m->h_peer_err) cudaFreeHost(m->h_peer_err);

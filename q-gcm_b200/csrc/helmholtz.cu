@@ -458,12 +458,29 @@ __host__ __device__ constexpr int dst3_seg(int M) {
   return best;
 }
 
+// k_dst3 variants.  The DST is linear, so the layer<->mode projections of ocinvq commute with
+// it: the fused forward transform works on the vorticity LAYERS (the projection is applied by
+// the tridiagonal kernels, which hold all modes of a wavenumber anyway), and the fused inverse
+// transform produces pressure LAYERS.  That removes the two pointwise kernels (k_l2m, k_m2l)
+// and the 12 field passes they existed for.
+enum { DST_PLAIN_F = 0, DST_PLAIN_I = 1, DST_FUSED_F = 2, DST_FUSED_I = 3 };
 struct Dst3Args {
   int nitems, nrows;        // (mode,row) work items; solved rows per mode
   int ld, nyp, nxp, row0;
   size_t lsz;
   double *wrk;
   double *rowsum;
+  // fused variants (items are row-major: the nl layers of a row are adjacent in time, so the
+  // rows every layer re-reads -- ochom -- come from L2)
+  int nl, kbot;
+  const double *src;        // DST_FUSED_F: q [nl][nyp][ld] (src/ocisubs.F:117-139 without the projection)
+  double *dst;              // DST_FUSED_I: new p [nl][nyp][ld] (src/ocisubs.F:377-401)
+  const double *yrel;       // DST_FUSED_F: beta*y is subtracted from the row
+  double beta;
+  const double *ddyn;       // DST_FUSED_F: topography term of the bottom layer, null over a flat bottom
+  const double *hom;        // DST_FUSED_I: ochom [nl-1][nyp][ld]
+  const double *coef;       // DST_FUSED_I: device hclco[nl-1]
+  double ctm2l[NLMAX * NLMAX];
   const double2 *s1base;    // [L1][2]  (2 sin, 2 cos) of pi*(2t)/N and pi*(2t+1)/N
   const double2 *tw2;       // [R2-1][R1] twiddles of pass 2
   const double2 *tw3base;   // [L3][2]  w, w^2 of pass 3
@@ -472,8 +489,10 @@ struct Dst3Args {
   double2 wnr[16];          // exp(-2 pi i q L3/N)
 };
 
-template <int R3, bool INV>
+template <int R3, int MODE>
 __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
+  constexpr bool INV = (MODE == DST_PLAIN_I);       // xintp row sums of the result, wall column zeroed
+  constexpr bool FUSED = (MODE == DST_FUSED_F || MODE == DST_FUSED_I);
   constexpr int R1 = 16, R2 = 15;
   constexpr int M = R1 * R2 * R3, N = 2 * M;
   constexpr int L1 = M / R1, L2 = M / R2, L3 = M / R3;
@@ -499,9 +518,10 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (item < a.nitems) {
-      const int mode = item / a.nrows, r = item - mode * a.nrows;
+      const int mode = FUSED ? item % a.nl : item / a.nrows, r = FUSED ? item / a.nl : item - mode * a.nrows;
+      const double *in = (MODE == DST_FUSED_F) ? a.src : a.wrk;
       mbar_expect_tx(bar, N * 8);
-      bulk_g2s(in_s, a.wrk + (size_t)mode * a.lsz + (size_t)(r + a.row0) * a.ld, N * 8, bar);
+      bulk_g2s(in_s, in + (size_t)mode * a.lsz + (size_t)(r + a.row0) * a.ld, N * 8, bar);
     }
   }
   __syncthreads();
@@ -512,8 +532,8 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
     int t = t0;
     asm volatile("" : "+r"(t));
     const int lane = t & 31, wp = t >> 5;
-    const int mode = item / a.nrows, r = item - mode * a.nrows;
-    double *__restrict__ row = a.wrk + (size_t)mode * a.lsz + (size_t)(r + a.row0) * a.ld;
+    const int mode = FUSED ? item % a.nl : item / a.nrows, r = FUSED ? item / a.nl : item - mode * a.nrows;
+    double *__restrict__ row = ((MODE == DST_FUSED_I) ? a.dst : a.wrk) + (size_t)mode * a.lsz + (size_t)(r + a.row0) * a.ld;
     // ---- pass 1 (radix 16, no twiddles) fused with the DST pre-processing (dsint.f:17-30):
     //      t_e = (x_e - x_{N-e}) + 2 sin(e pi/N) (x_e + x_{N-e}),  z_n = t_{2n} + i t_{2n+1}.
     //      Output position i = 16 t + q is stored at i + (i >> 4) = 17 t + q: conflict-free
@@ -522,12 +542,23 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       double2 v1[R1];
       mbar_wait(bar, parity);
       const double2 b0 = ldg2_nohoist(a.s1base + 2 * t), b1 = ldg2_nohoist(a.s1base + 2 * t + 1);
+      // fused forward transform: the row is q_k(:,j); the right-hand side of the layer is
+      // q_k - beta*y_j (- ddynoc in the bottom layer), src/ocisubs.F:121-138
+      double by = 0.0;
+      if (MODE == DST_FUSED_F) by = a.beta * a.yrel[r + a.row0];
+      const double *dd = nullptr;
+      if (MODE == DST_FUSED_F && a.ddyn && mode == a.kbot) dd = a.ddyn + (size_t)(r + a.row0) * a.ld;
 #pragma unroll
       for (int q = 0; q < R1; ++q) {
         const int n = t + q * L1;
-        const double2 xo = IN2[n];
-        const double xb0 = IN[(q == 0) ? ((t == 0) ? 0 : N - 2 * t) : N - 2 * n];
-        const double xb1 = IN[N - 2 * n - 1];
+        double2 xo = IN2[n];
+        const int ib0 = (q == 0) ? ((t == 0) ? 0 : N - 2 * t) : N - 2 * n;
+        double xb0 = IN[ib0];
+        double xb1 = IN[N - 2 * n - 1];
+        if (MODE == DST_FUSED_F) {
+          xo.x -= by; xo.y -= by; xb0 -= by; xb1 -= by;
+          if (dd) { xo.x -= dd[2 * n]; xo.y -= dd[2 * n + 1]; xb0 -= dd[ib0]; xb1 -= dd[N - 2 * n - 1]; }
+        }
         const double s0 = (q == 0) ? b0.x : fma(b0.x, a.c1[q], b0.y * a.s1[q]);
         const double s1 = (q == 0) ? b1.x : fma(b1.x, a.c1[q], b1.y * a.s1[q]);
         v1[q].x = fma(s0, xo.x + xb0, xo.x - xb0);
@@ -589,9 +620,10 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
     if (t == 0) {      // pass 3 has read the ping-pong buffer: the next raw row may land in it
       const int nxt = item + gridDim.x;
       if (nxt < a.nitems) {
-        const int m2 = nxt / a.nrows, r2 = nxt - m2 * a.nrows;
+        const int m2 = FUSED ? nxt % a.nl : nxt / a.nrows, r2 = FUSED ? nxt / a.nl : nxt - m2 * a.nrows;
+        const double *in = (MODE == DST_FUSED_F) ? a.src : a.wrk;
         mbar_expect_tx(bar, N * 8);
-        bulk_g2s(in_s, a.wrk + (size_t)m2 * a.lsz + (size_t)(r2 + a.row0) * a.ld, N * 8, bar);
+        bulk_g2s(in_s, in + (size_t)m2 * a.lsz + (size_t)(r2 + a.row0) * a.ld, N * 8, bar);
       }
     }
     // ---- real post-processing: even outputs -Im F_k stay in registers, Re F_k is the
@@ -659,7 +691,36 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
     __syncthreads();
     // ---- interleave and store: row[2k] = even_k, row[2k+1] = odd_k ----
     double part = 0.0;
-    if (t < L3) {
+    if (MODE == DST_FUSED_I) {
+      // fused inverse transform: the row is sum_m ctm2l(m,k) wrk_m(:,j) already (the tridiagonal
+      // kernel projected in spectral space); add the homogeneous solutions of the baroclinic
+      // modes, sum_m ctm2l(m,k) hclco(m-1) ochom(:,j,m-1), and store p_k (src/ocisubs.F:377-401)
+      if (t < L3) {
+        double2 *__restrict__ out = reinterpret_cast<double2 *>(row);
+        const double2 *hrow = reinterpret_cast<const double2 *>(a.hom + (size_t)(r + a.row0) * a.ld);
+        double2 acc[R3];
+#pragma unroll
+        for (int q = 0; q < R3; ++q) acc[q] = make_double2(ev[q], SC[t + q * L3]);
+        for (int mm = 1; mm < a.nl; ++mm) {
+          const double hc = a.coef[mm - 1], cm = a.ctm2l[mm + a.nl * mode];
+          const double2 *h2 = hrow + (size_t)(mm - 1) * (a.lsz / 2);
+#pragma unroll
+          for (int q = 0; q < R3; ++q) {
+            const double2 h = __ldg(h2 + t + q * L3);
+            acc[q].x = fma(cm, hc * h.x, acc[q].x);
+            acc[q].y = fma(cm, hc * h.y, acc[q].y);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < R3; ++q) out[t + q * L3] = acc[q];
+      }
+      if (t == 255) {      // the eastern wall column (the transform covers columns 0 .. nxp-2)
+        double e = 0.0;
+        for (int mm = 1; mm < a.nl; ++mm)
+          e = fma(a.ctm2l[mm + a.nl * mode], a.coef[mm - 1] * a.hom[(size_t)(mm - 1) * a.lsz + (size_t)(r + a.row0) * a.ld + a.nxp - 1], e);
+        row[a.nxp - 1] = e;
+      }
+    } else if (t < L3) {
       double2 *__restrict__ out = reinterpret_cast<double2 *>(row);
 #pragma unroll
       for (int q = 0; q < R3; ++q) {
@@ -798,6 +859,186 @@ __global__ void __launch_bounds__(128, 3) k_tri_local(TriArgs t) {
     for (int j = 0; j < TRI_L; ++j) gl = fma((j == len - 1) ? 1.0 : 0.0, u[j], gl);   // arithmetic select keeps u in registers
     t.fg[fb + (size_t)(t.nchunk + c) * ld] = gl;
   }
+}
+
+// Fused variant of k_tri_local for the box ocean (NL layers = NL modes per wavenumber in one
+// thread).  The work array holds spectral LAYER rows (the forward transform of q_k - beta*y): the
+// thread projects them onto the modes, r_m = f0 sum_k ctl2m(k,m) s_k (src/ocisubs.F:117-139 in
+// spectral space), solves the NL chunk systems in registers and
+//   FINAL = false : keeps the first/last values of each mode (the interface system's rhs);
+//   FINAL = true  : projects the solution back onto the layers, l_k = sum_m ctm2l(m,k) u_m
+//                   (src/ocisubs.F:377-401 without the homogeneous part, which the inverse
+//                   transform adds in physical space), stores it, and leaves the block's share of
+//                   the area integrals xinhom(m) of the modal solutions: the x-sum of a sine
+//                   series is sum_k 2 cot(k pi / 2N) X_k over odd k, so the integral the
+//                   constraint algebra needs (src/ocisubs.F:146-162) is known before the
+//                   inverse transform runs.
+// grid (ceil(nk/128), nchunk).
+struct Mix3 {
+  double f0;
+  double ctl2m[NLMAX * NLMAX], ctm2l[NLMAX * NLMAX];
+  const double *wsum;     // [ld] 2 cot(k pi / 2N) at odd wavenumber columns, 0 elsewhere
+  double *spec;           // [nl][nchunk * gridDim.x] partial integrals (FINAL)
+};
+
+// first/last values of the chunk-local solutions, streaming: one sweep over the chunk's rows
+// with the layer values of a row in flight only.  The last value of a Thomas solve is what the
+// forward elimination ends with; the first value is the dot product of the right-hand side with
+// the first row of the inverse, which by symmetry is the left spike of the chunk over -a.
+template <int NL>
+__global__ void __launch_bounds__(128, 4) k_tri3_fg(TriArgs t, Mix3 mx) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (s >= t.nk) return;
+  const int col = t.koff + s;
+  const bool lastc = (c == t.nchunk - 1);
+  const int len = lastc ? t.lastlen : TRI_L;
+  const double a = t.a;
+  const int ld = t.ld;
+  const double *__restrict__ base = t.wrk + (size_t)(t.row0 + c * TRI_L) * ld + col;
+  const double *__restrict__ bi = t.binv + col;
+  const double *__restrict__ sp = (lastc ? t.vll : t.vl) + col;
+  double d[NL], f[NL];
+#pragma unroll
+  for (int m = 0; m < NL; ++m) d[m] = f[m] = 0.0;
+#pragma unroll 8
+  for (int j = 0; j < len; ++j) {
+    double sk[NL];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) sk[k] = base[(size_t)k * t.lsz + (size_t)j * ld];
+#pragma unroll
+    for (int m = 0; m < NL; ++m) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < NL; ++k) acc = acc + mx.ctl2m[k + NL * m] * sk[k];
+      const double r = mx.f0 * acc;
+      const size_t tb = ((size_t)m * TRI_L + j) * ld;
+      d[m] = (r - a * d[m]) * __ldg(bi + tb);
+      f[m] = fma(__ldg(sp + tb), r, f[m]);
+    }
+  }
+  const double ra = -1.0 / a;
+#pragma unroll
+  for (int m = 0; m < NL; ++m) {
+    const size_t fb = ((size_t)m * 2 * t.nchunk) * ld + col;
+    t.fg[fb + (size_t)c * ld] = f[m] * ra;
+    t.fg[fb + (size_t)(t.nchunk + c) * ld] = d[m];
+  }
+}
+
+// final chunk solves of all modes of a wavenumber in one thread: modes 0 .. NL-2 in registers,
+// the last mode in shared memory ([row][thread], conflict free), so that the kernel stays clear
+// of register spills at two blocks per SM
+template <int NL>
+__global__ void __launch_bounds__(128, 2) k_tri3_fin(TriArgs t, Mix3 mx) {
+  __shared__ double us[TRI_L][128];
+  __shared__ double red[NL][4];
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  const bool live = s < t.nk;
+  const int col = t.koff + (live ? s : 0);
+  const int len = (c == t.nchunk - 1) ? t.lastlen : TRI_L;
+  const double a = t.a;
+  const int ld = t.ld, tx = threadIdx.x;
+  double *__restrict__ base = t.wrk + (size_t)(t.row0 + c * TRI_L) * ld + col;
+  double u[NL - 1][TRI_L];
+  // layers -> modes (rows >= len: harmless duplicates of the last row)
+#pragma unroll
+  for (int j = 0; j < TRI_L; ++j) {
+    double sk[NL];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) sk[k] = base[(size_t)k * t.lsz + (size_t)min(j, len - 1) * ld];
+#pragma unroll
+    for (int m = 0; m < NL; ++m) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < NL; ++k) acc = acc + mx.ctl2m[k + NL * m] * sk[k];
+      if (m < NL - 1) u[m][j] = mx.f0 * acc; else us[j][tx] = mx.f0 * acc;
+    }
+    // loads are kept within groups of eight rows (24 in flight per thread): hoisting all 96 above
+    // the projection costs more registers than the kernel has
+    if ((j & 7) == 7) asm volatile("" ::: "memory");
+  }
+  double sm[NL];
+#pragma unroll
+  for (int m = 0; m < NL - 1; ++m) {
+    const double *__restrict__ bi = t.binv + ((size_t)m * TRI_L) * ld + col;
+    const size_t fb = ((size_t)m * 2 * t.nchunk) * ld + col;
+    if (t.use_yx) {
+      const double yp = t.yx[fb + (size_t)c * ld], xn = t.yx[fb + (size_t)(t.nchunk + c) * ld];
+      u[m][0] -= a * yp;
+#pragma unroll
+      for (int j = 0; j < TRI_L; ++j) u[m][j] = fma(-a, (j == len - 1) ? xn : 0.0, u[m][j]);
+    }
+    u[m][0] = u[m][0] * __ldg(bi);
+#pragma unroll
+    for (int j = 1; j < TRI_L; ++j) u[m][j] = (u[m][j] - a * u[m][j - 1]) * __ldg(bi + (size_t)j * ld);
+#pragma unroll
+    for (int j = TRI_L - 2; j >= 0; --j) {
+      const double v = u[m][j] - (a * __ldg(bi + (size_t)j * ld)) * u[m][j + 1];
+      u[m][j] = (j < len - 1) ? v : u[m][j];
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < TRI_L; ++j) acc += (j < len) ? u[m][j] : 0.0;
+    sm[m] = acc;
+  }
+  {
+    constexpr int m = NL - 1;
+    const double *__restrict__ bi = t.binv + ((size_t)m * TRI_L) * ld + col;
+    const size_t fb = ((size_t)m * 2 * t.nchunk) * ld + col;
+    if (t.use_yx) {
+      const double yp = t.yx[fb + (size_t)c * ld], xn = t.yx[fb + (size_t)(t.nchunk + c) * ld];
+      us[0][tx] -= a * yp;
+      us[len - 1][tx] = fma(-a, xn, us[len - 1][tx]);
+    }
+    double prev = us[0][tx] * __ldg(bi);
+    us[0][tx] = prev;
+#pragma unroll 8
+    for (int j = 1; j < len; ++j) {
+      prev = (us[j][tx] - a * prev) * __ldg(bi + (size_t)j * ld);
+      us[j][tx] = prev;
+    }
+    double acc = prev;
+#pragma unroll 8
+    for (int j = len - 2; j >= 0; --j) {
+      prev = us[j][tx] - (a * __ldg(bi + (size_t)j * ld)) * prev;
+      us[j][tx] = prev;
+      acc += prev;
+    }
+    sm[m] = acc;
+  }
+  const double fn = t.ftnorm;
+  // modes -> layers, times ftnorm (src/ocisubs.F:484-487)
+#pragma unroll
+  for (int j = 0; j < TRI_L; ++j) {
+    if (j < len) {
+      double um[NL];
+#pragma unroll
+      for (int m = 0; m < NL - 1; ++m) um[m] = fn * u[m][j];
+      um[NL - 1] = fn * us[j][tx];
+#pragma unroll
+      for (int k = 0; k < NL; ++k) {
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < NL; ++m) acc = acc + mx.ctm2l[m + NL * k] * um[m];
+        if (live) base[(size_t)k * t.lsz + (size_t)j * ld] = acc;
+      }
+    }
+    if ((j & 7) == 7) asm volatile("" ::: "memory");
+  }
+  // the block's share of the modal area integrals: fixed-order reduction
+  const double w = live ? fn * __ldg(mx.wsum + col) : 0.0;
+#pragma unroll
+  for (int m = 0; m < NL; ++m) {
+    double v = w * sm[m];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((tx & 31) == 0) red[m][tx >> 5] = v;
+  }
+  __syncthreads();
+  if (tx < NL)
+    mx.spec[(size_t)tx * (t.nchunk * gridDim.x) + (size_t)c * gridDim.x + blockIdx.x] = (red[tx][0] + red[tx][1]) + (red[tx][2] + red[tx][3]);
 }
 
 struct SlabArgs {
@@ -1070,21 +1311,27 @@ __global__ void k_zero_rows(double *wrk, size_t lsz, int ld, int nyp, int nxp, i
 // --------------------------------------------------------------------------------------
 // ---- fast DST path: instantiated plans, tables, launch ----
 template <int R3>
-static void dst3_launch_t(qgcm_model *md, HelmPlan &hp, const Dst3Args &a, bool inverse) {
+static void dst3_launch_t(qgcm_model *md, HelmPlan &hp, const Dst3Args &a, int mode) {
   constexpr int M = 16 * 15 * R3;
   const size_t smem = (size_t)M * 16 + (size_t)(M + M / 16) * 16 + (size_t)M * 8 + 64 * 8 + 16;
-  auto kf = k_dst3<R3, false>;
-  auto ki = k_dst3<R3, true>;
+  auto kf = k_dst3<R3, DST_PLAIN_F>;
+  auto ki = k_dst3<R3, DST_PLAIN_I>;
+  auto kff = k_dst3<R3, DST_FUSED_F>;
+  auto kfi = k_dst3<R3, DST_FUSED_I>;
   if (!hp.fast_attr) {
     QG_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QG_CUDA(cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QG_CUDA(cudaFuncSetAttribute(kff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QG_CUDA(cudaFuncSetAttribute(kfi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hp.fast_attr = 1;
   }
-  const int grid = std::min(a.nitems, hp.fast_grid);
-  if (inverse)
-    QG_LAUNCH(md, "k_xform", grid, 256, smem, ki, a);
-  else
-    QG_LAUNCH(md, "k_xform", grid, 256, smem, kf, a);
+  const int grid = std::min(a.nitems, hp.fast_grid);      // persistent blocks, two per SM
+  switch (mode) {
+    case DST_PLAIN_F: QG_LAUNCH(md, "k_xform", grid, 256, smem, kf, a); break;
+    case DST_PLAIN_I: QG_LAUNCH(md, "k_xform", grid, 256, smem, ki, a); break;
+    case DST_FUSED_F: QG_LAUNCH(md, "k_xform", grid, 256, smem, kff, a); break;
+    default: QG_LAUNCH(md, "k_xform", grid, 256, smem, kfi, a); break;
+  }
 }
 
 // box decks whose half length is 240*R3 run the three-pass plan (16, 15, R3)
@@ -1094,20 +1341,25 @@ static int dst3_r3(const HelmPlan &hp) {
   return (r3 == 2 || r3 == 3 || r3 == 4 || r3 == 5 || r3 == 6 || r3 == 8 || r3 == 10) ? r3 : 0;
 }
 
-static void dst3_launch(qgcm_model *md, HelmPlan &hp, double *wrk, size_t lsz, int nmodes, bool inverse) {
-  Dst3Args a;
+static void dst3_launch(qgcm_model *md, HelmPlan &hp, double *wrk, size_t lsz, int nmodes, int mode, const FusedInv *fz = nullptr) {
+  Dst3Args a = {};
   a.nitems = nmodes * hp.nrows; a.nrows = hp.nrows; a.ld = hp.ld; a.nyp = hp.nyp; a.nxp = hp.nxp; a.row0 = hp.row0; a.lsz = lsz;
   a.wrk = wrk; a.rowsum = hp.rowsum;
   a.s1base = hp.s1base; a.tw2 = hp.tw2; a.tw3base = hp.tw3base; a.wnbase = hp.wnbase;
   for (int i = 0; i < 16; ++i) { a.c1[i] = hp.c1[i]; a.s1[i] = hp.s1c[i]; a.wnr[i] = hp.wnr[i]; }
+  a.nl = nmodes; a.kbot = nmodes - 1;
+  if (fz) {
+    a.src = fz->q; a.dst = fz->pnew; a.yrel = fz->yrel; a.beta = fz->beta; a.ddyn = fz->ddyn; a.hom = fz->hom; a.coef = fz->coef;
+    for (int i = 0; i < NLMAX * NLMAX; ++i) a.ctm2l[i] = fz->ctm2l[i];
+  }
   switch (hp.fast) {
-    case 2: dst3_launch_t<2>(md, hp, a, inverse); break;
-    case 3: dst3_launch_t<3>(md, hp, a, inverse); break;
-    case 4: dst3_launch_t<4>(md, hp, a, inverse); break;
-    case 5: dst3_launch_t<5>(md, hp, a, inverse); break;
-    case 6: dst3_launch_t<6>(md, hp, a, inverse); break;
-    case 8: dst3_launch_t<8>(md, hp, a, inverse); break;
-    case 10: dst3_launch_t<10>(md, hp, a, inverse); break;
+    case 2: dst3_launch_t<2>(md, hp, a, mode); break;
+    case 3: dst3_launch_t<3>(md, hp, a, mode); break;
+    case 4: dst3_launch_t<4>(md, hp, a, mode); break;
+    case 5: dst3_launch_t<5>(md, hp, a, mode); break;
+    case 6: dst3_launch_t<6>(md, hp, a, mode); break;
+    case 8: dst3_launch_t<8>(md, hp, a, mode); break;
+    case 10: dst3_launch_t<10>(md, hp, a, mode); break;
     default: throw std::runtime_error("helmholtz: no fast DST plan");
   }
 }
@@ -1251,6 +1503,17 @@ void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, con
   hp.fg = (double *)dalloc(md, sizeof(double) * nmodes * 2 * hp.nchunk * row);
   hp.yx = (double *)dalloc(md, sizeof(double) * nmodes * 2 * hp.nchunk * row);
   hp.rowsum = (double *)dalloc(md, sizeof(double) * nmodes * hp.nyp);
+  if (kind == 0) {
+    // x-sum of a sine series: sum_{i=1}^{n-1} sin(k i pi/n) = cot(k pi / 2n) for odd k, 0 for even
+    // k; times 2 for dsint's definition (fft.doc: x(i) = sum_k 2 X(k) sin(k i pi/(n+1)), its n+1 = our n)
+    std::vector<double> ws(row, 0.0);
+    const long double PI_Q = 3.141592653589793238462643383279502884L;
+    for (int k = 1; k < hp.n; k += 2) ws[k] = (double)(2.0L * cosl(PI_Q * k / (2.0L * hp.n)) / sinl(PI_Q * k / (2.0L * hp.n)));
+    hp.wsum = (double *)dalloc(md, sizeof(double) * row);
+    QG_CUDA(cudaMemcpy(hp.wsum, ws.data(), sizeof(double) * row, cudaMemcpyHostToDevice));
+    hp.nspec = hp.nchunk * ((hp.nk + 127) / 128);
+    hp.spec = (double *)dalloc(md, sizeof(double) * nmodes * hp.nspec);
+  }
   for (int r = 0; r < 16; ++r) hp.slab_rows[r] = 0;
   if (hp.nranks > 1) {
     if (hp.nranks > 8) throw std::runtime_error("helmholtz: at most 8 y-slabs");
@@ -1352,19 +1615,65 @@ static XfArgs xf_args(HelmPlan &hp, double *wrk, size_t lsz) {
 
 // first half: forward transform, chunk-local solves, chunk interface system; with slabs also
 // the first/last rows of the slab-local solution (hp.slab_send, to be all-gathered)
-void helm_solve_a(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
+static Mix3 mix3_args(const HelmPlan &hp, const FusedInv &fz) {
+  Mix3 mx;
+  mx.f0 = fz.f0;
+  for (int i = 0; i < NLMAX * NLMAX; ++i) { mx.ctl2m[i] = fz.ctl2m[i]; mx.ctm2l[i] = fz.ctm2l[i]; }
+  mx.wsum = hp.wsum; mx.spec = hp.spec;
+  return mx;
+}
+
+bool helm_can_fuse(const qgcm_model *m, const HelmPlan &hp, int nl) {
+  static const bool off = env_int("QGCM_NOFUSE", 0) != 0;      // A/B switch (scripts/ab_env.sh)
+  return !off && hp.kind == 0 && hp.fast && nl == 3 && hp.nmodes == 3 && hp.spec;
+}
+
+// wall rows of the new pressure: the inhomogeneous solution vanishes there, the homogeneous
+// solutions do not (src/ocisubs.F:377-401 on rows 1 and nypo)
+__global__ void k_hom_walls(double *pnew, const double *hom, const double *coef, Mix3 mx, int nl, size_t lsz, int ld, int nyp, int nxp,
+                            int south, int north) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nxp) return;
+  for (int side = 0; side < 2; ++side) {
+    if (!(side == 0 ? south : north)) continue;
+    const size_t idx = (size_t)(side == 0 ? 0 : nyp - 1) * ld + i;
+    for (int k = 0; k < nl; ++k) {
+      double e = 0.0;
+      for (int mm = 1; mm < nl; ++mm) e = fma(mx.ctm2l[mm + nl * k], coef[mm - 1] * hom[(size_t)(mm - 1) * lsz + idx], e);
+      pnew[(size_t)k * lsz + idx] = e;
+    }
+  }
+}
+
+// after the constraint algebra: spectral layer rows -> pressure layers (+ homogeneous solutions)
+void helm_fused_inverse(qgcm_model *md, HelmPlan &hp, double *wrk, int nl, const FusedInv &fz) {
+  const size_t lsz = (size_t)hp.ld * hp.nyp;
+  dst3_launch(md, hp, wrk, lsz, nl, DST_FUSED_I, &fz);
+  if (hp.wall_s || hp.wall_n)
+    QG_LAUNCH(md, "k_hom_walls", (hp.nxp + 255) / 256, 256, 0, k_hom_walls, fz.pnew, fz.hom, fz.coef, mix3_args(hp, fz), nl, lsz, hp.ld,
+              hp.nyp, hp.nxp, hp.wall_s, hp.wall_n);
+  QG_CUDA(cudaGetLastError());
+}
+
+void helm_solve_a(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes, const FusedInv *fz) {
   const size_t lsz = (size_t)hp.ld * hp.nyp;
   XfArgs x = xf_args(hp, wrk, lsz);
   dim3 gx(hp.nrows, nmodes);
-  if (hp.fast)
-    dst3_launch(md, hp, wrk, lsz, nmodes, false);
+  if (fz)
+    dst3_launch(md, hp, wrk, lsz, nmodes, DST_FUSED_F, fz);
+  else if (hp.fast)
+    dst3_launch(md, hp, wrk, lsz, nmodes, DST_PLAIN_F);
   else
     QG_LAUNCH(md, "k_xform", gx, 256, hp.smem_bytes, k_xform, x);
   TriArgs t = tri_args(hp, wrk, lsz, nmodes);
   dim3 gl((hp.nk + 127) / 128, hp.nchunk, nmodes), gr((hp.nk + 127) / 128, nmodes);
   if (hp.nchunk > 1 || hp.nranks > 1) {
-    auto kfg = k_tri_local<false>;
-    QG_LAUNCH(md, "k_tri_fg", gl, 128, 0, kfg, t);
+    if (fz) {
+      QG_LAUNCH(md, "k_tri_fg", dim3(gl.x, gl.y), 128, 0, k_tri3_fg<3>, t, mix3_args(hp, *fz));
+    } else {
+      auto kfg = k_tri_local<false>;
+      QG_LAUNCH(md, "k_tri_fg", gl, 128, 0, kfg, t);
+    }
   }
   t.slab_phase = hp.nranks > 1 ? 1 : 0;
   hp.slab_pushed = false;
@@ -1386,7 +1695,7 @@ void helm_solve_a(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
 
 // second half: (slabs: inter-slab system from the gathered rows, interface system again with
 // the neighbour rows) final chunk solves, inverse transform, wall rows
-void helm_solve_b(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
+void helm_solve_b(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes, const FusedInv *fz) {
   const size_t lsz = (size_t)hp.ld * hp.nyp;
   TriArgs t = tri_args(hp, wrk, lsz, nmodes);
   dim3 gl((hp.nk + 127) / 128, hp.nchunk, nmodes), gr((hp.nk + 127) / 128, nmodes);
@@ -1400,10 +1709,17 @@ void helm_solve_b(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes) {
       QG_LAUNCH(md, "k_slab_outer", gr, 128, 0, k_slab_outer, sa);
     }
   }
+  if (fz) {
+    // fused: the final chunk solves project back onto the layers and leave the modal integrals;
+    // the inverse transform follows the constraint algebra (helm_fused_inverse)
+    QG_LAUNCH(md, "k_tri_local", dim3(gl.x, gl.y), 128, 0, k_tri3_fin<3>, t, mix3_args(hp, *fz));
+    QG_CUDA(cudaGetLastError());
+    return;
+  }
   auto kfin = k_tri_local<true>;
   QG_LAUNCH(md, "k_tri_local", gl, 128, 0, kfin, t);
   if (hp.fast) {
-    dst3_launch(md, hp, wrk, lsz, nmodes, true);
+    dst3_launch(md, hp, wrk, lsz, nmodes, DST_PLAIN_I);
   } else {
     XfArgs x = xf_args(hp, wrk, lsz);
     dim3 gx(hp.nrows, nmodes);

@@ -122,6 +122,11 @@ struct ScalArgs {
   double dx, f0, tdt, xl, yl;
   double h[NLMAX], gp[NLMAX], ctl2m[NLMAX * NLMAX], ctm2l[NLMAX * NLMAX];
   const double *rowsum;   // [nl][nyp]
+  // where the modal area integrals come from: xintp row sums of the inverse transform
+  // (sumsrc = rowsum, stride nyp, rows [sumlo, sumhi)) or, on the fused box path, the per-block
+  // spectral shares left by k_tri3 (sumsrc = spec, stride nspec, [0, nspec))
+  const double *sumsrc;
+  int sumstride, sumlo, sumhi;
   qgcm_scalars *sc;
   double *coef;
   // y-slabs (box ocean): cv[3] = xon(1), cv[4+m] = xinhom(m), already summed over the ranks
@@ -137,11 +142,11 @@ struct ScalArgs {
 
 // y-slabs: this rank's share of the xintp integrals of the modal solutions -> cv[4+m]
 // (with the peer-memory transport it also sums cv[3 .. 4+nl) over the ranks)
-__global__ void __launch_bounds__(256) k_inv_partials(const double *rowsum, int nl, int nyp, int lo, int hi, double dx, double *cv,
+__global__ void __launch_bounds__(256) k_inv_partials(const double *sumsrc, int nl, int stride, int lo, int hi, double dx, double *cv,
                                                       PeerCtx peer, int *peer_err) {
   __shared__ double red[8];
   for (int m = 0; m < nl; ++m) {
-    const double s = block256_range_sum(rowsum + (size_t)m * nyp, lo, hi, red);   // wall rows are exactly zero
+    const double s = block256_range_sum(sumsrc + (size_t)m * stride, lo, hi, red);   // wall rows are exactly zero
     if (threadIdx.x == 0) cv[4 + m] = s * dx * dx;
     __syncthreads();
   }
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(256) k_inv_scalars(ScalArgs a) {
     double sm[NLMAX];
     for (int m = 0; m < nl; ++m) {
       double acc = 0.0;
-      for (int i = a.lo + (int)threadIdx.x; i < a.hi; i += 256) acc += a.rowsum[(size_t)m * nyp + i];
+      for (int i = a.sumlo + (int)threadIdx.x; i < a.sumhi; i += 256) acc += a.sumsrc[(size_t)m * a.sumstride + i];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
       sm[m] = acc;
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(256) k_inv_scalars(ScalArgs a) {
     __syncthreads();
     peer_allreduce_block(a.peer, a.cvw + 3, 1 + nl, a.cvw + 3, a.peer_err);
   }
-  for (int m = 0; m < nl; ++m) sums[m] = a.cv ? 0.0 : block256_range_sum(a.rowsum + (size_t)m * nyp, 1, nyp - 1, red);
+  for (int m = 0; m < nl; ++m) sums[m] = a.cv ? 0.0 : block256_range_sum(a.sumsrc + (size_t)m * a.sumstride, a.sumlo, a.sumhi, red);
   if (threadIdx.x != 0) return;
   if (a.cv) s->xon[0] = a.cv[3];
   for (int m = 0; m < nl; ++m) {
@@ -325,7 +330,14 @@ static void fill_inv(qgcm_model *m, bool atmos, InvArgs &a) {
   a.coef = m->d_coef + (atmos ? 64 : 0);
 }
 
-static void inv_scalars_m2l(qgcm_model *m, bool atmos, const InvArgs &a) {
+static FusedInv fused_args(qgcm_model *m, const InvArgs &a) {
+  FusedInv f;
+  f.q = a.q; f.pnew = a.pnew; f.yrel = a.yrel; f.beta = a.beta; f.f0 = a.f0; f.ddyn = a.ddyn; f.hom = a.hom; f.coef = a.coef;
+  for (int i = 0; i < NLMAX * NLMAX; ++i) { f.ctl2m[i] = a.ctl2m[i]; f.ctm2l[i] = a.ctm2l[i]; }
+  return f;
+}
+
+static void inv_scalars_m2l(qgcm_model *m, bool atmos, const InvArgs &a, bool fused = false) {
   const Grid &g = a.g;
   HelmPlan &hp = atmos ? m->hpa : m->hpo;
   ScalArgs s;
@@ -335,14 +347,23 @@ static void inv_scalars_m2l(qgcm_model *m, bool atmos, const InvArgs &a) {
   for (int k = 0; k < NLMAX; ++k) { s.h[k] = lc.h[k]; s.gp[k] = lc.gp[k]; }
   for (int i = 0; i < NLMAX * NLMAX; ++i) { s.ctl2m[i] = lc.ctl2m[i]; s.ctm2l[i] = lc.ctm2l[i]; }
   s.rowsum = hp.rowsum;
+  s.sumsrc = fused ? hp.spec : hp.rowsum;
+  s.sumstride = fused ? hp.nspec : g.nyp;
+  // one GPU: interior rows 1 .. nyp-2 (the wall rows are exactly zero); y-slabs: the solved rows
+  s.sumlo = fused ? 0 : (m->nranks > 1 ? hp.row0 : 1);
+  s.sumhi = fused ? hp.nspec : (m->nranks > 1 ? hp.row0 + hp.nrows : g.nyp - 1);
   s.sc = m->d_scal;
   s.coef = (double *)a.coef;
   s.cv = (!atmos && m->nranks > 1) ? m->d_cv : nullptr;
   s.peer.n = 0; s.peer_err = m->d_peer_err; s.cvw = m->d_cv; s.lo = hp.row0; s.hi = hp.row0 + hp.nrows;
   if (!atmos && m->nranks > 1) s.peer = peer_next_vec(m);
   QG_LAUNCH(m, "k_inv_scalars", 1, 256, 0, k_inv_scalars, s);
-  dim3 gm((g.nxp + 255) / 256, g.nyp);
-  QG_LAUNCH(m, "k_m2l", gm, 256, 0, k_m2l, a);
+  if (fused) {
+    helm_fused_inverse(m, hp, a.wrk, g.nl, fused_args(m, a));
+  } else {
+    dim3 gm((g.nxp + 255) / 256, g.nyp);
+    QG_LAUNCH(m, "k_m2l", gm, 256, 0, k_m2l, a);
+  }
   QG_CUDA(cudaGetLastError());
   // pom <- po, po <- new: pointer rotation (src/ocisubs.F:392, src/atisubs.F:282)
   m->swapf(atmos ? "pa" : "po", atmos ? "pam" : "pom");
@@ -353,6 +374,14 @@ static void invert(qgcm_model *m, bool atmos) {
   fill_inv(m, atmos, a);
   const Grid &g = a.g;
   HelmPlan &hp = atmos ? m->hpa : m->hpo;
+  if (!atmos && helm_can_fuse(m, hp, g.nl)) {
+    // box ocean, fast DST plan: no k_l2m / k_m2l, the projections ride on the solver's kernels
+    const FusedInv fz = fused_args(m, a);
+    helm_solve_a(m, hp, a.wrk, g.nl, &fz);
+    helm_solve_b(m, hp, a.wrk, g.nl, &fz);
+    inv_scalars_m2l(m, atmos, a, true);
+    return;
+  }
   dim3 gi((g.nxp + 511) / 512, g.nyp - 2);
   QG_LAUNCH(m, "k_l2m", gi, 256, 0, k_l2m, a);
   helm_solve(m, hp, a.wrk, g.nl);
@@ -365,6 +394,11 @@ void ocinvq_phase_a(qgcm_model *m) {
   InvArgs a;
   fill_inv(m, false, a);
   const Grid &g = a.g;
+  if (helm_can_fuse(m, m->hpo, g.nl)) {
+    const FusedInv fz = fused_args(m, a);
+    helm_solve_a(m, m->hpo, a.wrk, g.nl, &fz);
+    return;
+  }
   dim3 gi((g.nxp + 511) / 512, g.nyp - 2);
   QG_LAUNCH(m, "k_l2m", gi, 256, 0, k_l2m, a);
   helm_solve_a(m, m->hpo, a.wrk, g.nl);
@@ -372,16 +406,27 @@ void ocinvq_phase_a(qgcm_model *m) {
 void ocinvq_phase_b(qgcm_model *m) {
   const Grid &g = m->go;
   HelmPlan &hp = m->hpo;
-  helm_solve_b(m, hp, m->wrk_o, g.nl);
+  const bool fused = helm_can_fuse(m, hp, g.nl);
+  if (fused) {
+    InvArgs a;
+    fill_inv(m, false, a);
+    const FusedInv fz = fused_args(m, a);
+    helm_solve_b(m, hp, m->wrk_o, g.nl, &fz);
+  } else {
+    helm_solve_b(m, hp, m->wrk_o, g.nl);
+  }
   if (peer_active(m)) return;      // k_inv_scalars forms and all-reduces the integrals itself
   PeerCtx none = {};
-  QG_LAUNCH(m, "k_inv_partials", 1, 256, 0, k_inv_partials, hp.rowsum, g.nl, g.nyp, hp.row0, hp.row0 + hp.nrows, g.dx, m->d_cv,
-            none, m->d_peer_err);
+  if (fused)
+    QG_LAUNCH(m, "k_inv_partials", 1, 256, 0, k_inv_partials, hp.spec, g.nl, hp.nspec, 0, hp.nspec, g.dx, m->d_cv, none, m->d_peer_err);
+  else
+    QG_LAUNCH(m, "k_inv_partials", 1, 256, 0, k_inv_partials, hp.rowsum, g.nl, g.nyp, hp.row0, hp.row0 + hp.nrows, g.dx, m->d_cv,
+              none, m->d_peer_err);
 }
 void ocinvq_phase_c(qgcm_model *m) {
   InvArgs a;
   fill_inv(m, false, a);
-  inv_scalars_m2l(m, false, a);
+  inv_scalars_m2l(m, false, a, helm_can_fuse(m, m->hpo, m->go.nl));
 }
 
 void launch_ocinvq(qgcm_model *m) { invert(m, false); }

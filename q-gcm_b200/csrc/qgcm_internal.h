@@ -165,8 +165,26 @@ struct HelmPlan {
   bool slab_pushed = false;    // helm_solve_a already delivered the slab rows to the peers' mailboxes
   PeerCtx slab_peer = {};      // peer-memory transport: the gathered rows arrive in the mailbox, k_slab_solve waits for them
   int *slab_err = nullptr;
+  double *wsum = nullptr;    // [ld] box: 2 cot(k pi / 2n) at odd sine wavenumbers k (x-sum of a sine series), else 0
+  double *spec = nullptr;    // [nmodes][nspec] per-block shares of the modal area integrals (k_tri3)
+  int nspec = 0;
   double *rowsum = nullptr;  // [nmodes][nyp]  xintp row sums of the solution
   double *ayrow = nullptr;   // [nmodes][2]    periodic: line sums of rows 2 and nyp-1
+};
+
+// Box ocean with the fast DST plan: ocinvq runs as forward transform of the vorticity layers ->
+// tridiagonal kernels that project layers <-> modes in spectral space -> constraint algebra ->
+// inverse transform that adds the homogeneous solutions and writes the pressure layers
+// (helmholtz.cu, k_dst3 / k_tri3); this is what those kernels need beyond the plan
+struct FusedInv {
+  const double *q;          // vorticity layers [nl][nyp][ld]
+  double *pnew;             // new pressure layers (the lagged-p buffer)
+  const double *yrel;
+  double beta, f0;
+  const double *ddyn;       // null over a flat bottom
+  const double *hom;        // ochom [nl-1][nyp][ld]
+  const double *coef;       // device hclco[nl-1], written by k_inv_scalars before the inverse transform
+  double ctl2m[NLMAX * NLMAX], ctm2l[NLMAX * NLMAX];
 };
 
 // Scratch and tables of the coupled forcing xforc (atmos.cu); built on first use
@@ -419,7 +437,9 @@ void homsol_box_c(qgcm_model *m, const std::vector<double> &aipohs);
 void constr_ocean_share(qgcm_model *m, std::vector<double> &v);
 void constr_ocean_store(qgcm_model *m, const std::vector<double> &v);
 void helm_clean_walls(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes);
-void helm_solve_a(qgcm_model *m, HelmPlan &hp, double *wrk, int nmodes);
-void helm_solve_b(qgcm_model *m, HelmPlan &hp, double *wrk, int nmodes);
+void helm_solve_a(qgcm_model *m, HelmPlan &hp, double *wrk, int nmodes, const FusedInv *fz = nullptr);
+void helm_solve_b(qgcm_model *m, HelmPlan &hp, double *wrk, int nmodes, const FusedInv *fz = nullptr);
+bool helm_can_fuse(const qgcm_model *m, const HelmPlan &hp, int nl);   // box ocean, fast DST plan, 3 layers
+void helm_fused_inverse(qgcm_model *m, HelmPlan &hp, double *wrk, int nl, const FusedInv &fz);
 
 }  // namespace qg

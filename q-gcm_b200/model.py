@@ -362,5 +362,9 @@ class SlabGroup:
         for m in self.ranks:
             m.sync()
 
+    def close(self):
+        for m in reversed(self.ranks):
+            m.close()
+
     def launch_count(self):
         return sum(m.launch_count() for m in self.ranks)

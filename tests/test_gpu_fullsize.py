@@ -46,11 +46,7 @@ def _run_deck(qg, pyorc, deck, slab_counts, nsteps):
         compare_scalars(m, frozen, ("xon",), tol=1e-11, floor=fle)
         for nm in ("po", "qo", "sst"):
             assert np.isfinite(m.get_field(nm)).all()
-        if hasattr(m, "ranks"):
-            for r in m.ranks:
-                r.close()
-        else:
-            m.close()
+        m.close()
 
 
 def test_natl1km_full_size_one_gpu_and_8_slabs(qg, pyorc):
