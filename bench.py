@@ -46,7 +46,10 @@ def passes_per_launch(kernel, cyclic):
     table = {
         "k_oml_step": 9.0, "k_oml_entoc": 2.0,
         "k_qgstep": 17.0,
-        "k_l2m": 6.0, "k_xform": 6.0, "k_tri_local": 6.0, "k_tri_fg": 3.0,
+        # box decks with the fast DST plan run ocinvq fused: the forward transform reads q and writes the
+        # spectral layers (6), the inverse reads them and ochom and writes p (8 box); k_l2m / k_m2l are
+        # launched only on the unfused path (channel, atmosphere), where both transforms move 6
+        "k_l2m": 6.0, "k_xform": 6.0, "k_xform_inv": 6.0 if cyclic else 8.0, "k_tri_local": 6.0, "k_tri_fg": 3.0,
         "k_m2l": 6.0 if cyclic else 8.0,
         "k_avg2": None,
     }

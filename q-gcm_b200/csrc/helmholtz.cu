@@ -881,164 +881,116 @@ struct Mix3 {
   double *spec;           // [nl][nchunk * gridDim.x] partial integrals (FINAL)
 };
 
-// first/last values of the chunk-local solutions, streaming: one sweep over the chunk's rows
-// with the layer values of a row in flight only.  The last value of a Thomas solve is what the
-// forward elimination ends with; the first value is the dot product of the right-hand side with
-// the first row of the inverse, which by symmetry is the left spike of the chunk over -a.
-template <int NL>
-__global__ void __launch_bounds__(128, 4) k_tri3_fg(TriArgs t, Mix3 mx) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = blockIdx.y;
-  if (s >= t.nk) return;
-  const int col = t.koff + s;
-  const bool lastc = (c == t.nchunk - 1);
-  const int len = lastc ? t.lastlen : TRI_L;
-  const double a = t.a;
-  const int ld = t.ld;
-  const double *__restrict__ base = t.wrk + (size_t)(t.row0 + c * TRI_L) * ld + col;
-  const double *__restrict__ bi = t.binv + col;
-  const double *__restrict__ sp = (lastc ? t.vll : t.vl) + col;
-  double d[NL], f[NL];
-#pragma unroll
-  for (int m = 0; m < NL; ++m) d[m] = f[m] = 0.0;
-#pragma unroll 8
-  for (int j = 0; j < len; ++j) {
-    double sk[NL];
-#pragma unroll
-    for (int k = 0; k < NL; ++k) sk[k] = base[(size_t)k * t.lsz + (size_t)j * ld];
-#pragma unroll
-    for (int m = 0; m < NL; ++m) {
-      double acc = 0.0;
-#pragma unroll
-      for (int k = 0; k < NL; ++k) acc = acc + mx.ctl2m[k + NL * m] * sk[k];
-      const double r = mx.f0 * acc;
-      const size_t tb = ((size_t)m * TRI_L + j) * ld;
-      d[m] = (r - a * d[m]) * __ldg(bi + tb);
-      f[m] = fma(__ldg(sp + tb), r, f[m]);
-    }
-  }
-  const double ra = -1.0 / a;
-#pragma unroll
-  for (int m = 0; m < NL; ++m) {
-    const size_t fb = ((size_t)m * 2 * t.nchunk) * ld + col;
-    t.fg[fb + (size_t)c * ld] = f[m] * ra;
-    t.fg[fb + (size_t)(t.nchunk + c) * ld] = d[m];
-  }
-}
-
-// final chunk solves of all modes of a wavenumber in one thread: modes 0 .. NL-2 in registers,
-// the last mode in shared memory ([row][thread], conflict free), so that the kernel stays clear
-// of register spills at two blocks per SM
-template <int NL>
-__global__ void __launch_bounds__(128, 2) k_tri3_fin(TriArgs t, Mix3 mx) {
-  __shared__ double us[TRI_L][128];
-  __shared__ double red[NL][4];
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// One block = TC wavenumber columns x NL "parts" of one chunk.  Part p of a column
+//   1. loads rows j = p, p+NL, ... of ALL layers (the loads of a warp are 32 neighbouring
+//      columns of one row: coalesced), projects them onto the modes and parks the NL modal
+//      right-hand sides of each row in shared memory ([mode][row][column], conflict free);
+//   2. solves mode p of its column in registers (Thomas, elimination reciprocals from the
+//      L2-resident table) and parks the solution;
+//   3. FINAL: projects rows j = p, p+NL, ... of all modes back onto the layers and stores them.
+// So every thread carries one 32-row recurrence, as in the unfused kernel, and a value crosses
+// shared memory four times per point and mode (against one HBM read and one write).
+constexpr size_t tri3_smem = sizeof(double) * 3 * TRI_L * 64;      // 48 KB for NL = 3
+template <int NL, bool FINAL>
+__global__ void __launch_bounds__(64 * NL, 2) k_tri3(TriArgs t, Mix3 mx) {
+  constexpr int TC = 64;
+  extern __shared__ double us_raw[];
+  double (*us)[TRI_L][TC] = reinterpret_cast<double (*)[TRI_L][TC]>(us_raw);      // [NL][TRI_L][TC]
+  __shared__ double red[NL][2];
+  const int tc = threadIdx.x % TC, p = threadIdx.x / TC;      // warps are uniform in p
+  const int s = blockIdx.x * TC + tc;
   const int c = blockIdx.y;
   const bool live = s < t.nk;
   const int col = t.koff + (live ? s : 0);
   const int len = (c == t.nchunk - 1) ? t.lastlen : TRI_L;
   const double a = t.a;
-  const int ld = t.ld, tx = threadIdx.x;
+  const int ld = t.ld;
   double *__restrict__ base = t.wrk + (size_t)(t.row0 + c * TRI_L) * ld + col;
-  double u[NL - 1][TRI_L];
-  // layers -> modes (rows >= len: harmless duplicates of the last row)
+  // ---- 1. layers -> modes for this part's rows
+  constexpr int NJ = (TRI_L + NL - 1) / NL;
 #pragma unroll
-  for (int j = 0; j < TRI_L; ++j) {
-    double sk[NL];
+  for (int jj = 0; jj < NJ; ++jj) {
+    const int j = p + jj * NL;
+    if (j < TRI_L) {
+      double sk[NL];
+      const size_t ro = (size_t)min(j, len - 1) * ld;      // rows >= len: harmless duplicates of the last row
 #pragma unroll
-    for (int k = 0; k < NL; ++k) sk[k] = base[(size_t)k * t.lsz + (size_t)min(j, len - 1) * ld];
+      for (int k = 0; k < NL; ++k) sk[k] = base[(size_t)k * t.lsz + ro];
 #pragma unroll
-    for (int m = 0; m < NL; ++m) {
-      double acc = 0.0;
+      for (int m = 0; m < NL; ++m) {
+        double acc = 0.0;
 #pragma unroll
-      for (int k = 0; k < NL; ++k) acc = acc + mx.ctl2m[k + NL * m] * sk[k];
-      if (m < NL - 1) u[m][j] = mx.f0 * acc; else us[j][tx] = mx.f0 * acc;
+        for (int k = 0; k < NL; ++k) acc = acc + mx.ctl2m[k + NL * m] * sk[k];
+        us[m][j][tc] = mx.f0 * acc;
+      }
     }
-    // loads are kept within groups of eight rows (24 in flight per thread): hoisting all 96 above
-    // the projection costs more registers than the kernel has
-    if ((j & 7) == 7) asm volatile("" ::: "memory");
   }
-  double sm[NL];
+  __syncthreads();
+  // ---- 2. mode p of this column
+  const int m = p;
+  const double *__restrict__ bi = t.binv + ((size_t)m * TRI_L) * ld + col;
+  const size_t fb = ((size_t)m * 2 * t.nchunk) * ld + col;
+  double u[TRI_L];
 #pragma unroll
-  for (int m = 0; m < NL - 1; ++m) {
-    const double *__restrict__ bi = t.binv + ((size_t)m * TRI_L) * ld + col;
-    const size_t fb = ((size_t)m * 2 * t.nchunk) * ld + col;
-    if (t.use_yx) {
-      const double yp = t.yx[fb + (size_t)c * ld], xn = t.yx[fb + (size_t)(t.nchunk + c) * ld];
-      u[m][0] -= a * yp;
+  for (int j = 0; j < TRI_L; ++j) u[j] = us[m][j][tc];
+  if (FINAL && t.use_yx) {
+    const double yp = t.yx[fb + (size_t)c * ld], xn = t.yx[fb + (size_t)(t.nchunk + c) * ld];
+    u[0] -= a * yp;
 #pragma unroll
-      for (int j = 0; j < TRI_L; ++j) u[m][j] = fma(-a, (j == len - 1) ? xn : 0.0, u[m][j]);
-    }
-    u[m][0] = u[m][0] * __ldg(bi);
-#pragma unroll
-    for (int j = 1; j < TRI_L; ++j) u[m][j] = (u[m][j] - a * u[m][j - 1]) * __ldg(bi + (size_t)j * ld);
-#pragma unroll
-    for (int j = TRI_L - 2; j >= 0; --j) {
-      const double v = u[m][j] - (a * __ldg(bi + (size_t)j * ld)) * u[m][j + 1];
-      u[m][j] = (j < len - 1) ? v : u[m][j];
-    }
-    double acc = 0.0;
-#pragma unroll
-    for (int j = 0; j < TRI_L; ++j) acc += (j < len) ? u[m][j] : 0.0;
-    sm[m] = acc;
+    for (int j = 0; j < TRI_L; ++j) u[j] = fma(-a, (j == len - 1) ? xn : 0.0, u[j]);
   }
-  {
-    constexpr int m = NL - 1;
-    const double *__restrict__ bi = t.binv + ((size_t)m * TRI_L) * ld + col;
-    const size_t fb = ((size_t)m * 2 * t.nchunk) * ld + col;
-    if (t.use_yx) {
-      const double yp = t.yx[fb + (size_t)c * ld], xn = t.yx[fb + (size_t)(t.nchunk + c) * ld];
-      us[0][tx] -= a * yp;
-      us[len - 1][tx] = fma(-a, xn, us[len - 1][tx]);
+  u[0] = u[0] * __ldg(bi);
+#pragma unroll
+  for (int j = 1; j < TRI_L; ++j) u[j] = (u[j] - a * u[j - 1]) * __ldg(bi + (size_t)j * ld);
+#pragma unroll
+  for (int j = TRI_L - 2; j >= 0; --j) {
+    const double v = u[j] - (a * __ldg(bi + (size_t)j * ld)) * u[j + 1];
+    u[j] = (j < len - 1) ? v : u[j];
+  }
+  if (!FINAL) {
+    if (live && (t.nchunk > 1 || t.nranks > 1)) {
+      t.fg[fb + (size_t)c * ld] = u[0];                    // f_c : first row of the chunk
+      double gl = 0.0;                                     // g_c : last row of the chunk
+#pragma unroll
+      for (int j = 0; j < TRI_L; ++j) gl = fma((j == len - 1) ? 1.0 : 0.0, u[j], gl);
+      t.fg[fb + (size_t)(t.nchunk + c) * ld] = gl;
     }
-    double prev = us[0][tx] * __ldg(bi);
-    us[0][tx] = prev;
-#pragma unroll 8
-    for (int j = 1; j < len; ++j) {
-      prev = (us[j][tx] - a * prev) * __ldg(bi + (size_t)j * ld);
-      us[j][tx] = prev;
-    }
-    double acc = prev;
-#pragma unroll 8
-    for (int j = len - 2; j >= 0; --j) {
-      prev = us[j][tx] - (a * __ldg(bi + (size_t)j * ld)) * prev;
-      us[j][tx] = prev;
-      acc += prev;
-    }
-    sm[m] = acc;
+    return;
   }
   const double fn = t.ftnorm;
-  // modes -> layers, times ftnorm (src/ocisubs.F:484-487)
+  double sm = 0.0;
 #pragma unroll
   for (int j = 0; j < TRI_L; ++j) {
+    const double v = fn * u[j];      // times ftnorm (src/ocisubs.F:484-487)
+    us[m][j][tc] = v;
+    sm += (j < len) ? v : 0.0;
+  }
+  // the block's share of the area integral of mode p: fixed-order reduction over its 64 columns
+  {
+    double v = live ? __ldg(mx.wsum + col) * sm : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((tc & 31) == 0) red[p][tc >> 5] = v;
+  }
+  __syncthreads();
+  if (tc == 0) mx.spec[(size_t)p * (t.nchunk * gridDim.x) + (size_t)c * gridDim.x + blockIdx.x] = red[p][0] + red[p][1];
+  // ---- 3. modes -> layers for this part's rows
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) {
+    const int j = p + jj * NL;
     if (j < len) {
       double um[NL];
 #pragma unroll
-      for (int m = 0; m < NL - 1; ++m) um[m] = fn * u[m][j];
-      um[NL - 1] = fn * us[j][tx];
+      for (int mm = 0; mm < NL; ++mm) um[mm] = us[mm][j][tc];
 #pragma unroll
       for (int k = 0; k < NL; ++k) {
         double acc = 0.0;
 #pragma unroll
-        for (int m = 0; m < NL; ++m) acc = acc + mx.ctm2l[m + NL * k] * um[m];
+        for (int mm = 0; mm < NL; ++mm) acc = acc + mx.ctm2l[mm + NL * k] * um[mm];
         if (live) base[(size_t)k * t.lsz + (size_t)j * ld] = acc;
       }
     }
-    if ((j & 7) == 7) asm volatile("" ::: "memory");
   }
-  // the block's share of the modal area integrals: fixed-order reduction
-  const double w = live ? fn * __ldg(mx.wsum + col) : 0.0;
-#pragma unroll
-  for (int m = 0; m < NL; ++m) {
-    double v = w * sm[m];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((tx & 31) == 0) red[m][tx >> 5] = v;
-  }
-  __syncthreads();
-  if (tx < NL)
-    mx.spec[(size_t)tx * (t.nchunk * gridDim.x) + (size_t)c * gridDim.x + blockIdx.x] = (red[tx][0] + red[tx][1]) + (red[tx][2] + red[tx][3]);
 }
 
 struct SlabArgs {
@@ -1328,9 +1280,9 @@ static void dst3_launch_t(qgcm_model *md, HelmPlan &hp, const Dst3Args &a, int m
   const int grid = std::min(a.nitems, hp.fast_grid);      // persistent blocks, two per SM
   switch (mode) {
     case DST_PLAIN_F: QG_LAUNCH(md, "k_xform", grid, 256, smem, kf, a); break;
-    case DST_PLAIN_I: QG_LAUNCH(md, "k_xform", grid, 256, smem, ki, a); break;
+    case DST_PLAIN_I: QG_LAUNCH(md, "k_xform_inv", grid, 256, smem, ki, a); break;
     case DST_FUSED_F: QG_LAUNCH(md, "k_xform", grid, 256, smem, kff, a); break;
-    default: QG_LAUNCH(md, "k_xform", grid, 256, smem, kfi, a); break;
+    default: QG_LAUNCH(md, "k_xform_inv", grid, 256, smem, kfi, a); break;
   }
 }
 
@@ -1511,7 +1463,9 @@ void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, con
     for (int k = 1; k < hp.n; k += 2) ws[k] = (double)(2.0L * cosl(PI_Q * k / (2.0L * hp.n)) / sinl(PI_Q * k / (2.0L * hp.n)));
     hp.wsum = (double *)dalloc(md, sizeof(double) * row);
     QG_CUDA(cudaMemcpy(hp.wsum, ws.data(), sizeof(double) * row, cudaMemcpyHostToDevice));
-    hp.nspec = hp.nchunk * ((hp.nk + 127) / 128);
+    hp.nspec = hp.nchunk * ((hp.nk + 63) / 64);
+    QG_CUDA(cudaFuncSetAttribute(k_tri3<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri3_smem));
+    QG_CUDA(cudaFuncSetAttribute(k_tri3<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri3_smem));
     hp.spec = (double *)dalloc(md, sizeof(double) * nmodes * hp.nspec);
   }
   for (int r = 0; r < 16; ++r) hp.slab_rows[r] = 0;
@@ -1669,7 +1623,7 @@ void helm_solve_a(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes, const F
   dim3 gl((hp.nk + 127) / 128, hp.nchunk, nmodes), gr((hp.nk + 127) / 128, nmodes);
   if (hp.nchunk > 1 || hp.nranks > 1) {
     if (fz) {
-      QG_LAUNCH(md, "k_tri_fg", dim3(gl.x, gl.y), 128, 0, k_tri3_fg<3>, t, mix3_args(hp, *fz));
+      QG_LAUNCH(md, "k_tri_fg", dim3((hp.nk + 63) / 64, hp.nchunk), 192, tri3_smem, (k_tri3<3, false>), t, mix3_args(hp, *fz));
     } else {
       auto kfg = k_tri_local<false>;
       QG_LAUNCH(md, "k_tri_fg", gl, 128, 0, kfg, t);
@@ -1712,7 +1666,7 @@ void helm_solve_b(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes, const F
   if (fz) {
     // fused: the final chunk solves project back onto the layers and leave the modal integrals;
     // the inverse transform follows the constraint algebra (helm_fused_inverse)
-    QG_LAUNCH(md, "k_tri_local", dim3(gl.x, gl.y), 128, 0, k_tri3_fin<3>, t, mix3_args(hp, *fz));
+    QG_LAUNCH(md, "k_tri_local", dim3((hp.nk + 63) / 64, hp.nchunk), 192, tri3_smem, (k_tri3<3, true>), t, mix3_args(hp, *fz));
     QG_CUDA(cudaGetLastError());
     return;
   }
@@ -1724,7 +1678,7 @@ void helm_solve_b(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes, const F
     XfArgs x = xf_args(hp, wrk, lsz);
     dim3 gx(hp.nrows, nmodes);
     x.inverse = 1;
-    QG_LAUNCH(md, "k_xform", gx, 256, hp.smem_bytes, k_xform, x);
+    QG_LAUNCH(md, "k_xform_inv", gx, 256, hp.smem_bytes, k_xform, x);
   }
   // the wall rows of the work array stay zero from one ocean/atmosphere step to the next (the
   // right-hand side kernel writes interior rows only); only homsol and qgcm_helmholtz fill them
