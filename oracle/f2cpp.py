@@ -632,6 +632,9 @@ class Emitter:
         if isinstance(e, Logical):
             return "bool"
         if isinstance(e, Name):
+            if u.kind == "function" and e.name == u.name:
+                rt = u.rtype or u.syms[u.name].ftype
+                return "int" if rt == "integer" else "bool" if rt == "logical" else "double"
             sy, _ = self.lookup(u, e.name)
             if sy is None:
                 raise RuntimeError("%s: undeclared name %s" % (u.where, e.name))
@@ -698,6 +701,8 @@ class Emitter:
         if isinstance(e, Logical):
             return "true" if e.v else "false"
         if isinstance(e, Name):
+            if u.kind == "function" and e.name == u.name:
+                return "%s_res" % u.name
             sy, owner = self.lookup(u, e.name)
             if sy is None:
                 raise RuntimeError("%s: undeclared name %s" % (u.where, e.name))
@@ -928,12 +933,12 @@ class Emitter:
             if sy.dummy or sy.ftype == "?":
                 continue
             if u.kind == "function" and n == u.name:
-                o.append("  %s %s_ = 0;" % (sy.ctype, n))
                 continue
             if sy.dims is None:
                 static = "static " if (sy.save or u.save_all or sy.data) else ""
                 if sy.param is not None:
-                    o.append("  const %s %s_ = (%s)(%s);" % (sy.ctype, n, sy.ctype, self.ex(u, sy.param)))
+                    # not const: Fortran passes named constants by address like any other object
+                    o.append("  %s %s_ = (%s)(%s);" % (sy.ctype, n, sy.ctype, self.ex(u, sy.param)))
                 elif sy.ftype == "character":
                     o.append("  %sstd::string %s_;" % (static, n))
                 elif sy.data:
@@ -959,6 +964,9 @@ class Emitter:
                          if sy.ctype != "bool" else
                          "  std::vector<char> %s_v((size_t)(%s)); bool *%s_ = reinterpret_cast<bool *>(%s_v.data());" %
                          (n, self.total(u, sy), n, n))
+        if u.kind == "function":
+            rt = u.rtype or u.syms[u.name].ftype
+            o.append("  %s %s_res = 0;" % (CTYPE["double" if rt == "double" else rt], u.name))
         labels = set()
         for s in u.body:
             for m in re.finditer(r"\bgo\s*to\s+(\d+)", s.text):
@@ -970,7 +978,7 @@ class Emitter:
         if self.blocks:
             raise RuntimeError("%s: unterminated block in %s" % (u.where, u.name))
         if u.kind == "function":
-            o.append("  return %s_;" % u.name)
+            o.append("  return %s_res;" % u.name)
         o.append("}")
 
     def ind(self):
@@ -991,14 +999,14 @@ class Emitter:
             while self.do_labels and self.do_labels[-1] == s.label:
                 self.do_labels.pop()
                 self.blocks.pop()
-                o.append(self.ind() + "}")
+                o.append(self.ind() + "} }")
 
     def exec_inner(self, u, s, t, labels):
         o = self.out
         if t == "continue":
             return
         if t == "return":
-            o.append(self.ind() + ("return %s_;" % u.name if u.kind == "function" else "return;"))
+            o.append(self.ind() + ("return %s_res;" % u.name if u.kind == "function" else "return;"))
             return
         if t.startswith("stop"):
             o.append(self.ind() + 'f2c_stop("%s");' % s.where)
@@ -1093,6 +1101,21 @@ class Emitter:
             acts = [self.actual(u, a, None) for a in args]
             if callee is None and name not in self.stubs:
                 raise RuntimeError("call to unknown procedure %s" % name)
+            if callee is not None:
+                if len(callee.args) != len(args):
+                    raise RuntimeError("call of %s with %d arguments, it declares %d" % (name, len(args), len(callee.args)))
+                for k, (a, f) in enumerate(zip(args, callee.args)):
+                    fs = callee.syms[f]
+                    if fs.ftype == "character":
+                        continue
+                    at = self.etype(u, a)
+                    ft = {"integer": "int", "double": "double", "logical": "bool", "real": "double"}[fs.ftype]
+                    if at != ft:
+                        # storage association across types: pass the same address, as Fortran does
+                        # (FFTPACK keeps its integer factor table in the tail of the double work array)
+                        if not isinstance(a, (Name, Ref)):
+                            raise RuntimeError("type mismatch on an expression argument of %s" % name)
+                        acts[k] = "(%s *)(void *)(%s)" % (fs.ctype, acts[k])
             o.append(self.ind() + "%s_(%s);" % (name, ", ".join(acts)))
             return
         # assignment
@@ -1105,7 +1128,7 @@ class Emitter:
         if not p.done():
             raise RuntimeError("trailing tokens after assignment")
         if isinstance(lhs, Name) and u.kind == "function" and lhs.name == u.name:
-            o.append(self.ind() + "%s_ = %s;" % (u.name, self.ex(u, rhs)))
+            o.append(self.ind() + "%s_res = %s;" % (u.name, self.ex(u, rhs)))
             return
         lt = self.etype(u, lhs)
         r = self.ex(u, rhs)

@@ -885,15 +885,20 @@ struct Mix3 {
 //   1. loads rows j = p, p+NL, ... of ALL layers (the loads of a warp are 32 neighbouring
 //      columns of one row: coalesced), projects them onto the modes and parks the NL modal
 //      right-hand sides of each row in shared memory ([mode][row][column], conflict free);
-//   2. solves mode p of its column in registers (Thomas, elimination reciprocals from the
-//      L2-resident table) and parks the solution;
+//   2. owns mode p of its column:
+//      FINAL = false: one sweep over the parked values gives the last value of the chunk-local
+//        solution (where the forward elimination ends) and the first one (the dot product with
+//        the first row of the inverse, which by symmetry is the chunk's left spike over -a);
+//      FINAL = true : Thomas solve in place in shared memory (the elimination reciprocals come
+//        from the L2-resident table, fetched a group of rows ahead of the recurrence);
 //   3. FINAL: projects rows j = p, p+NL, ... of all modes back onto the layers and stores them.
-// So every thread carries one 32-row recurrence, as in the unfused kernel, and a value crosses
-// shared memory four times per point and mode (against one HBM read and one write).
+// The solve keeps no row in registers, so four blocks (24 warps) fit an SM and the load phase of
+// one block overlaps the recurrences of the others.
 constexpr size_t tri3_smem = sizeof(double) * 3 * TRI_L * 64;      // 48 KB for NL = 3
 template <int NL, bool FINAL>
-__global__ void __launch_bounds__(64 * NL, 2) k_tri3(TriArgs t, Mix3 mx) {
-  constexpr int TC = 64;
+__global__ void __launch_bounds__(64 * NL, 4) k_tri3(TriArgs t, Mix3 mx) {
+  constexpr int TC = 64, G = 8;
+  static_assert(TRI_L % G == 0, "row groups");
   extern __shared__ double us_raw[];
   double (*us)[TRI_L][TC] = reinterpret_cast<double (*)[TRI_L][TC]>(us_raw);      // [NL][TRI_L][TC]
   __shared__ double red[NL][2];
@@ -902,7 +907,8 @@ __global__ void __launch_bounds__(64 * NL, 2) k_tri3(TriArgs t, Mix3 mx) {
   const int c = blockIdx.y;
   const bool live = s < t.nk;
   const int col = t.koff + (live ? s : 0);
-  const int len = (c == t.nchunk - 1) ? t.lastlen : TRI_L;
+  const bool lastc = (c == t.nchunk - 1);
+  const int len = lastc ? t.lastlen : TRI_L;
   const double a = t.a;
   const int ld = t.ld;
   double *__restrict__ base = t.wrk + (size_t)(t.row0 + c * TRI_L) * ld + col;
@@ -930,43 +936,87 @@ __global__ void __launch_bounds__(64 * NL, 2) k_tri3(TriArgs t, Mix3 mx) {
   const int m = p;
   const double *__restrict__ bi = t.binv + ((size_t)m * TRI_L) * ld + col;
   const size_t fb = ((size_t)m * 2 * t.nchunk) * ld + col;
-  double u[TRI_L];
-#pragma unroll
-  for (int j = 0; j < TRI_L; ++j) u[j] = us[m][j][tc];
-  if (FINAL && t.use_yx) {
-    const double yp = t.yx[fb + (size_t)c * ld], xn = t.yx[fb + (size_t)(t.nchunk + c) * ld];
-    u[0] -= a * yp;
-#pragma unroll
-    for (int j = 0; j < TRI_L; ++j) u[j] = fma(-a, (j == len - 1) ? xn : 0.0, u[j]);
-  }
-  u[0] = u[0] * __ldg(bi);
-#pragma unroll
-  for (int j = 1; j < TRI_L; ++j) u[j] = (u[j] - a * u[j - 1]) * __ldg(bi + (size_t)j * ld);
-#pragma unroll
-  for (int j = TRI_L - 2; j >= 0; --j) {
-    const double v = u[j] - (a * __ldg(bi + (size_t)j * ld)) * u[j + 1];
-    u[j] = (j < len - 1) ? v : u[j];
-  }
   if (!FINAL) {
-    if (live && (t.nchunk > 1 || t.nranks > 1)) {
-      t.fg[fb + (size_t)c * ld] = u[0];                    // f_c : first row of the chunk
-      double gl = 0.0;                                     // g_c : last row of the chunk
+    const double *__restrict__ sp = (lastc ? t.vll : t.vl) + ((size_t)m * TRI_L) * ld + col;
+    double d = 0.0, f = 0.0;
+    double bq[G], vq[G];
 #pragma unroll
-      for (int j = 0; j < TRI_L; ++j) gl = fma((j == len - 1) ? 1.0 : 0.0, u[j], gl);
-      t.fg[fb + (size_t)(t.nchunk + c) * ld] = gl;
+    for (int u = 0; u < G; ++u) { bq[u] = __ldg(bi + (size_t)u * ld); vq[u] = __ldg(sp + (size_t)u * ld); }
+#pragma unroll
+    for (int g = 0; g < TRI_L / G; ++g) {
+      double bn[G], vn[G];
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        const int j = min((g + 1) * G + u, TRI_L - 1);
+        bn[u] = __ldg(bi + (size_t)j * ld);
+        vn[u] = __ldg(sp + (size_t)j * ld);
+      }
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        const int j = g * G + u;
+        const double r = us[m][j][tc];
+        const double dn = (r - a * d) * bq[u];
+        d = (j < len) ? dn : d;
+        f = fma((j < len) ? vq[u] : 0.0, r, f);
+      }
+#pragma unroll
+      for (int u = 0; u < G; ++u) { bq[u] = bn[u]; vq[u] = vn[u]; }
+    }
+    if (live && (t.nchunk > 1 || t.nranks > 1)) {
+      t.fg[fb + (size_t)c * ld] = -f / a;                    // f_c : first row of the chunk-local solution
+      t.fg[fb + (size_t)(t.nchunk + c) * ld] = d;            // g_c : its last row
     }
     return;
   }
-  const double fn = t.ftnorm;
-  double sm = 0.0;
-#pragma unroll
-  for (int j = 0; j < TRI_L; ++j) {
-    const double v = fn * u[j];      // times ftnorm (src/ocisubs.F:484-487)
-    us[m][j][tc] = v;
-    sm += (j < len) ? v : 0.0;
-  }
-  // the block's share of the area integral of mode p: fixed-order reduction over its 64 columns
   {
+    if (t.use_yx) {
+      const double yp = t.yx[fb + (size_t)c * ld], xn = t.yx[fb + (size_t)(t.nchunk + c) * ld];
+      us[m][0][tc] -= a * yp;
+      us[m][len - 1][tc] = fma(-a, xn, us[m][len - 1][tc]);
+    }
+    double bq[G];
+#pragma unroll
+    for (int u = 0; u < G; ++u) bq[u] = __ldg(bi + (size_t)u * ld);
+    double prev = 0.0;
+#pragma unroll
+    for (int g = 0; g < TRI_L / G; ++g) {
+      double bn[G];
+#pragma unroll
+      for (int u = 0; u < G; ++u) bn[u] = __ldg(bi + (size_t)min((g + 1) * G + u, TRI_L - 1) * ld);
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        const int j = g * G + u;
+        prev = (us[m][j][tc] - a * prev) * bq[u];
+        us[m][j][tc] = prev;      // rows >= len hold values nobody reads
+      }
+#pragma unroll
+      for (int u = 0; u < G; ++u) bq[u] = bn[u];
+    }
+    // back substitution from row len-1 downwards, times ftnorm on the way out (src/ocisubs.F:484-487)
+    const double fn = t.ftnorm;
+    double nxt = us[m][len - 1][tc];
+    double sm = fn * nxt;
+    us[m][len - 1][tc] = fn * nxt;
+#pragma unroll
+    for (int u = 0; u < G; ++u) bq[u] = __ldg(bi + (size_t)(TRI_L - 1 - u) * ld);
+#pragma unroll
+    for (int g = 0; g < TRI_L / G; ++g) {
+      double bn[G];
+#pragma unroll
+      for (int u = 0; u < G; ++u) bn[u] = __ldg(bi + (size_t)max(TRI_L - 1 - (g + 1) * G - u, 0) * ld);
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        const int j = TRI_L - 1 - g * G - u;
+        if (j < len - 1) {
+          nxt = us[m][j][tc] - (a * bq[u]) * nxt;
+          us[m][j][tc] = fn * nxt;
+          sm += fn * nxt;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < G; ++u) bq[u] = bn[u];
+    }
+    // the block's share of the area integral of mode p: fixed-order reduction over its 64 columns
     double v = live ? __ldg(mx.wsum + col) * sm : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
