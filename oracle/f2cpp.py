@@ -565,9 +565,9 @@ class Program:
                 u.param_order.append(sy.name)
 
     def data_stmt(self, u, text, s):
-        # data name / v1, v2, ... / [, name / ... /]
-        for m in re.finditer(r"(\w+)\s*/([^/]*)/", text):
-            sy = self.sym(u, m.group(1), None, s)
+        # data obj [, obj ...] / v1, v2, ... / [[,] obj ... / ... /]: objects are scalars, whole
+        # arrays (filled in element order) or array elements with constant subscripts
+        for m in re.finditer(r"([^/]+)/([^/]*)/\s*,?", text):
             vals = []
             for v in split_top(m.group(2)):
                 r = re.match(r"^(\d+)\s*\*\s*(.*)$", v)
@@ -575,8 +575,28 @@ class Program:
                     vals += [parse_expr(r.group(2), s.where)] * int(r.group(1))
                 else:
                     vals.append(parse_expr(v, s.where))
-            sy.data = vals
-            sy.save = True
+            for obj in split_top(m.group(1).strip().lstrip(",")):
+                e = parse_expr(obj, s.where)
+                name = e.name
+                sy = self.sym(u, name, None, s)
+                sy.save = True
+                if sy.data is None:
+                    sy.data = []
+                if isinstance(e, Ref):
+                    if not vals:
+                        raise RuntimeError("%s: DATA has too few values" % s.where)
+                    sy.data.append((e.args, vals.pop(0)))
+                elif sy.dims is not None:
+                    n = 1
+                    for rng in sy.dims:
+                        lo = int(rng.lo.text) if rng.lo is not None else 1
+                        n *= int(rng.hi.text) - lo + 1
+                    for k in range(n):
+                        sy.data.append((k, vals.pop(0)))
+                else:
+                    sy.data.append((None, vals.pop(0)))
+            if vals:
+                raise RuntimeError("%s: DATA has too many values" % s.where)
 
 
 # --------------------------------------------------------------------------------------
@@ -865,9 +885,8 @@ class Emitter:
                 sy = mod.syms[n]
                 if sy.dims is not None and sy.ftype != "?":
                     o.append("  %s_ = f2c_alloc<%s>(%s);" % (n, sy.ctype, self.total(mod, sy)))
-                    if sy.data:
-                        for k, v in enumerate(sy.data):
-                            o.append("  %s_[%d] = %s;" % (n, k, self.ex(mod, v)))
+                    for where, v in (sy.data or []):
+                        o.append("  %s_[%s] = %s;" % (n, self.data_index(mod, sy, where), self.ex(mod, v)))
         o.append("  f2c_ready = true;")
         o.append("}")
         for n in procs:
@@ -894,6 +913,11 @@ class Emitter:
             for dep in u.uses:
                 visit(dep)
         return order
+
+    def data_index(self, u, sy, where):
+        if isinstance(where, int):
+            return str(where)
+        return self.index(u, sy, where, u.where)
 
     def total(self, u, sy):
         parts = []
@@ -942,7 +966,7 @@ class Emitter:
                 elif sy.ftype == "character":
                     o.append("  %sstd::string %s_;" % (static, n))
                 elif sy.data:
-                    o.append("  static %s %s_ = %s;" % (sy.ctype, n, self.ex(u, sy.data[0])))
+                    o.append("  static %s %s_ = %s;" % (sy.ctype, n, self.ex(u, sy.data[0][1])))
                 else:
                     # uninitialised in Fortran; zero here so that a use-before-set is at least repeatable
                     o.append("  %s%s %s_ = 0;" % (static, sy.ctype, n))
@@ -954,8 +978,8 @@ class Emitter:
                 o.append("  static %s *%s_ = nullptr;" % (sy.ctype, n))
                 o.append("  if (!%s_) {" % n)
                 o.append("    %s_ = f2c_alloc<%s>(%s);" % (n, sy.ctype, self.total(u, sy)))
-                for k, v in enumerate(sy.data or []):
-                    o.append("    %s_[%d] = %s;" % (n, k, self.ex(u, v)))
+                for where, v in (sy.data or []):
+                    o.append("    %s_[%s] = %s;" % (n, self.data_index(u, sy, where), self.ex(u, v)))
                 o.append("  }")
             else:
                 # automatic array: the reference gets stack garbage, we get zeros (repeatable)

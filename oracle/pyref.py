@@ -2,9 +2,10 @@
 (oracle/_ref/libqgcmref.so: the reference's own Fortran sources, translated statement by
 statement by oracle/f2cpp.py and compiled by g++; see oracle/Makefile, target `ref`).
 
-The library keeps the reference's program structure: module variables are process-global, so
-ONE configuration lives in a process (each test case runs in a fresh worker process,
-tests/test_reference_pin.py).  `Reference` fills the module variables the Fortran main program
+The library keeps the reference's program structure: module variables and SAVEd locals are
+global to a loaded library, so every `Reference` loads its own private copy of the .so (a
+temporary file, unlinked once mapped): several configurations can coexist in one process.
+`setup` fills the module variables the Fortran main program
 would fill from input.params (src/q-gcm.F:377-452, :929-973) and then calls the reference's
 subroutines by name.
 """
@@ -22,6 +23,15 @@ def available():
     return os.path.isdir("/root/reference/src") or os.path.exists(os.path.join(REFDIR, "libqgcmref_box.so"))
 
 
+def provenance():
+    """how the library under oracle/_ref was made (written by `make ref` next to it)"""
+    try:
+        with open(os.path.join(REFDIR, "PROVENANCE.txt")) as f:
+            return f.read()
+    except OSError:
+        return "unknown"
+
+
 def build():
     """translate + compile (needs /root/reference; on a box without it the prebuilt .so is used)"""
     if os.path.isdir("/root/reference/src"):
@@ -36,7 +46,17 @@ class Reference:
         path = os.path.join(REFDIR, "libqgcmref_%s.so" % variant)
         if not os.path.exists(path):
             build()
-        self.lib = C.CDLL(path)
+        if not os.path.exists(path):
+            raise RuntimeError("%s is missing and /root/reference is not here to build it from" % path)
+        import shutil
+        import tempfile
+        fd, tmp = tempfile.mkstemp(suffix=".so", prefix="qgcmref_")
+        os.close(fd)
+        shutil.copyfile(path, tmp)
+        try:
+            self.lib = C.CDLL(tmp)
+        finally:
+            os.unlink(tmp)
         self.lib.ref_last_error.restype = C.c_char_p
         for k, v in params.items():
             if self.lib.ref_set_param(k.encode(), C.c_double(float(v))) != 0:
