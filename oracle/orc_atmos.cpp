@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY -- CPU oracle (parity unpinned, see orc_model.h).
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (pinned against the translated reference, see orc_model.h).
 // Atmosphere routines: restatement of src/qgasubs.F, src/atisubs.F, src/amlsubs.F,
 // src/vorsubs.F:396-480 (atqzbd), src/q-gcm.F:738-749, :1370-1407.
 #include <algorithm>

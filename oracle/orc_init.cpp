@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY -- CPU oracle (parity unpinned, see orc_model.h).
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (pinned against the translated reference, see orc_model.h).
 // Restatement of constr (src/conhoms.F:44-314) and homsol (src/conhoms.F:318-818),
 // and the main-loop body of src/q-gcm.F:1220-1408.
 #include <cmath>

@@ -1,6 +1,9 @@
-// TEST INFRASTRUCTURE ONLY -- CPU oracle for the Q-GCM hot path (parity UNPINNED by the
-// reference's own tests: the reference ships no golden vectors and cannot be compiled
-// in this image, see oracle/README.md).  Never linked into or imported by the product.
+// TEST INFRASTRUCTURE ONLY -- CPU oracle for the Q-GCM hot path.  Never linked into or imported
+// by the product.  Pinned: the reference ships no golden vectors and no Fortran compiler exists
+// here, so the reference's own sources are translated statement by statement to C++
+// (oracle/f2cpp.py -> oracle/_ref) and this restatement is compared with that translation after
+// every procedure call on box, channel and coupled decks (tests/test_reference_pin.py: 1e-17 ..
+// 1e-14; see oracle/README.md for what the translation does and does not cover).
 //
 // Loop-for-loop C++ restatement of the reference's Fortran step routines, same loop
 // order and expression association, compiled with -ffp-contract=off.

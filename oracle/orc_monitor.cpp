@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY -- CPU oracle (parity unpinned, see orc_model.h).
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (pinned against the translated reference, see orc_model.h).
 // Restatement of the ocean section of monnc_comp (src/monitor_diag.F:480-840) with its helpers
 // del4bx (:900-1015), del4ch (:1020-1155) and genint (:1160-1210).  Same loops, same
 // expression association (including the reference's own ugdot expression, :676-677, whose

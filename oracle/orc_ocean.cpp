@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY -- CPU oracle (parity unpinned, see orc_model.h).
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (pinned against the translated reference, see orc_model.h).
 // Ocean routines: restatement of src/qgosubs.F, src/ocisubs.F, src/omlsubs.F,
 // src/vorsubs.F (qcomp, merqcy, ocqbdy), src/intsubs.f, src/conhoms.F (ocean parts),
 // src/xfosubs.F:568-709, src/q-gcm.F:1328-1366.  All indices below are 1-based

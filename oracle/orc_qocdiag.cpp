@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY -- CPU oracle (parity unpinned, see orc_model.h).
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (pinned against the translated reference, see orc_model.h).
 // Restatement of qocdiag_out (src/qocdiag.F:303-683) without its netCDF calls: per layer the
 // vorticity tendency and its Jacobian, del-4th, del-6th and forcing/drag terms, sub-sampled
 // by nsko into the vectors the reference hands to nf_put_vara_double.

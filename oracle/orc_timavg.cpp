@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY -- CPU oracle (parity unpinned, see orc_model.h).
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (pinned against the translated reference, see orc_model.h).
 // Restatement of the running-sum accumulators of src/timavge.F: tavini (:108-273), tavatm
 // (:278-419), tavocn (:425-617) and the fork's avg_ocn_k247 (:624-660).  tavout's netCDF
 // dump stays Fortran; the sums and the contribution counts are what it reads.

@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY -- CPU oracle (parity unpinned, see orc_model.h).
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (pinned against the translated reference, see orc_model.h).
 // Restatement of the extreme-value scan and thickness check of valids
 // (src/valsubs.F:43-630) without its diagnostic print-outs.
 #include <algorithm>

@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY -- CPU oracle (parity unpinned, see orc_model.h).
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (pinned against the translated reference, see orc_model.h).
 // Coupled forcing: restatement of src/xfosubs.F:52-858 (xforc), :862-887 (fsprim),
 // :891-993 (bilint), :997-1234 (auvbcu), :1238-1621 (bcuini), :1625-1728 (wts2bb).
 // Loop order and expression association follow the Fortran; 1-based accessor macros.

@@ -215,3 +215,98 @@ def test_radiat_matches_the_translated_reference(qg, deck):
         worst = max(worst, e)
         assert e <= 1e-10, (n, e, got.tolist()[:4], want.tolist()[:4])
     print("radiat worst relative difference:", worst)
+
+
+OC_SUMS = ("txocav", "tyocav", "wpocav", "wtocav", "fmocav", "sstav", "uufo", "tufo", "utufo", "vvfo", "tvfo", "vtvfo", "pocav", "qocav", "po_avg")
+AT_SUMS = ("txatav", "tyatav", "wtatav", "fmatav", "astav", "uufa", "tufa", "utufa", "vvfa", "tvfa", "vtvfa", "patav", "qatav")
+
+
+@pytest.mark.parametrize("deck", ["box", "chan", "boxcpl", "chancpl"])
+def test_diagnostics_match_the_translated_reference(qg, pyorc, deck):
+    """SURVEY 8f rows that moved to the device: valids (src/valsubs.F:43), the running sums of
+    src/timavge.F:109-662 and monnc_comp with couroc / courat (src/monitor_diag.F:89-893, :1215-1928),
+    oracle restatement against the reference's own translated code"""
+    p = decks(qg)[deck]
+    cfg = qg.build_config(p)
+    cpu = pyorc.Oracle(cfg)
+    ref = pyref.RefModel(p, cfg)
+    amp = min(1.0, (p.nxto * p.dxo) / 4.8e6 * 4.0)
+    st = qg.synth.ocean_state(p, cfg, "random", qg.synth.SEED, amp)
+    if not p.has("ocean_only"):
+        st.update(qg.synth.atmos_state(p, cfg, "random", qg.synth.SEED + 1))
+    for k, v in st.items():
+        cpu.set_field(k, v)
+        ref.set_field(k, v)
+    coupled = not p.has("ocean_only")
+    for name in ["constr", "qcomp_ocean"] + (["qcomp_atmos"] if coupled else []) + ["xforc", "homsol"]:
+        getattr(cpu, name)()
+        getattr(ref, name)()
+
+    def ocean_step():
+        for name in (["xforc"] if coupled else []) + ["oml", "qgostep", "ocinvq", "ocqbdy"]:
+            getattr(cpu, name)()
+            getattr(ref, name)()
+
+    def atmos_step():
+        for name in ["aml", "qgastep", "atinvq", "atqzbd"]:
+            getattr(cpu, name)()
+            getattr(ref, name)()
+
+    ocean_step()
+    if coupled:
+        atmos_step()
+    # ---- running sums
+    cpu.tavini()
+    ref.ref.call("tavini")
+    ref.ref.set("nsum_ocavg", 0)
+    for _ in range(2):
+        ocean_step()
+        cpu.tavocn(); ref.ref.call("tavocn")
+        cpu.avg_ocn_k247(); ref.ref.call("avg_ocn_k247")
+        if coupled:
+            atmos_step()
+            cpu.tavatm(); ref.ref.call("tavatm")
+    for n in OC_SUMS + (AT_SUMS if coupled else ()):
+        e = rel(cpu.get_field(n), ref.get_field(n))
+        assert e <= TOL, (deck, n, e)
+    assert cpu.tav_counts()[1] == int(ref.ref.get("nsumoc")[0]) == 2
+    # ---- monnc_comp: every member of the C structs that the reference's module `monitor` also holds
+    ref.ref.call("monnc_comp")
+    from test_gpu_monitor import SCALE, scales, atmos_scales      # the rounding scales of the signed integrals
+    checked = 0
+    rep_o = cpu.monnc_ocean().as_dict()
+    sc_o = scales(cpu, p, cfg, rep_o)
+    todo = [(rep_o, lambda n, xb: sc_o[SCALE[n]] if SCALE.get(n) in sc_o else
+             (max(np.abs(np.atleast_1d(rep_o[SCALE[n]])).max(), 1e-300) if SCALE.get(n) else max(np.abs(xb).max(), 1e-300)))]
+    if coupled:
+        rep_a = cpu.monnc_atmos().as_dict()
+        sc_a = atmos_scales(cpu, p, cfg, rep_a)
+        todo.append((rep_a, lambda n, xb: max(sc_a.get(n, 0.0), np.abs(xb).max(), 1e-300)))
+    for rep, scale_of in todo:
+        for name, val in rep.items():
+            if name.startswith("reserved") or not ref.ref.has(name):
+                continue
+            want = ref.ref.get(name).astype(float)
+            got = np.atleast_1d(np.asarray(val, dtype=float))[: want.size]
+            if name in ("ocjpos", "atstpos"):
+                vname, uscale = ("ocjval", sc_o["u_scale"]) if name == "ocjpos" else ("atstval", sc_a["u_scale"])
+                for k in range(want.size):       # a zonal mean that vanishes identically leaves rounding to pick the row
+                    if np.atleast_1d(rep[vname])[k] > 1e-6 * uscale:
+                        assert got[k] == want[k], (deck, name, k)
+                checked += 1
+                continue
+            e = float(np.abs(got - want).max() / scale_of(name, want))
+            assert e <= 1e-10, (deck, name, e, got.tolist(), want.tolist())
+            checked += 1
+    assert checked >= (30 if not coupled else 55), checked
+    # ---- valids: same verdict on the healthy state and on a state whose top layer is too thin
+    ok_ref = np.array([True], dtype=np.bool_)
+    ref.ref.call("valids", ok_ref)
+    assert bool(ok_ref[0]) == bool(cpu.valids().solnok) == True      # noqa: E712
+    po = cpu.get_field("po", (p.nxpo, p.nypo, p.nlo)).copy()
+    po[: p.nxpo // 3, :, 1] += 400.0 * cfg.gpoc[0]
+    cpu.set_field("po", po)
+    ref.set_field("po", po)
+    ok_ref[0] = True
+    ref.ref.call("valids", ok_ref)
+    assert bool(ok_ref[0]) == bool(cpu.valids().solnok) == False      # noqa: E712
