@@ -167,6 +167,19 @@ int qgcm_field_size(qgcm_model *m, const char *name, int64_t *n);
  * (a field uploaded more than once before a commit keeps the last upload). */
 int qgcm_set_field_async(qgcm_model *m, const char *name, const double *host, int64_t n);
 int qgcm_commit_fields(qgcm_model *m);
+/* Restart and output I/O at PCIe speed (resave_nc writes po, pom, sst, sstm and the atmosphere's
+ * pa, pam, ast, astm, hmixa, hmixam, src/nc_subs.F:1331-1360; restart_nc reads them back,
+ * :1923-1943).  The Fortran state arrays are static module storage that lives as long as the
+ * process: qgcm_host_register page-locks such an array once (cudaHostRegister), after which every
+ * qgcm_set_field / qgcm_get_field on it is a DMA straight from / into the array.
+ * qgcm_get_fields / qgcm_set_fields move n fields with one synchronisation at the end instead of
+ * one per field (names[i], hosts[i], counts[i] as in qgcm_get_field); with registered arrays the
+ * whole transfer is one stream of back-to-back DMAs.  Unregistered (pageable) arrays work too,
+ * at the driver's staging speed. */
+int qgcm_host_register(void *host, int64_t bytes);
+int qgcm_host_unregister(void *host);
+int qgcm_get_fields(qgcm_model *m, int32_t n, const char *const *names, double *const *hosts, const int64_t *counts);
+int qgcm_set_fields(qgcm_model *m, int32_t n, const char *const *names, const double *const *hosts, const int64_t *counts);
 int qgcm_set_scalars(qgcm_model *m, const qgcm_scalars *s);
 int qgcm_get_scalars(qgcm_model *m, qgcm_scalars *s);
 int qgcm_sync(qgcm_model *m);

@@ -254,7 +254,7 @@ static qgcm_model::Field &lookup(qgcm_model *m, const char *name, int64_t n) {
   return f;
 }
 
-static void copy_field(qgcm_model *m, qgcm_model::Field &f, double *host, bool to_device) {
+static void copy_field(qgcm_model *m, qgcm_model::Field &f, double *host, bool to_device, bool sync = true) {
   if (f.ld == 0) {
     const size_t bytes = sizeof(double) * (size_t)f.nx * f.ny * f.nl;
     if (to_device) QG_CUDA(cudaMemcpyAsync(f.d, host, bytes, cudaMemcpyHostToDevice, m->stream));
@@ -274,8 +274,36 @@ static void copy_field(qgcm_model *m, qgcm_model::Field &f, double *host, bool t
                                   sizeof(double) * f.nx, f.o1 - f.o0, cudaMemcpyDeviceToHost, m->stream));
     }
   }
+  if (!sync) return;
   QG_CUDA(cudaStreamSynchronize(m->stream));
   if (!to_device) check_peer_err(m);      // never hand back state a timed-out exchange has spoilt
+}
+
+static void invalidate_graphs(qgcm_model *m);
+
+static void note_topography(qgcm_model *m, const char *name, const double *host, int64_t n) {
+  const bool oc = std::strcmp(name, "ddynoc") == 0, at = std::strcmp(name, "ddynat") == 0;
+  if (oc || at) {      // flat bottom / no orography: remember it (invert.cu skips the field)
+    bool flat = true;
+    for (int64_t i = 0; i < n && flat; ++i) flat = (host[i] == 0.0);
+    (oc ? m->ddynoc_flat : m->ddynat_flat) = flat;
+  }
+}
+
+// n fields, one synchronisation: with page-locked host arrays (qgcm_host_register) the copies are
+// back-to-back DMAs on the model's stream
+static void copy_fields(qgcm_model *m, int n, const char *const *names, double *const *hosts, const int64_t *counts, bool to_device) {
+  if (n < 0 || (n > 0 && (!names || !hosts || !counts))) throw std::runtime_error("qgcm_get_fields/qgcm_set_fields: bad argument list");
+  for (int i = 0; i < n; ++i) lookup(m, names[i], counts[i]);      // validate everything before the first byte moves
+  for (int i = 0; i < n; ++i) {
+    copy_field(m, lookup(m, names[i], counts[i]), hosts[i], to_device, false);
+    if (to_device) {
+      note_topography(m, names[i], hosts[i], counts[i]);
+      if (std::strncmp(names[i], "ddyn", 4) == 0) invalidate_graphs(m);
+    }
+  }
+  QG_CUDA(cudaStreamSynchronize(m->stream));
+  if (!to_device) check_peer_err(m);
 }
 
 void launch_xforc(qgcm_model *m);
@@ -311,8 +339,8 @@ static void set_field_async(qgcm_model *m, const char *name, const double *host,
   // a field uploaded twice before one commit overwrites its shadow buffer (same copy stream, in
   // order) and is swapped exactly once
   if (std::find(m->pending.begin(), m->pending.end(), name) == m->pending.end()) m->pending.push_back(name);
-  if (std::strcmp(name, "ddynoc") == 0) m->ddynoc_flat = false;     // contents unknown until inspected: read the field
-  if (std::strcmp(name, "ddynat") == 0) m->ddynat_flat = false;
+  if (std::strcmp(name, "ddynoc") == 0) { m->ddynoc_flat = false; invalidate_graphs(m); }     // contents unknown until inspected: read the field
+  if (std::strcmp(name, "ddynat") == 0) { m->ddynat_flat = false; invalidate_graphs(m); }
 }
 static void commit_fields(qgcm_model *m) {
   if (m->pending.empty()) return;
@@ -323,19 +351,81 @@ static void commit_fields(qgcm_model *m) {
   QG_CUDA(cudaEventRecord(m->ev_step, m->stream));   // everything that reads the retired buffers is before this point
 }
 
-static void ocean_step(qgcm_model *m) {
-  if (m->nranks > 1) { slab_ocean_step(ranks_of(m)); return; }
+static void ocean_step_eager(qgcm_model *m) {
   launch_oml(m);
   launch_qgostep(m);
   launch_ocinvq(m);
   launch_ocqbdy(m, m->F("qo"), m->F("po"));
 }
-static void atmos_step(qgcm_model *m) {
+static void atmos_step_eager(qgcm_model *m) {
   launch_aml(m);
   launch_qgastep(m);
   launch_atinvq(m);
   launch_atqzbd(m, m->F("qa"), m->F("pa"));
 }
+
+// ---- whole steps as CUDA graphs (single GPU) ----
+static std::vector<double *> pointer_state(qgcm_model *m) {
+  std::vector<double *> v;
+  for (auto &kv : m->fields) v.push_back(kv.second.d);
+  v.push_back(m->sstnew); v.push_back(m->astnew); v.push_back(m->hmnew);
+  return v;
+}
+static void set_pointer_state(qgcm_model *m, const std::vector<double *> &v) {
+  size_t i = 0;
+  for (auto &kv : m->fields) kv.second.d = v[i++];
+  m->sstnew = v[i++]; m->astnew = v[i++]; m->hmnew = v[i++];
+}
+// a captured step bakes in everything the launch code read on the host: drop the graphs whenever
+// such state may have changed outside a step (tables, flags, communicators)
+static void invalidate_graphs(qgcm_model *m) {
+  for (auto &kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
+  m->graphs.clear();
+}
+// kind: 0 atmosphere step, 1 xforc + ocean step + atmosphere step (coupled), 2 ocean step (ocean only)
+template <class Body>
+static void run_graphed(qgcm_model *m, int kind, Body body) {
+  static const bool off = env_int("QGCM_GRAPH", 1) == 0;
+  // the first steps run eagerly: lazily built plans and function attributes are set up in them
+  if (off || m->prof || m->nranks > 1 || m->eager_steps[kind] < 2) {
+    m->eager_steps[kind]++;
+    body();
+    return;
+  }
+  const std::vector<double *> before = pointer_state(m);
+  std::string key(1, (char)('0' + kind));
+  key.append(reinterpret_cast<const char *>(before.data()), before.size() * sizeof(double *));
+  auto it = m->graphs.find(key);
+  if (it == m->graphs.end()) {
+    const int64_t l0 = m->launches;
+    cudaGraph_t g = nullptr;
+    QG_CUDA(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      body();
+    } catch (...) {
+      cudaStreamEndCapture(m->stream, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    QG_CUDA(cudaStreamEndCapture(m->stream, &g));
+    qgcm_model::StepGraph sg;
+    QG_CUDA(cudaGraphInstantiate(&sg.exec, g, 0));
+    QG_CUDA(cudaGraphDestroy(g));
+    sg.after = pointer_state(m);
+    sg.launches = m->launches - l0;
+    m->launches = l0;
+    it = m->graphs.emplace(key, sg).first;
+  }
+  QG_CUDA(cudaGraphLaunch(it->second.exec, m->stream));
+  set_pointer_state(m, it->second.after);
+  m->launches += it->second.launches;
+}
+
+static void ocean_step(qgcm_model *m) {
+  if (m->nranks > 1) { slab_ocean_step(ranks_of(m)); return; }
+  run_graphed(m, 2, [m] { ocean_step_eager(m); });
+}
+static void atmos_step(qgcm_model *m) { run_graphed(m, 0, [m] { atmos_step_eager(m); }); }
 
 }  // namespace qg
 
@@ -365,6 +455,7 @@ int qgcm_destroy(qgcm_model *m) {
   }
   m->peers.clear();
   peer_close(m);
+  for (auto &kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
   for (void *p : m->allocs) cudaFree(p);
   if (m->h_peer_err) cudaFreeHost(m->h_peer_err);
   if (m->nccl) { try { nccl_destroy(m); } catch (...) {} }
@@ -380,13 +471,22 @@ int qgcm_field_size(qgcm_model *m, const char *name, int64_t *n) {
 int qgcm_set_field(qgcm_model *m, const char *name, const double *host, int64_t n) {
   QG_TRY({
     copy_field(m, lookup(m, name, n), const_cast<double *>(host), true);
-    const bool oc = std::strcmp(name, "ddynoc") == 0, at = std::strcmp(name, "ddynat") == 0;
-    if (oc || at) {      // flat bottom / no orography: remember it (invert.cu skips the field)
-      bool flat = true;
-      for (int64_t i = 0; i < n && flat; ++i) flat = (host[i] == 0.0);
-      (oc ? m->ddynoc_flat : m->ddynat_flat) = flat;
-    }
+    note_topography(m, name, host, n);
+    if (std::strncmp(name, "ddyn", 4) == 0) invalidate_graphs(m);      // the flat-bottom flag is baked into captured steps
   });
+}
+int qgcm_host_register(void *host, int64_t bytes) {
+  QG_TRY({
+    if (!host || bytes <= 0) throw std::runtime_error("qgcm_host_register: bad range");
+    QG_CUDA(cudaHostRegister(host, (size_t)bytes, cudaHostRegisterPortable));
+  });
+}
+int qgcm_host_unregister(void *host) { QG_TRY(QG_CUDA(cudaHostUnregister(host))); }
+int qgcm_get_fields(qgcm_model *m, int32_t n, const char *const *names, double *const *hosts, const int64_t *counts) {
+  QG_TRY(copy_fields(m, n, names, hosts, counts, false));
+}
+int qgcm_set_fields(qgcm_model *m, int32_t n, const char *const *names, const double *const *hosts, const int64_t *counts) {
+  QG_TRY(copy_fields(m, n, names, const_cast<double *const *>(hosts), counts, true));
 }
 int qgcm_get_field(qgcm_model *m, const char *name, double *host, int64_t n) {
   QG_TRY(copy_field(m, lookup(m, name, n), host, false));
@@ -409,8 +509,8 @@ int qgcm_sync(qgcm_model *m) {
   });
 }
 
-int qgcm_constr(qgcm_model *m) { QG_TRY(launch_constr(m)); }
-int qgcm_homsol(qgcm_model *m) { QG_TRY(launch_homsol(m)); }
+int qgcm_constr(qgcm_model *m) { QG_TRY(invalidate_graphs(m); launch_constr(m)); }
+int qgcm_homsol(qgcm_model *m) { QG_TRY(invalidate_graphs(m); launch_homsol(m)); }
 int qgcm_qcomp_ocean(qgcm_model *m) {
   QG_TRY(if (m->nranks > 1) { slab_qcomp_ocean(ranks_of(m)); } else {
          launch_qcomp(m, true, m->F("qo"), m->F("po")); launch_qcomp(m, true, m->F("qom"), m->F("pom"));
@@ -425,6 +525,7 @@ int qgcm_helmholtz(qgcm_model *m, int which, double *wrk, const double *b) {
   QG_TRY({
     const bool atmos = which != 0;
     if (atmos ? !m->has_atmos : !m->has_ocean) throw std::runtime_error("qgcm_helmholtz: grid not present");
+    invalidate_graphs(m);
     const Grid &g = atmos ? m->ga : m->go;
     HelmPlan &hp = atmos ? m->hpa : m->hpo;
     const LayerConsts &lc = atmos ? m->la : m->lo;
@@ -482,15 +583,21 @@ int qgcm_run(qgcm_model *m, int64_t nt_first, int64_t nt_last) {
     const int nstr = m->cfg.nstr;
     for (int64_t nt = nt_first; nt <= nt_last; ++nt) {
       const bool ocstep = (nstr == 1) ? true : (nt % nstr == 1);
-      if (ocstep) {
-        if (m->has_atmos) launch_xforc(m);
-        if (m->has_ocean) {
-          ocean_step(m);
-          if (m->flags & QGCM_OCNC_AVG_K247)      // src/q-gcm.F:1250-1252; every rank of a loopback group
-            for (qgcm_model *r : ranks_of(m)) launch_avg_ocn_k247(r);
+      if (ocstep && m->has_atmos && m->has_ocean && m->nranks == 1) {
+        // coupled: xforc + ocean step + this nt's atmosphere step as one graph (67 launches)
+        run_graphed(m, 1, [m] { launch_xforc(m); ocean_step_eager(m); atmos_step_eager(m); });
+        if (m->flags & QGCM_OCNC_AVG_K247) launch_avg_ocn_k247(m);      // src/q-gcm.F:1250-1252 (po is final after the ocean step)
+      } else {
+        if (ocstep) {
+          if (m->has_atmos) launch_xforc(m);
+          if (m->has_ocean) {
+            ocean_step(m);
+            if (m->flags & QGCM_OCNC_AVG_K247)      // src/q-gcm.F:1250-1252; every rank of a loopback group
+              for (qgcm_model *r : ranks_of(m)) launch_avg_ocn_k247(r);
+          }
         }
+        if (m->has_atmos) atmos_step(m);
       }
-      if (m->has_atmos) atmos_step(m);
       if (m->has_ocean && ((nt - 1) % (25 * (int64_t)nstr) == 0)) slab_tlavg_ocean(ranks_of(m));
       if (m->has_atmos && ((nt - 1) % 100 == 0)) launch_tlavg_atmos(m);
     }
@@ -547,7 +654,7 @@ int qgcm_profile(qgcm_model *m, int enable) {
     QG_CUDA(cudaStreamSynchronize(m->stream));
     for (auto &r : m->prof_recs) { m->prof_pool.push_back(r.e0); m->prof_pool.push_back(r.e1); }
     m->prof_recs.clear();
-    m->prof = enable != 0;
+    m->prof = enable != 0;      // profiled steps are launched kernel by kernel (run_graphed)
   });
 }
 

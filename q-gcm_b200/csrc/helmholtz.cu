@@ -480,6 +480,7 @@ struct Dst3Args {
   const double *ddyn;       // DST_FUSED_F: topography term of the bottom layer, null over a flat bottom
   const double *hom;        // DST_FUSED_I: ochom [nl-1][nyp][ld]
   const double *coef;       // DST_FUSED_I: device hclco[nl-1]
+  int wall_s, wall_n;       // DST_FUSED_I: this grid holds the southern / northern wall row (written by block 0)
   double ctm2l[NLMAX * NLMAX];
   const double2 *s1base;    // [L1][2]  (2 sin, 2 cos) of pi*(2t)/N and pi*(2t+1)/N
   const double2 *tw2;       // [R2-1][R1] twiddles of pass 2
@@ -741,6 +742,20 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       prev_slot = mode * a.nyp + (r + a.row0);
     }
   }
+  if (MODE == DST_FUSED_I && blockIdx.x == 0) {
+    // wall rows of the new pressure: the inhomogeneous solution vanishes there, the homogeneous
+    // solutions do not (src/ocisubs.F:377-401 on rows 1 and nypo)
+    for (int side = 0; side < 2; ++side) {
+      if (!(side == 0 ? a.wall_s : a.wall_n)) continue;
+      const size_t ro = (size_t)(side == 0 ? 0 : a.nyp - 1) * a.ld;
+      for (int i = t0; i < a.nxp; i += 256)
+        for (int k = 0; k < a.nl; ++k) {
+          double e = 0.0;
+          for (int mm = 1; mm < a.nl; ++mm) e = fma(a.ctm2l[mm + a.nl * k], a.coef[mm - 1] * a.hom[(size_t)(mm - 1) * a.lsz + ro + i], e);
+          a.dst[(size_t)k * a.lsz + ro + i] = e;
+        }
+    }
+  }
   if (INV) {
     __syncthreads();
     if (t0 == 0 && prev_slot >= 0) {
@@ -881,165 +896,202 @@ struct Mix3 {
   double *spec;           // [nl][nchunk * gridDim.x] partial integrals (FINAL)
 };
 
-// One block = TC wavenumber columns x NL "parts" of one chunk.  Part p of a column
-//   1. loads rows j = p, p+NL, ... of ALL layers (the loads of a warp are 32 neighbouring
-//      columns of one row: coalesced), projects them onto the modes and parks the NL modal
-//      right-hand sides of each row in shared memory ([mode][row][column], conflict free);
-//   2. owns mode p of its column:
-//      FINAL = false: one sweep over the parked values gives the last value of the chunk-local
-//        solution (where the forward elimination ends) and the first one (the dot product with
-//        the first row of the inverse, which by symmetry is the chunk's left spike over -a);
-//      FINAL = true : Thomas solve in place in shared memory (the elimination reciprocals come
-//        from the L2-resident table, fetched a group of rows ahead of the recurrence);
-//   3. FINAL: projects rows j = p, p+NL, ... of all modes back onto the layers and stores them.
-// The solve keeps no row in registers, so four blocks (24 warps) fit an SM and the load phase of
-// one block overlaps the recurrences of the others.
-constexpr size_t tri3_smem = sizeof(double) * 3 * TRI_L * 64;      // 48 KB for NL = 3
+// Work item = a tile of 2*TRI3_TP wavenumber columns x one chunk; a thread is part p (of NL) of one
+// column PAIR (even column first: rows are 128-byte aligned, so every global and shared access
+// is a 16-byte one -- the kernel is bound by the number of load/store instructions, not by
+// bytes).  Persistent blocks (two per SM) take contiguous ranges of the chunk-fastest item list,
+// so a block stays on one column tile for many chunks and its table reads hit L1.  Per item
+//   1. part p loads rows j = p, p+NL, ... of ALL layers of its pair, projects them onto the
+//      modes and parks them in shared memory ([mode][row][pair], conflict free);
+//   2. part p owns mode p of its pair (two interleaved recurrences):
+//      FINAL = false: the last value of the chunk-local solution is where the forward
+//        elimination ends; the first value is where the same elimination ends when it runs over
+//        the rows in reverse order (symmetric Toeplitz system: same reciprocals);
+//      FINAL = true : Thomas solve in place in shared memory, reciprocals from the L2-resident
+//        table a group of rows ahead of the recurrence;
+//   3. FINAL: part p projects rows j = p, p+NL, ... of all modes back onto the layers and stores
+//      them, and the block leaves its share of the modal area integrals.
+// Columns outside the solved range (the wall columns 0 and nxp-1 of the box, the row padding)
+// ride along with zero reciprocals and are never stored.
+constexpr int TRI3_TP = 64;                                                    // column pairs per tile (32 with four blocks per SM measured slower)
+constexpr int TRI3_BLK = 2;                                                    // blocks per SM (96 KB of shared memory each)
+constexpr size_t tri3_smem = sizeof(double2) * 3 * TRI_L * TRI3_TP;            // 96 KB for NL = 3
+__device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 template <int NL, bool FINAL>
-__global__ void __launch_bounds__(64 * NL, 4) k_tri3(TriArgs t, Mix3 mx) {
-  constexpr int TC = 64, G = 8;
+__global__ void __launch_bounds__(TRI3_TP * NL, TRI3_BLK) k_tri3(TriArgs t, Mix3 mx, int ntx, int order) {
+  constexpr int TP = TRI3_TP, G = 8;
   static_assert(TRI_L % G == 0, "row groups");
-  extern __shared__ double us_raw[];
-  double (*us)[TRI_L][TC] = reinterpret_cast<double (*)[TRI_L][TC]>(us_raw);      // [NL][TRI_L][TC]
-  __shared__ double red[NL][2];
-  const int tc = threadIdx.x % TC, p = threadIdx.x / TC;      // warps are uniform in p
-  const int s = blockIdx.x * TC + tc;
-  const int c = blockIdx.y;
-  const bool live = s < t.nk;
-  const int col = t.koff + (live ? s : 0);
-  const bool lastc = (c == t.nchunk - 1);
-  const int len = lastc ? t.lastlen : TRI_L;
+  extern __shared__ double2 us_raw2[];
+  double2 (*us)[TRI_L][TP] = reinterpret_cast<double2 (*)[TRI_L][TP]>(us_raw2);      // [NL][TRI_L][TP]
+  __shared__ double red[NL][TRI3_TP / 32];
+  const int tp = threadIdx.x % TP, p = threadIdx.x / TP;      // warps are uniform in p
   const double a = t.a;
   const int ld = t.ld;
-  double *__restrict__ base = t.wrk + (size_t)(t.row0 + c * TRI_L) * ld + col;
-  // ---- 1. layers -> modes for this part's rows
+  const int nitems = ntx * t.nchunk;
   constexpr int NJ = (TRI_L + NL - 1) / NL;
+  const int per = (nitems + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int first = order ? (int)blockIdx.x : blockIdx.x * per, last = order ? nitems : min(first + per, nitems);
+  const int step = order ? (int)gridDim.x : 1;
+  for (int item = first; item < last; item += step) {
+    // order 0: chunk-fastest items in contiguous ranges (a block walks down one column tile);
+    // order 1: tile-fastest items, strided (at any time the blocks work on neighbouring tiles of a
+    // few chunk rows, i.e. on one narrow band of rows per layer)
+    const int bx = order ? item % ntx : item / t.nchunk, c = order ? item / ntx : item - bx * t.nchunk;
+    int c0 = 2 * (bx * TP + tp);                               // even column of the pair
+    const bool inrow = c0 < ld;
+    if (!inrow) c0 = 0;
+    const bool live0 = inrow && c0 >= t.koff && c0 < t.koff + t.nk, live1 = inrow && c0 + 1 >= t.koff && c0 + 1 < t.koff + t.nk;
+    const bool lastc = (c == t.nchunk - 1);
+    const int len = lastc ? t.lastlen : TRI_L;
+    double *__restrict__ base = t.wrk + (size_t)(t.row0 + c * TRI_L) * ld + c0;
+    // ---- 1. layers -> modes for this part's rows
 #pragma unroll
-  for (int jj = 0; jj < NJ; ++jj) {
-    const int j = p + jj * NL;
-    if (j < TRI_L) {
-      double sk[NL];
-      const size_t ro = (size_t)min(j, len - 1) * ld;      // rows >= len: harmless duplicates of the last row
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int j = p + jj * NL;
+      if (j < TRI_L) {
+        double2 sk[NL];
+        const size_t ro = (size_t)min(j, len - 1) * ld;      // rows >= len: harmless duplicates of the last row
 #pragma unroll
-      for (int k = 0; k < NL; ++k) sk[k] = base[(size_t)k * t.lsz + ro];
+        for (int k = 0; k < NL; ++k) sk[k] = *reinterpret_cast<const double2 *>(base + (size_t)k * t.lsz + ro);
 #pragma unroll
-      for (int m = 0; m < NL; ++m) {
-        double acc = 0.0;
+        for (int m = 0; m < NL; ++m) {
+          double ax = 0.0, ay = 0.0;
 #pragma unroll
-        for (int k = 0; k < NL; ++k) acc = acc + mx.ctl2m[k + NL * m] * sk[k];
-        us[m][j][tc] = mx.f0 * acc;
-      }
-    }
-  }
-  __syncthreads();
-  // ---- 2. mode p of this column
-  const int m = p;
-  const double *__restrict__ bi = t.binv + ((size_t)m * TRI_L) * ld + col;
-  const size_t fb = ((size_t)m * 2 * t.nchunk) * ld + col;
-  if (!FINAL) {
-    const double *__restrict__ sp = (lastc ? t.vll : t.vl) + ((size_t)m * TRI_L) * ld + col;
-    double d = 0.0, f = 0.0;
-    double bq[G], vq[G];
-#pragma unroll
-    for (int u = 0; u < G; ++u) { bq[u] = __ldg(bi + (size_t)u * ld); vq[u] = __ldg(sp + (size_t)u * ld); }
-#pragma unroll
-    for (int g = 0; g < TRI_L / G; ++g) {
-      double bn[G], vn[G];
-#pragma unroll
-      for (int u = 0; u < G; ++u) {
-        const int j = min((g + 1) * G + u, TRI_L - 1);
-        bn[u] = __ldg(bi + (size_t)j * ld);
-        vn[u] = __ldg(sp + (size_t)j * ld);
-      }
-#pragma unroll
-      for (int u = 0; u < G; ++u) {
-        const int j = g * G + u;
-        const double r = us[m][j][tc];
-        const double dn = (r - a * d) * bq[u];
-        d = (j < len) ? dn : d;
-        f = fma((j < len) ? vq[u] : 0.0, r, f);
-      }
-#pragma unroll
-      for (int u = 0; u < G; ++u) { bq[u] = bn[u]; vq[u] = vn[u]; }
-    }
-    if (live && (t.nchunk > 1 || t.nranks > 1)) {
-      t.fg[fb + (size_t)c * ld] = -f / a;                    // f_c : first row of the chunk-local solution
-      t.fg[fb + (size_t)(t.nchunk + c) * ld] = d;            // g_c : its last row
-    }
-    return;
-  }
-  {
-    if (t.use_yx) {
-      const double yp = t.yx[fb + (size_t)c * ld], xn = t.yx[fb + (size_t)(t.nchunk + c) * ld];
-      us[m][0][tc] -= a * yp;
-      us[m][len - 1][tc] = fma(-a, xn, us[m][len - 1][tc]);
-    }
-    double bq[G];
-#pragma unroll
-    for (int u = 0; u < G; ++u) bq[u] = __ldg(bi + (size_t)u * ld);
-    double prev = 0.0;
-#pragma unroll
-    for (int g = 0; g < TRI_L / G; ++g) {
-      double bn[G];
-#pragma unroll
-      for (int u = 0; u < G; ++u) bn[u] = __ldg(bi + (size_t)min((g + 1) * G + u, TRI_L - 1) * ld);
-#pragma unroll
-      for (int u = 0; u < G; ++u) {
-        const int j = g * G + u;
-        prev = (us[m][j][tc] - a * prev) * bq[u];
-        us[m][j][tc] = prev;      // rows >= len hold values nobody reads
-      }
-#pragma unroll
-      for (int u = 0; u < G; ++u) bq[u] = bn[u];
-    }
-    // back substitution from row len-1 downwards, times ftnorm on the way out (src/ocisubs.F:484-487)
-    const double fn = t.ftnorm;
-    double nxt = us[m][len - 1][tc];
-    double sm = fn * nxt;
-    us[m][len - 1][tc] = fn * nxt;
-#pragma unroll
-    for (int u = 0; u < G; ++u) bq[u] = __ldg(bi + (size_t)(TRI_L - 1 - u) * ld);
-#pragma unroll
-    for (int g = 0; g < TRI_L / G; ++g) {
-      double bn[G];
-#pragma unroll
-      for (int u = 0; u < G; ++u) bn[u] = __ldg(bi + (size_t)max(TRI_L - 1 - (g + 1) * G - u, 0) * ld);
-#pragma unroll
-      for (int u = 0; u < G; ++u) {
-        const int j = TRI_L - 1 - g * G - u;
-        if (j < len - 1) {
-          nxt = us[m][j][tc] - (a * bq[u]) * nxt;
-          us[m][j][tc] = fn * nxt;
-          sm += fn * nxt;
+          for (int k = 0; k < NL; ++k) {
+            ax = ax + mx.ctl2m[k + NL * m] * sk[k].x;
+            ay = ay + mx.ctl2m[k + NL * m] * sk[k].y;
+          }
+          us[m][j][tp] = make_double2(live0 ? mx.f0 * ax : 0.0, live1 ? mx.f0 * ay : 0.0);
         }
       }
-#pragma unroll
-      for (int u = 0; u < G; ++u) bq[u] = bn[u];
     }
-    // the block's share of the area integral of mode p: fixed-order reduction over its 64 columns
-    double v = live ? __ldg(mx.wsum + col) * sm : 0.0;
+    __syncthreads();
+    // ---- 2. mode p of this pair
+    const int m = p;
+    const double *__restrict__ bi = t.binv + ((size_t)m * TRI_L) * ld + c0;
+    const size_t fb = ((size_t)m * 2 * t.nchunk) * ld + c0;
+    if (!FINAL) {
+      double2 d = make_double2(0.0, 0.0), e = make_double2(0.0, 0.0);
+      double2 bq[G];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((tc & 31) == 0) red[p][tc >> 5] = v;
-  }
-  __syncthreads();
-  if (tc == 0) mx.spec[(size_t)p * (t.nchunk * gridDim.x) + (size_t)c * gridDim.x + blockIdx.x] = red[p][0] + red[p][1];
-  // ---- 3. modes -> layers for this part's rows
+      for (int u = 0; u < G; ++u) bq[u] = ldg2(bi + (size_t)u * ld);
 #pragma unroll
-  for (int jj = 0; jj < NJ; ++jj) {
-    const int j = p + jj * NL;
-    if (j < len) {
-      double um[NL];
+      for (int g = 0; g < TRI_L / G; ++g) {
+        double2 bn[G];
 #pragma unroll
-      for (int mm = 0; mm < NL; ++mm) um[mm] = us[mm][j][tc];
+        for (int u = 0; u < G; ++u) bn[u] = ldg2(bi + (size_t)min((g + 1) * G + u, TRI_L - 1) * ld);
 #pragma unroll
-      for (int k = 0; k < NL; ++k) {
-        double acc = 0.0;
+        for (int u = 0; u < G; ++u) {
+          const int j = g * G + u;
+          const double2 r = us[m][j][tp], rr = us[m][max(len - 1 - j, 0)][tp];
+          if (j < len) {
+            d = make_double2((r.x - a * d.x) * bq[u].x, (r.y - a * d.y) * bq[u].y);
+            e = make_double2((rr.x - a * e.x) * bq[u].x, (rr.y - a * e.y) * bq[u].y);
+          }
+        }
 #pragma unroll
-        for (int mm = 0; mm < NL; ++mm) acc = acc + mx.ctm2l[mm + NL * k] * um[mm];
-        if (live) base[(size_t)k * t.lsz + (size_t)j * ld] = acc;
+        for (int u = 0; u < G; ++u) bq[u] = bn[u];
+      }
+      if (inrow && (t.nchunk > 1 || t.nranks > 1)) {
+        *reinterpret_cast<double2 *>(t.fg + fb + (size_t)c * ld) = e;                      // f_c : first row of the chunk-local solution
+        *reinterpret_cast<double2 *>(t.fg + fb + (size_t)(t.nchunk + c) * ld) = d;         // g_c : its last row
+      }
+      __syncthreads();      // the buffer is reused by the next item
+      continue;
+    }
+    {
+      if (t.use_yx) {
+        const double2 yp = ldg2(t.yx + fb + (size_t)c * ld), xn = ldg2(t.yx + fb + (size_t)(t.nchunk + c) * ld);
+        double2 v0 = us[m][0][tp];
+        v0.x -= a * yp.x; v0.y -= a * yp.y;
+        us[m][0][tp] = v0;
+        double2 v1 = us[m][len - 1][tp];
+        v1.x = fma(-a, xn.x, v1.x); v1.y = fma(-a, xn.y, v1.y);
+        us[m][len - 1][tp] = v1;
+      }
+      double2 bq[G];
+#pragma unroll
+      for (int u = 0; u < G; ++u) bq[u] = ldg2(bi + (size_t)u * ld);
+      double2 prev = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int g = 0; g < TRI_L / G; ++g) {
+        double2 bn[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) bn[u] = ldg2(bi + (size_t)min((g + 1) * G + u, TRI_L - 1) * ld);
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+          const int j = g * G + u;
+          const double2 r = us[m][j][tp];
+          prev = make_double2((r.x - a * prev.x) * bq[u].x, (r.y - a * prev.y) * bq[u].y);
+          us[m][j][tp] = prev;      // rows >= len hold values nobody reads
+        }
+#pragma unroll
+        for (int u = 0; u < G; ++u) bq[u] = bn[u];
+      }
+      // back substitution from row len-1 downwards, times ftnorm on the way out (src/ocisubs.F:484-487)
+      const double fn = t.ftnorm;
+      double2 nxt = us[m][len - 1][tp];
+      double2 sm = make_double2(fn * nxt.x, fn * nxt.y);
+      us[m][len - 1][tp] = sm;
+#pragma unroll
+      for (int u = 0; u < G; ++u) bq[u] = ldg2(bi + (size_t)(TRI_L - 1 - u) * ld);
+#pragma unroll
+      for (int g = 0; g < TRI_L / G; ++g) {
+        double2 bn[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) bn[u] = ldg2(bi + (size_t)max(TRI_L - 1 - (g + 1) * G - u, 0) * ld);
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+          const int j = TRI_L - 1 - g * G - u;
+          if (j < len - 1) {
+            const double2 r = us[m][j][tp];
+            nxt = make_double2(r.x - (a * bq[u].x) * nxt.x, r.y - (a * bq[u].y) * nxt.y);
+            const double2 o = make_double2(fn * nxt.x, fn * nxt.y);
+            us[m][j][tp] = o;
+            sm.x += o.x; sm.y += o.y;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < G; ++u) bq[u] = bn[u];
+      }
+      // the block's share of the area integral of mode p: fixed-order reduction over its columns
+      const double2 w = ldg2(mx.wsum + c0);
+      double v = inrow ? (w.x * sm.x + w.y * sm.y) : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if ((tp & 31) == 0) red[p][tp >> 5] = v;
+    }
+    __syncthreads();
+    if (tp == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < TRI3_TP / 32; ++w) tot += red[p][w];
+      mx.spec[(size_t)p * nitems + item] = tot;
+    }
+    // ---- 3. modes -> layers for this part's rows
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int j = p + jj * NL;
+      if (j < len) {
+        double2 um[NL];
+#pragma unroll
+        for (int mm = 0; mm < NL; ++mm) um[mm] = us[mm][j][tp];
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+          double ax = 0.0, ay = 0.0;
+#pragma unroll
+          for (int mm = 0; mm < NL; ++mm) {
+            ax = ax + mx.ctm2l[mm + NL * k] * um[mm].x;
+            ay = ay + mx.ctm2l[mm + NL * k] * um[mm].y;
+          }
+          double *dst = base + (size_t)k * t.lsz + (size_t)j * ld;
+          if (live0 && live1) *reinterpret_cast<double2 *>(dst) = make_double2(ax, ay);
+          else if (live0) dst[0] = ax;
+          else if (live1) dst[1] = ay;
+        }
       }
     }
+    __syncthreads();      // the buffer is reused by the next item
   }
 }
 
@@ -1350,6 +1402,7 @@ static void dst3_launch(qgcm_model *md, HelmPlan &hp, double *wrk, size_t lsz, i
   a.s1base = hp.s1base; a.tw2 = hp.tw2; a.tw3base = hp.tw3base; a.wnbase = hp.wnbase;
   for (int i = 0; i < 16; ++i) { a.c1[i] = hp.c1[i]; a.s1[i] = hp.s1c[i]; a.wnr[i] = hp.wnr[i]; }
   a.nl = nmodes; a.kbot = nmodes - 1;
+  a.wall_s = hp.wall_s; a.wall_n = hp.wall_n;
   if (fz) {
     a.src = fz->q; a.dst = fz->pnew; a.yrel = fz->yrel; a.beta = fz->beta; a.ddyn = fz->ddyn; a.hom = fz->hom; a.coef = fz->coef;
     for (int i = 0; i < NLMAX * NLMAX; ++i) a.ctm2l[i] = fz->ctm2l[i];
@@ -1513,9 +1566,11 @@ void helm_plan_create(qgcm_model *md, HelmPlan &hp, const Grid &g, int kind, con
     for (int k = 1; k < hp.n; k += 2) ws[k] = (double)(2.0L * cosl(PI_Q * k / (2.0L * hp.n)) / sinl(PI_Q * k / (2.0L * hp.n)));
     hp.wsum = (double *)dalloc(md, sizeof(double) * row);
     QG_CUDA(cudaMemcpy(hp.wsum, ws.data(), sizeof(double) * row, cudaMemcpyHostToDevice));
-    hp.nspec = hp.nchunk * ((hp.nk + 63) / 64);
+    hp.nspec = hp.nchunk * ((hp.koff + hp.nk + 2 * TRI3_TP - 1) / (2 * TRI3_TP));
     QG_CUDA(cudaFuncSetAttribute(k_tri3<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri3_smem));
     QG_CUDA(cudaFuncSetAttribute(k_tri3<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri3_smem));
+    // (no carve-out preference: forcing the largest shared-memory carve-out shrinks L1, which these
+    // kernels and k_dst3 use for their L2-resident tables -- measured 10-25 % slower)
     hp.spec = (double *)dalloc(md, sizeof(double) * nmodes * hp.nspec);
   }
   for (int r = 0; r < 16; ++r) hp.slab_rows[r] = 0;
@@ -1632,30 +1687,10 @@ bool helm_can_fuse(const qgcm_model *m, const HelmPlan &hp, int nl) {
   return !off && hp.kind == 0 && hp.fast && nl == 3 && hp.nmodes == 3 && hp.spec;
 }
 
-// wall rows of the new pressure: the inhomogeneous solution vanishes there, the homogeneous
-// solutions do not (src/ocisubs.F:377-401 on rows 1 and nypo)
-__global__ void k_hom_walls(double *pnew, const double *hom, const double *coef, Mix3 mx, int nl, size_t lsz, int ld, int nyp, int nxp,
-                            int south, int north) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nxp) return;
-  for (int side = 0; side < 2; ++side) {
-    if (!(side == 0 ? south : north)) continue;
-    const size_t idx = (size_t)(side == 0 ? 0 : nyp - 1) * ld + i;
-    for (int k = 0; k < nl; ++k) {
-      double e = 0.0;
-      for (int mm = 1; mm < nl; ++mm) e = fma(mx.ctm2l[mm + nl * k], coef[mm - 1] * hom[(size_t)(mm - 1) * lsz + idx], e);
-      pnew[(size_t)k * lsz + idx] = e;
-    }
-  }
-}
-
 // after the constraint algebra: spectral layer rows -> pressure layers (+ homogeneous solutions)
 void helm_fused_inverse(qgcm_model *md, HelmPlan &hp, double *wrk, int nl, const FusedInv &fz) {
   const size_t lsz = (size_t)hp.ld * hp.nyp;
-  dst3_launch(md, hp, wrk, lsz, nl, DST_FUSED_I, &fz);
-  if (hp.wall_s || hp.wall_n)
-    QG_LAUNCH(md, "k_hom_walls", (hp.nxp + 255) / 256, 256, 0, k_hom_walls, fz.pnew, fz.hom, fz.coef, mix3_args(hp, fz), nl, lsz, hp.ld,
-              hp.nyp, hp.nxp, hp.wall_s, hp.wall_n);
+  dst3_launch(md, hp, wrk, lsz, nl, DST_FUSED_I, &fz);      // block 0 also writes the wall rows
   QG_CUDA(cudaGetLastError());
 }
 
@@ -1673,7 +1708,8 @@ void helm_solve_a(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes, const F
   dim3 gl((hp.nk + 127) / 128, hp.nchunk, nmodes), gr((hp.nk + 127) / 128, nmodes);
   if (hp.nchunk > 1 || hp.nranks > 1) {
     if (fz) {
-      QG_LAUNCH(md, "k_tri_fg", dim3((hp.nk + 63) / 64, hp.nchunk), 192, tri3_smem, (k_tri3<3, false>), t, mix3_args(hp, *fz));
+      const int ntx = (hp.koff + hp.nk + 2 * TRI3_TP - 1) / (2 * TRI3_TP);      // tiles start at column 0
+      QG_LAUNCH(md, "k_tri_fg", std::min(ntx * hp.nchunk, hp.fast_grid / 2 * TRI3_BLK), 3 * TRI3_TP, tri3_smem, (k_tri3<3, false>), t, mix3_args(hp, *fz), ntx, env_int("QGCM_TRI_ORDER", 1));
     } else {
       auto kfg = k_tri_local<false>;
       QG_LAUNCH(md, "k_tri_fg", gl, 128, 0, kfg, t);
@@ -1716,7 +1752,8 @@ void helm_solve_b(qgcm_model *md, HelmPlan &hp, double *wrk, int nmodes, const F
   if (fz) {
     // fused: the final chunk solves project back onto the layers and leave the modal integrals;
     // the inverse transform follows the constraint algebra (helm_fused_inverse)
-    QG_LAUNCH(md, "k_tri_local", dim3((hp.nk + 63) / 64, hp.nchunk), 192, tri3_smem, (k_tri3<3, true>), t, mix3_args(hp, *fz));
+    const int ntx = (hp.koff + hp.nk + 2 * TRI3_TP - 1) / (2 * TRI3_TP);
+    QG_LAUNCH(md, "k_tri_local", std::min(ntx * hp.nchunk, hp.fast_grid / 2 * TRI3_BLK), 3 * TRI3_TP, tri3_smem, (k_tri3<3, true>), t, mix3_args(hp, *fz), ntx, env_int("QGCM_TRI_ORDER", 1));
     QG_CUDA(cudaGetLastError());
     return;
   }

@@ -162,6 +162,8 @@ __device__ __forceinline__ OmlOut oml_cell(const OmlArgs &a, int gi, int gj, int
   return o;
 }
 
+__device__ void oml_monitors(const OmlArgs &a, double (*red)[8]);
+
 // grid (ceil(warps/4), ceil(nyt/MR)); each lane owns the even/odd column pair (g0, g0+1):
 // 16-byte cp.async and 16-byte stores, one shuffle pair per field row for two cells
 __global__ void __launch_bounds__(128) k_oml_march(OmlArgs a) {
@@ -289,6 +291,47 @@ __global__ void __launch_bounds__(128) k_oml_march(OmlArgs a) {
     for (int i = 0; i < 4; ++i) t += red[threadIdx.x][i];
     a.part[(size_t)threadIdx.x * a.nblocks + blockIdx.y * gridDim.x + blockIdx.x] = t;
   }
+  // The block that finishes last adds the block partials in a fixed order (thread t takes partials
+  // t, t+128, ...; shuffle tree; the four warp sums in index order), evaluates the boundary
+  // monitors and, on y-slabs over peer memory, all-reduces the three sums with the other ranks:
+  // what used to be a second, latency-bound launch (k_oml_reduce).
+  __shared__ bool last;
+  __shared__ double mred[6][8];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(a.ticket + 2, 1u) == (unsigned int)a.nblocks - 1u);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double s3[3] = {0.0, 0.0, 0.0};
+  for (int q = 0; q < 3; ++q)
+    for (int i = threadIdx.x; i < a.nblocks; i += 128) s3[q] += __ldcg(a.part + (size_t)q * a.nblocks + i);
+  for (int q = 0; q < 3; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s3[q] += __shfl_down_sync(0xffffffffu, s3[q], o);
+    if (lane == 0) mred[q][wib] = s3[q];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.ticket[2] = 0u;
+    double t[3];
+    for (int q = 0; q < 3; ++q) t[q] = (mred[q][0] + mred[q][1]) + (mred[q][2] + mred[q][3]);
+    a.cv[0] = t[0];                         // xfosum, read by k_oml_entoc (after the all-reduce on slabs)
+    a.cv[1] = t[1];
+    a.cv[2] = t[2];
+    if (!a.multi) {
+      a.sc->cfraoc = t[1] * a.g.norm;       // omlsubs.F:211
+      a.sc->centoc = t[2] * (a.g.dx * a.g.dx);   // omlsubs.F:212
+    }
+  }
+  if (a.sb || a.nb) {
+    __syncthreads();
+    oml_monitors(a, mred);                  // they only read the old fields
+  }
+  if (a.peer.n) {       // the slab ranks' sums meet here, over NVLink peer memory
+    __syncthreads();
+    peer_allreduce_block(a.peer, a.cv, 3, a.cv, a.peer_err);
+  }
 }
 
 // boundary-flux monitors of the sb_hflux / nb_hflux options (omlsubs.F:684-726); called by
@@ -298,7 +341,7 @@ __device__ void oml_monitors(const OmlArgs &a, double (*red)[8]) {
   const int nxt = g.nxt, nyt = g.nyt, ld = g.ld;
   double s[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll 4
-  for (int i = threadIdx.x; i < nxt; i += 256) {
+  for (int i = threadIdx.x; i < nxt; i += blockDim.x) {
     if (a.sb && g.wall_s()) {   // y-slabs: the rank that holds the wall owns these monitors
       const double vm = -a.rhf0hm * (a.taux[i + 1] + a.taux[i]);
       const double tm = a.sst[i] + a.tsbdy;
@@ -320,67 +363,15 @@ __device__ void oml_monitors(const OmlArgs &a, double (*red)[8]) {
   __syncthreads();
   if (threadIdx.x == 0) {
     double t[6];
-    for (int q = 0; q < 6; ++q) { t[q] = 0.0; for (int i = 0; i < 8; ++i) t[q] += red[q][i]; }
+    const int nw = blockDim.x >> 5;
+    for (int q = 0; q < 6; ++q) { t[q] = 0.0; for (int i = 0; i < nw; ++i) t[q] += red[q][i]; }
     const double n = (double)nxt;
     a.sc->vfmads = t[0] / n; a.sc->ttmads = a.hdxm1 * t[1] / n; a.sc->ttmdfs = a.d2tfac * t[2] / n;
     a.sc->vfmadn = t[3] / n; a.sc->ttmadn = a.hdxm1 * t[4] / n; a.sc->ttmdfn = a.d2tfac * t[5] / n;
   }
 }
 
-// Sum the block partials of k_oml_step in a fixed order.  ORB blocks each add a contiguous
-// slice; the block that finishes last (ticket counter) adds the ORB slice sums in index
-// order -- deterministic -- and also evaluates the boundary monitors.
-constexpr int ORB = 64;
-// On decks with boundary heat-flux monitors one extra block evaluates them alongside.
-__global__ void __launch_bounds__(256) k_oml_reduce(OmlArgs a, double dxdy, int nred) {
-  __shared__ double red[6][8];
-  __shared__ bool last;
-  if ((int)blockIdx.x >= nred) {       // the monitors only read the old fields: they run beside the reduction
-    oml_monitors(a, red);
-    return;
-  }
-  const int per = (a.nblocks + nred - 1) / nred;
-  const int b0 = blockIdx.x * per, b1 = min(a.nblocks, b0 + per);
-  double s[3] = {0.0, 0.0, 0.0};
-  for (int q = 0; q < 3; ++q)
-    for (int i = b0 + threadIdx.x; i < b1; i += 256) s[q] += a.part[(size_t)q * a.nblocks + i];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int q = 0; q < 3; ++q) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_down_sync(0xffffffffu, s[q], o);
-    if (lane == 0) red[q][w] = s[q];
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int q = 0; q < 3; ++q) {
-      double t = 0.0;
-      for (int i = 0; i < 8; ++i) t += red[q][i];
-      a.part2[q * ORB + blockIdx.x] = t;
-    }
-    __threadfence();
-    last = (atomicAdd(a.ticket, 1u) == (unsigned int)nred - 1u);
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  if (threadIdx.x == 0) {
-    *a.ticket = 0u;
-    double t[3] = {0.0, 0.0, 0.0};
-    for (int q = 0; q < 3; ++q)
-      for (int i = 0; i < nred; ++i) t[q] += a.part2[q * ORB + i];
-    a.cv[0] = t[0];                         // xfosum, read by k_oml_entoc (after the all-reduce on slabs)
-    a.cv[1] = t[1];
-    a.cv[2] = t[2];
-    if (!a.multi) {
-      a.sc->cfraoc = t[1] * a.g.norm;       // omlsubs.F:211
-      a.sc->centoc = t[2] * dxdy;           // omlsubs.F:212
-    }
-  }
-  if (a.peer.n) {       // the slab ranks' sums meet here, over NVLink peer memory
-    __syncthreads();
-    peer_allreduce_block(a.peer, a.cv, 3, a.cv, a.peer_err);
-  }
-}
+__device__ void oml_finish(const OmlArgs &a, double dx, double *red);
 
 // entoc = 4-point average of (xfo - mean) with the edge/corner rules (omlsubs.F:151-205);
 // one block per p row; also the xintp row sum of that row (intsubs.f:103-131)
@@ -446,11 +437,20 @@ __global__ void __launch_bounds__(256) k_oml_entoc(OmlArgs a) {
     for (int i = 0; i < 8; ++i) t += red[i];
     a.rowsum[j] = t;
   }
+  // the block that finishes last forms xon(1) from the row sums (what used to be k_oml_finish)
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(a.ticket + 1, 1u) == gridDim.x - 1u);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x == 0) a.ticket[1] = 0u;
+  oml_finish(a, a.g.dx, red);
 }
 
-// xon(1) = dx*dy*xintp(entoc); channel: enisoc(1), eninoc(1) (omlsubs.F:214-233)
-__global__ void __launch_bounds__(256) k_oml_finish(OmlArgs a, double dx) {
-  __shared__ double red[8];
+// xon(1) = dx*dy*xintp(entoc); channel: enisoc(1), eninoc(1) (omlsubs.F:214-233); one block of 256 threads
+__device__ void oml_finish(const OmlArgs &a, double dx, double *red) {
   const int nyp = a.g.nyp;
   if (a.multi) {
     // owned rows only; the rows on the real walls carry half weight (intsubs.f:120-131)
@@ -536,14 +536,10 @@ void oml_phase_a(qgcm_model *m) {
   dim3 grid;
   OmlArgs a = oml_args(m, grid);
   const Grid &g = m->go;
-  {
-    const size_t smem = 4 * MD * MNF * 32 * sizeof(double2);   // attribute set per model in oml_args
-    QG_LAUNCH(m, "k_oml_step", grid, 128, smem, k_oml_march, a);
-  }
-  a.peer = peer_next_vec(m);    // y-slabs over peer memory: the reduction all-reduces its sums itself
-  // one block per 2048 partials (the marching kernel leaves a few hundred), at most ORB
-  const int nred = std::min(ORB, (a.nblocks + 2047) / 2048);
-  QG_LAUNCH(m, "k_oml_reduce", nred + ((a.sb || a.nb) ? 1 : 0), 256, 0, k_oml_reduce, a, g.dx * g.dx, nred);
+  a.peer = peer_next_vec(m);    // y-slabs over peer memory: the last block of the march all-reduces the sums itself
+  const size_t smem = 4 * MD * MNF * 32 * sizeof(double2);   // attribute set per model in oml_args
+  QG_LAUNCH(m, "k_oml_step", grid, 128, smem, k_oml_march, a);
+  (void)g;
 }
 
 // entoc from xfo minus the global mean, its integral (y-slabs: the rank's share in d_cv[3])
@@ -551,8 +547,7 @@ void oml_phase_b(qgcm_model *m) {
   dim3 grid;
   OmlArgs a = oml_args(m, grid);
   const Grid &g = m->go;
-  QG_LAUNCH(m, "k_oml_entoc", g.nyp, 256, 0, k_oml_entoc, a);
-  QG_LAUNCH(m, "k_oml_finish", 1, 256, 0, k_oml_finish, a, g.dx);
+  QG_LAUNCH(m, "k_oml_entoc", g.nyp, 256, 0, k_oml_entoc, a);      // its last block also forms xon(1)
   QG_CUDA(cudaGetLastError());
   // sstm <- sst, sst <- new: three-buffer rotation (omlsubs.F:124-125)
   double *old_m = m->fields.at("sstm").d;

@@ -282,6 +282,18 @@ struct qgcm_model {
   std::vector<ProfRec> prof_recs;
   std::vector<cudaEvent_t> prof_pool;
 
+  // CUDA graphs of whole timesteps (api.cu, run_graphed): the 15 launches of an ocean step and the
+  // ~20 of an atmosphere step are latency bound on small decks.  The leapfrog rotates buffer
+  // pointers on the host (q and p with period 2, the mixed layers with period 3), so a graph is
+  // cached per (kind of step, pointer state) together with the pointer state it leaves behind.
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<double *> after;   // pointer state after the step (fields in map order, then sstnew, astnew, hmnew)
+    int64_t launches = 0;
+  };
+  std::map<std::string, StepGraph> graphs;
+  int eager_steps[4] = {0, 0, 0, 0};     // steps of each kind run before graphs are used (lazy set-up happens in them)
+
   double *F(const char *name) { return fields.at(name).d; }
   void swapf(const char *a, const char *b) { std::swap(fields.at(a).d, fields.at(b).d); }
 };

@@ -29,6 +29,8 @@ struct QgArgs {
   double *qm;                 // lagged q in, new q out (in place)
   const double *wek, *ent;    // Ekman velocity and entrainment at p points
   int mrows;                  // rows marched by one warp of k_qgstep2 (<= RCH)
+  int erows;                  // > 0: the first and the last march cover only this many rows (the rows that need
+                              // the boundary formulas), so that every other march runs the interior fast path
 };
 
 __device__ __forceinline__ double shl(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }    // value of lane-1 (west)
@@ -73,7 +75,96 @@ __device__ __forceinline__ double qg_jac(double pA, double pAw, double pAe, doub
          qA * (pAe - pAw) + pC * (qCe - qCw) - pA * (qAe - qAw) - pBe * (qCe - qAe) + pBw * (qCw - qAw);
 }
 
-__global__ void __launch_bounds__(128) k_qgstep2(QgArgs a) {
+// ---- interior fast path -------------------------------------------------------------------
+// A warp whose 64 columns hold no wall or padding column and whose march needs no boundary row
+// (the vast majority at benchmark sizes) runs the same arithmetic without the wall / boundary
+// predicates, with its row windows rotated at compile time (the march is unrolled by three, so
+// "the last three rows" are three fixed register sets instead of two register moves per value
+// and row) and with the pipeline fill split from the steady state (no output predicate).
+struct QgWin {
+  double pm[3][2], d2[3][2], d4[3][2], p[3][2], q[3][2];
+  double pw[3], pe[3], qw[3], qe[3];      // west neighbour of column 0, east neighbour of column 1
+};
+// the constants of a row step are read from the kernel's parameter block where they are used
+// (constant-bank operands), not copied into registers
+struct QgRowK {
+  const QgArgs &a;
+  int k, kind;       // kind 0: top layer (wek, ent), 1: second layer (ent), 2: unforced; 3: unforced + ocean bottom drag
+};
+template <int PH, bool OUT>
+__device__ __forceinline__ void qg_row_interior(QgWin &S, const double2 *slot, const QgRowK &cq, double *qm_row, bool outl) {
+  struct { double dxm2, adf, ah2f, ah4f, tdt, foh, bdr; int atmos, kind; } c = {
+      cq.a.g.dxm2, cq.a.adfac, cq.a.ah2fac[cq.k], cq.a.ah4fac[cq.k], cq.a.g.tdt, cq.a.fohfac[cq.k < 2 ? cq.k : 0], cq.a.bdrfac, cq.a.atmos, cq.kind};
+  constexpr int N = PH, M = (PH + 2) % 3, O = (PH + 1) % 3;      // newest, middle, oldest row of every window
+  const double2 vpm = slot[0], vp = slot[32], vq = slot[64];
+  S.pm[N][0] = vpm.x; S.pm[N][1] = vpm.y;
+  S.p[N][0] = vp.x; S.p[N][1] = vp.y;
+  S.q[N][0] = vq.x; S.q[N][1] = vq.y;
+  S.pw[N] = shl(vp.y); S.pe[N] = shr(vp.x);
+  S.qw[N] = shl(vq.y); S.qe[N] = shr(vq.x);
+  {   // del2 at row r-1 (same association as qg_lap)
+    const double w0 = shl(S.pm[M][1]), e1 = shr(S.pm[M][0]);
+    S.d2[N][0] = (S.pm[O][0] + w0 + S.pm[M][1] + S.pm[N][0] - 4.0 * S.pm[M][0]) * c.dxm2;
+    S.d2[N][1] = (S.pm[O][1] + S.pm[M][0] + e1 + S.pm[N][1] - 4.0 * S.pm[M][1]) * c.dxm2;
+  }
+  {   // del4 at row r-2
+    const double w0 = shl(S.d2[M][1]), e1 = shr(S.d2[M][0]);
+    S.d4[N][0] = (S.d2[O][0] + w0 + S.d2[M][1] + S.d2[N][0] - 4.0 * S.d2[M][0]) * c.dxm2;
+    S.d4[N][1] = (S.d2[O][1] + S.d2[M][0] + e1 + S.d2[N][1] - 4.0 * S.d2[M][1]) * c.dxm2;
+  }
+  const double d4w0 = shl(S.d4[M][1]), d4e1 = shr(S.d4[M][0]);
+  if (!OUT) return;
+  // row r-3: del6, Jacobian, forcing, leapfrog
+  const double2 qold = slot[96];
+  double qn[2];
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const double d4w = cc == 0 ? d4w0 : S.d4[M][0], d4e = cc == 0 ? S.d4[M][1] : d4e1;
+    const double d6p = c.dxm2 * (S.d4[O][cc] + d4w + d4e + S.d4[N][cc] - 4.0 * S.d4[M][cc]);
+    const double jac = cc == 0 ? qg_jac(S.p[O][0], S.pw[O], S.p[O][1], S.pw[M], S.p[M][1], S.p[N][0], S.pw[N], S.p[N][1],
+                                        S.q[O][0], S.qw[O], S.q[O][1], S.qw[M], S.q[M][1], S.q[N][0], S.qw[N], S.q[N][1])
+                               : qg_jac(S.p[O][1], S.p[O][0], S.pe[O], S.p[M][0], S.pe[M], S.p[N][1], S.p[N][0], S.pe[N],
+                                        S.q[O][1], S.q[O][0], S.qe[O], S.q[M][0], S.qe[M], S.q[N][1], S.q[N][0], S.qe[N]);
+    double dqdt;
+    if (c.atmos) {
+      dqdt = c.adf * jac - c.ah4f * d6p;
+    } else {
+      const double diffus = c.ah2f * S.d4[M][cc] - c.ah4f * d6p;
+      dqdt = c.adf * jac + diffus;
+    }
+    double qdot = dqdt;
+    if (c.kind == 0) {
+      const double2 wk = slot[128], en = slot[160];
+      const double wkc = cc == 0 ? wk.x : wk.y, enc = cc == 0 ? en.x : en.y;
+      qdot = c.atmos ? dqdt + c.foh * (enc - wkc) : dqdt + c.foh * (wkc - enc);
+    } else if (c.kind == 1) {
+      const double2 en = slot[160];
+      const double enc = cc == 0 ? en.x : en.y;
+      qdot = c.atmos ? dqdt - c.foh * enc : dqdt + c.foh * enc;
+    } else if (c.kind == 3) {
+      qdot = qdot - c.bdr * S.d2[O][cc];      // del2p(i, jo)
+    }
+    qn[cc] = (cc == 0 ? qold.x : qold.y) + c.tdt * qdot;
+  }
+  if (outl) *reinterpret_cast<double2 *>(qm_row) = make_double2(qn[0], qn[1]);
+}
+
+// rows [ja, jb) of march `by`
+__device__ __forceinline__ void qg_march_rows(const QgArgs &a, int by, int nby, int nyp, int &ja, int &jb) {
+  if (a.erows > 0) {
+    if (by == 0) { ja = 0; jb = a.erows; }
+    else if (by == nby - 1) { ja = nyp - a.erows; jb = nyp; }
+    else { ja = a.erows + (by - 1) * a.mrows; jb = min(nyp - a.erows, ja + a.mrows); }
+  } else {
+    ja = by * a.mrows; jb = min(nyp, ja + a.mrows);
+  }
+}
+
+// PART 0: the warps that touch a wall column or a boundary row (general loop); PART 1: the interior
+// warps (fast path).  Two kernels so that each gets its own register allocation; every warp belongs to
+// exactly one of them and each element of q is read and written by exactly one lane.
+template <int PART, int BLK>
+__global__ void __launch_bounds__(128, BLK) k_qgstep2(QgArgs a) {
   extern __shared__ double2 ring2_all[];
   const Grid &g = a.g;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -81,6 +172,22 @@ __global__ void __launch_bounds__(128) k_qgstep2(QgArgs a) {
   const int wx = blockIdx.x * 4 + wib;
   const int nxp = g.nxp, nyp = g.nyp, ld = g.ld, cyc = g.cyclic, per = nxp - 1;
   if (wx * W2OUT >= nxp) return;   // whole warp exits together
+  bool interior = false;
+  {
+    // interior warp: columns g0 .. g0+63 all strictly inside the walls (box) or inside one period
+    // without wrap (channel), and the rows the outputs depend on (ja-3 .. jb+2) inside the domain;
+    // a two-layer model's second layer is also the bottom layer: forcing and drag together are
+    // left to the general loop
+    const int gw = wx * W2OUT - 4;
+    int ja_, jb_;
+    qg_march_rows(a, blockIdx.y, gridDim.y, nyp, ja_, jb_);
+    const bool cols_in = cyc ? (gw >= 0 && gw + 64 <= per) : (gw >= 1 && gw + 64 <= nxp - 1);
+    const bool rows_in = ja_ >= 3 && jb_ <= nyp - 3;
+    const bool simple_kind = !(k < 2 && !a.atmos && k == g.nl - 1);
+    interior = cols_in && rows_in && simple_kind;
+    if (PART == 0 && interior) return;      // PART 2: every warp takes the general loop; PART 3: each warp its own
+    if (PART == 1 && !interior) return;
+  }
   double2 *ring = ring2_all + (size_t)wib * (Q2_D * QG_NF * 32) + lane;
   const int g0 = wx * W2OUT - 4 + 2 * lane;      // first column of the pair (even)
   int c0 = g0;                                    // canonical column for loads
@@ -91,7 +198,8 @@ __global__ void __launch_bounds__(128) k_qgstep2(QgArgs a) {
   const bool wallE1 = !cyc && g0 + 1 == nxp - 1;  // the odd column is never the western wall
   const bool outl = lane >= 2 && lane < 30;
   const bool out0 = outl && g0 < nxp, out1 = outl && g0 + 1 < nxp;
-  const int ja = blockIdx.y * a.mrows, jb = min(nyp, ja + a.mrows);
+  int ja, jb;
+  qg_march_rows(a, blockIdx.y, gridDim.y, nyp, ja, jb);
   const size_t lo = (size_t)k * g.lsz;
   const int cc = ld0 ? c0 : 0;
   const double *__restrict__ pm = a.pm + lo + cc;
@@ -119,7 +227,7 @@ __global__ void __launch_bounds__(128) k_qgstep2(QgArgs a) {
       cp_async16(slot + 32, p + (size_t)r2c * ld);
       cp_async16(slot + 64, q + (size_t)r2c * ld);
       if (forced) {
-        cp_async16(slot + 128, wek + (size_t)r3c * ld);
+        if (k == 0) cp_async16(slot + 128, wek + (size_t)r3c * ld);      // only the top layer feels the Ekman pumping
         cp_async16(slot + 160, ent + (size_t)r3c * ld);
       }
     }
@@ -136,6 +244,44 @@ __global__ void __launch_bounds__(128) k_qgstep2(QgArgs a) {
   const int r0 = ja - 3;
 #pragma unroll
   for (int s = 0; s < Q2_D - 1; ++s) issue(r0 + s);
+  {
+    if (PART == 1 || (PART == 3 && interior)) {
+      const QgRowK ck = {a, k, k == 0 ? 0 : k == 1 ? 1 : (!a.atmos && k == nl - 1) ? 3 : 2};
+      QgWin S;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) S.pm[i][cc] = S.d2[i][cc] = S.d4[i][cc] = S.p[i][cc] = S.q[i][cc] = 0.0;
+        S.pw[i] = S.pe[i] = S.qw[i] = S.qe[i] = 0.0;
+      }
+      int r = r0;
+      auto slot_of = [&](int rr) { return ring + (size_t)((rr + 8 * Q2_D) % Q2_D) * (QG_NF * 32); };
+      // pipeline fill: six rows without output (phases 0,1,2,0,1,2)
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        issue(r + Q2_D - 1); cp_async_wait<Q2_D - 1>(); qg_row_interior<0, false>(S, slot_of(r), ck, nullptr, false); ++r;
+        issue(r + Q2_D - 1); cp_async_wait<Q2_D - 1>(); qg_row_interior<1, false>(S, slot_of(r), ck, nullptr, false); ++r;
+        issue(r + Q2_D - 1); cp_async_wait<Q2_D - 1>(); qg_row_interior<2, false>(S, slot_of(r), ck, nullptr, false); ++r;
+      }
+      // steady state: row r produces output row r-3
+      double *qrow = qm + (size_t)(r - 3) * ld;
+      const int rend = jb + 3;
+      for (; r + 2 < rend; r += 3, qrow += 3 * (size_t)ld) {
+        issue(r + Q2_D - 1); cp_async_wait<Q2_D - 1>(); qg_row_interior<0, true>(S, slot_of(r), ck, qrow, outl);
+        issue(r + Q2_D); cp_async_wait<Q2_D - 1>(); qg_row_interior<1, true>(S, slot_of(r + 1), ck, qrow + ld, outl);
+        issue(r + Q2_D + 1); cp_async_wait<Q2_D - 1>(); qg_row_interior<2, true>(S, slot_of(r + 2), ck, qrow + 2 * (size_t)ld, outl);
+      }
+      if (r < rend) {
+        issue(r + Q2_D - 1); cp_async_wait<Q2_D - 1>(); qg_row_interior<0, true>(S, slot_of(r), ck, qrow, outl); ++r;
+        if (r < rend) {
+          issue(r + Q2_D - 1); cp_async_wait<Q2_D - 1>(); qg_row_interior<1, true>(S, slot_of(r), ck, qrow + ld, outl);
+        }
+      }
+      cp_async_wait<0>();
+      return;
+    }
+  }
+  if (PART == 1) return;
   for (int r = r0; r < jb + 3; ++r) {
     issue(r + Q2_D - 1);
     cp_async_wait<Q2_D - 1>();
@@ -185,7 +331,7 @@ __global__ void __launch_bounds__(128) k_qgstep2(QgArgs a) {
       qn[0] = qB[0]; qn[1] = qB[1];
     } else {
       double2 wk = make_double2(0.0, 0.0), en = make_double2(0.0, 0.0);
-      if (forced) { wk = slot[128]; en = slot[160]; }
+      if (forced) { if (k == 0) wk = slot[128]; en = slot[160]; }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const bool wall = c == 0 ? (wallW0 || wallE0) : wallE1;
@@ -326,6 +472,7 @@ static void fill_common(qgcm_model *m, bool atmos, QgArgs &a, StripArgs &s) {
   const double bcco = atmos ? m->cfg.bccoat : m->cfg.bccooc;
   a.g = g;
   a.mrows = RCH;
+  a.erows = 0;
   a.atmos = atmos;
   a.f0 = m->fnot;
   a.adfac = 1.0 / (12.0 * g.dx * g.dx * m->fnot);
@@ -374,17 +521,43 @@ static void launch(qgcm_model *m, bool atmos) {
     const size_t smem = 4 * Q2_D * QG_NF * 32 * sizeof(double2);
     int &resident = m->qg_resident;
     if (!resident) {
-      QG_CUDA(cudaFuncSetAttribute(k_qgstep2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      QG_CUDA(cudaFuncSetAttribute((k_qgstep2<0, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      QG_CUDA(cudaFuncSetAttribute((k_qgstep2<2, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      QG_CUDA(cudaFuncSetAttribute((k_qgstep2<3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      QG_CUDA(cudaFuncSetAttribute((k_qgstep2<1, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      QG_CUDA(cudaFuncSetAttribute((k_qgstep2<1, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 0, sms = 0;
-      QG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qgstep2, 128, smem));
+      if (env_int("QGCM_QG_BLK", 1) == 1)
+        QG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_qgstep2<3, 3>), 128, smem));
+      else if (env_int("QGCM_QG_BLK", 1) == 3)
+        QG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_qgstep2<1, 3>), 128, smem));
+      else
+        QG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_qgstep2<1, 4>), 128, smem));
       QG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->cfg.device));
       resident = std::max(1, per_sm * sms);
     }
     const int bx = ((nwx + 3) / 4) * g.nl;
-    a.mrows = pick_march_rows(g.nyp, bx, resident, 24, RCH);
+    // the three rows next to a zonal boundary need the boundary formulas: they get two short marches
+    // of their own, every march between them is interior in y
+    a.erows = (g.nyp >= 64 && env_int("QGCM_QG_EROWS", 1)) ? 4 : 0;
+    const int inner = g.nyp - 2 * a.erows;
+    a.mrows = pick_march_rows(inner, bx, resident, 24, RCH);
     a.mrows = std::max(8, std::min(1024, env_int("QGCM_QG_MROWS", a.mrows)));
-    dim3 grid((nwx + 3) / 4, (g.nyp + a.mrows - 1) / a.mrows, g.nl);
-    QG_LAUNCH(m, "k_qgstep", grid, 128, smem, k_qgstep2, a);
+    dim3 grid((nwx + 3) / 4, (inner + a.mrows - 1) / a.mrows + (a.erows ? 2 : 0), g.nl);
+    // 1 (default): one launch, every warp takes the path that fits it; 0: the general loop for every warp
+    // (round-1 kernel); 3 / 4: interior and edge warps in two launches (A/B experiments)
+    const int mode = env_int("QGCM_QG_BLK", 1);
+    if (mode == 1) {
+      QG_LAUNCH(m, "k_qgstep", grid, 128, smem, (k_qgstep2<3, 3>), a);
+    } else if (mode == 0) {
+      QG_LAUNCH(m, "k_qgstep", grid, 128, smem, (k_qgstep2<2, 4>), a);
+    } else {
+      if (mode == 3)
+        QG_LAUNCH(m, "k_qgstep", grid, 128, smem, (k_qgstep2<1, 3>), a);        // interior warps
+      else
+        QG_LAUNCH(m, "k_qgstep", grid, 128, smem, (k_qgstep2<1, 4>), a);
+      QG_LAUNCH(m, "k_qgstep_edge", grid, 128, smem, (k_qgstep2<0, 4>), a);     // warps on walls and boundary rows
+    }
   }
   QG_CUDA(cudaGetLastError());
   m->swapf(nq, nqm);   // new q lives in the old qom buffer; old q becomes qom

@@ -95,6 +95,20 @@ class CModel:
             out = out.reshape(shape, order="F")
         return out
 
+    def get_fields(self, arrays: dict):
+        """batched download into caller-owned flat float64 arrays (one synchronisation): {name: array}"""
+        self._fields_call("get_fields", arrays)
+
+    def set_fields(self, arrays: dict):
+        self._fields_call("set_fields", arrays)
+
+    def _fields_call(self, which, arrays):
+        n = len(arrays)
+        names = (C.c_char_p * n)(*[k.encode() for k in arrays])
+        ptrs = (C.POINTER(C.c_double) * n)(*[a.ctypes.data_as(C.POINTER(C.c_double)) for a in arrays.values()])
+        cnts = (C.c_int64 * n)(*[a.size for a in arrays.values()])
+        self._call(which, C.c_int32(n), names, ptrs, cnts)
+
     def set_scalars(self, s: QgcmScalars):
         self._call("set_scalars", C.byref(s))
 
@@ -206,6 +220,19 @@ class Model(CModel):
             out = np.full(n.value, np.nan, dtype=np.float64)
         self._call("get_field_sub", name.encode(), C.c_int32(nsk), out.ctypes.data_as(C.POINTER(C.c_double)), n)
         return out
+
+    @staticmethod
+    def host_register(arr):
+        """page-lock a caller-owned numpy array for DMA (qgcm_host_register)"""
+        lib = load_library()
+        if lib.qgcm_host_register(C.c_void_p(arr.ctypes.data), C.c_int64(arr.nbytes)) != 0:
+            f = lib.qgcm_last_error
+            f.restype = C.c_char_p
+            raise RuntimeError("qgcm_host_register failed: %s" % (f() or b"").decode())
+
+    @staticmethod
+    def host_unregister(arr):
+        load_library().qgcm_host_unregister(C.c_void_p(arr.ctypes.data))
 
     def stream(self):
         f = self._lib.qgcm_stream

@@ -204,6 +204,42 @@ def test_roundtrip_and_errors(qg):
         m.set_field("po", t)
 
 
+def test_batched_restart_transfer_with_registered_arrays(qg, pyorc):
+    """qgcm_host_register + qgcm_get_fields / qgcm_set_fields (the restart path, src/nc_subs.F:1331-1360,
+    :1923-1943): bit-exact round trip, one synchronisation per batch; element counts are validated
+    before anything moves"""
+    p = small_configs(qg)["box_dg"]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    gpu.run(1, 2 * p.nstr)
+    names = ("po", "pom", "sst", "sstm")
+    want = {n: gpu.get_field(n) for n in names}
+    host = {n: np.full(want[n].size, np.nan) for n in names}
+    for a in host.values():
+        qg.Model.host_register(a)
+    try:
+        gpu.get_fields(host)
+        for n in names:
+            assert np.array_equal(host[n], want[n]), n
+        # restart: a fresh model fed from the registered arrays continues identically
+        other = qg.Model(cfg)
+        qg.synth.init_model(other, p, cfg, "random")
+        other.set_fields(host)
+        other.set_scalars(gpu.get_scalars())
+        for n in ("qo", "qom", "entoc", "wekto", "wekpo"):
+            other.set_field(n, gpu.get_field(n))
+        gpu.run(2 * p.nstr + 1, 3 * p.nstr)
+        other.run(2 * p.nstr + 1, 3 * p.nstr)
+        for n in OCEAN_CHECK:
+            assert np.array_equal(other.get_field(n), gpu.get_field(n)), n
+        bad = dict(host)
+        bad["sst"] = host["sst"][:-1]
+        with pytest.raises(RuntimeError):
+            gpu.get_fields(bad)
+    finally:
+        for a in host.values():
+            qg.Model.host_unregister(a)
+
+
 def test_async_forcing_upload(qg, pyorc):
     """qgcm_set_field_async + qgcm_commit_fields: the step after the commit sees the new forcing,
     the step before it the old one"""
