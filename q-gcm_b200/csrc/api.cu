@@ -460,6 +460,7 @@ int qgcm_destroy(qgcm_model *m) {
   if (m->h_peer_err) cudaFreeHost(m->h_peer_err);
   if (m->nccl) { try { nccl_destroy(m); } catch (...) {} }
   if (m->copy_stream) { cudaStreamSynchronize(m->copy_stream); cudaStreamDestroy(m->copy_stream); cudaEventDestroy(m->ev_copy); cudaEventDestroy(m->ev_step); }
+  if (m->side_stream) { cudaStreamSynchronize(m->side_stream); cudaStreamDestroy(m->side_stream); cudaEventDestroy(m->ev_fork); cudaEventDestroy(m->ev_join); }
   if (!m->shared_stream) cudaStreamDestroy(m->stream);
   delete m;
   return 0;

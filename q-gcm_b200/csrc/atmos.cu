@@ -316,8 +316,10 @@ __global__ void __launch_bounds__(128) k_xf_stress(XfArgsK a) {
         ud = a.u1[(size_t)(jc + jd) * lda + ix[q]];
         vd = a.v1[(size_t)(jc + jd) * lda + ix[q]];
       }
-      usum = usum + ud * __ldg(wu + (size_t)(4 * row + q) * npt);
-      vsum = vsum + vd * __ldg(wv + (size_t)(4 * row + q) * npt);
+      const double wuq = __ldg(wu + (size_t)(4 * row + q) * npt);
+      const double wvq = (south || north) ? __ldg(wv + (size_t)(4 * row + q) * npt) : wuq;   // one table away from the walls
+      usum = usum + ud * wuq;
+      vsum = vsum + vd * wvq;
     }
   }
   // velocity difference over the ocean (tau_udiff), src/xfosubs.F:250-300
@@ -417,18 +419,20 @@ __global__ void __launch_bounds__(256) k_xf_wekpa(XfArgsK a) {
   const int jbeg = ja * n - (n - 1) / 2, ibeg = ia * n - (n - 1) / 2;     // 1-based T subscripts of the box start
   const int jlo = max(1, jbeg), jhi = min(jbeg + nij - 1, nytf);
   double wsum = 0.0, wtasum = 0.0;
-  for (int j = jlo; j <= jhi; ++j) {
-    const int dj = j - jbeg;
+  // the box is walked as one flat list (row-major), so that all 32 lanes work whatever ndxr is
+  // (with ndxr = 16 a lane-per-column walk would leave half the warp idle)
+  const int nrows = jhi - jlo + 1;
+  for (int e = lane; e < nrows * nij; e += 32) {
+    const int jr = e / nij, di = e - jr * nij;
+    const int j = jlo + jr, dj = j - jbeg;
     const double wtj = odd ? ((dj == 0 || dj == n) ? 0.5 : 1.0) : ((dj == n) ? 0.0 : 1.0);
-    for (int di = lane; di < nij; di += 32) {
-      const double wti = odd ? ((di == 0 || di == n) ? 0.5 : 1.0) : ((di == n) ? 0.0 : 1.0);
-      const int it = (ibeg + di - 1 + nxtf) % nxtf;     // 0-based fine T column
-      const size_t r = (size_t)(j - 1) * ldf + it, rn = r + ldf;
-      const double w = a.hxofac * (a.tauy[r + 1] + a.tauy[rn + 1] - (a.tauy[r] + a.tauy[rn]) + a.taux[r] + a.taux[r + 1] -
-                                   (a.taux[rn] + a.taux[rn + 1]));
-      wsum += wti * wtj;
-      wtasum += wti * wtj * w;
-    }
+    const double wti = odd ? ((di == 0 || di == n) ? 0.5 : 1.0) : ((di == n) ? 0.0 : 1.0);
+    const int it = (ibeg + di - 1 + nxtf) % nxtf;     // 0-based fine T column
+    const size_t r = (size_t)(j - 1) * ldf + it, rn = r + ldf;
+    const double w = a.hxofac * (a.tauy[r + 1] + a.tauy[rn + 1] - (a.tauy[r] + a.tauy[rn]) + a.taux[r] + a.taux[r + 1] -
+                                 (a.taux[rn] + a.taux[rn + 1]));
+    wsum += wti * wtj;
+    wtasum += wti * wtj * w;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -104,9 +104,10 @@ inline int env_int(const char *name, int dflt) {
 // blocks on 444 slots 0.46 ms, 440 blocks 0.33 ms), so the number of marches is the largest
 // that fills a whole number of waves, with the fewest waves whose marches stay under `cap` rows.
 //   bx: blocks per march row, resident: blocks the GPU holds at once, lo: shortest useful march
-inline int pick_march_rows(int nrows, int bx, int resident, int lo, int cap) {
+//   extra: marches outside the count (the two short boundary marches of k_qgstep2) that share the waves
+inline int pick_march_rows(int nrows, int bx, int resident, int lo, int cap, int extra = 0) {
   for (int w = 1; w <= 64; ++w) {
-    const int c = std::max(1, (w * resident) / bx);
+    const int c = std::max(1, (w * resident) / bx - extra);
     const int rows = (nrows + c - 1) / c;
     if (rows <= cap) return std::max(lo, rows);
   }
@@ -276,6 +277,11 @@ struct qgcm_model {
   // shared-memory attribute is (re)set with them, so two models on two devices in one
   // process each configure their own device
   int qg_resident = 0, oml_resident = 0;
+  // second stream for small launches that are independent of a big one running beside them (the
+  // wall-warp launches of the vorticity step); forked from and joined to `stream` with events, so
+  // stream order -- and a stream capture -- sees them as part of the step
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // per-kernel event timing (qgcm_profile)
   bool prof = false;
   struct ProfRec { const char *name; cudaEvent_t e0, e1; };

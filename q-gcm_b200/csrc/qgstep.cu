@@ -31,6 +31,11 @@ struct QgArgs {
   int mrows;                  // rows marched by one warp of k_qgstep2 (<= RCH)
   int erows;                  // > 0: the first and the last march cover only this many rows (the rows that need
                               // the boundary formulas), so that every other march runs the interior fast path
+  // compact launches of the general loop (PART 0):
+  //   pmode 1: one warp per block, only the warps that hold a wall or padding column (wx = 0 and
+  //            wx >= w_hi), all rows in marches of mrows_edge rows;
+  //   pmode 2: the two short boundary marches for the warps in between
+  int pmode, w_hi, mrows_edge;
 };
 
 __device__ __forceinline__ double shl(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }    // value of lane-1 (west)
@@ -169,8 +174,15 @@ __global__ void __launch_bounds__(128, BLK) k_qgstep2(QgArgs a) {
   const Grid &g = a.g;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int k = blockIdx.z;
-  const int wx = blockIdx.x * 4 + wib;
   const int nxp = g.nxp, nyp = g.nyp, ld = g.ld, cyc = g.cyclic, per = nxp - 1;
+  int wx = blockIdx.x * 4 + wib, ja, jb;
+  qg_march_rows(a, blockIdx.y, gridDim.y, nyp, ja, jb);
+  if (PART == 0 && a.pmode == 1) {        // one warp per block: the warps next to the walls, every row
+    wx = blockIdx.x == 0 ? 0 : a.w_hi + (int)blockIdx.x - 1;
+    ja = blockIdx.y * a.mrows_edge; jb = min(nyp, ja + a.mrows_edge);
+  } else if (PART == 0 && a.pmode == 2) { // the two boundary marches
+    ja = blockIdx.y ? nyp - a.erows : 0; jb = ja + a.erows;
+  }
   if (wx * W2OUT >= nxp) return;   // whole warp exits together
   bool interior = false;
   {
@@ -179,13 +191,12 @@ __global__ void __launch_bounds__(128, BLK) k_qgstep2(QgArgs a) {
     // a two-layer model's second layer is also the bottom layer: forcing and drag together are
     // left to the general loop
     const int gw = wx * W2OUT - 4;
-    int ja_, jb_;
-    qg_march_rows(a, blockIdx.y, gridDim.y, nyp, ja_, jb_);
     const bool cols_in = cyc ? (gw >= 0 && gw + 64 <= per) : (gw >= 1 && gw + 64 <= nxp - 1);
-    const bool rows_in = ja_ >= 3 && jb_ <= nyp - 3;
+    const bool rows_in = ja >= 3 && jb <= nyp - 3;
     const bool simple_kind = !(k < 2 && !a.atmos && k == g.nl - 1);
     interior = cols_in && rows_in && simple_kind;
-    if (PART == 0 && interior) return;      // PART 2: every warp takes the general loop; PART 3: each warp its own
+    if (PART == 0 && a.pmode == 0 && interior) return;      // PART 2: every warp takes the general loop; PART 3: each warp its own
+    if (PART == 0 && a.pmode == 2 && !cols_in) return;      // the wall warps did these rows themselves (pmode 1)
     if (PART == 1 && !interior) return;
   }
   double2 *ring = ring2_all + (size_t)wib * (Q2_D * QG_NF * 32) + lane;
@@ -198,8 +209,6 @@ __global__ void __launch_bounds__(128, BLK) k_qgstep2(QgArgs a) {
   const bool wallE1 = !cyc && g0 + 1 == nxp - 1;  // the odd column is never the western wall
   const bool outl = lane >= 2 && lane < 30;
   const bool out0 = outl && g0 < nxp, out1 = outl && g0 + 1 < nxp;
-  int ja, jb;
-  qg_march_rows(a, blockIdx.y, gridDim.y, nyp, ja, jb);
   const size_t lo = (size_t)k * g.lsz;
   const int cc = ld0 ? c0 : 0;
   const double *__restrict__ pm = a.pm + lo + cc;
@@ -473,6 +482,7 @@ static void fill_common(qgcm_model *m, bool atmos, QgArgs &a, StripArgs &s) {
   a.g = g;
   a.mrows = RCH;
   a.erows = 0;
+  a.pmode = 0; a.w_hi = 0; a.mrows_edge = RCH;
   a.atmos = atmos;
   a.f0 = m->fnot;
   a.adfac = 1.0 / (12.0 * g.dx * g.dx * m->fnot);
@@ -527,9 +537,9 @@ static void launch(qgcm_model *m, bool atmos) {
       QG_CUDA(cudaFuncSetAttribute((k_qgstep2<1, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       QG_CUDA(cudaFuncSetAttribute((k_qgstep2<1, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 0, sms = 0;
-      if (env_int("QGCM_QG_BLK", 1) == 1)
+      if (env_int("QGCM_QG_BLK", 2) == 1)
         QG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_qgstep2<3, 3>), 128, smem));
-      else if (env_int("QGCM_QG_BLK", 1) == 3)
+      else if (env_int("QGCM_QG_BLK", 2) == 3)
         QG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_qgstep2<1, 3>), 128, smem));
       else
         QG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_qgstep2<1, 4>), 128, smem));
@@ -541,13 +551,57 @@ static void launch(qgcm_model *m, bool atmos) {
     // of their own, every march between them is interior in y
     a.erows = (g.nyp >= 64 && env_int("QGCM_QG_EROWS", 1)) ? 4 : 0;
     const int inner = g.nyp - 2 * a.erows;
-    a.mrows = pick_march_rows(inner, bx, resident, 24, RCH);
+    a.mrows = pick_march_rows(inner, bx, resident, 24, RCH, a.erows ? 2 : 0);
     a.mrows = std::max(8, std::min(1024, env_int("QGCM_QG_MROWS", a.mrows)));
     dim3 grid((nwx + 3) / 4, (inner + a.mrows - 1) / a.mrows + (a.erows ? 2 : 0), g.nl);
-    // 1 (default): one launch, every warp takes the path that fits it; 0: the general loop for every warp
-    // (round-1 kernel); 3 / 4: interior and edge warps in two launches (A/B experiments)
-    const int mode = env_int("QGCM_QG_BLK", 1);
-    if (mode == 1) {
+    // 2 (default): interior warps in one launch at four blocks per SM; the general loop in two compact
+    //   launches -- the warps next to the walls, one warp per block in short marches (their rows are a
+    //   serial chain: 128-row marches would make this launch as long as a whole wave of the main one),
+    //   and the two boundary marches of everyone else;
+    // 1: one launch, every warp takes the path that fits it (three blocks per SM);
+    // 0: the general loop for every warp (round-1 kernel); 3 / 4: A/B experiments
+    // (a two-layer ocean, whose second layer is forced and dragged at once, stays on the general loop)
+    const int mode = (a.erows == 0 || (!atmos && g.nl == 2)) ? 0 : env_int("QGCM_QG_BLK", 2);
+    if (mode == 2) {
+      // the wall-warp launches run beside the interior launch on a second stream (they write
+      // disjoint elements); while profiling they stay on the main stream so that they are timed
+      const bool side = !m->prof && env_int("QGCM_QG_SIDE", 1);
+      if (side) {
+        if (!m->side_stream) {
+          QG_CUDA(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
+          QG_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+          QG_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+        }
+        QG_CUDA(cudaEventRecord(m->ev_fork, m->stream));
+        QG_CUDA(cudaStreamWaitEvent(m->side_stream, m->ev_fork, 0));
+      }
+      QG_LAUNCH(m, "k_qgstep", grid, 128, smem, (k_qgstep2<1, 4>), a);
+      QgArgs e = a;
+      // warps that are not interior in x: wx = 0 and wx >= w_hi
+      int w_hi = nwx;
+      while (w_hi > 1) {
+        const int gw = (w_hi - 1) * W2OUT - 4;
+        const bool in = g.cyclic ? (gw >= 0 && gw + 64 <= g.nxp - 1) : (gw >= 1 && gw + 64 <= g.nxp - 1);
+        if (in) break;
+        --w_hi;
+      }
+      e.pmode = 1; e.w_hi = w_hi; e.mrows_edge = std::max(8, env_int("QGCM_QG_EDGE_ROWS", 16));
+      const dim3 g1(1 + (nwx - w_hi), (g.nyp + e.mrows_edge - 1) / e.mrows_edge, g.nl), g2((nwx + 3) / 4, 2, g.nl);
+      if (side) {
+        k_qgstep2<0, 4><<<g1, 32, smem / 4, m->side_stream>>>(e);
+        launch_check(m, "k_qgstep_edge");
+        e.pmode = 2;
+        k_qgstep2<0, 4><<<g2, 128, smem, m->side_stream>>>(e);
+        launch_check(m, "k_qgstep_edge");
+        m->launches += 2;
+        QG_CUDA(cudaEventRecord(m->ev_join, m->side_stream));
+        QG_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+      } else {
+        QG_LAUNCH(m, "k_qgstep_edge", g1, 32, smem / 4, (k_qgstep2<0, 4>), e);
+        e.pmode = 2;
+        QG_LAUNCH(m, "k_qgstep_edge", g2, 128, smem, (k_qgstep2<0, 4>), e);
+      }
+    } else if (mode == 1) {
       QG_LAUNCH(m, "k_qgstep", grid, 128, smem, (k_qgstep2<3, 3>), a);
     } else if (mode == 0) {
       QG_LAUNCH(m, "k_qgstep", grid, 128, smem, (k_qgstep2<2, 4>), a);
