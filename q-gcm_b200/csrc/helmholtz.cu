@@ -545,8 +545,8 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       const double2 b0 = ldg2_nohoist(a.s1base + 2 * t), b1 = ldg2_nohoist(a.s1base + 2 * t + 1);
       // fused forward transform: the row is q_k(:,j); the right-hand side of the layer is
       // q_k - beta*y_j (- ddynoc in the bottom layer), src/ocisubs.F:121-138
-      double by2 = 0.0;
-      if (MODE == DST_FUSED_F) by2 = 2.0 * (a.beta * a.yrel[r + a.row0]);
+      double by = 0.0;
+      if (MODE == DST_FUSED_F) by = a.beta * a.yrel[r + a.row0];
       const double *dd = nullptr;
       if (MODE == DST_FUSED_F && a.ddyn && mode == a.kbot) dd = a.ddyn + (size_t)(r + a.row0) * a.ld;
 #pragma unroll
@@ -556,12 +556,14 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
         const int ib0 = (q == 0) ? ((t == 0) ? 0 : N - 2 * t) : N - 2 * n;
         double xb0 = IN[ib0];
         double xb1 = IN[N - 2 * n - 1];
-        if (MODE == DST_FUSED_F && dd) { xo.x -= dd[2 * n]; xo.y -= dd[2 * n + 1]; xb0 -= dd[ib0]; xb1 -= dd[N - 2 * n - 1]; }
+        if (MODE == DST_FUSED_F) {
+          xo.x -= by; xo.y -= by; xb0 -= by; xb1 -= by;
+          if (dd) { xo.x -= dd[2 * n]; xo.y -= dd[2 * n + 1]; xb0 -= dd[ib0]; xb1 -= dd[N - 2 * n - 1]; }
+        }
         const double s0 = (q == 0) ? b0.x : fma(b0.x, a.c1[q], b0.y * a.s1[q]);
         const double s1 = (q == 0) ? b1.x : fma(b1.x, a.c1[q], b1.y * a.s1[q]);
-        // the constant beta*y drops out of the difference of a mirror pair and shifts its sum by 2 beta*y
-        v1[q].x = fma(s0, (xo.x + xb0) - by2, xo.x - xb0);
-        v1[q].y = fma(s1, (xo.y + xb1) - by2, xo.y - xb1);
+        v1[q].x = fma(s0, xo.x + xb0, xo.x - xb0);
+        v1[q].y = fma(s1, xo.y + xb1, xo.y - xb1);
       }
       if (t == 0) v1[0].x = 0.0;
       dft<R1>(v1);

@@ -16,14 +16,14 @@ timeout 600 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.
 echo "bench rc=$?"; cut -c1-400 $out/${tag}_bench_n1.json
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
-    --log-file $out/${tag}_launches_raw.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e \
+    --log-file $out/${tag}_launches_raw.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --no-verify \
     > $out/${tag}_ncu_list.log 2>&1
   echo "ncu list rc=$?"
   # init launches ~ 40; skip into the steady step loop, capture one step's worth of every main kernel
   timeout 900 ncu --set full --clock-control none --import-source on \
-    -k 'regex:k_dst3|k_qgstep|k_oml_march|k_oml_entoc|k_l2m|k_m2l|k_tri_local|k_tri_reduced' \
-    --launch-skip ${NCU_SKIP:-40} -c ${NCU_COUNT:-14} -o $out/${tag}_full -f \
-    python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > $out/${tag}_ncu_full.log 2>&1
+    -k 'regex:k_dst3|k_qgstep2|k_oml_march|k_oml_entoc|k_tri3|k_tri_reduced|k_inv_scalars' \
+    --launch-skip ${NCU_SKIP:-30} -c ${NCU_COUNT:-16} -o $out/${tag}_full -f \
+    env QGCM_GRAPH=0 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --no-verify > $out/${tag}_ncu_full.log 2>&1
   echo "ncu full rc=$?"
 fi
 if [ "${SKIP_DECKS:-0}" != "1" ]; then
