@@ -33,7 +33,13 @@ extern "C" {
 #define QGCM_NLMAX 9          /* nlmax in src/eigmode.f:86 */
 #define QGCM_ABI_VERSION 1
 
-/* cpp macros of src/make.config:11-45 become run-time flags */
+/* cpp macros of src/make.config:11-45 become run-time flags.  Variants of the reference that no
+ * shipped deck uses and this library does NOT implement -- each fails loudly instead of computing
+ * something else: -Datmos_only inside xforc (qgcm_xforc returns an error; the other atmosphere
+ * procedures work), the fork's -Dsponge_layer_k247 relaxation term of qgostep
+ * (src/qgosubs.F:203-205; there is no flag for it, so a deck that needs it cannot be expressed),
+ * and y-slab partitions (nranks > 1) of channel or coupled decks (qgcm_create returns an error:
+ * they fit one GPU). */
 enum {
   QGCM_OCEAN_ONLY   = 1 << 0,   /* -Docean_only   */
   QGCM_ATMOS_ONLY   = 1 << 1,   /* -Datmos_only   */

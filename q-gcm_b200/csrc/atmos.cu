@@ -279,49 +279,9 @@ __global__ void __launch_bounds__(256) k_xf_wind(XfArgsK a) {
   a.v1[(size_t)j * ld + i] = v;
 }
 
-// bicubic wind on the fine grid, ocean-velocity correction, quadratic drag; one thread per
-// fine p point.  grid (ceil(nxf/128), nyf)
-__global__ void __launch_bounds__(128) k_xf_stress(XfArgsK a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
-  if (i >= a.nxf) return;
-  const Grid &ga = a.ga;
-  const int n = a.ndxr, nxta = ga.nxt, nyta = ga.nyt, lda = ga.ld;
-  // coarse cell and position inside it; the last fine column repeats the first
-  // (src/xfosubs.F:1211-1214) and the last fine row belongs to the northern cells with jj = ndxr
-  const int ifi = (i == a.nxf - 1) ? 0 : i;
-  const int ic = ifi / n, ii = ifi - ic * n;
-  int jc = j / n, jj = j - jc * n;
-  if (j == a.nyf - 1) { jc = nyta - 1; jj = n; }
-  const bool south = (jc == 0), north = (jc == nyta - 1);
-  const int icm1 = (ic == 0) ? nxta - 1 : ic - 1, icp2 = (ic + 2) % nxta;
-  const int ix[4] = {icm1, ic, ic + 1, icp2};
-  // weights are stored [variant][k][fine point] so that neighbouring lanes read neighbouring doubles
-  const int npt = (n + 1) * (n + 1);
-  const double *wu = a.stb + (size_t)(south ? 1 : (north ? 3 : 0)) * npt * 16 + (ii + (n + 1) * jj);
-  const double *wv = a.stb + (size_t)(south ? 2 : (north ? 4 : 0)) * npt * 16 + (ii + (n + 1) * jj);
-  double usum = 0.0, vsum = 0.0;
-#pragma unroll
-  for (int row = 0; row < 4; ++row) {
-    const int jd = row - 1;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      double ud, vd;
-      if (south && jd == -1) {
-        ud = 0.0;
-        vd = a.u1[ix[q]];                                    // u on the boundary pads v (vy = -ux)
-      } else if (north && jd == 2) {
-        ud = 0.0;
-        vd = a.u1[(size_t)nyta * lda + ix[q]];
-      } else {
-        ud = a.u1[(size_t)(jc + jd) * lda + ix[q]];
-        vd = a.v1[(size_t)(jc + jd) * lda + ix[q]];
-      }
-      const double wuq = __ldg(wu + (size_t)(4 * row + q) * npt);
-      const double wvq = (south || north) ? __ldg(wv + (size_t)(4 * row + q) * npt) : wuq;   // one table away from the walls
-      usum = usum + ud * wuq;
-      vsum = vsum + vd * wvq;
-    }
-  }
+// velocity difference over the ocean, quadratic drag law and the stores of one fine p point
+// (src/xfosubs.F:250-354, :554-559)
+__device__ __forceinline__ void xf_stress_point(const XfArgsK &a, int i, int j, double usum, double vsum) {
   // velocity difference over the ocean (tau_udiff), src/xfosubs.F:250-300
   const Grid &go = a.go;
   const int io = i - a.iocoff, jo = j - a.jocoff;
@@ -365,6 +325,101 @@ __global__ void __launch_bounds__(128) k_xf_stress(XfArgsK a) {
   if (over_ocean) {   // src/xfosubs.F:554-559
     a.tauxo[(size_t)jo * go.ld + io] = a.raoro * tx;
     a.tauyo[(size_t)jo * go.ld + io] = a.raoro * ty;
+  }
+}
+
+// bicubic wind on the fine grid, ocean-velocity correction, quadratic drag; one thread per
+// fine p point.  grid (ceil(nxf/128), nyf)
+// `edge` != 0: only the fine rows of the southernmost and northernmost coarse cells (the separable
+// kernel below does the rest): blockIdx.y < ndxr -> southern rows, otherwise the northern ones
+__global__ void __launch_bounds__(128) k_xf_stress(XfArgsK a, int edge) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y;
+  if (edge && j >= a.ndxr) j = (a.ga.nyt - 1) * a.ndxr + (j - a.ndxr);
+  if (i >= a.nxf) return;
+  const Grid &ga = a.ga;
+  const int n = a.ndxr, nxta = ga.nxt, nyta = ga.nyt, lda = ga.ld;
+  // coarse cell and position inside it; the last fine column repeats the first
+  // (src/xfosubs.F:1211-1214) and the last fine row belongs to the northern cells with jj = ndxr
+  const int ifi = (i == a.nxf - 1) ? 0 : i;
+  const int ic = ifi / n, ii = ifi - ic * n;
+  int jc = j / n, jj = j - jc * n;
+  if (j == a.nyf - 1) { jc = nyta - 1; jj = n; }
+  const bool south = (jc == 0), north = (jc == nyta - 1);
+  const int icm1 = (ic == 0) ? nxta - 1 : ic - 1, icp2 = (ic + 2) % nxta;
+  const int ix[4] = {icm1, ic, ic + 1, icp2};
+  // weights are stored [variant][k][fine point] so that neighbouring lanes read neighbouring doubles
+  const int npt = (n + 1) * (n + 1);
+  const double *wu = a.stb + (size_t)(south ? 1 : (north ? 3 : 0)) * npt * 16 + (ii + (n + 1) * jj);
+  const double *wv = a.stb + (size_t)(south ? 2 : (north ? 4 : 0)) * npt * 16 + (ii + (n + 1) * jj);
+  double usum = 0.0, vsum = 0.0;
+#pragma unroll
+  for (int row = 0; row < 4; ++row) {
+    const int jd = row - 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double ud, vd;
+      if (south && jd == -1) {
+        ud = 0.0;
+        vd = a.u1[ix[q]];                                    // u on the boundary pads v (vy = -ux)
+      } else if (north && jd == 2) {
+        ud = 0.0;
+        vd = a.u1[(size_t)nyta * lda + ix[q]];
+      } else {
+        ud = a.u1[(size_t)(jc + jd) * lda + ix[q]];
+        vd = a.v1[(size_t)(jc + jd) * lda + ix[q]];
+      }
+      const double wuq = __ldg(wu + (size_t)(4 * row + q) * npt);
+      const double wvq = (south || north) ? __ldg(wv + (size_t)(4 * row + q) * npt) : wuq;   // one table away from the walls
+      usum = usum + ud * wuq;
+      vsum = vsum + vd * wvq;
+    }
+  }
+  xf_stress_point(a, i, j, usum, vsum);
+}
+
+// Away from the zonal boundaries the bicubic patch with centred-difference derivatives is the
+// separable Catmull-Rom spline: stb(k = 4 row + q; ii, jj) = ay_row(jj) bx_q(ii).  One thread then
+// takes a whole column of ndxr fine points of a coarse cell: the 32 coarse values are loaded and
+// combined in x once (16 multiply-adds per component) and every fine point costs 4 more per
+// component, instead of 16 with 16 weight loads.  The 1-D factors are read from the reference's own
+// table (bx_q(ii) = stb(4+q; ii, 0), ay_row(jj) = stb(4 row + 1; 0, jj)), so no new constants enter;
+// sums are associated differently from the 16-term loop of src/xfosubs.F:1100-1180 (1e-16 level).
+// grid (ceil(nxf/128), nyta-2): coarse rows 1 .. nyta-2.
+__global__ void __launch_bounds__(128) k_xf_stress_sep(XfArgsK a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jc = blockIdx.y + 1;
+  if (i >= a.nxf) return;
+  const Grid &ga = a.ga;
+  const int n = a.ndxr, nxta = ga.nxt, lda = ga.ld;
+  const int ifi = (i == a.nxf - 1) ? 0 : i;
+  const int ic = ifi / n, ii = ifi - ic * n;
+  const int icm1 = (ic == 0) ? nxta - 1 : ic - 1, icp2 = (ic + 2) % nxta;
+  const int ix[4] = {icm1, ic, ic + 1, icp2};
+  const int npt = (n + 1) * (n + 1);
+  double bx[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) bx[q] = __ldg(a.stb + (size_t)(4 + q) * npt + ii);
+  double ux[4], vx[4];
+#pragma unroll
+  for (int row = 0; row < 4; ++row) {
+    double su = 0.0, sv = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      su = su + a.u1[(size_t)(jc + row - 1) * lda + ix[q]] * bx[q];
+      sv = sv + a.v1[(size_t)(jc + row - 1) * lda + ix[q]] * bx[q];
+    }
+    ux[row] = su; vx[row] = sv;
+  }
+  for (int jj = 0; jj < n; ++jj) {
+    double usum = 0.0, vsum = 0.0;
+#pragma unroll
+    for (int row = 0; row < 4; ++row) {
+      const double ay = __ldg(a.stb + (size_t)(4 * row + 1) * npt + (size_t)(n + 1) * jj);
+      usum = usum + ux[row] * ay;
+      vsum = vsum + vx[row] * ay;
+    }
+    xf_stress_point(a, i, jc * n + jj, usum, vsum);
   }
 }
 
@@ -773,7 +828,14 @@ void launch_xforc(qgcm_model *m) {
   a.wekta = m->F("wekta"); a.wekpa = m->F("wekpa"); a.tauxo = m->F("tauxo"); a.tauyo = m->F("tauyo");
   a.sc = m->d_scal;
   QG_LAUNCH(m, "k_xf_wind", dim3((ga.nxp + 255) / 256, ga.nyp), 256, 0, k_xf_wind, a);
-  QG_LAUNCH(m, "k_xf_stress", dim3((x.nxf + 127) / 128, x.nyf), 128, 0, k_xf_stress, a);
+  if (ga.nyt >= 3 && env_int("QGCM_XF_SEP", 1)) {
+    // interior coarse rows: separable kernel; the first and last coarse rows (2 ndxr + 1 fine rows) keep the
+    // general one, whose weights carry the boundary conditions
+    QG_LAUNCH(m, "k_xf_stress", dim3((x.nxf + 127) / 128, ga.nyt - 2), 128, 0, k_xf_stress_sep, a);
+    QG_LAUNCH(m, "k_xf_stress_edge", dim3((x.nxf + 127) / 128, 2 * n + 1), 128, 0, k_xf_stress, a, 1);
+  } else {
+    QG_LAUNCH(m, "k_xf_stress", dim3((x.nxf + 127) / 128, x.nyf), 128, 0, k_xf_stress, a, 0);
+  }
   QG_LAUNCH(m, "k_xf_sample", dim3((ga.nxp + 255) / 256, ga.nyp), 256, 0, k_xf_sample, a);
   QG_LAUNCH(m, "k_xf_wekta", dim3((ga.nxt + 255) / 256, ga.nyt), 256, 0, k_xf_wekta, a);
   QG_LAUNCH(m, "k_xf_wekpa", (ga.nxp * ga.nyp * 32 + 255) / 256, 256, 0, k_xf_wekpa, a);

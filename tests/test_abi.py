@@ -89,11 +89,12 @@ def test_header_and_library_work_from_plain_c(qg, tmp_path):
     assert "ABI mismatch" in r.stdout
 
 
-def test_integration_md_fortran_mirror_matches_the_header(qg):
-    """no Fortran compiler exists here, so the bind(C) mirror of qgcm_config printed in
-    INTEGRATION.md is checked textually: same members, same order, same extents as the header"""
+def test_fortran_mirror_of_the_config_matches_the_header(qg):
+    """no Fortran compiler exists here, so the bind(C) mirror of qgcm_config in
+    integration/qgcm_types.f90 (the file INTEGRATION.md tells a maintainer to compile) is checked
+    textually: same members, same order, same extents as the header"""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    text = open(os.path.join(root, "integration", "qgcm_types.f90")).read()
     block = re.search(r"type, bind\(C\) :: qgcm_config(.*?)end type", text, re.S).group(1)
     members = []
     for line in block.splitlines():

@@ -56,7 +56,7 @@ def test_slab_steps_match_oracle_and_single_gpu(qg, pyorc, case, nranks):
     fl = integral_scale(cpu, p)
     compare_scalars(grp, cpu, ("dpioc", "dpiocp", "xinhom_oc"), tol=1e-11, floor=fl)
     compare_scalars(grp, cpu, ("xon",), tol=1e-11, floor=integral_scale(cpu, p, "entoc"))
-    compare_scalars(grp, cpu, ("centoc", "cfraoc"), tol=1e-9)
+    compare_scalars(grp, cpu, ("centoc", "cfraoc"), tol=1e-12)      # sums over ranks in rank order: measured <= 1e-15
 
 
 @pytest.mark.parametrize("case,nranks", [("box_dg", 3), ("box_fast", 8)])
@@ -69,7 +69,7 @@ def test_slab_hundred_steps_drift(qg, pyorc, case, nranks):
     for name in ("po", "qo", "sst"):
         a = grp.get_field(name)
         assert np.isfinite(a).all()
-        assert rel_l2(a, cpu.get_field(name)) <= 1e-8, (case, nranks, name)
+        assert rel_l2(a, cpu.get_field(name)) <= 1e-10, (case, nranks, name)      # as test_hundred_steps_drift
 
 
 def test_slab_rejects_unsupported_decks(qg):

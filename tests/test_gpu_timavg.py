@@ -45,7 +45,9 @@ def test_tavatm_and_tavocn_coupled(qg, pyorc, case):
     for m in (gpu, cpu):
         m.tavatm()              # sums allocate on first use
         m.tavocn()
-    compare(gpu, cpu, AT_SUMS + OC_SUMS, tol=1e-14, label=case + " first contribution")
+    # 1e-13: the sums are copies of fields the start-up xforc produced, and its separable stress kernel
+    # associates the 16-term interpolation sums differently from the oracle (measured 1.1e-14 on wtocav)
+    compare(gpu, cpu, AT_SUMS + OC_SUMS, tol=1e-13, label=case + " first contribution")
     for m in (gpu, cpu):
         m.run(1, p.nstr + 1)
         m.tavatm()
