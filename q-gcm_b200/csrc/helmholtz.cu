@@ -463,7 +463,9 @@ __host__ __device__ constexpr int dst3_seg(int M) {
 // the tridiagonal kernels, which hold all modes of a wavenumber anyway), and the fused inverse
 // transform produces pressure LAYERS.  That removes the two pointwise kernels (k_l2m, k_m2l)
 // and the 12 field passes they existed for.
-enum { DST_PLAIN_F = 0, DST_PLAIN_I = 1, DST_FUSED_F = 2, DST_FUSED_I = 3 };
+// DST_FUSED_FT: DST_FUSED_F over topography (its own instantiation: the flat-bottom kernel carries no predicated
+// ddynoc loads, which were 7 % of its instructions)
+enum { DST_PLAIN_F = 0, DST_PLAIN_I = 1, DST_FUSED_F = 2, DST_FUSED_I = 3, DST_FUSED_FT = 4 };
 struct Dst3Args {
   int nitems, nrows;        // (mode,row) work items; solved rows per mode
   int ld, nyp, nxp, row0;
@@ -493,7 +495,8 @@ struct Dst3Args {
 template <int R3, int MODE>
 __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
   constexpr bool INV = (MODE == DST_PLAIN_I);       // xintp row sums of the result, wall column zeroed
-  constexpr bool FUSED = (MODE == DST_FUSED_F || MODE == DST_FUSED_I);
+  constexpr bool FWD_F = (MODE == DST_FUSED_F || MODE == DST_FUSED_FT), TOPO = (MODE == DST_FUSED_FT);
+  constexpr bool FUSED = (FWD_F || MODE == DST_FUSED_I);
   constexpr int R1 = 16, R2 = 15;
   constexpr int M = R1 * R2 * R3, N = 2 * M;
   constexpr int L1 = M / R1, L2 = M / R2, L3 = M / R3;
@@ -520,7 +523,7 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (item < a.nitems) {
       const int mode = FUSED ? item % a.nl : item / a.nrows, r = FUSED ? item / a.nl : item - mode * a.nrows;
-      const double *in = (MODE == DST_FUSED_F) ? a.src : a.wrk;
+      const double *in = FWD_F ? a.src : a.wrk;
       mbar_expect_tx(bar, N * 8);
       bulk_g2s(in_s, in + (size_t)mode * a.lsz + (size_t)(r + a.row0) * a.ld, N * 8, bar);
     }
@@ -546,9 +549,9 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       // fused forward transform: the row is q_k(:,j); the right-hand side of the layer is
       // q_k - beta*y_j (- ddynoc in the bottom layer), src/ocisubs.F:121-138
       double by = 0.0;
-      if (MODE == DST_FUSED_F) by = a.beta * a.yrel[r + a.row0];
+      if (FWD_F) by = a.beta * a.yrel[r + a.row0];
       const double *dd = nullptr;
-      if (MODE == DST_FUSED_F && a.ddyn && mode == a.kbot) dd = a.ddyn + (size_t)(r + a.row0) * a.ld;
+      if (TOPO && mode == a.kbot) dd = a.ddyn + (size_t)(r + a.row0) * a.ld;
 #pragma unroll
       for (int q = 0; q < R1; ++q) {
         const int n = t + q * L1;
@@ -556,9 +559,9 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
         const int ib0 = (q == 0) ? ((t == 0) ? 0 : N - 2 * t) : N - 2 * n;
         double xb0 = IN[ib0];
         double xb1 = IN[N - 2 * n - 1];
-        if (MODE == DST_FUSED_F) {
+        if (FWD_F) {
           xo.x -= by; xo.y -= by; xb0 -= by; xb1 -= by;
-          if (dd) { xo.x -= dd[2 * n]; xo.y -= dd[2 * n + 1]; xb0 -= dd[ib0]; xb1 -= dd[N - 2 * n - 1]; }
+          if (TOPO && dd) { xo.x -= dd[2 * n]; xo.y -= dd[2 * n + 1]; xb0 -= dd[ib0]; xb1 -= dd[N - 2 * n - 1]; }
         }
         const double s0 = (q == 0) ? b0.x : fma(b0.x, a.c1[q], b0.y * a.s1[q]);
         const double s1 = (q == 0) ? b1.x : fma(b1.x, a.c1[q], b1.y * a.s1[q]);
@@ -622,7 +625,7 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       const int nxt = item + gridDim.x;
       if (nxt < a.nitems) {
         const int m2 = FUSED ? nxt % a.nl : nxt / a.nrows, r2 = FUSED ? nxt / a.nl : nxt - m2 * a.nrows;
-        const double *in = (MODE == DST_FUSED_F) ? a.src : a.wrk;
+        const double *in = FWD_F ? a.src : a.wrk;
         mbar_expect_tx(bar, N * 8);
         bulk_g2s(in_s, in + (size_t)m2 * a.lsz + (size_t)(r2 + a.row0) * a.ld, N * 8, bar);
       }
@@ -698,8 +701,8 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       // modes, sum_m ctm2l(m,k) hclco(m-1) ochom(:,j,m-1), and store p_k (src/ocisubs.F:377-401)
       if (t < L3) {
         double2 *__restrict__ out = reinterpret_cast<double2 *>(row);
-        const double2 *hrow = reinterpret_cast<const double2 *>(a.hom + (size_t)(r + a.row0) * a.ld);
         double2 acc[R3];
+        const double2 *hrow = reinterpret_cast<const double2 *>(a.hom + (size_t)(r + a.row0) * a.ld);
 #pragma unroll
         for (int q = 0; q < R3; ++q) acc[q] = make_double2(ev[q], SC[t + q * L3]);
         for (int mm = 1; mm < a.nl; ++mm) {
@@ -1201,7 +1204,7 @@ __global__ void __launch_bounds__(128) k_tri_reduced(TriArgs t, SlabArgs sa) {
   // Both sweeps are latency bound (one thread per wavenumber, ~C dependent steps), so the
   // loads of PF chunks are issued together ahead of their dependent chain: one exposed
   // memory latency per PF steps instead of one per step.
-  constexpr int PF = 16;
+  constexpr int PF = 24;
   // forward elimination: h0_c is parked in yp[c] (overwritten by the back substitution)
   double h0 = g[0], h1 = f[ld], p = pt[ld], dinv = di[ld];
   yp[ld] = h0;
@@ -1372,7 +1375,9 @@ static void dst3_launch_t(qgcm_model *md, HelmPlan &hp, const Dst3Args &a, int m
   auto ki = k_dst3<R3, DST_PLAIN_I>;
   auto kff = k_dst3<R3, DST_FUSED_F>;
   auto kfi = k_dst3<R3, DST_FUSED_I>;
+  auto kfft = k_dst3<R3, DST_FUSED_FT>;
   if (!hp.fast_attr) {
+    QG_CUDA(cudaFuncSetAttribute(kfft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QG_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QG_CUDA(cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QG_CUDA(cudaFuncSetAttribute(kff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1383,7 +1388,10 @@ static void dst3_launch_t(qgcm_model *md, HelmPlan &hp, const Dst3Args &a, int m
   switch (mode) {
     case DST_PLAIN_F: QG_LAUNCH(md, "k_xform", grid, 256, smem, kf, a); break;
     case DST_PLAIN_I: QG_LAUNCH(md, "k_xform_inv", grid, 256, smem, ki, a); break;
-    case DST_FUSED_F: QG_LAUNCH(md, "k_xform", grid, 256, smem, kff, a); break;
+    case DST_FUSED_F:
+      if (a.ddyn) QG_LAUNCH(md, "k_xform", grid, 256, smem, kfft, a);
+      else QG_LAUNCH(md, "k_xform", grid, 256, smem, kff, a);
+      break;
     default: QG_LAUNCH(md, "k_xform_inv", grid, 256, smem, kfi, a); break;
   }
 }
