@@ -235,6 +235,9 @@ static qgcm_model *create(const qgcm_config *cfg) {
     }
     m->red_elems = red + 512;
     m->d_red = (double *)dalloc(m, sizeof(double) * m->red_elems);
+    // the atmosphere's mixed layer has its own scratch: a coupled cycle runs the ocean step beside the
+    // atmosphere steps (run_cycle below)
+    m->d_red_a = (cfg->flags & QGCM_OCEAN_ONLY) ? m->d_red : (double *)dalloc(m, sizeof(double) * m->red_elems);
     QG_CUDA(cudaStreamSynchronize(m->stream));
   } catch (...) {
     for (void *p : m->allocs) cudaFree(p);
@@ -382,7 +385,8 @@ static void invalidate_graphs(qgcm_model *m) {
   for (auto &kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
   m->graphs.clear();
 }
-// kind: 0 atmosphere step, 1 xforc + ocean step + atmosphere step (coupled), 2 ocean step (ocean only)
+// kind: 0 atmosphere step, 1 xforc + ocean step + atmosphere step (coupled), 2 ocean step (ocean only),
+// 3 a whole coupled cycle (cycle_body)
 template <class Body>
 static void run_graphed(qgcm_model *m, int kind, Body body) {
   static const bool off = env_int("QGCM_GRAPH", 1) == 0;
@@ -419,6 +423,42 @@ static void run_graphed(qgcm_model *m, int kind, Body body) {
   QG_CUDA(cudaGraphLaunch(it->second.exec, m->stream));
   set_pointer_state(m, it->second.after);
   m->launches += it->second.launches;
+}
+
+// One coupled cycle, nt = first .. first + nstr - 1 with mod(first, nstr) = 1 (src/q-gcm.F:1220-1269): xforc, the
+// ocean step and nstr atmosphere steps.  After xforc the ocean step and the atmosphere steps touch disjoint
+// state (the ocean reads tauxo, tauyo, wekto, wekpo, fnetoc and its own fields; the atmosphere reads wekta,
+// wekpa, fnetat, tauxa, tauya and its own; the scalars of the two live in separate members of qgcm_scalars), and
+// nothing reads the other side before the next xforc.  So the atmosphere steps are a second branch of the cycle's
+// graph: their small kernels (385 x 97 points in the double-gyre deck) fill the SMs the ocean kernels' last
+// waves leave idle instead of queueing behind them.
+static void cycle_body(qgcm_model *m) {
+  if (!m->at_stream) {
+    // (a higher stream priority for this branch measured no different: 0.667 ms per dg_coupled cycle either way)
+    QG_CUDA(cudaStreamCreateWithFlags(&m->at_stream, cudaStreamNonBlocking));
+    QG_CUDA(cudaEventCreateWithFlags(&m->ev_atfork, cudaEventDisableTiming));
+    QG_CUDA(cudaEventCreateWithFlags(&m->ev_atjoin, cudaEventDisableTiming));
+  }
+  launch_xforc(m);
+  cudaStream_t main = m->stream;
+  const bool split = !m->prof && env_int("QGCM_CYCLE_FORK", 1) != 0;      // profiled cycles stay on one stream
+  if (split) {
+    QG_CUDA(cudaEventRecord(m->ev_atfork, main));
+    QG_CUDA(cudaStreamWaitEvent(m->at_stream, m->ev_atfork, 0));
+    m->stream = m->at_stream;      // every launch goes through (m)->stream
+  }
+  try {
+    for (int i = 0; i < m->cfg.nstr; ++i) atmos_step_eager(m);
+  } catch (...) {
+    m->stream = main;
+    throw;
+  }
+  m->stream = main;
+  ocean_step_eager(m);
+  if (split) {
+    QG_CUDA(cudaEventRecord(m->ev_atjoin, m->at_stream));
+    QG_CUDA(cudaStreamWaitEvent(main, m->ev_atjoin, 0));
+  }
 }
 
 static void ocean_step(qgcm_model *m) {
@@ -460,6 +500,7 @@ int qgcm_destroy(qgcm_model *m) {
   if (m->h_peer_err) cudaFreeHost(m->h_peer_err);
   if (m->nccl) { try { nccl_destroy(m); } catch (...) {} }
   if (m->copy_stream) { cudaStreamSynchronize(m->copy_stream); cudaStreamDestroy(m->copy_stream); cudaEventDestroy(m->ev_copy); cudaEventDestroy(m->ev_step); }
+  if (m->at_stream) { cudaStreamSynchronize(m->at_stream); cudaStreamDestroy(m->at_stream); cudaEventDestroy(m->ev_atfork); cudaEventDestroy(m->ev_atjoin); }
   if (m->side_stream) { cudaStreamSynchronize(m->side_stream); cudaStreamDestroy(m->side_stream); cudaEventDestroy(m->ev_fork); cudaEventDestroy(m->ev_join); }
   if (!m->shared_stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -584,7 +625,19 @@ int qgcm_run(qgcm_model *m, int64_t nt_first, int64_t nt_last) {
     const int nstr = m->cfg.nstr;
     for (int64_t nt = nt_first; nt <= nt_last; ++nt) {
       const bool ocstep = (nstr == 1) ? true : (nt % nstr == 1);
-      if (ocstep && m->has_atmos && m->has_ocean && m->nranks == 1) {
+      const bool coupled1 = m->has_atmos && m->has_ocean && m->nranks == 1;
+      // a whole cycle in one graph when no averaging falls inside it (tlavg_ocean follows the nt of an ocean
+      // step on its 1-in-25 cadence, tlavg_atmos every 100th nt; the k247 accumulator wants po between steps)
+      bool whole = ocstep && coupled1 && nstr > 1 && nt + nstr - 1 <= nt_last && !(m->flags & QGCM_OCNC_AVG_K247) &&
+                   (nt - 1) % (25 * (int64_t)nstr) != 0;
+      for (int64_t k = nt; whole && k < nt + nstr; ++k)
+        if ((k - 1) % 100 == 0) whole = false;
+      if (whole) {
+        run_graphed(m, 3, [m] { cycle_body(m); });
+        nt += nstr - 1;
+        continue;
+      }
+      if (ocstep && coupled1) {
         // coupled: xforc + ocean step + this nt's atmosphere step as one graph (67 launches)
         run_graphed(m, 1, [m] { launch_xforc(m); ocean_step_eager(m); atmos_step_eager(m); });
         if (m->flags & QGCM_OCNC_AVG_K247) launch_avg_ocn_k247(m);      // src/q-gcm.F:1250-1252 (po is final after the ocean step)

@@ -218,8 +218,8 @@ void launch_aml(qgcm_model *m) {
   a.astnew = m->astnew; a.hmnew = m->hmnew; a.xfa = m->xfa; a.entat = m->F("entat");
   dim3 grid((g.nxt + 63) / 64, (g.nyt + 3) / 4);
   a.nblocks = grid.x * grid.y;
-  a.part = m->d_red;
-  a.rowsum = m->d_red + 2 * (size_t)a.nblocks;
+  a.part = m->d_red_a;
+  a.rowsum = m->d_red_a + 2 * (size_t)a.nblocks;
   a.sc = m->d_scal;
   if (m->red_elems < 2 * (size_t)a.nblocks + g.nyp) throw std::runtime_error("aml: reduction scratch too small");
   QG_LAUNCH(m, "k_aml_step", grid, 256, 0, k_aml_step, a);

@@ -235,6 +235,9 @@ struct qgcm_model {
   qgcm_scalars *d_scal = nullptr;        // device-resident scalar state
   double *d_coef = nullptr;              // small device scratch for step coefficients
   double *d_red = nullptr;               // reduction scratch
+  double *d_red_a = nullptr;             // the atmosphere mixed layer's (= d_red in ocean-only models)
+  cudaStream_t at_stream = nullptr;      // coupled cycles: the atmosphere steps' branch (api.cu cycle_body)
+  cudaEvent_t ev_atfork = nullptr, ev_atjoin = nullptr;
   size_t red_elems = 0;
   qg::HelmPlan hpo, hpa;
   qg::XfPlan xf;

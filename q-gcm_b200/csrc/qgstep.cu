@@ -565,7 +565,9 @@ static void launch(qgcm_model *m, bool atmos) {
     if (mode == 2) {
       // the wall-warp launches run beside the interior launch on a second stream (they write
       // disjoint elements); while profiling they stay on the main stream so that they are timed
-      const bool side = !m->prof && env_int("QGCM_QG_SIDE", 1);
+      // (ocean only: the atmosphere's launches are a few blocks each, and inside a coupled cycle its steps
+      // run beside the ocean step, which owns the side stream)
+      const bool side = !m->prof && !atmos && env_int("QGCM_QG_SIDE", 1);
       if (side) {
         if (!m->side_stream) {
           QG_CUDA(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));

@@ -389,6 +389,29 @@ def test_coupled_steps_and_drift(qg, pyorc, case):
         assert np.isfinite(gpu.get_field(name)).all()
 
 
+@pytest.mark.parametrize("case,ncycles", [(c, 40) for c in COUPLED] + [("dg_coupled", 12), ("so_coupled", 12)])
+def test_coupled_cycle_branches_are_bitwise_serial(qg, monkeypatch, case, ncycles):
+    """qgcm_run captures a coupled cycle (xforc, ocean step, nstr atmosphere steps) as one graph whose
+    atmosphere steps are a branch beside the ocean step (api.cu cycle_body).  The branches touch disjoint
+    state, so the result is bit-identical with the single-stream order (QGCM_CYCLE_FORK=0), which is the
+    one the step-by-step tests check against the oracle.  Small decks for 40 cycles (eager warm-up,
+    capture, replays, and the averaging steps that fall back to the per-nt path) and the two shipped
+    coupled decks at full size, where the ocean kernels fill the GPU, for 12."""
+    p = coupled_configs(qg)[case] if case in COUPLED else qg.named_config(case)
+    cfg = qg.build_config(p)
+    nt = ncycles * p.nstr + 2
+    out = []
+    for fork in ("1", "0"):
+        monkeypatch.setenv("QGCM_CYCLE_FORK", fork)
+        m = qg.Model(cfg)
+        qg.synth.init_model(m, p, cfg, "random")
+        m.run(1, nt)
+        out.append({n: m.get_field(n) for n in OCEAN_CHECK + ATMOS_CHECK + ("tauxo", "fnetoc", "fnetat")})
+        out[-1]["scal"] = np.array([getattr(m.get_scalars(), n) for n in ("centoc", "centat", "cfraoc", "cfraat")], dtype=np.float64).ravel()
+    for n in out[0]:
+        assert np.array_equal(out[0][n], out[1][n]), (case, n, rel_l2(out[0][n], out[1][n]))
+
+
 @pytest.mark.parametrize("deck", ["dg_coupled", "so_coupled", "dg_oo"])
 def test_full_size_decks_one_coupled_step(qg, pyorc, deck):
     """the shipped decks at their own resolution (BASELINE.json configs 0-2): double gyre
