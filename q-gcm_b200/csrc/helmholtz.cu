@@ -446,12 +446,12 @@ __device__ __forceinline__ void twiddle_apply(double2 *v, double2 w1, double2 w2
   for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw[r]);
 }
 
-__host__ __device__ constexpr int dst3_seg(int M) {
-  // values per thread in the running-sum sweep: even, >= M/256, divides M, preferably an
+__host__ __device__ constexpr int dst3_seg(int M, int NT) {
+  // values per thread in the running-sum sweep: even, >= M/NT, divides M, preferably an
   // odd number of 16-byte units (conflict-free 128-bit shared loads)
   int best = 0;
   for (int s = 2; s <= 64; s += 2)
-    if (M % s == 0 && s * 256 >= M) {
+    if (M % s == 0 && s * NT >= M) {
       if (!best) best = s;
       if ((s / 2) & 1) return s;
     }
@@ -492,8 +492,20 @@ struct Dst3Args {
   double2 wnr[16];          // exp(-2 pi i q L3/N)
 };
 
+// Threads per block: the first two passes have M/16 and M/15 butterflies, so rows of half length M <= 1200
+// (NAtl 2 km and coarser) keep less than a third of a 256-thread block busy in them, and their per-row
+// latencies (six barriers, the exchanges) weigh twice as much against half the arithmetic.  Those plans run
+// 128-thread blocks, four per SM instead of two -- twice the rows in flight per SM from the same registers
+// and less shared memory -- and take the 240 butterflies of the last pass in two rounds.
+#ifndef DST3_SMALL_NT
+#define DST3_SMALL_NT 128      // 256: every plan on 256-thread blocks (A/B builds)
+#endif
+__host__ __device__ constexpr int dst3_threads(int R3) { return R3 <= 5 ? DST3_SMALL_NT : 256; }
+__host__ __device__ constexpr int dst3_blocks(int R3) { return 512 / dst3_threads(R3); }
+
 template <int R3, int MODE>
-__global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
+__global__ void __launch_bounds__(dst3_threads(R3), dst3_blocks(R3)) k_dst3(const Dst3Args a) {
+  constexpr int NT = dst3_threads(R3), NW = NT / 32;
   constexpr bool INV = (MODE == DST_PLAIN_I);       // xintp row sums of the result, wall column zeroed
   constexpr bool FWD_F = (MODE == DST_FUSED_F || MODE == DST_FUSED_FT), TOPO = (MODE == DST_FUSED_FT);
   constexpr bool FUSED = (FWD_F || MODE == DST_FUSED_I);
@@ -502,8 +514,9 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
   constexpr int L1 = M / R1, L2 = M / R2, L3 = M / R3;
   constexpr int NS2 = R1, NS3 = R1 * R2;
   constexpr int WSZ = M + M / 16;              // exchange buffer incl. the skew of pass 1's output
-  constexpr int SEG = dst3_seg(M), NSC = M / SEG;
-  static_assert(L1 <= 256 && L2 <= 256 && L3 <= 256 && NSC <= 256 && SEG > 0 && L2 % 16 == 0, "plan does not fit one block");
+  constexpr int SEG = dst3_seg(M, NT), NSC = M / SEG;
+  constexpr int RND = (L3 + NT - 1) / NT;      // rounds of the last pass (and of everything after it)
+  static_assert(L1 <= NT && L2 <= NT && NSC <= NT && SEG > 0 && L2 % 16 == 0, "plan does not fit one block");
   static_assert(NS3 == L3, "last pass must be a single sweep");
   extern __shared__ __align__(128) unsigned char smraw[];
   double *IN = reinterpret_cast<double *>(smraw);                 // N doubles: raw row (TMA target)
@@ -578,7 +591,7 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       // row sum of the previous row: the per-warp partials were parked before this barrier
       double sum = 0.0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sum += red[16 + i];
+      for (int i = 0; i < NW; ++i) sum += red[16 + i];
       a.rowsum[prev_slot] = sum;
     }
     // ---- pass 2 (radix 15): exchange buffer -> raw-row buffer (autosort stores) ----
@@ -603,20 +616,25 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       }
     }
     __syncthreads();
-    // ---- pass 3 (radix R3), raw-row buffer -> exchange buffer: thread t ends with Z_k, k = t + q*L3 ----
-    double2 v[R3];
+    // ---- pass 3 (radix R3), raw-row buffer -> exchange buffer: butterfly tt = t + rr*NT ends with Z_k,
+    //      k = tt + q*L3 (RND rounds: one with 256 threads, two with 128) ----
+    double2 v[RND][R3];
 #pragma unroll
-    for (int q = 0; q < R3; ++q) v[q] = make_double2(0.0, 0.0);
-    if (t < L3) {
+    for (int rr = 0; rr < RND; ++rr) {
+      const int tt = t + rr * NT;
 #pragma unroll
-      for (int q = 0; q < R3; ++q) v[q] = Z[t + q * L3];
-      const double2 w1 = ldg2_nohoist(a.tw3base + 2 * t), w2 = ldg2_nohoist(a.tw3base + 2 * t + 1);
-      twiddle_apply<R3>(v, w1, w2);
-      dft<R3>(v);
-    }
-    if (t < L3) {
+      for (int q = 0; q < R3; ++q) v[rr][q] = make_double2(0.0, 0.0);
+      if (tt < L3) {
 #pragma unroll
-      for (int q = 0; q < R3; ++q) W[t + q * L3] = v[q];
+        for (int q = 0; q < R3; ++q) v[rr][q] = Z[tt + q * L3];
+        const double2 w1 = ldg2_nohoist(a.tw3base + 2 * tt), w2 = ldg2_nohoist(a.tw3base + 2 * tt + 1);
+        twiddle_apply<R3>(v[rr], w1, w2);
+        dft<R3>(v[rr]);
+      }
+      if (tt < L3) {
+#pragma unroll
+        for (int q = 0; q < R3; ++q) W[tt + q * L3] = v[rr][q];
+      }
     }
     // generic-proxy stores of pass 2 into the buffer the bulk copy is about to overwrite
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -632,29 +650,34 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
     }
     // ---- real post-processing: even outputs -Im F_k stay in registers, Re F_k is the
     //      summand of the odd outputs ----
-    double ev[R3], cs[R3];
+    double ev[RND][R3];
 #pragma unroll
-    for (int q = 0; q < R3; ++q) ev[q] = cs[q] = 0.0;
-    if (t < L3) {
-      const double2 wb = ldg2_nohoist(a.wnbase + t);
+    for (int rr = 0; rr < RND; ++rr) {
+      const int tt = t + rr * NT;
+      double cs[R3];
 #pragma unroll
-      for (int q = 0; q < R3; ++q) {
-        const int k = t + q * L3;
-        const double2 zb = (q == 0) ? ((t == 0) ? v[0] : W[M - t]) : W[M - k];
-        const double2 w = (q == 0) ? wb : cmul(wb, a.wnr[q]);
-        const double2 F = real_post(v[q], zb, w);
-        ev[q] = -F.y;
-        cs[q] = F.x;
-        asm volatile("" ::: "memory");   // keep the partner loads in step with their use (register budget)
+      for (int q = 0; q < R3; ++q) ev[rr][q] = cs[q] = 0.0;
+      if (tt < L3) {
+        const double2 wb = ldg2_nohoist(a.wnbase + tt);
+#pragma unroll
+        for (int q = 0; q < R3; ++q) {
+          const int k = tt + q * L3;
+          const double2 zb = (q == 0) ? ((tt == 0) ? v[rr][0] : W[M - tt]) : W[M - k];
+          const double2 w = (q == 0) ? wb : cmul(wb, a.wnr[q]);
+          const double2 F = real_post(v[rr][q], zb, w);
+          ev[rr][q] = -F.y;
+          cs[q] = F.x;
+          asm volatile("" ::: "memory");   // keep the partner loads in step with their use (register budget)
+        }
+        if (tt == 0) {
+          ev[rr][0] = 0.0;
+          cs[0] = 0.5 * (v[rr][0].x + v[rr][0].y);   // out_1 = F_0 / 2
+        }
       }
-      if (t == 0) {
-        ev[0] = 0.0;
-        cs[0] = 0.5 * (v[0].x + v[0].y);   // out_1 = F_0 / 2
-      }
-    }
-    if (t < L3) {
+      if (tt < L3) {
 #pragma unroll
-      for (int q = 0; q < R3; ++q) SC[t + q * L3] = cs[q];
+        for (int q = 0; q < R3; ++q) SC[tt + q * L3] = cs[q];
+      }
     }
     __syncthreads();
     // ---- running sum over k (dsint.f:33-37): contiguous segment per thread ----
@@ -684,7 +707,7 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       __syncthreads();
       double off = inc - tot;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < NW; ++i)
         if (i < wp) off += red[i];
       if (t < NSC) {
         double2 *dst = reinterpret_cast<double2 *>(SC + t * SEG);
@@ -699,39 +722,49 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
       // fused inverse transform: the row is sum_m ctm2l(m,k) wrk_m(:,j) already (the tridiagonal
       // kernel projected in spectral space); add the homogeneous solutions of the baroclinic
       // modes, sum_m ctm2l(m,k) hclco(m-1) ochom(:,j,m-1), and store p_k (src/ocisubs.F:377-401)
-      if (t < L3) {
-        double2 *__restrict__ out = reinterpret_cast<double2 *>(row);
-        double2 acc[R3];
-        const double2 *hrow = reinterpret_cast<const double2 *>(a.hom + (size_t)(r + a.row0) * a.ld);
 #pragma unroll
-        for (int q = 0; q < R3; ++q) acc[q] = make_double2(ev[q], SC[t + q * L3]);
-        for (int mm = 1; mm < a.nl; ++mm) {
-          const double hc = a.coef[mm - 1], cm = a.ctm2l[mm + a.nl * mode];
-          const double2 *h2 = hrow + (size_t)(mm - 1) * (a.lsz / 2);
+      for (int rr = 0; rr < RND; ++rr) {
+        const int tt = t + rr * NT;
+        if (tt < L3) {
+          double2 *__restrict__ out = reinterpret_cast<double2 *>(row);
+          const double2 *hrow = reinterpret_cast<const double2 *>(a.hom + (size_t)(r + a.row0) * a.ld);
+          double2 acc[R3];
 #pragma unroll
-          for (int q = 0; q < R3; ++q) {
-            const double2 h = __ldg(h2 + t + q * L3);
-            acc[q].x = fma(cm, hc * h.x, acc[q].x);
-            acc[q].y = fma(cm, hc * h.y, acc[q].y);
+          for (int q = 0; q < R3; ++q) acc[q] = make_double2(ev[rr][q], SC[tt + q * L3]);
+          for (int mm = 1; mm < a.nl; ++mm) {
+            const double hc = a.coef[mm - 1], cm = a.ctm2l[mm + a.nl * mode];
+            const double2 *h2 = hrow + (size_t)(mm - 1) * (a.lsz / 2);
+#pragma unroll
+            for (int q = 0; q < R3; ++q) {
+              const double2 h = __ldg(h2 + tt + q * L3);
+              acc[q].x = fma(cm, hc * h.x, acc[q].x);
+              acc[q].y = fma(cm, hc * h.y, acc[q].y);
+            }
           }
-        }
 #pragma unroll
-        for (int q = 0; q < R3; ++q) out[t + q * L3] = acc[q];
+          for (int q = 0; q < R3; ++q) out[tt + q * L3] = acc[q];
+        }
       }
-      if (t == 255) {      // the eastern wall column (the transform covers columns 0 .. nxp-2)
+      if (t == NT - 1) {      // the eastern wall column (the transform covers columns 0 .. nxp-2)
         double e = 0.0;
         for (int mm = 1; mm < a.nl; ++mm)
           e = fma(a.ctm2l[mm + a.nl * mode], a.coef[mm - 1] * a.hom[(size_t)(mm - 1) * a.lsz + (size_t)(r + a.row0) * a.ld + a.nxp - 1], e);
         row[a.nxp - 1] = e;
       }
-    } else if (t < L3) {
-      double2 *__restrict__ out = reinterpret_cast<double2 *>(row);
+    } else {
 #pragma unroll
-      for (int q = 0; q < R3; ++q) {
-        const int k = t + q * L3;
-        const double od = SC[k];
-        out[k] = make_double2(ev[q], od);
-        if (INV) part += ev[q] + od;
+      for (int rr = 0; rr < RND; ++rr) {
+        const int tt = t + rr * NT;
+        if (tt < L3) {
+          double2 *__restrict__ out = reinterpret_cast<double2 *>(row);
+#pragma unroll
+          for (int q = 0; q < R3; ++q) {
+            const int k = tt + q * L3;
+            const double od = SC[k];
+            out[k] = make_double2(ev[rr][q], od);
+            if (INV) part += ev[rr][q] + od;
+          }
+        }
       }
     }
     if (INV) {
@@ -751,7 +784,7 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
     for (int side = 0; side < 2; ++side) {
       if (!(side == 0 ? a.wall_s : a.wall_n)) continue;
       const size_t ro = (size_t)(side == 0 ? 0 : a.nyp - 1) * a.ld;
-      for (int i = blockIdx.x * 256 + t0; i < a.nxp; i += gridDim.x * 256)
+      for (int i = blockIdx.x * NT + t0; i < a.nxp; i += gridDim.x * NT)
         for (int k = 0; k < a.nl; ++k) {
           double e = 0.0;
           for (int mm = 1; mm < a.nl; ++mm) e = fma(a.ctm2l[mm + a.nl * k], a.coef[mm - 1] * a.hom[(size_t)(mm - 1) * a.lsz + ro + i], e);
@@ -764,7 +797,7 @@ __global__ void __launch_bounds__(256, 2) k_dst3(const Dst3Args a) {
     if (t0 == 0 && prev_slot >= 0) {
       double sum = 0.0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sum += red[16 + i];
+      for (int i = 0; i < NW; ++i) sum += red[16 + i];
       a.rowsum[prev_slot] = sum;
     }
   }
@@ -1384,15 +1417,16 @@ static void dst3_launch_t(qgcm_model *md, HelmPlan &hp, const Dst3Args &a, int m
     QG_CUDA(cudaFuncSetAttribute(kfi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hp.fast_attr = 1;
   }
-  const int grid = std::min(a.nitems, hp.fast_grid);      // persistent blocks, two per SM
+  constexpr int NT = dst3_threads(R3);
+  const int grid = std::min(a.nitems, hp.fast_grid / 2 * dst3_blocks(R3));      // persistent blocks, two or four per SM
   switch (mode) {
-    case DST_PLAIN_F: QG_LAUNCH(md, "k_xform", grid, 256, smem, kf, a); break;
-    case DST_PLAIN_I: QG_LAUNCH(md, "k_xform_inv", grid, 256, smem, ki, a); break;
+    case DST_PLAIN_F: QG_LAUNCH(md, "k_xform", grid, NT, smem, kf, a); break;
+    case DST_PLAIN_I: QG_LAUNCH(md, "k_xform_inv", grid, NT, smem, ki, a); break;
     case DST_FUSED_F:
-      if (a.ddyn) QG_LAUNCH(md, "k_xform", grid, 256, smem, kfft, a);
-      else QG_LAUNCH(md, "k_xform", grid, 256, smem, kff, a);
+      if (a.ddyn) QG_LAUNCH(md, "k_xform", grid, NT, smem, kfft, a);
+      else QG_LAUNCH(md, "k_xform", grid, NT, smem, kff, a);
       break;
-    default: QG_LAUNCH(md, "k_xform_inv", grid, 256, smem, kfi, a); break;
+    default: QG_LAUNCH(md, "k_xform_inv", grid, NT, smem, kfi, a); break;
   }
 }
 
