@@ -336,6 +336,34 @@ def run_reference(args, qg):
     dt = time.time() - t0
     v = n / dt
     step_passes = 59.0 if p.has("cyclic_ocean") else 61.0
+    # the reference's own Fortran, translated to C++ (oracle/_ref, oracle/f2cpp.py) on the same state: single
+    # threaded -- the translator drops the OpenMP directives -- so it is reported beside the OpenMP restatement,
+    # which stays the arm's value (the faster, i.e. the more demanding, baseline)
+    translated = None
+    if not args.no_translated and not coupled:
+        try:
+            import pyref
+            if pyref.available():
+                r = pyref.RefModel(p, cfg)
+                qg.synth.init_model(r, p, cfg, "random")
+
+                def rstep():
+                    r.oml(); r.qgostep(); r.ocinvq(); r.ocqbdy()
+
+                rstep()
+                t1 = time.time()
+                k = 0
+                while k < 3:
+                    rstep()
+                    k += 1
+                    if time.time() - t1 > 40.0:
+                        break
+                translated = {"value": k / (time.time() - t1), "unit": UNIT, "cores": 1, "kind": "reference",
+                              "sample": "%d ocean steps after 1 warm-up of the reference's Fortran sources translated "
+                                        "statement by statement to C++ (oracle/_ref; OpenMP directives not honoured)" % k}
+                del r
+        except Exception as e:      # the arm's own number does not depend on this leg
+            translated = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
         "warmup": done_w, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -348,6 +376,7 @@ def run_reference(args, qg):
                                    "Fortran reference cannot be compiled here: no Fortran compiler in the image or on "
                                    "the GPU box, profiles/r02_fortran_probe.txt)" % (n, done_w)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_translated": translated,
     }
     print(json.dumps(line), flush=True)
 
@@ -361,6 +390,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-translated", action="store_true",
+                    help="--impl reference: skip the single-threaded run of the translated Fortran reference")
     ap.add_argument("--no-verify", action="store_true",
                     help="skip the parity leg (two ocean steps against the CPU oracle before the warm-up, outside every timed region)")
     ap.add_argument("--transport", default=os.environ.get("QGCM_SLAB_TRANSPORT", "peer"), choices=["peer", "nccl"],

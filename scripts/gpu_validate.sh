@@ -14,6 +14,11 @@ if [ "${SKIP_TESTS:-0}" != "1" ]; then
 fi
 timeout 600 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
 echo "bench rc=$?"; cut -c1-400 $out/${tag}_bench_n1.json
+if [ "${SKIP_REF:-0}" != "1" ]; then
+  # the reference arm on this box's host cores (OpenMP restatement + a few steps of the translated Fortran)
+  timeout 500 python bench.py --impl reference --steps 8 --warmup 1 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err
+  echo "reference arm rc=$?"; cut -c1-300 $out/${tag}_bench_reference.json
+fi
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
     --log-file $out/${tag}_launches_raw.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --no-verify \
