@@ -483,6 +483,7 @@ struct Dst3Args {
   const double *hom;        // DST_FUSED_I: ochom [nl-1][nyp][ld]
   const double *coef;       // DST_FUSED_I: device hclco[nl-1]
   int wall_s, wall_n;       // DST_FUSED_I: this grid holds the southern / northern wall row (written by block 0)
+  int pdl;                  // DST_FUSED_I: launched as a programmatic dependent of k_inv_scalars
   double ctm2l[NLMAX * NLMAX];
   const double2 *s1base;    // [L1][2]  (2 sin, 2 cos) of pi*(2t)/N and pi*(2t+1)/N
   const double2 *tw2;       // [R2-1][R1] twiddles of pass 2
@@ -719,6 +720,8 @@ __global__ void __launch_bounds__(dst3_threads(R3), dst3_blocks(R3)) k_dst3(cons
     // ---- interleave and store: row[2k] = even_k, row[2k+1] = odd_k ----
     double part = 0.0;
     if (MODE == DST_FUSED_I) {
+      // coef comes from the kernel launched before this one, which may still be running
+      if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
       // fused inverse transform: the row is sum_m ctm2l(m,k) wrk_m(:,j) already (the tridiagonal
       // kernel projected in spectral space); add the homogeneous solutions of the baroclinic
       // modes, sum_m ctm2l(m,k) hclco(m-1) ochom(:,j,m-1), and store p_k (src/ocisubs.F:377-401)
@@ -779,6 +782,7 @@ __global__ void __launch_bounds__(dst3_threads(R3), dst3_blocks(R3)) k_dst3(cons
     }
   }
   if (MODE == DST_FUSED_I) {
+    if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     // wall rows of the new pressure: the inhomogeneous solution vanishes there, the homogeneous
     // solutions do not (src/ocisubs.F:377-401 on rows 1 and nypo); a slice of columns per block
     for (int side = 0; side < 2; ++side) {
@@ -1426,7 +1430,12 @@ static void dst3_launch_t(qgcm_model *md, HelmPlan &hp, const Dst3Args &a, int m
       if (a.ddyn) QG_LAUNCH(md, "k_xform", grid, NT, smem, kfft, a);
       else QG_LAUNCH(md, "k_xform", grid, NT, smem, kff, a);
       break;
-    default: QG_LAUNCH(md, "k_xform_inv", grid, NT, smem, kfi, a); break;
+    default:
+      // the fused inverse transform needs the constraint coefficients (k_inv_scalars, the launch before it)
+      // only in its epilogues: it may start beside that kernel and waits for it there (griddepcontrol.wait)
+      if (a.pdl) QG_LAUNCH_PDL(md, "k_xform_inv", grid, NT, smem, kfi, a);
+      else QG_LAUNCH(md, "k_xform_inv", grid, NT, smem, kfi, a);
+      break;
   }
 }
 
@@ -1445,6 +1454,7 @@ static void dst3_launch(qgcm_model *md, HelmPlan &hp, double *wrk, size_t lsz, i
   for (int i = 0; i < 16; ++i) { a.c1[i] = hp.c1[i]; a.s1[i] = hp.s1c[i]; a.wnr[i] = hp.wnr[i]; }
   a.nl = nmodes; a.kbot = nmodes - 1;
   a.wall_s = hp.wall_s; a.wall_n = hp.wall_n;
+  a.pdl = (mode == DST_FUSED_I && !md->prof && env_int("QGCM_PDL", 1)) ? 1 : 0;
   if (fz) {
     a.src = fz->q; a.dst = fz->pnew; a.yrel = fz->yrel; a.beta = fz->beta; a.ddyn = fz->ddyn; a.hom = fz->hom; a.coef = fz->coef;
     for (int i = 0; i < NLMAX * NLMAX; ++i) a.ctm2l[i] = fz->ctm2l[i];

@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(256) k_inv_partials(const double *sumsrc, int 
 // synchronises with the host (src/ocisubs.F:146-162, :174-294, :333-370;
 // src/atisubs.F:137-258).  xinhom(m) = dx*dy * sum of the xintp row sums.
 __global__ void __launch_bounds__(256) k_inv_scalars(ScalArgs a) {
+  // the fused inverse transform that follows needs this kernel's result only in its epilogues: let it start
+  asm volatile("griddepcontrol.launch_dependents;");
   __shared__ double red[8];
   qgcm_scalars *s = a.sc;
   const int nl = a.nl, nyp = a.nyp;

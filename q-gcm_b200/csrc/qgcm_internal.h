@@ -31,6 +31,25 @@
     (m)->launches++;                                                \
   } while (0)
 
+// the same for a kernel that may start while the previous kernel of the stream still runs (programmatic
+// dependent launch): the previous kernel executes griddepcontrol.launch_dependents, this one executes
+// griddepcontrol.wait before it touches anything the previous one writes
+#define QG_LAUNCH_PDL(m, name, grid, block, smem, kern, ...)                                   \
+  do {                                                                                         \
+    qg::prof_begin(m, name);                                                                   \
+    cudaLaunchConfig_t lc_ = {};                                                               \
+    lc_.gridDim = dim3(grid); lc_.blockDim = dim3(block); lc_.dynamicSmemBytes = smem;         \
+    lc_.stream = (m)->stream;                                                                  \
+    cudaLaunchAttribute at_[1];                                                                \
+    at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                            \
+    at_[0].val.programmaticStreamSerializationAllowed = 1;                                     \
+    lc_.attrs = at_; lc_.numAttrs = 1;                                                         \
+    QG_CUDA(cudaLaunchKernelEx(&lc_, kern, __VA_ARGS__));                                      \
+    qg::launch_check(m, name);                                                                 \
+    qg::prof_end(m);                                                                           \
+    (m)->launches++;                                                                           \
+  } while (0)
+
 namespace qg {
 
 constexpr int NLMAX = QGCM_NLMAX;
