@@ -225,7 +225,11 @@ int qgcm_ocean_step(qgcm_model *m);
 int qgcm_atmos_step(qgcm_model *m);
 /* The loop body of src/q-gcm.F:1220-1408 for nt = nt_first..nt_last inclusive:
  * ocean step when mod(nt,nstr)==1 (every step when nstr==1),
- * atmosphere step unless ocean_only, time-level averaging on its cadence. */
+ * atmosphere step unless ocean_only, time-level averaging on its cadence.
+ * Coupled models: a whole cycle (xforc, the ocean step, nstr atmosphere steps) inside the range runs as
+ * one CUDA graph in which the atmosphere steps are a branch beside the ocean step (after xforc the two
+ * touch disjoint state); the results are bit-identical with the call-by-call order, and every other entry
+ * point sees the state only after both branches have joined. */
 int qgcm_run(qgcm_model *m, int64_t nt_first, int64_t nt_last);
 
 /* ---- y-slab multi-GPU (new: the reference is single-node OpenMP over j, src/qgosubs.F:173-184)

@@ -117,6 +117,69 @@ __device__ void lu_solve_refine(const double *a, int n, const double *rhs, doubl
   }
 }
 
+// the same with a compile-time order: every index is a constant after unrolling (row exchanges become
+// conditional swaps), so the factors live in registers instead of local memory; same operations, same order
+template <int N>
+__device__ __forceinline__ void lu_solve_refine_t(const double *a, const double *rhs, double *x) {
+  double lu[N * N];
+  int piv[N];
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) lu[i] = a[i];
+#pragma unroll
+  for (int kk = 0; kk < N; ++kk) {
+    int p = kk;
+    double best = fabs(lu[kk + N * kk]);
+#pragma unroll
+    for (int i = kk + 1; i < N; ++i)
+      if (fabs(lu[i + N * kk]) > best) { p = i; best = fabs(lu[i + N * kk]); }
+    piv[kk] = p;
+#pragma unroll
+    for (int i = kk + 1; i < N; ++i)
+      if (p == i) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) { const double t = lu[kk + N * j]; lu[kk + N * j] = lu[i + N * j]; lu[i + N * j] = t; }
+      }
+#pragma unroll
+    for (int i = kk + 1; i < N; ++i) {
+      lu[i + N * kk] /= lu[kk + N * kk];
+#pragma unroll
+      for (int j = kk + 1; j < N; ++j) lu[i + N * j] -= lu[i + N * kk] * lu[kk + N * j];
+    }
+  }
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    double b[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double acc = rhs[i];
+      if (pass == 1) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc -= a[i + N * j] * x[j];
+      }
+      b[i] = acc;
+    }
+#pragma unroll
+    for (int kk = 0; kk < N; ++kk) {
+#pragma unroll
+      for (int i = kk + 1; i < N; ++i)
+        if (piv[kk] == i) { const double t = b[kk]; b[kk] = b[i]; b[i] = t; }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+      for (int j = 0; j < i; ++j) b[i] -= lu[i + N * j] * b[j];
+    }
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+#pragma unroll
+      for (int j = i + 1; j < N; ++j) b[i] -= lu[i + N * j] * b[j];
+      b[i] /= lu[i + N * i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = pass == 0 ? b[i] : x[i] + b[i];
+  }
+}
+
 struct ScalArgs {
   int atmos, cyclic, nl, nyp;
   double dx, f0, tdt, xl, yl;
@@ -156,48 +219,60 @@ __global__ void __launch_bounds__(256) k_inv_partials(const double *sumsrc, int 
 // Single-thread constraint algebra on device-resident scalars, so the step never
 // synchronises with the host (src/ocisubs.F:146-162, :174-294, :333-370;
 // src/atisubs.F:137-258).  xinhom(m) = dx*dy * sum of the xintp row sums.
-__global__ void __launch_bounds__(256) k_inv_scalars(ScalArgs a) {
-  // the fused inverse transform that follows needs this kernel's result only in its epilogues: let it start
-  asm volatile("griddepcontrol.launch_dependents;");
-  __shared__ double red[8];
-  qgcm_scalars *s = a.sc;
-  const int nl = a.nl, nyp = a.nyp;
-  const double ecrit = 1.0e-13;
-  double xinhom[NLMAX], ayis[NLMAX], ayin[NLMAX];
-  double sums[NLMAX];
-  // box: the scalar state the constraint algebra needs is fetched before the sums (and the
-  // all-reduce of the y-slab ranks), so that its latency hides behind them
-  double dpi0[NLMAX], dpip0[NLMAX], cdf[NLMAX * NLMAX], cdh[NLMAX * NLMAX], xon_own = 0.0;
-  if (threadIdx.x == 0 && !a.cyclic) {
-    xon_own = s->xon[0];
-    for (int k = 0; k < nl - 1; ++k) { dpi0[k] = s->dpioc[k]; dpip0[k] = s->dpiocp[k]; }
-    for (int i = 0; i < nl * (nl - 1); ++i) cdf[i] = s->cdiffo[i];
-    for (int i = 0; i < (nl - 1) * (nl - 1); ++i) cdh[i] = s->cdhoc[i];
-  }
-  if (a.peer.n) {
-    // the three modal integrals together: one pass over the row sums, one block reduction
-    double sm[NLMAX];
-    for (int m = 0; m < nl; ++m) {
-      double acc = 0.0;
-      for (int i = a.sumlo + (int)threadIdx.x; i < a.sumhi; i += 256) acc += a.sumsrc[(size_t)m * a.sumstride + i];
+// (One block of INV_NT threads.  The kernel is a chain of dependent round trips to L2 -- the scalar state, the
+// partial sums, the algebra's operands -- so everything it reads is fetched by all threads at once: the
+// scalar block into shared memory, the partial sums eight strides at a time.)
+constexpr int INV_NT = 512;
+
+// tot[m] = sum of src[m*stride + lo .. hi): fixed strided partials (thread t takes lo+t, lo+t+INV_NT, ... in
+// increasing order), fixed-order tree; the loads of eight strides are in flight together
+__device__ __forceinline__ void inv_mode_sums(const double *src, int stride, int lo, int hi, int nl, double (*redm)[INV_NT / 32], double *tot) {
+  constexpr int U = 8;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int m = 0; m < nl; ++m) {
+    const double *v = src + (size_t)m * stride;
+    double acc = 0.0;
+    for (int i0 = lo + (int)threadIdx.x; i0 < hi; i0 += U * INV_NT) {
+      double x[U];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-      sm[m] = acc;
+      for (int u = 0; u < U; ++u) x[u] = (i0 + u * INV_NT < hi) ? v[i0 + u * INV_NT] : 0.0;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i0 + u * INV_NT < hi) acc += x[u];
     }
-    __shared__ double red3[NLMAX][8];
-    if ((threadIdx.x & 31) == 0)
-      for (int m = 0; m < nl; ++m) red3[m][threadIdx.x >> 5] = sm[m];
-    __syncthreads();
-    if ((int)threadIdx.x < nl) {
-      double t = 0.0;
-      for (int i = 0; i < 8; ++i) t += red3[threadIdx.x][i];
-      a.cvw[4 + threadIdx.x] = t * a.dx * a.dx;
-    }
-    __syncthreads();
-    peer_allreduce_block(a.peer, a.cvw + 3, 1 + nl, a.cvw + 3, a.peer_err);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) redm[m][w] = acc;
   }
-  for (int m = 0; m < nl; ++m) sums[m] = a.cv ? 0.0 : block256_range_sum(a.sumsrc + (size_t)m * a.sumstride, a.sumlo, a.sumhi, red);
-  if (threadIdx.x != 0) return;
+  __syncthreads();
+  if ((int)threadIdx.x < nl) {
+    double t = 0.0;
+    for (int i = 0; i < INV_NT / 32; ++i) t += redm[threadIdx.x][i];
+    tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+}
+
+// The constraint algebra itself, one thread (src/ocisubs.F:146-162, :174-294, :333-370; src/atisubs.F:137-258).
+// NLC = the layer count as a compile-time constant (2, 3, 4: every loop unrolls and every small array lives in
+// registers) or 0 = read it from the arguments (any count up to NLMAX; the arrays then live in local memory,
+// and the thread spends most of its 15 microseconds waiting on them).  Same statements either way.
+template <int NLC>
+__device__ __forceinline__ void inv_algebra(const ScalArgs &a, qgcm_scalars *s, const qgcm_scalars *ls, const double *tot) {
+  constexpr int NA = NLC ? NLC : NLMAX;
+  const int nl = NLC ? NLC : a.nl, nyp = a.nyp;
+  const double ecrit = 1.0e-13;
+  double xinhom[NA], ayis[NA], ayin[NA];
+  double sums[NA];
+  for (int m = 0; m < nl; ++m) sums[m] = a.cv ? 0.0 : tot[m];
+  // box: the scalar state the constraint algebra needs
+  double dpi0[NA], dpip0[NA], cdf[NA * NA], cdh[NA * NA], xon_own = 0.0;
+  if (!a.cyclic) {
+    xon_own = ls->xon[0];
+    for (int k = 0; k < nl - 1; ++k) { dpi0[k] = ls->dpioc[k]; dpip0[k] = ls->dpiocp[k]; }
+    for (int i = 0; i < nl * (nl - 1); ++i) cdf[i] = ls->cdiffo[i];
+    for (int i = 0; i < (nl - 1) * (nl - 1); ++i) cdh[i] = ls->cdhoc[i];
+  }
   if (a.cv) s->xon[0] = a.cv[3];
   for (int m = 0; m < nl; ++m) {
     const double sump = sums[m];
@@ -210,7 +285,7 @@ __global__ void __launch_bounds__(256) k_inv_scalars(ScalArgs a) {
   }
   if (!a.cyclic) {
     // finite box: mass constraints (src/ocisubs.F:333-370)
-    double aient[NLMAX], rhs[NLMAX], hclco[NLMAX];
+    double aient[NA], rhs[NA], hclco[NA];
     aient[0] = a.cv ? a.cv[3] : xon_own;
     for (int k = 1; k < nl - 1; ++k) aient[k] = 0.0;
     for (int k = 0; k < nl - 1; ++k) {
@@ -222,43 +297,46 @@ __global__ void __launch_bounds__(256) k_inv_scalars(ScalArgs a) {
       for (int m = 0; m < nl; ++m) rhsum = rhsum + cdf[m + nl * k] * xinhom[m];
       rhs[k] = dnew - rhsum;
     }
-    lu_solve_refine(cdh, nl - 1, rhs, hclco);
+    if (NLC > 1) lu_solve_refine_t<(NLC > 1 ? NLC - 1 : 1)>(cdh, rhs, hclco);
+    else lu_solve_refine(cdh, nl - 1, rhs, hclco);
     for (int k = 0; k < nl - 1; ++k) a.coef[k] = hclco[k];
     return;
   }
   // periodic channel: momentum constraints
-  double rhss[NLMAX], rhsn[NLMAX], snew[NLMAX], nnew[NLMAX], clhss[NLMAX], clhsn[NLMAX];
-  double c1[NLMAX], c2[NLMAX], c3, aipmod[NLMAX], aiplay[NLMAX];
+  double rhss[NA], rhsn[NA], snew[NA], nnew[NA], clhss[NA], clhsn[NA];
+  double c1[NA], c2[NA], c3, aipmod[NA], aiplay[NA];
   const double entfac = 0.5 * a.dx * a.f0 * a.f0;
   const double *h = a.h;
   if (!a.atmos) {
-    rhss[0] = (entfac / h[0]) * s->enisoc[0] + (a.f0 / h[0]) * s->txisoc + s->ajisoc[0] - s->ap3soc[0] + s->ap5soc[0];
-    rhsn[0] = (entfac / h[0]) * s->eninoc[0] - (a.f0 / h[0]) * s->txinoc + s->ajinoc[0] + s->ap3noc[0] - s->ap5noc[0];
+    rhss[0] = (entfac / h[0]) * ls->enisoc[0] + (a.f0 / h[0]) * ls->txisoc + ls->ajisoc[0] - ls->ap3soc[0] + ls->ap5soc[0];
+    rhsn[0] = (entfac / h[0]) * ls->eninoc[0] - (a.f0 / h[0]) * ls->txinoc + ls->ajinoc[0] + ls->ap3noc[0] - ls->ap5noc[0];
     for (int k = 1; k < nl - 1; ++k) {
-      rhss[k] = (entfac / h[k]) * (s->enisoc[k] - s->enisoc[k - 1]) + s->ajisoc[k] - s->ap3soc[k] + s->ap5soc[k];
-      rhsn[k] = (entfac / h[k]) * (s->eninoc[k] - s->eninoc[k - 1]) + s->ajinoc[k] + s->ap3noc[k] - s->ap5noc[k];
+      rhss[k] = (entfac / h[k]) * (ls->enisoc[k] - ls->enisoc[k - 1]) + ls->ajisoc[k] - ls->ap3soc[k] + ls->ap5soc[k];
+      rhsn[k] = (entfac / h[k]) * (ls->eninoc[k] - ls->eninoc[k - 1]) + ls->ajinoc[k] + ls->ap3noc[k] - ls->ap5noc[k];
     }
-    rhss[nl - 1] = -(entfac / h[nl - 1]) * s->enisoc[nl - 2] + s->ajisoc[nl - 1] - s->ap3soc[nl - 1] + s->ap5soc[nl - 1] +
-                   (a.f0 / h[nl - 1]) * s->bdrins;
-    rhsn[nl - 1] = -(entfac / h[nl - 1]) * s->eninoc[nl - 2] + s->ajinoc[nl - 1] + s->ap3noc[nl - 1] - s->ap5noc[nl - 1] -
-                   (a.f0 / h[nl - 1]) * s->bdrinn;
+    rhss[nl - 1] = -(entfac / h[nl - 1]) * ls->enisoc[nl - 2] + ls->ajisoc[nl - 1] - ls->ap3soc[nl - 1] + ls->ap5soc[nl - 1] +
+                   (a.f0 / h[nl - 1]) * ls->bdrins;
+    rhsn[nl - 1] = -(entfac / h[nl - 1]) * ls->eninoc[nl - 2] + ls->ajinoc[nl - 1] + ls->ap3noc[nl - 1] - ls->ap5noc[nl - 1] -
+                   (a.f0 / h[nl - 1]) * ls->bdrinn;
   } else {
-    rhss[0] = -(entfac / h[0]) * s->enisat[0] - (a.f0 / h[0]) * s->txisat + s->ajisat[0] + s->ap5sat[0];
-    rhsn[0] = -(entfac / h[0]) * s->eninat[0] + (a.f0 / h[0]) * s->txinat + s->ajinat[0] - s->ap5nat[0];
+    rhss[0] = -(entfac / h[0]) * ls->enisat[0] - (a.f0 / h[0]) * ls->txisat + ls->ajisat[0] + ls->ap5sat[0];
+    rhsn[0] = -(entfac / h[0]) * ls->eninat[0] + (a.f0 / h[0]) * ls->txinat + ls->ajinat[0] - ls->ap5nat[0];
     for (int k = 1; k < nl - 1; ++k) {
-      rhss[k] = -(entfac / h[k]) * (s->enisat[k] - s->enisat[k - 1]) + s->ajisat[k] + s->ap5sat[k];
-      rhsn[k] = -(entfac / h[k]) * (s->eninat[k] - s->eninat[k - 1]) + s->ajinat[k] - s->ap5nat[k];
+      rhss[k] = -(entfac / h[k]) * (ls->enisat[k] - ls->enisat[k - 1]) + ls->ajisat[k] + ls->ap5sat[k];
+      rhsn[k] = -(entfac / h[k]) * (ls->eninat[k] - ls->eninat[k - 1]) + ls->ajinat[k] - ls->ap5nat[k];
     }
-    rhss[nl - 1] = (entfac / h[nl - 1]) * s->enisat[nl - 2] + s->ajisat[nl - 1] + s->ap5sat[nl - 1];
-    rhsn[nl - 1] = (entfac / h[nl - 1]) * s->eninat[nl - 2] + s->ajinat[nl - 1] - s->ap5nat[nl - 1];
+    rhss[nl - 1] = (entfac / h[nl - 1]) * ls->enisat[nl - 2] + ls->ajisat[nl - 1] + ls->ap5sat[nl - 1];
+    rhsn[nl - 1] = (entfac / h[nl - 1]) * ls->eninat[nl - 2] + ls->ajinat[nl - 1] - ls->ap5nat[nl - 1];
   }
   double *cs = a.atmos ? s->atmcs : s->ocncs, *cn = a.atmos ? s->atmcn : s->ocncn;
   double *csp = a.atmos ? s->atmcsp : s->ocncsp, *cnp = a.atmos ? s->atmcnp : s->ocncnp;
+  const double *cs0 = a.atmos ? ls->atmcs : ls->ocncs, *cn0 = a.atmos ? ls->atmcn : ls->ocncn;
+  const double *csp0 = a.atmos ? ls->atmcsp : ls->ocncsp, *cnp0 = a.atmos ? ls->atmcnp : ls->ocncnp;
   for (int k = 0; k < nl; ++k) {
-    snew[k] = csp[k] + a.tdt * rhss[k];
-    nnew[k] = cnp[k] + a.tdt * rhsn[k];
-    csp[k] = cs[k];
-    cnp[k] = cn[k];
+    snew[k] = csp0[k] + a.tdt * rhss[k];
+    nnew[k] = cnp0[k] + a.tdt * rhsn[k];
+    csp[k] = cs0[k];
+    cnp[k] = cn0[k];
     cs[k] = snew[k];
     cn[k] = nnew[k];
   }
@@ -272,10 +350,10 @@ __global__ void __launch_bounds__(256) k_inv_scalars(ScalArgs a) {
     clhss[m] = clhss[m] + ayis[m];
     clhsn[m] = clhsn[m] - ayin[m];
   }
-  const double *hc1s = a.atmos ? s->hc1sat : s->hc1soc, *hc2s = a.atmos ? s->hc2sat : s->hc2soc;
-  const double *hc1n = a.atmos ? s->hc1nat : s->hc1noc, *hc2n = a.atmos ? s->hc2nat : s->hc2noc;
-  const double *aipch = a.atmos ? s->aipcha : s->aipcho;
-  const double hbsi = a.atmos ? s->hbsiat : s->hbsioc, aipbh = a.atmos ? s->aipbha : s->aipbho;
+  const double *hc1s = a.atmos ? ls->hc1sat : ls->hc1soc, *hc2s = a.atmos ? ls->hc2sat : ls->hc2soc;
+  const double *hc1n = a.atmos ? ls->hc1nat : ls->hc1noc, *hc2n = a.atmos ? ls->hc2nat : ls->hc2noc;
+  const double *aipch = a.atmos ? ls->aipcha : ls->aipcho;
+  const double hbsi = a.atmos ? ls->hbsiat : ls->hbsioc, aipbh = a.atmos ? ls->aipbha : ls->aipbho;
   c3 = clhss[0] * hbsi;
   for (int m = 0; m < nl - 1; ++m) {
     c1[m] = hc2n[m] * clhss[m + 1] - hc2s[m] * clhsn[m + 1];
@@ -289,23 +367,57 @@ __global__ void __launch_bounds__(256) k_inv_scalars(ScalArgs a) {
     aiplay[k] = pl;
   }
   double *dpi = a.atmos ? s->dpiat : s->dpioc, *dpip = a.atmos ? s->dpiatp : s->dpiocp;
-  const double *xn = a.atmos ? s->xan : s->xon;
+  const double *dpi0c = a.atmos ? ls->dpiat : ls->dpioc, *dpip0c = a.atmos ? ls->dpiatp : ls->dpiocp;
+  const double *xn = a.atmos ? ls->xan : ls->xon;
   double *erma = a.atmos ? s->ermasa : s->ermaso, *emfr = a.atmos ? s->emfrat : s->emfroc;
   for (int k = 0; k < nl - 1; ++k) {
     // sign conventions: ocean dpioc = p(k+1)-p(k) (ocisubs.F:272), atmosphere p(k)-p(k+1) (atisubs.F:237)
     const double est1 = a.atmos ? aiplay[k] - aiplay[k + 1] : aiplay[k + 1] - aiplay[k];
-    const double est2 = dpip[k] - a.tdt * a.gp[k] * xn[k];
+    const double est2 = dpip0c[k] - a.tdt * a.gp[k] * xn[k];
     const double edif = est1 - est2;
     const double esum = fabs(est1) + fabs(est2);
     erma[k] = edif;
     emfr[k] = (esum > (ecrit * a.xl * a.yl * a.tdt * a.gp[k])) ? 2.0 * edif / esum : 0.0;
-    dpip[k] = dpi[k];
+    dpip[k] = dpi0c[k];
     dpi[k] = est1;
   }
   a.coef[0] = c3;
   for (int m = 1; m < nl; ++m) {
     a.coef[m] = c1[m - 1];
     a.coef[nl - 1 + m] = c2[m - 1];
+  }
+}
+
+__global__ void __launch_bounds__(INV_NT) k_inv_scalars(ScalArgs a) {
+  // the fused inverse transform that follows needs this kernel's result only in its epilogues: let it start
+  asm volatile("griddepcontrol.launch_dependents;");
+  __shared__ qgcm_scalars sh;      // snapshot of the scalar block: every read below comes from it, every write goes to *s
+  __shared__ double redm[NLMAX][INV_NT / 32];
+  __shared__ double tot[NLMAX];
+  qgcm_scalars *s = a.sc;
+  const qgcm_scalars *ls = &sh;
+  {
+    static_assert(sizeof(qgcm_scalars) % 8 == 0, "qgcm_scalars is copied in 8-byte words");
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(a.sc);
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(&sh);
+    for (int i = threadIdx.x; i < (int)(sizeof(qgcm_scalars) / 8); i += INV_NT) dst[i] = src[i];
+  }
+  const int nl = a.nl;
+  if (a.peer.n) {
+    // y-slabs over peer memory: this rank's share of the modal integrals, then their sum over the ranks
+    inv_mode_sums(a.sumsrc, a.sumstride, a.sumlo, a.sumhi, nl, redm, tot);
+    if ((int)threadIdx.x < nl) a.cvw[4 + threadIdx.x] = tot[threadIdx.x] * a.dx * a.dx;
+    __syncthreads();
+    peer_allreduce_block(a.peer, a.cvw + 3, 1 + nl, a.cvw + 3, a.peer_err);
+  }
+  if (!a.cv) inv_mode_sums(a.sumsrc, a.sumstride, a.sumlo, a.sumhi, nl, redm, tot);
+  __syncthreads();      // the snapshot is complete
+  if (threadIdx.x != 0) return;
+  switch (nl) {
+    case 2: inv_algebra<2>(a, s, ls, tot); break;
+    case 3: inv_algebra<3>(a, s, ls, tot); break;
+    case 4: inv_algebra<4>(a, s, ls, tot); break;
+    default: inv_algebra<0>(a, s, ls, tot); break;
   }
 }
 
@@ -359,7 +471,7 @@ static void inv_scalars_m2l(qgcm_model *m, bool atmos, const InvArgs &a, bool fu
   s.cv = (!atmos && m->nranks > 1) ? m->d_cv : nullptr;
   s.peer.n = 0; s.peer_err = m->d_peer_err; s.cvw = m->d_cv; s.lo = hp.row0; s.hi = hp.row0 + hp.nrows;
   if (!atmos && m->nranks > 1) s.peer = peer_next_vec(m);
-  QG_LAUNCH(m, "k_inv_scalars", 1, 256, 0, k_inv_scalars, s);
+  QG_LAUNCH(m, "k_inv_scalars", 1, INV_NT, 0, k_inv_scalars, s);
   if (fused) {
     helm_fused_inverse(m, hp, a.wrk, g.nl, fused_args(m, a));
   } else {

@@ -293,6 +293,35 @@ def test_async_upload_twice_before_one_commit(qg, pyorc):
     assert np.array_equal(gpu.get_field("fnetoc"), 2.0 * old)
 
 
+LAYERS = {2: ([350.0, 3650.0], [0.02]),
+          4: ([300.0, 700.0, 1000.0, 2000.0], [0.02, 0.01, 0.005]),
+          5: ([250.0, 450.0, 800.0, 1000.0, 1500.0], [0.02, 0.012, 0.008, 0.004])}
+
+
+@pytest.mark.parametrize("nlo", [2, 4, 5])
+@pytest.mark.parametrize("cyc", [0, 1])
+def test_other_layer_counts(qg, pyorc, nlo, cyc):
+    """two, four and five ocean layers (every deck ships three): the unfused inversion, the general
+    vorticity loop of the two-layer case, and the constraint algebra's instantiations for 2 and 4 layers
+    and its run-time path for 5 (invert.cu inv_algebra)"""
+    from dataclasses import replace
+    base = qg.named_config("so_coupled" if cyc else "dg_oo").scaled(48 if cyc else 24, 20, nxta=48 if cyc else None, nyta=40, ndxr=4)
+    hoc, gp = LAYERS[nlo]
+    tabs = (list(base.tabsoc) + [base.tabsoc[-1]] * nlo)[:nlo]
+    p = replace(base, nlo=nlo, hoc=hoc, gpoc=gp, ah2oc=[0.0] * nlo, ah4oc=[2.0e9] * nlo, tabsoc=tabs, name="nl%d_%d" % (nlo, cyc))
+    p.flags = ["ocean_only"] + (["cyclic_ocean"] if cyc else []) + ["sb_hflux"]
+    cfg, gpu, cpu = make_pair(qg, pyorc, p)
+    compare(gpu, cpu, ("qo", "qom"), label=p.name + " start-up")
+    n = 2 * p.nstr + 1
+    gpu.run(1, n)
+    cpu.run(1, n)
+    compare(gpu, cpu, OCEAN_CHECK, label=p.name)
+    fl = integral_scale(cpu, p)
+    compare_scalars(gpu, cpu, ("dpioc", "dpiocp", "xinhom_oc"), tol=1e-11, floor=fl)
+    if cyc:
+        compare_scalars(gpu, cpu, ("ocncs", "ocncn"), tol=1e-12)
+
+
 @pytest.mark.parametrize("nxto,cyc", [(96, 0), (120, 0), (160, 0), (180, 0), (200, 0), (216, 0), (240, 1),
                                       (288, 1), (400, 1), (324, 0), (480, 1), (960, 0), (1440, 0), (1920, 0),
                                       (2400, 0), (2880, 0), (3840, 0), (4800, 0)])
