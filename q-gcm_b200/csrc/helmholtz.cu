@@ -384,15 +384,16 @@ __global__ void __launch_bounds__(256, 2) k_xform(XfArgs a) {
 // Fast path for the box solver: DST-I rows whose half length is M = 16*15*R3 = 240*R3
 // (all box benchmark decks: 2400 = 240*10, 1200 = 240*5, 480 = 240*2).
 //
-//   * persistent blocks (2 per SM), each walks rows blockIdx.x, +gridDim.x, ...
+//   * persistent blocks (two of 256 threads per SM; four of 128 threads for M <= 1200, see dst3_threads),
+//     each walks rows blockIdx.x, +gridDim.x, ...
 //   * the raw row is fetched by the TMA engine (cp.async.bulk global->shared, mbarrier
 //     completion) while the previous row is post-processed and stored, so no warp ever
 //     waits on HBM;
 //   * the FFTPACK pre-processing (dsint.f:17-30) is fused into the register load of the
 //     first butterfly pass, its sine weights are rebuilt from a per-thread base angle and
 //     R1 constants (no table traffic);
-//   * three register butterfly passes (16, 15, R3: one butterfly per thread in every pass,
-//     under 128 registers at two blocks per SM) with two shared-memory exchanges laid out
+//   * three register butterfly passes (16, 15, R3: one butterfly per thread in every pass -- the last one
+//     in two rounds on 128-thread blocks -- under 128 registers) with two shared-memory exchanges laid out
 //     free of bank conflicts (the first one skewed by i >> 4); the exchanges ping-pong
 //     between the exchange buffer and the raw row's buffer (free once pass 1 has read it), so
 //     no pass needs a barrier between its loads and its stores: six block barriers per row;
