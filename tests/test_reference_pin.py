@@ -131,6 +131,37 @@ def test_oracle_matches_the_translated_reference(qg, pyorc, deck):
     print("worst relative differences, %s:" % deck, {k: "%.1e" % v for k, v in sorted(worst.items()) if v > 0})
 
 
+LAYERS = {2: ([350.0, 3650.0], [0.02]),
+          4: ([300.0, 700.0, 1000.0, 2000.0], [0.02, 0.01, 0.005]),
+          5: ([250.0, 450.0, 800.0, 1000.0, 1500.0], [0.02, 0.012, 0.008, 0.004])}
+
+
+@pytest.mark.parametrize("nlo", [2, 4, 5])
+@pytest.mark.parametrize("cyc", [0, 1])
+def test_oracle_matches_the_translated_reference_for_other_layer_counts(qg, pyorc, nlo, cyc):
+    """every deck ships three layers; the GPU parity tests also run two, four and five
+    (tests/test_gpu_parity.py::test_other_layer_counts), so the oracle is pinned there too: start-up and
+    three ocean steps of a box and a channel deck, every field and scalar after every call"""
+    from dataclasses import replace
+    base = decks(qg)["chan" if cyc else "box"]
+    hoc, gp = LAYERS[nlo]
+    tabs = (list(base.tabsoc) + [base.tabsoc[-1]] * nlo)[:nlo]
+    p = replace(base, nlo=nlo, hoc=hoc, gpoc=gp, ah2oc=[0.0] * nlo, ah4oc=[2.0e9] * nlo, tabsoc=tabs, name="pin_nl%d_%d" % (nlo, cyc))
+    p.flags = list(base.flags)
+    cfg = qg.build_config(p)
+    cpu = pyorc.Oracle(cfg)
+    ref = pyref.RefModel(p, cfg)
+    st = qg.synth.ocean_state(p, cfg, "random", qg.synth.SEED, min(1.0, (p.nxto * p.dxo) / 4.8e6 * 4.0))
+    for k, v in st.items():
+        cpu.set_field(k, v)
+        ref.set_field(k, v)
+    worst = {}
+    for name in ["constr", "qcomp_ocean", "xforc", "homsol"] + 3 * ["oml", "qgostep", "ocinvq", "ocqbdy"]:
+        getattr(cpu, name)()
+        getattr(ref, name)()
+        compare(cpu, ref, p, "%d layers, %s, after %s" % (nlo, "channel" if cyc else "box", name), worst)
+
+
 def test_translator_handles_the_fortran_it_claims(tmp_path):
     """f2cpp on a hand-made unit: declared lower bounds, sequence association, DATA, labelled DO, GOTO,
     integer division, real->integer truncation, sign(), mod(), x**n, DO trip count fixed at entry"""
